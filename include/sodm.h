@@ -1,0 +1,218 @@
+/* sodm.h -- C ABI of the B200-native ensemble simulator behind pySODM's model API.
+ *
+ * pySODM (twallema/pySODM v0.2.8) has no plugin / FFI interface of its own: the drop-in boundary is
+ * its Python class API.  This library is what a maintainer binds (ctypes) at
+ * the two seams of the hot path:
+ *
+ *   seam S (simulate):  the loop over draws inside `JumpProcess.sim` / `ODE.sim`
+ *                       src/pySODM/models/base.py:558-566 and :950-957
+ *                       (N x `_mp_sim_single` -> `_sim_single` -> `_solve_discrete` | `solve_ivp`)
+ *                       -> sodm_jump_run / sodm_ode_run          (one call for all N trajectories)
+ *   seam L (posterior): `log_posterior_probability.compute_log_likelihood` + `ll_*`
+ *                       src/pySODM/optimization/objective_functions.py:235-288, :550-666
+ *                       -> sodm_loglik                           (one call for a whole population)
+ *   output contract:    `_output_to_xarray_dataset` + concat along "draws", base.py:969-1042, :569-571
+ *                       -> sodm_to_draws_major                   ([state][time][traj] -> [traj][time][state dims])
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative SODM_E* code; sodm_last_error() returns a
+ *     thread-local message for the last failure on the calling thread;
+ *   - no allocation and no ownership transfer: every pointer marked (device) is a CALLER-owned
+ *     device buffer (the Python layer allocates them with PyTorch) that must stay alive until the
+ *     work queued on `stream` has completed; pointers marked (host) are read before the call returns;
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream);
+ *     no hidden synchronisation; no global mutable state; one call never spans devices -- the caller
+ *     shards trajectories over GPUs (rows [traj_id0, traj_id0 + n_traj));
+ *   - trajectory-major arrays are structure-of-arrays: element (row r, trajectory i) lives at
+ *     base[r * ld + i], so a warp of consecutive trajectories touches consecutive addresses.
+ */
+#ifndef SODM_H
+#define SODM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SODM_ABI_VERSION 1
+
+/* error codes */
+#define SODM_OK            0
+#define SODM_EINVAL       -1   /* bad argument */
+#define SODM_EMODEL       -2   /* unknown model / model does not support the request */
+#define SODM_ECUDA        -3   /* CUDA runtime error */
+#define SODM_EUNSUPPORTED -4   /* valid request that this build does not implement */
+
+/* model kinds */
+#define SODM_KIND_JUMP 0
+#define SODM_KIND_ODE  1
+
+/* element types of output buffers */
+#define SODM_I32 0
+#define SODM_F32 1
+#define SODM_F64 2
+
+/* per-trajectory status bits (int32 status[n_traj]) */
+#define SODM_ST_OK             0
+#define SODM_ST_BAD_PROB       1   /* transition probability NaN or outside [0,1]: NumPy's binomial raises
+                                      ValueError there (base.py:303) */
+#define SODM_ST_NONFINITE      2   /* non-finite model output (objective_functions.py:264-265 raises) */
+#define SODM_ST_STEP_TOO_SMALL 4   /* RK45: step size fell below 10 ulp(t) (scipy: status -1) */
+#define SODM_ST_MAX_STEPS      8   /* step / event budget exhausted */
+#define SODM_ST_TRUNCATED_Y0  16   /* non-integer initial count truncated to an integer */
+
+/* compat flags of sodm_jump_args.compat */
+#define SODM_COMPAT_STAY_QUIRK      1u  /* tau-leap: reference's stay probability 1 - sum_{i<m-1} p_i (base.py:339-342) */
+#define SODM_COMPAT_SSA_FIRST_MATCH 2u  /* SSA: reaction looked up by propensity VALUE, first match wins (base.py:254) */
+#define SODM_COMPAT_REFERENCE       3u
+
+/* methods */
+#define SODM_JUMP_TAU_LEAP 0
+#define SODM_JUMP_SSA      1
+#define SODM_ODE_RK45      0   /* scipy.integrate.solve_ivp(method='RK45') step for step (base.py:855) */
+#define SODM_ODE_EULER     1   /* explicit Euler with step tau + interpolation (base.py:800-819) */
+#define SODM_ODE_RK4       2   /* classical fixed-step RK4 (extension; the reference has none) */
+
+#define SODM_MAX_PARAM 32      /* flat parameter elements per model */
+#define SODM_MAX_STATE 32      /* flat state elements of a jump model */
+
+typedef struct sodm_model_info {
+    int32_t kind;          /* SODM_KIND_* */
+    int32_t n_state;       /* flat state elements (states in declaration order, C-order ravel; utils.py:45-55) */
+    int32_t n_param;       /* flat parameter elements, in the order documented per model in DESIGN.md */
+    int32_t n_channel;     /* jump models: transition channels (state, transition, element) */
+    int32_t tdpf_offset;   /* first flat parameter element that is read from the time-dependent table */
+    int32_t tdpf_count;    /* number of such elements (0: none) */
+    int32_t supports_ssa;
+    int32_t reserved;
+} sodm_model_info;
+
+int         sodm_abi_version(void);
+const char* sodm_last_error(void);
+/* Selects the device for the calling thread and checks that it is an sm_100 part. */
+int         sodm_init(int device);
+/* "sir_jump", "sir_si_jump", "influenza_1718_jump", "sir_ode", "sir_rate_ode", "sir_si_ode", "ppbb_ode",
+ * "packed_pfr_ode"; < 0 if unknown. */
+int         sodm_model_id(const char* name);
+/* model_arg: packed_pfr_ode = number of axial nodes nx; ignored otherwise. */
+int         sodm_model_info_get(int model, int model_arg, sodm_model_info* out);
+
+/* ---- seam S, jump processes: replaces base.py:421-440 (+ :206-348) for n_traj trajectories ------------ */
+typedef struct sodm_jump_args {
+    int32_t  model;
+    int32_t  method;            /* SODM_JUMP_* */
+    uint32_t compat;            /* SODM_COMPAT_* (SODM_COMPAT_REFERENCE reproduces the reference's laws) */
+    int32_t  out_dtype;         /* SODM_I32 only when every output time is hit exactly by a step (tau = 2^-k) */
+    int64_t  n_traj;
+    int64_t  traj_id0;          /* global id of the first trajectory: RNG stream = Philox(seed, traj_id0 + i) */
+    uint64_t seed;
+    int64_t  ld_in;             /* row stride of y0 / var_values, >= n_traj */
+    int64_t  ld_out;            /* row stride of out, >= n_traj */
+    const double*  y0;          /* (device) [n_state][ld_in], or [n_state] if y0_broadcast */
+    int32_t  y0_broadcast;
+    int32_t  n_var;             /* number of parameter elements that vary per trajectory */
+    const double*  par;         /* (host)   [n_param] value of every parameter element (used unless overridden) */
+    const int32_t* var_index;   /* (host)   [n_var] flat parameter element of each varying row */
+    const double*  var_values;  /* (device) [n_var][ld_in] */
+    const double*  tdpf_table;  /* (device) [n_tdpf_values][tdpf_count]; NULL if the model has tdpf_count == 0 */
+    const int32_t* tdpf_index;  /* (device) [n_steps] table row in force during tau-leap step k (t_k = t0 + k*tau
+                                   accumulated in FP64 as base.py:433) */
+    int32_t  n_tdpf_values;
+    int32_t  n_tdpf_index;      /* length of tdpf_index; must be >= the number of steps (see sodm_jump_n_steps) */
+    double   t0;                /* first output time; outputs at t0, t0+1, ..., t0+n_out-1 (base.py:449) */
+    int32_t  n_out;
+    int32_t  n_sel;             /* 0: all states, else number of entries of state_sel */
+    double   tau;               /* tau-leap step (ignored by SSA) */
+    const int32_t* state_sel;   /* (host)   [n_sel] flat state elements to output, in output-row order */
+    void*    out;               /* (device) [n_rows][n_out][ld_out] of out_dtype, n_rows = n_sel ? n_sel : n_state */
+    int32_t* status;            /* (device) [n_traj] SODM_ST_* bits, may be NULL */
+    int64_t  max_events;        /* SSA: event budget per trajectory (0 = 2^62) */
+    void*    stream;
+} sodm_jump_args;
+
+int sodm_jump_run(const sodm_jump_args* args);
+/* Number of tau-leap steps the reference's loop `while t < t1: t = t + tau` takes (base.py:428-434). */
+int64_t sodm_jump_n_steps(double t0, int32_t n_out, double tau);
+
+/* ---- seam S, ODEs: replaces base.py:855 (solve_ivp) / :800-819 (Euler) for n_traj parameter draws ------ */
+typedef struct sodm_ode_args {
+    int32_t  model;
+    int32_t  model_arg;         /* packed_pfr_ode: nx */
+    int32_t  method;            /* SODM_ODE_* */
+    int32_t  out_dtype;         /* SODM_F32 | SODM_F64 */
+    int64_t  n_traj;
+    int64_t  ld_in;
+    int64_t  ld_out;
+    const double*  y0;          /* (device) [n_state][ld_in] or [n_state] */
+    int32_t  y0_broadcast;
+    int32_t  n_var;
+    const double*  par;         /* (host) [n_param] */
+    const int32_t* var_index;   /* (host) [n_var] */
+    const double*  var_values;  /* (device) [n_var][ld_in] */
+    double   t0;
+    int32_t  n_out;             /* reference grid t0 .. t0+n_out-1 */
+    int32_t  out_stride;        /* keep grid points 0, out_stride, 2*out_stride, ... (1 = reference grid) */
+    int32_t  out_last_only;     /* 1: keep only the final grid point (the tutorial's isel(time=-1)) */
+    int32_t  reserved;
+    double   rtol;              /* RK45 (reference default 1e-4, base.py:877) */
+    double   atol;              /* RK45 (scipy default 1e-6: the reference does not pass atol) */
+    double   tau;               /* Euler / RK4 step */
+    void*    out;               /* (device) [n_state][n_kept][ld_out] */
+    int32_t* nfev;              /* (device) [n_traj] right-hand-side evaluations (scipy's sol.nfev), may be NULL */
+    int32_t* status;            /* (device) [n_traj], may be NULL */
+    int64_t  max_steps;         /* 0 = 2^31-1 */
+    void*    stream;
+} sodm_ode_args;
+
+int sodm_ode_run(const sodm_ode_args* args);
+/* number of grid points kept for (n_out, out_stride, out_last_only) */
+int32_t sodm_ode_n_kept(int32_t n_out, int32_t out_stride, int32_t out_last_only);
+
+/* ---- seam L: replaces objective_functions.py:250-288 + :550-666 for n_traj trajectories --------------- */
+#define SODM_LL_POISSON   0
+#define SODM_LL_NORMAL    1
+#define SODM_LL_LOGNORMAL 2
+#define SODM_LL_NEGBIN    3
+/* ll_arg broadcasting (sigma / alpha): one value, one per data column, one per data point */
+#define SODM_ARG_NONE   0
+#define SODM_ARG_SCALAR 1
+#define SODM_ARG_COLUMN 2
+#define SODM_ARG_FULL   3
+
+typedef struct sodm_loglik_args {
+    int32_t  kind;              /* SODM_LL_* */
+    int32_t  traj_dtype;        /* SODM_I32 | SODM_F32 | SODM_F64 */
+    int64_t  n_traj;
+    int64_t  ld;                /* row stride of traj */
+    const void*    traj;        /* (device) [n_row][n_out][ld] simulator output */
+    int32_t  n_out;             /* grid points t0 .. t0+n_out-1 */
+    int32_t  n_col;             /* data columns */
+    const int32_t* col_ptr;     /* (device) [n_col+1] CSR offsets into col_rows: model output rows summed into a column
+                                   (the sum over dimensions absent from the data, objective_functions.py:250-252) */
+    const int32_t* col_rows;    /* (device) [col_ptr[n_col]] */
+    double   t0;
+    int32_t  n_t;               /* data time points */
+    int32_t  arg_mode;          /* SODM_ARG_* */
+    const double*  t_data;      /* (device) [n_t] data times in simulation time units (linear interpolation, :254) */
+    const double*  ydata;       /* (device) [n_t][n_col]; NaN entries are skipped */
+    const double*  ll_arg;      /* (device) sigma / alpha per arg_mode */
+    double   weight;            /* dataset weight (:266-269) */
+    double*  lp;                /* (device) [n_traj] log-probability, ACCUMULATED (+=) */
+    int32_t* status;            /* (device) [n_traj] |= SODM_ST_NONFINITE when the model output holds NaN; may be NULL */
+    void*    stream;
+} sodm_loglik_args;
+
+int sodm_loglik(const sodm_loglik_args* args);
+
+/* ---- output contract: [row][time][traj] (device layout) -> [traj][time][row] per state variable -------- */
+/* For one state variable whose rows are r0 .. r0+n_dim-1:  dst[(i*n_t + j)*n_dim + d] = src[((r0+d)*n_t + j)*ld + i]
+ * (base.py:1009-1010 moveaxis + :569-571 concat along "draws").  dst may be device or pinned host memory that is
+ * device-accessible; dtype converts src_dtype -> dst_dtype (I32/F32/F64). */
+int sodm_to_draws_major(const void* src, int32_t src_dtype, int64_t ld, int32_t r0, int32_t n_dim, int32_t n_t,
+                        int64_t n_traj, void* dst, int32_t dst_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SODM_H */

@@ -1,0 +1,159 @@
+// Exact binomial sampling for one SIMT lane.
+//
+// The reference draws its transition counts with NumPy's legacy `RandomState.binomial`
+// (/root/reference/src/pySODM/models/base.py:303): sequential inversion when n*p <= 30, BTPE
+// otherwise.  Both are exact samplers, so any other exact sampler gives the same law; the ones
+// below are chosen for SIMT execution:
+//   * n*min(p,1-p) <  SODM_BINV_THRESHOLD : sequential inversion from 0 (short, FP32, one uniform);
+//   * otherwise: Hoermann's BTRS transformed rejection (1993).  One attempt = two uniforms; ~80 % of
+//     attempts are accepted by BTRS's own box test, which needs no logarithm.  The rest are settled
+//     in FP32 by the quadratic squeeze of Kachitvichyanukul & Schmeiser's BTPE (step 5.2: for
+//     x = |k - mode| < npq/2 - 1,  -x^2/(2npq) - rho <= log f(k)/f(mode) <= -x^2/(2npq) + rho), widened
+//     by an FP32 round-off margin; only the sliver in between (~0.5-5 % of attempts) evaluates the
+//     exact FP64 log-pmf ratio, whose Stirling terms cancel from O(n*p) to O(1) and need double.
+// p > 0.5 is handled by the symmetry Bin(n, p) = n - Bin(n, 1 - p).
+//
+// `binomial_try` performs ONE attempt and reports whether it finished, so that the lanes of a warp
+// can each work through their own list of draws without waiting for each other's rejections
+// (see sample_worklist in jump_run.cuh).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include "philox.cuh"
+
+namespace sodm {
+
+#ifndef SODM_BINV_THRESHOLD
+#define SODM_BINV_THRESHOLD 10.0f
+#endif
+
+// Buffered 32-bit words from a Philox stream (4 words per block, no word is wasted).
+struct PhiloxWords {
+    Philox4x32 gen;
+    uint32_t w0, w1, w2, w3;
+    int pos;
+
+    __host__ __device__ __forceinline__ void init(uint64_t seed, uint64_t traj, uint32_t purpose = 0) {
+        gen.init(seed, traj, purpose);
+        pos = 4;
+        w0 = w1 = w2 = w3 = 0u;
+    }
+    __host__ __device__ __forceinline__ uint32_t next() {
+        if (pos >= 4) {
+            uint32_t b[4];
+            gen.next4(b);
+            w0 = b[0]; w1 = b[1]; w2 = b[2]; w3 = b[3];
+            pos = 0;
+        }
+        const uint32_t v = pos == 0 ? w0 : (pos == 1 ? w1 : (pos == 2 ? w2 : w3));
+        ++pos;
+        return v;
+    }
+};
+
+#define SODM_STIRLING_TABLE {0.0810614667953272, 0.0413406959554092, 0.0276779256849983, 0.02079067210376509, \
+                             0.0166446911898211, 0.0138761288230707, 0.0118967099458917, 0.0104112652619720,  \
+                             0.00925546218271273, 0.00833056343336287}
+#ifdef __CUDACC__
+static __constant__ double kStirlingTailDev[10] = SODM_STIRLING_TABLE;
+#endif
+
+// log(k!) - [ (k+1/2) log(k+1) - (k+1) + 1/2 log(2 pi) ]   (Stirling tail fc(k), Hoermann 1993)
+__host__ __device__ __forceinline__ double stirling_tail(double k) {
+    if (k <= 9.0) {
+#ifdef __CUDA_ARCH__
+        return kStirlingTailDev[(int)k];
+#else
+        static const double tab[10] = SODM_STIRLING_TABLE;
+        return tab[(int)k];
+#endif
+    }
+    const double kp1 = k + 1.0;
+    const double kp1sq = kp1 * kp1;
+    return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / kp1;
+}
+
+// Sequential-search inversion; requires 0 < p <= 0.5 and n*p small.
+template <class Rng>
+__host__ __device__ __forceinline__ int binomial_inversion(Rng& rng, int n, float p) {
+    const float q = 1.0f - p;
+    const float s = p / q;
+    float f = expf((float)n * log1pf(-p));      // q^n = P(X = 0)
+    float u = u01(rng.next());
+    int k = 0;
+    // P(X=k+1) = P(X=k) * s * (n-k)/(k+1).  The cap only guards against FP32 round-off in the far tail.
+    while (u > f && k < n && k < 1024) {
+        u -= f;
+        ++k;
+        f *= s * (float)(n - k + 1) / (float)k;
+    }
+    return k;
+}
+
+// exact log f(k)/f(m) for Bin(n, p), m = floor((n+1)p)   (Hoermann 1993, BTRS step 3.2)
+__host__ __device__ __forceinline__ double binomial_log_ratio(double nd, double pd, double m, double kd) {
+    const double r = pd / (1.0 - pd);
+    return (m + 0.5) * log((m + 1.0) / (r * (nd - m + 1.0))) + stirling_tail(m) + stirling_tail(nd - m)
+         + (nd + 1.0) * log((nd - m + 1.0) / (nd - kd + 1.0))
+         + (kd + 0.5) * log(r * (nd - kd + 1.0) / (kd + 1.0))
+         - stirling_tail(kd) - stirling_tail(nd - kd);
+}
+
+// One BTRS attempt; requires 0 < p <= 0.5 and n*p >= 10.  Returns true and sets k when accepted.
+template <class Rng>
+__host__ __device__ __forceinline__ bool btrs_try(Rng& rng, int n, float p, int& k) {
+    const float nf = (float)n;
+    const float npq = nf * p * (1.0f - p);
+    const float stddev = sqrtf(npq);
+    const float b = 1.15f + 2.53f * stddev;
+    const float a = -0.0873f + 0.0248f * b + 0.01f * p;
+    const float inv_b = 1.0f / b;
+    const float v_r = 0.92f - 4.2f * inv_b;
+    const float u = u01(rng.next()) - 0.5f;
+    const float v = u01(rng.next());
+    const float us = 0.5f - fabsf(u);
+    const double nd = (double)n, pd = (double)p;
+    const double kd = floor(fma((double)(2.0f * a / us + b), (double)u, fma(nd, pd, 0.5)));
+    k = (int)kd;
+    if (us >= 0.07f && v <= v_r) return true;                    // BTRS box: no logarithm needed
+    if (kd < 0.0 || kd > nd) return false;
+    const float alpha = (2.83f + 5.1f * inv_b) * stddev;
+    const float lhs = logf(v * alpha / (a / (us * us) + b));
+    const double m = floor((nd + 1.0) * pd);
+    const float x = fabsf((float)(kd - m));
+    if (x < 0.5f * npq - 1.0f) {                                  // BTPE step 5.2 squeeze, in FP32
+        const float t = -x * x / (2.0f * npq);
+        const float rho = (x / npq) * ((x * (x * (1.0f / 3.0f) + 0.625f) + (1.0f / 6.0f)) / npq + 0.5f);
+        const float eps = 4e-6f * (1.0f + fabsf(t) + fabsf(lhs));
+        if (lhs < t - rho - eps) return true;
+        if (lhs > t + rho + eps) return false;
+    }
+    return (double)lhs <= binomial_log_ratio(nd, pd, m, kd);     // exact test (rare)
+}
+
+// ONE attempt at Bin(n, p), 0 <= p <= 1.  Returns true when finished with the variate in k.
+// NaN / out-of-range p or n < 0 finish with k = -1 (the reference's NumPy call raises ValueError there;
+// callers turn -1 into a status flag).
+template <class Rng>
+__host__ __device__ __forceinline__ bool binomial_try(Rng& rng, int n, float p, int& k) {
+    if (!(p >= 0.0f && p <= 1.0f) || n < 0) { k = -1; return true; }
+    const bool flip = p > 0.5f;
+    const float pp = flip ? 1.0f - p : p;
+    if (n == 0 || pp == 0.0f) { k = flip ? n : 0; return true; }
+    int kk;
+    bool done = true;
+    if ((float)n * pp < SODM_BINV_THRESHOLD) kk = binomial_inversion(rng, n, pp);
+    else done = btrs_try(rng, n, pp, kk);
+    k = flip ? n - kk : kk;
+    return done;
+}
+
+template <class Rng>
+__host__ __device__ __forceinline__ int binomial(Rng& rng, int n, float p) {
+    int k = 0;
+    for (int attempt = 0; attempt < 1000; ++attempt)
+        if (binomial_try(rng, n, p, k)) return k;
+    return k;
+}
+
+}  // namespace sodm

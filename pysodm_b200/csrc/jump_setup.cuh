@@ -1,0 +1,116 @@
+// Validation of a sodm_jump_args request and its translation into the by-value kernel argument block.
+// Host-only; shared by the CUDA entry point (sodm_jump.cu) and the test-only CPU harness
+// (tests/hostcheck), which runs the same __host__ __device__ trajectory code without a GPU.
+#pragma once
+#include <cmath>
+#include "common.cuh"
+#include "jump_run.cuh"
+
+namespace sodm {
+
+// tau = 2^-k (k >= 0): step times are exact in FP64 and every integer output time is a step time
+inline bool tau_is_aligned(double tau, int* steps_per_out) {
+    if (!(tau > 0.0) || tau > 1.0) return false;
+    const double inv = 1.0 / tau;
+    if (inv != floor(inv) || inv > 1048576.0) return false;
+    const int64_t n = (int64_t)inv;
+    if ((n & (n - 1)) != 0) return false;
+    *steps_per_out = (int)n;
+    return true;
+}
+
+
+inline int64_t jump_n_steps(double t0, int32_t n_out, double tau) {
+    if (!(tau > 0.0) || n_out < 1) return -1;
+    const double t_end = t0 + (double)(n_out - 1);
+    int64_t n = 0;
+    double t = t0;                       // same FP64 accumulation as base.py:428-434
+    while (t < t_end) {
+        t = t + tau;
+        if (++n > (int64_t)1 << 31) return -1;
+    }
+    return n;
+}
+
+// Fills L and `aligned`; returns SODM_OK or an error code (message in the thread-local buffer).
+inline int build_jump_launch(const sodm_jump_args* a, JumpLaunch& L, bool& aligned) {
+    if (!a) return fail(SODM_EINVAL, "sodm_jump_run: null args");
+    sodm_model_info info;
+    if (sodm_model_info_get(a->model, 0, &info) != SODM_OK || info.kind != SODM_KIND_JUMP)
+        return fail(SODM_EMODEL, "sodm_jump_run: model %d is not a jump-process model", a->model);
+    if (a->n_traj < 0 || a->ld_in < a->n_traj || a->ld_out < a->n_traj)
+        return fail(SODM_EINVAL, "sodm_jump_run: need 0 <= n_traj <= ld_in, ld_out");
+    if (a->n_out < 1) return fail(SODM_EINVAL, "sodm_jump_run: n_out must be >= 1");
+    if (!a->y0 || !a->par || !a->out) return fail(SODM_EINVAL, "sodm_jump_run: y0, par and out are required");
+    if (a->n_var < 0 || a->n_var > info.n_param || (a->n_var && (!a->var_index || !a->var_values)))
+        return fail(SODM_EINVAL, "sodm_jump_run: inconsistent per-trajectory parameter description");
+    if (a->method != SODM_JUMP_TAU_LEAP && a->method != SODM_JUMP_SSA)
+        return fail(SODM_EINVAL, "sodm_jump_run: unknown method %d", a->method);
+
+    L = JumpLaunch{};
+    L.n_traj = a->n_traj;
+    L.traj_id0 = a->traj_id0;
+    L.ld_in = a->ld_in;
+    L.ld_out = a->ld_out;
+    L.seed = a->seed;
+    L.y0 = a->y0;
+    L.y0_bcast = a->y0_broadcast;
+    for (int e = 0; e < MAX_PARAM; ++e) { L.par[e] = e < info.n_param ? a->par[e] : 0.0; L.var_row[e] = -1; }
+    for (int v = 0; v < a->n_var; ++v) {
+        const int e = a->var_index[v];
+        if (e < 0 || e >= info.n_param) return fail(SODM_EINVAL, "sodm_jump_run: var_index[%d]=%d out of range", v, e);
+        if (info.tdpf_count && e >= info.tdpf_offset && e < info.tdpf_offset + info.tdpf_count)
+            return fail(SODM_EUNSUPPORTED, "sodm_jump_run: parameter element %d is time dependent and cannot also vary per trajectory", e);
+        L.var_row[e] = (int8_t)v;
+    }
+    L.var_values = a->var_values;
+    L.t0 = a->t0;
+    L.tau = a->tau;
+    L.n_out = a->n_out;
+    for (int s = 0; s < MAX_STATE; ++s) L.out_row[s] = -1;
+    if (a->n_sel == 0) {
+        for (int s = 0; s < info.n_state; ++s) L.out_row[s] = (int8_t)s;
+    } else {
+        if (a->n_sel < 0 || a->n_sel > info.n_state || !a->state_sel)
+            return fail(SODM_EINVAL, "sodm_jump_run: bad state selection");
+        for (int r = 0; r < a->n_sel; ++r) {
+            const int s = a->state_sel[r];
+            if (s < 0 || s >= info.n_state || L.out_row[s] >= 0)
+                return fail(SODM_EINVAL, "sodm_jump_run: state_sel[%d]=%d invalid or repeated", r, s);
+            L.out_row[s] = (int8_t)r;
+        }
+    }
+    L.out = a->out;
+    L.status = a->status;
+    L.compat = a->compat;
+    L.max_events = a->max_events > 0 ? a->max_events : ((int64_t)1 << 62);
+
+    aligned = false;
+    if (a->method == SODM_JUMP_TAU_LEAP) {
+        const int64_t n_steps = jump_n_steps(a->t0, a->n_out, a->tau);
+        if (n_steps < 0) return fail(SODM_EINVAL, "sodm_jump_run: tau must be > 0 (and the run below 2^31 steps)");
+        L.n_steps = (int32_t)n_steps;
+        int spo = 0;
+        aligned = tau_is_aligned(a->tau, &spo);
+        L.steps_per_out = aligned ? spo : 0;
+        if (info.tdpf_count) {
+            if (!a->tdpf_table || !a->tdpf_index || a->n_tdpf_values < 1 || a->n_tdpf_index < n_steps)
+                return fail(SODM_EINVAL, "sodm_jump_run: model needs a time-dependent parameter table with >= %lld step entries",
+                            (long long)n_steps);
+            if ((size_t)a->n_tdpf_values * info.tdpf_count * sizeof(float) > 16 * 1024)
+                return fail(SODM_EUNSUPPORTED, "sodm_jump_run: more than %d distinct time-dependent values",
+                            (int)(16 * 1024 / sizeof(float) / info.tdpf_count));
+            L.n_tdpf_values = a->n_tdpf_values;
+            L.tdpf_index = a->tdpf_index;
+            L.tdpf_table = a->tdpf_table;
+        }
+    } else {
+        if (!info.supports_ssa) return fail(SODM_EUNSUPPORTED, "sodm_jump_run: model %d has no SSA functor", a->model);
+    }
+    if (a->out_dtype == SODM_I32 && !aligned)
+        return fail(SODM_EINVAL, "sodm_jump_run: int32 output needs tau-leap with tau = 2^-k (outputs are interpolated otherwise)");
+
+    return SODM_OK;
+}
+
+}  // namespace sodm

@@ -1,0 +1,68 @@
+// Philox4x32-10 counter-based generator, one independent stream per trajectory.
+//
+// Replaces the reference's per-draw reseeding of NumPy's global MT19937
+// (/root/reference/src/pySODM/models/base.py:481,561,566): there a 32-bit seed per draw is taken
+// from the parent's RNG; here the stream of trajectory `g` is the Philox keystream with
+//   key     = (seed_lo, seed_hi)
+//   counter = (block_index, lane_purpose, g_lo, g_hi)
+// so a trajectory's randomness depends only on (seed, global trajectory id) -- results do not change
+// with the number of GPUs or the launch geometry.
+#pragma once
+#include <cstdint>
+
+namespace sodm {
+
+struct Philox4x32 {
+    uint32_t key0, key1;      // seed
+    uint32_t ctr0, ctr1;      // running block counter (64 bit)
+    uint32_t ctr2, ctr3;      // global trajectory id
+
+    __host__ __device__ __forceinline__ void init(uint64_t seed, uint64_t traj, uint32_t purpose = 0) {
+        key0 = (uint32_t)seed;
+        key1 = (uint32_t)(seed >> 32);
+        ctr0 = 0u;
+        ctr1 = purpose;
+        ctr2 = (uint32_t)traj;
+        ctr3 = (uint32_t)(traj >> 32);
+    }
+
+    static __host__ __device__ __forceinline__ void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+        lo = a * b;
+        hi = __umulhi(a, b);
+#else
+        uint64_t p = (uint64_t)a * (uint64_t)b;
+        lo = (uint32_t)p;
+        hi = (uint32_t)(p >> 32);
+#endif
+    }
+
+    // Generates the next block of 4 x 32 random bits and advances the counter.
+    __host__ __device__ __forceinline__ void next4(uint32_t (&out)[4]) {
+        constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+        constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+        uint32_t c0 = ctr0, c1 = ctr1, c2 = ctr2, c3 = ctr3;
+        uint32_t k0 = key0, k1 = key1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0, lo0, hi1, lo1;
+            mulhilo(M0, c0, hi0, lo0);
+            mulhilo(M1, c2, hi1, lo1);
+            c0 = hi1 ^ c1 ^ k0;
+            c1 = lo1;
+            c2 = hi0 ^ c3 ^ k1;
+            c3 = lo0;
+            k0 += W0;
+            k1 += W1;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+        if (++ctr0 == 0u) ++ctr1;
+    }
+};
+
+// 24-bit uniform strictly inside (0, 1)
+__host__ __device__ __forceinline__ float u01(uint32_t x) {
+    return (float)(x >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;
+}
+
+}  // namespace sodm

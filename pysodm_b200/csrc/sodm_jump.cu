@@ -1,0 +1,81 @@
+// Jump-process ensemble kernels (tau-leap, SSA) and their C-ABI entry point.
+//
+// One thread per trajectory, state and parameters in registers, structure-of-arrays I/O so that a
+// warp's loads/stores are coalesced 128-byte transactions, the time-dependent-parameter table (the
+// influenza contact matrices) staged once per block in shared memory and read by broadcast.
+// Replaces /root/reference/src/pySODM/models/base.py:558-566 (the loop over draws in
+// `JumpProcess.sim`) and everything it calls (:206-348, :352-440).
+#include "jump_setup.cuh"
+
+namespace sodm {
+
+constexpr int JUMP_BLOCK = 128;
+
+template <class M, typename OutT, bool ALIGNED>
+__global__ void __launch_bounds__(JUMP_BLOCK) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
+    extern __shared__ float smem[];
+    // [NDRAW][JUMP_BLOCK] draw counts | [NDRAW][JUMP_BLOCK] probabilities | time-dependent parameter table
+    WorkList w;
+    w.n = reinterpret_cast<int*>(smem) + threadIdx.x;
+    w.p = smem + M::NDRAW * JUMP_BLOCK + threadIdx.x;
+    w.stride = JUMP_BLOCK;
+    float* table = smem + 2 * M::NDRAW * JUMP_BLOCK;
+    const int n_tab = L.n_tdpf_values * M::TDPF_COUNT;
+    for (int e = threadIdx.x; e < n_tab; e += blockDim.x) table[e] = (float)L.tdpf_table[e];   // ABI speaks FP64, rates are FP32
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < L.n_traj) tau_leap_trajectory<M, OutT, ALIGNED>(L, i, table, w);
+}
+
+template <class M, typename OutT>
+__global__ void __launch_bounds__(JUMP_BLOCK) ssa_kernel(const __grid_constant__ JumpLaunch L) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < L.n_traj) ssa_trajectory<M, OutT>(L, i);
+}
+
+template <class M, typename OutT>
+static int launch_jump(const JumpLaunch& L, int method, bool aligned, cudaStream_t stream) {
+    const unsigned grid = (unsigned)((L.n_traj + JUMP_BLOCK - 1) / JUMP_BLOCK);
+    if (method == SODM_JUMP_TAU_LEAP) {
+        const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
+        if (aligned) tau_leap_kernel<M, OutT, true><<<grid, JUMP_BLOCK, smem, stream>>>(L);
+        else         tau_leap_kernel<M, OutT, false><<<grid, JUMP_BLOCK, smem, stream>>>(L);
+    } else {
+        ssa_kernel<M, OutT><<<grid, JUMP_BLOCK, 0, stream>>>(L);
+    }
+    SODM_CUDA_CHECK(cudaGetLastError());
+    return SODM_OK;
+}
+
+template <class M>
+static int launch_jump_dtype(const JumpLaunch& L, int method, bool aligned, int dtype, cudaStream_t stream) {
+    switch (dtype) {
+        case SODM_I32: return launch_jump<M, int32_t>(L, method, aligned, stream);
+        case SODM_F32: return launch_jump<M, float>(L, method, aligned, stream);
+        case SODM_F64: return launch_jump<M, double>(L, method, aligned, stream);
+    }
+    return fail(SODM_EINVAL, "sodm_jump_run: unknown out_dtype %d", dtype);
+}
+
+}  // namespace sodm
+
+using namespace sodm;
+
+extern "C" int64_t sodm_jump_n_steps(double t0, int32_t n_out, double tau) { return jump_n_steps(t0, n_out, tau); }
+
+extern "C" int sodm_jump_run(const sodm_jump_args* a) {
+    JumpLaunch L;
+    bool aligned = false;
+    const int rc0 = build_jump_launch(a, L, aligned);
+    if (rc0 != SODM_OK) return rc0;
+    if (a->n_traj == 0) return SODM_OK;
+    cudaStream_t stream = (cudaStream_t)a->stream;
+    int rc;
+    switch (a->model) {
+        case MODEL_SIR_JUMP:       rc = launch_jump_dtype<SirJump>(L, a->method, aligned, a->out_dtype, stream); break;
+        case MODEL_SIR_SI_JUMP:    rc = launch_jump_dtype<SirSiJump>(L, a->method, aligned, a->out_dtype, stream); break;
+        case MODEL_INFLUENZA_JUMP: rc = launch_jump_dtype<InfluenzaJump>(L, a->method, aligned, a->out_dtype, stream); break;
+        default: rc = fail(SODM_EMODEL, "sodm_jump_run: model %d not registered", a->model);
+    }
+    return rc;
+}

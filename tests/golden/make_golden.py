@@ -1,0 +1,353 @@
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE UNMODIFIED REFERENCE.
+
+Run in the build container only (needs /root/reference):   python tests/golden/make_golden.py [what ...]
+`what` in {jump_single, jump_ensemble, ssa, ode, loglik, schedule}; default = all.
+
+The fixtures pin the oracle (oracle/*.py) -- see oracle/__init__.py -- and are what the GPU parity
+tests compare against on a box where the reference is absent.
+"""
+import os
+import random
+import sys
+import time
+from datetime import datetime
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_loader  # noqa: E402
+
+base, objf = ref_loader.load()
+
+# ------------------------------------------------------------------------------------------------
+# model set-ups, as the tutorials / tests make them
+# ------------------------------------------------------------------------------------------------
+
+# tutorials/influenza_1718/calibration.py:82-95
+N_NOHOLIDAY_WEEK = np.transpose(np.array([[10.47, 3.16, 10.65, 0.55], [1.65, 19.41, 11.79, 0.70],
+                                          [0.93, 1.98, 14.09, 0.96], [0.18, 0.45, 3.67, 3.09]]))
+N_NOHOLIDAY_WEEKEND = np.transpose(np.array([[1.81, 2.46, 8.92, 1.52], [1.28, 7.07, 14.76, 1.64],
+                                             [0.78, 2.49, 15.26, 1.17], [0.51, 1.05, 4.45, 2.00]]))
+N_HOLIDAY_WEEK = np.transpose(np.array([[4.54, 2.47, 10.86, 0.35], [1.29, 5.76, 9.64, 1.47],
+                                        [0.96, 1.63, 13.08, 1.38], [0.12, 0.94, 5.23, 5.10]]))
+CONTACTS = {'holiday': {'week': N_HOLIDAY_WEEK, 'weekend': N_NOHOLIDAY_WEEKEND},
+            'no_holiday': {'week': N_NOHOLIDAY_WEEK, 'weekend': N_NOHOLIDAY_WEEKEND}}
+AGE_GROUPS = pd.IntervalIndex.from_tuples([(0, 5), (5, 15), (15, 65), (65, 120)], closed='left')
+
+
+def influenza_data():
+    path = os.path.join(ref_loader.REFERENCE_ROOT, 'tutorials/influenza_1718/data/interim/ILI_weekly_ABS.csv')
+    data = pd.read_csv(path, index_col=[0, 1], parse_dates=True, date_format='%Y-%m-%d').squeeze()
+    dates = data.index.get_level_values('DATE').unique()
+    index = pd.MultiIndex.from_product([dates, AGE_GROUPS], names=['date', 'age_group'])
+    return pd.Series(index=index, name='CASES', data=data.values) / 7       # calibration.py:62
+
+
+def make_influenza():
+    flu = ref_loader.load_tutorial_module('tutorials/influenza_1718/models.py', 'ref_flu_models')
+    df = influenza_data()
+    start = df.index.get_level_values('date').unique()[8].strftime('%Y-%m-%d')
+    params = {'alpha': 1, 'beta': 0.0174, 'gamma': 1, 'delta': 3,
+              'f_ud': np.array([0.01, 0.64, 0.905, 0.60]), 'N': CONTACTS['holiday']['week']}
+    row = df.loc[start, slice(None)]
+    init = {'S': [620914, 1306826, 7317774, 2130556],
+            'E': list(np.rint((1 / (1 - params['f_ud'])) * row)),
+            'Ip': list(np.rint((1 / (1 - params['f_ud'])) * row)),
+            'Iud': list(np.rint((params['f_ud'] / (1 - params['f_ud'])) * row)),
+            'Id': list(np.rint(row)),
+            'Im_inc': list(np.rint(row))}
+    cf = flu.make_contact_matrix_function(CONTACTS).contact_function
+    model = flu.JumpProcess_influenza_model(initial_states=init, parameters=params,
+                                            coordinates={'age_group': AGE_GROUPS},
+                                            time_dependent_parameters={'N': cf})
+    return model, cf, df, start
+
+
+def make_sir_si(jump=True, scale=1.0):
+    m = ref_loader.load_tutorial_module('tutorials/SIR_SI/models.py', 'ref_sirsi_models')
+    params = {'alpha': np.array([0.05, 0.1, 0.2, 0.15]), 'gamma': 5, 'beta': 7}   # SIR_SI/calibration.py:31
+    S = [606938, 1328733, 7352492, 2204478]
+    init = {'S': [round(s * scale) for s in S], 'S_v': round(1e6 * scale), 'I_v': 2}
+    cls = m.JumpProcess_SIR_SI if jump else m.ODE_SIR_SI
+    return cls(init, params, coordinates={'age_group': AGE_GROUPS})
+
+
+def make_test_sir_jump():
+    class SIR(base.JumpProcess):                 # src/tests/test_JumpProcess.py:11-27
+        states = ['S', 'I', 'R']
+        parameters = ['beta', 'gamma']
+
+        @staticmethod
+        def compute_rates(t, S, I, R, beta, gamma):
+            return {'S': [beta * (I / (S + I + R)), ], 'I': [np.array([gamma]), ]}
+
+        @staticmethod
+        def apply_transitionings(t, tau, transitionings, S, I, R, beta, gamma):
+            S_new = S - transitionings['S'][0]
+            I_new = I + transitionings['S'][0] - transitionings['I'][0]
+            R_new = R + transitionings['I'][0]
+            return S_new, I_new, R_new
+    return SIR(initial_states={'S': 1_000_000 - 10, 'I': 10}, parameters={'beta': 0.9, 'gamma': 0.2})
+
+
+def contact_schedule(cf, start, n_steps, tau):
+    """Evaluate the reference TDPF at every tau-leap step time, as base.py:365-380 does."""
+    start_date = datetime.strptime(start, '%Y-%m-%d')
+    mats = [CONTACTS['no_holiday']['week'], CONTACTS['no_holiday']['weekend'], CONTACTS['holiday']['week']]
+    idx = np.empty(n_steps, dtype=np.int32)
+    t = 0
+    for k in range(n_steps):
+        date = base.time_to_date(float(t), start_date, 'D')
+        M = cf(date, {}, None)
+        idx[k] = [i for i, m in enumerate(mats) if M is m][0]
+        t = t + tau
+    return np.stack(mats), idx
+
+
+def flat_y0(model):
+    return np.concatenate([np.ravel(v) for v in model.initial_states.values()]).astype(np.float64)
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrays)
+    print(f'wrote {path}  ({os.path.getsize(path) / 1e6:.2f} MB)')
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_jump_single():
+    """Seeded single trajectories (global NumPy RNG seeded right before each sim call)."""
+    out = {}
+    flu, cf, df, start = make_influenza()
+    table, idx = contact_schedule(cf, start, 322, 0.5)
+    out['flu_table'], out['flu_step_index'], out['flu_y0'] = table, idx, flat_y0(flu)
+    seeds = [11, 12, 13]
+    ys = []
+    for s in seeds:
+        np.random.seed(s)
+        r = flu.sim([start, '2018-05-11'], N=1, tau=0.5)
+        ys.append(r['y'])
+    out['flu_seeds'], out['flu_y'] = np.array(seeds), np.stack(ys)
+    # non-dyadic tau -> real interpolation (F3/Q4/Q5)
+    np.random.seed(21)
+    out['flu_tau03_y'] = flu.sim([start, '2018-01-15'], N=1, tau=0.3)['y']
+    t, n = 0, 0
+    while t < 45:
+        t = t + 0.3
+        n += 1
+    out['flu_tau03_table'], out['flu_tau03_step_index'] = contact_schedule(cf, start, n, 0.3)
+
+    sirsi = make_sir_si()
+    out['sirsi_y0'] = flat_y0(sirsi)
+    ys = []
+    for s in seeds:
+        np.random.seed(s)
+        ys.append(sirsi.sim(120, N=1, tau=0.5)['y'])
+    out['sirsi_y'] = np.stack(ys)
+    np.random.seed(5)
+    out['sirsi_tau1_y'] = sirsi.sim(60, N=1, tau=1)['y']
+
+    sir = make_test_sir_jump()
+    out['sir_y0'] = flat_y0(sir)
+    ys = []
+    for s in seeds:
+        np.random.seed(s)
+        ys.append(sir.sim(50, N=1, tau=1)['y'])
+    out['sir_y'] = np.stack(ys)
+    save('jump_single.npz', **out)
+
+
+def gen_ssa():
+    """Seeded SSA runs; population / 1000 so that a run is ~6e3 events."""
+    out = {}
+    sirsi = make_sir_si(scale=1e-3)
+    sirsi.initial_states['I_v'] = np.array(2.0)
+    out['sirsi_small_y0'] = flat_y0(sirsi)
+    ys = []
+    seeds = [3, 4]
+    for s in seeds:
+        np.random.seed(s)
+        random.seed(1000 + s)
+        ys.append(sirsi.sim(30, N=1, method='SSA')['y'])
+    out['seeds'], out['sirsi_small_y'] = np.array(seeds), np.stack(ys)
+    # ensemble for KS (serial; 30 days of the /1000 population is ~1e3 events per run)
+    t = time.time()
+    np.random.seed(99)
+    random.seed(99)
+    n = 400
+    res = sirsi.sim(30, N=n, method='SSA')
+    out['sirsi_small_ens'] = np.stack([r['y'] for r in res]).astype(np.float32)
+    print(f'SSA ensemble n={n}: {time.time() - t:.1f}s')
+    save('ssa.npz', **out)
+
+
+def gen_jump_ensemble(n=2000, processes=8):
+    """Reference ensembles for KS tests of the batched oracle (and, transitively, of the GPU)."""
+    out = {}
+    flu, cf, df, start = make_influenza()
+    t = time.time()
+    np.random.seed(1718)
+    res = flu.sim([start, '2018-05-11'], N=n, tau=0.5, processes=processes)
+    Y = np.stack([r['y'] for r in res])                      # [n, 28, 162]
+    print(f'influenza reference ensemble n={n}: {time.time() - t:.1f}s ({n / (time.time() - t):.1f} traj/s)')
+    times = np.array([1, 3, 7, 14, 28, 42, 56, 70, 84, 100, 120, 140, 161])
+    out['flu_times'], out['flu_ens'] = times, Y[:, :, times].astype(np.int32)
+    out['flu_mean'] = Y.mean(axis=0)
+    out['flu_q'] = np.quantile(Y, [0.025, 0.5, 0.975], axis=0)
+
+    sirsi = make_sir_si()
+    t = time.time()
+    np.random.seed(4242)
+    res = sirsi.sim(120, N=n, tau=0.5, processes=processes)
+    Y = np.stack([r['y'] for r in res])                      # [n, 14, 121]
+    print(f'SIR_SI reference ensemble n={n}: {time.time() - t:.1f}s')
+    times = np.array([1, 5, 10, 20, 40, 60, 80, 100, 120])
+    out['sirsi_times'], out['sirsi_ens'] = times, Y[:, :, times].astype(np.int32)
+    out['sirsi_mean'] = Y.mean(axis=0)
+    out['sirsi_q'] = np.quantile(Y, [0.025, 0.5, 0.975], axis=0)
+    save('jump_ensemble.npz', **out)
+
+
+def gen_schedule():
+    """Contact-matrix schedule of the reference TDPF over a wide date range and several tau."""
+    flu, cf, df, start = make_influenza()
+    out = {}
+    for label, (s, n, tau) in {'season': ('2017-12-01', 322, 0.5), 'autumn': ('2017-10-01', 400, 1.0),
+                               'spring': ('2018-02-01', 600, 0.25)}.items():
+        table, idx = contact_schedule(cf, s, n, tau)
+        out[label + '_index'] = idx
+        out[label + '_meta'] = np.array([datetime.strptime(s, '%Y-%m-%d').toordinal(), n, tau])
+    out['table'] = table
+    save('contact_schedule.npz', **out)
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_ode():
+    out = {}
+    # C1: tutorial SIR, N=100 draws of beta (tutorials/SIR/workflow_tutorial.py:49-70)
+    class ODE_SIR(base.ODE):
+        states = ['S', 'I', 'R']
+        parameters = ['beta', 'gamma']
+
+        @staticmethod
+        def integrate(t, S, I, R, beta, gamma):
+            N = S + I + R
+            dS = -beta * S * I / N
+            dI = beta * S * I / N - 1 / gamma * I
+            dR = 1 / gamma * I
+            return dS, dI, dR
+    sir = ODE_SIR(initial_states={'S': 1000, 'I': 1}, parameters={'beta': 0.35, 'gamma': 5})
+    rng = np.random.default_rng(1718)
+    betas = rng.uniform(0.25, 0.45, size=100)
+    ys, nfev = [], []
+    for b in betas:
+        sir.parameters['beta'] = b
+        r = sir.sim(120)
+        ys.append(r['y'])
+        nfev.append(r['nfev'])
+    out['sir_betas'], out['sir_y'], out['sir_nfev'] = betas, np.stack(ys), np.array(nfev)
+    sir.parameters['beta'] = 0.35
+    for rtol in (1e-6, 1e-9):
+        r = sir.sim(120, rtol=rtol)
+        out[f'sir_rtol{rtol:g}_y'], out[f'sir_rtol{rtol:g}_nfev'] = r['y'], np.array(r['nfev'])
+    out['sir_euler_y'] = sir.sim(60, tau=0.25)['y']
+    out['sir_t20_121_y'] = sir.sim([20, 121])['y']
+
+    # SIR_SI ODE
+    sirsi = make_sir_si(jump=False)
+    r = sirsi.sim(120)
+    out['sirsi_y0'], out['sirsi_y'], out['sirsi_nfev'] = flat_y0(sirsi), r['y'], np.array(r['nfev'])
+
+    # PPBB (tutorials/enzyme_kinetics/models.py:53-69); values in the range of calibrate_intrinsic_kinetics.py
+    enz = ref_loader.load_tutorial_module('tutorials/enzyme_kinetics/models.py', 'ref_enzyme_models')
+    ppbb_par = {'c_enzyme': 10, 'Vf_Ks': 7.95e-04, 'R_AS': 0.047, 'R_AW': 1.10, 'R_Es': 0.131, 'K_eq': 0.66}
+    ppbb = enz.PPBB_model({'S': 46.0, 'A': 61.0, 'W': 37.0, 'Es': 0.0}, ppbb_par)
+    r = ppbb.sim(1500)
+    out['ppbb_y0'], out['ppbb_y'], out['ppbb_nfev'] = flat_y0(ppbb), r['y'], np.array(r['nfev'])
+    out['ppbb_par'] = np.array([ppbb_par[k] for k in ('c_enzyme', 'Vf_Ks', 'R_AS', 'R_AW', 'R_Es', 'K_eq')])
+
+    # C4: packed PFR nx=25, a few posterior draws (simulate_1D_PFR.py:64-120)
+    import math
+    from scipy.io import netcdf_file
+    nc = netcdf_file(os.path.join(ref_loader.REFERENCE_ROOT,
+                                  'tutorials/enzyme_kinetics/data/username_SAMPLES_2025-02-05.nc'), 'r', mmap=False)
+    names = ['Vf_Ks', 'R_AS', 'R_AW', 'R_Es', 'K_eq']
+    samples = np.stack([np.array(nc.variables[k][:], dtype=np.float64).ravel() for k in names], axis=1)
+    out['pfr_posterior'] = samples                                 # [900, 5] (iteration-major, chain)
+    for nx in (25,):
+        l, Q, dt = 1, (0.20 / 60) * 10 ** -6, 0.0024
+        dp, mu, rho_B, rho_F = 0.0004755, 3.35e-03, 545, 775
+        D_AB = np.array([3.47e-07, 2.33e-07, 1.95e-07, 1.39e-06])
+        epsilon = 0.39 + 1.74 / (dt / dp + 1.140) ** 2
+        A = (dt / 2) ** 2 * math.pi
+        U = Q / A
+        u = U / epsilon
+        Re = dp * U * rho_F / mu / (1 - epsilon)
+        a = 6 * (1 - epsilon) / dp
+        kL = (0.7 * D_AB + (dp * U) / (0.18 + 0.008 * Re ** 0.59))
+        D_ax = ((1.09 / 100) * (D_AB / dp) ** (2 / 3) * (U) ** (1 / 3))
+        params = {'epsilon': epsilon, 'kL_a': kL * a, 'D_ax': D_ax, 'delta_x': l / nx, 'u': u, 'rho_B': rho_B,
+                  'Vf_Ks': 7.88e-04, 'R_AS': 0.055, 'R_AW': 2.64, 'R_Es': 0.079, 'K_eq': 0.418}
+        coords = {'species': ['S', 'A', 'Es', 'W'], 'x': np.linspace(start=0, stop=l, num=nx)}
+        C_F = np.zeros([4, nx])
+        C_S = np.zeros([4, nx])
+        C_F[:, 0] = [30, 60, 0, 28]
+        C_S[:, 0] = [30, 60, 0, 28]
+        C_F[3, :] = 28
+        C_S[3, :] = 28
+        pfr = enz.packed_PFR({'C_F': C_F, 'C_S': C_S}, params, coords)
+        out[f'pfr{nx}_y0'] = flat_y0(pfr)
+        order = ('delta_x', 'epsilon', 'u', 'rho_B', 'Vf_Ks', 'R_AS', 'R_AW', 'K_eq', 'R_Es')
+        out[f'pfr{nx}_par_scalar'] = np.array([params[k] for k in order], dtype=np.float64)
+        out[f'pfr{nx}_kL_a'], out[f'pfr{nx}_D_ax'] = params['kL_a'], params['D_ax']
+        pick = [0, 123, 456, 899]
+        ys, nf = [], []
+        t = time.time()
+        for i in pick:
+            for j, k in enumerate(names):
+                pfr.parameters[k] = samples[i, j]
+            r = pfr.sim(8000)
+            ys.append(r['y'][:, ::100])                              # stride-100 subset of the 8001-point grid
+            nf.append(r['nfev'])
+        print(f'PFR nx={nx}: {len(pick)} draws in {time.time() - t:.1f}s, nfev={nf}')
+        out[f'pfr{nx}_pick'], out[f'pfr{nx}_y'], out[f'pfr{nx}_nfev'] = np.array(pick), np.stack(ys), np.array(nf)
+    save('ode.npz', **out)
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_loglik():
+    rng = np.random.default_rng(7)
+    out = {}
+    ymodel = rng.gamma(2.0, 200.0, size=(13, 4))
+    ydata = rng.poisson(ymodel).astype(np.float64) / 7
+    out['ymodel'], out['ydata'] = ymodel, ydata
+    out['poisson'] = np.array(objf.ll_poisson(ymodel, ydata))
+    out['negbin_vec'] = np.array(objf.ll_negative_binomial(ymodel, ydata, 4 * [0.03]))
+    out['negbin_scalar'] = np.array(objf.ll_negative_binomial(ymodel, ydata, 0.07))
+    sig_col = [3.0, 10.0, 25.0, 7.5]
+    sig_full = rng.uniform(1, 30, size=(13, 4))
+    out['sigma_col'], out['sigma_full'] = np.array(sig_col), sig_full
+    out['normal_scalar'] = np.array(objf.ll_normal(ymodel, ydata, 12.0))
+    out['normal_col'] = np.array(objf.ll_normal(ymodel, ydata, sig_col))
+    out['normal_full'] = np.array(objf.ll_normal(ymodel, ydata, sig_full))
+    out['lognormal_scalar'] = np.array(objf.ll_lognormal(ymodel, ydata, 0.4))
+    out['lognormal_col'] = np.array(objf.ll_lognormal(ymodel, ydata, [0.2, 0.3, 0.4, 0.5]))
+    # one-column data (the `not additional_axes_data` branch, objective_functions.py:256-269)
+    ym1 = rng.gamma(3.0, 50.0, size=(20, 1))
+    yd1 = rng.poisson(ym1).astype(np.float64)
+    out['ymodel1'], out['ydata1'] = ym1, yd1
+    out['poisson1'] = np.array(objf.ll_poisson(ym1, yd1))
+    out['negbin1'] = np.array(objf.ll_negative_binomial(ym1, yd1, 0.05))
+    out['normal1'] = np.array(objf.ll_normal(ym1, yd1, 4.0))
+    # uniform prior (objective_functions.py:343-367)
+    out['prior_inside'] = np.array(objf.log_prior_uniform(0.5, bounds=(0, 1)))
+    out['prior_outside'] = np.array(objf.log_prior_uniform(1.5, bounds=(0, 1)))
+    save('loglik.npz', **out)
+
+
+if __name__ == '__main__':
+    what = sys.argv[1:] or ['jump_single', 'ssa', 'jump_ensemble', 'schedule', 'ode', 'loglik']
+    for w in what:
+        globals()['gen_' + w]()

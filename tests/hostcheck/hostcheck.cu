@@ -1,0 +1,82 @@
+// TEST-ONLY harness: runs the __host__ __device__ trajectory code of pysodm_b200/csrc on the CPU.
+//
+// The build container has no GPU; this library lets the CPU test-suite check the STATISTICS of the
+// very code the kernels execute (binomial sampler, tau-leap / SSA steppers, model functors) against
+// the oracle and the reference-generated golden ensembles before any GPU time is spent.  It is not
+// part of the product: pysodm_b200 never loads it and has no CPU fallback.
+//
+// Same argument structs as include/sodm.h, but every "(device)" pointer is a HOST pointer here.
+#include <cstring>
+#include <vector>
+#include "../../pysodm_b200/csrc/jump_setup.cuh"
+
+using namespace sodm;
+
+template <class M, typename OutT>
+static void run_host(const JumpLaunch& L, int method, bool aligned) {
+    std::vector<float> table((size_t)L.n_tdpf_values * M::TDPF_COUNT + 1);
+    for (size_t e = 0; e + 1 < table.size(); ++e) table[e] = (float)L.tdpf_table[e];
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < L.n_traj; ++i) {
+        int wn[M::NDRAW];
+        float wp[M::NDRAW];
+        WorkList w{wn, wp, 1};
+        if (method == SODM_JUMP_TAU_LEAP) {
+            if (aligned) tau_leap_trajectory<M, OutT, true>(L, i, table.data(), w);
+            else         tau_leap_trajectory<M, OutT, false>(L, i, table.data(), w);
+        } else {
+            ssa_trajectory<M, OutT>(L, i);
+        }
+    }
+}
+
+template <class M>
+static int run_host_dtype(const JumpLaunch& L, int method, bool aligned, int dtype) {
+    switch (dtype) {
+        case SODM_I32: run_host<M, int32_t>(L, method, aligned); return SODM_OK;
+        case SODM_F32: run_host<M, float>(L, method, aligned); return SODM_OK;
+        case SODM_F64: run_host<M, double>(L, method, aligned); return SODM_OK;
+    }
+    return SODM_EINVAL;
+}
+
+extern "C" int hc_jump_run(const sodm_jump_args* a) {
+    JumpLaunch L;
+    bool aligned = false;
+    const int rc = build_jump_launch(a, L, aligned);
+    if (rc != SODM_OK) return rc;
+    switch (a->model) {
+        case MODEL_SIR_JUMP:       return run_host_dtype<SirJump>(L, a->method, aligned, a->out_dtype);
+        case MODEL_SIR_SI_JUMP:    return run_host_dtype<SirSiJump>(L, a->method, aligned, a->out_dtype);
+        case MODEL_INFLUENZA_JUMP: return run_host_dtype<InfluenzaJump>(L, a->method, aligned, a->out_dtype);
+    }
+    return SODM_EMODEL;
+}
+
+// `count` variates of Bin(n, p) from the stream (seed, traj); attempts[0] receives the number of tries.
+extern "C" void hc_binomial(uint64_t seed, uint64_t traj, int32_t n, float p, int64_t count, int32_t* out,
+                            int64_t* attempts) {
+    PhiloxWords rng;
+    rng.init(seed, traj);
+    int64_t tries = 0;
+    for (int64_t c = 0; c < count; ++c) {
+        int k = 0;
+        do { ++tries; } while (!binomial_try(rng, n, p, k));
+        out[c] = k;
+    }
+    if (attempts) attempts[0] = tries;
+}
+
+extern "C" void hc_philox(uint64_t seed, uint64_t traj, uint32_t purpose, int64_t n_blocks, uint32_t* out) {
+    Philox4x32 g;
+    g.init(seed, traj, purpose);
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        uint32_t w[4];
+        g.next4(w);
+        std::memcpy(out + 4 * b, w, sizeof(w));
+    }
+}
+
+extern "C" double hc_binomial_log_ratio(double n, double p, double k) {
+    return binomial_log_ratio(n, p, floor((n + 1.0) * p), k);
+}

@@ -1,0 +1,104 @@
+"""Loader for the TEST-ONLY CPU harness (tests/hostcheck): the kernels' __host__ __device__ code run on the CPU.
+
+Used by the `-m "not gpu"` tests to check sampler / stepper statistics without a GPU.  Never imported by
+pysodm_b200.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from pysodm_b200 import _ffi, build  # noqa: E402
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = build.build_hostcheck()
+        _lib = C.CDLL(path)
+        _lib.hc_jump_run.restype = C.c_int
+        _lib.hc_jump_run.argtypes = [C.POINTER(_ffi.JumpArgs)]
+        _lib.hc_binomial.restype = None
+        _lib.hc_binomial.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_float, C.c_int64, C.c_void_p, C.c_void_p]
+        _lib.hc_philox.restype = None
+        _lib.hc_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int64, C.c_void_p]
+        _lib.hc_binomial_log_ratio.restype = C.c_double
+        _lib.hc_binomial_log_ratio.argtypes = [C.c_double, C.c_double, C.c_double]
+        _lib.sodm_model_id.restype = C.c_int
+        _lib.sodm_model_id.argtypes = [C.c_char_p]
+        _lib.sodm_model_info_get.restype = C.c_int
+        _lib.sodm_model_info_get.argtypes = [C.c_int, C.c_int, C.POINTER(_ffi.ModelInfo)]
+        _lib.sodm_last_error.restype = C.c_char_p
+    return _lib
+
+
+def binomial(n, p, count, seed=1, traj=0):
+    out = np.empty(count, dtype=np.int32)
+    attempts = np.zeros(1, dtype=np.int64)
+    lib().hc_binomial(seed, traj, int(n), float(p), count, out.ctypes.data, attempts.ctypes.data)
+    return out, int(attempts[0])
+
+
+def philox(seed, traj, purpose, n_blocks):
+    out = np.empty(4 * n_blocks, dtype=np.uint32)
+    lib().hc_philox(seed, traj, purpose, n_blocks, out.ctypes.data)
+    return out.reshape(n_blocks, 4)
+
+
+_DT = {np.dtype(np.int32): _ffi.I32, np.dtype(np.float32): _ffi.F32, np.dtype(np.float64): _ffi.F64}
+
+
+def jump_run(model, y0, par, n_traj, t0, n_out, tau=0.5, method="tau_leap", var=None, tdpf=None,
+             compat=_ffi.COMPAT_REFERENCE, seed=1718, traj_id0=0, out_dtype=np.float64, state_sel=None,
+             max_events=0):
+    """Host run of the jump stepper.  Returns (out[n_rows, n_out, n_traj], status[n_traj]).
+
+    y0: [n_state] (broadcast) or [n_state, n_traj];  par: [n_param];  var: {flat_param_index: values[n_traj]};
+    tdpf: (table[n_values, tdpf_count], step_index[n_steps])."""
+    L = lib()
+    mid = L.sodm_model_id(model.encode())
+    assert mid >= 0, L.sodm_last_error()
+    info = _ffi.ModelInfo()
+    assert L.sodm_model_info_get(mid, 0, C.byref(info)) == 0
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    assert par.size == info.n_param, (par.size, info.n_param)
+    n_rows = info.n_state if state_sel is None else len(state_sel)
+    out = np.full((n_rows, n_out, n_traj), np.nan if np.dtype(out_dtype).kind == "f" else -1, dtype=out_dtype)
+    status = np.zeros(n_traj, dtype=np.int32)
+    a = _ffi.JumpArgs()
+    a.model, a.method = mid, (_ffi.JUMP_TAU_LEAP if method == "tau_leap" else _ffi.JUMP_SSA)
+    a.compat, a.out_dtype = compat, _DT[np.dtype(out_dtype)]
+    a.n_traj, a.traj_id0, a.seed = n_traj, traj_id0, seed
+    a.ld_in, a.ld_out = n_traj, n_traj
+    a.y0, a.y0_broadcast = y0.ctypes.data, int(y0.ndim == 1)
+    a.par = par.ctypes.data
+    keep = [y0, par, out, status]
+    if var:
+        idx = np.array(sorted(var), dtype=np.int32)
+        vals = np.ascontiguousarray(np.stack([np.asarray(var[i], dtype=np.float64) for i in sorted(var)]))
+        a.n_var, a.var_index, a.var_values = len(idx), idx.ctypes.data, vals.ctypes.data
+        keep += [idx, vals]
+    if tdpf is not None:
+        table = np.ascontiguousarray(np.asarray(tdpf[0], dtype=np.float64).reshape(len(tdpf[0]), -1))
+        index = np.ascontiguousarray(tdpf[1], dtype=np.int32)
+        a.tdpf_table, a.tdpf_index = table.ctypes.data, index.ctypes.data
+        a.n_tdpf_values, a.n_tdpf_index = table.shape[0], index.size
+        keep += [table, index]
+    a.t0, a.n_out, a.tau = float(t0), int(n_out), float(tau)
+    if state_sel is not None:
+        sel = np.ascontiguousarray(state_sel, dtype=np.int32)
+        a.n_sel, a.state_sel = sel.size, sel.ctypes.data
+        keep.append(sel)
+    a.out, a.status, a.max_events = out.ctypes.data, status.ctypes.data, max_events
+    rc = L.hc_jump_run(C.byref(a))
+    if rc != 0:
+        raise _ffi.SodmError(rc, L.sodm_last_error().decode())
+    return out, status
