@@ -195,7 +195,7 @@ typedef struct sodm_loglik_args {
     int32_t  n_t;               /* data time points */
     int32_t  arg_mode;          /* SODM_ARG_* */
     const double*  t_data;      /* (device) [n_t] data times in simulation time units (linear interpolation, :254) */
-    const double*  ydata;       /* (device) [n_t][n_col]; NaN entries are skipped */
+    const double*  ydata;       /* (device) [n_t][n_col] row-major, time first (:259, :276-278) */
     const double*  ll_arg;      /* (device) sigma / alpha per arg_mode */
     double   weight;            /* dataset weight (:266-269) */
     double*  lp;                /* (device) [n_traj] log-probability, ACCUMULATED (+=) */

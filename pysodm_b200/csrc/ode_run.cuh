@@ -1,0 +1,394 @@
+// Per-trajectory ODE integrators.
+//
+// `rk45_run` follows scipy.integrate.solve_ivp(method='RK45') STEP FOR STEP, because that is the call the
+// reference makes (/root/reference/src/pySODM/models/base.py:855) and the parity bar (rtol 1e-6 against
+// it at the default rtol=1e-4) can only be met by reproducing its step sequence.  The
+// published algorithm restated here (scipy 1.18, integrate/_ivp/{rk,common,ivp,base}.py):
+//   * Dormand-Prince 5(4) pair with FSAL, local extrapolation (the 5th-order solution is propagated);
+//   * error norm  = RMS( h * K^T E / (atol + max(|y|,|y_new|) * rtol) );
+//   * accept if norm < 1, next h_abs *= min(10, 0.9 * norm^(-1/5)) (capped at 1 after a rejection in the
+//     same step; 10 if norm == 0); reject: h_abs *= max(0.2, 0.9 * norm^(-1/5));
+//   * h_abs clamped from below by min_step = 10 * ulp(t); the last step is clipped to t_bound;
+//   * first step from Hairer's heuristic (`select_initial_step`, order 4);
+//   * output at `t_eval` from the quartic dense-output polynomial of the step that covers it
+//     (Shampine 1986; `RkDenseOutput`: y_old + h * Q p,  Q = K^T P,  p = [x, x^2, x^3, x^4]).
+// `euler_run` follows `ODE._solve_discrete` (base.py:800-819): explicit Euler + np.interp onto the grid.
+// `rk4_run` is an extension (classical RK4, same output rule); the reference has no RK4.
+//
+// The integrators are written against a small "system" concept so that the same controller code
+// serves a thread-per-trajectory layout (whole state in one thread's registers) and the
+// warp-per-trajectory layout of the packed-bed reactor (one axial node per lane): NL local elements,
+// rhs(), reduce() (sum over the lanes of the trajectory), global_index(), active().
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include "jump_models.cuh"   // status bits
+#include "ode_models.cuh"
+
+namespace sodm {
+
+constexpr int ODE_MAX_PARAM = 32;
+
+struct OdeLaunch {
+    int64_t n_traj, ld_in, ld_out;
+    const double* y0;
+    int32_t y0_bcast;
+    int32_t nx;                    // packed_pfr_ode
+    double par[ODE_MAX_PARAM];
+    int8_t var_row[ODE_MAX_PARAM];
+    const double* var_values;
+    double t0;
+    int32_t n_out, out_stride, out_last_only, n_kept;
+    double rtol, atol, tau;
+    void* out;
+    int32_t* nfev;
+    int32_t* status;
+    int64_t max_steps;
+    int32_t n_steps_fixed;         // Euler / RK4: number of steps (host replays the FP64 accumulation of t)
+};
+
+// ---- Dormand-Prince coefficients (scipy rk.py RK45; Dormand & Prince 1980, Shampine 1986) ------------
+#define DP_A21 (1.0 / 5.0)
+#define DP_A31 (3.0 / 40.0)
+#define DP_A32 (9.0 / 40.0)
+#define DP_A41 (44.0 / 45.0)
+#define DP_A42 (-56.0 / 15.0)
+#define DP_A43 (32.0 / 9.0)
+#define DP_A51 (19372.0 / 6561.0)
+#define DP_A52 (-25360.0 / 2187.0)
+#define DP_A53 (64448.0 / 6561.0)
+#define DP_A54 (-212.0 / 729.0)
+#define DP_A61 (9017.0 / 3168.0)
+#define DP_A62 (-355.0 / 33.0)
+#define DP_A63 (46732.0 / 5247.0)
+#define DP_A64 (49.0 / 176.0)
+#define DP_A65 (-5103.0 / 18656.0)
+#define DP_B1 (35.0 / 384.0)
+#define DP_B3 (500.0 / 1113.0)
+#define DP_B4 (125.0 / 192.0)
+#define DP_B5 (-2187.0 / 6784.0)
+#define DP_B6 (11.0 / 84.0)
+#define DP_E1 (-71.0 / 57600.0)
+#define DP_E3 (71.0 / 16695.0)
+#define DP_E4 (-71.0 / 1920.0)
+#define DP_E5 (17253.0 / 339200.0)
+#define DP_E6 (-22.0 / 525.0)
+#define DP_E7 (1.0 / 40.0)
+
+// kept grid index of grid point g, or -1
+__host__ __device__ __forceinline__ int kept_index(const OdeLaunch& L, int g) {
+    if (L.out_last_only) return g == L.n_out - 1 ? 0 : -1;
+    return (g % L.out_stride) == 0 ? g / L.out_stride : -1;
+}
+
+template <class Sys>
+__host__ __device__ __forceinline__ double rms_scaled(Sys& sys, const double* v, const double* scale) {
+    double acc = 0.0;
+#pragma unroll
+    for (int e = 0; e < Sys::NL; ++e) {
+        const double r = sys.active(e) ? v[e] / scale[e] : 0.0;
+        acc += r * r;
+    }
+    return sqrt(sys.reduce(acc)) / sqrt((double)sys.n_total());
+}
+
+template <class Sys, typename OutT>
+__host__ __device__ __forceinline__ void store_grid(Sys& sys, const OdeLaunch& L, int64_t i, int kj, const double* v) {
+    OutT* out = (OutT*)L.out + i;
+#pragma unroll
+    for (int e = 0; e < Sys::NL; ++e)
+        if (sys.active(e)) out[((int64_t)sys.global_index(e) * L.n_kept + kj) * L.ld_out] = (OutT)v[e];
+}
+
+template <class Sys, typename OutT>
+__host__ __device__ __forceinline__ void fill_nan_from(Sys& sys, const OdeLaunch& L, int64_t i, int g) {
+    double v[Sys::NL];
+#pragma unroll
+    for (int e = 0; e < Sys::NL; ++e) v[e] = NAN;
+    for (; g < L.n_out; ++g) {
+        const int kj = kept_index(L, g);
+        if (kj >= 0) store_grid<Sys, OutT>(sys, L, i, kj, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scipy-faithful RK45
+// ------------------------------------------------------------------------------------------------
+template <class Sys, typename OutT>
+__host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, int64_t i, double* y) {
+    constexpr int NL = Sys::NL;
+    double K1[NL], K2[NL], K3[NL], K4[NL], K5[NL], K6[NL], K7[NL];   // K1 = f(t, y) (FSAL) ... K7 = f(t+h, y_new)
+    double ytmp[NL], ynew[NL], scale[NL];
+    const double rtol = fmax(L.rtol, 100.0 * DBL_EPSILON);            // validate_tol
+    const double atol = L.atol;
+    const double t_bound = L.t0 + (double)(L.n_out - 1);
+    double t = L.t0;
+    uint32_t st = ST_OK;
+    int nfev = 0;
+    int g = 0;                                                        // next grid point to emit
+
+    sys.rhs(t, y, K1); ++nfev;
+    // ---- select_initial_step -------------------------------------------------------------------
+    double h_abs;
+    {
+        const double interval = fabs(t_bound - t);
+        if (interval == 0.0) {
+            h_abs = 0.0;
+        } else {
+#pragma unroll
+            for (int e = 0; e < NL; ++e) scale[e] = atol + fabs(y[e]) * rtol;
+            const double d0 = rms_scaled(sys, y, scale);
+            const double d1 = rms_scaled(sys, K1, scale);
+            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+            h0 = fmin(h0, interval);
+#pragma unroll
+            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + h0 * K1[e];
+            sys.rhs(t + h0, ytmp, K2); ++nfev;
+#pragma unroll
+            for (int e = 0; e < NL; ++e) K3[e] = K2[e] - K1[e];
+            const double d2 = rms_scaled(sys, K3, scale) / h0;
+            const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 0.2);
+            h_abs = fmin(fmin(100.0 * h0, h1), interval);
+        }
+    }
+    if (t == t_bound) {                                              // zero-length run: only y0 is output
+        const int kj = kept_index(L, 0);
+        if (kj >= 0) store_grid<Sys, OutT>(sys, L, i, kj, y);
+        g = 1;
+    }
+    int64_t steps = 0;
+    while (t < t_bound) {
+        if (steps++ >= L.max_steps) { st |= ST_MAX_STEPS; break; }
+        const double min_step = 10.0 * (nextafter(t, INFINITY) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false, failed = false;
+        double h, t_new;
+        for (;;) {
+            if (h_abs < min_step) { failed = true; break; }
+            h = h_abs;
+            t_new = t + h;
+            if (t_new - t_bound > 0.0) t_new = t_bound;
+            h = t_new - t;
+            h_abs = fabs(h);
+            // ---- rk_step ---------------------------------------------------------------------
+#pragma unroll
+            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A21) * h;
+            sys.rhs(t + (1.0 / 5.0) * h, ytmp, K2);
+#pragma unroll
+            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A31 + K2[e] * DP_A32) * h;
+            sys.rhs(t + (3.0 / 10.0) * h, ytmp, K3);
+#pragma unroll
+            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A41 + K2[e] * DP_A42 + K3[e] * DP_A43) * h;
+            sys.rhs(t + (4.0 / 5.0) * h, ytmp, K4);
+#pragma unroll
+            for (int e = 0; e < NL; ++e)
+                ytmp[e] = y[e] + (K1[e] * DP_A51 + K2[e] * DP_A52 + K3[e] * DP_A53 + K4[e] * DP_A54) * h;
+            sys.rhs(t + (8.0 / 9.0) * h, ytmp, K5);
+#pragma unroll
+            for (int e = 0; e < NL; ++e)
+                ytmp[e] = y[e] + (K1[e] * DP_A61 + K2[e] * DP_A62 + K3[e] * DP_A63 + K4[e] * DP_A64 + K5[e] * DP_A65) * h;
+            sys.rhs(t + h, ytmp, K6);
+#pragma unroll
+            for (int e = 0; e < NL; ++e)
+                ynew[e] = y[e] + h * (K1[e] * DP_B1 + K3[e] * DP_B3 + K4[e] * DP_B4 + K5[e] * DP_B5 + K6[e] * DP_B6);
+            sys.rhs(t + h, ynew, K7);
+            nfev += 6;
+            // ---- error norm --------------------------------------------------------------------
+            double acc = 0.0;
+#pragma unroll
+            for (int e = 0; e < NL; ++e) {
+                const double sc = atol + fmax(fabs(y[e]), fabs(ynew[e])) * rtol;
+                const double err = (K1[e] * DP_E1 + K3[e] * DP_E3 + K4[e] * DP_E4 + K5[e] * DP_E5 + K6[e] * DP_E6 +
+                                    K7[e] * DP_E7) * h;
+                const double r = sys.active(e) ? err / sc : 0.0;
+                acc += r * r;
+            }
+            const double error_norm = sqrt(sys.reduce(acc)) / sqrt((double)sys.n_total());
+            if (error_norm < 1.0) {
+                double factor = error_norm == 0.0 ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -0.2));
+                if (rejected) factor = fmin(1.0, factor);
+                h_abs *= factor;
+                break;
+            }
+            if (!(error_norm == error_norm)) { st |= ST_NONFINITE; failed = true; break; }
+            h_abs *= fmax(0.2, 0.9 * pow(error_norm, -0.2));
+            rejected = true;
+        }
+        if (failed) { st |= ST_STEP_TOO_SMALL; break; }
+        // ---- dense output for the grid points in (t_old, t_new] (and t0 itself on the first step) ------
+        while (g < L.n_out && L.t0 + (double)g <= t_new) {
+            const int kj = kept_index(L, g);
+            if (kj >= 0) {
+                const double x = (L.t0 + (double)g - t) / h;
+                const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+#pragma unroll
+                for (int e = 0; e < NL; ++e) {
+                    const double q0 = K1[e];                        // P[0] = [1, ...] and P[s>0][0] = 0
+                    const double q1 = K1[e] * (-8048581381.0 / 2820520608.0) + K3[e] * (131558114200.0 / 32700410799.0) +
+                                      K4[e] * (-1754552775.0 / 470086768.0) + K5[e] * (127303824393.0 / 49829197408.0) +
+                                      K6[e] * (-282668133.0 / 205662961.0) + K7[e] * (40617522.0 / 29380423.0);
+                    const double q2 = K1[e] * (8663915743.0 / 2820520608.0) + K3[e] * (-68118460800.0 / 10900136933.0) +
+                                      K4[e] * (14199869525.0 / 1410260304.0) + K5[e] * (-318862633887.0 / 49829197408.0) +
+                                      K6[e] * (2019193451.0 / 616988883.0) + K7[e] * (-110615467.0 / 29380423.0);
+                    const double q3 = K1[e] * (-12715105075.0 / 11282082432.0) + K3[e] * (87487479700.0 / 32700410799.0) +
+                                      K4[e] * (-10690763975.0 / 1880347072.0) + K5[e] * (701980252875.0 / 199316789632.0) +
+                                      K6[e] * (-1453857185.0 / 822651844.0) + K7[e] * (69997945.0 / 29380423.0);
+                    ytmp[e] = y[e] + h * (q0 * x + q1 * x2 + q2 * x3 + q3 * x4);
+                }
+                store_grid<Sys, OutT>(sys, L, i, kj, ytmp);
+            }
+            ++g;
+        }
+#pragma unroll
+        for (int e = 0; e < NL; ++e) { y[e] = ynew[e]; K1[e] = K7[e]; }
+        t = t_new;
+    }
+    if (g < L.n_out) fill_nan_from<Sys, OutT>(sys, L, i, g);
+    if (sys.leader()) {
+        if (L.nfev) L.nfev[i] = nfev;
+        if (L.status) L.status[i] = (int32_t)st;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fixed-step schemes + np.interp onto the grid (base.py:800-819)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ double mul_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b;
+    return r;
+#endif
+}
+__host__ __device__ __forceinline__ double add_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b;
+    return r;
+#endif
+}
+
+template <class Sys, typename OutT, bool RK4>
+__host__ __device__ __forceinline__ void fixed_step_run(Sys& sys, const OdeLaunch& L, int64_t i, double* y) {
+    constexpr int NL = Sys::NL;
+    double y_old[NL], k1[NL], k2[NL], k3[NL], k4[NL], ytmp[NL];
+    const double tau = L.tau;
+    double t = L.t0;
+    int g = 1, nfev = 0;
+    uint32_t st = ST_OK;
+    {
+        const int kj = kept_index(L, 0);
+        if (kj >= 0) store_grid<Sys, OutT>(sys, L, i, kj, y);
+    }
+    for (int k = 0; k < L.n_steps_fixed; ++k) {
+#pragma unroll
+        for (int e = 0; e < NL; ++e) y_old[e] = y[e];
+        sys.rhs(t, y, k1); ++nfev;
+        if (!RK4) {
+#pragma unroll
+            for (int e = 0; e < NL; ++e) y[e] = add_rn(y[e], mul_rn(k1[e], tau));     // y_prev + fun(t, y)*tau
+        } else {
+#pragma unroll
+            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + 0.5 * tau * k1[e];
+            sys.rhs(t + 0.5 * tau, ytmp, k2);
+#pragma unroll
+            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + 0.5 * tau * k2[e];
+            sys.rhs(t + 0.5 * tau, ytmp, k3);
+#pragma unroll
+            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + tau * k3[e];
+            sys.rhs(t + tau, ytmp, k4);
+            nfev += 3;
+#pragma unroll
+            for (int e = 0; e < NL; ++e) y[e] = y[e] + (tau / 6.0) * (k1[e] + 2.0 * k2[e] + 2.0 * k3[e] + k4[e]);
+        }
+        const double t_new = t + tau;
+        while (g < L.n_out && L.t0 + (double)g <= t_new) {
+            const int kj = kept_index(L, g);
+            if (kj >= 0) {
+                const double tg = L.t0 + (double)g;
+#pragma unroll
+                for (int e = 0; e < NL; ++e) {
+                    if (tg == t_new) ytmp[e] = y[e];
+                    else {   // np.interp: slope*(x - xp[j]) + fp[j]
+                        const double slope = (y[e] - y_old[e]) / (t_new - t);
+                        ytmp[e] = add_rn(mul_rn(slope, tg - t), y_old[e]);
+                    }
+                }
+                store_grid<Sys, OutT>(sys, L, i, kj, ytmp);
+            }
+            ++g;
+        }
+        t = t_new;
+    }
+    if (sys.leader()) {
+        if (L.nfev) L.nfev[i] = nfev;
+        if (L.status) L.status[i] = (int32_t)st;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// systems
+// ------------------------------------------------------------------------------------------------
+template <class M>
+struct ThreadSystem {                       // whole state in one thread
+    static constexpr int NL = M::N;
+    const double* par;
+    __host__ __device__ __forceinline__ int n_total() const { return M::N; }
+    __host__ __device__ __forceinline__ bool active(int) const { return true; }
+    __host__ __device__ __forceinline__ bool leader() const { return true; }
+    __host__ __device__ __forceinline__ int global_index(int e) const { return e; }
+    __host__ __device__ __forceinline__ double reduce(double x) const { return x; }
+    __host__ __device__ __forceinline__ void rhs(double t, const double* y, double* dy) const { M::rhs(t, y, par, dy); }
+};
+
+// packed-bed reactor with the whole 8*NX state in one thread (CPU harness only: reference for the
+// warp-per-trajectory device layout in sodm_ode.cu)
+template <int NX>
+struct PfrThreadSystem {
+    static constexpr int NL = 8 * NX;
+    const double* par;
+    __host__ __device__ __forceinline__ int n_total() const { return NL; }
+    __host__ __device__ __forceinline__ bool active(int) const { return true; }
+    __host__ __device__ __forceinline__ bool leader() const { return true; }
+    __host__ __device__ __forceinline__ int global_index(int e) const { return e; }
+    __host__ __device__ __forceinline__ double reduce(double x) const { return x; }
+    __host__ __device__ void rhs(double, const double* y, double* dy) const {
+        for (int j = 0; j < NX; ++j) {
+            double cl[4], cm[4], cr[4], cs[4], dcf[4], dcs[4];
+            for (int s = 0; s < 4; ++s) {
+                cm[s] = y[s * NX + j];
+                cl[s] = j > 0 ? y[s * NX + j - 1] : 0.0;
+                cr[s] = j < NX - 1 ? y[s * NX + j + 1] : 0.0;
+                cs[s] = y[4 * NX + s * NX + j];
+            }
+            PfrNode::rhs(par, j == 0, j == NX - 1, cl, cm, cr, cs, dcf, dcs);
+            for (int s = 0; s < 4; ++s) { dy[s * NX + j] = dcf[s]; dy[4 * NX + s * NX + j] = dcs[s]; }
+        }
+    }
+};
+
+template <int NPAR_>
+__host__ __device__ __forceinline__ void load_ode_params(const OdeLaunch& L, int64_t i, double* par) {
+#pragma unroll
+    for (int e = 0; e < NPAR_; ++e) {
+        par[e] = L.par[e];
+        if (L.var_row[e] >= 0) par[e] = L.var_values[(int64_t)L.var_row[e] * L.ld_in + i];
+    }
+}
+
+template <class M, typename OutT>
+__host__ __device__ __forceinline__ void ode_thread_trajectory(const OdeLaunch& L, int method, int64_t i) {
+    double par[M::NPAR], y[M::N];
+    load_ode_params<M::NPAR>(L, i, par);
+#pragma unroll
+    for (int s = 0; s < M::N; ++s) y[s] = L.y0_bcast ? L.y0[s] : L.y0[(int64_t)s * L.ld_in + i];
+    ThreadSystem<M> sys{par};
+    if (method == SODM_ODE_RK45) rk45_run<ThreadSystem<M>, OutT>(sys, L, i, y);
+    else if (method == SODM_ODE_EULER) fixed_step_run<ThreadSystem<M>, OutT, false>(sys, L, i, y);
+    else fixed_step_run<ThreadSystem<M>, OutT, true>(sys, L, i, y);
+}
+
+}  // namespace sodm

@@ -80,3 +80,47 @@ extern "C" void hc_philox(uint64_t seed, uint64_t traj, uint32_t purpose, int64_
 extern "C" double hc_binomial_log_ratio(double n, double p, double k) {
     return binomial_log_ratio(n, p, floor((n + 1.0) * p), k);
 }
+
+// ---------------------------------------------------------------------------------------------------
+// ODE integrators on the CPU (same rk45_run / fixed_step_run code as the kernels)
+// ---------------------------------------------------------------------------------------------------
+#include "../../pysodm_b200/csrc/ode_setup.cuh"
+
+template <class M, typename OutT>
+static void ode_host(const OdeLaunch& L, int method) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < L.n_traj; ++i) ode_thread_trajectory<M, OutT>(L, method, i);
+}
+
+template <int NX, typename OutT>
+static void pfr_host(const OdeLaunch& L, int method) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < L.n_traj; ++i) {
+        double par[PfrNode::NPAR];
+        load_ode_params<PfrNode::NPAR>(L, i, par);
+        static thread_local double y[8 * NX];
+        for (int s = 0; s < 8 * NX; ++s) y[s] = L.y0_bcast ? L.y0[s] : L.y0[(int64_t)s * L.ld_in + i];
+        PfrThreadSystem<NX> sys{par};
+        if (method == SODM_ODE_RK45) rk45_run<PfrThreadSystem<NX>, OutT>(sys, L, i, y);
+        else if (method == SODM_ODE_EULER) fixed_step_run<PfrThreadSystem<NX>, OutT, false>(sys, L, i, y);
+        else fixed_step_run<PfrThreadSystem<NX>, OutT, true>(sys, L, i, y);
+    }
+}
+
+extern "C" int hc_ode_run(const sodm_ode_args* a) {
+    OdeLaunch L;
+    sodm_model_info info;
+    const int rc = build_ode_launch(a, L, info);
+    if (rc != SODM_OK) return rc;
+    if (a->out_dtype != SODM_F64) return SODM_EUNSUPPORTED;
+    switch (a->model) {
+        case MODEL_SIR_ODE:      ode_host<SirOde, double>(L, a->method); return SODM_OK;
+        case MODEL_SIR_RATE_ODE: ode_host<SirRateOde, double>(L, a->method); return SODM_OK;
+        case MODEL_SIR_SI_ODE:   ode_host<SirSiOde, double>(L, a->method); return SODM_OK;
+        case MODEL_PPBB_ODE:     ode_host<PpbbOde, double>(L, a->method); return SODM_OK;
+        case MODEL_PACKED_PFR_ODE:
+            if (L.nx == 25) { pfr_host<25, double>(L, a->method); return SODM_OK; }
+            return SODM_EUNSUPPORTED;
+    }
+    return SODM_EMODEL;
+}

@@ -102,3 +102,44 @@ def jump_run(model, y0, par, n_traj, t0, n_out, tau=0.5, method="tau_leap", var=
     if rc != 0:
         raise _ffi.SodmError(rc, L.sodm_last_error().decode())
     return out, status
+
+
+def ode_run(model, y0, par, n_traj, t0, n_out, method="RK45", rtol=1e-4, atol=1e-6, tau=0.0, var=None,
+            model_arg=0, out_stride=1, out_last_only=False):
+    """Host run of the ODE integrators.  Returns (out[n_state, n_kept, n_traj], nfev[n_traj], status[n_traj])."""
+    L = lib()
+    if not hasattr(L, "_ode_ready"):
+        L.hc_ode_run.restype = C.c_int
+        L.hc_ode_run.argtypes = [C.POINTER(_ffi.OdeArgs)]
+        L._ode_ready = True
+    mid = L.sodm_model_id(model.encode())
+    assert mid >= 0, L.sodm_last_error()
+    info = _ffi.ModelInfo()
+    assert L.sodm_model_info_get(mid, model_arg, C.byref(info)) == 0, L.sodm_last_error()
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    assert par.size == info.n_param, (par.size, info.n_param)
+    n_kept = 1 if out_last_only else (n_out - 1) // out_stride + 1
+    out = np.full((info.n_state, n_kept, n_traj), np.nan)
+    nfev = np.zeros(n_traj, dtype=np.int32)
+    status = np.zeros(n_traj, dtype=np.int32)
+    a = _ffi.OdeArgs()
+    a.model, a.model_arg = mid, model_arg
+    a.method = {"RK45": _ffi.ODE_RK45, "euler": _ffi.ODE_EULER, "RK4": _ffi.ODE_RK4}[method]
+    a.out_dtype = _ffi.F64
+    a.n_traj, a.ld_in, a.ld_out = n_traj, n_traj, n_traj
+    a.y0, a.y0_broadcast = y0.ctypes.data, int(y0.ndim == 1)
+    a.par = par.ctypes.data
+    keep = [y0, par]
+    if var:
+        idx = np.array(sorted(var), dtype=np.int32)
+        vals = np.ascontiguousarray(np.stack([np.asarray(var[i], dtype=np.float64) for i in sorted(var)]))
+        a.n_var, a.var_index, a.var_values = len(idx), idx.ctypes.data, vals.ctypes.data
+        keep += [idx, vals]
+    a.t0, a.n_out, a.out_stride, a.out_last_only = float(t0), int(n_out), int(out_stride), int(out_last_only)
+    a.rtol, a.atol, a.tau = rtol, atol, tau
+    a.out, a.nfev, a.status = out.ctypes.data, nfev.ctypes.data, status.ctypes.data
+    rc = L.hc_ode_run(C.byref(a))
+    if rc != 0:
+        raise _ffi.SodmError(rc, L.sodm_last_error().decode())
+    return out, nfev, status
