@@ -62,8 +62,10 @@ def tau_leap_draw(model, y, rates, tau, stay_quirk=True, binomial=None):
     for name, rate_list in rates.items():
         p = transition_probabilities(rate_list, tau, stay_quirk)
         n = np.array(y[name], np.int64)                       # truncation as base.py:345 (Q2)
-        if n.shape != p.shape[:-1]:
-            n = np.broadcast_to(n, p.shape[:-1]).copy()
+        if n.shape != p.shape[:-1]:                           # batch axes present on only one of the two
+            shape = np.broadcast_shapes(n.shape, p.shape[:-1])
+            n = np.broadcast_to(n, shape).copy()
+            p = np.broadcast_to(p, shape + p.shape[-1:])
         draws = multinomial_by_conditional_binomials(n, p, binomial)
         T[name] = [draws[..., i] for i in range(draws.shape[-1])]
     return T

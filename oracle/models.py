@@ -18,12 +18,11 @@ def _matvec(M, x):
     return np.einsum("...ij,...j->...i", M, x)
 
 
-def _bcast_last(v, like):
-    """Give a per-trajectory scalar `v` (shape `...`) a trailing axis so it multiplies `like` (`..., k`)."""
+def _col(v):
+    """A per-trajectory scalar (shape = batch axes) gets a trailing axis so that it multiplies state
+    vectors of shape batch + (k,); plain scalars (no batch) are returned unchanged."""
     v = np.asarray(v, dtype=np.float64)
-    if like.ndim >= 1 and v.ndim == like.ndim - 1 and v.ndim > 0:
-        return v[..., None]
-    return v
+    return v[..., None] if v.ndim > 0 else v
 
 
 class JumpModelSpec:
@@ -95,8 +94,8 @@ class SIRSIJump(JumpModelSpec):
         N_v = S_v + I_v
         frac_v = I_v / N_v
         return {
-            "S": [alpha * _bcast_last(frac_v, alpha)],
-            "I": [_bcast_last(1 / np.asarray(p["gamma"], dtype=np.float64), N) * np.ones(N.shape)],
+            "S": [alpha * _col(frac_v)],
+            "I": [_col(1 / np.asarray(p["gamma"], dtype=np.float64)) * np.ones(N.shape)],
             "S_v": [np.sum(alpha * (I / N), axis=-1) * np.ones(np.shape(N_v)),
                     (1 / np.asarray(p["beta"], dtype=np.float64)) * np.ones(np.shape(N_v))],
             "I_v": [(1 / np.asarray(p["beta"], dtype=np.float64)) * np.ones(np.shape(N_v))],
@@ -129,13 +128,13 @@ class InfluenzaJump(JumpModelSpec):
         f_ud = p["f_ud"]
         T = S + E + Ip + Iud + Id + R
         ones = np.ones(T.shape)
-        inv_gamma = _bcast_last(1 / np.asarray(p["gamma"], dtype=np.float64), T)
+        inv_gamma = _col(1 / np.asarray(p["gamma"], dtype=np.float64))
         return {
-            "S": [_bcast_last(p["beta"], T) * _matvec(p["N"], (Ip + Iud + 0.22 * Id) / T)],
-            "E": [_bcast_last(1 / np.asarray(p["alpha"], dtype=np.float64), T) * ones],
+            "S": [_col(p["beta"]) * _matvec(p["N"], (Ip + Iud + 0.22 * Id) / T)],
+            "E": [_col(1 / np.asarray(p["alpha"], dtype=np.float64)) * ones],
             "Ip": [f_ud * inv_gamma, (1 - f_ud) * inv_gamma],
-            "Iud": [_bcast_last(1 / np.asarray(p["delta"], dtype=np.float64), T) * ones],
-            "Id": [_bcast_last(1 / np.asarray(p["delta"], dtype=np.float64), T) * ones],
+            "Iud": [_col(1 / np.asarray(p["delta"], dtype=np.float64)) * ones],
+            "Id": [_col(1 / np.asarray(p["delta"], dtype=np.float64)) * ones],
         }
 
     @staticmethod

@@ -250,6 +250,7 @@ __host__ __device__ __forceinline__ void ssa_trajectory(const JumpLaunch& L, int
         }
         t = t_new;
     }
+    while (j < L.n_out) emit_counts<M, OutT>(L, i, j++, y);   // only after an aborted run: hold the last state
     if (L.status) L.status[i] = (int32_t)st;
 }
 

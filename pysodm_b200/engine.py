@@ -1,0 +1,257 @@
+"""Thin device layer: PyTorch owns the buffers and streams, `libsodm.so` does the work.
+
+Every function here takes / returns `torch` CUDA tensors (or NumPy arrays that are copied to the device),
+fills one argument struct of `include/sodm.h` with raw pointers and sizes and calls the C ABI through
+`_ffi`.  Nothing is computed in Python or in torch; there is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _ffi
+
+_TORCH_DT = {torch.int32: _ffi.I32, torch.float32: _ffi.F32, torch.float64: _ffi.F64}
+_NP_TO_TORCH = {np.dtype(np.int32): torch.int32, np.dtype(np.float32): torch.float32,
+                np.dtype(np.float64): torch.float64}
+_initialised = set()
+
+
+def as_torch_dtype(dt):
+    if isinstance(dt, torch.dtype):
+        return dt
+    if isinstance(dt, str):
+        dt = {"i32": np.int32, "int32": np.int32, "f32": np.float32, "float32": np.float32,
+              "f64": np.float64, "float64": np.float64}[dt]
+    return _NP_TO_TORCH[np.dtype(dt)]
+
+
+def device(index=None) -> torch.device:
+    """Select (and, the first time, initialise) a CUDA device.  Raises if there is no GPU."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("pysodm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if index is None:
+        index = torch.cuda.current_device()
+    if index not in _initialised:
+        lib = _ffi.load()
+        _ffi.check(lib.sodm_init(int(index)), lib)
+        _initialised.add(index)
+    torch.cuda.set_device(index)
+    return torch.device("cuda", index)
+
+
+def _dev_f64(x, dev):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+
+
+def _dev_i32(x, dev):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.int32).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.int32)).to(dev)
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)
+
+
+def _pack_var(var, n_traj, dev):
+    """{flat parameter element: values[n_traj]} -> (index[int32 host], values[n_var, n_traj] device)."""
+    if not var:
+        return None, None
+    if isinstance(var, tuple):                      # already packed: (flat element indices, values[n_var, n_traj])
+        idx = np.ascontiguousarray(var[0], dtype=np.int32)
+        vals = _dev_f64(var[1], dev)
+        if vals.shape != (len(idx), n_traj):
+            raise ValueError(f"packed per-trajectory parameters must be [{len(idx)}, {n_traj}], got {tuple(vals.shape)}")
+        return idx, vals
+    keys = sorted(var)
+    rows = []
+    for k in keys:
+        v = _dev_f64(var[k], dev).reshape(-1)
+        if v.numel() != n_traj:
+            raise ValueError(f"per-trajectory parameter element {k}: expected {n_traj} values, got {v.numel()}")
+        rows.append(v)
+    return np.asarray(keys, dtype=np.int32), torch.stack(rows).contiguous()
+
+
+def jump_run(model, y0, par, n_traj, t0, n_out, tau=0.5, method="tau_leap", var=None, tdpf=None,
+             compat=_ffi.COMPAT_REFERENCE, seed=0, traj_id0=0, out_dtype=torch.float64, state_sel=None,
+             out=None, status=None, max_events=0, dev=None, stream=None):
+    """Run n_traj jump-process trajectories (`sodm_jump_run`).
+
+    model: registered functor name.  y0: [n_state] (shared) or [n_state, n_traj].  par: [n_param] host values.
+    var: {flat parameter element: per-trajectory values}.  tdpf: (table[n_values, tdpf_count], step_index[n_steps]).
+    Returns (out[n_rows, n_out, n_traj] device tensor, status[n_traj] int32 device tensor); asynchronous.
+    """
+    dev = dev or device()
+    lib = _ffi.load()
+    mid = _ffi.model_id(model)
+    info = _ffi.model_info(mid)
+    out_dtype = as_torch_dtype(out_dtype)
+    y0_d = _dev_f64(y0, dev)
+    if y0_d.shape[0] != info.n_state or (y0_d.dim() == 2 and y0_d.shape[1] != n_traj):
+        raise ValueError(f"y0 must be [{info.n_state}] or [{info.n_state}, {n_traj}], got {tuple(y0_d.shape)}")
+    par_h = np.ascontiguousarray(par, dtype=np.float64)
+    if par_h.size != info.n_param:
+        raise ValueError(f"{model}: expected {info.n_param} flat parameter values, got {par_h.size}")
+    var_idx, var_vals = _pack_var(var, n_traj, dev)
+    n_rows = info.n_state if state_sel is None else len(state_sel)
+    if out is None:
+        out = torch.empty((n_rows, n_out, n_traj), dtype=out_dtype, device=dev)
+    if status is None:
+        status = torch.zeros(n_traj, dtype=torch.int32, device=dev)
+    a = _ffi.JumpArgs()
+    a.model = mid
+    a.method = {"tau_leap": _ffi.JUMP_TAU_LEAP, "SSA": _ffi.JUMP_SSA}[method]
+    a.compat, a.out_dtype = int(compat), _TORCH_DT[out.dtype]
+    a.n_traj, a.traj_id0, a.seed = int(n_traj), int(traj_id0), int(seed) & 0xFFFFFFFFFFFFFFFF
+    a.ld_in, a.ld_out = int(n_traj), int(out.stride(1))
+    a.y0, a.y0_broadcast = y0_d.data_ptr(), int(y0_d.dim() == 1)
+    a.par = par_h.ctypes.data
+    if var_idx is not None:
+        a.n_var, a.var_index, a.var_values = len(var_idx), var_idx.ctypes.data, var_vals.data_ptr()
+    keep = [y0_d, par_h, var_idx, var_vals]
+    if tdpf is not None:
+        table = tdpf[0] if isinstance(tdpf[0], torch.Tensor) else np.asarray(tdpf[0], dtype=np.float64)
+        table = _dev_f64(table.reshape(len(table), -1), dev)
+        index = _dev_i32(tdpf[1], dev)
+        a.tdpf_table, a.tdpf_index = table.data_ptr(), index.data_ptr()
+        a.n_tdpf_values, a.n_tdpf_index = int(table.shape[0]), int(index.numel())
+        keep += [table, index]
+    a.t0, a.n_out, a.tau = float(t0), int(n_out), float(tau)
+    if state_sel is not None:
+        sel = np.ascontiguousarray(state_sel, dtype=np.int32)
+        a.n_sel, a.state_sel = int(sel.size), sel.ctypes.data
+        keep.append(sel)
+    a.out, a.status, a.max_events = out.data_ptr(), status.data_ptr(), int(max_events)
+    a.stream = _stream_ptr(stream)
+    _ffi.check(lib.sodm_jump_run(C.byref(a)), lib)
+    # device inputs are only read by work already queued on the stream; torch's caching allocator keeps
+    # stream-ordered reuse safe on the current stream, so dropping `keep` here is fine
+    return out, status
+
+
+def ode_run(model, y0, par, n_traj, t0, n_out, method="RK45", rtol=1e-4, atol=1e-6, tau=0.0, var=None,
+            model_arg=0, out_stride=1, out_last_only=False, out_dtype=torch.float64, out=None, dev=None,
+            stream=None, max_steps=0):
+    """Integrate n_traj parameter draws of an ODE model (`sodm_ode_run`).
+
+    Returns (out[n_state, n_kept, n_traj], nfev[n_traj], status[n_traj]) device tensors; asynchronous."""
+    dev = dev or device()
+    lib = _ffi.load()
+    mid = _ffi.model_id(model)
+    info = _ffi.model_info(mid, model_arg)
+    out_dtype = as_torch_dtype(out_dtype)
+    y0_d = _dev_f64(y0, dev)
+    if y0_d.shape[0] != info.n_state or (y0_d.dim() == 2 and y0_d.shape[1] != n_traj):
+        raise ValueError(f"y0 must be [{info.n_state}] or [{info.n_state}, {n_traj}], got {tuple(y0_d.shape)}")
+    par_h = np.ascontiguousarray(par, dtype=np.float64)
+    if par_h.size != info.n_param:
+        raise ValueError(f"{model}: expected {info.n_param} flat parameter values, got {par_h.size}")
+    var_idx, var_vals = _pack_var(var, n_traj, dev)
+    n_kept = int(lib.sodm_ode_n_kept(int(n_out), int(out_stride), int(bool(out_last_only))))
+    if out is None:
+        out = torch.empty((info.n_state, n_kept, n_traj), dtype=out_dtype, device=dev)
+    nfev = torch.zeros(n_traj, dtype=torch.int32, device=dev)
+    status = torch.zeros(n_traj, dtype=torch.int32, device=dev)
+    a = _ffi.OdeArgs()
+    a.model, a.model_arg = mid, int(model_arg)
+    a.method = {"RK45": _ffi.ODE_RK45, "euler": _ffi.ODE_EULER, "RK4": _ffi.ODE_RK4}[method]
+    a.out_dtype = _TORCH_DT[out.dtype]
+    a.n_traj, a.ld_in, a.ld_out = int(n_traj), int(n_traj), int(out.stride(1))
+    a.y0, a.y0_broadcast = y0_d.data_ptr(), int(y0_d.dim() == 1)
+    a.par = par_h.ctypes.data
+    if var_idx is not None:
+        a.n_var, a.var_index, a.var_values = len(var_idx), var_idx.ctypes.data, var_vals.data_ptr()
+    a.t0, a.n_out, a.out_stride, a.out_last_only = float(t0), int(n_out), int(out_stride), int(bool(out_last_only))
+    a.rtol, a.atol, a.tau = float(rtol), float(atol), float(tau or 0.0)
+    a.out, a.nfev, a.status = out.data_ptr(), nfev.data_ptr(), status.data_ptr()
+    a.max_steps = int(max_steps)
+    a.stream = _stream_ptr(stream)
+    _ffi.check(lib.sodm_ode_run(C.byref(a)), lib)
+    return out, nfev, status
+
+
+_LL_KIND = {"poisson": _ffi.LL_POISSON, "normal": _ffi.LL_NORMAL, "lognormal": _ffi.LL_LOGNORMAL,
+            "negative_binomial": _ffi.LL_NEGBIN}
+
+
+def loglik(kind, traj, t0, columns, t_data, ydata, ll_arg=None, weight=1.0, lp=None, status=None, dev=None,
+           stream=None):
+    """Accumulate the log-likelihood of every trajectory against one dataset (`sodm_loglik`).
+
+    traj: device tensor [n_row, n_out, n_traj] (any of int32/float32/float64).
+    columns: list (one entry per data column) of lists of rows of `traj` that are summed into that column.
+    t_data: [n_t] data times in simulation time units.  ydata: [n_t, n_col].
+    ll_arg: None | scalar | [n_col] | [n_t, n_col].  Returns lp[n_traj] (float64 device tensor, accumulated)."""
+    dev = dev or device()
+    lib = _ffi.load()
+    n_row, n_out, n_traj = traj.shape
+    ydata_h = np.ascontiguousarray(ydata, dtype=np.float64)
+    if ydata_h.ndim == 1:
+        ydata_h = ydata_h[:, None]
+    n_t, n_col = ydata_h.shape
+    if len(columns) != n_col:
+        raise ValueError(f"{len(columns)} column definitions for {n_col} data columns")
+    col_ptr = np.zeros(n_col + 1, dtype=np.int32)
+    col_ptr[1:] = np.cumsum([len(c) for c in columns])
+    col_rows = np.asarray([r for c in columns for r in c], dtype=np.int32)
+    if col_rows.size and (col_rows.min() < 0 or col_rows.max() >= n_row):
+        raise ValueError("column row index outside the trajectory tensor")
+    t_data_h = np.ascontiguousarray(t_data, dtype=np.float64)
+    if t_data_h.shape != (n_t,):
+        raise ValueError("t_data must have one entry per data row")
+    a = _ffi.LoglikArgs()
+    a.kind = _LL_KIND[kind]
+    a.traj_dtype, a.n_traj, a.ld = _TORCH_DT[traj.dtype], int(n_traj), int(traj.stride(1))
+    a.traj, a.n_out, a.n_col = traj.data_ptr(), int(n_out), int(n_col)
+    d_ptr, d_rows = _dev_i32(col_ptr, dev), _dev_i32(col_rows, dev)
+    d_t, d_y = _dev_f64(t_data_h, dev), _dev_f64(ydata_h, dev)
+    a.col_ptr, a.col_rows, a.t_data, a.ydata = d_ptr.data_ptr(), d_rows.data_ptr(), d_t.data_ptr(), d_y.data_ptr()
+    a.t0, a.n_t = float(t0), int(n_t)
+    d_arg = None
+    if ll_arg is None:
+        a.arg_mode = _ffi.ARG_NONE
+    else:
+        arg = np.asarray(ll_arg, dtype=np.float64)
+        if arg.ndim == 0 or arg.size == 1 and arg.ndim <= 1 and n_col != 1:
+            a.arg_mode, arg = _ffi.ARG_SCALAR, arg.reshape(1)
+        elif arg.shape == (n_col,):
+            a.arg_mode = _ffi.ARG_COLUMN
+        elif arg.shape == (n_t, n_col):
+            a.arg_mode = _ffi.ARG_FULL
+        else:
+            raise ValueError(f"ll_arg of shape {arg.shape} does not broadcast to data of shape {(n_t, n_col)}")
+        d_arg = _dev_f64(arg, dev)
+        a.ll_arg = d_arg.data_ptr()
+    a.weight = float(weight)
+    if lp is None:
+        lp = torch.zeros(n_traj, dtype=torch.float64, device=dev)
+    if status is None:
+        status = torch.zeros(n_traj, dtype=torch.int32, device=dev)
+    a.lp, a.status = lp.data_ptr(), status.data_ptr()
+    a.stream = _stream_ptr(stream)
+    _ffi.check(lib.sodm_loglik(C.byref(a)), lib)
+    return lp, status
+
+
+def to_draws_major(src, r0, n_dim, dst=None, dst_dtype=torch.float64, dev=None, stream=None):
+    """[row][time][traj] -> [traj][time][n_dim] for the state variable occupying rows r0..r0+n_dim-1
+    (`sodm_to_draws_major`).  `dst` may be a CUDA tensor or a pinned host tensor (written over PCIe)."""
+    dev = dev or device()
+    lib = _ffi.load()
+    n_row, n_t, n_traj = src.shape
+    if dst is None:
+        dst = torch.empty((n_traj, n_t, n_dim), dtype=as_torch_dtype(dst_dtype), device=dev)
+    if not dst.is_contiguous() or dst.numel() != n_traj * n_t * n_dim:
+        raise ValueError("dst must be contiguous with n_traj * n_t * n_dim elements")
+    if not dst.is_cuda and not dst.is_pinned():
+        raise ValueError("dst must be a CUDA tensor or a pinned host tensor")
+    _ffi.check(lib.sodm_to_draws_major(src.data_ptr(), _TORCH_DT[src.dtype], int(src.stride(1)), int(r0), int(n_dim),
+                                       int(n_t), int(n_traj), dst.data_ptr(), _TORCH_DT[dst.dtype],
+                                       _stream_ptr(stream)), lib)
+    return dst

@@ -1,0 +1,118 @@
+"""Statistics of the KERNEL CODE itself, run on the CPU by the test-only harness (tests/hostcheck): the same
+__host__ __device__ sampler / stepper / integrator sources the GPU executes, compiled for the host.  These tests
+let the build container (no GPU) catch a wrong law before GPU time is spent; the `-m gpu` tests repeat the
+comparisons on the device."""
+import numpy as np
+import pytest
+from scipy import stats
+
+import cases
+import hostcheck_util as hc
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors: counter/key all-zero and all-ones)."""
+    out = hc.philox(0, 0, 0, 1)[0]
+    assert [hex(int(x)) for x in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    # generic: distinct trajectories / purposes give distinct, well-mixed streams
+    a, b, c = hc.philox(7, 1, 0, 4096), hc.philox(7, 2, 0, 4096), hc.philox(7, 1, 1, 4096)
+    assert not np.array_equal(a, b) and not np.array_equal(a, c)
+    bits = np.unpackbits(a.view(np.uint8))
+    assert abs(bits.mean() - 0.5) < 5 * 0.5 / np.sqrt(bits.size)
+
+
+@pytest.mark.parametrize("n,p", [(7317774, 1.2e-3), (4292, 0.28), (100, 0.3), (50, 0.5), (30, 0.4), (1000, 0.005),
+                                 (7317774, 1e-7), (81, 0.13), (5, 0.9), (2130556, 0.02), (40, 0.26), (12, 0.97),
+                                 (200000, 0.5), (1, 0.3), (20, 0.5), (1000000, 0.9999)])
+def test_binomial_sampler_is_exact(n, p):
+    """Chi-square goodness of fit against the exact binomial pmf, across the inversion / BTRS / flipped regimes."""
+    x, attempts = hc.binomial(n, p, 300_000, seed=n % 97 + 1)
+    p32 = float(np.float32(p))
+    lo, hi = int(x.min()), int(x.max())
+    assert 0 <= lo and hi <= n
+    ks = np.arange(lo, hi + 1)
+    obs = np.bincount(x - lo, minlength=len(ks)).astype(float)
+    exp = stats.binom.pmf(ks, n, p32) * len(x)
+    big = exp >= 8
+    o = np.append(obs[big], obs[~big].sum())
+    e = np.append(exp[big], len(x) - exp[big].sum())
+    if e[-1] < 4:
+        o, e = o[:-1], e[:-1]
+    if len(o) > 1:
+        chi2 = ((o - e) ** 2 / e).sum()
+        assert stats.chi2.sf(chi2, len(o) - 1) > 1e-4, (n, p)
+    assert attempts / len(x) < 1.6
+
+
+def test_binomial_edge_cases():
+    assert (hc.binomial(0, 0.3, 100)[0] == 0).all()
+    assert (hc.binomial(50, 0.0, 100)[0] == 0).all()
+    assert (hc.binomial(50, 1.0, 100)[0] == 50).all()
+    assert (hc.binomial(50, float("nan"), 10)[0] == -1).all()
+    assert (hc.binomial(50, 1.5, 10)[0] == -1).all()
+    assert (hc.binomial(-3, 0.5, 10)[0] == -1).all()
+
+
+def test_exact_log_pmf_ratio():
+    from scipy.special import gammaln
+    for n, p, k in [(100, 0.3, 41), (7317774, 1.2e-3, 9001), (50, 0.5, 10), (4292, 0.28, 1100)]:
+        m = np.floor((n + 1) * p)
+        want = (gammaln(m + 1) + gammaln(n - m + 1) - gammaln(k + 1) - gammaln(n - k + 1)
+                + (k - m) * np.log(p / (1 - p)))
+        assert hc.lib().hc_binomial_log_ratio(n, p, k) == pytest.approx(want, abs=2e-7 * max(1, abs(want)) + 1e-6)
+
+
+def test_tau_leap_influenza_law(golden):
+    g, e = golden["jump_single"], golden["jump_ensemble"]
+    out, st = hc.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, 12000, 0, cases.FLU_N_OUT, 0.5,
+                          tdpf=(g["flu_table"], g["flu_step_index"]), out_dtype=np.int32, seed=5)
+    assert (st == 0).all()
+    mine = out[:, e["flu_times"], :]
+    ref = np.transpose(e["flu_ens"], (1, 2, 0))
+    cases.assert_ks_ok(cases.ks_pvalues(mine, ref), "influenza kernel code (host) vs reference ensemble")
+    tot = out[:24].reshape(6, 4, cases.FLU_N_OUT, -1).sum(axis=0)
+    assert (tot == tot[:, :1, :]).all()
+
+
+def test_tau_leap_sir_si_law(golden):
+    g, e = golden["jump_single"], golden["jump_ensemble"]
+    out, st = hc.jump_run("sir_si_jump", g["sirsi_y0"], cases.SIRSI_PAR, 12000, 0, 121, 0.5, out_dtype=np.int32)
+    mine = out[:, e["sirsi_times"], :]
+    cases.assert_ks_ok(cases.ks_pvalues(mine, np.transpose(e["sirsi_ens"], (1, 2, 0))),
+                       "SIR_SI kernel code (host) vs reference ensemble")
+
+
+def test_interpolated_output_and_shard_invariance(golden):
+    g = golden["jump_single"]
+    tdpf = (g["flu_tau03_table"], g["flu_tau03_step_index"])
+    full, _ = hc.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, 64, 0, 46, 0.3, tdpf=tdpf, seed=3)
+    part, _ = hc.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, 16, 0, 46, 0.3, tdpf=tdpf, seed=3,
+                          traj_id0=40)
+    assert np.array_equal(part, full[:, :, 40:56])
+    assert np.any(full != np.round(full))
+    # every third step (0.9 -> ... 3.0) lands within 1 ulp of an integer time: interpolation weights stay in [0,1]
+    assert full.min() >= 0
+
+
+def test_ssa_law(golden):
+    g = golden["ssa"]
+    out, st = hc.jump_run("sir_si_jump", g["sirsi_small_y0"], cases.SIRSI_PAR, 4000, 0, 31, method="SSA", seed=2)
+    assert (st == 0).all()
+    times = [1, 3, 7, 15, 30]
+    ref = np.transpose(g["sirsi_small_ens"], (1, 2, 0)).astype(np.float64)
+    cases.assert_ks_ok(cases.ks_pvalues(out[:, times, :], ref[:, times, :]), "SSA kernel code (host) vs reference")
+
+
+def test_rk45_follows_scipy_step_for_step(golden):
+    g = golden["ode"]
+    out, nfev, st = hc.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], 100, 0, 121, var={0: g["sir_betas"]})
+    assert np.array_equal(nfev, g["sir_nfev"]) and (st == 0).all()
+    np.testing.assert_allclose(out, np.transpose(g["sir_y"], (1, 2, 0)), rtol=1e-9, atol=1e-9)
+    out, _, _ = hc.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], 1, 0, 61, method="euler", tau=0.25)
+    assert np.array_equal(out[:, :, 0], g["sir_euler_y"])
+    par = np.concatenate([g["pfr25_par_scalar"], g["pfr25_kL_a"], g["pfr25_D_ax"]])
+    post = g["pfr_posterior"][g["pfr25_pick"]]
+    out, nfev, st = hc.ode_run("packed_pfr_ode", g["pfr25_y0"], par, 4, 0, 8001, model_arg=25, out_stride=100,
+                               var={4: post[:, 0], 5: post[:, 1], 6: post[:, 2], 8: post[:, 3], 7: post[:, 4]})
+    assert np.array_equal(nfev, g["pfr25_nfev"])
+    np.testing.assert_allclose(out, np.transpose(g["pfr25_y"], (1, 2, 0)), rtol=1e-6, atol=1e-7)
