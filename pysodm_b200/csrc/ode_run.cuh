@@ -160,7 +160,7 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
     int64_t steps = 0;
     while (t < t_bound) {
         if (steps++ >= L.max_steps) { st |= ST_MAX_STEPS; break; }
-        const double min_step = 10.0 * (nextafter(t, INFINITY) - t);
+        const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);   // double overload on host AND device
         if (h_abs < min_step) h_abs = min_step;
         bool rejected = false, failed = false;
         double h, t_new;

@@ -42,7 +42,9 @@ def test_influenza_matches_reference_ensemble(eng, golden):
     assert np.all(np.abs(mine.mean(-1) - ref.mean(-1)) < 5 * sd / np.sqrt(ref.shape[-1]) + 1e-9)
     q_mine = np.quantile(out, [0.025, 0.5, 0.975], axis=-1)
     sd_all = np.transpose(e["flu_q"][2] - e["flu_q"][0], (0, 1)) / 3.92 + 1.0
-    assert np.all(np.abs(q_mine - e["flu_q"]) < 0.2 * sd_all + 1.5)
+    # the reference's tail quantiles come from 2000 members: s.e. ~ 0.06 sd (tails) / 0.03 sd (median); 13 608 cells
+    assert np.all(np.abs(q_mine - e["flu_q"]) < 0.4 * sd_all + 2.0)
+    assert np.mean(np.abs(q_mine - e["flu_q"]) < 0.15 * sd_all + 1.0) > 0.97
     # population of every age group is conserved exactly (S+E+Ip+Iud+Id+R)
     tot = out[:24].reshape(6, 4, cases.FLU_N_OUT, n).sum(axis=0)
     assert (tot == tot[:, :1, :]).all()
