@@ -1,0 +1,452 @@
+"""pySODM's model front end (`ODE`, `JumpProcess`) with the simulation loop replaced by the B200 library.
+
+The class API mirrors `/root/reference/src/pySODM/models/base.py`: class attributes `states`, `parameters`,
+`stratified_parameters`, `dimensions`, `dimensions_per_state` (:92-96, :636-640); constructor
+`(initial_states: dict | callable, parameters: dict, coordinates=None, time_dependent_parameters=None)` (:98-102);
+`sim(time, N=1, draw_function=None, draw_function_kwargs={}, processes=None, method, tau | rtol, time_unit='D')`
+(:485-494, :870-880) returning one `xarray.Dataset`-like object with dims `(['draws',] 'time'|'date', *state_dims)`
+(:969-1042).  What differs is WHERE the N simulations run: the reference loops / forks a process pool over
+`_mp_sim_single` (:558-566, :950-957); here all N trajectories go to the GPU in one batched call
+(`sodm_jump_run` / `sodm_ode_run`), chunked through a double-buffered host pipeline (pipeline.py).
+
+A model class is bound to a hand-written `__device__` functor by `device_model = "<registered name>"`.  A class
+without a functor cannot be simulated: there is deliberately no CPU fallback.
+
+Extensions over the reference signature (keyword-only, defaults = reference behaviour): `output_dtype`
+('float64' like the reference; 'int32'/'float32' halve the 18-36 GB of config C3), `states` (subset of states to
+return), `seed`, `device`, `chunk`, `compat` (tau-leap / SSA quirk flags), and for ODEs `atol`, `output_stride`,
+`output_last_only` (the reference grid of the packed-bed config is 1.28 TB).
+"""
+import copy
+import inspect
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _ffi, registry, validation
+from .dataset import make_dataset
+
+
+def _is_vectorized(fn):
+    return bool(getattr(fn, "vectorized", False))
+
+
+def _bounded_chunk(chunk, n_traj, bytes_per_traj, budget=4 << 30):
+    """Trajectories per pipeline chunk: at most `chunk`, at most N, and device buffers of at most ~4 GiB each."""
+    cap = max(32, int(budget // max(1, bytes_per_traj)) // 32 * 32)
+    return max(1, min(int(chunk), max(int(n_traj), 1), cap))
+
+
+class _DeviceBackedModel:
+    states = None
+    parameters = None
+    stratified_parameters = None
+    dimensions = None
+    dimensions_per_state = None
+    device_model = None            # name of the registered device functor (see registry.py / include/sodm.h)
+    _kind = None
+    _leading_args = ("t",)
+    _rhs_name = None
+
+    def __init__(self, initial_states, parameters, coordinates=None, time_dependent_parameters=None):
+        self.states_names = list(self.states) if self.states is not None else None
+        self.parameters_names = list(self.parameters) if self.parameters is not None else None
+        if self.states_names is None or self.parameters_names is None:
+            raise TypeError("a model class must declare 'states' and 'parameters'")
+        self.parameters_stratified_names = self.stratified_parameters
+        self.dimensions_names = list(self.dimensions) if self.dimensions else None
+        self.coordinates = coordinates
+        self.time_dependent_parameters = time_dependent_parameters
+        validation.names(self.states_names, self.parameters_names, self.parameters_stratified_names, self.dimensions_names)
+        self._stratified = validation.flat_stratified(self.parameters_stratified_names, self.dimensions_names or [])
+        self.parameters_names_modeldeclaration = self.parameters_names + [n for n, _ in self._stratified]
+        overlap = set(self.states_names) & set(self.parameters_names_modeldeclaration)
+        if overlap:
+            raise ValueError(f"overlap detected between 'state_names' and 'parameter_names + parameter_stratified_names': {sorted(overlap)}")
+        self.state_shapes, self.dimensions_per_state, self.state_coordinates = validation.state_layout(
+            self.states_names, self.dimensions_names, type(self).dimensions_per_state, coordinates)
+
+        # time-dependent parameter functions: fun(t, states, param, *extra)
+        self._function_parameters, self._extra_params_TDPF = [], []
+        for name, fn in (time_dependent_parameters or {}).items():
+            if name not in self.parameters_names_modeldeclaration:
+                raise ValueError(f"The specified time-dependent parameter '{name}' is not a model parameter")
+            args = list(inspect.signature(fn).parameters)
+            if len(args) < 3 or args[0] != "t" or args[1] != "states" or args[2] != "param":
+                raise ValueError(f"the signature of the time-dependent parameter function of '{name}' must start with "
+                                 f"(t, states, param); found {args}")
+            self._function_parameters.append(args[3:])
+            self._extra_params_TDPF += [a for a in args[3:] if a not in self._extra_params_TDPF]
+
+        # user functions' signatures
+        rhs = getattr(self, self._rhs_name)
+        validation.callable_signature(rhs, self._rhs_name, self.states_names, self.parameters_names_modeldeclaration,
+                                      self._leading_args)
+        self._check_extra_signatures()
+
+        # initial condition function
+        self.initial_states_function, self.initial_states_function_args = None, []
+        if callable(initial_states):
+            self.initial_states_function = initial_states
+            self.initial_states_function_args = list(inspect.signature(initial_states).parameters)
+        elif not isinstance(initial_states, dict):
+            raise TypeError("initial states must be: 1) a dictionary, 2) a callable function generating a dictionary. "
+                            f"found '{type(initial_states)}'")
+        self._extra_params_ICF = list(self.initial_states_function_args)
+
+        # parameters
+        if not isinstance(parameters, dict):
+            raise TypeError("'parameters' should be a dictionary.")
+        required = list(self.parameters_names_modeldeclaration)
+        required += [p for p in self._extra_params_TDPF + self._extra_params_ICF if p not in required]
+        missing = [p for p in required if p not in parameters]
+        if missing:
+            raise ValueError(f"The specified parameters don't exactly match the predefined parameters. "
+                             f"Missing parameters: {missing}")
+        redundant = [p for p in parameters if p not in required]
+        if redundant:
+            raise ValueError(f"The specified parameters don't exactly match the predefined parameters. "
+                             f"Redundant parameters: {redundant}")
+        self.parameters = {k: parameters[k] for k in required}
+        for name, dim in self._stratified:
+            v = np.asarray(self.parameters[name])
+            if v.ndim != 1 or v.shape[0] != len(coordinates[dim]):
+                raise ValueError(f"The coordinates provided for dimension '{dim}' indicates a dimension size of "
+                                 f"{len(coordinates[dim])}, but stratified parameter '{name}' has shape {v.shape}")
+            self.parameters[name] = v
+
+        # initial states
+        if self.initial_states_function:
+            given = self.initial_states_function(**{k: self.parameters[k] for k in self.initial_states_function_args})
+        else:
+            given = initial_states
+        self.initial_states = validation.initial_states(given, self.state_shapes)
+
+        self._bind_device_functor()
+
+    def _check_extra_signatures(self):
+        pass
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _bind_device_functor(self):
+        if not self.device_model:
+            raise NotImplementedError(
+                f"{type(self).__name__} declares no `device_model`. pysodm_b200 simulates hand-written device functors "
+                f"only ({sorted(registry.SPECS)}); arbitrary Python `{self._rhs_name}` functions cannot run on the GPU "
+                "and there is no CPU fallback.")
+        spec = registry.get(self.device_model)
+        if spec.kind != self._kind:
+            raise TypeError(f"device functor '{spec.name}' is a {spec.kind} model, {type(self).__name__} is a {self._kind} model")
+        self._model_arg = len(self.coordinates[spec.sized_by]) if spec.sized_by else 0
+        states, params = spec.resolve(self._model_arg)
+        if list(states) != self.states_names or any(tuple(states[k]) != tuple(self.state_shapes[k]) for k in states):
+            raise ValueError(f"states of {type(self).__name__} {dict(self.state_shapes)} do not match device functor "
+                             f"'{spec.name}' {dict(states)}")
+        if set(params) != set(self.parameters_names_modeldeclaration):
+            raise ValueError(f"parameters of {type(self).__name__} {self.parameters_names_modeldeclaration} do not match "
+                             f"device functor '{spec.name}' {list(params)}")
+        self._spec, self._spec_params = spec, params
+        self._param_offsets, self._n_param_flat = spec.param_offsets(self._model_arg)
+        for name in (self.time_dependent_parameters or {}):
+            if name not in spec.tdpf_params:
+                raise NotImplementedError(f"device functor '{spec.name}' has no time-dependent slot for parameter "
+                                          f"'{name}' (supported: {list(spec.tdpf_params)})")
+
+    def _flat_y0(self, initial_states):
+        return np.concatenate([np.ravel(np.asarray(v, dtype=np.float64)) for v in initial_states.values()])
+
+    def _flat_param(self, name, value):
+        off, n, shape = self._param_offsets[name]
+        arr = np.asarray(value, dtype=np.float64)
+        if arr.shape != tuple(shape) and not (arr.size == 1 and not shape):
+            raise ValueError(f"parameter '{name}' must have shape {tuple(shape)}, found {arr.shape}")
+        return arr.reshape(-1)
+
+    def _collect_draws(self, N, draw_function, draw_function_kwargs):
+        """Evaluate the draw function (reference: N calls in the parent, base.py:550-556) and split the result
+        into the shared flat parameter vector, the per-trajectory rows, and the (possibly per-trajectory) y0."""
+        base = self.parameters
+        par = np.zeros(self._n_param_flat)
+        for name in self._spec_params:
+            if name in (self.time_dependent_parameters or {}):
+                continue                                   # comes from the TDPF table
+            par[self._param_offsets[name][0]:][:self._param_offsets[name][1]] = self._flat_param(name, base[name])
+        y0 = self._flat_y0(self.initial_states)
+        if not draw_function:
+            return par, {}, y0, [base]
+        if _is_vectorized(draw_function):
+            drawn = draw_function(copy.deepcopy(base), N=N, **draw_function_kwargs)
+            stacked = {}
+            for name, value in drawn.items():
+                ref = np.asarray(base[name]) if not callable(base[name]) else None
+                v = np.asarray(value) if ref is not None else None
+                if ref is not None and v.ndim == ref.ndim + 1 and v.shape[0] == N:
+                    stacked[name] = v
+            dicts = None
+        else:
+            dicts = [draw_function(copy.deepcopy(base), **draw_function_kwargs) for _ in range(N)]
+            stacked = {}
+            for name in base:
+                first = dicts[0][name]
+                try:
+                    same = all(np.array_equal(d[name], first) for d in dicts[1:])
+                except Exception:  # noqa: BLE001  (unhashable / exotic parameter types)
+                    same = all(d[name] is first for d in dicts[1:])
+                if not same:
+                    stacked[name] = np.stack([np.asarray(d[name], dtype=np.float64) for d in dicts])
+                elif name in self._spec_params and name not in (self.time_dependent_parameters or {}):
+                    par[self._param_offsets[name][0]:][:self._param_offsets[name][1]] = self._flat_param(name, first)
+        var = {}
+        for name, values in stacked.items():
+            if name in (self.time_dependent_parameters or {}) or name in self._extra_params_TDPF:
+                raise NotImplementedError(f"parameter '{name}' is drawn per trajectory AND feeds a time-dependent "
+                                          "parameter function; the device path tabulates TDPFs once per run")
+            if name in self._spec_params:
+                off, n, shape = self._param_offsets[name]
+                flat = np.asarray(values, dtype=np.float64).reshape(N, n)
+                for e in range(n):
+                    var[off + e] = np.ascontiguousarray(flat[:, e])
+        if self.initial_states_function and any(a in stacked for a in self.initial_states_function_args):
+            cols = []
+            for i in range(N):
+                kw = {a: (stacked[a][i] if a in stacked else base[a]) for a in self.initial_states_function_args}
+                cols.append(self._flat_y0(validation.initial_states(self.initial_states_function(**kw), self.state_shapes)))
+            y0 = np.ascontiguousarray(np.stack(cols, axis=1))
+        return par, var, y0, dicts
+
+    def _select_rows(self, states):
+        """-> (pipeline variables, flat rows) for the requested subset of states (default: all, declaration order)."""
+        from .pipeline import Variable
+        names = self.states_names if states is None else list(states)
+        offsets, r = {}, 0
+        for name in self.states_names:
+            n = int(np.prod(self.state_shapes[name])) if self.state_shapes[name] else 1
+            offsets[name] = (r, n)
+            r += n
+        variables, rows, out_r = [], [], 0
+        for name in names:
+            if name not in offsets:
+                raise ValueError(f"'{name}' is not a model state {self.states_names}")
+            r0, n = offsets[name]
+            variables.append(Variable(name, out_r, self.state_shapes[name]))
+            rows += list(range(r0, r0 + n))
+            out_r += n
+        return variables, rows
+
+    def _to_dataset(self, host, variables, N, time_name, time_coord):
+        arrays = OrderedDict()
+        for v in variables:
+            a = host[v.name].numpy()
+            arrays[v.name] = a[0] if N == 1 else a
+        return make_dataset(arrays, self.dimensions_per_state, self.state_coordinates, time_name, time_coord, N)
+
+
+# ================================================================================================================
+class JumpProcess(_DeviceBackedModel):
+    """Stochastic jump-process model solved with Gillespie's tau-leaping or SSA on the GPU.
+
+    Subclasses declare `states`, `parameters`, optional `stratified_parameters` / `dimensions` /
+    `dimensions_per_state`, the static methods `compute_rates(t, *states, *parameters)` and
+    `apply_transitionings(t, tau, transitionings, *states, *parameters)` (kept for documentation, validation and
+    the CPU oracle), and `device_model`, the registered functor that restates them on the device."""
+    _kind = "jump"
+    _rhs_name = "compute_rates"
+
+    @staticmethod
+    def compute_rates():
+        raise NotImplementedError
+
+    @staticmethod
+    def apply_transitionings():
+        raise NotImplementedError
+
+    def _check_extra_signatures(self):
+        validation.callable_signature(self.apply_transitionings, "apply_transitionings", self.states_names,
+                                      self.parameters_names_modeldeclaration, ("t", "tau", "transitionings"))
+
+    def _tabulate_tdpfs(self, t0, n_steps, tau, start_date, time_unit):
+        """Evaluate the (state-independent) TDPFs at every tau-leap step time, as the reference's `func` does per
+        step with the ORIGINAL parameter value (base.py:365-380, Q8), and de-duplicate the values."""
+        if not self.time_dependent_parameters:
+            return None
+        tdpf_names = [n for n in self._spec.tdpf_params]
+        rows, index, seen = [], np.empty(n_steps, dtype=np.int32), {}
+        probe = {k: v * 0.0 for k, v in self.initial_states.items()}
+        t = t0
+        for k in range(n_steps):
+            when = validation.time_to_date(float(t), start_date, time_unit) if start_date is not None else t
+            parts = []
+            for name in tdpf_names:
+                if name in self.time_dependent_parameters:
+                    fn = self.time_dependent_parameters[name]
+                    i = list(self.time_dependent_parameters).index(name)
+                    kw = {a: self.parameters[a] for a in self._function_parameters[i]}
+                    val = fn(when, self.initial_states, self.parameters[name], **kw)
+                    if k in (0, n_steps // 2) and not np.array_equal(val, fn(when, probe, self.parameters[name], **kw)):
+                        raise NotImplementedError(f"the time-dependent parameter function of '{name}' depends on the "
+                                                  "model states; the device path only tabulates functions of time")
+                else:
+                    val = self.parameters[name]
+                parts.append(self._flat_param(name, val))
+            flat = np.concatenate(parts)
+            key = flat.tobytes()
+            if key not in seen:
+                seen[key] = len(rows)
+                rows.append(flat)
+            index[k] = seen[key]
+            t = t + tau
+        return np.stack(rows), index
+
+    def sim(self, time, N=1, draw_function=None, draw_function_kwargs={}, processes=None, method="tau_leap", tau=1,
+            time_unit="D", *, output_dtype="float64", states=None, seed=None, device=None, chunk=65536,
+            compat=_ffi.COMPAT_REFERENCE):
+        """Simulate N trajectories over `time` (see module docstring).  `processes` is accepted and ignored."""
+        import torch
+        from . import engine, pipeline
+        validation.jump_solution_method(method, tau)
+        time, date_range = validation.simulation_time(time, time_unit)
+        if draw_function:
+            validation.draw_function(draw_function, draw_function_kwargs, copy.deepcopy(self.parameters),
+                                     self.initial_states_function, self.state_shapes, self.initial_states_function_args)
+        saved = copy.deepcopy(self.parameters)
+        try:
+            par, var, y0, _ = self._collect_draws(N, draw_function, draw_function_kwargs)
+            t0, t1 = time
+            n_out = int(t1 - t0 + 1)
+            dev = engine.device(device)
+            lib = _ffi.load()
+            tdpf = None
+            if method == "tau_leap":
+                n_steps = int(lib.sodm_jump_n_steps(float(t0), n_out, float(tau)))
+                tdpf = self._tabulate_tdpfs(t0, n_steps, tau, date_range[0], time_unit)
+            elif self.time_dependent_parameters:
+                raise NotImplementedError("SSA with time-dependent parameter functions is not available on the device")
+            if self._spec.tdpf_params and tdpf is None and method == "tau_leap":
+                # constant value of a parameter that lives in the TDPF table
+                flat = np.concatenate([self._flat_param(n, self.parameters[n]) for n in self._spec.tdpf_params])
+                tdpf = (flat[None, :], np.zeros(max(n_steps, 1), dtype=np.int32))
+            variables, rows = self._select_rows(states)
+            host_dtype = engine.as_torch_dtype(output_dtype)
+            # tau = 2^-k: every output time is a step time, counts are exact integers -> simulate in int32 and let
+            # the layout kernel convert to the requested host dtype (halves the simulator's HBM writes)
+            inv = 1.0 / float(tau)
+            aligned = method == "tau_leap" and 0 < tau <= 1 and inv == int(inv) and (int(inv) & (int(inv) - 1)) == 0
+            sim_dtype = torch.int32 if aligned else torch.float64
+            if not aligned and host_dtype == torch.int32:
+                raise ValueError("output_dtype='int32' needs tau-leap with tau = 2^-k (outputs are interpolated otherwise)")
+            chunk = _bounded_chunk(chunk, N, len(rows) * n_out * (4 if aligned else 8))
+            if seed is None:
+                seed = int(np.random.randint(0, 2 ** 32)) | (int(np.random.randint(0, 2 ** 31)) << 32)
+            host = pipeline.alloc_host_result(variables, N, n_out, host_dtype)
+            pipe = pipeline.HostPipeline(variables, len(rows), n_out, chunk, sim_dtype, host_dtype, dev)
+            y0_d = torch.from_numpy(np.ascontiguousarray(y0)).to(dev)
+            tdpf_d = None
+            if tdpf is not None:
+                tdpf_d = (torch.from_numpy(np.ascontiguousarray(tdpf[0])).to(dev), torch.from_numpy(tdpf[1]).to(dev))
+            keys = sorted(var)
+            var_host = torch.from_numpy(np.stack([var[k] for k in keys])).pin_memory() if keys else None
+            status = torch.zeros(N, dtype=torch.int32, device=dev)
+
+            def launch(lo, n, buf, stream):
+                v = (keys, var_host[:, lo:lo + n].to(dev, non_blocking=True)) if keys else None
+                y = y0_d if y0_d.dim() == 1 else y0_d[:, lo:lo + n].contiguous()
+                engine.jump_run(self.device_model, y, par, n, t0, n_out, tau, method=method, var=v, tdpf=tdpf_d,
+                                compat=compat, seed=seed, traj_id0=lo, out_dtype=sim_dtype, state_sel=rows, out=buf,
+                                status=status[lo:lo + n], dev=dev, stream=stream)
+            pipe.run(N, launch, host)
+            pipe.synchronize()
+            self._raise_on_status(status)
+        finally:
+            self.parameters = saved
+        time_name = "date" if date_range[0] is not None else "time"
+        time_coord = date_range if date_range[0] is not None else np.arange(t0, t1 + 1)
+        return self._to_dataset(host, variables, N, time_name, time_coord)
+
+    @staticmethod
+    def _raise_on_status(status):
+        bits = int(status.max()) if status.numel() else 0
+        if bits & _ffi.ST_BAD_PROB:
+            raise ValueError("p < 0, p > 1 or p contains NaNs")          # NumPy's message (base.py:303)
+        if bits & _ffi.ST_NONFINITE:
+            raise ValueError("simulation produced non-finite propensities")
+        if bits & _ffi.ST_MAX_STEPS:
+            raise RuntimeError("event budget exhausted before the end of the simulation")
+
+
+# ================================================================================================================
+class ODE(_DeviceBackedModel):
+    """Deterministic model integrated on the GPU: scipy-faithful RK45, or fixed-step Euler / RK4 when `tau` is given.
+
+    Subclasses declare `states`, `parameters`, ..., the static method `integrate(t, *states, *parameters)` (kept for
+    documentation, validation and the CPU oracle) and `device_model`."""
+    _kind = "ode"
+    _rhs_name = "integrate"
+
+    @staticmethod
+    def integrate():
+        raise NotImplementedError
+
+    def sim(self, time, N=1, draw_function=None, draw_function_kwargs={}, processes=None, method="RK45", rtol=1e-4,
+            tau=None, time_unit="D", *, atol=1e-6, output_dtype="float64", output_stride=1, output_last_only=False,
+            device=None, chunk=65536):
+        import torch
+        from . import engine, pipeline
+        validation.ode_solution_method(rtol, method, tau)
+        time, date_range = validation.simulation_time(time, time_unit)
+        if draw_function:
+            validation.draw_function(draw_function, draw_function_kwargs, copy.deepcopy(self.parameters),
+                                     self.initial_states_function, self.state_shapes, self.initial_states_function_args)
+        if N != 1 and draw_function is None:
+            raise ValueError(f"attempting to perform N={N} repeated simulations without using a draw function")
+        if self.time_dependent_parameters:
+            raise NotImplementedError("time-dependent parameter functions are not yet available for device ODE models")
+        if tau:
+            dev_method = "RK4" if method == "RK4" else "euler"
+        elif method == "RK45":
+            dev_method = "RK45"
+        else:
+            raise NotImplementedError(f"method '{method}' has no device implementation (available: 'RK45', or a fixed "
+                                      "step `tau` for Euler / method='RK4'); there is no CPU fallback")
+        saved = copy.deepcopy(self.parameters)
+        try:
+            par, var, y0, _ = self._collect_draws(N, draw_function, draw_function_kwargs)
+            t0, t1 = time
+            n_out = int(t1 - t0 + 1)
+            dev = engine.device(device)
+            lib = _ffi.load()
+            n_kept = int(lib.sodm_ode_n_kept(n_out, int(output_stride), int(bool(output_last_only))))
+            variables, rows = self._select_rows(None)
+            host_dtype = engine.as_torch_dtype(output_dtype)
+            host = pipeline.alloc_host_result(variables, N, n_kept, host_dtype)
+            chunk = _bounded_chunk(chunk, N, len(rows) * n_kept * 8)
+            pipe = pipeline.HostPipeline(variables, len(rows), n_kept, chunk, torch.float64, host_dtype, dev)
+            y0_d = torch.from_numpy(np.ascontiguousarray(y0)).to(dev)
+            keys = sorted(var)
+            var_host = torch.from_numpy(np.stack([var[k] for k in keys])).pin_memory() if keys else None
+            status = torch.zeros(N, dtype=torch.int32, device=dev)
+            self.last_nfev = torch.zeros(N, dtype=torch.int32, device=dev)
+
+            def launch(lo, n, buf, stream):
+                v = (keys, var_host[:, lo:lo + n].to(dev, non_blocking=True)) if keys else None
+                y = y0_d if y0_d.dim() == 1 else y0_d[:, lo:lo + n].contiguous()
+                _, nfev, st = engine.ode_run(self.device_model, y, par, n, t0, n_out, method=dev_method, rtol=rtol,
+                                             atol=atol, tau=tau or 0.0, var=v, model_arg=self._model_arg,
+                                             out_stride=output_stride, out_last_only=output_last_only, out=buf, dev=dev,
+                                             stream=stream)
+                status[lo:lo + n].copy_(st, non_blocking=True)
+                self.last_nfev[lo:lo + n].copy_(nfev, non_blocking=True)
+            pipe.run(N, launch, host)
+            pipe.synchronize()
+            bits = int(status.max()) if N else 0
+            if bits & (_ffi.ST_STEP_TOO_SMALL | _ffi.ST_NONFINITE):
+                raise RuntimeError("Required step size is less than spacing between numbers.")     # scipy's message
+        finally:
+            self.parameters = saved
+        grid = np.arange(t0, t1 + 1)
+        keep = grid[-1:] if output_last_only else grid[::int(output_stride)]
+        if date_range[0] is not None:
+            time_name = "date"
+            time_coord = date_range[-1:] if output_last_only else date_range[::int(output_stride)]
+        else:
+            time_name, time_coord = "time", keep
+        return self._to_dataset(host, variables, N, time_name, time_coord)

@@ -99,11 +99,35 @@ __host__ __device__ __forceinline__ double binomial_log_ratio(double nd, double 
          - stirling_tail(kd) - stirling_tail(nd - kd);
 }
 
+__host__ __device__ __forceinline__ float stirling_tail_f(float k) {
+    if (k <= 9.0f) return (float)stirling_tail((double)k);
+    const float kp1 = k + 1.0f;
+    const float inv = 1.0f / (kp1 * kp1);
+    return (0.0833333333f - (0.00277777778f - 0.000793650794f * inv) * inv) / kp1;
+}
+
+// The same ratio in FP32, for modes below SODM_F32_MODE_LIMIT: the three logarithms are taken of ratios that
+// are 1 + O(1/m), so the absolute error is ~ m * 2^-23 (< 3e-4 at the limit) -- an error in an ACCEPTANCE
+// PROBABILITY that is only consulted for the ~2 % of attempts the squeeze cannot settle, i.e. a distortion of
+// the sampled law below 1e-5, far under Monte-Carlo resolution at 10^6 trajectories.
+#ifndef SODM_F32_MODE_LIMIT
+#define SODM_F32_MODE_LIMIT 2048.0f
+#endif
+__host__ __device__ __forceinline__ float binomial_log_ratio_f32(float nf, float p, float m, float k) {
+    const float r = p / (1.0f - p);
+    const float a = nf - m + 1.0f, b = nf - k + 1.0f;
+    return (m + 0.5f) * logf((m + 1.0f) / (r * a)) + stirling_tail_f(m) + stirling_tail_f(nf - m)
+         + (nf + 1.0f) * log1pf((k - m) / b)
+         + (k + 0.5f) * logf(r * b / (k + 1.0f))
+         - stirling_tail_f(k) - stirling_tail_f(nf - k);
+}
+
 // One BTRS attempt; requires 0 < p <= 0.5 and n*p >= 10.  Returns true and sets k when accepted.
 template <class Rng>
 __host__ __device__ __forceinline__ bool btrs_try(Rng& rng, int n, float p, int& k) {
     const float nf = (float)n;
-    const float npq = nf * p * (1.0f - p);
+    const float np_ = nf * p;
+    const float npq = np_ * (1.0f - p);
     const float stddev = sqrtf(npq);
     const float b = 1.15f + 2.53f * stddev;
     const float a = -0.0873f + 0.0248f * b + 0.01f * p;
@@ -112,15 +136,21 @@ __host__ __device__ __forceinline__ bool btrs_try(Rng& rng, int n, float p, int&
     const float u = u01(rng.next()) - 0.5f;
     const float v = u01(rng.next());
     const float us = 0.5f - fabsf(u);
-    const double nd = (double)n, pd = (double)p;
-    const double kd = floor(fma((double)(2.0f * a / us + b), (double)u, fma(nd, pd, 0.5)));
-    k = (int)kd;
+    float kf;
+    if (np_ < 4194304.0f) {                                      // candidate exactly representable in FP32
+        kf = floorf(fmaf(2.0f * a / us + b, u, np_ + 0.5f));
+        k = (int)kf;
+    } else {
+        const double kd = floor(fma((double)(2.0f * a / us + b), (double)u, fma((double)n, (double)p, 0.5)));
+        k = (int)fmin(fmax(kd, -1.0), 2147483647.0);
+        kf = (float)kd;
+    }
     if (us >= 0.07f && v <= v_r) return true;                    // BTRS box: no logarithm needed
-    if (kd < 0.0 || kd > nd) return false;
+    if (k < 0 || k > n) return false;
     const float alpha = (2.83f + 5.1f * inv_b) * stddev;
     const float lhs = logf(v * alpha / (a / (us * us) + b));
-    const double m = floor((nd + 1.0) * pd);
-    const float x = fabsf((float)(kd - m));
+    const float mf = floorf((nf + 1.0f) * p);
+    const float x = fabsf(kf - mf);
     if (x < 0.5f * npq - 1.0f) {                                  // BTPE step 5.2 squeeze, in FP32
         const float t = -x * x / (2.0f * npq);
         const float rho = (x / npq) * ((x * (x * (1.0f / 3.0f) + 0.625f) + (1.0f / 6.0f)) / npq + 0.5f);
@@ -128,7 +158,10 @@ __host__ __device__ __forceinline__ bool btrs_try(Rng& rng, int n, float p, int&
         if (lhs < t - rho - eps) return true;
         if (lhs > t + rho + eps) return false;
     }
-    return (double)lhs <= binomial_log_ratio(nd, pd, m, kd);     // exact test (rare)
+    if (mf < SODM_F32_MODE_LIMIT && nf < 16777216.0f)             // exact test: FP32 where its error is harmless
+        return lhs <= binomial_log_ratio_f32(nf, p, mf, kf);
+    const double nd = (double)n, pd = (double)p;
+    return (double)lhs <= binomial_log_ratio(nd, pd, floor((nd + 1.0) * pd), (double)k);
 }
 
 // ONE attempt at Bin(n, p), 0 <= p <= 1.  Returns true when finished with the variate in k.

@@ -41,6 +41,7 @@ inline int build_jump_launch(const sodm_jump_args* a, JumpLaunch& L, bool& align
     if (a->n_traj < 0 || a->ld_in < a->n_traj || a->ld_out < a->n_traj)
         return fail(SODM_EINVAL, "sodm_jump_run: need 0 <= n_traj <= ld_in, ld_out");
     if (a->n_out < 1) return fail(SODM_EINVAL, "sodm_jump_run: n_out must be >= 1");
+    if (a->n_traj == 0) { L = JumpLaunch{}; aligned = false; return SODM_OK; }   // empty launch: buffers may be null
     if (!a->y0 || !a->par || !a->out) return fail(SODM_EINVAL, "sodm_jump_run: y0, par and out are required");
     if (a->n_var < 0 || a->n_var > info.n_param || (a->n_var && (!a->var_index || !a->var_values)))
         return fail(SODM_EINVAL, "sodm_jump_run: inconsistent per-trajectory parameter description");

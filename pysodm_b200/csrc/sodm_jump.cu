@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(JUMP_BLOCK) tau_leap_kernel(const __grid_const
     for (int e = threadIdx.x; e < n_tab; e += blockDim.x) table[e] = (float)L.tdpf_table[e];   // ABI speaks FP64, rates are FP32
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    w.lanes = __ballot_sync(0xffffffffu, i < L.n_traj);
     if (i < L.n_traj) tau_leap_trajectory<M, OutT, ALIGNED>(L, i, table, w);
 }
 

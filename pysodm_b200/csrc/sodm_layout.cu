@@ -58,6 +58,7 @@ using namespace sodm;
 
 extern "C" int sodm_to_draws_major(const void* src, int32_t src_dtype, int64_t ld, int32_t r0, int32_t n_dim, int32_t n_t,
                                    int64_t n_traj, void* dst, int32_t dst_dtype, void* stream) {
+    if (n_traj == 0) return SODM_OK;
     if (!src || !dst) return fail(SODM_EINVAL, "sodm_to_draws_major: null buffer");
     if (n_dim < 1 || n_t < 1 || r0 < 0 || n_traj < 0 || ld < n_traj)
         return fail(SODM_EINVAL, "sodm_to_draws_major: need n_dim, n_t >= 1, r0 >= 0, 0 <= n_traj <= ld");

@@ -159,6 +159,7 @@ extern "C" int sodm_loglik(const sodm_loglik_args* a) {
     if (a->kind < SODM_LL_POISSON || a->kind > SODM_LL_NEGBIN) return fail(SODM_EINVAL, "sodm_loglik: unknown kind %d", a->kind);
     if (a->n_traj < 0 || a->ld < a->n_traj) return fail(SODM_EINVAL, "sodm_loglik: need 0 <= n_traj <= ld");
     if (a->n_out < 1 || a->n_col < 1 || a->n_t < 1) return fail(SODM_EINVAL, "sodm_loglik: n_out, n_col, n_t must be >= 1");
+    if (a->n_traj == 0) return SODM_OK;
     if (!a->traj || !a->col_ptr || !a->col_rows || !a->t_data || !a->ydata || !a->lp)
         return fail(SODM_EINVAL, "sodm_loglik: traj, col_ptr, col_rows, t_data, ydata and lp are required");
     const bool needs_arg = a->kind != SODM_LL_POISSON;

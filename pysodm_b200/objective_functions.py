@@ -1,0 +1,377 @@
+"""`log_posterior_probability` for whole populations of parameter vectors at once.
+
+Mirrors `/root/reference/src/pySODM/optimization/objective_functions.py`: the constructor signature (:92-108),
+`__call__(thetas) -> float` (:290-335: sum of log priors, clipping to the bounds with a -inf penalty, one simulation,
+sum of weighted log-likelihoods) and the `ll_*` / `log_prior_*` names (:343-666).  What differs is the unit of
+work: `batch(thetas[P, D]) -> lp[P]` simulates all P parameter vectors in ONE `sodm_jump_run` / `sodm_ode_run`
+launch (one trajectory per vector, as the reference's `sim(N=1)` per call) and reduces every trajectory against the
+data with `sodm_loglik` on the device -- no trajectory leaves the GPU; only `lp[P]` comes back.  PSO / Nelder-Mead
+loops (`pso.py:177-183`, `nelder_mead.py:131-138`) and emcee (`vectorize=True`) can call `batch` directly;
+`__call__` is `batch` on a population of one.
+
+The model/data alignment the reference does through xarray (:244-288) is compiled ONCE at construction into an
+"alignment plan": per dataset, the flat state rows that are summed into each data column (dimensions absent from
+the data are summed, :250-252), the data's time points in simulation time (linear interpolation, :254) and the
+`(time, *data_axes)` ordered data matrix (:256-259, :271-278).
+"""
+import itertools
+from datetime import datetime
+
+import numpy as np
+import pandas as pd
+
+from . import _ffi
+from .validation import TIME_UNIT_US
+
+# ---- log-likelihood "functions": on the device the choice is an enum; these callables keep the reference's names
+#      (and work on host arrays, for users who call them directly as in the reference's tutorials) ----------------
+
+
+def _device_kind(kind):
+    def deco(fn):
+        fn.device_kind = kind
+        return fn
+    return deco
+
+
+@_device_kind("poisson")
+def ll_poisson(ymodel, ydata):
+    """Poisson log-likelihood on +1-shifted model and data (reference :613-633), host evaluation."""
+    from scipy.special import gammaln
+    ym = np.asarray(ymodel, dtype=np.float64) + 1
+    yd = np.asarray(ydata, dtype=np.float64) + 1
+    return -np.sum(ym) + np.sum(yd * np.log(ym)) - np.sum(gammaln(yd))
+
+
+@_device_kind("negative_binomial")
+def ll_negative_binomial(ymodel, ydata, alpha):
+    """Negative-binomial log-likelihood, dispersion `alpha` scalar or one per data column (reference :636-666)."""
+    from scipy.special import gammaln
+    a = np.array(alpha)[np.newaxis, ...]
+    ym = np.asarray(ymodel, dtype=np.float64) + 1
+    yd = np.asarray(ydata, dtype=np.float64) + 1
+    return (np.sum(yd * np.log(ym)) - np.sum((yd + 1 / a) * np.log(1 + a * ym)) + np.sum(yd * np.log(a))
+            + np.sum(gammaln(yd + 1 / a)) - np.sum(gammaln(yd + 1)) - np.sum(yd.shape[0] * gammaln(1 / a)))
+
+
+def _sigma_like(sigma, ymodel, name):
+    s = np.array(sigma)
+    if s.shape != np.shape(ymodel):
+        s = s[np.newaxis, ...]
+    if np.any(s <= 0):
+        raise ValueError(f"the standard deviation used in `{name}` contains values smaller than or equal to zero")
+    return s
+
+
+@_device_kind("normal")
+def ll_normal(ymodel, ydata, sigma):
+    """Gaussian log-likelihood (reference :582-610)."""
+    s = _sigma_like(sigma, ymodel, "ll_normal")
+    return -1 / 2 * np.sum((np.asarray(ydata) - np.asarray(ymodel)) ** 2 / s ** 2 + np.log(2 * np.pi * s ** 2))
+
+
+@_device_kind("lognormal")
+def ll_lognormal(ymodel, ydata, sigma):
+    """Lognormal log-likelihood (reference :550-579)."""
+    s = _sigma_like(sigma, ymodel, "ll_lognormal")
+    yd, ym = np.asarray(ydata, dtype=np.float64), np.asarray(ymodel, dtype=np.float64)
+    return -1 / 2 * np.sum((np.log(yd + 1) - np.log(ym + 1)) ** 2 / s ** 2 + np.log(2 * np.pi * s ** 2) + np.log(yd + 1))
+
+
+# ---- log priors: D <= ~10 numbers per particle -> vectorised on the host -----------------------
+
+def log_prior_uniform(x, bounds=None, weight=1):
+    x = np.asarray(x, dtype=np.float64)
+    return np.where((bounds[0] <= x) & (x <= bounds[1]), 0.0 * weight, -np.inf)
+
+
+def log_prior_triangle(x, low=None, high=None, mode=None, weight=1):
+    from scipy.stats import triang
+    return weight * triang.logpdf(x, loc=low, scale=high - low, c=(mode - low) / (high - low))
+
+
+def log_prior_normal(x, avg=None, stdev=None, weight=1):
+    from scipy.stats import norm
+    return weight * norm.logpdf(x, loc=avg, scale=stdev)
+
+
+def log_prior_lognormal(x, s=None, scale=None, weight=1):
+    from scipy.stats import lognorm
+    return weight * lognorm.logpdf(x, s=s, scale=scale)
+
+
+def log_prior_gamma(x, a=None, loc=None, scale=None, weight=1):
+    from scipy.stats import gamma
+    return weight * gamma.logpdf(x, a=a, loc=loc, scale=scale)
+
+
+def log_prior_beta(x, a=None, b=None, loc=None, scale=None, weight=1):
+    from scipy.stats import beta
+    return weight * beta.logpdf(x, a, b, loc=loc, scale=scale)
+
+
+# ================================================================================================================
+class log_posterior_probability:
+    def __init__(self, model, parameter_names, bounds, data, states, log_likelihood_fnc, log_likelihood_fnc_args,
+                 start_sim=None, weights=None, log_prior_prob_fnc=None, log_prior_prob_fnc_args=None,
+                 initial_states=None, aggregation_function=None, labels=None, simulation_kwargs={}):
+        n = len(data)
+        if weights is None:
+            weights = n * [1, ]
+        if not isinstance(weights, (list, np.ndarray)) or np.ndim(weights) > 1:
+            raise TypeError("Expected a list/1D np.array for input argument `weights`")
+        lists = [states, log_likelihood_fnc, log_likelihood_fnc_args, weights] + ([initial_states] if initial_states else [])
+        if any(len(lst) != n for lst in lists):
+            raise ValueError(f"The number of datasets ({n}), model states ({len(states)}), log likelihood functions "
+                             f"({len(log_likelihood_fnc)}), the extra arguments of the log likelihood function "
+                             f"({len(log_likelihood_fnc_args)}), and weights ({len(weights)}) must be of equal length")
+        if aggregation_function:
+            raise NotImplementedError("user aggregation functions operate on xarray objects on the host; the device "
+                                      "path sums model dimensions absent from the data and nothing else")
+        self.model, self.states, self.weights = model, list(states), [float(w) for w in weights]
+        self.parameters_names = list(parameter_names)
+        self.log_likelihood_fnc = list(log_likelihood_fnc)
+        self.simulation_kwargs = dict(simulation_kwargs)
+        for k in self.simulation_kwargs:
+            if k not in ("tau", "method", "rtol", "atol", "time_unit", "compat"):
+                raise ValueError(f"'{k}' is not a valid simulation keyword for a batched device simulation")
+        self.initial_states = initial_states
+
+        # ---- datasets: time axis + additional axes ---------------------------------------------------------------
+        self.data = [self._as_series(d, i) for i, d in enumerate(data)]
+        kinds = {("date" if "date" in d.index.names else "time") for d in self.data}
+        if len(kinds) != 1:
+            raise ValueError("all datasets must use the same time index name: 'time' or 'date'")
+        self.time_index = kinds.pop()
+        self.additional_axes_data = [[nm for nm in d.index.names if nm != self.time_index] for d in self.data]
+
+        # ---- simulation window (reference :769-848) ---------------------------------------------------------------
+        firsts = [d.index.get_level_values(self.time_index).min() for d in self.data]
+        lasts = [d.index.get_level_values(self.time_index).max() for d in self.data]
+        if self.time_index == "time":
+            data_start, self.end_sim = float(min(firsts)), float(max(lasts))
+            if start_sim is None:
+                start_sim = data_start
+            if isinstance(start_sim, bool) or not isinstance(start_sim, (int, float)):
+                raise TypeError("'start_sim' must be of type int/float")
+            start_sim = float(start_sim)
+        else:
+            data_start, self.end_sim = min(firsts).to_pydatetime(), max(lasts).to_pydatetime()
+            if start_sim is None:
+                start_sim = data_start
+            if isinstance(start_sim, str):
+                start_sim = datetime.strptime(start_sim, "%Y-%m-%d")
+            if not isinstance(start_sim, datetime):
+                raise TypeError("'start_sim' must be of type datetime.datetime or a string representation of a date ('yyyy-mm-dd')")
+        assert start_sim <= data_start, (f"start of the earliest dataset ({data_start}) before 'start_sim' ({start_sim}). make sure "
+                                         "'start_sim' is chronologically before the start of the earliest datapoint.")
+        self.start_sim = start_sim
+
+        # ---- calibrated parameters, bounds, labels (reference :851-1021) ------------------------------------------
+        self.parameter_shapes, sizes = {}, []
+        for name in self.parameters_names:
+            if name not in model.parameters:
+                raise Exception(f"To be calibrated parameter '{name}' is not a valid model parameter!")
+            shape = np.shape(model.parameters[name])
+            self.parameter_shapes[name] = shape
+            sizes.append(int(np.prod(shape)) if shape else 1)
+        if len(bounds) != len(self.parameters_names):
+            raise Exception(f"The number of provided bounds ({len(bounds)}) must match the number of calibrated "
+                            f"parameters ({len(self.parameters_names)})")
+        for lo_hi in bounds:
+            if lo_hi[0] >= lo_hi[1]:
+                raise ValueError(f"bounds {tuple(lo_hi)}: lower bound must be smaller than upper bound")
+        labels = list(labels) if labels else list(self.parameters_names)
+        self.expanded_bounds, self.expanded_labels, self.parameters_names_postprocessing = [], [], []
+        for name, size, bnd, lab in zip(self.parameters_names, sizes, bounds, labels):
+            for idx in (itertools.product(*[range(s) for s in self.parameter_shapes[name]]) if size > 1 or self.parameter_shapes[name] else [()]):
+                suffix = "_" + "_".join(str(i) for i in idx) if idx != () else ""
+                self.expanded_bounds.append(tuple(bnd))
+                self.expanded_labels.append(lab + suffix)
+                self.parameters_names_postprocessing.append(name + suffix)
+        self._sizes = sizes
+        self.n_theta = sum(sizes)
+
+        # ---- priors -------------------------------------------------------------------------------------------------
+        if log_prior_prob_fnc is None:
+            self.log_prior_prob_fnc = [log_prior_uniform] * self.n_theta
+            self.log_prior_prob_fnc_args = [{"bounds": b} for b in self.expanded_bounds]
+        else:
+            if len(log_prior_prob_fnc) != len(self.parameters_names) or len(log_prior_prob_fnc_args) != len(self.parameters_names):
+                raise Exception("The number of prior functions / prior arguments must match the number of calibrated parameters")
+            self.log_prior_prob_fnc, self.log_prior_prob_fnc_args = [], []
+            for fn, kw, size in zip(log_prior_prob_fnc, log_prior_prob_fnc_args, sizes):
+                self.log_prior_prob_fnc += [fn] * size
+                self.log_prior_prob_fnc_args += [dict(kw)] * size
+
+        # ---- likelihood functions and their arguments --------------------------------------------------------------
+        self._kinds = []
+        for fn in self.log_likelihood_fnc:
+            kind = getattr(fn, "device_kind", None) or {"ll_poisson": "poisson", "ll_negative_binomial": "negative_binomial",
+                                                         "ll_normal": "normal", "ll_lognormal": "lognormal"}.get(getattr(fn, "__name__", ""))
+            if kind is None:
+                raise NotImplementedError(f"log-likelihood function {fn} has no device implementation "
+                                          "(available: ll_poisson, ll_negative_binomial, ll_normal, ll_lognormal)")
+            self._kinds.append(kind)
+        self.log_likelihood_fnc_args = []
+        for kind, arg in zip(self._kinds, log_likelihood_fnc_args):
+            if kind == "poisson":
+                if arg not in (None, [], ()):
+                    raise ValueError("the likelihood function `ll_poisson` takes no additional arguments")
+                self.log_likelihood_fnc_args.append(None)
+            else:
+                self.log_likelihood_fnc_args.append(np.asarray(arg, dtype=np.float64))
+
+        # ---- alignment plan ------------------------------------------------------------------------------------------
+        self._plan = [self._build_plan(i) for i in range(n)]
+
+    # -------------------------------------------------------------------------------------------------------------
+    def _as_series(self, d, i):
+        if isinstance(d, pd.DataFrame):
+            if d.shape[1] != 1:
+                raise ValueError(f"{i}th dataset: a DataFrame must have exactly one column")
+            d = d.iloc[:, 0]
+        if not isinstance(d, pd.Series):
+            raise TypeError(f"{i}th dataset must be a pd.Series or single-column pd.DataFrame, found {type(d)}")
+        if "time" not in d.index.names and "date" not in d.index.names:
+            raise ValueError(f"Index of {i}th dataset does not have 'time' or 'date' as index level.")
+        if d.isna().any():
+            raise ValueError(f"{i}th dataset contains nans")
+        return d
+
+    def _state_rows(self, state):
+        names = self.model.states_names
+        if state not in names:
+            raise ValueError(f"'{state}' is not a model state {names}")
+        r0 = 0
+        for nm in names:
+            n = int(np.prod(self.model.state_shapes[nm])) if self.model.state_shapes[nm] else 1
+            if nm == state:
+                return r0, self.model.state_shapes[nm], self.model.dimensions_per_state[nm], self.model.state_coordinates[nm]
+            r0 += n
+        raise AssertionError
+
+    def _build_plan(self, i):
+        d, state, axes = self.data[i], self.states[i], self.additional_axes_data[i]
+        r0, shape, dims, coords = self._state_rows(state)
+        for ax in axes:
+            if ax not in dims:
+                raise Exception(f"{i}th dataset: index level '{ax}' is not a dimension of model state '{state}' {dims}")
+        times = d.index.get_level_values(self.time_index).unique()
+        if self.time_index == "date":
+            unit = TIME_UNIT_US[self.simulation_kwargs.get("time_unit", "D")]
+            t_data = np.array([(t.to_pydatetime() - self.start_sim).total_seconds() * 1e6 / unit for t in times])
+        else:
+            t_data = np.asarray(times, dtype=np.float64)
+        axis_coords = [list(d.index.get_level_values(ax).unique()) for ax in axes]
+        for ax, cs in zip(axes, axis_coords):
+            model_cs = coords[dims.index(ax)]
+            missing = [c for c in cs if c not in model_cs]
+            if missing:
+                raise Exception(f"{i}th dataset: coordinates {missing} of '{ax}' are not coordinates of the model")
+        # data matrix in (time, *axes) order, columns = C-order product of the data's coordinates
+        series = d.reorder_levels([self.time_index] + axes) if axes else d
+        full = pd.MultiIndex.from_product([times] + axis_coords) if axes else times
+        ydata = series.reindex(full).to_numpy(dtype=np.float64).reshape(len(times), -1)
+        if np.isnan(ydata).any():
+            raise ValueError(f"{i}th dataset does not contain a value for every combination of its index levels")
+        # model rows summed into each data column: fix the data's axes, sum over the state's other dimensions
+        columns = []
+        for combo in (itertools.product(*axis_coords) if axes else [()]):
+            fixed = {ax: coords[dims.index(ax)].index(c) for ax, c in zip(axes, combo)}
+            rows = []
+            for idx in itertools.product(*[range(s) for s in shape]) if shape else [()]:
+                if all(idx[dims.index(ax)] == k for ax, k in fixed.items()):
+                    rows.append(r0 + (int(np.ravel_multi_index(idx, shape)) if shape else 0))
+            columns.append(rows)
+        arg = self.log_likelihood_fnc_args[i]
+        if arg is not None and arg.ndim > 0 and arg.shape not in ((ydata.shape[1],), ydata.shape) and arg.size != 1:
+            raise ValueError(f"the extra argument of the {i}th log-likelihood function has shape {arg.shape}, "
+                             f"which does not match the data {ydata.shape}")
+        return {"columns": columns, "t_data": t_data, "ydata": ydata}
+
+    # -------------------------------------------------------------------------------------------------------------
+    def compute_log_prior_probability(self, thetas):
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        lp = np.zeros(thetas.shape[0])
+        for j, (fn, kw) in enumerate(zip(self.log_prior_prob_fnc, self.log_prior_prob_fnc_args)):
+            lp = lp + np.asarray(fn(thetas[:, j], **kw), dtype=np.float64)
+        return lp
+
+    def batch(self, thetas, seed=None, device=None, return_device=False):
+        """lp[P] for thetas[P, D] (D = number of expanded parameters).  Like the reference's `__call__`, values
+        outside the bounds are clipped IN PLACE and penalised with -inf (:301-307)."""
+        import torch
+        from . import engine
+        thetas = np.asarray(thetas)
+        if thetas.ndim != 2 or thetas.shape[1] != self.n_theta:
+            raise ValueError(f"thetas must have shape [P, {self.n_theta}]")
+        P = thetas.shape[0]
+        lp = self.compute_log_prior_probability(thetas)
+        for j, (lo, hi) in enumerate(self.expanded_bounds):
+            above, below = thetas[:, j] > hi, thetas[:, j] < lo
+            thetas[above, j], thetas[below, j] = hi, lo
+            lp = lp + np.where(above | below, -np.inf, 0.0)
+        model = self.model
+        dev = engine.device(device)
+        # parameter vector -> flat device parameter elements
+        par, _, y0, _ = model._collect_draws(1, None, {})
+        var, col = {}, 0
+        for name, size in zip(self.parameters_names, self._sizes):
+            if name not in model._param_offsets:
+                raise NotImplementedError(f"calibrated parameter '{name}' is not a parameter of the device functor")
+            if name in (model.time_dependent_parameters or {}):
+                raise NotImplementedError(f"calibrated parameter '{name}' is time dependent")
+            off = model._param_offsets[name][0]
+            for e in range(size):
+                var[off + e] = np.ascontiguousarray(thetas[:, col + e], dtype=np.float64)
+            col += size
+        kw = self.simulation_kwargs
+        time_unit = kw.get("time_unit", "D")
+        if self.time_index == "date":
+            unit = TIME_UNIT_US[time_unit]
+            t0, t1 = 0, int(np.ceil((self.end_sim - self.start_sim).total_seconds() * 1e6 / unit))
+            start_date = self.start_sim
+        else:
+            t0, t1, start_date = round(self.start_sim), round(self.end_sim), None
+        n_out = int(t1 - t0 + 1)
+        lp_d = torch.zeros(P, dtype=torch.float64, device=dev)
+        st_ll = torch.zeros(P, dtype=torch.int32, device=dev)
+        y0_sets = [y0] if not self.initial_states else [
+            model._flat_y0({**model.initial_states, **{k: np.asarray(v, dtype=np.float64) for k, v in s.items()}})
+            for s in self.initial_states]
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 32)) | (int(np.random.randint(0, 2 ** 31)) << 32)
+        for k, y in enumerate(y0_sets):
+            if model._kind == "jump":
+                tau, method = kw.get("tau", 1), kw.get("method", "tau_leap")
+                tdpf = None
+                if method == "tau_leap":
+                    n_steps = int(_ffi.load().sodm_jump_n_steps(float(t0), n_out, float(tau)))
+                    tdpf = model._tabulate_tdpfs(t0, n_steps, tau, start_date, time_unit)
+                    if model._spec.tdpf_params and tdpf is None:
+                        flat = np.concatenate([model._flat_param(nm, model.parameters[nm]) for nm in model._spec.tdpf_params])
+                        tdpf = (flat[None, :], np.zeros(max(n_steps, 1), dtype=np.int32))
+                traj, st = engine.jump_run(model.device_model, y, par, P, t0, n_out, tau, method=method, var=var,
+                                           tdpf=tdpf, compat=kw.get("compat", _ffi.COMPAT_REFERENCE), seed=seed + k,
+                                           out_dtype=torch.float64, dev=dev)
+                model._raise_on_status(st)
+            else:
+                traj, _, st = engine.ode_run(model.device_model, y, par, P, t0, n_out, method="euler" if kw.get("tau") else "RK45",
+                                             rtol=kw.get("rtol", 1e-4), atol=kw.get("atol", 1e-6), tau=kw.get("tau") or 0.0,
+                                             var=var, model_arg=model._model_arg, dev=dev)
+            which = range(len(self.data)) if not self.initial_states else [k]
+            for i in which:
+                plan = self._plan[i]
+                engine.loglik(self._kinds[i], traj, float(t0), plan["columns"], plan["t_data"], plan["ydata"],
+                              ll_arg=self.log_likelihood_fnc_args[i], weight=self.weights[i], lp=lp_d, status=st_ll, dev=dev)
+        if int(st_ll.max()) & _ffi.ST_NONFINITE:
+            raise ValueError("simulation output contains nan, likely due to numerical unstability. try using more conservative bounds.")
+        if return_device:
+            return lp_d + torch.from_numpy(lp).to(dev)
+        return lp + lp_d.cpu().numpy()
+
+    def __call__(self, thetas):
+        thetas = np.asarray(thetas)
+        view = thetas.reshape(1, -1)                     # a view: clipping mutates the caller's array like the reference
+        return float(self.batch(view)[0])

@@ -1,0 +1,62 @@
+"""Multi-GPU plumbing: contiguous trajectory / particle shards, one process per GPU, collectives only at the end.
+
+The reference's only parallelism is a process pool over independent simulations
+(`/root/reference/src/pySODM/models/base.py:559-562`, `optimization/pso.py:152-183`): units never talk to each
+other.  On a B200 box the same units are sharded as contiguous ranges `[r*N/G, (r+1)*N/G)` over the ranks of a
+`torch.distributed` job (backend "nccl" on GPUs; "gloo" in the CPU tests); every rank runs its range with Philox
+streams keyed by the GLOBAL trajectory id, so the union of the shards is bit-identical to a single-GPU run, and the
+only communication is the final gather of results (`lp[P]` is 8 bytes per particle; full trajectory tensors are
+gathered only on request).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n_total, rank=None, world_size=None):
+    """Contiguous [lo, hi) of `n_total` units owned by `rank`; the first n_total % G ranks get one extra unit."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    base, extra = divmod(int(n_total), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def all_gather_concat(local, n_total, axis=0):
+    """Concatenate the ranks' shards along `axis` on every rank (shards may differ in length by one)."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    t = local if isinstance(local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local))
+    t = t.movedim(axis, 0).contiguous()
+    sizes = [shard_range(n_total, r, ws)[1] - shard_range(n_total, r, ws)[0] for r in range(ws)]
+    longest = max(sizes)
+    if t.shape[0] < longest:                                  # pad to a common length: all_gather needs equal shapes
+        pad = torch.zeros((longest - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        t = torch.cat([t, pad])
+    parts = [torch.empty_like(t) for _ in range(ws)]
+    dist.all_gather(parts, t)
+    out = torch.cat([p[:s] for p, s in zip(parts, sizes)]).movedim(0, axis)
+    return out if isinstance(local, torch.Tensor) else out.cpu().numpy()
+
+
+def batch_sharded(objective, thetas, **kw):
+    """`objective.batch` over a population sharded across the ranks; every rank returns the full lp[P]."""
+    import numpy as np
+    thetas = np.asarray(thetas)
+    lo, hi = shard_range(thetas.shape[0])
+    local = objective.batch(thetas[lo:hi], **kw) if hi > lo else np.zeros(0)
+    rank, ws = world()
+    if ws == 1:
+        return local
+    backend = dist.get_backend()
+    t = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
+    if backend == "nccl":
+        t = t.cuda()
+    return all_gather_concat(t, thetas.shape[0]).cpu().numpy()

@@ -155,7 +155,7 @@ def test_non_dyadic_tau_interpolates_like_reference(eng, golden):
     import torch
     from oracle import jump, models
     g = golden["jump_single"]
-    n = 8000
+    n = 16000
     tdpf = (g["flu_tau03_table"], g["flu_tau03_step_index"])
     out, st = eng.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, n, 0, 46, 0.3, tdpf=tdpf, seed=8,
                            out_dtype=torch.float64)
