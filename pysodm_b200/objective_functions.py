@@ -352,18 +352,26 @@ class log_posterior_probability:
                     if model._spec.tdpf_params and tdpf is None:
                         flat = np.concatenate([model._flat_param(nm, model.parameters[nm]) for nm in model._spec.tdpf_params])
                         tdpf = (flat[None, :], np.zeros(max(n_steps, 1), dtype=np.int32))
+                # only the rows the datasets look at leave the simulator; exact integer counts when tau = 2^-k
+                which_sets = range(len(self.data)) if not self.initial_states else [k]
+                needed = sorted({r for i in which_sets for c in self._plan[i]["columns"] for r in c})
+                remap = {r: j for j, r in enumerate(needed)}
+                inv = 1.0 / float(tau)
+                aligned = method == "tau_leap" and 0 < tau <= 1 and inv == int(inv) and (int(inv) & (int(inv) - 1)) == 0
                 traj, st = engine.jump_run(model.device_model, y, par, P, t0, n_out, tau, method=method, var=var,
                                            tdpf=tdpf, compat=kw.get("compat", _ffi.COMPAT_REFERENCE), seed=seed + k,
-                                           out_dtype=torch.float64, dev=dev)
+                                           out_dtype=torch.int32 if aligned else torch.float64, state_sel=needed, dev=dev)
                 model._raise_on_status(st)
             else:
                 traj, _, st = engine.ode_run(model.device_model, y, par, P, t0, n_out, method="euler" if kw.get("tau") else "RK45",
                                              rtol=kw.get("rtol", 1e-4), atol=kw.get("atol", 1e-6), tau=kw.get("tau") or 0.0,
                                              var=var, model_arg=model._model_arg, dev=dev)
+                remap = None
             which = range(len(self.data)) if not self.initial_states else [k]
             for i in which:
                 plan = self._plan[i]
-                engine.loglik(self._kinds[i], traj, float(t0), plan["columns"], plan["t_data"], plan["ydata"],
+                columns = plan["columns"] if remap is None else [[remap[r] for r in c] for c in plan["columns"]]
+                engine.loglik(self._kinds[i], traj, float(t0), columns, plan["t_data"], plan["ydata"],
                               ll_arg=self.log_likelihood_fnc_args[i], weight=self.weights[i], lp=lp_d, status=st_ll, dev=dev)
         if int(st_ll.max()) & _ffi.ST_NONFINITE:
             raise ValueError("simulation output contains nan, likely due to numerical unstability. try using more conservative bounds.")

@@ -1,0 +1,181 @@
+"""Host-side logic of the front end (no GPU): validation, time handling, draw collection, dataset container,
+alignment-plan construction.  Mirrors the API-contract assertions of the reference's tests."""
+from datetime import datetime
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from pysodm_b200 import registry, tutorial_data as td, tutorial_models as tm, validation
+from pysodm_b200.base import JumpProcess, ODE
+from pysodm_b200.dataset import SimpleDataArray, SimpleDataset, make_dataset
+
+
+def test_registry_matches_library():
+    registry.check_against_library()
+
+
+def test_simulation_time_forms():
+    """validation.py:77-116 of the reference."""
+    assert validation.simulation_time(50.4, "D") == ([0, 50], [None])
+    assert validation.simulation_time(50, "D") == ([0, 50], [None])
+    assert validation.simulation_time([10.2, 49.6], "D")[0] == [10, 50]
+    t, dates = validation.simulation_time(["2017-12-01", "2018-05-11"], "D")
+    assert t == [0, 161] and len(dates) == 162 and dates[0] == datetime(2017, 12, 1) and dates[-1] == datetime(2018, 5, 11)
+    t, dates = validation.simulation_time([datetime(2020, 1, 1), datetime(2020, 1, 29)], "W")
+    assert t == [0, 4] and len(dates) == 5
+    for bad, exc in [([1], ValueError), ([5, 1], ValueError), ([3, 3], ValueError), ("2020-01-01", TypeError),
+                     ([1, "2020-01-01"], ValueError)]:
+        with pytest.raises(exc):
+            validation.simulation_time(bad, "D")
+
+
+def test_model_declaration_errors():
+    class NoFunctor(ODE):
+        states = ["A"]
+        parameters = ["k"]
+
+        @staticmethod
+        def integrate(t, A, k):
+            return -k * A,
+    with pytest.raises(NotImplementedError, match="no CPU fallback"):
+        NoFunctor({"A": 1.0}, {"k": 0.1})
+    with pytest.raises(ValueError, match="Missing parameters"):
+        tm.ODE_SIR({"S": 1000, "I": 1}, {"beta": 0.35})
+    with pytest.raises(ValueError, match="Redundant parameters"):
+        tm.ODE_SIR({"S": 1000, "I": 1}, {"beta": 0.35, "gamma": 5, "zeta": 1})
+    with pytest.raises(ValueError, match="not model states"):
+        tm.ODE_SIR({"S": 1000, "X": 1}, {"beta": 0.35, "gamma": 5})
+    with pytest.raises(ValueError, match="desired shape"):
+        tm.JumpProcess_SIR_SI({"S": [1, 2, 3]}, td.SIRSI_PARAMETERS, coordinates={"age_group": td.AGE_GROUPS})
+    with pytest.raises(ValueError, match="stratified parameter 'alpha'"):
+        tm.JumpProcess_SIR_SI(td.SIRSI_INITIAL_STATES, dict(td.SIRSI_PARAMETERS, alpha=np.ones(3)),
+                              coordinates={"age_group": td.AGE_GROUPS})
+    with pytest.raises(ValueError, match="coordinates"):
+        tm.JumpProcess_SIR_SI(td.SIRSI_INITIAL_STATES, td.SIRSI_PARAMETERS)
+
+    class WrongSig(JumpProcess):
+        states = ["S", "I", "R"]
+        parameters = ["beta", "gamma"]
+        device_model = "sir_jump"
+
+        @staticmethod
+        def compute_rates(t, S, R, I, beta, gamma):
+            return {}
+
+        @staticmethod
+        def apply_transitionings(t, tau, transitionings, S, I, R, beta, gamma):
+            return S, I, R
+    with pytest.raises(ValueError, match="don't match the model's states"):
+        WrongSig({"S": 10}, {"beta": 1, "gamma": 1})
+
+
+def test_state_layout_and_flat_order():
+    m = tm.JumpProcess_SIR_SI(td.SIRSI_INITIAL_STATES, td.SIRSI_PARAMETERS, coordinates={"age_group": td.AGE_GROUPS})
+    assert dict(m.state_shapes) == {"S": (4,), "I": (4,), "R": (4,), "S_v": (), "I_v": ()}
+    assert m.dimensions_per_state["S_v"] == [] and m.dimensions_per_state["S"] == ["age_group"]
+    assert np.array_equal(m._flat_y0(m.initial_states), td.sirsi_flat_y0())
+    p = tm.packed_PFR(td.pfr_initial_states(25), td.pfr_parameters(25),
+                      {"species": ["S", "A", "Es", "W"], "x": np.linspace(0, 1, 25)})
+    assert p._model_arg == 25 and np.array_equal(p._flat_y0(p.initial_states), td.pfr_flat_y0(25))
+    par, var, y0, _ = p._collect_draws(1, None, {})
+    assert np.array_equal(par, td.pfr_flat_par(25)) and not var
+
+
+def test_draw_collection_and_icf():
+    m = tm.ODE_SIR({"S": 1000, "I": 1}, {"beta": 0.35, "gamma": 5})
+    betas = [0.3, 0.4, 0.5]
+    it = iter(betas)
+
+    def draw(parameters):
+        parameters["beta"] = next(it)
+        return parameters
+    par, var, y0, dicts = m._collect_draws(3, draw, {})
+    assert list(var) == [0] and np.array_equal(var[0], betas) and par[1] == 5 and y0.shape == (3,)
+
+    def icf(I0):
+        return {"S": 1000 - I0, "I": I0}
+
+    class WithICF(tm.ODE_SIR):
+        pass
+    m2 = WithICF(icf, {"beta": 0.35, "gamma": 5, "I0": 3})
+    assert m2.initial_states["I"] == 3 and m2.initial_states["S"] == 997
+
+    def draw_icf(parameters, N):
+        parameters["I0"] = np.arange(1, N + 1)
+        return parameters
+    draw_icf.vectorized = True
+    par, var, y0, _ = m2._collect_draws(4, draw_icf, {})
+    assert y0.shape == (3, 4) and np.array_equal(y0[1], [1, 2, 3, 4]) and np.array_equal(y0[0], [999, 998, 997, 996])
+    with pytest.raises(ValueError, match="must have 'parameters' as its first input"):
+        validation.draw_function(lambda pars: pars, {}, {}, None, {}, [])
+    with pytest.raises(ValueError, match="forgotten to pass `draw_function_kwargs`"):
+        validation.draw_function(lambda parameters, x: parameters, {}, {}, None, {}, [])
+
+
+def test_tdpf_tabulation_and_state_dependence_check():
+    m = tm.JumpProcess_influenza_model(td.INFLUENZA_INITIAL_STATES, td.INFLUENZA_PARAMETERS,
+                                       coordinates={"age_group": td.AGE_GROUPS},
+                                       time_dependent_parameters={"N": td.influenza_contact_function})
+    table, index = m._tabulate_tdpfs(0, 322, 0.5, datetime(2017, 12, 1), "D")
+    assert table.shape == (3, 16) and np.array_equal(index, td.influenza_schedule())
+    assert np.array_equal(table[index[0]].reshape(4, 4), td.CONTACT_TABLE[0])
+
+    def state_dependent(t, states, param):
+        return param * (1 + states["S"].sum())
+    bad = tm.JumpProcess_influenza_model(td.INFLUENZA_INITIAL_STATES, td.INFLUENZA_PARAMETERS,
+                                         coordinates={"age_group": td.AGE_GROUPS},
+                                         time_dependent_parameters={"N": state_dependent})
+    with pytest.raises(NotImplementedError, match="depends on the model states"):
+        bad._tabulate_tdpfs(0, 10, 0.5, None, "D")
+    with pytest.raises(NotImplementedError, match="no time-dependent slot"):
+        tm.JumpProcess_influenza_model(td.INFLUENZA_INITIAL_STATES, td.INFLUENZA_PARAMETERS,
+                                       coordinates={"age_group": td.AGE_GROUPS},
+                                       time_dependent_parameters={"beta": lambda t, states, param: param})
+
+
+def test_dataset_container():
+    vals = np.arange(2 * 3 * 4, dtype=float).reshape(2, 3, 4)
+    ds = make_dataset({"S": vals, "T": vals[:, :, 0]}, {"S": ["age"], "T": []}, {"S": [["a", "b", "c", "d"]], "T": []},
+                      "time", np.arange(3), 2)
+    assert tuple(ds["S"].dims) == ("draws", "time", "age")
+    assert ds["S"].sel(age="c").values.shape == (2, 3) and ds["S"].sel(age="c").values[1, 2] == vals[1, 2, 2]
+    assert ds["S"].isel(time=-1).values.shape == (2, 4)
+    assert ds["S"].mean(dim="draws").values.shape == (3, 4)
+    assert np.allclose(ds["S"].quantile(dim="draws", q=0.5).values, np.median(vals, axis=0))
+    assert ds["S"].sum(dim="age").values.shape == (2, 3)
+    assert np.array_equal(np.asarray(ds["time"]), np.arange(3))
+    one = make_dataset({"S": vals[0]}, {"S": ["age"]}, {"S": [["a", "b", "c", "d"]]}, "time", np.arange(3), 1)
+    assert tuple(one["S"].dims) == ("time", "age")
+
+
+def test_alignment_plan():
+    from pysodm_b200.objective_functions import (ll_negative_binomial, ll_normal, ll_poisson,
+                                                 log_posterior_probability, log_prior_normal)
+    m = tm.JumpProcess_influenza_model(td.INFLUENZA_INITIAL_STATES, td.INFLUENZA_PARAMETERS,
+                                       coordinates={"age_group": td.AGE_GROUPS},
+                                       time_dependent_parameters={"N": td.influenza_contact_function})
+    dates = pd.date_range("2017-12-08", periods=5, freq="7D")
+    idx = pd.MultiIndex.from_product([td.AGE_GROUPS[1:3], dates], names=["age_group", "date"])   # age first, subset
+    data = pd.Series(np.arange(10.0), index=idx)
+    lpp = log_posterior_probability(m, ["beta", "f_ud"], [(1e-6, 0.08), (1e-3, 0.999)], [data, data.groupby(level="date").sum()],
+                                    ["Im_inc", "Id"], [ll_negative_binomial, ll_poisson], [[0.03, 0.04], []],
+                                    start_sim="2017-12-01", weights=[1, 0.5])
+    plan = lpp._plan[0]
+    assert plan["columns"] == [[25], [26]]                         # Im_inc rows 24..27, age groups 1 and 2
+    assert np.array_equal(plan["t_data"], [7, 14, 21, 28, 35])
+    assert np.array_equal(plan["ydata"], np.arange(10.0).reshape(2, 5).T)         # (time, age) order
+    assert lpp._plan[1]["columns"] == [[16, 17, 18, 19]]          # Id summed over age
+    assert lpp.n_theta == 5 and lpp.expanded_bounds[1] == (1e-3, 0.999)
+    lp = lpp.compute_log_prior_probability(np.array([[0.01, .5, .5, .5, .5], [0.2, .5, .5, .5, .5]]))
+    assert lp[0] == 0 and lp[1] == -np.inf
+    lpp2 = log_posterior_probability(m, ["beta"], [(1e-6, 0.08)], [data], ["Im_inc"], [ll_normal], [3.0],
+                                     log_prior_prob_fnc=[log_prior_normal], log_prior_prob_fnc_args=[{"avg": 0.02, "stdev": 0.01}])
+    from scipy.stats import norm
+    assert lpp2.compute_log_prior_probability([[0.03]])[0] == pytest.approx(norm.logpdf(0.03, 0.02, 0.01))
+    with pytest.raises(Exception, match="not a valid model parameter"):
+        log_posterior_probability(m, ["zeta"], [(0, 1)], [data], ["Im_inc"], [ll_poisson], [[]])
+    with pytest.raises(NotImplementedError, match="no device implementation"):
+        log_posterior_probability(m, ["beta"], [(0, 1)], [data], ["Im_inc"], [lambda a, b: 0.0], [[]])
+    with pytest.raises(ValueError, match="must be of equal length"):
+        log_posterior_probability(m, ["beta"], [(0, 1)], [data], ["Im_inc", "S"], [ll_poisson], [[]])

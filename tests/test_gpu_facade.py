@@ -1,0 +1,214 @@
+"""GPU tests of the pySODM-style front end: `JumpProcess.sim`, `ODE.sim`, `log_posterior_probability` (API contract
+of the reference's own tests -- shapes, dims, initial-value echo, loose dynamics -- plus parity against the oracle)."""
+from datetime import datetime
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def td():
+    from pysodm_b200 import tutorial_data
+    return tutorial_data
+
+
+def _influenza(td):
+    from pysodm_b200 import tutorial_models as tm
+    return tm.JumpProcess_influenza_model(td.INFLUENZA_INITIAL_STATES, td.INFLUENZA_PARAMETERS,
+                                          coordinates={"age_group": td.AGE_GROUPS},
+                                          time_dependent_parameters={"N": td.influenza_contact_function})
+
+
+def test_jump_sim_single_and_draws(td, golden):
+    """Reference contract (src/tests/test_JumpProcess.py:144-151, :374-376, :508-512): dims, coords, S[0] echo."""
+    model = _influenza(td)
+    np.random.seed(3)
+    out = model.sim([td.INFLUENZA_START, td.INFLUENZA_END], tau=0.5)
+    S = out["S"]
+    assert tuple(S.dims) == ("date", "age_group") and S.values.shape == (162, 4)
+    assert list(out["date"][:2]) == [datetime(2017, 12, 1), datetime(2017, 12, 2)]
+    assert np.array_equal(S.values[0], td.INFLUENZA_INITIAL_STATES["S"])
+    assert S.values.dtype == np.float64
+    before = dict(model.parameters)
+
+    def draw_fcn(parameters, spread):
+        parameters["beta"] = 0.0174 * np.random.uniform(1 - spread, 1 + spread)
+        return parameters
+
+    n = 512
+    out = model.sim([td.INFLUENZA_START, td.INFLUENZA_END], N=n, tau=0.5, draw_function=draw_fcn,
+                    draw_function_kwargs={"spread": 0.05}, output_dtype="int32", processes=4)
+    Im = out["Im_inc"]
+    assert tuple(Im.dims) == ("draws", "date", "age_group") and Im.values.shape == (n, 162, 4)
+    assert Im.values.dtype == np.int32
+    assert model.parameters["beta"] == before["beta"]                       # parameters restored (base.py:548,574)
+    e = golden["jump_ensemble"]
+    # beta jitter of +-5 % around the tutorial value: ensemble mean stays within a few % of the reference's
+    ref_mean = e["flu_mean"][24:28].T                                       # [time, age]
+    rel = np.abs(Im.values.mean(axis=0)[30:120] - ref_mean[30:120]) / (ref_mean[30:120] + 5)
+    assert np.median(rel) < 0.15
+    mean_via_api = out["Im_inc"].mean(dim="draws")
+    assert mean_via_api.values.shape == (162, 4)
+    sel = out["Im_inc"].sel(age_group=td.AGE_GROUPS[2]).isel(draws=0)
+    assert sel.values.shape == (162,)
+
+
+def test_jump_sim_vectorized_draws_and_seed_reproducibility(td):
+    model = _influenza(td)
+
+    def draw(parameters, N):
+        rng = np.random.default_rng(0)
+        parameters["beta"] = rng.uniform(0.015, 0.02, size=N)
+        parameters["f_ud"] = np.clip(parameters["f_ud"][None, :] * rng.uniform(0.9, 1.1, size=(N, 4)), 1e-3, 0.999)
+        return parameters
+    draw.vectorized = True
+    a = model.sim(30, N=300, tau=0.5, draw_function=draw, seed=11, output_dtype="int32", chunk=128)
+    b = model.sim(30, N=300, tau=0.5, draw_function=draw, seed=11, output_dtype="int32", chunk=300)
+    assert tuple(a["S"].dims) == ("draws", "time", "age_group")
+    assert np.array_equal(np.asarray(a["time"]), np.arange(31))
+    for s in ("S", "E", "Im_inc"):
+        assert np.array_equal(a[s].values, b[s].values)                     # chunking does not change the result
+    c = model.sim(30, N=300, tau=0.5, draw_function=draw, seed=12, output_dtype="int32")
+    assert not np.array_equal(a["E"].values, c["E"].values)
+    sub = model.sim(30, N=8, tau=0.5, states=["Im_inc", "S"], output_dtype="float32")
+    assert list(sub.keys()) == ["Im_inc", "S"]
+
+
+def test_sir_si_mixed_state_shapes_and_ssa(td):
+    from pysodm_b200 import tutorial_models as tm
+    model = tm.JumpProcess_SIR_SI(td.SIRSI_INITIAL_STATES, td.SIRSI_PARAMETERS, coordinates={"age_group": td.AGE_GROUPS})
+    out = model.sim(50, N=4, tau=0.5)
+    assert out["S"].values.shape == (4, 51, 4) and out["S_v"].values.shape == (4, 51)
+    assert tuple(out["I_v"].dims) == ("draws", "time")
+    small = tm.JumpProcess_SIR_SI({"S": [607, 1329, 7352, 2204], "S_v": 1000, "I_v": 2}, td.SIRSI_PARAMETERS,
+                                  coordinates={"age_group": td.AGE_GROUPS})
+    out = small.sim(20, N=64, method="SSA")
+    assert out["S"].values.shape == (64, 21, 4)
+    assert np.any(out["I"].values != np.round(out["I"].values))               # F3: SSA output is interpolated
+    with pytest.raises(ValueError, match="invalid solution method"):
+        model.sim(10, method="euler")
+    with pytest.raises(TypeError, match="'tau' must be of type int or float"):
+        model.sim(10, tau="0.5")
+    with pytest.raises(ValueError, match="start of simulation is chronologically after"):
+        model.sim([10, 5])
+
+
+def test_ode_sim_contract_and_parity(td, golden):
+    from pysodm_b200 import tutorial_models as tm
+    g = golden["ode"]
+    model = tm.ODE_SIR({"S": 1000, "I": 1}, {"beta": 0.35, "gamma": 5})
+    out = model.sim(120)
+    assert tuple(out["S"].dims) == ("time",) and out["S"].values.shape == (121,)
+    ref = g["sir_y"][np.argmin(np.abs(g["sir_betas"] - 0.35))]          # not the same beta: only a sanity bound
+    assert abs(out["S"].values[-1] - ref[0, -1]) / ref[0, -1] < 0.5
+    betas = g["sir_betas"]
+    it = iter(betas)
+
+    def draw_fcn(parameters):
+        parameters["beta"] = next(it)
+        return parameters
+    # the draw function is called once for validation, then N times (Q12): start the iterator one early
+    it = iter(np.concatenate([[betas[0]], betas]))
+    out = model.sim(120, N=100, draw_function=draw_fcn)
+    y = np.stack([out[s].values for s in ("S", "I", "R")], axis=1)          # [draws, state, time]
+    np.testing.assert_allclose(y, g["sir_y"], rtol=1e-6, atol=1e-9)
+    assert np.array_equal(model.last_nfev.cpu().numpy(), g["sir_nfev"])
+    with pytest.raises(ValueError, match="without using a draw function"):
+        model.sim(10, N=5)
+    with pytest.raises(NotImplementedError, match="no device implementation"):
+        model.sim(10, method="LSODA")
+    eu = model.sim(60, tau=0.25)
+    np.testing.assert_allclose(eu["I"].values, g["sir_euler_y"][1], rtol=1e-12)
+
+
+def test_packed_pfr_last_profile(td, golden):
+    from pysodm_b200 import tutorial_models as tm
+    g = golden["ode"]
+    nx = 25
+    model = tm.packed_PFR(td.pfr_initial_states(nx), td.pfr_parameters(nx),
+                          {"species": ["S", "A", "Es", "W"], "x": np.linspace(0, 1, nx)})
+    post = g["pfr_posterior"]
+
+    def draw(parameters, N):
+        pick = g["pfr25_pick"]
+        for j, k in enumerate(("Vf_Ks", "R_AS", "R_AW", "R_Es", "K_eq")):
+            parameters[k] = post[pick, j]
+        return parameters
+    draw.vectorized = True
+    out = model.sim(8000, N=4, draw_function=draw, output_last_only=True)
+    cf = out["C_F"]
+    assert tuple(cf.dims) == ("draws", "time", "species", "x") and cf.values.shape == (4, 1, 4, nx)
+    ref = g["pfr25_y"][:, :, -1]                                             # [draw, 200]
+    np.testing.assert_allclose(cf.values[:, 0].reshape(4, -1), ref[:, :100], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(out["C_S"].values[:, 0].reshape(4, -1), ref[:, 100:], rtol=1e-6, atol=1e-7)
+
+
+def test_log_posterior_batch_matches_oracle(td):
+    """Config C5 in miniature: NB log-posterior of P particles; same trajectories scored by the oracle."""
+    import torch
+    from oracle import loglik as oll
+    from pysodm_b200 import engine
+    from pysodm_b200.objective_functions import ll_negative_binomial, ll_poisson, log_posterior_probability
+    model = _influenza(td)
+    dates = pd.date_range("2017-12-01", periods=13, freq="7D")
+    idx = pd.MultiIndex.from_product([dates, td.AGE_GROUPS], names=["date", "age_group"])
+    rng = np.random.default_rng(0)
+    data = pd.Series(rng.gamma(2.0, 150.0, size=len(idx)), index=idx, name="CASES")
+    lpp = log_posterior_probability(model, ["beta", "f_ud"], [(1e-6, 0.08), (1e-3, 1 - 1e-3)], [data], ["Im_inc"],
+                                    [ll_negative_binomial], [4 * [0.03]], simulation_kwargs={"tau": 0.5})
+    assert lpp.expanded_labels == ["beta", "f_ud_0", "f_ud_1", "f_ud_2", "f_ud_3"]
+    assert lpp.start_sim == datetime(2017, 12, 1) and lpp.end_sim == dates[-1].to_pydatetime()
+    P = 257
+    thetas = np.column_stack([rng.uniform(0.01, 0.03, P), rng.uniform(0.05, 0.95, size=(P, 4))])
+    thetas[0, 0] = 0.5                                                       # out of bounds: clipped, -inf (Q15)
+    lp = lpp.batch(thetas, seed=77)
+    assert lp.shape == (P,) and lp[0] == -np.inf and thetas[0, 0] == 0.08
+    assert np.isfinite(lp[1:]).all()
+    # the same trajectories, regenerated with the same seed, scored on the host by the oracle
+    var = {1: thetas[:, 0], 4: thetas[:, 1], 5: thetas[:, 2], 6: thetas[:, 3], 7: thetas[:, 4]}
+    n_out = 85
+    traj, _ = engine.jump_run("influenza_1718_jump", td.influenza_flat_y0(), td.influenza_flat_par(), P, 0, n_out, 0.5,
+                              var=var, tdpf=(td.CONTACT_TABLE.reshape(3, 16), td.influenza_schedule(n_steps=168)),
+                              seed=77, out_dtype=torch.float64)
+    traj = traj.cpu().numpy()
+    ydata = data.to_numpy().reshape(13, 4)
+    want = np.array([oll.log_likelihood("negative_binomial", traj[24:28, :, i], 0.0, [[0], [1], [2], [3]],
+                                        np.arange(13) * 7.0, ydata, 4 * [0.03]) for i in range(P)])
+    np.testing.assert_allclose(lp[1:], want[1:], rtol=1e-9)
+    single = lpp(thetas[5].copy())
+    assert np.isfinite(single)
+    # aggregated data (no age axis): the model's age dimension is summed (objective_functions.py:250-252)
+    total = data.groupby(level="date").sum()
+    lpp2 = log_posterior_probability(model, ["beta"], [(1e-6, 0.08)], [total], ["Im_inc"], [ll_poisson], [[]],
+                                     simulation_kwargs={"tau": 0.5})
+    lp2 = lpp2.batch(thetas[:9, :1].copy(), seed=5)
+    traj2, _ = engine.jump_run("influenza_1718_jump", td.influenza_flat_y0(), td.influenza_flat_par(), 9, 0, n_out, 0.5,
+                               var={1: thetas[:9, 0]}, tdpf=(td.CONTACT_TABLE.reshape(3, 16), td.influenza_schedule(n_steps=168)),
+                               seed=5, out_dtype=torch.float64)
+    traj2 = traj2.cpu().numpy()
+    want2 = [oll.log_likelihood("poisson", traj2[:, :, i], 0.0, [[24, 25, 26, 27]], np.arange(13) * 7.0,
+                                total.to_numpy()[:, None]) for i in range(9)]
+    np.testing.assert_allclose(lp2, want2, rtol=1e-9)
+
+
+def test_log_posterior_ode_time_index(td):
+    """`time`-indexed data at non-integer times (src/tests/test_calibration.py:20-36) on an ODE model."""
+    from oracle import loglik as oll, models, ode
+    from pysodm_b200 import tutorial_models as tm
+    from pysodm_b200.objective_functions import ll_normal, log_posterior_probability
+    model = tm.ODE_SIR_rate({"S": 1_000_000 - 10, "I": 10}, {"beta": 0.9, "gamma": 0.2})
+    t = np.linspace(50, 60, 20)
+    data = pd.Series(np.linspace(4000, 900, 20), index=pd.Index(t, name="time"))
+    lpp = log_posterior_probability(model, ["beta"], [(0.1, 2.0)], [data], ["I"], [ll_normal], [250.0], start_sim=0)
+    betas = np.array([[0.7], [0.9], [1.1]])
+    lp = lpp.batch(betas.copy())
+    want = []
+    for b in betas[:, 0]:
+        _, y, _ = ode.simulate(models.SIRRateODE, [1_000_000 - 10, 10, 0], {"beta": b, "gamma": 0.2}, 0, 60)
+        want.append(oll.log_likelihood("normal", y, 0.0, [[1]], t, data.to_numpy(), 250.0))
+    np.testing.assert_allclose(lp, want, rtol=1e-6)       # ODE trajectories agree to ~1e-12; ll amplifies by < 1e3
