@@ -67,16 +67,21 @@ def test_jump_sim_vectorized_draws_and_seed_reproducibility(td):
         parameters["f_ud"] = np.clip(parameters["f_ud"][None, :] * rng.uniform(0.9, 1.1, size=(N, 4)), 1e-3, 0.999)
         return parameters
     draw.vectorized = True
-    a = model.sim(30, N=300, tau=0.5, draw_function=draw, seed=11, output_dtype="int32", chunk=128)
-    b = model.sim(30, N=300, tau=0.5, draw_function=draw, seed=11, output_dtype="int32", chunk=300)
-    assert tuple(a["S"].dims) == ("draws", "time", "age_group")
-    assert np.array_equal(np.asarray(a["time"]), np.arange(31))
+    span = ["2017-12-01", "2017-12-31"]                      # the tutorial's contact function needs dates
+    a = model.sim(span, N=300, tau=0.5, draw_function=draw, seed=11, output_dtype="int32", chunk=128)
+    b = model.sim(span, N=300, tau=0.5, draw_function=draw, seed=11, output_dtype="int32", chunk=300)
+    assert tuple(a["S"].dims) == ("draws", "date", "age_group") and a["S"].values.shape == (300, 31, 4)
     for s in ("S", "E", "Im_inc"):
         assert np.array_equal(a[s].values, b[s].values)                     # chunking does not change the result
-    c = model.sim(30, N=300, tau=0.5, draw_function=draw, seed=12, output_dtype="int32")
+    c = model.sim(span, N=300, tau=0.5, draw_function=draw, seed=12, output_dtype="int32")
     assert not np.array_equal(a["E"].values, c["E"].values)
-    sub = model.sim(30, N=8, tau=0.5, states=["Im_inc", "S"], output_dtype="float32")
+    sub = model.sim(span, N=8, tau=0.5, states=["Im_inc", "S"], output_dtype="float32")
     assert list(sub.keys()) == ["Im_inc", "S"]
+    from pysodm_b200 import tutorial_models as tm
+    sir = tm.JumpProcess_SIR({"S": 1_000_000 - 10, "I": 10}, {"beta": 0.9, "gamma": 0.2})
+    out = sir.sim(50, N=64, tau=1)                            # integer 'time' axis (src/tests/test_JumpProcess.py:144-151)
+    assert tuple(out["S"].dims) == ("draws", "time") and np.array_equal(np.asarray(out["time"]), np.arange(51))
+    assert (out["S"].values[:, 0] == 1_000_000 - 10).all() and np.median(out["S"].values[:, -1]) < 12000
 
 
 def test_sir_si_mixed_state_shapes_and_ssa(td):
