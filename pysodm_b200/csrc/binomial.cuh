@@ -164,6 +164,83 @@ __host__ __device__ __forceinline__ bool btrs_try(Rng& rng, int n, float p, int&
     return (double)lhs <= binomial_log_ratio(nd, pd, floor((nd + 1.0) * pd), (double)k);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Building blocks of the PHASED work-list sampler (jump_run.cuh): the same BTRS / squeeze / exact test /
+// inversion as above, split so that each phase of a step runs ONE of them on all lanes that need it.
+// ------------------------------------------------------------------------------------------------
+enum : int { BIN_DONE = 0, BIN_INVERT = 1, BIN_EXACT = 2, BIN_RETRY = 3, BIN_BTRS = 4 };
+
+// Trivial cases and regime of Bin(n, p): BIN_DONE (k set; -1 = invalid arguments), BIN_INVERT or BIN_BTRS.
+__host__ __device__ __forceinline__ int binomial_classify(int n, float p, int& k) {
+    if (!(p >= 0.0f && p <= 1.0f) || n < 0) { k = -1; return BIN_DONE; }
+    const bool flip = p > 0.5f;
+    const float pp = flip ? 1.0f - p : p;
+    if (n == 0 || pp == 0.0f) { k = flip ? n : 0; return BIN_DONE; }
+    return ((float)n * pp < SODM_BINV_THRESHOLD) ? BIN_INVERT : BIN_BTRS;
+}
+
+// Sequential-search inversion driven by a given uniform word (0 < p <= 0.5, n*p small).
+__host__ __device__ __forceinline__ int binomial_inversion_word(int n, float p, uint32_t word) {
+    const float s = p / (1.0f - p);
+    float f = expf((float)n * log1pf(-p));
+    float u = u01(word);
+    int k = 0;
+    while (u > f && k < n && k < 1024) {
+        u -= f;
+        ++k;
+        f *= s * (float)(n - k + 1) / (float)k;
+    }
+    return k;
+}
+
+// One BTRS attempt from two random words (0 < p <= 0.5, n*p >= 10): BIN_DONE (k accepted), BIN_RETRY (rejected) or
+// BIN_EXACT (the squeeze could not settle candidate k; `lhs` = log of the scaled uniform to compare with log f(k)/f(m)).
+__host__ __device__ __forceinline__ int btrs_attempt_words(int n, float p, uint32_t wu, uint32_t wv, int& k, float& lhs) {
+    const float nf = (float)n;
+    const float np_ = nf * p;
+    const float npq = np_ * (1.0f - p);
+    const float stddev = sqrtf(npq);
+    const float b = 1.15f + 2.53f * stddev;
+    const float a = -0.0873f + 0.0248f * b + 0.01f * p;
+    const float inv_b = 1.0f / b;
+    const float v_r = 0.92f - 4.2f * inv_b;
+    const float u = u01(wu) - 0.5f;
+    const float v = u01(wv);
+    const float us = 0.5f - fabsf(u);
+    float kf;
+    if (np_ < 4194304.0f) {
+        kf = floorf(fmaf(2.0f * a / us + b, u, np_ + 0.5f));
+        k = (int)kf;
+    } else {
+        const double kd = floor(fma((double)(2.0f * a / us + b), (double)u, fma((double)n, (double)p, 0.5)));
+        k = (int)fmin(fmax(kd, -1.0), 2147483647.0);
+        kf = (float)kd;
+    }
+    if (us >= 0.07f && v <= v_r) return BIN_DONE;
+    if (k < 0 || k > n) return BIN_RETRY;
+    const float alpha = (2.83f + 5.1f * inv_b) * stddev;
+    lhs = logf(v * alpha / (a / (us * us) + b));
+    const float mf = floorf((nf + 1.0f) * p);
+    const float x = fabsf(kf - mf);
+    if (x < 0.5f * npq - 1.0f) {
+        const float t = -x * x / (2.0f * npq);
+        const float rho = (x / npq) * ((x * (x * (1.0f / 3.0f) + 0.625f) + (1.0f / 6.0f)) / npq + 0.5f);
+        const float eps = 4e-6f * (1.0f + fabsf(t) + fabsf(lhs));
+        if (lhs < t - rho - eps) return BIN_DONE;
+        if (lhs > t + rho + eps) return BIN_RETRY;
+    }
+    return BIN_EXACT;
+}
+
+// The exact acceptance test of candidate k (FP32 where harmless, FP64 otherwise).
+__host__ __device__ __forceinline__ bool btrs_exact_accept(int n, float p, int k, float lhs) {
+    const float nf = (float)n;
+    const float mf = floorf((nf + 1.0f) * p);
+    if (mf < SODM_F32_MODE_LIMIT && nf < 16777216.0f) return lhs <= binomial_log_ratio_f32(nf, p, mf, (float)k);
+    const double nd = (double)n, pd = (double)p;
+    return (double)lhs <= binomial_log_ratio(nd, pd, floor((nd + 1.0) * pd), (double)k);
+}
+
 // ONE attempt at Bin(n, p), 0 <= p <= 1.  Returns true when finished with the variate in k.
 // NaN / out-of-range p or n < 0 finish with k = -1 (the reference's NumPy call raises ValueError there;
 // callers turn -1 into a status flag).

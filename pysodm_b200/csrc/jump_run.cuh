@@ -10,6 +10,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include "jump_models.cuh"
 
 namespace sodm {
@@ -17,7 +18,7 @@ namespace sodm {
 constexpr int MAX_PARAM = 32;   // flat parameter elements passed by value
 constexpr int MAX_STATE = 32;   // flat state elements of a jump model
 
-enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, COMPAT_WALK_DECOUPLED = 256u };
+enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, COMPAT_WALK_DECOUPLED = 256u, COMPAT_WALK_LOCKSTEP = 512u };
 
 struct JumpLaunch {
     int64_t n_traj;            // trajectories in this launch
@@ -107,11 +108,156 @@ __host__ __device__ __forceinline__ void emit_interp(const JumpLaunch& L, int64_
 struct WorkList {
     int* n;
     float* p;
+    uint32_t* a;        // phased sampler scratch: random word / BTRS candidate of a pending slot
+    uint32_t* b;        //                         random word / log of the scaled uniform of a pending slot
     int stride;
     unsigned lanes;     // device: lanes of this warp that run a trajectory (mask for __syncwarp)
     __host__ __device__ __forceinline__ void put(int d, int nd, float pd) { n[d * stride] = nd; p[d * stride] = pd; }
     __host__ __device__ __forceinline__ int get(int d) const { return n[d * stride]; }
 };
+
+__host__ __device__ __forceinline__ int lowest_bit(uint32_t m) {
+#ifdef __CUDA_ARCH__
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
+__host__ __device__ __forceinline__ float word_as_float(uint32_t w) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(w);
+#else
+    float f; memcpy(&f, &w, 4); return f;
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t float_as_word(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t w; memcpy(&w, &f, 4); return w;
+#endif
+}
+
+// dependency level of every slot: 0 = independent, L = conditional on a slot of level L-1 (bit d of DEP_MASK:
+// slot d's n is what slot d-1 left behind)
+constexpr uint32_t level_mask(uint32_t dep_mask, int ndraw, int level) {
+    uint32_t out = 0u;
+    int run = 0;
+    for (int d = 0; d < ndraw; ++d) {
+        run = ((dep_mask >> d) & 1u) ? run + 1 : 0;
+        if (run == level) out |= 1u << d;
+    }
+    return out;
+}
+constexpr int max_level(uint32_t dep_mask, int ndraw) {
+    int best = 0, run = 0;
+    for (int d = 0; d < ndraw; ++d) {
+        run = ((dep_mask >> d) & 1u) ? run + 1 : 0;
+        best = run > best ? run : best;
+    }
+    return best;
+}
+
+// PHASED sampler (default).  The cost of a divergent SIMT loop is (trips) x (union of the branches any lane takes), so
+// a step's draws are organised in phases whose bodies are homogeneous:
+//   A  first pass, uniform over the warp: one Philox block per two slots; every slot is classified (trivial /
+//      inversion regime / BTRS regime) and BTRS slots get their first attempt.  ~80 % of them finish here.
+//   X  the candidates the squeeze could not settle: exact log-pmf test, lanes pop their own pending slots;
+//   R  rejected slots: fresh attempts from a second Philox stream until accepted (lanes pop their own slots);
+//   I  inversion-regime slots: sequential search, lanes pop their own slots.
+// Slots conditional on another slot (DEP_MASK) run as a second level after their predecessors are final; their random
+// words are drawn in the first level's pass A and parked in the scratch arrays.
+template <int NDRAW, uint32_t DEP_MASK, class Rng>
+__host__ __device__ __forceinline__ void sample_worklist_phased(Philox4x32& first, Rng& retry, WorkList& w, uint32_t& st) {
+    static_assert(NDRAW <= 32, "at most 32 draws per step");
+    constexpr int LEVELS = max_level(DEP_MASK, NDRAW) + 1;
+    const int S = w.stride;
+#pragma unroll
+    for (int level = 0; level < LEVELS; ++level) {
+        const uint32_t in_level = level_mask(DEP_MASK, NDRAW, level);
+        uint32_t inv = 0u, exact = 0u, again = 0u;
+        // ---- phase A --------------------------------------------------------------------------------------
+        uint32_t blk[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+        for (int d = 0; d < NDRAW; ++d) {
+            uint32_t wu, wv;
+            if (level == 0) {
+                if ((d & 1) == 0) first.next4(blk);
+                wu = (d & 1) ? blk[2] : blk[0];
+                wv = (d & 1) ? blk[3] : blk[1];
+                if (!((in_level >> d) & 1u)) {            // a later level's slot: park its words
+                    w.a[d * S] = wu;
+                    w.b[d * S] = wv;
+                    continue;
+                }
+            } else {
+                if (!((in_level >> d) & 1u)) continue;
+                wu = w.a[d * S];
+                wv = w.b[d * S];
+            }
+            int n = w.n[d * S];
+            const float p = w.p[d * S];
+            if (level > 0) { n -= w.n[(d - 1) * S]; w.n[d * S] = n; }     // what the previous exit left behind
+            int k;
+            int state = binomial_classify(n, p, k);
+            if (state == BIN_BTRS) {
+                const bool flip = p > 0.5f;
+                float lhs = 0.0f;
+                state = btrs_attempt_words(n, flip ? 1.0f - p : p, wu, wv, k, lhs);
+                if (state == BIN_DONE) k = flip ? n - k : k;
+                else if (state == BIN_EXACT) { w.a[d * S] = (uint32_t)k; w.b[d * S] = float_as_word(lhs); exact |= 1u << d; }
+                else again |= 1u << d;
+            } else if (state == BIN_INVERT) {
+                w.a[d * S] = wu;
+                inv |= 1u << d;
+            }
+            if (state == BIN_DONE) {
+                if (k < 0) { st |= ST_BAD_PROB; k = 0; }
+                w.n[d * S] = k;
+            }
+        }
+        // ---- phases X + R: settle ambiguous candidates, re-draw rejected ones ------------------------------
+        while (exact | again) {
+            if (exact) {
+                const int d = lowest_bit(exact);
+                const uint32_t bit = 1u << d;
+                const int n = w.n[d * S];
+                const float p = w.p[d * S];
+                const bool flip = p > 0.5f;
+                const int k = (int)w.a[d * S];
+                exact &= ~bit;
+                if (btrs_exact_accept(n, flip ? 1.0f - p : p, k, word_as_float(w.b[d * S]))) w.n[d * S] = flip ? n - k : k;
+                else again |= bit;
+            }
+            if (again) {
+                const int d = lowest_bit(again);
+                const uint32_t bit = 1u << d;
+                const int n = w.n[d * S];
+                const float p = w.p[d * S];
+                const bool flip = p > 0.5f;
+                int k;
+                float lhs = 0.0f;
+                const uint32_t wu = retry.next(), wv = retry.next();
+                const int state = btrs_attempt_words(n, flip ? 1.0f - p : p, wu, wv, k, lhs);
+                if (state == BIN_DONE) { w.n[d * S] = flip ? n - k : k; again &= ~bit; }
+                else if (state == BIN_EXACT) { w.a[d * S] = (uint32_t)k; w.b[d * S] = float_as_word(lhs); exact |= bit; again &= ~bit; }
+            }
+        }
+        // ---- phase I: inversion-regime slots ----------------------------------------------------------------
+        while (inv) {
+            const int d = lowest_bit(inv);
+            inv &= inv - 1u;
+            const int n = w.n[d * S];
+            const float p = w.p[d * S];
+            const bool flip = p > 0.5f;
+            const int k = binomial_inversion_word(n, flip ? 1.0f - p : p, w.a[d * S]);
+            w.n[d * S] = flip ? n - k : k;
+        }
+#ifdef __CUDA_ARCH__
+        __syncwarp(w.lanes);
+#endif
+    }
+}
 
 // Draws every slot of the list.
 //   lockstep (default): all lanes of the warp are at the SAME slot -- i.e. the same compartment and age group of
@@ -121,7 +267,7 @@ struct WorkList {
 //     at the price of lanes drifting to different slots and hence different sampler branches.
 // Which one wins is a measurement (profiles/): on influenza the lockstep walk executes ~5x fewer warp instructions.
 template <int NDRAW, uint32_t DEP_MASK, class Rng>
-__host__ __device__ __forceinline__ void sample_worklist(Rng& rng, WorkList& w, uint32_t& st, bool decoupled) {
+__host__ __device__ __forceinline__ void sample_worklist_walk(Rng& rng, WorkList& w, uint32_t& st, bool decoupled) {
     int prev = 0;
     if (!decoupled) {
 #pragma unroll 1
@@ -163,11 +309,13 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
     uint32_t st = ST_OK;
     load_trajectory<M>(L, i, par, y, st);
     const bool quirk = (L.compat & COMPAT_STAY_QUIRK) != 0u;
-    const bool decoupled = (L.compat & COMPAT_WALK_DECOUPLED) != 0u;
+    const uint32_t walk = L.compat & (COMPAT_WALK_DECOUPLED | COMPAT_WALK_LOCKSTEP);
     const float tau = (float)L.tau;
     const typename M::Pre pre = M::prepare(par, tau, quirk);
-    PhiloxWords rng;
+    PhiloxWords rng;                       // stream 0: re-draws (phased sampler) / every draw (walk samplers)
     rng.init(L.seed, (uint64_t)(L.traj_id0 + i));
+    Philox4x32 first;                      // stream 2: first-attempt words of the phased sampler
+    first.init(L.seed, (uint64_t)(L.traj_id0 + i), 2u);
 
     emit_counts<M, OutT>(L, i, 0, y);
     int j = 1;
@@ -176,7 +324,8 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
         for (int k = 0; k < L.n_steps; ++k) {
             const float* tab = M::TDPF_COUNT ? table + (int64_t)L.tdpf_index[k] * M::TDPF_COUNT : table;
             M::propose(y, pre, tab, tau, quirk, w);
-            sample_worklist<M::NDRAW, M::DEP_MASK>(rng, w, st, decoupled);
+            if (walk == 0u) sample_worklist_phased<M::NDRAW, M::DEP_MASK>(first, rng, w, st);
+            else sample_worklist_walk<M::NDRAW, M::DEP_MASK>(rng, w, st, walk == COMPAT_WALK_DECOUPLED);
             M::apply(y, w);
             if (--until_out == 0) {
                 emit_counts<M, OutT>(L, i, j++, y);
@@ -192,7 +341,8 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
             for (int s = 0; s < M::NS; ++s) y_old[s] = y[s];
             const float* tab = M::TDPF_COUNT ? table + (int64_t)L.tdpf_index[k] * M::TDPF_COUNT : table;
             M::propose(y, pre, tab, tau, quirk, w);
-            sample_worklist<M::NDRAW, M::DEP_MASK>(rng, w, st, decoupled);
+            if (walk == 0u) sample_worklist_phased<M::NDRAW, M::DEP_MASK>(first, rng, w, st);
+            else sample_worklist_walk<M::NDRAW, M::DEP_MASK>(rng, w, st, walk == COMPAT_WALK_DECOUPLED);
             M::apply(y, w);
             const double t_new = t + L.tau;
             while (j < L.n_out && L.t0 + (double)j <= t_new) {

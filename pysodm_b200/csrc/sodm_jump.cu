@@ -14,12 +14,14 @@ constexpr int JUMP_BLOCK = 128;
 template <class M, typename OutT, bool ALIGNED>
 __global__ void __launch_bounds__(JUMP_BLOCK) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
     extern __shared__ float smem[];
-    // [NDRAW][JUMP_BLOCK] draw counts | [NDRAW][JUMP_BLOCK] probabilities | time-dependent parameter table
+    // 4 x [NDRAW][JUMP_BLOCK] (draw counts | probabilities | 2 scratch words) | time-dependent parameter table
     WorkList w;
     w.n = reinterpret_cast<int*>(smem) + threadIdx.x;
     w.p = smem + M::NDRAW * JUMP_BLOCK + threadIdx.x;
+    w.a = reinterpret_cast<uint32_t*>(smem) + 2 * M::NDRAW * JUMP_BLOCK + threadIdx.x;
+    w.b = reinterpret_cast<uint32_t*>(smem) + 3 * M::NDRAW * JUMP_BLOCK + threadIdx.x;
     w.stride = JUMP_BLOCK;
-    float* table = smem + 2 * M::NDRAW * JUMP_BLOCK;
+    float* table = smem + 4 * M::NDRAW * JUMP_BLOCK;
     const int n_tab = L.n_tdpf_values * M::TDPF_COUNT;
     for (int e = threadIdx.x; e < n_tab; e += blockDim.x) table[e] = (float)L.tdpf_table[e];   // ABI speaks FP64, rates are FP32
     __syncthreads();
@@ -38,7 +40,13 @@ template <class M, typename OutT>
 static int launch_jump(const JumpLaunch& L, int method, bool aligned, cudaStream_t stream) {
     const unsigned grid = (unsigned)((L.n_traj + JUMP_BLOCK - 1) / JUMP_BLOCK);
     if (method == SODM_JUMP_TAU_LEAP) {
-        const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
+        static bool attr_done = false;     // opt in to > 48 KB dynamic shared memory once per instantiation
+        if (!attr_done) {
+            cudaFuncSetAttribute(tau_leap_kernel<M, OutT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            cudaFuncSetAttribute(tau_leap_kernel<M, OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            attr_done = true;
+        }
+        const size_t smem = ((size_t)4 * M::NDRAW * JUMP_BLOCK + (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
         if (aligned) tau_leap_kernel<M, OutT, true><<<grid, JUMP_BLOCK, smem, stream>>>(L);
         else         tau_leap_kernel<M, OutT, false><<<grid, JUMP_BLOCK, smem, stream>>>(L);
     } else {

@@ -20,7 +20,8 @@ static void run_host(const JumpLaunch& L, int method, bool aligned) {
     for (int64_t i = 0; i < L.n_traj; ++i) {
         int wn[M::NDRAW];
         float wp[M::NDRAW];
-        WorkList w{wn, wp, 1, 1u};
+        uint32_t wa[M::NDRAW], wb[M::NDRAW];
+        WorkList w{wn, wp, wa, wb, 1, 1u};
         if (method == SODM_JUMP_TAU_LEAP) {
             if (aligned) tau_leap_trajectory<M, OutT, true>(L, i, table.data(), w);
             else         tau_leap_trajectory<M, OutT, false>(L, i, table.data(), w);
