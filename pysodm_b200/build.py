@@ -20,7 +20,8 @@ HOSTCHECK_LIB = os.path.join(ROOT, "tests", "hostcheck", "libsodm_hostcheck.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-strict-aliasing"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-strict-aliasing",
+          "-Werror", "cross-execution-space-call"]      # a host constexpr called from device code silently misbehaves
 
 
 def _sources():
@@ -46,6 +47,8 @@ def _run(cmd):
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         raise RuntimeError("command failed: " + " ".join(cmd) + "\n" + proc.stdout)
+    if "warning" in proc.stdout and "-Xptxas" not in cmd:
+        sys.stderr.write(proc.stdout)
     return proc.stdout
 
 

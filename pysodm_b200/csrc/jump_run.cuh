@@ -140,7 +140,7 @@ __host__ __device__ __forceinline__ uint32_t float_as_word(float f) {
 
 // dependency level of every slot: 0 = independent, L = conditional on a slot of level L-1 (bit d of DEP_MASK:
 // slot d's n is what slot d-1 left behind)
-constexpr uint32_t level_mask(uint32_t dep_mask, int ndraw, int level) {
+__host__ __device__ constexpr uint32_t level_mask(uint32_t dep_mask, int ndraw, int level) {
     uint32_t out = 0u;
     int run = 0;
     for (int d = 0; d < ndraw; ++d) {
@@ -149,7 +149,7 @@ constexpr uint32_t level_mask(uint32_t dep_mask, int ndraw, int level) {
     }
     return out;
 }
-constexpr int max_level(uint32_t dep_mask, int ndraw) {
+__host__ __device__ constexpr int max_level(uint32_t dep_mask, int ndraw) {
     int best = 0, run = 0;
     for (int d = 0; d < ndraw; ++d) {
         run = ((dep_mask >> d) & 1u) ? run + 1 : 0;
