@@ -18,7 +18,7 @@ namespace sodm {
 constexpr int MAX_PARAM = 32;   // flat parameter elements passed by value
 constexpr int MAX_STATE = 32;   // flat state elements of a jump model
 
-enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, COMPAT_WALK_DECOUPLED = 256u, COMPAT_WALK_LOCKSTEP = 512u };
+enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, COMPAT_WALK_DECOUPLED = 256u };
 
 struct JumpLaunch {
     int64_t n_traj;            // trajectories in this launch
@@ -102,27 +102,38 @@ __host__ __device__ __forceinline__ void emit_interp(const JumpLaunch& L, int64_
 // tau-leap
 // ------------------------------------------------------------------------------------------------
 
-// The binomial draws of one step of one trajectory: slot d holds (n_d, p_d) and, once drawn, T_d in
-// place of n_d.  On the device the slots live in shared memory, one column per thread (element
-// [d][thread]), so lanes that are at DIFFERENT slots still hit 32 different banks.
+// The binomial draws of one step of the 32 trajectories of a warp: slot d of lane l holds (n, p) and, once
+// drawn, the count T in place of n.  On the device the arrays live in shared memory as [slot][thread of block], so
+// a warp touching ONE slot of 32 different lanes (own or not) hits 32 different banks.
 struct WorkList {
-    int* n;
+    int* n;             // warp base pointers: element (d, lane) at [d * stride + lane]
     float* p;
-    uint32_t* a;        // phased sampler scratch: random word / BTRS candidate of a pending slot
-    uint32_t* b;        //                         random word / log of the scaled uniform of a pending slot
+    uint32_t* a;        // scratch: random word / BTRS candidate k of a pending item
+    uint32_t* b;        // scratch: random word / log of the scaled uniform of a pending item
+    uint16_t* qm;       // warp queue: BTRS items from the front, inversion items from the back ((d << 5) | lane)
+    uint16_t* qx;       // warp queue: items waiting for the exact acceptance test
     int stride;
-    unsigned lanes;     // device: lanes of this warp that run a trajectory (mask for __syncwarp)
-    __host__ __device__ __forceinline__ void put(int d, int nd, float pd) { n[d * stride] = nd; p[d * stride] = pd; }
-    __host__ __device__ __forceinline__ int get(int d) const { return n[d * stride]; }
+    int lane;
+    unsigned lanes;     // device: lanes of the warp that run a trajectory
+    __host__ __device__ __forceinline__ void put(int d, int nd, float pd) { n[d * stride + lane] = nd; p[d * stride + lane] = pd; }
+    __host__ __device__ __forceinline__ int get(int d) const { return n[d * stride + lane]; }
 };
 
-__host__ __device__ __forceinline__ int lowest_bit(uint32_t m) {
 #ifdef __CUDA_ARCH__
-    return __ffs((int)m) - 1;
+constexpr int COOP_LANES = 32;
+__device__ __forceinline__ unsigned coop_ballot(bool x) { return __ballot_sync(0xffffffffu, x); }
+__device__ __forceinline__ unsigned coop_lt(int lane) { return (1u << lane) - 1u; }
+__device__ __forceinline__ int coop_popc(unsigned m) { return __popc(m); }
+__device__ __forceinline__ void coop_sync() { __syncwarp(); }
 #else
-    return __builtin_ctz(m);
+constexpr int COOP_LANES = 1;        // CPU harness: a "warp" of one lane runs the same algorithm
+inline unsigned coop_ballot(bool x) { return x ? 1u : 0u; }
+inline unsigned coop_lt(int) { return 0u; }
+inline int coop_popc(unsigned m) { return (int)(m & 1u); }
+inline void coop_sync() {}
 #endif
-}
+constexpr int COOP_QX_CAP = 128;
+
 __host__ __device__ __forceinline__ float word_as_float(uint32_t w) {
 #ifdef __CUDA_ARCH__
     return __uint_as_float(w);
@@ -158,201 +169,244 @@ __host__ __device__ constexpr int max_level(uint32_t dep_mask, int ndraw) {
     return best;
 }
 
-// PHASED sampler (default).  The cost of a divergent SIMT loop is (trips) x (union of the branches any lane takes), so
-// a step's draws are organised in phases whose bodies are homogeneous:
-//   A  first pass, uniform over the warp: one Philox block per two slots; every slot is classified (trivial /
-//      inversion regime / BTRS regime) and BTRS slots get their first attempt.  ~80 % of them finish here.
-//   X  the candidates the squeeze could not settle: exact log-pmf test, lanes pop their own pending slots;
-//   R  rejected slots: fresh attempts from a second Philox stream until accepted (lanes pop their own slots);
-//   I  inversion-regime slots: sequential search, lanes pop their own slots.
-// Slots conditional on another slot (DEP_MASK) run as a second level after their predecessors are final; their random
-// words are drawn in the first level's pass A and parked in the scratch arrays.
-template <int NDRAW, uint32_t DEP_MASK, class Rng>
-__host__ __device__ __forceinline__ void sample_worklist_phased(Philox4x32& first, Rng& retry, WorkList& w, uint32_t& st) {
+// Random words of one (trajectory, step): counter-based, so ANY lane can regenerate the words of ANY item.
+//   first attempt of slots 2b, 2b+1 : Philox(seed; step, 0x20000000 | b,                     traj)
+//   attempt a >= 1 of slot d        : Philox(seed; step, 0x30000000 | d << 16 | a,           traj)   (words 0,1)
+struct StepKey {
+    uint64_t seed;
+    uint64_t traj0;      // global id of lane 0's trajectory
+    uint32_t step;
+};
+__host__ __device__ __forceinline__ void philox_block(const StepKey& key, int lane, uint32_t tag, uint32_t (&out)[4]) {
+    Philox4x32 g;
+    g.init(key.seed, key.traj0 + (uint64_t)lane);
+    g.ctr0 = key.step;
+    g.ctr1 = tag;
+    g.next4(out);
+}
+
+// WARP-COOPERATIVE sampler (default).  In a divergent SIMT loop the warp pays (trips) x (union of the branches any
+// lane takes), and a per-lane rejection sampler takes a different branch on almost every lane: measured on this
+// kernel, 8 of 32 lanes were active per instruction (profiles/).  Here the 32 x NDRAW draws of a warp-step are
+// pooled instead: every lane classifies its own slots and appends them to warp queues by REGIME; the queues are
+// then processed 32 items at a time, so all lanes of the warp run the same code on different items:
+//   pass 0   own slots: trivial cases, first-attempt random words, queue by regime (ballot + popc compaction)
+//   BTRS     first attempts; accepted -> result; rejected -> compacted in place for the next round with fresh
+//            counter-based words; undecided by the squeeze -> exact-test queue
+//   exact    log-pmf ratio test on queued candidates; failures rejoin the BTRS queue
+//   inverse  sequential-search inversion on the small-mean items
+// Items conditional on another slot (DEP_MASK) form a second level that runs after the first is final.
+template <int NDRAW, uint32_t DEP_MASK>
+__host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key, WorkList& w, uint32_t& st) {
     static_assert(NDRAW <= 32, "at most 32 draws per step");
     constexpr int LEVELS = max_level(DEP_MASK, NDRAW) + 1;
-    const int S = w.stride;
+    constexpr int CAP = NDRAW * COOP_LANES;
+    const int S = w.stride, lane = w.lane;
+    const unsigned lt = coop_lt(lane);
 #pragma unroll
     for (int level = 0; level < LEVELS; ++level) {
         const uint32_t in_level = level_mask(DEP_MASK, NDRAW, level);
-        uint32_t inv = 0u, exact = 0u, again = 0u;
-        // ---- phase A --------------------------------------------------------------------------------------
+        int nb = 0, ni = 0, nx = 0;
+        // ---- pass 0 -------------------------------------------------------------------------------------------
         uint32_t blk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
         for (int d = 0; d < NDRAW; ++d) {
             uint32_t wu, wv;
             if (level == 0) {
-                if ((d & 1) == 0) first.next4(blk);
+                if ((d & 1) == 0) philox_block(key, lane, 0x20000000u | (uint32_t)(d >> 1), blk);
                 wu = (d & 1) ? blk[2] : blk[0];
                 wv = (d & 1) ? blk[3] : blk[1];
                 if (!((in_level >> d) & 1u)) {            // a later level's slot: park its words
-                    w.a[d * S] = wu;
-                    w.b[d * S] = wv;
+                    w.a[d * S + lane] = wu;
+                    w.b[d * S + lane] = wv;
                     continue;
                 }
             } else {
                 if (!((in_level >> d) & 1u)) continue;
-                wu = w.a[d * S];
-                wv = w.b[d * S];
+                wu = w.a[d * S + lane];
+                wv = w.b[d * S + lane];
             }
-            int n = w.n[d * S];
-            const float p = w.p[d * S];
-            if (level > 0) { n -= w.n[(d - 1) * S]; w.n[d * S] = n; }     // what the previous exit left behind
+            int n = w.n[d * S + lane];
+            const float p = w.p[d * S + lane];
+            if (level > 0) { n -= w.n[(d - 1) * S + lane]; w.n[d * S + lane] = n; }   // what the previous exit left behind
             int k;
-            int state = binomial_classify(n, p, k);
-            if (state == BIN_BTRS) {
-                const bool flip = p > 0.5f;
-                float lhs = 0.0f;
-                state = btrs_attempt_words(n, flip ? 1.0f - p : p, wu, wv, k, lhs);
-                if (state == BIN_DONE) k = flip ? n - k : k;
-                else if (state == BIN_EXACT) { w.a[d * S] = (uint32_t)k; w.b[d * S] = float_as_word(lhs); exact |= 1u << d; }
-                else again |= 1u << d;
-            } else if (state == BIN_INVERT) {
-                w.a[d * S] = wu;
-                inv |= 1u << d;
-            }
+            const int state = binomial_classify(n, p, k);
             if (state == BIN_DONE) {
                 if (k < 0) { st |= ST_BAD_PROB; k = 0; }
-                w.n[d * S] = k;
+                w.n[d * S + lane] = k;
+            } else {
+                w.a[d * S + lane] = wu;
+                w.b[d * S + lane] = wv;
             }
+            const unsigned mB = coop_ballot(state == BIN_BTRS), mI = coop_ballot(state == BIN_INVERT);
+            if (state == BIN_BTRS) w.qm[nb + coop_popc(mB & lt)] = (uint16_t)((d << 5) | lane);
+            if (state == BIN_INVERT) w.qm[CAP - 1 - (ni + coop_popc(mI & lt))] = (uint16_t)((d << 5) | lane);
+            nb += coop_popc(mB);
+            ni += coop_popc(mI);
         }
-        // ---- phases X + R: settle ambiguous candidates, re-draw rejected ones ------------------------------
-        while (exact | again) {
-            if (exact) {
-                const int d = lowest_bit(exact);
-                const uint32_t bit = 1u << d;
-                const int n = w.n[d * S];
-                const float p = w.p[d * S];
+        coop_sync();
+        // ---- BTRS rounds ------------------------------------------------------------------------------------------
+        int count = nb;
+        uint32_t attempt = 0u;
+        while (count > 0) {
+            int keep = 0;
+            for (int base = 0; base < count; base += COOP_LANES) {
+                const bool valid = base + lane < count;
+                int state = BIN_DONE;
+                uint16_t e = 0;
+                if (valid) {
+                    e = w.qm[base + lane];
+                    const int d = e >> 5, o = e & 31;
+                    const int n = w.n[d * S + o];
+                    const float p = w.p[d * S + o];
+                    const bool flip = p > 0.5f;
+                    uint32_t wu, wv;
+                    if (attempt == 0u) {
+                        wu = w.a[d * S + o];
+                        wv = w.b[d * S + o];
+                    } else {
+                        uint32_t r[4];
+                        philox_block(key, o, 0x30000000u | ((uint32_t)d << 16) | attempt, r);
+                        wu = r[0];
+                        wv = r[1];
+                    }
+                    int k;
+                    float lhs = 0.0f;
+                    state = btrs_attempt_words(n, flip ? 1.0f - p : p, wu, wv, k, lhs);
+                    if (state == BIN_DONE) w.n[d * S + o] = flip ? n - k : k;
+                    else if (state == BIN_EXACT) { w.a[d * S + o] = (uint32_t)k; w.b[d * S + o] = float_as_word(lhs); }
+                }
+                coop_sync();                                 // every lane has read its queue entry
+                const unsigned mR = coop_ballot(valid && state == BIN_RETRY), mX = coop_ballot(valid && state == BIN_EXACT);
+                if (valid && state == BIN_RETRY) w.qm[keep + coop_popc(mR & lt)] = e;     // keep <= base: already consumed
+                if (valid && state == BIN_EXACT) w.qx[nx + coop_popc(mX & lt)] = e;
+                keep += coop_popc(mR);
+                nx += coop_popc(mX);
+                coop_sync();
+                if (nx > COOP_QX_CAP - COOP_LANES || base + COOP_LANES >= count) {
+                    // ---- exact tests (queue nearly full, or end of the round); failures rejoin the retry queue ----
+                    for (int xb = 0; xb < nx; xb += COOP_LANES) {
+                        const bool xv = xb + lane < nx;
+                        bool fail = false;
+                        uint16_t xe = 0;
+                        if (xv) {
+                            xe = w.qx[xb + lane];
+                            const int d = xe >> 5, o = xe & 31;
+                            const int n = w.n[d * S + o];
+                            const float p = w.p[d * S + o];
+                            const bool flip = p > 0.5f;
+                            const int k = (int)w.a[d * S + o];
+                            if (btrs_exact_accept(n, flip ? 1.0f - p : p, k, word_as_float(w.b[d * S + o])))
+                                w.n[d * S + o] = flip ? n - k : k;
+                            else fail = true;
+                        }
+                        const unsigned mF = coop_ballot(fail);
+                        // the retry queue is compacted in place below `base + COOP_LANES`; at most `nx` <= consumed items join
+                        if (fail) w.qm[keep + coop_popc(mF & lt)] = xe;
+                        keep += coop_popc(mF);
+                    }
+                    nx = 0;
+                    coop_sync();
+                }
+            }
+            count = keep;
+            ++attempt;
+        }
+        // ---- inversion-regime items ----------------------------------------------------------------------------------
+        for (int base = 0; base < ni; base += COOP_LANES) {
+            if (base + lane < ni) {
+                const uint16_t e = w.qm[CAP - 1 - (base + lane)];
+                const int d = e >> 5, o = e & 31;
+                const int n = w.n[d * S + o];
+                const float p = w.p[d * S + o];
                 const bool flip = p > 0.5f;
-                const int k = (int)w.a[d * S];
-                exact &= ~bit;
-                if (btrs_exact_accept(n, flip ? 1.0f - p : p, k, word_as_float(w.b[d * S]))) w.n[d * S] = flip ? n - k : k;
-                else again |= bit;
-            }
-            if (again) {
-                const int d = lowest_bit(again);
-                const uint32_t bit = 1u << d;
-                const int n = w.n[d * S];
-                const float p = w.p[d * S];
-                const bool flip = p > 0.5f;
-                int k;
-                float lhs = 0.0f;
-                const uint32_t wu = retry.next(), wv = retry.next();
-                const int state = btrs_attempt_words(n, flip ? 1.0f - p : p, wu, wv, k, lhs);
-                if (state == BIN_DONE) { w.n[d * S] = flip ? n - k : k; again &= ~bit; }
-                else if (state == BIN_EXACT) { w.a[d * S] = (uint32_t)k; w.b[d * S] = float_as_word(lhs); exact |= bit; again &= ~bit; }
+                const int k = binomial_inversion_word(n, flip ? 1.0f - p : p, w.a[d * S + o]);
+                w.n[d * S + o] = flip ? n - k : k;
             }
         }
-        // ---- phase I: inversion-regime slots ----------------------------------------------------------------
-        while (inv) {
-            const int d = lowest_bit(inv);
-            inv &= inv - 1u;
-            const int n = w.n[d * S];
-            const float p = w.p[d * S];
-            const bool flip = p > 0.5f;
-            const int k = binomial_inversion_word(n, flip ? 1.0f - p : p, w.a[d * S]);
-            w.n[d * S] = flip ? n - k : k;
-        }
-#ifdef __CUDA_ARCH__
-        __syncwarp(w.lanes);
-#endif
+        coop_sync();
     }
 }
 
-// Draws every slot of the list.
-//   lockstep (default): all lanes of the warp are at the SAME slot -- i.e. the same compartment and age group of
-//     32 neighbouring trajectories, whose (n, p) are alike, so the lanes take the same sampler branch; a lane whose
-//     attempt is rejected retries while its neighbours wait (max over lanes of a geometric number of attempts).
-//   decoupled (COMPAT_WALK_DECOUPLED): each lane walks its OWN list and never waits for a neighbour's rejection,
-//     at the price of lanes drifting to different slots and hence different sampler branches.
-// Which one wins is a measurement (profiles/): on influenza the lockstep walk executes ~5x fewer warp instructions.
+// Per-lane walk (tuning flag COMPAT_WALK_DECOUPLED, kept for A/B measurements): each lane draws its own slots one
+// after the other with a private Philox stream, retrying rejected attempts without waiting for its neighbours.
 template <int NDRAW, uint32_t DEP_MASK, class Rng>
-__host__ __device__ __forceinline__ void sample_worklist_walk(Rng& rng, WorkList& w, uint32_t& st, bool decoupled) {
-    int prev = 0;
-    if (!decoupled) {
-#pragma unroll 1
-        for (int d = 0; d < NDRAW; ++d) {
-            int n = w.n[d * w.stride];
-            const float p = w.p[d * w.stride];
-            if ((DEP_MASK >> d) & 1u) n -= prev;      // conditional draw: what the previous exit left behind
-            int k;
-            while (!binomial_try(rng, n, p, k)) {}
-#ifdef __CUDA_ARCH__
-            __syncwarp(w.lanes);                      // reconverge before the next slot
-#endif
-            if (k < 0) { st |= ST_BAD_PROB; k = 0; }
-            w.n[d * w.stride] = k;
-            prev = k;
-        }
-        return;
-    }
-    int d = 0;
+__host__ __device__ __forceinline__ void sample_worklist_walk(Rng& rng, WorkList& w, uint32_t& st) {
+    const int S = w.stride, lane = w.lane;
+    int d = 0, prev = 0;
     while (d < NDRAW) {
-        int n = w.n[d * w.stride];
-        const float p = w.p[d * w.stride];
+        int n = w.n[d * S + lane];
+        const float p = w.p[d * S + lane];
         if ((DEP_MASK >> d) & 1u) n -= prev;
         int k;
         if (binomial_try(rng, n, p, k)) {
             if (k < 0) { st |= ST_BAD_PROB; k = 0; }
-            w.n[d * w.stride] = k;
+            w.n[d * S + lane] = k;
             prev = k;
             ++d;
         }
     }
 }
 
+// One trajectory per lane.  `active` = the lane owns a trajectory; the remaining lanes of a partially filled warp
+// still take part in the warp-cooperative sampling (they own no items) but neither load nor store.
 template <class M, typename OutT, bool ALIGNED>
-__host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L, int64_t i, const float* table,
-                                                             WorkList w) {
+__host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L, int64_t i, bool active,
+                                                             const float* table, WorkList w) {
     double par[M::NPAR];
     int y[M::NS];
     uint32_t st = ST_OK;
-    load_trajectory<M>(L, i, par, y, st);
+    if (active) load_trajectory<M>(L, i, par, y, st);
+    else {
+#pragma unroll
+        for (int e = 0; e < M::NPAR; ++e) par[e] = L.par[e];
+#pragma unroll
+        for (int s = 0; s < M::NS; ++s) y[s] = 0;
+    }
     const bool quirk = (L.compat & COMPAT_STAY_QUIRK) != 0u;
-    const uint32_t walk = L.compat & (COMPAT_WALK_DECOUPLED | COMPAT_WALK_LOCKSTEP);
+    const bool walk = (L.compat & COMPAT_WALK_DECOUPLED) != 0u;
     const float tau = (float)L.tau;
     const typename M::Pre pre = M::prepare(par, tau, quirk);
-    PhiloxWords rng;                       // stream 0: re-draws (phased sampler) / every draw (walk samplers)
+    PhiloxWords rng;                       // private stream of the per-lane walk
     rng.init(L.seed, (uint64_t)(L.traj_id0 + i));
-    Philox4x32 first;                      // stream 2: first-attempt words of the phased sampler
-    first.init(L.seed, (uint64_t)(L.traj_id0 + i), 2u);
+    StepKey key;
+    key.seed = L.seed;
+    key.traj0 = (uint64_t)(L.traj_id0 + i - w.lane);
+    key.step = 0u;
 
-    emit_counts<M, OutT>(L, i, 0, y);
+    if (active) emit_counts<M, OutT>(L, i, 0, y);
     int j = 1;
-    if (ALIGNED) {
-        int until_out = L.steps_per_out;
-        for (int k = 0; k < L.n_steps; ++k) {
-            const float* tab = M::TDPF_COUNT ? table + (int64_t)L.tdpf_index[k] * M::TDPF_COUNT : table;
-            M::propose(y, pre, tab, tau, quirk, w);
-            if (walk == 0u) sample_worklist_phased<M::NDRAW, M::DEP_MASK>(first, rng, w, st);
-            else sample_worklist_walk<M::NDRAW, M::DEP_MASK>(rng, w, st, walk == COMPAT_WALK_DECOUPLED);
-            M::apply(y, w);
-            if (--until_out == 0) {
-                emit_counts<M, OutT>(L, i, j++, y);
-                until_out = L.steps_per_out;
-            }
-        }
-    } else {
-        // general tau: interpolate onto the integer grid between consecutive step states
-        int y_old[M::NS];
-        double t = L.t0;
-        for (int k = 0; k < L.n_steps; ++k) {
+    int y_old[ALIGNED ? 1 : M::NS];
+    int until_out = L.steps_per_out;
+    double t = L.t0;
+    for (int k = 0; k < L.n_steps; ++k) {
+        if (!ALIGNED) {
 #pragma unroll
             for (int s = 0; s < M::NS; ++s) y_old[s] = y[s];
-            const float* tab = M::TDPF_COUNT ? table + (int64_t)L.tdpf_index[k] * M::TDPF_COUNT : table;
-            M::propose(y, pre, tab, tau, quirk, w);
-            if (walk == 0u) sample_worklist_phased<M::NDRAW, M::DEP_MASK>(first, rng, w, st);
-            else sample_worklist_walk<M::NDRAW, M::DEP_MASK>(rng, w, st, walk == COMPAT_WALK_DECOUPLED);
-            M::apply(y, w);
+        }
+        const float* tab = M::TDPF_COUNT ? table + (int64_t)L.tdpf_index[k] * M::TDPF_COUNT : table;
+        M::propose(y, pre, tab, tau, quirk, w);
+        key.step = (uint32_t)k;
+        if (walk) sample_worklist_walk<M::NDRAW, M::DEP_MASK>(rng, w, st);
+        else sample_worklist_coop<M::NDRAW, M::DEP_MASK>(key, w, st);
+        M::apply(y, w);
+        if (ALIGNED) {
+            if (--until_out == 0) {
+                if (active) emit_counts<M, OutT>(L, i, j, y);
+                ++j;
+                until_out = L.steps_per_out;
+            }
+        } else {
+            // general tau: interpolate onto the integer grid between consecutive step states
             const double t_new = t + L.tau;
             while (j < L.n_out && L.t0 + (double)j <= t_new) {
-                emit_interp<M, OutT>(L, i, j, L.t0 + (double)j, t, t_new, y_old, y);
+                if (active) emit_interp<M, OutT>(L, i, j, L.t0 + (double)j, t, t_new, y_old, y);
                 ++j;
             }
             t = t_new;
         }
     }
-    if (L.status) L.status[i] = (int32_t)st;
+    if (active && L.status) L.status[i] = (int32_t)st;
 }
 
 // ------------------------------------------------------------------------------------------------

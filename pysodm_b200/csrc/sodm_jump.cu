@@ -14,20 +14,28 @@ constexpr int JUMP_BLOCK = 128;
 template <class M, typename OutT, bool ALIGNED>
 __global__ void __launch_bounds__(JUMP_BLOCK) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
     extern __shared__ float smem[];
-    // 4 x [NDRAW][JUMP_BLOCK] (draw counts | probabilities | 2 scratch words) | time-dependent parameter table
+    // 4 x [NDRAW][JUMP_BLOCK] words (draw counts | probabilities | 2 scratch words) | per-warp queues | TDPF table
+    constexpr int WARPS = JUMP_BLOCK / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WorkList w;
-    w.n = reinterpret_cast<int*>(smem) + threadIdx.x;
-    w.p = smem + M::NDRAW * JUMP_BLOCK + threadIdx.x;
-    w.a = reinterpret_cast<uint32_t*>(smem) + 2 * M::NDRAW * JUMP_BLOCK + threadIdx.x;
-    w.b = reinterpret_cast<uint32_t*>(smem) + 3 * M::NDRAW * JUMP_BLOCK + threadIdx.x;
+    w.n = reinterpret_cast<int*>(smem) + warp * 32;
+    w.p = smem + M::NDRAW * JUMP_BLOCK + warp * 32;
+    w.a = reinterpret_cast<uint32_t*>(smem) + 2 * M::NDRAW * JUMP_BLOCK + warp * 32;
+    w.b = reinterpret_cast<uint32_t*>(smem) + 3 * M::NDRAW * JUMP_BLOCK + warp * 32;
+    uint16_t* queues = reinterpret_cast<uint16_t*>(smem + 4 * M::NDRAW * JUMP_BLOCK);
+    w.qm = queues + warp * (M::NDRAW * 32 + COOP_QX_CAP);
+    w.qx = w.qm + M::NDRAW * 32;
     w.stride = JUMP_BLOCK;
-    float* table = smem + 4 * M::NDRAW * JUMP_BLOCK;
+    w.lane = lane;
+    float* table = smem + 4 * M::NDRAW * JUMP_BLOCK + WARPS * (M::NDRAW * 32 + COOP_QX_CAP) / 2;
     const int n_tab = L.n_tdpf_values * M::TDPF_COUNT;
     for (int e = threadIdx.x; e < n_tab; e += blockDim.x) table[e] = (float)L.tdpf_table[e];   // ABI speaks FP64, rates are FP32
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    w.lanes = __ballot_sync(0xffffffffu, i < L.n_traj);
-    if (i < L.n_traj) tau_leap_trajectory<M, OutT, ALIGNED>(L, i, table, w);
+    const bool active = i < L.n_traj;
+    w.lanes = __ballot_sync(0xffffffffu, active);
+    if (w.lanes == 0u) return;                                    // whole warp past the end
+    tau_leap_trajectory<M, OutT, ALIGNED>(L, i, active, table, w);
 }
 
 template <class M, typename OutT>
@@ -46,7 +54,8 @@ static int launch_jump(const JumpLaunch& L, int method, bool aligned, cudaStream
             cudaFuncSetAttribute(tau_leap_kernel<M, OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             attr_done = true;
         }
-        const size_t smem = ((size_t)4 * M::NDRAW * JUMP_BLOCK + (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
+        const size_t smem = ((size_t)4 * M::NDRAW * JUMP_BLOCK + (size_t)(JUMP_BLOCK / 32) * (M::NDRAW * 32 + COOP_QX_CAP) / 2 +
+                             (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
         if (aligned) tau_leap_kernel<M, OutT, true><<<grid, JUMP_BLOCK, smem, stream>>>(L);
         else         tau_leap_kernel<M, OutT, false><<<grid, JUMP_BLOCK, smem, stream>>>(L);
     } else {
