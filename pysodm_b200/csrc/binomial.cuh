@@ -51,6 +51,25 @@ struct PhiloxWords {
     }
 };
 
+// ---- fast device arithmetic for the PROPOSAL side of the rejection sampler -------------------------------------
+// The hat function / squeeze of BTRS may be evaluated with approximate division and logarithm: an error of a few ulp
+// there moves a candidate boundary or an acceptance threshold by ~1e-7 relative, i.e. perturbs a uniform variate by
+// 1e-7 -- invisible in the sampled law.  The exact pmf ratio (binomial_log_ratio*) keeps accurate arithmetic.
+__host__ __device__ __forceinline__ float fast_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+__host__ __device__ __forceinline__ float fast_log(float x) {
+#ifdef __CUDA_ARCH__
+    return __logf(x);
+#else
+    return logf(x);
+#endif
+}
+
 #define SODM_STIRLING_TABLE {0.0810614667953272, 0.0413406959554092, 0.0276779256849983, 0.02079067210376509, \
                              0.0166446911898211, 0.0138761288230707, 0.0118967099458917, 0.0104112652619720,  \
                              0.00925546218271273, 0.00833056343336287}
@@ -122,51 +141,9 @@ __host__ __device__ __forceinline__ float binomial_log_ratio_f32(float nf, float
          - stirling_tail_f(k) - stirling_tail_f(nf - k);
 }
 
-// One BTRS attempt; requires 0 < p <= 0.5 and n*p >= 10.  Returns true and sets k when accepted.
-template <class Rng>
-__host__ __device__ __forceinline__ bool btrs_try(Rng& rng, int n, float p, int& k) {
-    const float nf = (float)n;
-    const float np_ = nf * p;
-    const float npq = np_ * (1.0f - p);
-    const float stddev = sqrtf(npq);
-    const float b = 1.15f + 2.53f * stddev;
-    const float a = -0.0873f + 0.0248f * b + 0.01f * p;
-    const float inv_b = 1.0f / b;
-    const float v_r = 0.92f - 4.2f * inv_b;
-    const float u = u01(rng.next()) - 0.5f;
-    const float v = u01(rng.next());
-    const float us = 0.5f - fabsf(u);
-    float kf;
-    if (np_ < 4194304.0f) {                                      // candidate exactly representable in FP32
-        kf = floorf(fmaf(2.0f * a / us + b, u, np_ + 0.5f));
-        k = (int)kf;
-    } else {
-        const double kd = floor(fma((double)(2.0f * a / us + b), (double)u, fma((double)n, (double)p, 0.5)));
-        k = (int)fmin(fmax(kd, -1.0), 2147483647.0);
-        kf = (float)kd;
-    }
-    if (us >= 0.07f && v <= v_r) return true;                    // BTRS box: no logarithm needed
-    if (k < 0 || k > n) return false;
-    const float alpha = (2.83f + 5.1f * inv_b) * stddev;
-    const float lhs = logf(v * alpha / (a / (us * us) + b));
-    const float mf = floorf((nf + 1.0f) * p);
-    const float x = fabsf(kf - mf);
-    if (x < 0.5f * npq - 1.0f) {                                  // BTPE step 5.2 squeeze, in FP32
-        const float t = -x * x / (2.0f * npq);
-        const float rho = (x / npq) * ((x * (x * (1.0f / 3.0f) + 0.625f) + (1.0f / 6.0f)) / npq + 0.5f);
-        const float eps = 4e-6f * (1.0f + fabsf(t) + fabsf(lhs));
-        if (lhs < t - rho - eps) return true;
-        if (lhs > t + rho + eps) return false;
-    }
-    if (mf < SODM_F32_MODE_LIMIT && nf < 16777216.0f)             // exact test: FP32 where its error is harmless
-        return lhs <= binomial_log_ratio_f32(nf, p, mf, kf);
-    const double nd = (double)n, pd = (double)p;
-    return (double)lhs <= binomial_log_ratio(nd, pd, floor((nd + 1.0) * pd), (double)k);
-}
-
 // ------------------------------------------------------------------------------------------------
-// Building blocks of the PHASED work-list sampler (jump_run.cuh): the same BTRS / squeeze / exact test /
-// inversion as above, split so that each phase of a step runs ONE of them on all lanes that need it.
+// Building blocks of the samplers: BTRS candidate / squeeze / exact test and inversion as separate functions, so that
+// the warp-cooperative sampler (jump_run.cuh) can run ONE of them on all lanes at a time.
 // ------------------------------------------------------------------------------------------------
 enum : int { BIN_DONE = 0, BIN_INVERT = 1, BIN_EXACT = 2, BIN_RETRY = 3, BIN_BTRS = 4 };
 
@@ -188,44 +165,53 @@ __host__ __device__ __forceinline__ int binomial_inversion_word(int n, float p, 
     while (u > f && k < n && k < 1024) {
         u -= f;
         ++k;
-        f *= s * (float)(n - k + 1) / (float)k;
+        f *= fast_div(s * (float)(n - k + 1), (float)k);       // P(k)/P(k-1); a few ulp here only nudge u by ~1e-7
     }
     return k;
 }
 
-// One BTRS attempt from two random words (0 < p <= 0.5, n*p >= 10): BIN_DONE (k accepted), BIN_RETRY (rejected) or
-// BIN_EXACT (the squeeze could not settle candidate k; `lhs` = log of the scaled uniform to compare with log f(k)/f(m)).
-__host__ __device__ __forceinline__ int btrs_attempt_words(int n, float p, uint32_t wu, uint32_t wv, int& k, float& lhs) {
+// Split form of one BTRS attempt, for queue-based processing (jump_run.cuh):
+//   btrs_candidate : setup + candidate k + BTRS box test            -> BIN_DONE | BIN_RETRY (k outside 0..n) | BIN_SQUEEZE
+//   btrs_squeeze   : scaled uniform + BTPE squeeze on the same words -> BIN_DONE | BIN_RETRY | BIN_EXACT (lhs set)
+enum : int { BIN_SQUEEZE = 5 };
+__host__ __device__ __forceinline__ int btrs_candidate(int n, float p, uint32_t wu, uint32_t wv, int& k) {
     const float nf = (float)n;
     const float np_ = nf * p;
-    const float npq = np_ * (1.0f - p);
-    const float stddev = sqrtf(npq);
+    const float stddev = sqrtf(np_ * (1.0f - p));
     const float b = 1.15f + 2.53f * stddev;
     const float a = -0.0873f + 0.0248f * b + 0.01f * p;
-    const float inv_b = 1.0f / b;
-    const float v_r = 0.92f - 4.2f * inv_b;
+    const float v_r = 0.92f - fast_div(4.2f, b);
     const float u = u01(wu) - 0.5f;
     const float v = u01(wv);
     const float us = 0.5f - fabsf(u);
-    float kf;
     if (np_ < 4194304.0f) {
-        kf = floorf(fmaf(2.0f * a / us + b, u, np_ + 0.5f));
-        k = (int)kf;
+        k = (int)floorf(fmaf(fast_div(2.0f * a, us) + b, u, np_ + 0.5f));
     } else {
         const double kd = floor(fma((double)(2.0f * a / us + b), (double)u, fma((double)n, (double)p, 0.5)));
         k = (int)fmin(fmax(kd, -1.0), 2147483647.0);
-        kf = (float)kd;
     }
     if (us >= 0.07f && v <= v_r) return BIN_DONE;
     if (k < 0 || k > n) return BIN_RETRY;
-    const float alpha = (2.83f + 5.1f * inv_b) * stddev;
-    lhs = logf(v * alpha / (a / (us * us) + b));
+    return BIN_SQUEEZE;
+}
+__host__ __device__ __forceinline__ int btrs_squeeze(int n, float p, int k, uint32_t wu, uint32_t wv, float& lhs) {
+    const float nf = (float)n;
+    const float npq = nf * p * (1.0f - p);
+    const float stddev = sqrtf(npq);
+    const float b = 1.15f + 2.53f * stddev;
+    const float a = -0.0873f + 0.0248f * b + 0.01f * p;
+    const float alpha = (2.83f + fast_div(5.1f, b)) * stddev;
+    const float u = u01(wu) - 0.5f;
+    const float v = u01(wv);
+    const float us = 0.5f - fabsf(u);
+    lhs = fast_log(fast_div(v * alpha, fast_div(a, us * us) + b));
     const float mf = floorf((nf + 1.0f) * p);
-    const float x = fabsf(kf - mf);
+    const float x = fabsf((float)k - mf);
     if (x < 0.5f * npq - 1.0f) {
-        const float t = -x * x / (2.0f * npq);
-        const float rho = (x / npq) * ((x * (x * (1.0f / 3.0f) + 0.625f) + (1.0f / 6.0f)) / npq + 0.5f);
-        const float eps = 4e-6f * (1.0f + fabsf(t) + fabsf(lhs));
+        const float inv_npq = fast_div(1.0f, npq);
+        const float t = -0.5f * x * x * inv_npq;
+        const float rho = (x * inv_npq) * ((x * (x * (1.0f / 3.0f) + 0.625f) + (1.0f / 6.0f)) * inv_npq + 0.5f);
+        const float eps = 8e-6f * (1.0f + fabsf(t) + fabsf(lhs));
         if (lhs < t - rho - eps) return BIN_DONE;
         if (lhs > t + rho + eps) return BIN_RETRY;
     }
@@ -239,6 +225,20 @@ __host__ __device__ __forceinline__ bool btrs_exact_accept(int n, float p, int k
     if (mf < SODM_F32_MODE_LIMIT && nf < 16777216.0f) return lhs <= binomial_log_ratio_f32(nf, p, mf, (float)k);
     const double nd = (double)n, pd = (double)p;
     return (double)lhs <= binomial_log_ratio(nd, pd, floor((nd + 1.0) * pd), (double)k);
+}
+
+// One complete BTRS attempt of a single lane (per-lane walk); requires 0 < p <= 0.5 and n*p >= 10.
+template <class Rng>
+__host__ __device__ __forceinline__ bool btrs_try(Rng& rng, int n, float p, int& k) {
+    const uint32_t wu = rng.next(), wv = rng.next();
+    int state = btrs_candidate(n, p, wu, wv, k);
+    if (state == BIN_DONE) return true;
+    if (state == BIN_RETRY) return false;
+    float lhs = 0.0f;
+    state = btrs_squeeze(n, p, k, wu, wv, lhs);
+    if (state == BIN_DONE) return true;
+    if (state == BIN_RETRY) return false;
+    return btrs_exact_accept(n, p, k, lhs);
 }
 
 // ONE attempt at Bin(n, p), 0 <= p <= 1.  Returns true when finished with the variate in k.

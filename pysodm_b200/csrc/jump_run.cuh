@@ -111,6 +111,7 @@ struct WorkList {
     uint32_t* a;        // scratch: random word / BTRS candidate k of a pending item
     uint32_t* b;        // scratch: random word / log of the scaled uniform of a pending item
     uint16_t* qm;       // warp queue: BTRS items from the front, inversion items from the back ((d << 5) | lane)
+    uint16_t* qs;       // warp queue: candidates outside the BTRS box, waiting for the squeeze
     uint16_t* qx;       // warp queue: items waiting for the exact acceptance test
     int stride;
     int lane;
@@ -132,7 +133,8 @@ inline unsigned coop_lt(int) { return 0u; }
 inline int coop_popc(unsigned m) { return (int)(m & 1u); }
 inline void coop_sync() {}
 #endif
-constexpr int COOP_QX_CAP = 128;
+constexpr int COOP_QS_CAP = 256;
+constexpr int COOP_QX_CAP = 256;      // >= COOP_QS_CAP: one squeeze drain can never overflow it
 
 __host__ __device__ __forceinline__ float word_as_float(uint32_t w) {
 #ifdef __CUDA_ARCH__
@@ -246,7 +248,11 @@ __host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key
         }
         coop_sync();
         // ---- BTRS rounds ------------------------------------------------------------------------------------------
-        int count = nb;
+        // qm[0, count): items to attempt.  Consumed entries are re-used in place for the items that must be re-drawn
+        // (keep <= number consumed, always).  Candidates outside the BTRS box wait in qs for the squeeze, candidates the
+        // squeeze cannot settle wait in qx for the exact test; both queues are drained when nearly full and at the end
+        // of a round, and what they reject rejoins the re-draw list.
+        int count = nb, ns = 0;
         uint32_t attempt = 0u;
         while (count > 0) {
             int keep = 0;
@@ -271,20 +277,48 @@ __host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key
                         wv = r[1];
                     }
                     int k;
-                    float lhs = 0.0f;
-                    state = btrs_attempt_words(n, flip ? 1.0f - p : p, wu, wv, k, lhs);
+                    state = btrs_candidate(n, flip ? 1.0f - p : p, wu, wv, k);
                     if (state == BIN_DONE) w.n[d * S + o] = flip ? n - k : k;
-                    else if (state == BIN_EXACT) { w.a[d * S + o] = (uint32_t)k; w.b[d * S + o] = float_as_word(lhs); }
+                    else if (state == BIN_SQUEEZE && attempt != 0u) { w.a[d * S + o] = wu; w.b[d * S + o] = wv; }
                 }
                 coop_sync();                                 // every lane has read its queue entry
-                const unsigned mR = coop_ballot(valid && state == BIN_RETRY), mX = coop_ballot(valid && state == BIN_EXACT);
-                if (valid && state == BIN_RETRY) w.qm[keep + coop_popc(mR & lt)] = e;     // keep <= base: already consumed
-                if (valid && state == BIN_EXACT) w.qx[nx + coop_popc(mX & lt)] = e;
+                const unsigned mR = coop_ballot(valid && state == BIN_RETRY), mS = coop_ballot(valid && state == BIN_SQUEEZE);
+                if (valid && state == BIN_RETRY) w.qm[keep + coop_popc(mR & lt)] = e;
+                if (valid && state == BIN_SQUEEZE) w.qs[ns + coop_popc(mS & lt)] = e;
                 keep += coop_popc(mR);
-                nx += coop_popc(mX);
+                ns += coop_popc(mS);
                 coop_sync();
-                if (nx > COOP_QX_CAP - COOP_LANES || base + COOP_LANES >= count) {
-                    // ---- exact tests (queue nearly full, or end of the round); failures rejoin the retry queue ----
+                const bool last = base + COOP_LANES >= count;
+                if (ns > COOP_QS_CAP - COOP_LANES || last) {
+                    // ---- squeeze: the words of the attempt are parked in a/b; candidate k is recomputed ----
+                    for (int sb = 0; sb < ns; sb += COOP_LANES) {
+                        const bool sv = sb + lane < ns;
+                        int sstate = BIN_DONE;
+                        uint16_t se = 0;
+                        if (sv) {
+                            se = w.qs[sb + lane];
+                            const int d = se >> 5, o = se & 31;
+                            const int n = w.n[d * S + o];
+                            const float p = w.p[d * S + o];
+                            const bool flip = p > 0.5f;
+                            const float pp = flip ? 1.0f - p : p;
+                            const uint32_t wu = w.a[d * S + o], wv = w.b[d * S + o];
+                            int k;
+                            float lhs = 0.0f;
+                            btrs_candidate(n, pp, wu, wv, k);
+                            sstate = btrs_squeeze(n, pp, k, wu, wv, lhs);
+                            if (sstate == BIN_DONE) w.n[d * S + o] = flip ? n - k : k;
+                            else if (sstate == BIN_EXACT) { w.a[d * S + o] = (uint32_t)k; w.b[d * S + o] = float_as_word(lhs); }
+                        }
+                        const unsigned mR2 = coop_ballot(sv && sstate == BIN_RETRY), mX = coop_ballot(sv && sstate == BIN_EXACT);
+                        if (sv && sstate == BIN_RETRY) w.qm[keep + coop_popc(mR2 & lt)] = se;
+                        if (sv && sstate == BIN_EXACT) w.qx[nx + coop_popc(mX & lt)] = se;
+                        keep += coop_popc(mR2);
+                        nx += coop_popc(mX);
+                        coop_sync();
+                    }
+                    ns = 0;
+                    // ---- exact log-pmf ratio test (qx can hold a full squeeze queue, so it is drained right after it) ----
                     for (int xb = 0; xb < nx; xb += COOP_LANES) {
                         const bool xv = xb + lane < nx;
                         bool fail = false;
@@ -301,7 +335,6 @@ __host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key
                             else fail = true;
                         }
                         const unsigned mF = coop_ballot(fail);
-                        // the retry queue is compacted in place below `base + COOP_LANES`; at most `nx` <= consumed items join
                         if (fail) w.qm[keep + coop_popc(mF & lt)] = xe;
                         keep += coop_popc(mF);
                     }

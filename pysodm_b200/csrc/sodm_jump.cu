@@ -23,11 +23,12 @@ __global__ void __launch_bounds__(JUMP_BLOCK) tau_leap_kernel(const __grid_const
     w.a = reinterpret_cast<uint32_t*>(smem) + 2 * M::NDRAW * JUMP_BLOCK + warp * 32;
     w.b = reinterpret_cast<uint32_t*>(smem) + 3 * M::NDRAW * JUMP_BLOCK + warp * 32;
     uint16_t* queues = reinterpret_cast<uint16_t*>(smem + 4 * M::NDRAW * JUMP_BLOCK);
-    w.qm = queues + warp * (M::NDRAW * 32 + COOP_QX_CAP);
-    w.qx = w.qm + M::NDRAW * 32;
+    w.qm = queues + warp * (M::NDRAW * 32 + COOP_QS_CAP + COOP_QX_CAP);
+    w.qs = w.qm + M::NDRAW * 32;
+    w.qx = w.qs + COOP_QS_CAP;
     w.stride = JUMP_BLOCK;
     w.lane = lane;
-    float* table = smem + 4 * M::NDRAW * JUMP_BLOCK + WARPS * (M::NDRAW * 32 + COOP_QX_CAP) / 2;
+    float* table = smem + 4 * M::NDRAW * JUMP_BLOCK + WARPS * (M::NDRAW * 32 + COOP_QS_CAP + COOP_QX_CAP) / 2;
     const int n_tab = L.n_tdpf_values * M::TDPF_COUNT;
     for (int e = threadIdx.x; e < n_tab; e += blockDim.x) table[e] = (float)L.tdpf_table[e];   // ABI speaks FP64, rates are FP32
     __syncthreads();
@@ -54,7 +55,7 @@ static int launch_jump(const JumpLaunch& L, int method, bool aligned, cudaStream
             cudaFuncSetAttribute(tau_leap_kernel<M, OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             attr_done = true;
         }
-        const size_t smem = ((size_t)4 * M::NDRAW * JUMP_BLOCK + (size_t)(JUMP_BLOCK / 32) * (M::NDRAW * 32 + COOP_QX_CAP) / 2 +
+        const size_t smem = ((size_t)4 * M::NDRAW * JUMP_BLOCK + (size_t)(JUMP_BLOCK / 32) * (M::NDRAW * 32 + COOP_QS_CAP + COOP_QX_CAP) / 2 +
                              (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
         if (aligned) tau_leap_kernel<M, OutT, true><<<grid, JUMP_BLOCK, smem, stream>>>(L);
         else         tau_leap_kernel<M, OutT, false><<<grid, JUMP_BLOCK, smem, stream>>>(L);

@@ -21,8 +21,8 @@ static void run_host(const JumpLaunch& L, int method, bool aligned) {
         int wn[M::NDRAW];
         float wp[M::NDRAW];
         uint32_t wa[M::NDRAW], wb[M::NDRAW];
-        uint16_t qm[M::NDRAW], qx[COOP_QX_CAP];
-        WorkList w{wn, wp, wa, wb, qm, qx, 1, 0, 1u};
+        uint16_t qm[M::NDRAW], qs[COOP_QS_CAP], qx[COOP_QX_CAP];
+        WorkList w{wn, wp, wa, wb, qm, qs, qx, 1, 0, 1u};
         if (method == SODM_JUMP_TAU_LEAP) {
             if (aligned) tau_leap_trajectory<M, OutT, true>(L, i, true, table.data(), w);
             else         tau_leap_trajectory<M, OutT, false>(L, i, true, table.data(), w);
