@@ -75,6 +75,7 @@ __host__ __device__ __forceinline__ float fast_log(float x) {
                              0.00925546218271273, 0.00833056343336287}
 #ifdef __CUDACC__
 static __constant__ double kStirlingTailDev[10] = SODM_STIRLING_TABLE;
+static __constant__ float kStirlingTailDevF[10] = SODM_STIRLING_TABLE;
 #endif
 
 // log(k!) - [ (k+1/2) log(k+1) - (k+1) + 1/2 log(2 pi) ]   (Stirling tail fc(k), Hoermann 1993)
@@ -109,8 +110,15 @@ __host__ __device__ __forceinline__ int binomial_inversion(Rng& rng, int n, floa
     return k;
 }
 
-// exact log f(k)/f(m) for Bin(n, p), m = floor((n+1)p)   (Hoermann 1993, BTRS step 3.2)
-__host__ __device__ __forceinline__ double binomial_log_ratio(double nd, double pd, double m, double kd) {
+// exact log f(k)/f(m) for Bin(n, p), m = floor((n+1)p)   (Hoermann 1993, BTRS step 3.2).  Rarely executed (modes
+// >= SODM_F32_MODE_LIMIT that the squeeze cannot settle) and large (three FP64 logarithms, twelve FP64 divisions):
+// kept out of line so that it does not occupy the instruction cache of the hot loop.
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+double binomial_log_ratio(double nd, double pd, double m, double kd) {
     const double r = pd / (1.0 - pd);
     return (m + 0.5) * log((m + 1.0) / (r * (nd - m + 1.0))) + stirling_tail(m) + stirling_tail(nd - m)
          + (nd + 1.0) * log((nd - m + 1.0) / (nd - kd + 1.0))
@@ -119,10 +127,16 @@ __host__ __device__ __forceinline__ double binomial_log_ratio(double nd, double 
 }
 
 __host__ __device__ __forceinline__ float stirling_tail_f(float k) {
-    if (k <= 9.0f) return (float)stirling_tail((double)k);
-    const float kp1 = k + 1.0f;
-    const float inv = 1.0f / (kp1 * kp1);
-    return (0.0833333333f - (0.00277777778f - 0.000793650794f * inv) * inv) / kp1;
+    if (k <= 9.0f) {
+#ifdef __CUDA_ARCH__
+        return kStirlingTailDevF[(int)k];
+#else
+        return (float)stirling_tail((double)k);
+#endif
+    }
+    const float r1 = fast_div(1.0f, k + 1.0f);
+    const float inv = r1 * r1;
+    return (0.0833333333f - (0.00277777778f - 0.000793650794f * inv) * inv) * r1;
 }
 
 // The same ratio in FP32, for modes below SODM_F32_MODE_LIMIT: the three logarithms are taken of ratios that
@@ -136,7 +150,7 @@ __host__ __device__ __forceinline__ float binomial_log_ratio_f32(float nf, float
     const float r = p / (1.0f - p);
     const float a = nf - m + 1.0f, b = nf - k + 1.0f;
     return (m + 0.5f) * logf((m + 1.0f) / (r * a)) + stirling_tail_f(m) + stirling_tail_f(nf - m)
-         + (nf + 1.0f) * log1pf((k - m) / b)
+         + (nf + 1.0f) * log1pf(fast_div(k - m, b))
          + (k + 0.5f) * logf(r * b / (k + 1.0f))
          - stirling_tail_f(k) - stirling_tail_f(nf - k);
 }
@@ -218,8 +232,14 @@ __host__ __device__ __forceinline__ int btrs_squeeze(int n, float p, int k, uint
     return BIN_EXACT;
 }
 
-// The exact acceptance test of candidate k (FP32 where harmless, FP64 otherwise).
-__host__ __device__ __forceinline__ bool btrs_exact_accept(int n, float p, int k, float lhs) {
+// The exact acceptance test of candidate k (FP32 where harmless, FP64 otherwise).  Out of line on the device: it runs
+// for a few per cent of the attempts only and would otherwise be replicated at every call site of the hot loop.
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+bool btrs_exact_accept(int n, float p, int k, float lhs) {
     const float nf = (float)n;
     const float mf = floorf((nf + 1.0f) * p);
     if (mf < SODM_F32_MODE_LIMIT && nf < 16777216.0f) return lhs <= binomial_log_ratio_f32(nf, p, mf, (float)k);

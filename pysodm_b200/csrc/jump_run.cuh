@@ -41,6 +41,7 @@ struct JumpLaunch {
     double tau;
     void* out;                 // [n_rows][n_out][ld_out]
     int8_t out_row[MAX_STATE]; // state s -> output row, or -1 (state not selected)
+    int64_t out_off[MAX_STATE];// state s -> element offset of its output row (row * n_out * ld_out), or -1
     int32_t* status;           // [n_traj] or null
     uint32_t compat;
     int64_t max_events;        // SSA event budget per trajectory
@@ -64,10 +65,10 @@ __host__ __device__ __forceinline__ void load_trajectory(const JumpLaunch& L, in
 
 template <class M, typename OutT>
 __host__ __device__ __forceinline__ void emit_counts(const JumpLaunch& L, int64_t i, int j, const int* y) {
-    OutT* out = (OutT*)L.out + i;
+    OutT* out = (OutT*)L.out + i + (int64_t)j * L.ld_out;        // column j of trajectory i
 #pragma unroll
     for (int s = 0; s < M::NS; ++s) {
-        if (L.out_row[s] >= 0) out[((int64_t)L.out_row[s] * L.n_out + j) * L.ld_out] = (OutT)y[s];
+        if (L.out_off[s] >= 0) out[L.out_off[s]] = (OutT)y[s];
     }
 }
 
@@ -179,7 +180,12 @@ struct StepKey {
     uint64_t traj0;      // global id of lane 0's trajectory
     uint32_t step;
 };
-__host__ __device__ __forceinline__ void philox_block(const StepKey& key, int lane, uint32_t tag, uint32_t (&out)[4]) {
+#ifdef __CUDA_ARCH__
+__device__ __noinline__          // one copy for the first pass and the re-draws: keeps the hot loop's code small
+#else
+inline
+#endif
+void philox_block(const StepKey& key, int lane, uint32_t tag, uint32_t (&out)[4]) {
     Philox4x32 g;
     g.init(key.seed, key.traj0 + (uint64_t)lane);
     g.ctr0 = key.step;
@@ -383,7 +389,7 @@ __host__ __device__ __forceinline__ void sample_worklist_walk(Rng& rng, WorkList
 
 // One trajectory per lane.  `active` = the lane owns a trajectory; the remaining lanes of a partially filled warp
 // still take part in the warp-cooperative sampling (they own no items) but neither load nor store.
-template <class M, typename OutT, bool ALIGNED>
+template <class M, typename OutT, bool ALIGNED, bool WALK>
 __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L, int64_t i, bool active,
                                                              const float* table, WorkList w) {
     double par[M::NPAR];
@@ -397,7 +403,6 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
         for (int s = 0; s < M::NS; ++s) y[s] = 0;
     }
     const bool quirk = (L.compat & COMPAT_STAY_QUIRK) != 0u;
-    const bool walk = (L.compat & COMPAT_WALK_DECOUPLED) != 0u;
     const float tau = (float)L.tau;
     const typename M::Pre pre = M::prepare(par, tau, quirk);
     PhiloxWords rng;                       // private stream of the per-lane walk
@@ -420,7 +425,7 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
         const float* tab = M::TDPF_COUNT ? table + (int64_t)L.tdpf_index[k] * M::TDPF_COUNT : table;
         M::propose(y, pre, tab, tau, quirk, w);
         key.step = (uint32_t)k;
-        if (walk) sample_worklist_walk<M::NDRAW, M::DEP_MASK>(rng, w, st);
+        if (WALK) sample_worklist_walk<M::NDRAW, M::DEP_MASK>(rng, w, st);
         else sample_worklist_coop<M::NDRAW, M::DEP_MASK>(key, w, st);
         M::apply(y, w);
         if (ALIGNED) {

@@ -81,6 +81,8 @@ inline int build_jump_launch(const sodm_jump_args* a, JumpLaunch& L, bool& align
             L.out_row[s] = (int8_t)r;
         }
     }
+    for (int s = 0; s < MAX_STATE; ++s)
+        L.out_off[s] = L.out_row[s] >= 0 ? (int64_t)L.out_row[s] * a->n_out * a->ld_out : -1;
     L.out = a->out;
     L.status = a->status;
     L.compat = a->compat;

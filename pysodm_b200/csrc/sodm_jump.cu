@@ -11,7 +11,7 @@ namespace sodm {
 
 constexpr int JUMP_BLOCK = 128;
 
-template <class M, typename OutT, bool ALIGNED>
+template <class M, typename OutT, bool ALIGNED, bool WALK>
 __global__ void __launch_bounds__(JUMP_BLOCK) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
     extern __shared__ float smem[];
     // 4 x [NDRAW][JUMP_BLOCK] words (draw counts | probabilities | 2 scratch words) | per-warp queues | TDPF table
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(JUMP_BLOCK) tau_leap_kernel(const __grid_const
     const bool active = i < L.n_traj;
     w.lanes = __ballot_sync(0xffffffffu, active);
     if (w.lanes == 0u) return;                                    // whole warp past the end
-    tau_leap_trajectory<M, OutT, ALIGNED>(L, i, active, table, w);
+    tau_leap_trajectory<M, OutT, ALIGNED, WALK>(L, i, active, table, w);
 }
 
 template <class M, typename OutT>
@@ -49,16 +49,13 @@ template <class M, typename OutT>
 static int launch_jump(const JumpLaunch& L, int method, bool aligned, cudaStream_t stream) {
     const unsigned grid = (unsigned)((L.n_traj + JUMP_BLOCK - 1) / JUMP_BLOCK);
     if (method == SODM_JUMP_TAU_LEAP) {
-        static bool attr_done = false;     // opt in to > 48 KB dynamic shared memory once per instantiation
-        if (!attr_done) {
-            cudaFuncSetAttribute(tau_leap_kernel<M, OutT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            cudaFuncSetAttribute(tau_leap_kernel<M, OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            attr_done = true;
-        }
         const size_t smem = ((size_t)4 * M::NDRAW * JUMP_BLOCK + (size_t)(JUMP_BLOCK / 32) * (M::NDRAW * 32 + COOP_QS_CAP + COOP_QX_CAP) / 2 +
                              (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
-        if (aligned) tau_leap_kernel<M, OutT, true><<<grid, JUMP_BLOCK, smem, stream>>>(L);
-        else         tau_leap_kernel<M, OutT, false><<<grid, JUMP_BLOCK, smem, stream>>>(L);
+        const bool walk = (L.compat & COMPAT_WALK_DECOUPLED) != 0u;
+        void (*kernel)(JumpLaunch) = aligned ? (walk ? tau_leap_kernel<M, OutT, true, true> : tau_leap_kernel<M, OutT, true, false>)
+                                             : (walk ? tau_leap_kernel<M, OutT, false, true> : tau_leap_kernel<M, OutT, false, false>);
+        SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        kernel<<<grid, JUMP_BLOCK, smem, stream>>>(L);
     } else {
         ssa_kernel<M, OutT><<<grid, JUMP_BLOCK, 0, stream>>>(L);
     }

@@ -24,8 +24,11 @@ static void run_host(const JumpLaunch& L, int method, bool aligned) {
         uint16_t qm[M::NDRAW], qs[COOP_QS_CAP], qx[COOP_QX_CAP];
         WorkList w{wn, wp, wa, wb, qm, qs, qx, 1, 0, 1u};
         if (method == SODM_JUMP_TAU_LEAP) {
-            if (aligned) tau_leap_trajectory<M, OutT, true>(L, i, true, table.data(), w);
-            else         tau_leap_trajectory<M, OutT, false>(L, i, true, table.data(), w);
+            const bool walk = (L.compat & COMPAT_WALK_DECOUPLED) != 0u;
+            if (aligned) { if (walk) tau_leap_trajectory<M, OutT, true, true>(L, i, true, table.data(), w);
+                           else      tau_leap_trajectory<M, OutT, true, false>(L, i, true, table.data(), w); }
+            else         { if (walk) tau_leap_trajectory<M, OutT, false, true>(L, i, true, table.data(), w);
+                           else      tau_leap_trajectory<M, OutT, false, false>(L, i, true, table.data(), w); }
         } else {
             ssa_trajectory<M, OutT>(L, i);
         }
