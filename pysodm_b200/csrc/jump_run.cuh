@@ -109,11 +109,13 @@ __host__ __device__ __forceinline__ void emit_interp(const JumpLaunch& L, int64_
 struct WorkList {
     int* n;             // warp base pointers: element (d, lane) at [d * stride + lane]
     float* p;
-    uint32_t* a;        // scratch: random word / BTRS candidate k of a pending item
-    uint32_t* b;        // scratch: random word / log of the scaled uniform of a pending item
-    uint16_t* qm;       // warp queue: BTRS items from the front, inversion items from the back ((d << 5) | lane)
-    uint16_t* qs;       // warp queue: candidates outside the BTRS box, waiting for the squeeze
-    uint16_t* qx;       // warp queue: items waiting for the exact acceptance test
+    uint16_t* qm;       // warp queue of items ((d << 5) | lane): BTRS regime from the front, inversion regime from the back
+    uint16_t* qs;       // candidates outside the BTRS box, waiting for the squeeze; payload = the attempt's two words
+    uint32_t* qs_u;
+    uint32_t* qs_v;
+    uint16_t* qx;       // candidates the squeeze could not settle, waiting for the exact test; payload = k, log(scaled v)
+    uint32_t* qx_k;
+    float* qx_l;
     int stride;
     int lane;
     unsigned lanes;     // device: lanes of the warp that run a trajectory
@@ -134,8 +136,13 @@ inline unsigned coop_lt(int) { return 0u; }
 inline int coop_popc(unsigned m) { return (int)(m & 1u); }
 inline void coop_sync() {}
 #endif
-constexpr int COOP_QS_CAP = 256;
-constexpr int COOP_QX_CAP = 256;      // >= COOP_QS_CAP: one squeeze drain can never overflow it
+constexpr int COOP_QS_CAP = 96;
+constexpr int COOP_QX_CAP = 96;       // >= COOP_QS_CAP: one squeeze drain can never overflow it
+
+// 4-byte words of queue storage per warp: qm, qs (+2 payload words), qx (+2 payload words)
+__host__ __device__ constexpr int coop_queue_words(int ndraw) {
+    return (ndraw * 32 + COOP_QS_CAP + COOP_QX_CAP) / 2 + 2 * COOP_QS_CAP + 2 * COOP_QX_CAP;
+}
 
 __host__ __device__ __forceinline__ float word_as_float(uint32_t w) {
 #ifdef __CUDA_ARCH__
@@ -173,8 +180,9 @@ __host__ __device__ constexpr int max_level(uint32_t dep_mask, int ndraw) {
 }
 
 // Random words of one (trajectory, step): counter-based, so ANY lane can regenerate the words of ANY item.
-//   first attempt of slots 2b, 2b+1 : Philox(seed; step, 0x20000000 | b,                     traj)
-//   attempt a >= 1 of slot d        : Philox(seed; step, 0x30000000 | d << 16 | a,           traj)   (words 0,1)
+//   attempts 2c and 2c+1 of slot d : Philox(seed; step, 0x20000000 | d << 16 | c, traj)   (words 0,1 and 2,3)
+//   inversion of slot d            : the same block c = 0, word 0
+// Nothing random is stored: a pending item carries at most its attempt's two words through the squeeze queue.
 struct StepKey {
     uint64_t seed;
     uint64_t traj0;      // global id of lane 0's trajectory
@@ -215,25 +223,10 @@ __host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key
     for (int level = 0; level < LEVELS; ++level) {
         const uint32_t in_level = level_mask(DEP_MASK, NDRAW, level);
         int nb = 0, ni = 0, nx = 0;
-        // ---- pass 0 -------------------------------------------------------------------------------------------
-        uint32_t blk[4] = {0u, 0u, 0u, 0u};
+        // ---- pass 0: own slots -> trivial results, regime queues ----------------------------------------------------
 #pragma unroll 1
         for (int d = 0; d < NDRAW; ++d) {
-            uint32_t wu, wv;
-            if (level == 0) {
-                if ((d & 1) == 0) philox_block(key, lane, 0x20000000u | (uint32_t)(d >> 1), blk);
-                wu = (d & 1) ? blk[2] : blk[0];
-                wv = (d & 1) ? blk[3] : blk[1];
-                if (!((in_level >> d) & 1u)) {            // a later level's slot: park its words
-                    w.a[d * S + lane] = wu;
-                    w.b[d * S + lane] = wv;
-                    continue;
-                }
-            } else {
-                if (!((in_level >> d) & 1u)) continue;
-                wu = w.a[d * S + lane];
-                wv = w.b[d * S + lane];
-            }
+            if (!((in_level >> d) & 1u)) continue;
             int n = w.n[d * S + lane];
             const float p = w.p[d * S + lane];
             if (level > 0) { n -= w.n[(d - 1) * S + lane]; w.n[d * S + lane] = n; }   // what the previous exit left behind
@@ -242,9 +235,6 @@ __host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key
             if (state == BIN_DONE) {
                 if (k < 0) { st |= ST_BAD_PROB; k = 0; }
                 w.n[d * S + lane] = k;
-            } else {
-                w.a[d * S + lane] = wu;
-                w.b[d * S + lane] = wv;
             }
             const unsigned mB = coop_ballot(state == BIN_BTRS), mI = coop_ballot(state == BIN_INVERT);
             if (state == BIN_BTRS) w.qm[nb + coop_popc(mB & lt)] = (uint16_t)((d << 5) | lane);
@@ -266,40 +256,40 @@ __host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key
                 const bool valid = base + lane < count;
                 int state = BIN_DONE;
                 uint16_t e = 0;
+                uint32_t wu = 0u, wv = 0u;
                 if (valid) {
                     e = w.qm[base + lane];
                     const int d = e >> 5, o = e & 31;
                     const int n = w.n[d * S + o];
                     const float p = w.p[d * S + o];
                     const bool flip = p > 0.5f;
-                    uint32_t wu, wv;
-                    if (attempt == 0u) {
-                        wu = w.a[d * S + o];
-                        wv = w.b[d * S + o];
-                    } else {
-                        uint32_t r[4];
-                        philox_block(key, o, 0x30000000u | ((uint32_t)d << 16) | attempt, r);
-                        wu = r[0];
-                        wv = r[1];
-                    }
+                    uint32_t r[4];
+                    philox_block(key, o, 0x20000000u | ((uint32_t)d << 16) | (attempt >> 1), r);
+                    wu = (attempt & 1u) ? r[2] : r[0];
+                    wv = (attempt & 1u) ? r[3] : r[1];
                     int k;
                     state = btrs_candidate(n, flip ? 1.0f - p : p, wu, wv, k);
                     if (state == BIN_DONE) w.n[d * S + o] = flip ? n - k : k;
-                    else if (state == BIN_SQUEEZE && attempt != 0u) { w.a[d * S + o] = wu; w.b[d * S + o] = wv; }
                 }
                 coop_sync();                                 // every lane has read its queue entry
                 const unsigned mR = coop_ballot(valid && state == BIN_RETRY), mS = coop_ballot(valid && state == BIN_SQUEEZE);
                 if (valid && state == BIN_RETRY) w.qm[keep + coop_popc(mR & lt)] = e;
-                if (valid && state == BIN_SQUEEZE) w.qs[ns + coop_popc(mS & lt)] = e;
+                if (valid && state == BIN_SQUEEZE) {
+                    const int q = ns + coop_popc(mS & lt);
+                    w.qs[q] = e;
+                    w.qs_u[q] = wu;
+                    w.qs_v[q] = wv;
+                }
                 keep += coop_popc(mR);
                 ns += coop_popc(mS);
                 coop_sync();
                 const bool last = base + COOP_LANES >= count;
                 if (ns > COOP_QS_CAP - COOP_LANES || last) {
-                    // ---- squeeze: the words of the attempt are parked in a/b; candidate k is recomputed ----
+                    // ---- squeeze ----
                     for (int sb = 0; sb < ns; sb += COOP_LANES) {
                         const bool sv = sb + lane < ns;
-                        int sstate = BIN_DONE;
+                        int sstate = BIN_DONE, k = 0;
+                        float lhs = 0.0f;
                         uint16_t se = 0;
                         if (sv) {
                             se = w.qs[sb + lane];
@@ -308,17 +298,19 @@ __host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key
                             const float p = w.p[d * S + o];
                             const bool flip = p > 0.5f;
                             const float pp = flip ? 1.0f - p : p;
-                            const uint32_t wu = w.a[d * S + o], wv = w.b[d * S + o];
-                            int k;
-                            float lhs = 0.0f;
-                            btrs_candidate(n, pp, wu, wv, k);
-                            sstate = btrs_squeeze(n, pp, k, wu, wv, lhs);
+                            const uint32_t su = w.qs_u[sb + lane], sw = w.qs_v[sb + lane];
+                            btrs_candidate(n, pp, su, sw, k);
+                            sstate = btrs_squeeze(n, pp, k, su, sw, lhs);
                             if (sstate == BIN_DONE) w.n[d * S + o] = flip ? n - k : k;
-                            else if (sstate == BIN_EXACT) { w.a[d * S + o] = (uint32_t)k; w.b[d * S + o] = float_as_word(lhs); }
                         }
                         const unsigned mR2 = coop_ballot(sv && sstate == BIN_RETRY), mX = coop_ballot(sv && sstate == BIN_EXACT);
                         if (sv && sstate == BIN_RETRY) w.qm[keep + coop_popc(mR2 & lt)] = se;
-                        if (sv && sstate == BIN_EXACT) w.qx[nx + coop_popc(mX & lt)] = se;
+                        if (sv && sstate == BIN_EXACT) {
+                            const int q = nx + coop_popc(mX & lt);
+                            w.qx[q] = se;
+                            w.qx_k[q] = (uint32_t)k;
+                            w.qx_l[q] = lhs;
+                        }
                         keep += coop_popc(mR2);
                         nx += coop_popc(mX);
                         coop_sync();
@@ -335,9 +327,8 @@ __host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key
                             const int n = w.n[d * S + o];
                             const float p = w.p[d * S + o];
                             const bool flip = p > 0.5f;
-                            const int k = (int)w.a[d * S + o];
-                            if (btrs_exact_accept(n, flip ? 1.0f - p : p, k, word_as_float(w.b[d * S + o])))
-                                w.n[d * S + o] = flip ? n - k : k;
+                            const int k = (int)w.qx_k[xb + lane];
+                            if (btrs_exact_accept(n, flip ? 1.0f - p : p, k, w.qx_l[xb + lane])) w.n[d * S + o] = flip ? n - k : k;
                             else fail = true;
                         }
                         const unsigned mF = coop_ballot(fail);
@@ -359,7 +350,9 @@ __host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key
                 const int n = w.n[d * S + o];
                 const float p = w.p[d * S + o];
                 const bool flip = p > 0.5f;
-                const int k = binomial_inversion_word(n, flip ? 1.0f - p : p, w.a[d * S + o]);
+                uint32_t r[4];
+                philox_block(key, o, 0x20000000u | ((uint32_t)d << 16), r);
+                const int k = binomial_inversion_word(n, flip ? 1.0f - p : p, r[0]);
                 w.n[d * S + o] = flip ? n - k : k;
             }
         }

@@ -14,21 +14,24 @@ constexpr int JUMP_BLOCK = 128;
 template <class M, typename OutT, bool ALIGNED, bool WALK>
 __global__ void __launch_bounds__(JUMP_BLOCK) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
     extern __shared__ float smem[];
-    // 4 x [NDRAW][JUMP_BLOCK] words (draw counts | probabilities | 2 scratch words) | per-warp queues | TDPF table
+    // [NDRAW][JUMP_BLOCK] draw counts | [NDRAW][JUMP_BLOCK] probabilities | per-warp queues | TDPF table
     constexpr int WARPS = JUMP_BLOCK / 32;
+    constexpr int QW = coop_queue_words(M::NDRAW);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WorkList w;
     w.n = reinterpret_cast<int*>(smem) + warp * 32;
     w.p = smem + M::NDRAW * JUMP_BLOCK + warp * 32;
-    w.a = reinterpret_cast<uint32_t*>(smem) + 2 * M::NDRAW * JUMP_BLOCK + warp * 32;
-    w.b = reinterpret_cast<uint32_t*>(smem) + 3 * M::NDRAW * JUMP_BLOCK + warp * 32;
-    uint16_t* queues = reinterpret_cast<uint16_t*>(smem + 4 * M::NDRAW * JUMP_BLOCK);
-    w.qm = queues + warp * (M::NDRAW * 32 + COOP_QS_CAP + COOP_QX_CAP);
+    uint32_t* q = reinterpret_cast<uint32_t*>(smem) + 2 * M::NDRAW * JUMP_BLOCK + warp * QW;
+    w.qs_u = q;
+    w.qs_v = q + COOP_QS_CAP;
+    w.qx_k = q + 2 * COOP_QS_CAP;
+    w.qx_l = reinterpret_cast<float*>(q + 2 * COOP_QS_CAP + COOP_QX_CAP);
+    w.qm = reinterpret_cast<uint16_t*>(q + 2 * COOP_QS_CAP + 2 * COOP_QX_CAP);
     w.qs = w.qm + M::NDRAW * 32;
     w.qx = w.qs + COOP_QS_CAP;
     w.stride = JUMP_BLOCK;
     w.lane = lane;
-    float* table = smem + 4 * M::NDRAW * JUMP_BLOCK + WARPS * (M::NDRAW * 32 + COOP_QS_CAP + COOP_QX_CAP) / 2;
+    float* table = smem + 2 * M::NDRAW * JUMP_BLOCK + WARPS * QW;
     const int n_tab = L.n_tdpf_values * M::TDPF_COUNT;
     for (int e = threadIdx.x; e < n_tab; e += blockDim.x) table[e] = (float)L.tdpf_table[e];   // ABI speaks FP64, rates are FP32
     __syncthreads();
@@ -49,7 +52,7 @@ template <class M, typename OutT>
 static int launch_jump(const JumpLaunch& L, int method, bool aligned, cudaStream_t stream) {
     const unsigned grid = (unsigned)((L.n_traj + JUMP_BLOCK - 1) / JUMP_BLOCK);
     if (method == SODM_JUMP_TAU_LEAP) {
-        const size_t smem = ((size_t)4 * M::NDRAW * JUMP_BLOCK + (size_t)(JUMP_BLOCK / 32) * (M::NDRAW * 32 + COOP_QS_CAP + COOP_QX_CAP) / 2 +
+        const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)(JUMP_BLOCK / 32) * coop_queue_words(M::NDRAW) +
                              (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
         const bool walk = (L.compat & COMPAT_WALK_DECOUPLED) != 0u;
         void (*kernel)(JumpLaunch) = aligned ? (walk ? tau_leap_kernel<M, OutT, true, true> : tau_leap_kernel<M, OutT, true, false>)

@@ -20,9 +20,10 @@ static void run_host(const JumpLaunch& L, int method, bool aligned) {
     for (int64_t i = 0; i < L.n_traj; ++i) {
         int wn[M::NDRAW];
         float wp[M::NDRAW];
-        uint32_t wa[M::NDRAW], wb[M::NDRAW];
         uint16_t qm[M::NDRAW], qs[COOP_QS_CAP], qx[COOP_QX_CAP];
-        WorkList w{wn, wp, wa, wb, qm, qs, qx, 1, 0, 1u};
+        uint32_t qsu[COOP_QS_CAP], qsv[COOP_QS_CAP], qxk[COOP_QX_CAP];
+        float qxl[COOP_QX_CAP];
+        WorkList w{wn, wp, qm, qs, qsu, qsv, qx, qxk, qxl, 1, 0, 1u};
         if (method == SODM_JUMP_TAU_LEAP) {
             const bool walk = (L.compat & COMPAT_WALK_DECOUPLED) != 0u;
             if (aligned) { if (walk) tau_leap_trajectory<M, OutT, true, true>(L, i, true, table.data(), w);
