@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsodm.so")
+LIB_PATH = os.environ.get("PYSODM_B200_LIB") or os.path.join(_HERE, "libsodm.so")     # override: tuning builds only
 
 # constants mirrored from include/sodm.h
 ABI_VERSION = 1

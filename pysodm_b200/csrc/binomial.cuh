@@ -140,11 +140,14 @@ __host__ __device__ __forceinline__ float stirling_tail_f(float k) {
 }
 
 // The same ratio in FP32, for modes below SODM_F32_MODE_LIMIT: the three logarithms are taken of ratios that
-// are 1 + O(1/m), so the absolute error is ~ m * 2^-23 (< 3e-4 at the limit) -- an error in an ACCEPTANCE
-// PROBABILITY that is only consulted for the ~2 % of attempts the squeeze cannot settle, i.e. a distortion of
-// the sampled law below 1e-5, far under Monte-Carlo resolution at 10^6 trajectories.
+// are 1 + O(1/m), so the absolute error is ~ 3 m * 2^-23 (< 3e-3 at the limit) -- an error in an ACCEPTANCE
+// PROBABILITY that is only consulted for the <= 2 % of attempts the squeeze cannot settle (far fewer at such large
+// modes, where the squeeze band is ~1/sqrt(npq) wide), i.e. a distortion of the sampled law below 6e-5, an order
+// of magnitude under the Monte-Carlo resolution of a KS test at 10^6 trajectories (1.6e-3).  Measured effect of
+// the limit on influenza (B200): 2048 -> 259 ms, 8192 -> 242 ms per 2^20 trajectories (the S->E draws of the large
+// age groups have modes of ~7000 and otherwise take the FP64 path, ~1000 instructions at 1-2 active lanes).
 #ifndef SODM_F32_MODE_LIMIT
-#define SODM_F32_MODE_LIMIT 2048.0f
+#define SODM_F32_MODE_LIMIT 8192.0f
 #endif
 __host__ __device__ __forceinline__ float binomial_log_ratio_f32(float nf, float p, float m, float k) {
     const float r = p / (1.0f - p);

@@ -18,7 +18,7 @@ namespace sodm {
 constexpr int MAX_PARAM = 32;   // flat parameter elements passed by value
 constexpr int MAX_STATE = 32;   // flat state elements of a jump model
 
-enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, COMPAT_WALK_DECOUPLED = 256u };
+enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, TUNE_COOPERATIVE = 256u };
 
 struct JumpLaunch {
     int64_t n_traj;            // trajectories in this launch
@@ -201,17 +201,22 @@ void philox_block(const StepKey& key, int lane, uint32_t tag, uint32_t (&out)[4]
     g.next4(out);
 }
 
-// WARP-COOPERATIVE sampler (default).  In a divergent SIMT loop the warp pays (trips) x (union of the branches any
-// lane takes), and a per-lane rejection sampler takes a different branch on almost every lane: measured on this
-// kernel, 8 of 32 lanes were active per instruction (profiles/).  Here the 32 x NDRAW draws of a warp-step are
-// pooled instead: every lane classifies its own slots and appends them to warp queues by REGIME; the queues are
-// then processed 32 items at a time, so all lanes of the warp run the same code on different items:
+// WARP-COOPERATIVE sampler (tuning flag SODM_TUNE_COOPERATIVE; NOT the default -- see the measurements below).
+// In a divergent SIMT loop the warp pays (trips) x (union of the branches any lane takes), and a per-lane rejection
+// sampler takes a different branch on almost every lane: measured on the per-lane walk, 8-9 of 32 lanes are active
+// per instruction (profiles/).  Here the 32 x NDRAW draws of a warp-step are pooled instead: every lane classifies
+// its own slots and appends them to warp queues by REGIME; the queues are then processed 32 items at a time, so all
+// lanes of the warp run the same code on different items:
 //   pass 0   own slots: trivial cases, first-attempt random words, queue by regime (ballot + popc compaction)
 //   BTRS     first attempts; accepted -> result; rejected -> compacted in place for the next round with fresh
 //            counter-based words; undecided by the squeeze -> exact-test queue
 //   exact    log-pmf ratio test on queued candidates; failures rejoin the BTRS queue
 //   inverse  sequential-search inversion on the small-mean items
 // Items conditional on another slot (DEP_MASK) form a second level that runs after the first is final.
+// Measured on B200 (influenza, 2^20 trajectories, profiles/r1_sampler_ab.txt): 22 of 32 lanes active and 40 % fewer
+// warp instructions than the walk, but the queue traffic through shared memory, the ballots and the extra Philox
+// blocks leave it at 3.6 M traj/s against 4.3 M traj/s for the walk at 32 resident warps per SM; it is kept for
+// models whose draws are more expensive relative to the bookkeeping.
 template <int NDRAW, uint32_t DEP_MASK>
 __host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key, WorkList& w, uint32_t& st) {
     static_assert(NDRAW <= 32, "at most 32 draws per step");
@@ -360,8 +365,9 @@ __host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key
     }
 }
 
-// Per-lane walk (tuning flag COMPAT_WALK_DECOUPLED, kept for A/B measurements): each lane draws its own slots one
-// after the other with a private Philox stream, retrying rejected attempts without waiting for its neighbours.
+// Per-lane walk (default): each lane draws its own slots one after the other with a private Philox stream, retrying
+// a rejected attempt on its next trip through the loop while its neighbours move on to their next slot -- the warp
+// runs for max_lane(sum of attempts) trips instead of sum_slot(max_lane attempts).  One copy of the sampler code.
 template <int NDRAW, uint32_t DEP_MASK, class Rng>
 __host__ __device__ __forceinline__ void sample_worklist_walk(Rng& rng, WorkList& w, uint32_t& st) {
     const int S = w.stride, lane = w.lane;
@@ -382,7 +388,7 @@ __host__ __device__ __forceinline__ void sample_worklist_walk(Rng& rng, WorkList
 
 // One trajectory per lane.  `active` = the lane owns a trajectory; the remaining lanes of a partially filled warp
 // still take part in the warp-cooperative sampling (they own no items) but neither load nor store.
-template <class M, typename OutT, bool ALIGNED, bool WALK>
+template <class M, typename OutT, bool ALIGNED, bool COOP>
 __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L, int64_t i, bool active,
                                                              const float* table, WorkList w) {
     double par[M::NPAR];
@@ -418,8 +424,8 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
         const float* tab = M::TDPF_COUNT ? table + (int64_t)L.tdpf_index[k] * M::TDPF_COUNT : table;
         M::propose(y, pre, tab, tau, quirk, w);
         key.step = (uint32_t)k;
-        if (WALK) sample_worklist_walk<M::NDRAW, M::DEP_MASK>(rng, w, st);
-        else sample_worklist_coop<M::NDRAW, M::DEP_MASK>(key, w, st);
+        if (COOP) sample_worklist_coop<M::NDRAW, M::DEP_MASK>(key, w, st);
+        else sample_worklist_walk<M::NDRAW, M::DEP_MASK>(rng, w, st);
         M::apply(y, w);
         if (ALIGNED) {
             if (--until_out == 0) {

@@ -10,9 +10,18 @@
 namespace sodm {
 
 constexpr int JUMP_BLOCK = 128;
+// Resident blocks per SM the compiler must allow for.  The samplers are latency / instruction-fetch bound (ncu:
+// `no_instruction` is the top stall), so resident warps matter more than registers: measured on influenza,
+// per-lane walk 352 / 272 / 262 / 259 ms at 1 / 5 / 6 / 8 blocks, cooperative 339 / 294 / 311 / 426 ms.
+#ifndef SODM_WALK_MIN_BLOCKS
+#define SODM_WALK_MIN_BLOCKS 8
+#endif
+#ifndef SODM_COOP_MIN_BLOCKS
+#define SODM_COOP_MIN_BLOCKS 5
+#endif
 
-template <class M, typename OutT, bool ALIGNED, bool WALK>
-__global__ void __launch_bounds__(JUMP_BLOCK) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
+template <class M, typename OutT, bool ALIGNED, bool COOP>
+__global__ void __launch_bounds__(JUMP_BLOCK, COOP ? SODM_COOP_MIN_BLOCKS : SODM_WALK_MIN_BLOCKS) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
     extern __shared__ float smem[];
     // [NDRAW][JUMP_BLOCK] draw counts | [NDRAW][JUMP_BLOCK] probabilities | per-warp queues | TDPF table
     constexpr int WARPS = JUMP_BLOCK / 32;
@@ -31,7 +40,7 @@ __global__ void __launch_bounds__(JUMP_BLOCK) tau_leap_kernel(const __grid_const
     w.qx = w.qs + COOP_QS_CAP;
     w.stride = JUMP_BLOCK;
     w.lane = lane;
-    float* table = smem + 2 * M::NDRAW * JUMP_BLOCK + WARPS * QW;
+    float* table = smem + 2 * M::NDRAW * JUMP_BLOCK + (COOP ? WARPS * QW : 0);       // the walk sampler has no queues
     const int n_tab = L.n_tdpf_values * M::TDPF_COUNT;
     for (int e = threadIdx.x; e < n_tab; e += blockDim.x) table[e] = (float)L.tdpf_table[e];   // ABI speaks FP64, rates are FP32
     __syncthreads();
@@ -39,7 +48,7 @@ __global__ void __launch_bounds__(JUMP_BLOCK) tau_leap_kernel(const __grid_const
     const bool active = i < L.n_traj;
     w.lanes = __ballot_sync(0xffffffffu, active);
     if (w.lanes == 0u) return;                                    // whole warp past the end
-    tau_leap_trajectory<M, OutT, ALIGNED, WALK>(L, i, active, table, w);
+    tau_leap_trajectory<M, OutT, ALIGNED, COOP>(L, i, active, table, w);
 }
 
 template <class M, typename OutT>
@@ -52,11 +61,11 @@ template <class M, typename OutT>
 static int launch_jump(const JumpLaunch& L, int method, bool aligned, cudaStream_t stream) {
     const unsigned grid = (unsigned)((L.n_traj + JUMP_BLOCK - 1) / JUMP_BLOCK);
     if (method == SODM_JUMP_TAU_LEAP) {
-        const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)(JUMP_BLOCK / 32) * coop_queue_words(M::NDRAW) +
+        const bool coop = (L.compat & TUNE_COOPERATIVE) != 0u;
+        const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK + (coop ? (size_t)(JUMP_BLOCK / 32) * coop_queue_words(M::NDRAW) : 0) +
                              (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
-        const bool walk = (L.compat & COMPAT_WALK_DECOUPLED) != 0u;
-        void (*kernel)(JumpLaunch) = aligned ? (walk ? tau_leap_kernel<M, OutT, true, true> : tau_leap_kernel<M, OutT, true, false>)
-                                             : (walk ? tau_leap_kernel<M, OutT, false, true> : tau_leap_kernel<M, OutT, false, false>);
+        void (*kernel)(JumpLaunch) = aligned ? (coop ? tau_leap_kernel<M, OutT, true, true> : tau_leap_kernel<M, OutT, true, false>)
+                                             : (coop ? tau_leap_kernel<M, OutT, false, true> : tau_leap_kernel<M, OutT, false, false>);
         SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         kernel<<<grid, JUMP_BLOCK, smem, stream>>>(L);
     } else {

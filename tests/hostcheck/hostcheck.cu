@@ -25,7 +25,7 @@ static void run_host(const JumpLaunch& L, int method, bool aligned) {
         float qxl[COOP_QX_CAP];
         WorkList w{wn, wp, qm, qs, qsu, qsv, qx, qxk, qxl, 1, 0, 1u};
         if (method == SODM_JUMP_TAU_LEAP) {
-            const bool walk = (L.compat & COMPAT_WALK_DECOUPLED) != 0u;
+            const bool walk = (L.compat & TUNE_COOPERATIVE) != 0u;   // template flag = cooperative sampler
             if (aligned) { if (walk) tau_leap_trajectory<M, OutT, true, true>(L, i, true, table.data(), w);
                            else      tau_leap_trajectory<M, OutT, true, false>(L, i, true, table.data(), w); }
             else         { if (walk) tau_leap_trajectory<M, OutT, false, true>(L, i, true, table.data(), w);

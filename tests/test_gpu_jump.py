@@ -244,3 +244,50 @@ def test_full_size_properties(eng, golden):
     del out
     out2, _ = eng.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, n, 0, cases.FLU_N_OUT, 0.5, **kw)
     assert int(out2.to(torch.int64).sum()) == checksum
+
+
+@pytest.mark.parametrize("coop", [False, True])
+@pytest.mark.parametrize("n,p", [(7_317_774, 1.2e-3), (4292, 0.28), (100, 0.3), (30, 0.4), (81, 0.13), (2_130_556, 0.02),
+                                 (200_000, 0.45), (1000, 0.005), (7_000_000, 1e-7), (12, 0.7), (3885, 0.133)])
+def test_device_binomial_is_exact(eng, coop, n, p):
+    """Chi-square goodness of fit of the DEVICE sampler (fast-math proposal, FP32/FP64 exact tests) against the exact
+    binomial pmf, driven through the public kernel: one tau-leap step of the dimensionless SIR with S = I = n, R = 0
+    and beta = -2 ln(1 - p) makes the S->I count Bin(n, p) (compat without the stay-probability quirk)."""
+    import torch
+    from scipy import stats
+    m = 400_000
+    beta = -2.0 * np.log1p(-p)
+    compat = 256 if coop else 0
+    out, st = eng.jump_run("sir_jump", [n, n, 0], [beta, 0.0], m, 0, 2, 1.0, seed=n % 1000 + 7, compat=compat,
+                           out_dtype=torch.int32)
+    assert int(st.abs().sum()) == 0
+    k = n - out[0, 1].cpu().numpy().astype(np.int64)
+    p_eff = float(-np.expm1(np.float32(-1.0) * np.float32(beta) * (np.float32(n) / np.float32(2 * n))))
+    lo, hi = int(k.min()), int(k.max())
+    assert 0 <= lo and hi <= n
+    ks = np.arange(lo, hi + 1)
+    obs = np.bincount(k - lo, minlength=len(ks)).astype(float)
+    exp = stats.binom.pmf(ks, n, p_eff) * m
+    big = exp >= 8
+    o = np.append(obs[big], obs[~big].sum())
+    e = np.append(exp[big], m - exp[big].sum())
+    if e[-1] < 4:
+        o, e = o[:-1], e[:-1]
+    if len(o) > 1:
+        chi2 = ((o - e) ** 2 / e).sum()
+        assert stats.chi2.sf(chi2, len(o) - 1) > 1e-4, (n, p, coop)
+
+
+def test_cooperative_sampler_has_the_same_law(eng, golden):
+    """SODM_TUNE_COOPERATIVE changes the schedule and the RNG streams, not the law."""
+    import torch
+    g, e = golden["jump_single"], golden["jump_ensemble"]
+    out, st = eng.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, 50_000, 0, cases.FLU_N_OUT, 0.5,
+                           tdpf=(g["flu_table"], g["flu_step_index"]), seed=21, out_dtype=torch.int32, compat=3 | 256)
+    assert int(st.abs().sum()) == 0
+    mine = _cpu(out)[:, e["flu_times"], :]
+    cases.assert_ks_ok(cases.ks_pvalues(mine, np.transpose(e["flu_ens"], (1, 2, 0))), "cooperative sampler vs reference")
+    part, _ = eng.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, 100, 0, cases.FLU_N_OUT, 0.5,
+                           tdpf=(g["flu_table"], g["flu_step_index"]), seed=21, out_dtype=torch.int32, compat=3 | 256,
+                           traj_id0=777)
+    assert torch.equal(part, out[:, :, 777:877])          # shard invariance holds for the cooperative schedule too
