@@ -1,0 +1,113 @@
+"""Throughput of the other BASELINE.json configurations (C1, C2, C4, C5 of SURVEY.md section 8d) on one B200.
+
+`bench.py` measures the headline metric (C3, influenza tau-leap); this script records the rest once per round into
+profiles/.  Device-resident timing with CUDA events, 1 warm-up + best of 3.  Usage: python tools/bench_configs.py [out.json]
+"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from pysodm_b200 import engine, tutorial_data as td
+
+
+def timed(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best
+
+
+def main():
+    dev = engine.device(0)
+    res = {}
+    rng = np.random.default_rng(1718)
+
+    # C1: SIR ODE, RK45 rtol 1e-4, t in [0, 120], N = 1e5 draws of beta
+    n = 100_000
+    betas = torch.from_numpy(rng.uniform(0.25, 0.45, size=n)).to(dev)
+    out = torch.empty((3, 121, n), dtype=torch.float64, device=dev)
+    ms = timed(lambda: engine.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], n, 0, 121, var=([0], betas[None, :]), out=out, dev=dev))
+    _, nfev, _ = engine.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], n, 0, 121, var=([0], betas[None, :]), out=out, dev=dev)
+    res["C1_sir_ode_rk45"] = {"n_traj": n, "ms": ms, "traj_per_s": n / ms * 1e3, "mean_nfev": float(nfev.double().mean()),
+                              "out_GBps": out.numel() * 8 / ms / 1e6}
+
+    # C2: SIR_SI tau-leap tau = 0.5, 120 d, N = 1e6 (int32 output); SSA at N = 1e4 on populations / 1000 and full size
+    y0 = torch.from_numpy(td.sirsi_flat_y0()).to(dev)
+    for n in (10_000, 100_000, 1_000_000):
+        out = torch.empty((14, 121, n), dtype=torch.int32, device=dev)
+        ms = timed(lambda: engine.jump_run("sir_si_jump", y0, td.sirsi_flat_par(), n, 0, 121, 0.5, seed=1, out_dtype=torch.int32, out=out, dev=dev))
+        res[f"C2_sir_si_tau_leap_n{n}"] = {"n_traj": n, "ms": ms, "traj_per_s": n / ms * 1e3}
+    del out
+    small = np.array([607, 1329, 7352, 2204, 0, 0, 0, 0, 0, 0, 0, 0, 1000, 2], dtype=np.float64)
+    n = 10_000
+    out = torch.empty((14, 121, n), dtype=torch.float64, device=dev)
+    ms = timed(lambda: engine.jump_run("sir_si_jump", small, td.sirsi_flat_par(), n, 0, 121, method="SSA", seed=1, out=out, dev=dev), reps=2)
+    res["C2_sir_si_ssa_pop_div_1000"] = {"n_traj": n, "ms": ms, "traj_per_s": n / ms * 1e3}
+    n = 2048
+    out = torch.empty((14, 31, n), dtype=torch.float64, device=dev)
+    t = time.perf_counter()
+    _, st = engine.jump_run("sir_si_jump", y0, td.sirsi_flat_par(), n, 0, 31, method="SSA", seed=1, out=out, dev=dev)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t
+    # events = every change of S (infection) + R (recovery) + vector switches are not all recoverable from the grid;
+    # report wall time per trajectory-day of the full-population model instead
+    res["C2_sir_si_ssa_full_population_30d"] = {"n_traj": n, "s": dt, "traj_days_per_s": n * 30 / dt,
+                                                "status_max": int(st.max())}
+    del out
+
+    # C4: packed PFR nx = 25, RK45, t in [0, 8000] s, 1e5 draws of the 5 kinetic parameters; output = final profile
+    n = 100_000
+    post = rng.normal(1.0, 0.03, size=(5, n)) * np.array([7.88e-04, 0.055, 2.64, 0.079, 0.418])[:, None]
+    var = ([4, 5, 6, 8, 7], torch.from_numpy(post).to(dev))
+    out = torch.empty((200, 1, n), dtype=torch.float64, device=dev)
+    ms = timed(lambda: engine.ode_run("packed_pfr_ode", td.pfr_flat_y0(25), td.pfr_flat_par(25), n, 0, 8001, model_arg=25,
+                                      out_last_only=True, var=var, out=out, dev=dev), reps=2)
+    _, nfev, st = engine.ode_run("packed_pfr_ode", td.pfr_flat_y0(25), td.pfr_flat_par(25), n, 0, 8001, model_arg=25,
+                                 out_last_only=True, var=var, out=out, dev=dev)
+    mean_nfev = float(nfev.double().mean())
+    flop = mean_nfev * 2.7e3 + (mean_nfev / 6) * 1.1e4
+    res["C4_packed_pfr_nx25_rk45"] = {"n_traj": n, "ms": ms, "traj_per_s": n / ms * 1e3, "mean_nfev": mean_nfev,
+                                      "fp64_tflops_est": flop * n / ms / 1e9, "status_max": int(st.max())}
+    del out
+
+    # C5: influenza calibration window (84 d), NB log-posterior of 1e5 particles: simulate 4 rows + reduce
+    n = 100_000
+    theta = np.column_stack([rng.uniform(1e-6, 0.08, n), rng.uniform(1e-3, 0.999, size=(n, 4))])
+    var = ([1, 4, 5, 6, 7], torch.from_numpy(np.ascontiguousarray(theta.T)).to(dev))
+    y0f = torch.from_numpy(td.influenza_flat_y0()).to(dev)
+    tab = torch.from_numpy(td.CONTACT_TABLE.reshape(3, 16).copy()).to(dev)
+    idx = torch.from_numpy(td.influenza_schedule(n_steps=168)).to(dev)
+    ydata = rng.gamma(2.0, 150.0, size=(13, 4))
+    traj = torch.empty((4, 85, n), dtype=torch.int32, device=dev)
+    lp = torch.zeros(n, dtype=torch.float64, device=dev)
+
+    def c5():
+        engine.jump_run("influenza_1718_jump", y0f, td.influenza_flat_par(), n, 0, 85, 0.5, var=var, tdpf=(tab, idx), seed=3,
+                        out_dtype=torch.int32, state_sel=[24, 25, 26, 27], out=traj, dev=dev)
+        engine.loglik("negative_binomial", traj, 0.0, [[0], [1], [2], [3]], np.arange(13) * 7.0, ydata, ll_arg=4 * [0.03], lp=lp, dev=dev)
+    ms = timed(c5)
+    res["C5_influenza_nb_log_posterior"] = {"n_particles": n, "ms": ms, "log_posteriors_per_s": n / ms * 1e3}
+    ms_ll = timed(lambda: engine.loglik("negative_binomial", traj, 0.0, [[0], [1], [2], [3]], np.arange(13) * 7.0, ydata,
+                                        ll_arg=4 * [0.03], lp=lp, dev=dev))
+    res["C5_loglik_kernel_only"] = {"n_particles": n, "ms": ms_ll, "GBps_read": 52 * 4 * n / ms_ll / 1e6}
+
+    text = json.dumps(res, indent=1)
+    print(text)
+    if len(sys.argv) > 1:
+        open(sys.argv[1], "w").write(text + "\n")
+
+
+if __name__ == "__main__":
+    main()
