@@ -264,6 +264,31 @@ __host__ __device__ __forceinline__ bool btrs_try(Rng& rng, int n, float p, int&
     return btrs_exact_accept(n, p, k, lhs);
 }
 
+// ONE attempt at Bin(n, p) from two given random words (the per-lane walk hands every trip exactly two words, so
+// that all lanes of a warp refill their Philox block on the same trips).  Same contract as binomial_try.
+__host__ __device__ __forceinline__ bool binomial_try_words(int n, float p, uint32_t wu, uint32_t wv, int& k) {
+    int state = binomial_classify(n, p, k);
+    if (state == BIN_DONE) return true;
+    const bool flip = p > 0.5f;
+    const float pp = flip ? 1.0f - p : p;
+    int kk;
+    bool done = true;
+    if (state == BIN_INVERT) {
+        kk = binomial_inversion_word(n, pp, wu);
+    } else {
+        state = btrs_candidate(n, pp, wu, wv, kk);
+        if (state == BIN_RETRY) done = false;
+        else if (state == BIN_SQUEEZE) {
+            float lhs = 0.0f;
+            state = btrs_squeeze(n, pp, kk, wu, wv, lhs);
+            if (state == BIN_RETRY) done = false;
+            else if (state == BIN_EXACT) done = btrs_exact_accept(n, pp, kk, lhs);
+        }
+    }
+    k = flip ? n - kk : kk;
+    return done;
+}
+
 // ONE attempt at Bin(n, p), 0 <= p <= 1.  Returns true when finished with the variate in k.
 // NaN / out-of-range p or n < 0 finish with k = -1 (the reference's NumPy call raises ValueError there;
 // callers turn -1 into a status flag).
