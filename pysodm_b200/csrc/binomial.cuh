@@ -149,9 +149,6 @@ __host__ __device__ __forceinline__ float stirling_tail_f(float k) {
 #ifndef SODM_F32_MODE_LIMIT
 #define SODM_F32_MODE_LIMIT 8192.0f
 #endif
-#ifndef SODM_EXACT_PRODUCT_SPAN
-#define SODM_EXACT_PRODUCT_SPAN 24
-#endif
 __host__ __device__ __forceinline__ float binomial_log_ratio_f32(float nf, float p, float m, float k) {
     const float r = p / (1.0f - p);
     const float a = nf - m + 1.0f, b = nf - k + 1.0f;
@@ -248,17 +245,6 @@ inline
 bool btrs_exact_accept(int n, float p, int k, float lhs) {
     const float nf = (float)n;
     const float mf = floorf((nf + 1.0f) * p);
-    const int m = (int)mf;
-    const int x = k - m;
-    if (x >= -SODM_EXACT_PRODUCT_SPAN && x <= SODM_EXACT_PRODUCT_SPAN && nf < 16777216.0f) {
-        // close to the mode: f(k)/f(m) as the product of the <= 24 ratios f(i)/f(i-1) = r (n-i+1)/i between them
-        // (BTPE step 5.1), in FP32 -- relative error ~ |x| ulp, no logarithm of the pmf, no Stirling series
-        const float r = p / (1.0f - p);
-        float F = 1.0f;
-        if (x > 0) { for (int i = m + 1; i <= k; ++i) F *= fast_div(r * (float)(n - i + 1), (float)i); }
-        else       { for (int i = k + 1; i <= m; ++i) F *= fast_div((float)i, r * (float)(n - i + 1)); }
-        return lhs <= fast_log(F);
-    }
     if (mf < SODM_F32_MODE_LIMIT && nf < 16777216.0f) return lhs <= binomial_log_ratio_f32(nf, p, mf, (float)k);
     const double nd = (double)n, pd = (double)p;
     return (double)lhs <= binomial_log_ratio(nd, pd, floor((nd + 1.0) * pd), (double)k);
