@@ -308,14 +308,18 @@ def run_gpu_arm(args):
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": prof.get("dram_bytes_per_launch"), "peak_source": peak_src,
-                    "kernel": "sodm::tau_leap_kernel<InfluenzaJump,int,true>", "kernel_ms": k_ms,
+                    "kernel": "sodm::tau_leap_kernel<InfluenzaJump,int,true,false>", "kernel_ms": k_ms,
                     "algorithmic_bytes_per_launch": n * BYTES_PER_TRAJ,
                     "note": "the kernel is ALU/issue-bound, not HBM-bound (7728 exact binomial variates per trajectory "
                             "vs 18 KB of output); see `alu`"}
         sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        # issue-slot roofline: one warp instruction per cycle per SM sub-partition (148 SMs x 4) at the measured clock;
+        # instructions per trajectory and the counters below come from the committed ncu capture of this kernel
         alu = {"binomial_variates_per_s": n * VARIATES_PER_TRAJ / (k_ms * 1e-3),
                "warp_inst_per_traj": prof.get("warp_inst_per_traj"),
-               "issue_slot_peak_per_s": 148 * 4 * sm_clock * 1e6}
+               "issue_slot_peak_per_s": 148 * 4 * sm_clock * 1e6,
+               "ncu_issue_active_pct": prof.get("issue_active_pct"), "ncu_lanes_per_inst": prof.get("lanes_per_inst"),
+               "ncu_source": prof.get("source")}
         if prof.get("warp_inst_per_traj"):
             alu["achieved_warp_inst_per_s"] = prof["warp_inst_per_traj"] * n / (k_ms * 1e-3)
             alu["frac"] = alu["achieved_warp_inst_per_s"] / alu["issue_slot_peak_per_s"]
