@@ -347,7 +347,35 @@ def gen_loglik():
     save('loglik.npz', **out)
 
 
+def optimizer_objective(x):
+    """Deterministic stand-in for a log posterior (to be MAXIMISED); shared with tests/test_optimization.py."""
+    x = np.asarray(x)
+    return -(np.sum((x - np.array([0.3, -1.2, 2.0])) ** 2) + 0.5 * np.sin(3 * x[0]) * x[1])
+
+
+OPTIMIZER_BOUNDS = [(-2, 2), (-3, 3), (0, 5)]
+
+
+def gen_optimizers():
+    """Seeded runs of the reference's pso.optimize / nelder_mead.optimize (pso.py:28, nelder_mead.py:19)."""
+    import contextlib
+    import io
+    import pySODM.optimization.nelder_mead as rnm
+    import pySODM.optimization.pso as rpso
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        for seed, S, it in [(1, 20, 15), (2, 64, 40)]:
+            np.random.seed(seed)
+            th, sc = rpso.optimize(optimizer_objective, bounds=OPTIMIZER_BOUNDS, swarmsize=S, max_iter=it)
+            out[f'pso_{seed}_theta'], out[f'pso_{seed}_score'] = np.asarray(th, dtype=float), np.array(sc)
+        th, sc = rnm.optimize(optimizer_objective, np.array([1.0, 1.0, 1.0]), [0.1, 0.1, 0.1], bounds=OPTIMIZER_BOUNDS, max_iter=60)
+        out['nm_theta'], out['nm_score'] = np.asarray(th, dtype=float), np.array(sc)
+        th, sc = rnm.optimize(optimizer_objective, np.array([1.9, 2.5, 0.2]), [0.3, 0.3, 0.3], bounds=OPTIMIZER_BOUNDS, max_iter=25)
+        out['nm2_theta'], out['nm2_score'] = np.asarray(th, dtype=float), np.array(sc)
+    save('optimizers.npz', **out)
+
+
 if __name__ == '__main__':
-    what = sys.argv[1:] or ['jump_single', 'ssa', 'jump_ensemble', 'schedule', 'ode', 'loglik']
+    what = sys.argv[1:] or ['jump_single', 'ssa', 'jump_ensemble', 'schedule', 'ode', 'loglik', 'optimizers']
     for w in what:
         globals()['gen_' + w]()

@@ -217,3 +217,21 @@ def test_log_posterior_ode_time_index(td):
         _, y, _ = ode.simulate(models.SIRRateODE, [1_000_000 - 10, 10, 0], {"beta": b, "gamma": 0.2}, 0, 60)
         want.append(oll.log_likelihood("normal", y, 0.0, [[1]], t, data.to_numpy(), 250.0))
     np.testing.assert_allclose(lp, want, rtol=1e-6)       # ODE trajectories agree to ~1e-12; ll amplifies by < 1e3
+
+
+def test_pso_calibration_recovers_parameter(td, capsys):
+    """The reference's calibration test in miniature (src/tests/test_calibration.py:440-479): PSO on an ODE model
+    recovers the beta that generated the data; every swarm iteration is ONE batched device evaluation."""
+    from pysodm_b200 import optimization, tutorial_models as tm
+    from pysodm_b200.objective_functions import ll_poisson, log_posterior_probability
+    truth = tm.ODE_SIR_rate({"S": 1_000_000 - 10, "I": 10}, {"beta": 0.9, "gamma": 0.2})
+    out = truth.sim(40)
+    t = np.arange(10, 41, 2)
+    data = pd.Series(out["I"].values[t], index=pd.Index(t.astype(float), name="time"))
+    model = tm.ODE_SIR_rate({"S": 1_000_000 - 10, "I": 10}, {"beta": 0.5, "gamma": 0.2})
+    lpp = log_posterior_probability(model, ["beta"], [(0.1, 2.0)], [data], ["I"], [ll_poisson], [[]], start_sim=0)
+    np.random.seed(0)
+    theta, score = optimization.pso(lpp, swarmsize=128, max_iter=20)
+    assert abs(theta[0] - 0.9) / 0.9 < 0.02
+    theta_nm, _ = optimization.nelder_mead(lpp, np.array([0.6]), [0.2], max_iter=30)
+    assert abs(theta_nm[0] - 0.9) / 0.9 < 0.02
