@@ -140,9 +140,9 @@ __host__ __device__ __forceinline__ float stirling_tail_f(float k) {
 }
 
 // The same ratio in FP32, for modes below SODM_F32_MODE_LIMIT: the three logarithms are taken of ratios that
-// are 1 + O(1/m), so the absolute error is ~ 3 m * 2^-23 (< 3e-3 at the limit) -- an error in an ACCEPTANCE
+// are 1 + O(1/m), so the absolute error is ~ 6 m * 2^-23 (< 6e-3 at the limit) -- an error in an ACCEPTANCE
 // PROBABILITY that is only consulted for the <= 2 % of attempts the squeeze cannot settle (far fewer at such large
-// modes, where the squeeze band is ~1/sqrt(npq) wide), i.e. a distortion of the sampled law below 6e-5, an order
+// modes, where the squeeze band is ~1/sqrt(npq) wide), i.e. a distortion of the sampled law below 1.2e-4, an order
 // of magnitude under the Monte-Carlo resolution of a KS test at 10^6 trajectories (1.6e-3).  Measured effect of
 // the limit on influenza (B200): 2048 -> 259 ms, 8192 -> 242 ms per 2^20 trajectories (the S->E draws of the large
 // age groups have modes of ~7000 and otherwise take the FP64 path, ~1000 instructions at 1-2 active lanes).
@@ -152,9 +152,11 @@ __host__ __device__ __forceinline__ float stirling_tail_f(float k) {
 __host__ __device__ __forceinline__ float binomial_log_ratio_f32(float nf, float p, float m, float k) {
     const float r = p / (1.0f - p);
     const float a = nf - m + 1.0f, b = nf - k + 1.0f;
-    return (m + 0.5f) * logf((m + 1.0f) / (r * a)) + stirling_tail_f(m) + stirling_tail_f(nf - m)
+    // the two plain logarithms take arguments 1 + O(1/sqrt(m)): the fast logarithm's absolute error (2^-21.4 there)
+    // times (m + 1/2) stays within the error budget stated above
+    return (m + 0.5f) * fast_log(fast_div(m + 1.0f, r * a)) + stirling_tail_f(m) + stirling_tail_f(nf - m)
          + (nf + 1.0f) * log1pf(fast_div(k - m, b))
-         + (k + 0.5f) * logf(r * b / (k + 1.0f))
+         + (k + 0.5f) * fast_log(fast_div(r * b, k + 1.0f))
          - stirling_tail_f(k) - stirling_tail_f(nf - k);
 }
 
@@ -304,14 +306,6 @@ __host__ __device__ __forceinline__ bool binomial_try(Rng& rng, int n, float p, 
     else done = btrs_try(rng, n, pp, kk);
     k = flip ? n - kk : kk;
     return done;
-}
-
-template <class Rng>
-__host__ __device__ __forceinline__ int binomial(Rng& rng, int n, float p) {
-    int k = 0;
-    for (int attempt = 0; attempt < 1000; ++attempt)
-        if (binomial_try(rng, n, p, k)) return k;
-    return k;
 }
 
 }  // namespace sodm
