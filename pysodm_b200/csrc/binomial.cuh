@@ -62,6 +62,13 @@ __host__ __device__ __forceinline__ float fast_div(float a, float b) {
     return a / b;
 #endif
 }
+__host__ __device__ __forceinline__ float fast_exp(float x) {
+#ifdef __CUDA_ARCH__
+    return __expf(x);
+#else
+    return expf(x);
+#endif
+}
 __host__ __device__ __forceinline__ float fast_log(float x) {
 #ifdef __CUDA_ARCH__
     return __logf(x);
@@ -75,7 +82,6 @@ __host__ __device__ __forceinline__ float fast_log(float x) {
                              0.00925546218271273, 0.00833056343336287}
 #ifdef __CUDACC__
 static __constant__ double kStirlingTailDev[10] = SODM_STIRLING_TABLE;
-static __constant__ float kStirlingTailDevF[10] = SODM_STIRLING_TABLE;
 #endif
 
 // log(k!) - [ (k+1/2) log(k+1) - (k+1) + 1/2 log(2 pi) ]   (Stirling tail fc(k), Hoermann 1993)
@@ -127,16 +133,12 @@ double binomial_log_ratio(double nd, double pd, double m, double kd) {
 }
 
 __host__ __device__ __forceinline__ float stirling_tail_f(float k) {
-    if (k <= 9.0f) {
-#ifdef __CUDA_ARCH__
-        return kStirlingTailDevF[(int)k];
-#else
-        return (float)stirling_tail((double)k);
-#endif
-    }
+    // series in 1/(k+1); its error is 3e-6 at k = 1 and smaller beyond, so only k = 0 needs the tabulated value
+    // (a per-lane table lookup would serialise in the constant cache)
     const float r1 = fast_div(1.0f, k + 1.0f);
     const float inv = r1 * r1;
-    return (0.0833333333f - (0.00277777778f - 0.000793650794f * inv) * inv) * r1;
+    const float series = (0.0833333333f - (0.00277777778f - 0.000793650794f * inv) * inv) * r1;
+    return k < 0.5f ? 0.0810614668f : series;
 }
 
 // The same ratio in FP32, for modes below SODM_F32_MODE_LIMIT: the three logarithms are taken of ratios that
@@ -178,7 +180,7 @@ __host__ __device__ __forceinline__ int binomial_classify(int n, float p, int& k
 // Sequential-search inversion driven by a given uniform word (0 < p <= 0.5, n*p small).
 __host__ __device__ __forceinline__ int binomial_inversion_word(int n, float p, uint32_t word) {
     const float s = p / (1.0f - p);
-    float f = expf((float)n * log1pf(-p));
+    float f = fast_exp((float)n * log1pf(-p));     // q^n = P(X = 0); n log q > -10.6 here, where __expf is good to ~1e-6
     float u = u01(word);
     int k = 0;
     while (u > f && k < n && k < 1024) {
