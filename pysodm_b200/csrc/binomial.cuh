@@ -62,6 +62,13 @@ __host__ __device__ __forceinline__ float fast_div(float a, float b) {
     return a / b;
 #endif
 }
+__host__ __device__ __forceinline__ float fast_sqrt(float x) {      // x > 0
+#ifdef __CUDA_ARCH__
+    return x * rsqrtf(x);
+#else
+    return sqrtf(x);
+#endif
+}
 __host__ __device__ __forceinline__ float fast_exp(float x) {
 #ifdef __CUDA_ARCH__
     return __expf(x);
@@ -198,7 +205,7 @@ enum : int { BIN_SQUEEZE = 5 };
 __host__ __device__ __forceinline__ int btrs_candidate(int n, float p, uint32_t wu, uint32_t wv, int& k) {
     const float nf = (float)n;
     const float np_ = nf * p;
-    const float stddev = sqrtf(np_ * (1.0f - p));
+    const float stddev = fast_sqrt(np_ * (1.0f - p));
     const float b = 1.15f + 2.53f * stddev;
     const float a = -0.0873f + 0.0248f * b + 0.01f * p;
     const float v_r = 0.92f - fast_div(4.2f, b);
@@ -218,7 +225,7 @@ __host__ __device__ __forceinline__ int btrs_candidate(int n, float p, uint32_t 
 __host__ __device__ __forceinline__ int btrs_squeeze(int n, float p, int k, uint32_t wu, uint32_t wv, float& lhs) {
     const float nf = (float)n;
     const float npq = nf * p * (1.0f - p);
-    const float stddev = sqrtf(npq);
+    const float stddev = fast_sqrt(npq);
     const float b = 1.15f + 2.53f * stddev;
     const float a = -0.0873f + 0.0248f * b + 0.01f * p;
     const float alpha = (2.83f + fast_div(5.1f, b)) * stddev;
