@@ -215,7 +215,7 @@ void philox_block(const StepKey& key, int lane, uint32_t tag, uint32_t (&out)[4]
 // Items conditional on another slot (DEP_MASK) form a second level that runs after the first is final.
 // Measured on B200 (influenza, 2^20 trajectories, profiles/r1_sampler_ab.txt): 22 of 32 lanes active and 40 % fewer
 // warp instructions than the walk, but the queue traffic through shared memory, the ballots and the extra Philox
-// blocks leave it at 3.6 M traj/s against 4.3 M traj/s for the walk at 32 resident warps per SM; it is kept for
+// blocks leave it at 4.6 M traj/s against 6.3 M traj/s for the walk at 32 resident warps per SM; it is kept for
 // models whose draws are more expensive relative to the bookkeeping.
 template <int NDRAW, uint32_t DEP_MASK>
 __host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key, WorkList& w, uint32_t& st) {
