@@ -83,24 +83,42 @@ struct PpbbOde {
 // cs: solid concentrations at node j.
 struct PfrNode {
     static constexpr int NPAR = 17;
-    __host__ __device__ static void rhs(const double* par, bool inlet, bool outlet, const double* cl, const double* cm,
+    // Per-trajectory coefficients, formed ONCE with the reference's own quotients (D_ax/dx^2, u/dx, kL_a/eps,
+    // kL_a/(1-eps), 1/K_eq -- `models.py:37-49`), so that a right-hand-side evaluation has one FP64 division (the
+    // kinetic denominator) instead of fourteen.  Same values as dividing in place, ~3x fewer instructions per call.
+    struct Coef {
+        double disp[4], film_f[4], film_s[4];
+        double conv, inv_keq, Vf_Ks, R_AS, R_AW, R_Es, rho_B;
+    };
+    __host__ __device__ static Coef coefficients(const double* par) {
+        Coef c;
+        const double dx = par[0], eps = par[1];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            c.disp[i] = par[13 + i] / (dx * dx);
+            c.film_f[i] = par[9 + i] / eps;
+            c.film_s[i] = par[9 + i] / (1.0 - eps);
+        }
+        c.conv = par[2] / dx;
+        c.inv_keq = 1.0 / par[7];
+        c.Vf_Ks = par[4]; c.R_AS = par[5]; c.R_AW = par[6]; c.R_Es = par[8]; c.rho_B = par[3];
+        return c;
+    }
+    __host__ __device__ static void rhs(const Coef& c, bool inlet, bool outlet, const double* cl, const double* cm,
                                         const double* cr, const double* cs, double* dcf, double* dcs) {
         if (inlet) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) { dcf[i] = 0.0; dcs[i] = 0.0; }
             return;
         }
-        const double dx = par[0], eps = par[1], u = par[2], rho_B = par[3];
-        const double v = (par[4] * (cs[0] * cs[1] - (1.0 / par[7]) * cs[2] * cs[3]) /
-                          (cs[1] + par[5] * cs[0] + par[6] * cs[3] + par[8] * cs[2])) / 60.0;
+        const double v = (c.Vf_Ks * (cs[0] * cs[1] - c.inv_keq * cs[2] * cs[3]) /
+                          (cs[1] + c.R_AS * cs[0] + c.R_AW * cs[3] + c.R_Es * cs[2])) / 60.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const double kla = par[9 + i], dax = par[13 + i];
             const double right = outlet ? cl[i] : cr[i];
-            dcf[i] = (dax / (dx * dx)) * (cl[i] - 2.0 * cm[i] + right) - (u / dx) * (cm[i] - cl[i]) +
-                     (kla / eps) * (cs[i] - cm[i]);
+            dcf[i] = c.disp[i] * (cl[i] - 2.0 * cm[i] + right) - c.conv * (cm[i] - cl[i]) + c.film_f[i] * (cs[i] - cm[i]);
             const double sto = i < 2 ? -1.0 : 1.0;
-            dcs[i] = -(kla / (1.0 - eps)) * (cs[i] - cm[i]) + rho_B * sto * v;
+            dcs[i] = -c.film_s[i] * (cs[i] - cm[i]) + c.rho_B * sto * v;
         }
     }
 };

@@ -349,7 +349,7 @@ struct ThreadSystem {                       // whole state in one thread
 template <int NX>
 struct PfrThreadSystem {
     static constexpr int NL = 8 * NX;
-    const double* par;
+    PfrNode::Coef coef;
     __host__ __device__ __forceinline__ int n_total() const { return NL; }
     __host__ __device__ __forceinline__ bool active(int) const { return true; }
     __host__ __device__ __forceinline__ bool leader() const { return true; }
@@ -364,7 +364,7 @@ struct PfrThreadSystem {
                 cr[s] = j < NX - 1 ? y[s * NX + j + 1] : 0.0;
                 cs[s] = y[4 * NX + s * NX + j];
             }
-            PfrNode::rhs(par, j == 0, j == NX - 1, cl, cm, cr, cs, dcf, dcs);
+            PfrNode::rhs(coef, j == 0, j == NX - 1, cl, cm, cr, cs, dcf, dcs);
             for (int s = 0; s < 4; ++s) { dy[s * NX + j] = dcf[s]; dy[4 * NX + s * NX + j] = dcs[s]; }
         }
     }

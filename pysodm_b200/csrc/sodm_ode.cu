@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(ODE_BLOCK) ode_thread_kernel(const __grid_cons
 template <int NPL>
 struct PfrWarpSystem {
     static constexpr int NL = 8 * NPL;
-    const double* par;
+    PfrNode::Coef coef;
     int nx, lane;
     __device__ __forceinline__ int n_total() const { return 8 * nx; }
     __device__ __forceinline__ bool active(int e) const { return lane * NPL + (e % NPL) < nx; }
@@ -53,7 +53,7 @@ struct PfrWarpSystem {
                 cr[s] = k < NPL - 1 ? y[s * NPL + k + 1] : from_right[s];
                 cs[s] = y[(4 + s) * NPL + k];
             }
-            PfrNode::rhs(par, j == 0, j == nx - 1, cl, cm, cr, cs, dcf, dcs);
+            PfrNode::rhs(coef, j == 0, j == nx - 1, cl, cm, cr, cs, dcf, dcs);
             const bool on = j < nx;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(ODE_BLOCK) ode_pfr_warp_kernel(const __grid_co
     if (i >= L.n_traj) return;                                   // whole warps leave together
     double par[PfrNode::NPAR];
     load_ode_params<PfrNode::NPAR>(L, i, par);
-    PfrWarpSystem<NPL> sys{par, L.nx, lane};
+    PfrWarpSystem<NPL> sys{PfrNode::coefficients(par), L.nx, lane};
     double y[8 * NPL];
 #pragma unroll
     for (int e = 0; e < 8 * NPL; ++e) {
