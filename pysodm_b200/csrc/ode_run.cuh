@@ -82,6 +82,14 @@ __host__ __device__ __forceinline__ int kept_index(const OdeLaunch& L, int g) {
     return (g % L.out_stride) == 0 ? g / L.out_stride : -1;
 }
 
+// smallest kept grid index >= g (n_out if there is none): lets the output loops jump over grid points that are not kept
+__host__ __device__ __forceinline__ int next_kept(const OdeLaunch& L, int g) {
+    if (L.out_last_only) return g <= L.n_out - 1 ? L.n_out - 1 : L.n_out;
+    const int r = g % L.out_stride;
+    const int k = r == 0 ? g : g + (L.out_stride - r);
+    return k < L.n_out ? k : L.n_out;
+}
+
 template <class Sys>
 __host__ __device__ __forceinline__ double rms_scaled(Sys& sys, const double* v, const double* scale) {
     double acc = 0.0;
@@ -217,9 +225,10 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
         }
         if (failed) { st |= ST_STEP_TOO_SMALL; break; }
         // ---- dense output for the grid points in (t_old, t_new] (and t0 itself on the first step) ------
+        g = next_kept(L, g);
         while (g < L.n_out && L.t0 + (double)g <= t_new) {
             const int kj = kept_index(L, g);
-            if (kj >= 0) {
+            {
                 const double x = (L.t0 + (double)g - t) / h;
                 const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
 #pragma unroll
@@ -238,7 +247,7 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
                 }
                 store_grid<Sys, OutT>(sys, L, i, kj, ytmp);
             }
-            ++g;
+            g = next_kept(L, g + 1);
         }
 #pragma unroll
         for (int e = 0; e < NL; ++e) { y[e] = ynew[e]; K1[e] = K7[e]; }

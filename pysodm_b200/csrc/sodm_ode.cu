@@ -12,6 +12,9 @@
 namespace sodm {
 
 constexpr int ODE_BLOCK = 128;
+#ifndef SODM_PFR_MIN_BLOCKS
+#define SODM_PFR_MIN_BLOCKS 2
+#endif
 
 template <class M, typename OutT>
 __global__ void __launch_bounds__(ODE_BLOCK) ode_thread_kernel(const __grid_constant__ OdeLaunch L, int method) {
@@ -65,7 +68,7 @@ struct PfrWarpSystem {
 };
 
 template <int NPL, typename OutT>
-__global__ void __launch_bounds__(ODE_BLOCK) ode_pfr_warp_kernel(const __grid_constant__ OdeLaunch L, int method) {
+__global__ void __launch_bounds__(ODE_BLOCK, SODM_PFR_MIN_BLOCKS) ode_pfr_warp_kernel(const __grid_constant__ OdeLaunch L, int method) {
     const int lane = threadIdx.x & 31;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= L.n_traj) return;                                   // whole warps leave together
