@@ -12,8 +12,11 @@
 namespace sodm {
 
 constexpr int ODE_BLOCK = 128;
+// resident blocks per SM for the reactor kernel: 248 registers / 2 blocks without the bound; measured on B200 (1e5 draws,
+// nx = 25): 330 / 294 / 310 ms at 2 / 3 / 4 blocks -- the kernel waits on FP64 dependency chains, so a third block helps
+// more than the spills cost
 #ifndef SODM_PFR_MIN_BLOCKS
-#define SODM_PFR_MIN_BLOCKS 2
+#define SODM_PFR_MIN_BLOCKS 3
 #endif
 
 template <class M, typename OutT>
