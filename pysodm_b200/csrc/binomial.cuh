@@ -147,6 +147,22 @@ __host__ __device__ __forceinline__ float stirling_tail_f(float k) {
     const float series = (0.0833333333f - (0.00277777778f - 0.000793650794f * inv) * inv) * r1;
     return k < 0.5f ? 0.0810614668f : series;
 }
+// the same for k >= 9 (the mode and n - mode of a BTRS variate: n p >= 10, p <= 1/2): two terms are exact to 1e-8
+__host__ __device__ __forceinline__ float stirling_tail_large_f(float k) {
+    const float r1 = fast_div(1.0f, k + 1.0f);
+    return (0.0833333333f - 0.00277777778f * r1 * r1) * r1;
+}
+
+// log(1 + x) to FP32 accuracy RELATIVE to the result (what the (n + 1) log(...) term needs): for |x| < 0.4 the
+// odd series of 2 atanh(x / (2 + x)) -- next term s^11 / 11 < 2e-9 relative -- else the library routine.
+__host__ __device__ __forceinline__ float log1p_rel(float x) {
+    if (fabsf(x) < 0.4f) {
+        const float s = fast_div(x, 2.0f + x);
+        const float s2 = s * s;
+        return 2.0f * s * fmaf(s2, fmaf(s2, fmaf(s2, fmaf(s2, 1.0f / 9.0f, 1.0f / 7.0f), 0.2f), 1.0f / 3.0f), 1.0f);
+    }
+    return log1pf(x);
+}
 
 // The same ratio in FP32, for modes below SODM_F32_MODE_LIMIT: the three logarithms are taken of ratios that
 // are 1 + O(1/m), so the absolute error is ~ 6 m * 2^-23 (< 6e-3 at the limit) -- an error in an ACCEPTANCE
@@ -159,12 +175,13 @@ __host__ __device__ __forceinline__ float stirling_tail_f(float k) {
 #define SODM_F32_MODE_LIMIT 8192.0f
 #endif
 __host__ __device__ __forceinline__ float binomial_log_ratio_f32(float nf, float p, float m, float k) {
-    const float r = p / (1.0f - p);
+    // r enters as (k - m) log r once the two logarithms below are added up, so an approximate quotient is harmless
+    const float r = fast_div(p, 1.0f - p);
     const float a = nf - m + 1.0f, b = nf - k + 1.0f;
     // the two plain logarithms take arguments 1 + O(1/sqrt(m)): the fast logarithm's absolute error (2^-21.4 there)
     // times (m + 1/2) stays within the error budget stated above
-    return (m + 0.5f) * fast_log(fast_div(m + 1.0f, r * a)) + stirling_tail_f(m) + stirling_tail_f(nf - m)
-         + (nf + 1.0f) * log1pf(fast_div(k - m, b))
+    return (m + 0.5f) * fast_log(fast_div(m + 1.0f, r * a)) + stirling_tail_large_f(m) + stirling_tail_large_f(nf - m)
+         + (nf + 1.0f) * log1p_rel(fast_div(k - m, b))
          + (k + 0.5f) * fast_log(fast_div(r * b, k + 1.0f))
          - stirling_tail_f(k) - stirling_tail_f(nf - k);
 }
@@ -184,18 +201,21 @@ __host__ __device__ __forceinline__ int binomial_classify(int n, float p, int& k
     return ((float)n * pp < SODM_BINV_THRESHOLD) ? BIN_INVERT : BIN_BTRS;
 }
 
-// Sequential-search inversion driven by a given uniform word (0 < p <= 0.5, n*p small).
+// Sequential-search inversion driven by a given uniform word (0 < p <= 0.5, n*p small).  The counters are kept in
+// FP32 (exact: the search stops at 1024) so that an iteration is a reciprocal, five multiply-adds and two compares.
 __host__ __device__ __forceinline__ int binomial_inversion_word(int n, float p, uint32_t word) {
-    const float s = p / (1.0f - p);
+    const float s = fast_div(p, 1.0f - p);
     float f = fast_exp((float)n * log1pf(-p));     // q^n = P(X = 0); n log q > -10.6 here, where __expf is good to ~1e-6
     float u = u01(word);
-    int k = 0;
-    while (u > f && k < n && k < 1024) {
+    const float kmax = (float)(n < 1024 ? n : 1024);
+    float kf = 0.0f, left = (float)n;              // left = n - k (exact in FP32 after the first few steps even for n > 2^24)
+    while (u > f && kf < kmax) {
         u -= f;
-        ++k;
-        f *= fast_div(s * (float)(n - k + 1), (float)k);       // P(k)/P(k-1); a few ulp here only nudge u by ~1e-7
+        kf += 1.0f;
+        f *= fast_div(s * left, kf);               // P(k)/P(k-1) = s (n-k+1)/k; a few ulp here only nudge u by ~1e-7
+        left -= 1.0f;
     }
-    return k;
+    return (int)kf;
 }
 
 // Split form of one BTRS attempt, for queue-based processing (jump_run.cuh):
@@ -275,29 +295,39 @@ __host__ __device__ __forceinline__ bool btrs_try(Rng& rng, int n, float p, int&
     return btrs_exact_accept(n, p, k, lhs);
 }
 
-// ONE attempt at Bin(n, p) from two given random words (the per-lane walk hands every trip exactly two words, so
-// that all lanes of a warp refill their Philox block on the same trips).  Same contract as binomial_try.
-__host__ __device__ __forceinline__ bool binomial_try_words(int n, float p, uint32_t wu, uint32_t wv, int& k) {
+// ONE attempt at Bin(n, p) from two given random words, up to but not including the exact acceptance test:
+// BIN_DONE (k final; -1 = invalid arguments), BIN_RETRY, or BIN_EXACT -- then `k` is the candidate ON THE FOLDED
+// SCALE (p <= 1/2) and `lhs` the log of the scaled uniform, to be settled by binomial_finish_exact.
+__host__ __device__ __forceinline__ int binomial_attempt_words(int n, float p, uint32_t wu, uint32_t wv, int& k, float& lhs) {
     int state = binomial_classify(n, p, k);
-    if (state == BIN_DONE) return true;
+    if (state == BIN_DONE) return BIN_DONE;
     const bool flip = p > 0.5f;
     const float pp = flip ? 1.0f - p : p;
     int kk;
-    bool done = true;
     if (state == BIN_INVERT) {
         kk = binomial_inversion_word(n, pp, wu);
+        state = BIN_DONE;
     } else {
         state = btrs_candidate(n, pp, wu, wv, kk);
-        if (state == BIN_RETRY) done = false;
-        else if (state == BIN_SQUEEZE) {
-            float lhs = 0.0f;
-            state = btrs_squeeze(n, pp, kk, wu, wv, lhs);
-            if (state == BIN_RETRY) done = false;
-            else if (state == BIN_EXACT) done = btrs_exact_accept(n, pp, kk, lhs);
-        }
+        if (state == BIN_SQUEEZE) state = btrs_squeeze(n, pp, kk, wu, wv, lhs);
     }
-    k = flip ? n - kk : kk;
-    return done;
+    k = (state == BIN_DONE && flip) ? n - kk : kk;
+    return state;
+}
+__host__ __device__ __forceinline__ bool binomial_finish_exact(int n, float p, float lhs, int& k) {
+    const bool flip = p > 0.5f;
+    const bool ok = btrs_exact_accept(n, flip ? 1.0f - p : p, k, lhs);
+    if (flip) k = n - k;
+    return ok;
+}
+
+// The same as one call (the exact test, if needed, right away).  Same contract as binomial_try.
+__host__ __device__ __forceinline__ bool binomial_try_words(int n, float p, uint32_t wu, uint32_t wv, int& k) {
+    float lhs = 0.0f;
+    const int state = binomial_attempt_words(n, p, wu, wv, k, lhs);
+    if (state == BIN_DONE) return true;
+    if (state == BIN_RETRY) return false;
+    return binomial_finish_exact(n, p, lhs, k);
 }
 
 // ONE attempt at Bin(n, p), 0 <= p <= 1.  Returns true when finished with the variate in k.

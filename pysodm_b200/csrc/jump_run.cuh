@@ -380,7 +380,15 @@ template <int NDRAW, uint32_t DEP_MASK>
 __host__ __device__ __forceinline__ void sample_worklist_walk(WalkRng& rng, WorkList& w, uint32_t& st) {
     const int S = w.stride, lane = w.lane;
     int d = 0, prev = 0;
+    // Every trip is one attempt that consumes exactly two Philox words, and every lane starts a step on a fresh block
+    // (the half-used one of the previous step is dropped): the lanes of a warp then refill on the same trips, so the
+    // generator -- a sixth of the kernel's instructions -- always runs with the whole warp.  Letting each lane carry
+    // its leftover pair across steps halves the active lanes per refill and costs 11 % (profiles/r1_sampler_ab.txt).
+    rng.second = false;
     while (d < NDRAW) {
+        int n = w.n[d * S + lane];
+        const float p = w.p[d * S + lane];
+        if ((DEP_MASK >> d) & 1u) n -= prev;
         if (!rng.second) {
             uint32_t b[4];
             rng.gen.next4(b);
@@ -388,9 +396,6 @@ __host__ __device__ __forceinline__ void sample_worklist_walk(WalkRng& rng, Work
         }
         const uint32_t wu = rng.second ? rng.w2 : rng.w0, wv = rng.second ? rng.w3 : rng.w1;
         rng.second = !rng.second;
-        int n = w.n[d * S + lane];
-        const float p = w.p[d * S + lane];
-        if ((DEP_MASK >> d) & 1u) n -= prev;
         int k;
         if (binomial_try_words(n, p, wu, wv, k)) {
             if (k < 0) { st |= ST_BAD_PROB; k = 0; }
