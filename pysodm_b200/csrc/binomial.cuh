@@ -281,6 +281,16 @@ bool btrs_exact_accept(int n, float p, int k, float lhs) {
     return (double)lhs <= binomial_log_ratio(nd, pd, floor((nd + 1.0) * pd), (double)k);
 }
 
+// log of the scaled uniform that the acceptance tests compare with log f(k)/f(m)   (BTRS step 3.1)
+__host__ __device__ __forceinline__ float btrs_lhs(int n, float p, uint32_t wu, uint32_t wv) {
+    const float stddev = fast_sqrt((float)n * p * (1.0f - p));
+    const float b = 1.15f + 2.53f * stddev;
+    const float a = -0.0873f + 0.0248f * b + 0.01f * p;
+    const float alpha = (2.83f + fast_div(5.1f, b)) * stddev;
+    const float us = 0.5f - fabsf(u01(wu) - 0.5f);
+    return fast_log(fast_div(u01(wv) * alpha, fast_div(a, us * us) + b));
+}
+
 // One complete BTRS attempt of a single lane (per-lane walk); requires 0 < p <= 0.5 and n*p >= 10.
 template <class Rng>
 __host__ __device__ __forceinline__ bool btrs_try(Rng& rng, int n, float p, int& k) {
@@ -295,39 +305,41 @@ __host__ __device__ __forceinline__ bool btrs_try(Rng& rng, int n, float p, int&
     return btrs_exact_accept(n, p, k, lhs);
 }
 
-// ONE attempt at Bin(n, p) from two given random words, up to but not including the exact acceptance test:
-// BIN_DONE (k final; -1 = invalid arguments), BIN_RETRY, or BIN_EXACT -- then `k` is the candidate ON THE FOLDED
-// SCALE (p <= 1/2) and `lhs` the log of the scaled uniform, to be settled by binomial_finish_exact.
-__host__ __device__ __forceinline__ int binomial_attempt_words(int n, float p, uint32_t wu, uint32_t wv, int& k, float& lhs) {
+// ONE attempt at Bin(n, p) from two given random words (the per-lane walk hands every trip exactly two words, so
+// that all lanes of a warp refill their Philox block on the same trips).  Same contract as binomial_try.
+// A candidate that fails the box test and whose exact test is the cheap FP32 one goes to it directly: among the 32
+// independent attempts of a warp some lane needs that test on four trips out of five anyway, so the squeeze (59
+// instructions, settles two candidates in three) mostly adds to what the warp executes.  Large modes, whose exact
+// test is the FP64 routine, keep the squeeze -- there it settles 98 %.
+#ifndef SODM_DIRECT_EXACT
+#define SODM_DIRECT_EXACT 1              // 0: squeeze in front of every exact test (tuning builds)
+#endif
+__host__ __device__ __forceinline__ bool binomial_try_words(int n, float p, uint32_t wu, uint32_t wv, int& k) {
     int state = binomial_classify(n, p, k);
-    if (state == BIN_DONE) return BIN_DONE;
+    if (state == BIN_DONE) return true;
     const bool flip = p > 0.5f;
     const float pp = flip ? 1.0f - p : p;
     int kk;
+    bool done = true;
     if (state == BIN_INVERT) {
         kk = binomial_inversion_word(n, pp, wu);
-        state = BIN_DONE;
     } else {
         state = btrs_candidate(n, pp, wu, wv, kk);
-        if (state == BIN_SQUEEZE) state = btrs_squeeze(n, pp, kk, wu, wv, lhs);
+        if (state == BIN_RETRY) done = false;
+        else if (state == BIN_SQUEEZE) {
+            float lhs = 0.0f;
+            if (SODM_DIRECT_EXACT && (float)n * pp < 0.9f * SODM_F32_MODE_LIMIT) {
+                lhs = btrs_lhs(n, pp, wu, wv);
+                state = BIN_EXACT;
+            } else {
+                state = btrs_squeeze(n, pp, kk, wu, wv, lhs);
+            }
+            if (state == BIN_RETRY) done = false;
+            else if (state == BIN_EXACT) done = btrs_exact_accept(n, pp, kk, lhs);
+        }
     }
-    k = (state == BIN_DONE && flip) ? n - kk : kk;
-    return state;
-}
-__host__ __device__ __forceinline__ bool binomial_finish_exact(int n, float p, float lhs, int& k) {
-    const bool flip = p > 0.5f;
-    const bool ok = btrs_exact_accept(n, flip ? 1.0f - p : p, k, lhs);
-    if (flip) k = n - k;
-    return ok;
-}
-
-// The same as one call (the exact test, if needed, right away).  Same contract as binomial_try.
-__host__ __device__ __forceinline__ bool binomial_try_words(int n, float p, uint32_t wu, uint32_t wv, int& k) {
-    float lhs = 0.0f;
-    const int state = binomial_attempt_words(n, p, wu, wv, k, lhs);
-    if (state == BIN_DONE) return true;
-    if (state == BIN_RETRY) return false;
-    return binomial_finish_exact(n, p, lhs, k);
+    k = flip ? n - kk : kk;
+    return done;
 }
 
 // ONE attempt at Bin(n, p), 0 <= p <= 1.  Returns true when finished with the variate in k.
