@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SODM_ABI_VERSION 1
+#define SODM_ABI_VERSION 2
 
 /* error codes */
 #define SODM_OK            0
@@ -213,6 +213,51 @@ int sodm_loglik(const sodm_loglik_args* args);
  * device-accessible; dtype converts src_dtype -> dst_dtype (I32/F32/F64). */
 int sodm_to_draws_major(const void* src, int32_t src_dtype, int64_t ld, int32_t r0, int32_t n_dim, int32_t n_t,
                         int64_t n_traj, void* dst, int32_t dst_dtype, void* stream);
+
+/* ---- ensemble post-processing ----------------------------------------------------------------------------
+ * What the reference's workflows do to a finished ensemble on the host, done where the ensemble lives:
+ *   add_poisson_noise / add_gaussian_noise / add_negative_binomial_noise
+ *                       src/pySODM/optimization/utils.py:11-33, :35-66, :68-95        -> sodm_noise
+ *   out[state].mean(dim='draws')       tutorials/influenza_1718/calibration.py:245   -> sodm_draws_sum
+ *   out[state].quantile(dim='draws', q=...)  tutorials/influenza_1718/calibration.py:246 -> sodm_draws_order_stats
+ * All three read the simulators' [cell][trajectory] layout (cell = row * n_time + time; element (c, i) at
+ * base[c * ld + i]).  Random streams are keyed by (seed, traj_id0 + i, c): the noisy ensemble does not depend on how
+ * trajectories are sharded over GPUs. */
+#define SODM_NOISE_POISSON       0    /* np.random.poisson(x)                                     utils.py:30    */
+#define SODM_NOISE_GAUSSIAN_ABS  1    /* np.random.normal(x, sigma)            relative=False     utils.py:62    */
+#define SODM_NOISE_GAUSSIAN_REL  2    /* np.random.normal(x, |sigma * x|)      relative=True      utils.py:64    */
+#define SODM_NOISE_NEGBIN        3    /* np.random.negative_binomial(1/alpha, (1/alpha)/(x + 1/alpha))  utils.py:91-92 */
+
+/* bits OR-ed into *status by sodm_noise */
+#define SODM_NOISE_ST_BAD_MEAN   1    /* negative / NaN / infinite model output under Poisson or NB noise
+                                         (NumPy: "lam < 0 or lam contains NaNs", "p < 0, p > 1 or p is NaN")   */
+
+typedef struct sodm_noise_args {
+    int32_t     kind;        /* SODM_NOISE_*                                                                      */
+    double      param;       /* sigma (Gaussian, >= 0) or alpha (negative binomial, > 0); ignored for Poisson       */
+    const void* in;          /* (device) [n_cells][ld] model output                                                */
+    int32_t     in_dtype;    /* SODM_I32 | SODM_F32 | SODM_F64                                                     */
+    void*       out;         /* (device) [n_cells][ld]; may be `in` itself when the dtypes are equal               */
+    int32_t     out_dtype;
+    int64_t     n_cells, n_traj, ld;
+    int64_t     traj_id0;    /* global id of trajectory 0 of this shard                                            */
+    uint64_t    seed;
+    int32_t*    status;      /* (device) one int32, OR-ed with SODM_NOISE_ST_*; may be NULL                        */
+    void*       stream;
+} sodm_noise_args;
+int sodm_noise(const sodm_noise_args* args);
+
+/* sum[c] = sum_i in[c * ld + i] in FP64 (int32 input: accumulated in int64, i.e. exact). */
+int sodm_draws_sum(const void* in, int32_t dtype, int64_t n_cells, int64_t n_traj, int64_t ld,
+                   double* sum /* (device) [n_cells] */, void* stream);
+
+/* out[j * n_cells + c] = the ranks[j]-th smallest (0-based) of the n_traj values of cell c -- the order statistics
+ * np.quantile interpolates between; the caller applies NumPy's `_lerp`.  A cell holding a NaN yields NaN for every
+ * rank, as np.quantile does.  `ranks` is a HOST array of at most SODM_MAX_RANKS entries. */
+#define SODM_MAX_RANKS 4
+int sodm_draws_order_stats(const void* in, int32_t dtype, int64_t n_cells, int64_t n_traj, int64_t ld,
+                           const int64_t* ranks, int32_t n_ranks, double* out /* (device) [n_ranks][n_cells] */,
+                           void* stream);
 
 #ifdef __cplusplus
 }

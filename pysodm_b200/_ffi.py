@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PYSODM_B200_LIB") or os.path.join(_HERE, "libsodm.so")     # override: tuning builds only
 
 # constants mirrored from include/sodm.h
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, EINVAL, EMODEL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4
 KIND_JUMP, KIND_ODE = 0, 1
 I32, F32, F64 = 0, 1, 2
@@ -22,6 +22,9 @@ ODE_RK45, ODE_EULER, ODE_RK4 = 0, 1, 2
 LL_POISSON, LL_NORMAL, LL_LOGNORMAL, LL_NEGBIN = 0, 1, 2, 3
 ARG_NONE, ARG_SCALAR, ARG_COLUMN, ARG_FULL = 0, 1, 2, 3
 MAX_PARAM, MAX_STATE = 32, 32
+NOISE_POISSON, NOISE_GAUSSIAN_ABS, NOISE_GAUSSIAN_REL, NOISE_NEGBIN = 0, 1, 2, 3
+NOISE_ST_BAD_MEAN = 1
+MAX_RANKS = 4
 
 
 class ModelInfo(C.Structure):
@@ -64,6 +67,13 @@ class LoglikArgs(C.Structure):
                 ("weight", C.c_double), ("lp", C.c_void_p), ("status", C.c_void_p), ("stream", C.c_void_p)]
 
 
+class NoiseArgs(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("param", C.c_double), ("in_", C.c_void_p), ("in_dtype", C.c_int32),
+                ("out", C.c_void_p), ("out_dtype", C.c_int32), ("n_cells", C.c_int64), ("n_traj", C.c_int64),
+                ("ld", C.c_int64), ("traj_id0", C.c_int64), ("seed", C.c_uint64), ("status", C.c_void_p),
+                ("stream", C.c_void_p)]
+
+
 # every symbol include/sodm.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "sodm_abi_version": (C.c_int, []),
@@ -78,6 +88,10 @@ SYMBOLS = {
     "sodm_loglik": (C.c_int, [C.POINTER(LoglikArgs)]),
     "sodm_to_draws_major": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                       C.c_void_p, C.c_int32, C.c_void_p]),
+    "sodm_noise": (C.c_int, [C.POINTER(NoiseArgs)]),
+    "sodm_draws_sum": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "sodm_draws_order_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
+                                         C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 

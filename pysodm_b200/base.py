@@ -233,6 +233,23 @@ class _DeviceBackedModel:
             out_r += n
         return variables, rows
 
+    def _sim_on_device(self, run, var, y0, variables, n_rows, n_kept, N, sim_dtype, dev, date_range, t0, t1, raise_on_status,
+                       time_coord=None):
+        """One launch for all N trajectories into a resident [row][time][N] buffer -> DeviceEnsemble."""
+        import torch
+        from .ensemble import DeviceEnsemble
+        buf = torch.empty((n_rows, n_kept, N), dtype=sim_dtype, device=dev)
+        keys = sorted(var)
+        v = (keys, torch.from_numpy(np.stack([var[k] for k in keys])).to(dev)) if keys else None
+        y = torch.from_numpy(np.ascontiguousarray(y0)).to(dev)
+        status = torch.zeros(N, dtype=torch.int32, device=dev)
+        run(buf, v, y, status)
+        raise_on_status(status)
+        time_name = "date" if date_range[0] is not None else "time"
+        if time_coord is None:
+            time_coord = date_range if date_range[0] is not None else np.arange(t0, t1 + 1)
+        return DeviceEnsemble(buf, variables, self.dimensions_per_state, self.state_coordinates, time_name, time_coord)
+
     def _to_dataset(self, host, variables, N, time_name, time_coord):
         arrays = OrderedDict()
         for v in variables:
@@ -299,8 +316,10 @@ class JumpProcess(_DeviceBackedModel):
 
     def sim(self, time, N=1, draw_function=None, draw_function_kwargs={}, processes=None, method="tau_leap", tau=1,
             time_unit="D", *, output_dtype="float64", states=None, seed=None, device=None, chunk=65536,
-            compat=_ffi.COMPAT_REFERENCE):
-        """Simulate N trajectories over `time` (see module docstring).  `processes` is accepted and ignored."""
+            compat=_ffi.COMPAT_REFERENCE, output="host"):
+        """Simulate N trajectories over `time` (see module docstring).  `processes` is accepted and ignored.
+        output='device' keeps the ensemble in HBM and returns a `DeviceEnsemble` (ensemble.py) for on-device noise /
+        mean / quantiles instead of copying `(draws, time, *dims)` arrays to the host."""
         import torch
         from . import engine, pipeline
         validation.jump_solution_method(method, tau)
@@ -337,6 +356,14 @@ class JumpProcess(_DeviceBackedModel):
             chunk = _bounded_chunk(chunk, N, len(rows) * n_out * (4 if aligned else 8))
             if seed is None:
                 seed = int(np.random.randint(0, 2 ** 32)) | (int(np.random.randint(0, 2 ** 31)) << 32)
+            if output == "device":
+                return self._sim_on_device(
+                    lambda buf, v, y, st: engine.jump_run(
+                        self.device_model, y, par, N, t0, n_out, tau, method=method, var=v, tdpf=self._to_device_tdpf(tdpf, dev),
+                        compat=compat, seed=seed, out_dtype=sim_dtype, state_sel=rows, out=buf, status=st, dev=dev),
+                    var, y0, variables, len(rows), n_out, N, sim_dtype, dev, date_range, t0, t1, self._raise_on_status)
+            if output != "host":
+                raise ValueError("output must be 'host' or 'device'")
             host = pipeline.alloc_host_result(variables, N, n_out, host_dtype)
             pipe = pipeline.HostPipeline(variables, len(rows), n_out, chunk, sim_dtype, host_dtype, dev)
             y0_d = torch.from_numpy(np.ascontiguousarray(y0)).to(dev)
@@ -361,6 +388,13 @@ class JumpProcess(_DeviceBackedModel):
         time_name = "date" if date_range[0] is not None else "time"
         time_coord = date_range if date_range[0] is not None else np.arange(t0, t1 + 1)
         return self._to_dataset(host, variables, N, time_name, time_coord)
+
+    @staticmethod
+    def _to_device_tdpf(tdpf, dev):
+        import torch
+        if tdpf is None:
+            return None
+        return (torch.from_numpy(np.ascontiguousarray(tdpf[0])).to(dev), torch.from_numpy(tdpf[1]).to(dev))
 
     @staticmethod
     def _raise_on_status(status):
@@ -388,7 +422,7 @@ class ODE(_DeviceBackedModel):
 
     def sim(self, time, N=1, draw_function=None, draw_function_kwargs={}, processes=None, method="RK45", rtol=1e-4,
             tau=None, time_unit="D", *, atol=1e-6, output_dtype="float64", output_stride=1, output_last_only=False,
-            device=None, chunk=65536):
+            device=None, chunk=65536, output="host"):
         import torch
         from . import engine, pipeline
         validation.ode_solution_method(rtol, method, tau)
@@ -417,6 +451,25 @@ class ODE(_DeviceBackedModel):
             n_kept = int(lib.sodm_ode_n_kept(n_out, int(output_stride), int(bool(output_last_only))))
             variables, rows = self._select_rows(None)
             host_dtype = engine.as_torch_dtype(output_dtype)
+            if output == "device":
+                grid = np.arange(t0, t1 + 1)
+                coord = date_range if date_range[0] is not None else grid
+                coord = coord[-1:] if output_last_only else coord[::int(output_stride)]
+
+                def run(buf, v, y, st):
+                    _, nfev, st_ = engine.ode_run(self.device_model, y, par, N, t0, n_out, method=dev_method, rtol=rtol,
+                                                  atol=atol, tau=tau or 0.0, var=v, model_arg=self._model_arg,
+                                                  out_stride=output_stride, out_last_only=output_last_only, out=buf, dev=dev)
+                    st.copy_(st_)
+                    self.last_nfev = nfev
+
+                def check(status):
+                    if N and int(status.max()) & (_ffi.ST_STEP_TOO_SMALL | _ffi.ST_NONFINITE):
+                        raise RuntimeError("Required step size is less than spacing between numbers.")
+                return self._sim_on_device(run, var, y0, variables, len(rows), n_kept, N, torch.float64, dev, date_range,
+                                           t0, t1, check, time_coord=coord)
+            if output != "host":
+                raise ValueError("output must be 'host' or 'device'")
             host = pipeline.alloc_host_result(variables, N, n_kept, host_dtype)
             chunk = _bounded_chunk(chunk, N, len(rows) * n_kept * 8)
             pipe = pipeline.HostPipeline(variables, len(rows), n_kept, chunk, torch.float64, host_dtype, dev)

@@ -1,0 +1,312 @@
+// Ensemble post-processing on the device: observation noise, and sums / order statistics over the trajectories of
+// every (row, time) cell -- what the reference's workflows do to a finished ensemble on the host:
+//   add_*_noise                         /root/reference/src/pySODM/optimization/utils.py:11-95
+//   out[state].mean(dim='draws'), .quantile(dim='draws', q=...)
+//                                       /root/reference/tutorials/influenza_1718/calibration.py:231,245-246
+// so that an 18 GB ensemble is reduced to a few hundred KB before anything crosses PCIe.
+//
+// Layout: the simulators' own [cell][trajectory] structure-of-arrays (cell = row * n_time + time, stride `ld`): a
+// cell's trajectories are contiguous, so every kernel here streams columns with fully coalesced loads.
+//   noise        one thread per element, grid-stride; HBM-bound for Gaussian noise, sampler-bound for Poisson / NB
+//   sum          one CTA per cell, 16-byte loads, int64 / FP64 accumulation (exact for integer counts)
+//   order stats  one CTA per cell, MSB-first radix select with 11-bit digits: 3 passes over a 32-bit column
+//                (6 over FP64), one shared-memory histogram per distinct prefix among the requested ranks
+#include "common.cuh"
+#include "noise.cuh"
+
+namespace sodm {
+
+template <typename T> __device__ __forceinline__ double load_as_double(const void* p, int64_t i) { return (double)((const T*)p)[i]; }
+
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256) noise_kernel(const Tin* __restrict__ in, Tout* __restrict__ out, int64_t n_cells,
+                                                    int64_t n_traj, int64_t ld, int64_t traj_id0, uint64_t seed, int kind,
+                                                    double param, int32_t* __restrict__ status) {
+    int32_t st = 0;
+    // 2-D decomposition: blockIdx.y walks cells, x walks trajectories, so consecutive threads touch consecutive addresses
+    for (int64_t c = blockIdx.y; c < n_cells; c += gridDim.y) {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_traj; i += (int64_t)gridDim.x * blockDim.x) {
+            ElementRng rng;
+            rng.init(seed, (uint64_t)(traj_id0 + i), (uint32_t)c);
+            const double y = noisy_value(rng, kind, param, (double)in[c * ld + i], st);
+            out[c * ld + i] = (Tout)y;
+        }
+    }
+    if (st && status) atomicOr(status, st);
+}
+
+// ---- sums ----------------------------------------------------------------------------------------------------
+template <typename T> struct Accum { using type = double; };
+template <> struct Accum<int32_t> { using type = long long; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) draws_sum_kernel(const T* __restrict__ in, int64_t n_traj, int64_t ld, double* __restrict__ out) {
+    using A = typename Accum<T>::type;
+    const T* col = in + (int64_t)blockIdx.x * ld;
+    A acc = 0;
+    constexpr int V = 16 / sizeof(T);
+    const bool vec = (((uintptr_t)col) & 15) == 0;
+    int64_t i = 0;
+    if (vec) {
+        const int64_t nv = n_traj / V;
+        const uint4* c4 = reinterpret_cast<const uint4*>(col);
+        for (int64_t j = threadIdx.x; j < nv; j += blockDim.x) {
+            const uint4 q = __ldg(c4 + j);
+            const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc += (A)e[k];
+        }
+        i = nv * V;
+    }
+    for (int64_t j = i + threadIdx.x; j < n_traj; j += blockDim.x) acc += (A)col[j];
+    __shared__ A part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        A s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w];
+        out[blockIdx.x] = (double)s;
+    }
+}
+
+// ---- order statistics ------------------------------------------------------------------------------------------
+template <typename T> struct Radix;
+template <> struct Radix<int32_t> {
+    using Key = uint32_t;
+    static constexpr int BITS = 32;
+    __device__ static Key encode(int32_t x) { return (uint32_t)x ^ 0x80000000u; }
+    __device__ static double decode(Key k) { return (double)(int32_t)(k ^ 0x80000000u); }
+    __device__ static bool is_nan(int32_t) { return false; }
+};
+template <> struct Radix<float> {
+    using Key = uint32_t;
+    static constexpr int BITS = 32;
+    __device__ static Key encode(float x) { const uint32_t b = __float_as_uint(x); return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
+    __device__ static double decode(Key k) { return (double)__uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu)); }
+    __device__ static bool is_nan(float x) { return x != x; }
+};
+template <> struct Radix<double> {
+    using Key = unsigned long long;
+    static constexpr int BITS = 64;
+    __device__ static Key encode(double x) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+        return b ^ ((b >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+    }
+    __device__ static double decode(Key k) { return __longlong_as_double((long long)(k ^ ((k >> 63) ? 0x8000000000000000ull : 0xffffffffffffffffull))); }
+    __device__ static bool is_nan(double x) { return x != x; }
+};
+
+constexpr int SELECT_THREADS = 512;
+constexpr int DIGIT_BITS = 11;
+constexpr int BINS = 1 << DIGIT_BITS;
+constexpr int MAX_RANKS = SODM_MAX_RANKS;
+
+struct RankList {
+    int64_t rank[MAX_RANKS];
+    int n;
+};
+
+// `out[j * n_cells + cell]` = the rank[j]-th smallest (0-based) of the cell's n_traj values; NaN for every rank of a
+// cell that holds a NaN (np.quantile's behaviour).
+template <typename T>
+__global__ void __launch_bounds__(SELECT_THREADS) draws_select_kernel(const T* __restrict__ in, int64_t n_traj, int64_t ld,
+                                                                       const __grid_constant__ RankList ranks, int64_t n_cells,
+                                                                       double* __restrict__ out) {
+    using R = Radix<T>;
+    using Key = typename R::Key;
+    __shared__ uint32_t hist[MAX_RANKS][BINS];
+    __shared__ Key prefix[MAX_RANKS];            // high bits settled so far, per GROUP of ranks that share them
+    __shared__ int64_t remaining[MAX_RANKS];     // per rank: its rank among the elements that match its group's prefix
+    __shared__ int group_of[MAX_RANKS];
+    __shared__ int n_groups;
+    __shared__ int any_nan;
+    const T* col = in + (int64_t)blockIdx.x * ld;
+    const int J = ranks.n;
+    if (threadIdx.x == 0) {
+        n_groups = 1;
+        any_nan = 0;
+        prefix[0] = 0;
+        for (int j = 0; j < J; ++j) { group_of[j] = 0; remaining[j] = ranks.rank[j]; }
+    }
+    __syncthreads();
+    int settled = 0;                             // number of high bits in `prefix`
+    while (settled < R::BITS) {
+        const int bits = (R::BITS - settled) < DIGIT_BITS ? (R::BITS - settled) : DIGIT_BITS;
+        const int shift = R::BITS - settled - bits;
+        const int G = n_groups;
+        for (int b = threadIdx.x; b < G * BINS; b += blockDim.x) (&hist[0][0])[b] = 0;
+        __syncthreads();
+        bool saw_nan = false;
+        for (int64_t i0 = 0; i0 < n_traj; i0 += blockDim.x) {
+            const int64_t i = i0 + threadIdx.x;
+            const bool valid = i < n_traj;
+            Key key = 0;
+            if (valid) {
+                const T x = col[i];
+                saw_nan |= R::is_nan(x);
+                key = R::encode(x);
+            }
+            const Key high = settled ? (key >> (shift + bits)) : (Key)0;
+            const uint32_t digit = (uint32_t)(key >> shift) & (uint32_t)((1u << bits) - 1u);
+            for (int g = 0; g < G; ++g) {
+                const bool hit = valid && (settled == 0 || high == prefix[g]);
+                // warp-aggregated: trajectories of one cell cluster in a few bins, one atomic per distinct digit per warp
+                const uint32_t voters = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    const uint32_t same = __match_any_sync(voters, digit);
+                    if ((int)(threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&hist[g][digit], (uint32_t)__popc(same));
+                }
+            }
+        }
+        if (saw_nan) any_nan = 1;
+        __syncthreads();
+        // one warp per rank finds the bin holding it: lane l owns bins [l * BINS/32, (l+1) * BINS/32)
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        int64_t my_remaining = 0;
+        uint32_t my_digit = 0;
+        if (warp < J) {
+            const uint32_t* h = hist[group_of[warp]];
+            constexpr int PER = BINS / 32;
+            uint32_t local = 0;
+            for (int b = 0; b < PER; ++b) local += h[lane * PER + b];
+            uint32_t incl = local;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const int64_t want = remaining[warp];
+            const int64_t before = (int64_t)incl - local;
+            const bool mine = want >= before && want < (int64_t)incl;
+            const uint32_t owner = __ballot_sync(0xffffffffu, mine);
+            if (mine) {
+                int64_t cum = before;
+                int b = 0;
+                for (; b < PER - 1; ++b) {
+                    const uint32_t c = h[lane * PER + b];
+                    if (want < cum + c) break;
+                    cum += c;
+                }
+                my_digit = (uint32_t)(lane * PER + b);
+                my_remaining = want - cum;
+            }
+            const int src = owner ? __ffs(owner) - 1 : 0;
+            my_digit = __shfl_sync(0xffffffffu, my_digit, src);
+            my_remaining = __shfl_sync(0xffffffffu, my_remaining, src);
+        }
+        __syncthreads();
+        __shared__ Key next_prefix[MAX_RANKS];
+        if (warp < J && lane == 0) {
+            next_prefix[warp] = (settled ? (prefix[group_of[warp]] << bits) : (Key)0) | (Key)my_digit;
+            remaining[warp] = my_remaining;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {                  // regroup: ranks with equal prefixes share a histogram
+            int g_count = 0;
+            for (int j = 0; j < J; ++j) {
+                int g = -1;
+                for (int q = 0; q < g_count; ++q) if (prefix[q] == next_prefix[j]) { g = q; break; }
+                if (g < 0) { g = g_count++; prefix[g] = next_prefix[j]; }
+                group_of[j] = g;
+            }
+            n_groups = g_count;
+        }
+        settled += bits;
+        __syncthreads();
+    }
+    if ((int)threadIdx.x < J) {
+        const double v = R::decode(prefix[group_of[threadIdx.x]]);
+        out[(int64_t)threadIdx.x * n_cells + blockIdx.x] = any_nan ? __longlong_as_double(0x7ff8000000000000ll) : v;
+    }
+}
+
+template <typename Tin>
+static int launch_noise(const sodm_noise_args* a, dim3 grid, cudaStream_t s) {
+    switch (a->out_dtype) {
+        case SODM_I32: noise_kernel<Tin, int32_t><<<grid, 256, 0, s>>>((const Tin*)a->in, (int32_t*)a->out, a->n_cells, a->n_traj, a->ld, a->traj_id0, a->seed, a->kind, a->param, a->status); break;
+        case SODM_F32: noise_kernel<Tin, float><<<grid, 256, 0, s>>>((const Tin*)a->in, (float*)a->out, a->n_cells, a->n_traj, a->ld, a->traj_id0, a->seed, a->kind, a->param, a->status); break;
+        case SODM_F64: noise_kernel<Tin, double><<<grid, 256, 0, s>>>((const Tin*)a->in, (double*)a->out, a->n_cells, a->n_traj, a->ld, a->traj_id0, a->seed, a->kind, a->param, a->status); break;
+        default: return fail(SODM_EINVAL, "sodm_noise: unknown out_dtype %d", a->out_dtype);
+    }
+    SODM_CUDA_CHECK(cudaGetLastError());
+    return SODM_OK;
+}
+
+}  // namespace sodm
+
+using namespace sodm;
+
+static int check_columns(const char* who, const void* in, int32_t dtype, int64_t n_cells, int64_t n_traj, int64_t ld) {
+    if (n_cells < 0 || n_traj < 0) return fail(SODM_EINVAL, "%s: negative size", who);
+    if (dtype != SODM_I32 && dtype != SODM_F32 && dtype != SODM_F64) return fail(SODM_EINVAL, "%s: unknown dtype %d", who, dtype);
+    if (n_cells && n_traj && !in) return fail(SODM_EINVAL, "%s: null input", who);
+    if (ld < n_traj) return fail(SODM_EINVAL, "%s: ld %lld < n_traj %lld", who, (long long)ld, (long long)n_traj);
+    return SODM_OK;
+}
+
+extern "C" int sodm_noise(const sodm_noise_args* a) {
+    if (!a) return fail(SODM_EINVAL, "sodm_noise: null args");
+    int rc = check_columns("sodm_noise", a->in, a->in_dtype, a->n_cells, a->n_traj, a->ld);
+    if (rc != SODM_OK) return rc;
+    if (a->kind < SODM_NOISE_POISSON || a->kind > SODM_NOISE_NEGBIN) return fail(SODM_EINVAL, "sodm_noise: unknown kind %d", a->kind);
+    if ((a->kind == SODM_NOISE_GAUSSIAN_ABS || a->kind == SODM_NOISE_GAUSSIAN_REL) && !(a->param >= 0.0))
+        return fail(SODM_EINVAL, "sodm_noise: scale < 0");                         // NumPy's message (utils.py:62-64)
+    if (a->kind == SODM_NOISE_NEGBIN && !(a->param > 0.0) )
+        return fail(SODM_EINVAL, "sodm_noise: alpha must be > 0 (n = 1/alpha, utils.py:91)");
+    if (a->n_cells == 0 || a->n_traj == 0) return SODM_OK;
+    if (!a->out) return fail(SODM_EINVAL, "sodm_noise: null output");
+    const unsigned gx = (unsigned)((a->n_traj + 255) / 256 > 4096 ? 4096 : (a->n_traj + 255) / 256);
+    const unsigned gy = (unsigned)(a->n_cells > 32768 ? 32768 : a->n_cells);
+    const dim3 grid(gx, gy);
+    cudaStream_t s = (cudaStream_t)a->stream;
+    switch (a->in_dtype) {
+        case SODM_I32: return launch_noise<int32_t>(a, grid, s);
+        case SODM_F32: return launch_noise<float>(a, grid, s);
+        default:       return launch_noise<double>(a, grid, s);
+    }
+}
+
+extern "C" int sodm_draws_sum(const void* in, int32_t dtype, int64_t n_cells, int64_t n_traj, int64_t ld, double* sum, void* stream) {
+    int rc = check_columns("sodm_draws_sum", in, dtype, n_cells, n_traj, ld);
+    if (rc != SODM_OK) return rc;
+    if (n_cells == 0) return SODM_OK;
+    if (!sum) return fail(SODM_EINVAL, "sodm_draws_sum: null output");
+    if (n_cells > 2147483647LL) return fail(SODM_EINVAL, "sodm_draws_sum: too many cells");
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)n_cells;
+    switch (dtype) {
+        case SODM_I32: draws_sum_kernel<int32_t><<<grid, 256, 0, s>>>((const int32_t*)in, n_traj, ld, sum); break;
+        case SODM_F32: draws_sum_kernel<float><<<grid, 256, 0, s>>>((const float*)in, n_traj, ld, sum); break;
+        default:       draws_sum_kernel<double><<<grid, 256, 0, s>>>((const double*)in, n_traj, ld, sum); break;
+    }
+    SODM_CUDA_CHECK(cudaGetLastError());
+    return SODM_OK;
+}
+
+extern "C" int sodm_draws_order_stats(const void* in, int32_t dtype, int64_t n_cells, int64_t n_traj, int64_t ld,
+                                      const int64_t* ranks, int32_t n_ranks, double* out, void* stream) {
+    int rc = check_columns("sodm_draws_order_stats", in, dtype, n_cells, n_traj, ld);
+    if (rc != SODM_OK) return rc;
+    if (n_ranks < 0 || n_ranks > MAX_RANKS) return fail(SODM_EINVAL, "sodm_draws_order_stats: n_ranks %d outside 0..%d", n_ranks, MAX_RANKS);
+    if (n_cells == 0 || n_ranks == 0) return SODM_OK;
+    if (n_traj == 0) return fail(SODM_EINVAL, "sodm_draws_order_stats: no trajectories");
+    if (!ranks || !out) return fail(SODM_EINVAL, "sodm_draws_order_stats: null ranks / output");
+    if (n_cells > 2147483647LL) return fail(SODM_EINVAL, "sodm_draws_order_stats: too many cells");
+    RankList rl;
+    rl.n = n_ranks;
+    for (int j = 0; j < n_ranks; ++j) {
+        if (ranks[j] < 0 || ranks[j] >= n_traj) return fail(SODM_EINVAL, "sodm_draws_order_stats: rank %lld outside 0..n_traj-1", (long long)ranks[j]);
+        rl.rank[j] = ranks[j];
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)n_cells;
+    switch (dtype) {
+        case SODM_I32: draws_select_kernel<int32_t><<<grid, SELECT_THREADS, 0, s>>>((const int32_t*)in, n_traj, ld, rl, n_cells, out); break;
+        case SODM_F32: draws_select_kernel<float><<<grid, SELECT_THREADS, 0, s>>>((const float*)in, n_traj, ld, rl, n_cells, out); break;
+        default:       draws_select_kernel<double><<<grid, SELECT_THREADS, 0, s>>>((const double*)in, n_traj, ld, rl, n_cells, out); break;
+    }
+    SODM_CUDA_CHECK(cudaGetLastError());
+    return SODM_OK;
+}

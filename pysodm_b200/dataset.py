@@ -148,6 +148,10 @@ class SimpleDataset:
             out.update(da.coords)
         return out
 
+    def copy(self):
+        """Deep copy of the values (what `xarray.Dataset.copy()` + a `.values` assignment amount to in utils.py:26-32)."""
+        return self._map(lambda v: SimpleDataArray(v.values.copy(), v.dims, v.coords, v.name))
+
     def _map(self, fn):
         return SimpleDataset(OrderedDict((k, fn(v)) for k, v in self.data_vars.items()))
 

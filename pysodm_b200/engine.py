@@ -255,3 +255,79 @@ def to_draws_major(src, r0, n_dim, dst=None, dst_dtype=torch.float64, dev=None, 
                                        int(n_t), int(n_traj), dst.data_ptr(), _TORCH_DT[dst.dtype],
                                        _stream_ptr(stream)), lib)
     return dst
+
+
+# ---- ensemble post-processing (sodm_noise / sodm_draws_sum / sodm_draws_order_stats) ------------------------------
+_NOISE_KINDS = {"poisson": _ffi.NOISE_POISSON, "gaussian": _ffi.NOISE_GAUSSIAN_ABS,
+                "gaussian_relative": _ffi.NOISE_GAUSSIAN_REL, "negative_binomial": _ffi.NOISE_NEGBIN}
+
+
+def _as_cells(ens):
+    """View a [..., n_traj] CUDA tensor with contiguous leading axes as (n_cells, n_traj, ld)."""
+    if not (isinstance(ens, torch.Tensor) and ens.is_cuda):
+        raise TypeError("expected a CUDA tensor laid out [..., trajectories]")
+    if ens.dtype not in _TORCH_DT:
+        raise TypeError(f"dtype {ens.dtype} is not one of int32 / float32 / float64")
+    if ens.dim() < 1 or (ens.shape[-1] > 1 and ens.stride(-1) != 1):
+        raise ValueError("trajectories must be the last, unit-stride axis")
+    n_traj = int(ens.shape[-1])
+    n_cells = int(np.prod(ens.shape[:-1])) if ens.dim() > 1 else 1
+    ld = int(ens.stride(-2)) if ens.dim() > 1 else n_traj
+    expect = ld
+    for ax in range(ens.dim() - 2, -1, -1):                       # leading axes must be packed with pitch ld
+        if ens.shape[ax] > 1 and ens.stride(ax) != expect:
+            raise ValueError("leading axes of the ensemble must be contiguous")
+        expect *= int(ens.shape[ax])
+    return n_cells, n_traj, ld
+
+
+def noise(kind, ens, param=0.0, seed=0, traj_id0=0, out=None, out_dtype=None, dev=None, stream=None):
+    """Replace every value of the ensemble `ens` [..., n_traj] by a noisy draw around it (`sodm_noise`).
+    kind: 'poisson' | 'gaussian' (param = sigma) | 'gaussian_relative' | 'negative_binomial' (param = alpha).
+    Returns (out, status) -- status is a one-element int32 CUDA tensor of SODM_NOISE_ST_* bits."""
+    dev = dev or device()
+    lib = _ffi.load()
+    n_cells, n_traj, ld = _as_cells(ens)
+    if out is None:
+        dt = as_torch_dtype(out_dtype) if out_dtype is not None else (
+            torch.float64 if kind.startswith("gaussian") and ens.dtype == torch.int32 else ens.dtype)
+        out = torch.empty_strided(ens.shape, ens.stride(), dtype=dt, device=dev)
+    elif out.shape != ens.shape or out.stride() != ens.stride():
+        raise ValueError("out must have the shape and strides of the input ensemble")
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    a = _ffi.NoiseArgs()
+    a.kind, a.param = _NOISE_KINDS[kind], float(param)
+    a.in_, a.in_dtype = ens.data_ptr(), _TORCH_DT[ens.dtype]
+    a.out, a.out_dtype = out.data_ptr(), _TORCH_DT[out.dtype]
+    a.n_cells, a.n_traj, a.ld = n_cells, n_traj, ld
+    a.traj_id0, a.seed = int(traj_id0), int(seed) & 0xFFFFFFFFFFFFFFFF
+    a.status, a.stream = status.data_ptr(), _stream_ptr(stream)
+    _ffi.check(lib.sodm_noise(C.byref(a)), lib)
+    return out, status
+
+
+def draws_sum(ens, dev=None, stream=None):
+    """Sum over the trajectory axis of `ens` [..., n_traj] -> float64 CUDA tensor [...] (`sodm_draws_sum`)."""
+    dev = dev or device()
+    lib = _ffi.load()
+    n_cells, n_traj, ld = _as_cells(ens)
+    out = torch.empty(ens.shape[:-1], dtype=torch.float64, device=dev)
+    _ffi.check(lib.sodm_draws_sum(ens.data_ptr(), _TORCH_DT[ens.dtype], n_cells, n_traj, ld, out.data_ptr(),
+                                  _stream_ptr(stream)), lib)
+    return out
+
+
+def draws_order_stats(ens, ranks, dev=None, stream=None):
+    """The ranks[j]-th smallest value (0-based) over the trajectory axis of `ens` [..., n_traj]
+    -> float64 CUDA tensor [len(ranks), ...] (`sodm_draws_order_stats`, at most MAX_RANKS ranks per launch)."""
+    dev = dev or device()
+    lib = _ffi.load()
+    n_cells, n_traj, ld = _as_cells(ens)
+    ranks = [int(r) for r in ranks]
+    out = torch.empty((len(ranks),) + tuple(ens.shape[:-1]), dtype=torch.float64, device=dev)
+    for lo in range(0, len(ranks), _ffi.MAX_RANKS):
+        part = ranks[lo:lo + _ffi.MAX_RANKS]
+        arr = (C.c_int64 * len(part))(*part)
+        _ffi.check(lib.sodm_draws_order_stats(ens.data_ptr(), _TORCH_DT[ens.dtype], n_cells, n_traj, ld, arr, len(part),
+                                              out[lo:lo + len(part)].data_ptr(), _stream_ptr(stream)), lib)
+    return out

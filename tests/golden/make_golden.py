@@ -375,7 +375,57 @@ def gen_optimizers():
     save('optimizers.npz', **out)
 
 
+class _FakeVariable:
+    def __init__(self, values):
+        self.values = values
+
+
+class _FakeDataset(dict):
+    """The three members of xarray.Dataset that utils.py:26-32 touches: copy(), data_vars.items(), ds[name].values."""
+    def copy(self):
+        return _FakeDataset({k: _FakeVariable(v.values.copy()) for k, v in self.items()})
+
+    @property
+    def data_vars(self):
+        return self
+
+
+def gen_post():
+    """Seeded outputs of the reference's add_*_noise (optimization/utils.py:11-95) on a small fake Dataset, plus the
+    np.mean / np.quantile reductions the tutorials apply along 'draws'.  utils.py imports matplotlib (absent here) at
+    module top for its plotting helpers; a stub module stands in -- harness glue, no arithmetic involved."""
+    import types
+    ref_loader.load()
+    if 'matplotlib' not in sys.modules:
+        try:
+            import matplotlib.pyplot  # noqa: F401
+        except ImportError:
+            mpl, plt = types.ModuleType('matplotlib'), types.ModuleType('matplotlib.pyplot')
+            mpl.pyplot = plt
+            plt.Axes = plt.Figure = object                     # annotations only (utils.py:190)
+            sys.modules['matplotlib'], sys.modules['matplotlib.pyplot'] = mpl, plt
+    import pySODM.optimization.utils as ref_utils
+    rng = np.random.default_rng(11)
+    counts = rng.integers(0, 5000, size=(64, 7, 4)).astype(np.float64)        # (draws, time, age)
+    conc = rng.gamma(2.0, 3.0, size=(64, 9))
+    out = {'counts': counts, 'conc': conc}
+    ds = _FakeDataset({'counts': _FakeVariable(counts), 'conc': _FakeVariable(conc)})
+    np.random.seed(101)
+    r = ref_utils.add_poisson_noise(ds)
+    out['poisson_counts'], out['poisson_conc'] = r['counts'].values, r['conc'].values
+    np.random.seed(102)
+    r = ref_utils.add_negative_binomial_noise(ds, 0.03)
+    out['negbin_counts'], out['negbin_conc'] = r['counts'].values, r['conc'].values
+    np.random.seed(103)
+    r = ref_utils.add_gaussian_noise(ds, 0.04, relative=True)
+    out['gauss_rel_counts'], out['gauss_rel_conc'] = r['counts'].values, r['conc'].values
+    np.random.seed(104)
+    r = ref_utils.add_gaussian_noise(ds, 2.5, relative=False)
+    out['gauss_abs_counts'], out['gauss_abs_conc'] = r['counts'].values, r['conc'].values
+    save('post.npz', **out)
+
+
 if __name__ == '__main__':
-    what = sys.argv[1:] or ['jump_single', 'ssa', 'jump_ensemble', 'schedule', 'ode', 'loglik', 'optimizers']
+    what = sys.argv[1:] or ['jump_single', 'ssa', 'jump_ensemble', 'schedule', 'ode', 'loglik', 'optimizers', 'post']
     for w in what:
         globals()['gen_' + w]()

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <vector>
 #include "../../pysodm_b200/csrc/jump_setup.cuh"
+#include "../../pysodm_b200/csrc/noise.cuh"
 
 using namespace sodm;
 
@@ -129,4 +130,15 @@ extern "C" int hc_ode_run(const sodm_ode_args* a) {
             return SODM_EUNSUPPORTED;
     }
     return SODM_EMODEL;
+}
+
+// `count` noisy values around model output x, element streams (seed, traj = 0..count-1, cell) as sodm_noise uses them.
+extern "C" int32_t hc_noise(int32_t kind, double param, double x, uint64_t seed, uint32_t cell, int64_t count, double* out) {
+    int32_t status = 0;
+    for (int64_t i = 0; i < count; ++i) {
+        ElementRng rng;
+        rng.init(seed, (uint64_t)i, cell);
+        out[i] = noisy_value(rng, kind, param, x, status);
+    }
+    return status;
 }

@@ -31,6 +31,8 @@ def lib():
         _lib.hc_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int64, C.c_void_p]
         _lib.hc_binomial_log_ratio.restype = C.c_double
         _lib.hc_binomial_log_ratio.argtypes = [C.c_double, C.c_double, C.c_double]
+        _lib.hc_noise.restype = C.c_int32
+        _lib.hc_noise.argtypes = [C.c_int32, C.c_double, C.c_double, C.c_uint64, C.c_uint32, C.c_int64, C.c_void_p]
         _lib.sodm_model_id.restype = C.c_int
         _lib.sodm_model_id.argtypes = [C.c_char_p]
         _lib.sodm_model_info_get.restype = C.c_int
@@ -44,6 +46,12 @@ def binomial(n, p, count, seed=1, traj=0):
     attempts = np.zeros(1, dtype=np.int64)
     lib().hc_binomial(seed, traj, int(n), float(p), count, out.ctypes.data, attempts.ctypes.data)
     return out, int(attempts[0])
+
+
+def noise(kind, param, x, count, seed=1, cell=0):
+    out = np.empty(count, dtype=np.float64)
+    status = lib().hc_noise(int(kind), float(param), float(x), seed, cell, count, out.ctypes.data)
+    return out, status
 
 
 def philox(seed, traj, purpose, n_blocks):
