@@ -274,11 +274,57 @@ def run_gpu_arm(args):
         e2e_step(1000 + k)
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_launches = pipe.kernel_launches
     if n_e2e == n:
         e2e_checksum = int(host_out["Im_inc"][:, -1, :].to(torch.int64).sum())
         last_seed_match = (e2e_steps == args.steps)
         if last_seed_match and e2e_checksum != checksum:
             raise SystemExit("bench: host pipeline result differs from the device-resident run")
+
+    # ---- the tutorial workflow, reduced on the device (N = 1 only) ------------------------------------------
+    # sim -> negative-binomial observation noise -> mean and 95 % band over draws (calibration.py:231,245-246), with
+    # only the drawn parameters going in and the (time, age) summaries coming out over PCIe
+    workflow = None
+    if world == 1 and not args.no_workflow:
+        del host_out, pipe
+        torch.cuda.empty_cache()
+        ens = torch.empty((N_STATE, N_OUT, n), dtype=torch.int32, device=dev)
+        noisy = torch.empty_like(ens)
+        lo_r, hi_r = int(np.floor((n - 1) * 0.025)), int(np.floor((n - 1) * 0.975))
+        ranks = [lo_r, min(lo_r + 1, n - 1), hi_r, min(hi_r + 1, n - 1)]
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
+        def workflow_step(seed):
+            d = draws_host.to(dev, non_blocking=True)
+            marks[0].record()
+            engine.jump_run("influenza_1718_jump", y0, par, n, 0, N_OUT, TAU, var=(VAR_INDEX, d), tdpf=(table, index),
+                            seed=seed, traj_id0=0, out_dtype=torch.int32, out=ens, status=status, dev=dev)
+            marks[1].record()
+            engine.noise("negative_binomial", ens, 0.03, seed=seed, out=noisy, dev=dev)
+            marks[2].record()
+            mean = engine.draws_sum(noisy, dev=dev)
+            marks[3].record()
+            band = engine.draws_order_stats(noisy, ranks, dev=dev)
+            marks[4].record()
+            return mean.cpu(), band.cpu()                      # the step's result reaches the host
+
+        workflow_step(50)
+        torch.cuda.synchronize(dev)
+        wf_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for k in range(wf_steps):
+            mean_h, band_h = workflow_step(2000 + k)
+        torch.cuda.synchronize(dev)
+        wf_s = time.perf_counter() - t0
+        stages = [marks[i].elapsed_time(marks[i + 1]) for i in range(4)]
+        workflow = {"value": n * wf_steps / wf_s, "unit": UNIT, "ms_per_step": wf_s / wf_steps * 1e3,
+                    "stages_ms": dict(zip(["sim", "negative_binomial_noise", "mean", "quantile_band"], stages)),
+                    "h2d_bytes_per_step": int(draws_host.numel() * 8),
+                    "d2h_bytes_per_step": int((mean_h.numel() + band_h.numel()) * 8),
+                    "gpu_launches_per_step": 4,
+                    "what": "sim -> add_negative_binomial_noise(alpha=0.03) -> mean + 2.5 % / 97.5 % order statistics over "
+                            "draws, all on the device (sodm_noise, sodm_draws_sum, sodm_draws_order_stats)"}
+        del ens, noisy
 
     # ---- max over ranks, final NCCL gather of per-rank summaries --------------------------------------------
     t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -334,7 +380,7 @@ def run_gpu_arm(args):
                              f"NumPy tau-leap vectorised over trajectories; the unmodified reference is ~5.6 traj/s/core)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "i32 counts / f32 rates (f64 acceptance test)",
+                "scaling": "weak", "vs_baseline": None, "dtype": "i32 counts / f32 rates and sampler (f64 exact test above mode 8192)",
                 "data": "synthetic",
                 "config": {"workload": "influenza_1718 tau-leap (BASELINE config 3): tau=0.5, 2017-12-01..2018-05-11 "
                                        "(322 steps, 162 outputs), 28 compartments, per-trajectory beta/f_ud draws",
@@ -346,7 +392,8 @@ def run_gpu_arm(args):
                         "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps, "n_traj_per_gpu_per_step": n_e2e,
                         "layout": "pinned host int32 (draws, time, age) per state, chunked double-buffered pipeline",
                         "chunk": args.chunk},
-                "gpu_launches": args.steps, "e2e_gpu_launches_per_step": pipe.kernel_launches // (e2e_warm + e2e_steps),
+                "workflow": workflow,
+                "gpu_launches": args.steps, "e2e_gpu_launches_per_step": e2e_launches // (e2e_warm + e2e_steps),
                 "kernel_ms_per_step": kernel_ms}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -363,6 +410,7 @@ def main():
     ap.add_argument("--e2e-traj", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-workflow", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -9,30 +9,50 @@
 // cell's trajectories are contiguous, so every kernel here streams columns with fully coalesced loads.
 //   noise        one thread per element, grid-stride; HBM-bound for Gaussian noise, sampler-bound for Poisson / NB
 //   sum          one CTA per cell, 16-byte loads, int64 / FP64 accumulation (exact for integer counts)
-//   order stats  one CTA per cell, MSB-first radix select with 11-bit digits: 3 passes over a 32-bit column
-//                (6 over FP64), one shared-memory histogram per distinct prefix among the requested ranks
+//   order stats  one CTA per cell: a min/max pass, then MSB-first radix select with 11-bit digits over the bits in
+//                which the cell's values actually differ (typically 2 passes), one shared-memory histogram per
+//                distinct prefix among the requested ranks
 #include "common.cuh"
 #include "noise.cuh"
 
 namespace sodm {
 
-template <typename T> __device__ __forceinline__ double load_as_double(const void* p, int64_t i) { return (double)((const T*)p)[i]; }
-
-template <typename Tin, typename Tout>
-__global__ void __launch_bounds__(256) noise_kernel(const Tin* __restrict__ in, Tout* __restrict__ out, int64_t n_cells,
-                                                    int64_t n_traj, int64_t ld, int64_t traj_id0, uint64_t seed, int kind,
-                                                    double param, int32_t* __restrict__ status) {
+// Poisson / negative-binomial noise: one thread per element, blockIdx.y walks cells, x walks trajectories (consecutive
+// threads touch consecutive addresses).  Bound by the samplers (~10^2 instructions per variate), not by HBM.
+template <typename Tin, typename Tout, bool NEGBIN>
+__global__ void __launch_bounds__(256) count_noise_kernel(const Tin* __restrict__ in, Tout* __restrict__ out, int64_t n_cells,
+                                                          int64_t n_traj, int64_t ld, int64_t traj_id0, uint64_t seed,
+                                                          double alpha, int32_t* __restrict__ status) {
     int32_t st = 0;
-    // 2-D decomposition: blockIdx.y walks cells, x walks trajectories, so consecutive threads touch consecutive addresses
     for (int64_t c = blockIdx.y; c < n_cells; c += gridDim.y) {
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_traj; i += (int64_t)gridDim.x * blockDim.x) {
             ElementRng rng;
             rng.init(seed, (uint64_t)(traj_id0 + i), (uint32_t)c);
-            const double y = noisy_value(rng, kind, param, (double)in[c * ld + i], st);
-            out[c * ld + i] = (Tout)y;
+            out[c * ld + i] = (Tout)count_noise<NEGBIN>(rng, alpha, (double)in[c * ld + i], st);
         }
     }
     if (st && status) atomicOr(status, st);
+}
+
+// Gaussian noise: one thread per (trajectory, group of four cells) -- one Philox block and two Box-Muller pairs serve
+// four elements, which brings the kernel down to its HBM traffic (read + write of the ensemble).
+template <typename Tin, typename Tout, bool RELATIVE>
+__global__ void __launch_bounds__(256, 4) gaussian_noise_kernel(const Tin* __restrict__ in, Tout* __restrict__ out, int64_t n_cells,
+                                                                int64_t n_traj, int64_t ld, int64_t traj_id0, uint64_t seed,
+                                                                double sigma) {
+    const int64_t n_groups = (n_cells + 3) / 4;
+    for (int64_t g = blockIdx.y; g < n_groups; g += gridDim.y) {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_traj; i += (int64_t)gridDim.x * blockDim.x) {
+            Tin x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = 4 * g + q < n_cells ? in[(4 * g + q) * ld + i] : Tin(0);   // four loads in flight
+            float z[4];
+            normal_quad(seed, (uint64_t)(traj_id0 + i), (uint32_t)g, z);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (4 * g + q < n_cells) out[(4 * g + q) * ld + i] = (Tout)gaussian_noise(RELATIVE, sigma, (double)x[q], z[q]);
+        }
+    }
 }
 
 // ---- sums ----------------------------------------------------------------------------------------------------
@@ -108,8 +128,47 @@ struct RankList {
     int n;
 };
 
+// Visit every element of a column: 16-byte loads where the column is aligned, four independent loads in flight per
+// thread otherwise.  `f(key)` is called by every thread for each of its elements.
+template <typename T, class F>
+__device__ __forceinline__ void for_each_key(const T* __restrict__ col, int64_t n, F&& f) {
+    using R = Radix<T>;
+    constexpr int V = 16 / sizeof(T);
+    int64_t done = 0;
+    if ((((uintptr_t)col) & 15) == 0) {
+        const int64_t nv = n / V;
+        const uint4* c4 = reinterpret_cast<const uint4*>(col);
+        int64_t j = threadIdx.x;
+        for (; j + blockDim.x < nv; j += 2 * blockDim.x) {          // two vectors in flight
+            const uint4 q0 = __ldg(c4 + j), q1 = __ldg(c4 + j + blockDim.x);
+            const T* e0 = reinterpret_cast<const T*>(&q0);
+            const T* e1 = reinterpret_cast<const T*>(&q1);
+#pragma unroll
+            for (int k = 0; k < V; ++k) f(e0[k]);
+#pragma unroll
+            for (int k = 0; k < V; ++k) f(e1[k]);
+        }
+        for (; j < nv; j += blockDim.x) {
+            const uint4 q = __ldg(c4 + j);
+            const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+            for (int k = 0; k < V; ++k) f(e[k]);
+        }
+        done = nv * V;
+    }
+    for (int64_t j = done + threadIdx.x; j < n; j += blockDim.x) f(col[j]);
+    (void)sizeof(R);
+}
+
 // `out[j * n_cells + cell]` = the rank[j]-th smallest (0-based) of the cell's n_traj values; NaN for every rank of a
 // cell that holds a NaN (np.quantile's behaviour).
+//
+// One CTA per cell.  Pass 0 finds the smallest and largest key: trajectories of one cell are close together (counts of
+// 6.0e6 .. 7.4e6, say), so the keys share their leading bits and the radix search only has to resolve
+// bits(max - min) of (key - min) -- two 11-bit passes instead of three for typical epidemic counts, none at all for a
+// constant cell -- and the first histogram is spread over its bins instead of hammering one shared-memory address.
+// Each further pass histograms one digit of the elements that match a rank's settled prefix; ranks with equal prefixes
+// share a histogram.
 template <typename T>
 __global__ void __launch_bounds__(SELECT_THREADS) draws_select_kernel(const T* __restrict__ in, int64_t n_traj, int64_t ld,
                                                                        const __grid_constant__ RankList ranks, int64_t n_cells,
@@ -117,53 +176,91 @@ __global__ void __launch_bounds__(SELECT_THREADS) draws_select_kernel(const T* _
     using R = Radix<T>;
     using Key = typename R::Key;
     __shared__ uint32_t hist[MAX_RANKS][BINS];
-    __shared__ Key prefix[MAX_RANKS];            // high bits settled so far, per GROUP of ranks that share them
+    __shared__ Key prefix[MAX_RANKS];            // settled high bits of (key - lo), per GROUP of ranks that share them
+    __shared__ Key next_prefix[MAX_RANKS];
     __shared__ int64_t remaining[MAX_RANKS];     // per rank: its rank among the elements that match its group's prefix
     __shared__ int group_of[MAX_RANKS];
     __shared__ int n_groups;
+    __shared__ Key warp_lo[SELECT_THREADS / 32], warp_hi[SELECT_THREADS / 32];
     __shared__ int any_nan;
+    __shared__ Key lo_s, hi_s;
     const T* col = in + (int64_t)blockIdx.x * ld;
     const int J = ranks.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         n_groups = 1;
         any_nan = 0;
         prefix[0] = 0;
         for (int j = 0; j < J; ++j) { group_of[j] = 0; remaining[j] = ranks.rank[j]; }
     }
+    // ---- pass 0: range of the keys ----
+    Key lo = ~(Key)0, hi = 0;
+    bool saw_nan = false;
+    for_each_key(col, n_traj, [&](T x) {
+        saw_nan |= R::is_nan(x);
+        const Key k = R::encode(x);
+        lo = k < lo ? k : lo;
+        hi = k > hi ? k : hi;
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const Key l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    if (lane == 0) { warp_lo[warp] = lo; warp_hi[warp] = hi; }
+    if (saw_nan) any_nan = 1;
     __syncthreads();
-    int settled = 0;                             // number of high bits in `prefix`
-    while (settled < R::BITS) {
-        const int bits = (R::BITS - settled) < DIGIT_BITS ? (R::BITS - settled) : DIGIT_BITS;
-        const int shift = R::BITS - settled - bits;
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < SELECT_THREADS / 32; ++w) {
+            lo = warp_lo[w] < lo ? warp_lo[w] : lo;
+            hi = warp_hi[w] > hi ? warp_hi[w] : hi;
+        }
+        lo_s = lo;
+        hi_s = hi;
+    }
+    __syncthreads();
+    lo = lo_s;
+    const Key range = hi_s - lo;
+    int total_bits = 0;                          // bits needed for key - lo
+    while (total_bits < R::BITS && (range >> total_bits) != 0) ++total_bits;
+
+    int settled = 0;                             // number of high bits (of total_bits) in `prefix`
+    while (settled < total_bits) {
+        const int bits = (total_bits - settled) < DIGIT_BITS ? (total_bits - settled) : DIGIT_BITS;
+        const int shift = total_bits - settled - bits;
         const int G = n_groups;
         for (int b = threadIdx.x; b < G * BINS; b += blockDim.x) (&hist[0][0])[b] = 0;
         __syncthreads();
-        bool saw_nan = false;
-        for (int64_t i0 = 0; i0 < n_traj; i0 += blockDim.x) {
-            const int64_t i = i0 + threadIdx.x;
-            const bool valid = i < n_traj;
-            Key key = 0;
-            if (valid) {
-                const T x = col[i];
-                saw_nan |= R::is_nan(x);
-                key = R::encode(x);
-            }
-            const Key high = settled ? (key >> (shift + bits)) : (Key)0;
-            const uint32_t digit = (uint32_t)(key >> shift) & (uint32_t)((1u << bits) - 1u);
-            for (int g = 0; g < G; ++g) {
-                const bool hit = valid && (settled == 0 || high == prefix[g]);
-                // warp-aggregated: trajectories of one cell cluster in a few bins, one atomic per distinct digit per warp
-                const uint32_t voters = __ballot_sync(0xffffffffu, hit);
-                if (hit) {
-                    const uint32_t same = __match_any_sync(voters, digit);
-                    if ((int)(threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&hist[g][digit], (uint32_t)__popc(same));
-                }
-            }
+        const uint32_t mask = (1u << bits) - 1u;
+        if (settled == 0 && total_bits <= 5) {
+            // at most 32 distinct values (early-epidemic counts, say): every warp would hammer a few shared-memory
+            // addresses, so lanes with equal digits elect one of them to add their count
+            for_each_key(col, n_traj, [&](T x) {
+                const uint32_t digit = (uint32_t)(R::encode(x) - lo);
+                const uint32_t same = __match_any_sync(__activemask(), digit);
+                if (lane == __ffs(same) - 1) atomicAdd(&hist[0][digit], (uint32_t)__popc(same));
+            });
+        } else if (settled == 0) {
+            for_each_key(col, n_traj, [&](T x) {
+                const Key k = R::encode(x) - lo;
+                atomicAdd(&hist[0][(uint32_t)(k >> shift) & mask], 1u);
+            });
+        } else {
+            Key p[MAX_RANKS];
+#pragma unroll
+            for (int g = 0; g < MAX_RANKS; ++g) p[g] = g < G ? prefix[g] : ~(Key)0;
+            for_each_key(col, n_traj, [&](T x) {
+                const Key k = R::encode(x) - lo;
+                const Key high = k >> (shift + bits);
+                const uint32_t digit = (uint32_t)(k >> shift) & mask;
+#pragma unroll
+                for (int g = 0; g < MAX_RANKS; ++g)
+                    if (g < G && high == p[g]) atomicAdd(&hist[g][digit], 1u);
+            });
         }
-        if (saw_nan) any_nan = 1;
         __syncthreads();
         // one warp per rank finds the bin holding it: lane l owns bins [l * BINS/32, (l+1) * BINS/32)
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         int64_t my_remaining = 0;
         uint32_t my_digit = 0;
         if (warp < J) {
@@ -197,7 +294,6 @@ __global__ void __launch_bounds__(SELECT_THREADS) draws_select_kernel(const T* _
             my_remaining = __shfl_sync(0xffffffffu, my_remaining, src);
         }
         __syncthreads();
-        __shared__ Key next_prefix[MAX_RANKS];
         if (warp < J && lane == 0) {
             next_prefix[warp] = (settled ? (prefix[group_of[warp]] << bits) : (Key)0) | (Key)my_digit;
             remaining[warp] = my_remaining;
@@ -217,21 +313,44 @@ __global__ void __launch_bounds__(SELECT_THREADS) draws_select_kernel(const T* _
         __syncthreads();
     }
     if ((int)threadIdx.x < J) {
-        const double v = R::decode(prefix[group_of[threadIdx.x]]);
+        const double v = R::decode(lo + prefix[group_of[threadIdx.x]]);
         out[(int64_t)threadIdx.x * n_cells + blockIdx.x] = any_nan ? __longlong_as_double(0x7ff8000000000000ll) : v;
     }
 }
 
-template <typename Tin>
-static int launch_noise(const sodm_noise_args* a, dim3 grid, cudaStream_t s) {
-    switch (a->out_dtype) {
-        case SODM_I32: noise_kernel<Tin, int32_t><<<grid, 256, 0, s>>>((const Tin*)a->in, (int32_t*)a->out, a->n_cells, a->n_traj, a->ld, a->traj_id0, a->seed, a->kind, a->param, a->status); break;
-        case SODM_F32: noise_kernel<Tin, float><<<grid, 256, 0, s>>>((const Tin*)a->in, (float*)a->out, a->n_cells, a->n_traj, a->ld, a->traj_id0, a->seed, a->kind, a->param, a->status); break;
-        case SODM_F64: noise_kernel<Tin, double><<<grid, 256, 0, s>>>((const Tin*)a->in, (double*)a->out, a->n_cells, a->n_traj, a->ld, a->traj_id0, a->seed, a->kind, a->param, a->status); break;
-        default: return fail(SODM_EINVAL, "sodm_noise: unknown out_dtype %d", a->out_dtype);
+template <typename Tin, typename Tout>
+static int launch_noise_typed(const sodm_noise_args* a, cudaStream_t s) {
+    const Tin* in = (const Tin*)a->in;
+    Tout* out = (Tout*)a->out;
+    const unsigned gx = (unsigned)((a->n_traj + 255) / 256 > 4096 ? 4096 : (a->n_traj + 255) / 256);
+    const bool gaussian = a->kind == SODM_NOISE_GAUSSIAN_ABS || a->kind == SODM_NOISE_GAUSSIAN_REL;
+    const int64_t rows = gaussian ? (a->n_cells + 3) / 4 : a->n_cells;
+    // ~32 blocks per SM in total: a block walks many cells for its 256 trajectories instead of 10^7 one-element blocks
+    int64_t gy = (148 * 32 + gx - 1) / gx;
+    gy = gy > rows ? rows : gy;
+    const dim3 grid(gx, (unsigned)gy);
+    switch (a->kind) {
+        case SODM_NOISE_POISSON:
+            count_noise_kernel<Tin, Tout, false><<<grid, 256, 0, s>>>(in, out, a->n_cells, a->n_traj, a->ld, a->traj_id0, a->seed, a->param, a->status); break;
+        case SODM_NOISE_NEGBIN:
+            count_noise_kernel<Tin, Tout, true><<<grid, 256, 0, s>>>(in, out, a->n_cells, a->n_traj, a->ld, a->traj_id0, a->seed, a->param, a->status); break;
+        case SODM_NOISE_GAUSSIAN_ABS:
+            gaussian_noise_kernel<Tin, Tout, false><<<grid, 256, 0, s>>>(in, out, a->n_cells, a->n_traj, a->ld, a->traj_id0, a->seed, a->param); break;
+        default:
+            gaussian_noise_kernel<Tin, Tout, true><<<grid, 256, 0, s>>>(in, out, a->n_cells, a->n_traj, a->ld, a->traj_id0, a->seed, a->param); break;
     }
     SODM_CUDA_CHECK(cudaGetLastError());
     return SODM_OK;
+}
+
+template <typename Tin>
+static int launch_noise(const sodm_noise_args* a, cudaStream_t s) {
+    switch (a->out_dtype) {
+        case SODM_I32: return launch_noise_typed<Tin, int32_t>(a, s);
+        case SODM_F32: return launch_noise_typed<Tin, float>(a, s);
+        case SODM_F64: return launch_noise_typed<Tin, double>(a, s);
+    }
+    return fail(SODM_EINVAL, "sodm_noise: unknown out_dtype %d", a->out_dtype);
 }
 
 }  // namespace sodm
@@ -253,18 +372,15 @@ extern "C" int sodm_noise(const sodm_noise_args* a) {
     if (a->kind < SODM_NOISE_POISSON || a->kind > SODM_NOISE_NEGBIN) return fail(SODM_EINVAL, "sodm_noise: unknown kind %d", a->kind);
     if ((a->kind == SODM_NOISE_GAUSSIAN_ABS || a->kind == SODM_NOISE_GAUSSIAN_REL) && !(a->param >= 0.0))
         return fail(SODM_EINVAL, "sodm_noise: scale < 0");                         // NumPy's message (utils.py:62-64)
-    if (a->kind == SODM_NOISE_NEGBIN && !(a->param > 0.0) )
+    if (a->kind == SODM_NOISE_NEGBIN && !(a->param > 0.0))
         return fail(SODM_EINVAL, "sodm_noise: alpha must be > 0 (n = 1/alpha, utils.py:91)");
     if (a->n_cells == 0 || a->n_traj == 0) return SODM_OK;
     if (!a->out) return fail(SODM_EINVAL, "sodm_noise: null output");
-    const unsigned gx = (unsigned)((a->n_traj + 255) / 256 > 4096 ? 4096 : (a->n_traj + 255) / 256);
-    const unsigned gy = (unsigned)(a->n_cells > 32768 ? 32768 : a->n_cells);
-    const dim3 grid(gx, gy);
     cudaStream_t s = (cudaStream_t)a->stream;
     switch (a->in_dtype) {
-        case SODM_I32: return launch_noise<int32_t>(a, grid, s);
-        case SODM_F32: return launch_noise<float>(a, grid, s);
-        default:       return launch_noise<double>(a, grid, s);
+        case SODM_I32: return launch_noise<int32_t>(a, s);
+        case SODM_F32: return launch_noise<float>(a, s);
+        default:       return launch_noise<double>(a, s);
     }
 }
 

@@ -132,13 +132,19 @@ extern "C" int hc_ode_run(const sodm_ode_args* a) {
     return SODM_EMODEL;
 }
 
-// `count` noisy values around model output x, element streams (seed, traj = 0..count-1, cell) as sodm_noise uses them.
+// `count` noisy values around model output x, streams (seed, traj = 0..count-1, cell) exactly as the sodm_noise kernels use them.
 extern "C" int32_t hc_noise(int32_t kind, double param, double x, uint64_t seed, uint32_t cell, int64_t count, double* out) {
     int32_t status = 0;
     for (int64_t i = 0; i < count; ++i) {
+        if (kind == SODM_NOISE_GAUSSIAN_ABS || kind == SODM_NOISE_GAUSSIAN_REL) {
+            float z[4];
+            normal_quad(seed, (uint64_t)i, cell / 4, z);
+            out[i] = gaussian_noise(kind == SODM_NOISE_GAUSSIAN_REL, param, x, z[cell % 4]);
+            continue;
+        }
         ElementRng rng;
         rng.init(seed, (uint64_t)i, cell);
-        out[i] = noisy_value(rng, kind, param, x, status);
+        out[i] = kind == SODM_NOISE_POISSON ? count_noise<false>(rng, param, x, status) : count_noise<true>(rng, param, x, status);
     }
     return status;
 }
