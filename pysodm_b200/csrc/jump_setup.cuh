@@ -33,10 +33,10 @@ inline int64_t jump_n_steps(double t0, int32_t n_out, double tau) {
 }
 
 // Fills L and `aligned`; returns SODM_OK or an error code (message in the thread-local buffer).
-inline int build_jump_launch(const sodm_jump_args* a, JumpLaunch& L, bool& aligned) {
+// `info` describes the model (from the registry, or a generated model's own constants)
+inline int build_jump_launch_for(const sodm_jump_args* a, JumpLaunch& L, bool& aligned, const sodm_model_info& info) {
     if (!a) return fail(SODM_EINVAL, "sodm_jump_run: null args");
-    sodm_model_info info;
-    if (sodm_model_info_get(a->model, 0, &info) != SODM_OK || info.kind != SODM_KIND_JUMP)
+    if (info.kind != SODM_KIND_JUMP)
         return fail(SODM_EMODEL, "sodm_jump_run: model %d is not a jump-process model", a->model);
     if (a->n_traj < 0 || a->ld_in < a->n_traj || a->ld_out < a->n_traj)
         return fail(SODM_EINVAL, "sodm_jump_run: need 0 <= n_traj <= ld_in, ld_out");
@@ -115,5 +115,15 @@ inline int build_jump_launch(const sodm_jump_args* a, JumpLaunch& L, bool& align
 
     return SODM_OK;
 }
+
+#ifndef SODM_PLUGIN_BUILD
+inline int build_jump_launch(const sodm_jump_args* a, JumpLaunch& L, bool& aligned) {
+    if (!a) return fail(SODM_EINVAL, "sodm_jump_run: null args");
+    sodm_model_info info;
+    if (sodm_model_info_get(a->model, 0, &info) != SODM_OK)
+        return fail(SODM_EMODEL, "sodm_jump_run: model %d is not registered", a->model);
+    return build_jump_launch_for(a, L, aligned, info);
+}
+#endif
 
 }  // namespace sodm

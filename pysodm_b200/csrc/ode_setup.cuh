@@ -14,9 +14,9 @@ inline int32_t ode_n_kept(int32_t n_out, int32_t out_stride, int32_t out_last_on
     return (n_out - 1) / out_stride + 1;
 }
 
-inline int build_ode_launch(const sodm_ode_args* a, OdeLaunch& L, sodm_model_info& info) {
+// `info` describes the model (from the registry, or a generated model's own constants)
+inline int build_ode_launch_for(const sodm_ode_args* a, OdeLaunch& L, const sodm_model_info& info) {
     if (!a) return fail(SODM_EINVAL, "sodm_ode_run: null args");
-    if (sodm_model_info_get(a->model, a->model_arg, &info) != SODM_OK) return SODM_EMODEL;
     if (info.kind != SODM_KIND_ODE) return fail(SODM_EMODEL, "sodm_ode_run: model %d is not an ODE model", a->model);
     if (a->n_traj < 0 || a->ld_in < a->n_traj || a->ld_out < a->n_traj)
         return fail(SODM_EINVAL, "sodm_ode_run: need 0 <= n_traj <= ld_in, ld_out");
@@ -64,5 +64,13 @@ inline int build_ode_launch(const sodm_ode_args* a, OdeLaunch& L, sodm_model_inf
     }
     return SODM_OK;
 }
+
+#ifndef SODM_PLUGIN_BUILD
+inline int build_ode_launch(const sodm_ode_args* a, OdeLaunch& L, sodm_model_info& info) {
+    if (!a) return fail(SODM_EINVAL, "sodm_ode_run: null args");
+    if (sodm_model_info_get(a->model, a->model_arg, &info) != SODM_OK) return SODM_EMODEL;
+    return build_ode_launch_for(a, L, info);
+}
+#endif
 
 }  // namespace sodm
