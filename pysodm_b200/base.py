@@ -130,10 +130,7 @@ class _DeviceBackedModel:
     # ---------------------------------------------------------------------------------------------------------
     def _bind_device_functor(self):
         if not self.device_model:
-            raise NotImplementedError(
-                f"{type(self).__name__} declares no `device_model`. pysodm_b200 simulates hand-written device functors "
-                f"only ({sorted(registry.SPECS)}); arbitrary Python `{self._rhs_name}` functions cannot run on the GPU "
-                "and there is no CPU fallback.")
+            return self._bind_generated_functor()
         spec = registry.get(self.device_model)
         if spec.kind != self._kind:
             raise TypeError(f"device functor '{spec.name}' is a {spec.kind} model, {type(self).__name__} is a {self._kind} model")
@@ -151,6 +148,36 @@ class _DeviceBackedModel:
             if name not in spec.tdpf_params:
                 raise NotImplementedError(f"device functor '{spec.name}' has no time-dependent slot for parameter "
                                           f"'{name}' (supported: {list(spec.tdpf_params)})")
+
+    def _bind_generated_functor(self):
+        """No hand-written functor declared: translate the class's own Python functions (codegen.py) and compile them
+        into a plugin library (plugin.py).  Flat parameter order: declaration order, time-dependent parameters last."""
+        from . import plugin
+        tdpf = [n for n in self.parameters_names_modeldeclaration if n in (self.time_dependent_parameters or {})]
+        order = [n for n in self.parameters_names_modeldeclaration if n not in tdpf] + tdpf
+        shapes = OrderedDict()
+        for name in order:
+            value = self.parameters[name]
+            if callable(value) or isinstance(value, (str, dict)):
+                raise NotImplementedError(f"parameter '{name}' is not numeric; generated device models take scalars and arrays")
+            shapes[name] = tuple(np.shape(np.asarray(value, dtype=np.float64)))
+        state_shapes = OrderedDict((k, tuple(self.state_shapes[k])) for k in self.states_names)
+        origin = f" of {type(self).__module__}.{type(self).__qualname__}"
+        if self._kind == "ode":
+            if tdpf:
+                raise NotImplementedError("time-dependent parameter functions are not yet available for device ODE models")
+            plug = plugin.build_ode(self.integrate, state_shapes, shapes, self.initial_states, self.parameters, origin)
+        else:
+            plug = plugin.build_jump(self.compute_rates, self.apply_transitionings, state_shapes, shapes, tdpf,
+                                     self.initial_states, self.parameters, origin)
+        spec = registry.DeviceSpec(plug.name, self._kind, list(state_shapes.items()), list(shapes.items()), tdpf_params=tdpf)
+        self.device_model = plug
+        self._model_arg = 0
+        self._spec, self._spec_params = spec, shapes
+        self._param_offsets, self._n_param_flat = spec.param_offsets(0)
+        if self._n_param_flat > _ffi.MAX_PARAM or plug.info.n_state > _ffi.MAX_STATE and self._kind == "jump":
+            raise NotImplementedError(f"generated models are limited to {_ffi.MAX_PARAM} flat parameter elements and "
+                                      f"{_ffi.MAX_STATE} flat state elements per launch block")
 
     def _flat_y0(self, initial_states):
         return np.concatenate([np.ravel(np.asarray(v, dtype=np.float64)) for v in initial_states.values()])

@@ -163,6 +163,27 @@ class Sym:
     def __repr__(self):
         return f"<Sym {self.i}:{self.g.nodes[self.i][0]}>"
 
+    # a model value behaves like a NumPy scalar / 0-d array where user code asks for its geometry
+    shape, ndim, size = (), 0, 1
+
+    @property
+    def T(self): return self
+    def sum(self, *a, **k): return self
+    def copy(self): return self
+    def item(self): return self
+    def squeeze(self, *a, **k): return self
+    def reshape(self, *shape):
+        shape = shape[0] if len(shape) == 1 and isinstance(shape[0], (tuple, list)) else shape
+        out = np.empty(shape, dtype=object)
+        out.fill(self)
+        if out.size != 1:
+            raise ValueError(f"cannot reshape a scalar into shape {tuple(shape)}")
+        return out
+    def __getitem__(self, key):
+        if key == () or key is Ellipsis:
+            return self
+        raise IndexError("a scalar model value cannot be indexed")
+
 
 for _name in _UNARY:                       # np.exp(object array) calls element.exp()
     setattr(Sym, _name, (lambda op: lambda self: self._unary(op))(_name))
@@ -256,11 +277,26 @@ def _collect(values, shapes, what):
         want = tuple(shape)
         if a.shape != want:
             try:
-                a = np.broadcast_to(a, want)
+                a = a.reshape(want) if a.size == max(1, int(np.prod(want))) else np.broadcast_to(a, want)
             except ValueError:
                 raise TraceError(f"{what}: '{name}' has shape {a.shape}, expected {want}") from None
         out.extend(a.reshape(-1).tolist())
     return out
+
+
+def _inputs(graph, state_shapes, param_shapes, kind_y):
+    """Symbolic keyword arguments {state / parameter name: array of leaves}; leaves are numbered in flat order.  The
+    model functions are called BY NAME, as the reference does (`self.compute_rates(date, **states, **params)`,
+    base.py:392), so the order of the parameters in their signatures is free."""
+    kw, off = {}, 0
+    for name, shape in state_shapes.items():
+        kw[name] = _sym_array(graph, "y", tuple(shape), kind_y, off)
+        off += int(np.prod(shape)) if shape else 1
+    off = 0
+    for name, shape in param_shapes.items():
+        kw[name] = _sym_array(graph, "par", tuple(shape), "f", off)
+        off += int(np.prod(shape)) if shape else 1
+    return kw
 
 
 def trace_ode(integrate, state_shapes, param_shapes):
@@ -268,15 +304,7 @@ def trace_ode(integrate, state_shapes, param_shapes):
     g = Graph()
     fn = _retarget(integrate, g)
     t = g.leaf(("t", 0), "f")
-    args, off = [], 0
-    for name, shape in state_shapes.items():
-        args.append(_sym_array(g, "y", tuple(shape), "f", off))
-        off += int(np.prod(shape)) if shape else 1
-    off = 0
-    for name, shape in param_shapes.items():
-        args.append(_sym_array(g, "par", tuple(shape), "f", off))
-        off += int(np.prod(shape)) if shape else 1
-    res = fn(t, *args)
+    res = fn(t, **_inputs(g, state_shapes, param_shapes, "f"))
     if not isinstance(res, (tuple, list)):
         res = (res,)
     outs = _collect(res, state_shapes, "integrate")
@@ -292,17 +320,7 @@ def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes):
     fn = _retarget(compute_rates, g)
     t = g.leaf(("t", 0), "f")
 
-    def inputs(graph, kind_y):
-        args, off = [], 0
-        for name, shape in state_shapes.items():
-            args.append(_sym_array(graph, "y", tuple(shape), kind_y, off))
-            off += state_sizes[name]
-        off = 0
-        for name, shape in param_shapes.items():
-            args.append(_sym_array(graph, "par", tuple(shape), "f", off))
-            off += int(np.prod(shape)) if shape else 1
-        return args
-    rates = fn(t, *inputs(g, "f"))
+    rates = fn(t, **_inputs(g, state_shapes, param_shapes, "f"))
     if not isinstance(rates, dict):
         raise TraceError("compute_rates must return a dict {state: [rate arrays]}")
     channels = {}                                    # state -> list over transitions of flat expression lists
@@ -312,8 +330,14 @@ def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes):
         per = []
         for r in lst:
             a = np.asarray(r, dtype=object)
-            if a.shape != tuple(state_shapes[name]):
-                raise TraceError(f"rate of '{name}' has shape {a.shape}, expected {tuple(state_shapes[name])} (base.py:392-401)")
+            want = tuple(state_shapes[name])
+            if a.shape != want:
+                # the reference holds dimensionless states as one-element arrays, so np.array([gamma]) is a valid rate
+                # for a scalar state (src/tests/test_JumpProcess.py:19); anything else must broadcast to the state
+                try:
+                    a = a.reshape(want) if a.size == max(1, int(np.prod(want))) else np.broadcast_to(a, want)
+                except ValueError:
+                    raise TraceError(f"rate of '{name}' has shape {a.shape}, expected {want} (base.py:392-401)") from None
             per.append([x if isinstance(x, Sym) else g.const(x) for x in a.reshape(-1).tolist()])
         channels[name] = per
     # ---- bookkeeping: integers
@@ -333,7 +357,7 @@ def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes):
                 slots[(name, i, e)] = c
                 c += 1
             T[name].append(arr.reshape(tuple(state_shapes[name])) if state_shapes[name] else arr[0])
-    new = fn2(t2, tau2, T, *inputs(g2, "i"))
+    new = fn2(t2, tau2, T, **_inputs(g2, state_shapes, param_shapes, "i"))
     if not isinstance(new, (tuple, list)):
         new = (new,)
     outs = _collect(new, state_shapes, "apply_transitionings")
@@ -424,3 +448,243 @@ def emit(graph, outputs, ctype, leaf_expr, prefix="v"):
         name[i] = f"{prefix}{i}"
         lines.append(f"const {ctype} {prefix}{i} = {expr};")
     return lines, [name[o.i] for o in outputs]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# functor sources
+# ---------------------------------------------------------------------------------------------------------------------
+def _indent(lines, n=8):
+    pad = " " * n
+    return "\n".join(pad + ln for ln in lines)
+
+
+def _reject_time(graph, outputs, what):
+    used = set()
+    stack = [o.i for o in outputs]
+    while stack:
+        i = stack.pop()
+        if i in used:
+            continue
+        used.add(i)
+        op, args, _ = graph.nodes[i]
+        if op == "in" and args[0][0] in ("t", "tau"):
+            raise TraceError(f"{what} uses its `{args[0][0]}` argument explicitly; on the device, time dependence of a "
+                             "jump process comes from time-dependent parameter functions")
+        if op not in ("in", "const"):
+            stack.extend(args)
+
+
+def ode_source(integrate, state_shapes, param_shapes, origin=""):
+    """C++ translation unit of a plugin holding the ODE `integrate`.  -> (source, n_state, n_param)."""
+    g, outs = trace_ode(integrate, state_shapes, param_shapes)
+    n_state = len(outs)
+    n_param = sum(int(np.prod(s)) if s else 1 for s in param_shapes.values())
+
+    def leaf(name):
+        return {"t": "t", "y": f"y[{name[1]}]", "par": f"par[{name[1]}]"}[name[0]]
+    lines, exprs = emit(g, outs, "double", leaf)
+    body = _indent(lines) + "\n" + _indent([f"dy[{j}] = {e};" for j, e in enumerate(exprs)])
+    src = f"""// GENERATED by pysodm_b200.codegen from the Python function `integrate`{origin} -- do not edit.
+// {len(g.nodes)} expression nodes, {len(lines)} statements.
+#include "plugin.cuh"
+
+namespace sodm {{
+struct GenModel {{
+    static constexpr int N = {n_state}, NPAR = {max(n_param, 1)};
+    __host__ __device__ static void rhs(double t, const double* y, const double* par, double* dy) {{
+        (void)t; (void)par;
+{body}
+    }}
+}};
+}}  // namespace sodm
+
+SODM_ODE_PLUGIN(::sodm::GenModel)
+
+// one evaluation on the HOST (the functor is __host__ __device__): build-time self-check against the Python function
+extern "C" void sodm_plugin_host_rhs(double t, const double* y, const double* par, double* dy) {{
+    ::sodm::GenModel::rhs(t, y, par, dy);
+}}
+"""
+    return src, n_state, n_param
+
+
+def jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes, tdpf_params=(), origin=""):
+    """C++ translation unit of a plugin holding a jump process.  `param_shapes` must list the time-dependent parameters
+    LAST (they are read from the per-step table instead of the parameter vector).
+    -> (source, layout) with layout = dict(n_state, n_param, n_channel, n_draw, tdpf_offset, tdpf_count, slot_of)."""
+    names = list(param_shapes)
+    n_tdpf = len(tdpf_params)
+    if n_tdpf and names[-n_tdpf:] != list(tdpf_params):
+        raise ValueError("time-dependent parameters must come last in the flat parameter order")
+    tr = trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes)
+    sizes = {k: (int(np.prod(s)) if s else 1) for k, s in param_shapes.items()}
+    n_param = sum(sizes.values())
+    tdpf_count = sum(sizes[k] for k in tdpf_params)
+    tdpf_offset = n_param - tdpf_count if tdpf_count else 0
+    n_state = sum(tr["state_sizes"].values())
+    g, g2 = tr["rate_graph"], tr["apply_graph"]
+    state_off, off = {}, 0
+    for name, n in tr["state_sizes"].items():
+        state_off[name] = off
+        off += n
+    # ---- which transitionings does the bookkeeping read?
+    used_T = set()
+    stack = [o.i for o in tr["new_states"]]
+    seen = set()
+    while stack:
+        i = stack.pop()
+        if i in seen:
+            continue
+        seen.add(i)
+        op, args, _ = g2.nodes[i]
+        if op == "in":
+            if args[0][0] == "T":
+                used_T.add(args[0][1])
+        elif op != "const":
+            stack.extend(args)
+    _reject_time(g2, tr["new_states"], "apply_transitionings")
+    # ---- draw slots: per compartment element, its exits in order; trailing exits nobody reads are not drawn (their
+    # probability still enters the normaliser W of the reference's quirk, base.py:339-342)
+    slot_of, groups, n_draw, dep_mask = {}, [], 0, 0
+    for name, per in tr["channels"].items():
+        m = len(per)
+        for e in range(tr["state_sizes"][name]):
+            drawn = m
+            while drawn > 0 and tr["slots"][(name, drawn - 1, e)] not in used_T:
+                drawn -= 1
+            first = n_draw
+            for i in range(drawn):
+                slot_of[tr["slots"][(name, i, e)]] = n_draw
+                if i > 0:
+                    dep_mask |= 1 << n_draw
+                n_draw += 1
+            groups.append((name, e, m, drawn, first))
+    if n_draw > 64:
+        raise TraceError(f"{n_draw} binomial draws per step; the sampler's work list holds at most 64")
+    if n_draw == 0:
+        raise TraceError("apply_transitionings reads none of the transitionings")
+    all_rates = [x for name, per in tr["channels"].items() for flat in per for x in flat]
+    _reject_time(g, all_rates, "compute_rates")
+
+    def leaf_f(name):
+        if name[0] == "y":
+            return f"(float)y[{name[1]}]"
+        if name[0] == "par":
+            e = name[1]
+            return f"tab[{e - tdpf_offset}]" if tdpf_count and e >= tdpf_offset else f"pre.par[{e}]"
+        raise TraceError(f"unexpected input {name}")
+
+    def leaf_d(name):
+        if name[0] == "y":
+            return f"(double)y[{name[1]}]"
+        if name[0] == "par":
+            return f"par[{name[1]}]"
+        raise TraceError(f"unexpected input {name}")
+    f_lines, f_exprs = emit(g, all_rates, "float", leaf_f)
+    d_lines, d_exprs = emit(g, all_rates, "double", leaf_d, prefix="u")
+    rate_expr, rate_expr_d, k = {}, {}, 0
+    for name, per in tr["channels"].items():
+        for i, flat in enumerate(per):
+            for e in range(len(flat)):
+                rate_expr[(name, i, e)] = f_exprs[k]
+                rate_expr_d[(name, i, e)] = d_exprs[k]
+                k += 1
+    put = []
+    for name, e, m, drawn, first in groups:
+        j = state_off[name] + e
+        ps = [f"leave_prob({rate_expr[(name, i, e)]}, tau)" for i in range(m)]
+        put.append("{")
+        for i in range(m):
+            put.append(f"    const float p{i} = {ps[i]};")
+        put.append(f"    const float W0 = quirk ? 1.0f + p{m - 1} : 1.0f;")
+        for i in range(drawn):
+            if i > 0:
+                put.append(f"    const float W{i} = W{i - 1} - p{i - 1};")
+            put.append(f"    w.put({first + i}, y[{j}], p{i} / W{i});")
+        put.append("}")
+
+    def leaf_i(name):
+        if name[0] == "y":
+            return f"y[{name[1]}]"
+        if name[0] == "T":
+            return f"T{name[1]}"
+        raise TraceError("apply_transitionings may only combine states and transitionings")
+    a_lines, a_exprs = emit(g2, tr["new_states"], "int", leaf_i, prefix="n")
+    get = [f"const int T{c} = w.get({s});" for c, s in sorted(slot_of.items())]
+    fire_T = [f"const int T{c} = ch == {c} ? 1 : 0;" for c in sorted(used_T)]
+    assign = [f"y[{j}] = {e};" for j, e in enumerate(a_exprs)]
+    prop = []
+    for (name, i, e), c in sorted(tr["slots"].items(), key=lambda kv: kv[1]):
+        prop.append(f"a[{c}] = (double)y[{state_off[name] + e}] * ({rate_expr_d[(name, i, e)]});")
+    npar_arr = max(n_param, 1)
+    src = f"""// GENERATED by pysodm_b200.codegen from the Python functions `compute_rates` / `apply_transitionings`{origin} -- do not edit.
+// {n_state} flat states, {n_param} flat parameters ({tdpf_count} time dependent), {tr['n_channel']} channels, {n_draw} binomial draws per step.
+#include "plugin.cuh"
+
+namespace sodm {{
+struct GenModel {{
+    static constexpr int NS = {n_state}, NPAR = {npar_arr}, NCH = {tr['n_channel']}, TDPF_OFFSET = {tdpf_offset}, TDPF_COUNT = {tdpf_count};
+    static constexpr int NDRAW = {n_draw};
+    static constexpr uint64_t DEP_MASK = {dep_mask}ull;
+    struct Pre {{ float par[{npar_arr}]; }};
+    __host__ __device__ static Pre prepare(const double* par, float, bool) {{
+        Pre pre;
+#pragma unroll
+        for (int e = 0; e < {npar_arr}; ++e) pre.par[e] = (float)par[e];
+        return pre;
+    }}
+    // rates in FP32 as in the hand-written functors; law of the draws: jump_models.cuh header (reference base.py:283-348)
+    template <class W>
+    __host__ __device__ static void propose(const int* y, const Pre& pre, const float* tab, float tau, bool quirk, W& w) {{
+        (void)tab; (void)pre;
+{_indent(f_lines)}
+{_indent(put)}
+    }}
+    template <class W>
+    __host__ __device__ static void apply(int* y, const W& w) {{
+{_indent(get)}
+{_indent(a_lines)}
+{_indent(assign)}
+    }}
+    __host__ __device__ static void propensities(const int* y, const double* par, double* a) {{
+        (void)par;
+{_indent(d_lines)}
+{_indent(prop)}
+    }}
+    __host__ __device__ static void fire(int* y, int ch) {{
+{_indent(fire_T)}
+{_indent(a_lines)}
+{_indent(assign)}
+    }}
+}};
+}}  // namespace sodm
+
+SODM_JUMP_PLUGIN(::sodm::GenModel)
+
+// one evaluation on the HOST (the functor is __host__ __device__): build-time self-check against the Python functions
+namespace {{
+struct HostList {{
+    int n[{n_draw}];
+    float p[{n_draw}];
+    __host__ __device__ void put(int d, int nd, float pd) {{ n[d] = nd; p[d] = pd; }}
+    __host__ __device__ int get(int d) const {{ return n[d]; }}
+}};
+}}
+extern "C" void sodm_plugin_host_propose(const int* y, const double* par, const float* tab, double tau, int quirk, int* n, float* p) {{
+    HostList w;
+    const auto pre = ::sodm::GenModel::prepare(par, (float)tau, quirk != 0);
+    ::sodm::GenModel::propose(y, pre, tab, (float)tau, quirk != 0, w);
+    for (int d = 0; d < {n_draw}; ++d) {{ n[d] = w.n[d]; p[d] = w.p[d]; }}
+}}
+extern "C" void sodm_plugin_host_apply(int* y, const int* draws) {{
+    HostList w;
+    for (int d = 0; d < {n_draw}; ++d) w.n[d] = draws[d];
+    ::sodm::GenModel::apply(y, w);
+}}
+extern "C" void sodm_plugin_host_propensities(const int* y, const double* par, double* a) {{ ::sodm::GenModel::propensities(y, par, a); }}
+extern "C" void sodm_plugin_host_fire(int* y, int ch) {{ ::sodm::GenModel::fire(y, ch); }}
+"""
+    layout = {"n_state": n_state, "n_param": n_param, "n_channel": tr["n_channel"], "n_draw": n_draw,
+              "tdpf_offset": tdpf_offset, "tdpf_count": tdpf_count, "slot_of": slot_of, "groups": groups,
+              "channel_slots": tr["slots"], "dep_mask": dep_mask}
+    return src, layout

@@ -217,10 +217,12 @@ void philox_block(const StepKey& key, int lane, uint32_t tag, uint32_t (&out)[4]
 // warp instructions than the walk, but the queue traffic through shared memory, the ballots and the extra Philox
 // blocks leave it at 4.6 M traj/s against 6.3 M traj/s for the walk at 32 resident warps per SM; it is kept for
 // models whose draws are more expensive relative to the bookkeeping.
-template <int NDRAW, uint32_t DEP_MASK>
+template <int NDRAW, uint64_t DEP_MASK64>
 __host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key, WorkList& w, uint32_t& st) {
-    static_assert(NDRAW <= 32, "at most 32 draws per step");
+    static_assert(NDRAW <= 32, "the cooperative sampler takes at most 32 draws per step");
+    constexpr uint32_t DEP_MASK = (uint32_t)DEP_MASK64;
     constexpr int LEVELS = max_level(DEP_MASK, NDRAW) + 1;
+    static_assert(LEVELS <= 2, "the cooperative sampler handles compartments with at most two exits");
     constexpr int CAP = NDRAW * COOP_LANES;
     const int S = w.stride, lane = w.lane;
     const unsigned lt = coop_lt(lane);
@@ -376,10 +378,10 @@ struct WalkRng {
     uint32_t w0, w1, w2, w3;
     bool second;
 };
-template <int NDRAW, uint32_t DEP_MASK>
+template <int NDRAW, uint64_t DEP_MASK>
 __host__ __device__ __forceinline__ void sample_worklist_walk(WalkRng& rng, WorkList& w, uint32_t& st) {
     const int S = w.stride, lane = w.lane;
-    int d = 0, prev = 0;
+    int d = 0, chain = 0;                // chain = what the earlier exits of the same compartment element have taken
     // Every trip is one attempt that consumes exactly two Philox words, and every lane starts a step on a fresh block
     // (the half-used one of the previous step is dropped): the lanes of a warp then refill on the same trips, so the
     // generator -- a sixth of the kernel's instructions -- always runs with the whole warp.  Letting each lane carry
@@ -388,7 +390,8 @@ __host__ __device__ __forceinline__ void sample_worklist_walk(WalkRng& rng, Work
     while (d < NDRAW) {
         int n = w.n[d * S + lane];
         const float p = w.p[d * S + lane];
-        if ((DEP_MASK >> d) & 1u) n -= prev;
+        const bool dep = (DEP_MASK >> d) & 1ull;
+        if (dep) n -= chain;
         if (!rng.second) {
             uint32_t b[4];
             rng.gen.next4(b);
@@ -400,7 +403,7 @@ __host__ __device__ __forceinline__ void sample_worklist_walk(WalkRng& rng, Work
         if (binomial_try_words(n, p, wu, wv, k)) {
             if (k < 0) { st |= ST_BAD_PROB; k = 0; }
             w.n[d * S + lane] = k;
-            prev = k;
+            chain = dep ? chain + k : k;
             ++d;
         }
     }
@@ -446,8 +449,8 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
         const float* tab = M::TDPF_COUNT ? table + (int64_t)L.tdpf_index[k] * M::TDPF_COUNT : table;
         M::propose(y, pre, tab, tau, quirk, w);
         key.step = (uint32_t)k;
-        if (COOP) sample_worklist_coop<M::NDRAW, M::DEP_MASK>(key, w, st);
-        else sample_worklist_walk<M::NDRAW, M::DEP_MASK>(rng, w, st);
+        if constexpr (COOP) sample_worklist_coop<M::NDRAW, (uint64_t)M::DEP_MASK>(key, w, st);
+        else sample_worklist_walk<M::NDRAW, (uint64_t)M::DEP_MASK>(rng, w, st);
         M::apply(y, w);
         if (ALIGNED) {
             if (--until_out == 0) {

@@ -1,0 +1,105 @@
+// Entry points of a model plugin (include/sodm_plugin.h): a generated translation unit defines ONE functor and expands
+// SODM_JUMP_PLUGIN(Functor) or SODM_ODE_PLUGIN(Functor); everything else -- kernels, launch validation, samplers,
+// integrators -- is the code of the built-in models, instantiated for the new functor.
+#pragma once
+#define SODM_PLUGIN_BUILD 1
+#include "../../include/sodm_plugin.h"
+#include "jump_kernels.cuh"
+#include "ode_kernels.cuh"
+
+namespace sodm {
+char* error_buffer() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+}  // namespace sodm
+
+#define SODM_PLUGIN_COMMON()                                                                      \
+    extern "C" int sodm_plugin_abi_version(void) { return SODM_ABI_VERSION; }                    \
+    extern "C" const char* sodm_plugin_last_error(void) { return ::sodm::error_buffer(); }
+
+#define SODM_JUMP_PLUGIN(M)                                                                       \
+    SODM_PLUGIN_COMMON()                                                                          \
+    static sodm_model_info plugin_info() {                                                        \
+        sodm_model_info info = {};                                                                \
+        info.kind = SODM_KIND_JUMP;                                                               \
+        info.n_state = M::NS;                                                                     \
+        info.n_param = M::NPAR;                                                                   \
+        info.n_channel = M::NCH;                                                                  \
+        info.tdpf_offset = M::TDPF_OFFSET;                                                        \
+        info.tdpf_count = M::TDPF_COUNT;                                                          \
+        info.supports_ssa = 1;                                                                    \
+        return info;                                                                              \
+    }                                                                                             \
+    extern "C" int sodm_plugin_info(sodm_model_info* out) {                                       \
+        if (!out) return ::sodm::fail(SODM_EINVAL, "sodm_plugin_info: null output");              \
+        *out = plugin_info();                                                                     \
+        return SODM_OK;                                                                           \
+    }                                                                                             \
+    extern "C" int sodm_plugin_jump_run(const sodm_jump_args* a) {                                \
+        static_assert(M::NS <= ::sodm::MAX_STATE && M::NPAR <= ::sodm::MAX_PARAM, "model too large for one launch block"); \
+        ::sodm::JumpLaunch L;                                                                     \
+        bool aligned = false;                                                                     \
+        const int rc = ::sodm::build_jump_launch_for(a, L, aligned, plugin_info());               \
+        if (rc != SODM_OK) return rc;                                                             \
+        if (a->n_traj == 0) return SODM_OK;                                                       \
+        if (a->compat & ::sodm::TUNE_COOPERATIVE)                                                 \
+            return ::sodm::fail(SODM_EUNSUPPORTED, "generated models use the per-lane walk sampler only"); \
+        return ::sodm::launch_plugin_jump<M>(L, a->method, aligned, a->out_dtype, (cudaStream_t)a->stream); \
+    }                                                                                             \
+    extern "C" int sodm_plugin_ode_run(const sodm_ode_args*) {                                    \
+        return ::sodm::fail(SODM_EUNSUPPORTED, "this plugin holds a jump-process model");         \
+    }
+
+#define SODM_ODE_PLUGIN(M)                                                                        \
+    SODM_PLUGIN_COMMON()                                                                          \
+    static sodm_model_info plugin_info() {                                                        \
+        sodm_model_info info = {};                                                                \
+        info.kind = SODM_KIND_ODE;                                                                \
+        info.n_state = M::N;                                                                      \
+        info.n_param = M::NPAR;                                                                   \
+        return info;                                                                              \
+    }                                                                                             \
+    extern "C" int sodm_plugin_info(sodm_model_info* out) {                                       \
+        if (!out) return ::sodm::fail(SODM_EINVAL, "sodm_plugin_info: null output");              \
+        *out = plugin_info();                                                                     \
+        return SODM_OK;                                                                           \
+    }                                                                                             \
+    extern "C" int sodm_plugin_ode_run(const sodm_ode_args* a) {                                  \
+        static_assert(M::NPAR <= ::sodm::ODE_MAX_PARAM, "too many flat parameter elements");      \
+        ::sodm::OdeLaunch L;                                                                      \
+        const int rc = ::sodm::build_ode_launch_for(a, L, plugin_info());                         \
+        if (rc != SODM_OK) return rc;                                                             \
+        if (a->n_traj == 0) return SODM_OK;                                                       \
+        return ::sodm::launch_thread<M>(L, a->method, a->out_dtype, (cudaStream_t)a->stream);     \
+    }                                                                                             \
+    extern "C" int sodm_plugin_jump_run(const sodm_jump_args*) {                                  \
+        return ::sodm::fail(SODM_EUNSUPPORTED, "this plugin holds an ODE model");                 \
+    }
+
+namespace sodm {
+
+// A generated model gets the kernels a front end can ask for -- int32 output on the aligned grid, FP64 otherwise, SSA in
+// FP64 -- with the default (walk) sampler: a third of the instantiations of a built-in model, ~15 s of nvcc.
+template <class M>
+static int launch_plugin_jump(const JumpLaunch& L, int method, bool aligned, int dtype, cudaStream_t stream) {
+    const unsigned grid = (unsigned)((L.n_traj + JUMP_BLOCK - 1) / JUMP_BLOCK);
+    if (method == SODM_JUMP_SSA) {
+        if (dtype != SODM_F64) return fail(SODM_EUNSUPPORTED, "generated models write SSA output as float64");
+        ssa_kernel<M, double><<<grid, JUMP_BLOCK, 0, stream>>>(L);
+    } else {
+        const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
+        void (*kernel)(JumpLaunch) = nullptr;
+        if (aligned && dtype == SODM_I32) kernel = tau_leap_kernel<M, int32_t, true, false>;
+        else if (aligned && dtype == SODM_F64) kernel = tau_leap_kernel<M, double, true, false>;
+        else if (!aligned && dtype == SODM_F64) kernel = tau_leap_kernel<M, double, false, false>;
+        else return fail(SODM_EUNSUPPORTED, "generated models write int32 (tau = 2^-k) or float64 output");
+        if (smem > 200 * 1024) return fail(SODM_EUNSUPPORTED, "model needs %zu bytes of shared memory per block", smem);
+        SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 96 * 1024 ? smem : 96 * 1024)));
+        kernel<<<grid, JUMP_BLOCK, smem, stream>>>(L);
+    }
+    SODM_CUDA_CHECK(cudaGetLastError());
+    return SODM_OK;
+}
+
+}  // namespace sodm

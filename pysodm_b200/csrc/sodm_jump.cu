@@ -5,87 +5,7 @@
 // influenza contact matrices) staged once per block in shared memory and read by broadcast.
 // Replaces /root/reference/src/pySODM/models/base.py:558-566 (the loop over draws in
 // `JumpProcess.sim`) and everything it calls (:206-348, :352-440).
-#include "jump_setup.cuh"
-
-namespace sodm {
-
-constexpr int JUMP_BLOCK = 128;
-// Resident blocks per SM the compiler must allow for.  The samplers are latency / instruction-fetch bound (ncu:
-// `no_instruction` is the top stall), so resident warps matter more than registers: measured on influenza,
-// per-lane walk 352 / 272 / 262 / 259 ms at 1 / 5 / 6 / 8 blocks, cooperative 339 / 294 / 311 / 426 ms.
-#ifndef SODM_WALK_MIN_BLOCKS
-#define SODM_WALK_MIN_BLOCKS 8
-#endif
-#ifndef SODM_COOP_MIN_BLOCKS
-#define SODM_COOP_MIN_BLOCKS 5
-#endif
-
-template <class M, typename OutT, bool ALIGNED, bool COOP>
-__global__ void __launch_bounds__(JUMP_BLOCK, COOP ? SODM_COOP_MIN_BLOCKS : SODM_WALK_MIN_BLOCKS) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
-    extern __shared__ float smem[];
-    // [NDRAW][JUMP_BLOCK] draw counts | [NDRAW][JUMP_BLOCK] probabilities | per-warp queues | TDPF table
-    constexpr int WARPS = JUMP_BLOCK / 32;
-    constexpr int QW = coop_queue_words(M::NDRAW);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WorkList w;
-    w.n = reinterpret_cast<int*>(smem) + warp * 32;
-    w.p = smem + M::NDRAW * JUMP_BLOCK + warp * 32;
-    uint32_t* q = reinterpret_cast<uint32_t*>(smem) + 2 * M::NDRAW * JUMP_BLOCK + warp * QW;
-    w.qs_u = q;
-    w.qs_v = q + COOP_QS_CAP;
-    w.qx_k = q + 2 * COOP_QS_CAP;
-    w.qx_l = reinterpret_cast<float*>(q + 2 * COOP_QS_CAP + COOP_QX_CAP);
-    w.qm = reinterpret_cast<uint16_t*>(q + 2 * COOP_QS_CAP + 2 * COOP_QX_CAP);
-    w.qs = w.qm + M::NDRAW * 32;
-    w.qx = w.qs + COOP_QS_CAP;
-    w.stride = JUMP_BLOCK;
-    w.lane = lane;
-    float* table = smem + 2 * M::NDRAW * JUMP_BLOCK + (COOP ? WARPS * QW : 0);       // the walk sampler has no queues
-    const int n_tab = L.n_tdpf_values * M::TDPF_COUNT;
-    for (int e = threadIdx.x; e < n_tab; e += blockDim.x) table[e] = (float)L.tdpf_table[e];   // ABI speaks FP64, rates are FP32
-    __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < L.n_traj;
-    w.lanes = __ballot_sync(0xffffffffu, active);
-    if (w.lanes == 0u) return;                                    // whole warp past the end
-    tau_leap_trajectory<M, OutT, ALIGNED, COOP>(L, i, active, table, w);
-}
-
-template <class M, typename OutT>
-__global__ void __launch_bounds__(JUMP_BLOCK) ssa_kernel(const __grid_constant__ JumpLaunch L) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < L.n_traj) ssa_trajectory<M, OutT>(L, i);
-}
-
-template <class M, typename OutT>
-static int launch_jump(const JumpLaunch& L, int method, bool aligned, cudaStream_t stream) {
-    const unsigned grid = (unsigned)((L.n_traj + JUMP_BLOCK - 1) / JUMP_BLOCK);
-    if (method == SODM_JUMP_TAU_LEAP) {
-        const bool coop = (L.compat & TUNE_COOPERATIVE) != 0u;
-        const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK + (coop ? (size_t)(JUMP_BLOCK / 32) * coop_queue_words(M::NDRAW) : 0) +
-                             (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
-        void (*kernel)(JumpLaunch) = aligned ? (coop ? tau_leap_kernel<M, OutT, true, true> : tau_leap_kernel<M, OutT, true, false>)
-                                             : (coop ? tau_leap_kernel<M, OutT, false, true> : tau_leap_kernel<M, OutT, false, false>);
-        SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        kernel<<<grid, JUMP_BLOCK, smem, stream>>>(L);
-    } else {
-        ssa_kernel<M, OutT><<<grid, JUMP_BLOCK, 0, stream>>>(L);
-    }
-    SODM_CUDA_CHECK(cudaGetLastError());
-    return SODM_OK;
-}
-
-template <class M>
-static int launch_jump_dtype(const JumpLaunch& L, int method, bool aligned, int dtype, cudaStream_t stream) {
-    switch (dtype) {
-        case SODM_I32: return launch_jump<M, int32_t>(L, method, aligned, stream);
-        case SODM_F32: return launch_jump<M, float>(L, method, aligned, stream);
-        case SODM_F64: return launch_jump<M, double>(L, method, aligned, stream);
-    }
-    return fail(SODM_EINVAL, "sodm_jump_run: unknown out_dtype %d", dtype);
-}
-
-}  // namespace sodm
+#include "jump_kernels.cuh"
 
 using namespace sodm;
 

@@ -7,23 +7,16 @@
 // of the warp takes the same accept/reject decisions, so a trajectory never diverges.
 // Replaces /root/reference/src/pySODM/models/base.py:950-957 (the loop over draws in `ODE.sim`) and the
 // `solve_ivp` / `_solve_discrete` calls below it (:853-855).
-#include "ode_setup.cuh"
+#include "ode_kernels.cuh"
 
 namespace sodm {
 
-constexpr int ODE_BLOCK = 128;
 // resident blocks per SM for the reactor kernel: 248 registers / 2 blocks without the bound; measured on B200 (1e5 draws,
 // nx = 25): 330 / 294 / 310 ms at 2 / 3 / 4 blocks -- the kernel waits on FP64 dependency chains, so a third block helps
 // more than the spills cost
 #ifndef SODM_PFR_MIN_BLOCKS
 #define SODM_PFR_MIN_BLOCKS 3
 #endif
-
-template <class M, typename OutT>
-__global__ void __launch_bounds__(ODE_BLOCK) ode_thread_kernel(const __grid_constant__ OdeLaunch L, int method) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < L.n_traj) ode_thread_trajectory<M, OutT>(L, method, i);
-}
 
 // One warp per trajectory; lane l owns axial nodes l*NPL .. l*NPL+NPL-1.
 // Local element e = (phase*4 + species)*NPL + k  (phase 0 = fluid C_F, 1 = solid C_S; k = node within lane).
@@ -90,15 +83,6 @@ __global__ void __launch_bounds__(ODE_BLOCK, SODM_PFR_MIN_BLOCKS) ode_pfr_warp_k
     if (method == SODM_ODE_RK45) rk45_run<PfrWarpSystem<NPL>, OutT>(sys, L, i, y);
     else if (method == SODM_ODE_EULER) fixed_step_run<PfrWarpSystem<NPL>, OutT, false>(sys, L, i, y);
     else fixed_step_run<PfrWarpSystem<NPL>, OutT, true>(sys, L, i, y);
-}
-
-template <class M>
-static int launch_thread(const OdeLaunch& L, int method, int dtype, cudaStream_t stream) {
-    const unsigned grid = (unsigned)((L.n_traj + ODE_BLOCK - 1) / ODE_BLOCK);
-    if (dtype == SODM_F64) ode_thread_kernel<M, double><<<grid, ODE_BLOCK, 0, stream>>>(L, method);
-    else                   ode_thread_kernel<M, float><<<grid, ODE_BLOCK, 0, stream>>>(L, method);
-    SODM_CUDA_CHECK(cudaGetLastError());
-    return SODM_OK;
 }
 
 template <int NPL>

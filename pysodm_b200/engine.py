@@ -52,6 +52,15 @@ def _dev_i32(x, dev):
     return torch.from_numpy(np.ascontiguousarray(x, dtype=np.int32)).to(dev)
 
 
+def _resolve(model, model_arg=0):
+    """-> (model id, sodm_model_info, plugin or None).  `model` is a registered functor name or a `plugin.Plugin`
+    (a generated model in its own library, include/sodm_plugin.h)."""
+    if isinstance(model, str):
+        mid = _ffi.model_id(model)
+        return mid, _ffi.model_info(mid, model_arg), None
+    return 0, model.info, model
+
+
 def _stream_ptr(stream):
     if stream is None:
         stream = torch.cuda.current_stream()
@@ -89,8 +98,7 @@ def jump_run(model, y0, par, n_traj, t0, n_out, tau=0.5, method="tau_leap", var=
     """
     dev = dev or device()
     lib = _ffi.load()
-    mid = _ffi.model_id(model)
-    info = _ffi.model_info(mid)
+    mid, info, plug = _resolve(model)
     out_dtype = as_torch_dtype(out_dtype)
     y0_d = _dev_f64(y0, dev)
     if y0_d.shape[0] != info.n_state or (y0_d.dim() == 2 and y0_d.shape[1] != n_traj):
@@ -129,7 +137,10 @@ def jump_run(model, y0, par, n_traj, t0, n_out, tau=0.5, method="tau_leap", var=
         keep.append(sel)
     a.out, a.status, a.max_events = out.data_ptr(), status.data_ptr(), int(max_events)
     a.stream = _stream_ptr(stream)
-    _ffi.check(lib.sodm_jump_run(C.byref(a)), lib)
+    if plug is not None:
+        plug.jump_run(a)
+    else:
+        _ffi.check(lib.sodm_jump_run(C.byref(a)), lib)
     # device inputs are only read by work already queued on the stream; torch's caching allocator keeps
     # stream-ordered reuse safe on the current stream, so dropping `keep` here is fine
     return out, status
@@ -143,8 +154,7 @@ def ode_run(model, y0, par, n_traj, t0, n_out, method="RK45", rtol=1e-4, atol=1e
     Returns (out[n_state, n_kept, n_traj], nfev[n_traj], status[n_traj]) device tensors; asynchronous."""
     dev = dev or device()
     lib = _ffi.load()
-    mid = _ffi.model_id(model)
-    info = _ffi.model_info(mid, model_arg)
+    mid, info, plug = _resolve(model, model_arg)
     out_dtype = as_torch_dtype(out_dtype)
     y0_d = _dev_f64(y0, dev)
     if y0_d.shape[0] != info.n_state or (y0_d.dim() == 2 and y0_d.shape[1] != n_traj):
@@ -172,7 +182,10 @@ def ode_run(model, y0, par, n_traj, t0, n_out, method="RK45", rtol=1e-4, atol=1e
     a.out, a.nfev, a.status = out.data_ptr(), nfev.data_ptr(), status.data_ptr()
     a.max_steps = int(max_steps)
     a.stream = _stream_ptr(stream)
-    _ffi.check(lib.sodm_ode_run(C.byref(a)), lib)
+    if plug is not None:
+        plug.ode_run(a)
+    else:
+        _ffi.check(lib.sodm_ode_run(C.byref(a)), lib)
     return out, nfev, status
 
 

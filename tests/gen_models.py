@@ -1,0 +1,114 @@
+"""Model classes WITHOUT a hand-written device functor: pysodm_b200 translates their Python functions (codegen.py).
+Shared by the CPU and GPU tests of the generic-model path."""
+import numpy as np
+
+from pysodm_b200 import tutorial_data as td
+from pysodm_b200 import tutorial_models as tm
+from pysodm_b200.base import ODE, JumpProcess
+
+
+class GenInfluenza(tm.JumpProcess_influenza_model):
+    device_model = None
+
+
+class GenSirSi(tm.JumpProcess_SIR_SI):
+    device_model = None
+
+
+class GenSir(tm.JumpProcess_SIR):
+    device_model = None
+
+
+class GenOdeSirSi(tm.ODE_SIR_SI):
+    device_model = None
+
+
+class GenOdeSir(tm.ODE_SIR):
+    device_model = None
+
+
+class GenPfr(tm.packed_PFR):
+    device_model = None
+
+
+class SEIRD(JumpProcess):
+    """Not among the built-in functors: three competing exits from I (recovery, death, hospitalisation), an
+    age-stratified force of infection through a contact matrix parameter, a cumulative counter, scalar + vector states."""
+    states = ['S', 'E', 'I', 'H', 'R', 'D', 'cases']
+    parameters = ['beta', 'sigma', 'gamma', 'mu', 'eta', 'rho', 'M']
+    stratified_parameters = ['h']
+    dimensions = ['age']
+
+    @staticmethod
+    def compute_rates(t, S, E, I, H, R, D, cases, beta, sigma, gamma, mu, eta, rho, M, h):
+        N = S + E + I + H + R
+        foi = beta * (M @ (I / N))
+        size = np.ones(S.shape)
+        return {'S': [foi], 'E': [sigma * size], 'I': [gamma * (1 - h), mu * size, eta * h], 'H': [rho * size]}
+
+    @staticmethod
+    def apply_transitionings(t, tau, transitionings, S, E, I, H, R, D, cases, beta, sigma, gamma, mu, eta, rho, M, h):
+        T = transitionings
+        S_new = S - T['S'][0]
+        E_new = E + T['S'][0] - T['E'][0]
+        I_new = I + T['E'][0] - T['I'][0] - T['I'][1] - T['I'][2]
+        H_new = H + T['I'][2] - T['H'][0]
+        R_new = R + T['I'][0] + T['H'][0]
+        D_new = D + T['I'][1]
+        return S_new, E_new, I_new, H_new, R_new, D_new, cases + T['E'][0]
+
+
+SEIRD_AGES = ['young', 'adult', 'old']
+SEIRD_STATES = {'S': np.array([40000., 90000., 30000.]), 'E': np.array([20., 60., 10.]), 'I': np.array([15., 40., 8.])}
+SEIRD_PARAMS = {'beta': 0.045, 'sigma': 0.4, 'gamma': 0.25, 'mu': 0.01, 'eta': 0.2, 'rho': 0.1,
+                'M': np.array([[9.0, 3.0, 1.0], [3.0, 6.0, 1.5], [1.0, 1.5, 2.0]]), 'h': np.array([0.02, 0.08, 0.3])}
+
+
+def make_seird():
+    return SEIRD(SEIRD_STATES, SEIRD_PARAMS, coordinates={'age': SEIRD_AGES})
+
+
+class LotkaVolterra(ODE):
+    """Not among the built-in functors: exp / sqrt / power, a loop over coupled patches filled element by element."""
+    states = ['prey', 'pred']
+    parameters = ['a', 'b', 'c', 'd', 'mig']
+    dimensions = ['patch']
+
+    @staticmethod
+    def integrate(t, prey, pred, a, b, c, d, mig):
+        n = len(prey)
+        dprey = np.zeros(n)
+        dpred = np.zeros(n)
+        for j in range(n):
+            left, right = prey[(j - 1) % n], prey[(j + 1) % n]
+            season = 1 + 0.1 * np.sin(0.0172 * t)
+            dprey[j] = a * season * prey[j] - b * prey[j] * pred[j] + mig * (left - 2 * prey[j] + right)
+            dpred[j] = -c * pred[j] + d * np.sqrt(prey[j] ** 2 + 1e-12) * pred[j] * np.exp(-1e-3 * pred[j])
+        return dprey, dpred
+
+
+def make_lotka(n=5):
+    rng = np.random.default_rng(0)
+    return LotkaVolterra({'prey': 10 + rng.random(n) * 5, 'pred': 3 + rng.random(n)},
+                         {'a': 1.1, 'b': 0.4, 'c': 0.4, 'd': 0.1, 'mig': 0.05}, coordinates={'patch': list(range(n))})
+
+
+def make_influenza():
+    return GenInfluenza(td.INFLUENZA_INITIAL_STATES, td.INFLUENZA_PARAMETERS, coordinates={"age_group": td.AGE_GROUPS},
+                        time_dependent_parameters={"N": td.influenza_contact_function})
+
+
+SIRSI_STATES = {"S": np.array([606938., 1328733., 7352492., 2204478.]), "S_v": 1e6, "I_v": 2}
+SIRSI_PARAMS = {"alpha": np.array([0.05, 0.1, 0.2, 0.15]), "gamma": 5, "beta": 7}
+
+
+def make_sirsi(cls=GenSirSi, scale=1.0):
+    st = {k: np.floor(np.asarray(v, dtype=np.float64) * scale) for k, v in SIRSI_STATES.items()}
+    if scale != 1.0:
+        st["I_v"] = 2.0
+    return cls(st, dict(SIRSI_PARAMS), coordinates={"age_group": td.AGE_GROUPS})
+
+
+def make_pfr(nx, cls=GenPfr):
+    return cls(td.pfr_initial_states(nx), td.pfr_parameters(nx),
+               coordinates={"species": ["S", "A", "Es", "W"], "x": list(range(nx))})

@@ -1,0 +1,142 @@
+"""Generic models, CPU side: the tracer (codegen.py), the generated translation units compile for sm_100a, the plugin
+libraries export include/sodm_plugin.h, and the generated functors -- evaluated on the host -- reproduce the Python
+functions and the oracle's tau-leap law.  No GPU involved; nvcc is."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gen_models as gm
+from oracle import jump as ojump
+from pysodm_b200 import codegen, plugin
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_tracer_records_numpy_arithmetic():
+    g = codegen.Graph()
+    x = codegen._sym_array(g, "y", (3,), "f", 0)
+    M = np.arange(9.0).reshape(3, 3)
+    out = np.exp(-(M @ x)) / np.sum(x) + x ** 2 * np.array([1.0, 0.0, 2.0])
+    lines, exprs = codegen.emit(g, list(out), "double", lambda n: f"{n[0]}[{n[1]}]")
+    src = "\n".join(lines)
+    assert "exp(" in src and len(exprs) == 3
+    # the same expressions, evaluated through a tiny interpreter over the DAG, equal NumPy's on numbers
+    vals = np.array([0.3, 1.7, 2.2])
+
+    def ev(i, memo={}):
+        op, args, _ = g.nodes[i]
+        if op == "in":
+            return vals[args[0][1]]
+        if op == "const":
+            return float(args[0])
+        a = [ev(j) for j in args]
+        return {"add": lambda: a[0] + a[1], "sub": lambda: a[0] - a[1], "mul": lambda: a[0] * a[1], "div": lambda: a[0] / a[1],
+                "neg": lambda: -a[0], "exp": lambda: np.exp(a[0]), "pow": lambda: a[0] ** a[1]}[op]()
+    want = np.exp(-(M @ vals)) / np.sum(vals) + vals ** 2 * np.array([1.0, 0.0, 2.0])
+    assert np.allclose([ev(o.i) for o in out], want, rtol=1e-15)
+    # hash-consing: the shared denominator is one node
+    assert sum(1 for n in g.nodes if n[0] == "div") == 3
+
+
+def test_tracer_refuses_what_it_cannot_translate():
+    shapes, pars = {"S": (), "I": ()}, {"beta": ()}
+
+    def branchy(t, S, I, beta):
+        return (-beta * S if S > 0 else 0.0), beta * I
+    with pytest.raises(codegen.TraceError, match="comparison"):
+        codegen.trace_ode(branchy, shapes, pars)
+
+    def wrong_shape(t, S, I, beta):
+        return np.ones(3) * S, I
+    with pytest.raises(codegen.TraceError, match="shape"):
+        codegen.trace_ode(wrong_shape, shapes, pars)
+
+    def rates(t, S, I, beta):
+        return {"S": [beta * I * t]}
+
+    def apply_(t, tau, T, S, I, beta):
+        return S - T["S"][0], I + T["S"][0]
+    with pytest.raises(codegen.TraceError, match="explicitly"):
+        codegen.jump_source(rates, apply_, shapes, pars)
+
+    def rates_ok(t, S, I, beta):
+        return {"S": [beta * I]}
+
+    def apply_frac(t, tau, T, S, I, beta):
+        return S - 0.5 * T["S"][0], I + T["S"][0]
+    with pytest.raises(codegen.TraceError, match="integral"):
+        codegen.jump_source(rates_ok, apply_frac, shapes, pars)
+    with pytest.raises(NotImplementedError):                      # still no CPU fallback: a model must translate or fail
+        class Bad(gm.ODE):
+            states, parameters = ["S", "I"], ["beta"]
+            integrate = staticmethod(branchy)
+        Bad({"S": 1.0, "I": 1.0}, {"beta": 0.1})
+
+
+@pytest.mark.parametrize("make", [gm.make_influenza, gm.make_sirsi, gm.make_seird, gm.make_lotka, lambda: gm.make_pfr(5),
+                                  lambda: gm.GenSir({"S": 990, "I": 10}, {"beta": 0.9, "gamma": 0.2}),
+                                  lambda: gm.make_sirsi(gm.GenOdeSirSi),
+                                  lambda: gm.GenOdeSir({"S": 999, "I": 1}, {"beta": 0.35, "gamma": 5})])
+def test_generated_models_build_and_pass_their_self_check(make):
+    model = make()                                                # traces, compiles for sm_100a, evaluates once on the host
+    plug = model.device_model
+    assert isinstance(plug, plugin.Plugin) and os.path.dirname(plug.path) == plugin.PLUGIN_DIR
+    n_state = sum(int(np.prod(s)) if s else 1 for s in model.state_shapes.values())
+    assert plug.info.n_state == n_state and plug.info.n_param == model._n_param_flat
+    # every symbol of include/sodm_plugin.h is exported
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "sodm_plugin.h")).read(), flags=re.S)
+    raw = C.CDLL(plug.path)
+    for name in set(re.findall(r"\b(sodm_plugin_[a-z0-9_]+)\s*\(", text)):
+        assert hasattr(raw, name), name
+    assert make().device_model is plug                            # cached: same source, same library
+
+
+def test_generated_influenza_lists_the_reference_law():
+    model = gm.make_influenza()
+    plug, lay = model.device_model, model.device_model.layout
+    assert (lay["n_draw"], lay["n_channel"], lay["tdpf_offset"], lay["tdpf_count"]) == (24, 24, 8, 16)
+    from pysodm_b200 import tutorial_data as td
+    y = td.influenza_flat_y0()
+    par = td.influenza_flat_par()
+    par[8:] = td.CONTACT_TABLE.reshape(3, 16)[0]
+    for quirk in (True, False):
+        n, p = plugin.host_propose(plug, y, par, 0.5, quirk)
+        states = {k: np.asarray(v, dtype=np.float64) for k, v in td.INFLUENZA_INITIAL_STATES.items()}
+        for k in td.INFLUENZA_STATES:
+            states.setdefault(k, np.zeros(4))
+        pr = dict(td.INFLUENZA_PARAMETERS, N=td.CONTACT_TABLE.reshape(3, 4, 4)[0])
+        rates = type(model).compute_rates(0.0, **{k: states[k] for k in td.INFLUENZA_STATES}, **pr)
+        for name, e, m, drawn, first in lay["groups"]:
+            probs = ojump.transition_probabilities([np.asarray(r, dtype=np.float64)[e] for r in rates[name]], 0.5, quirk)
+            cond = probs[:m] / np.cumsum(probs[::-1])[::-1][:m]             # sequential conditional binomials of Multinomial(p / sum p)
+            assert np.allclose(p[first:first + drawn], cond[:drawn], rtol=3e-6), (name, e, quirk)
+            assert (n[first:first + drawn] == int(states[name][e])).all()
+
+
+def test_three_exits_and_bookkeeping_of_a_new_model():
+    model = gm.make_seird()
+    plug, lay = model.device_model, model.device_model.layout
+    assert lay["n_draw"] == 3 * 6 and lay["n_channel"] == 18
+    dep = [d for d in range(lay["n_draw"]) if (lay["dep_mask"] >> d) & 1]
+    assert len(dep) == 6                                          # exits 2 and 3 of I, for each of the three ages
+    # SSA pieces on the host: propensities = state * rate in the reference's channel order; one event of each channel
+    y = np.concatenate([np.ravel(np.asarray(model.initial_states[k], dtype=np.float64)) for k in model.states_names])
+    par = np.concatenate([np.ravel(np.asarray(model.parameters[k], dtype=np.float64)) for k in model._spec_params])
+    a = np.empty(lay["n_channel"])
+    y_i = y.astype(np.int32)
+    plug.lib.sodm_plugin_host_propensities(y_i.ctypes.data, np.concatenate([par, [0.0]]).ctypes.data, a.ctypes.data)
+    kw = {k: np.asarray(model.initial_states[k], dtype=np.float64) for k in model.states_names}
+    rates = gm.SEIRD.compute_rates(0.0, **kw, **model.parameters)
+    want = np.concatenate([np.ravel(kw[s] * np.asarray(r, dtype=np.float64)) for s, lst in rates.items() for r in lst])
+    assert np.allclose(a, want, rtol=1e-14)
+    for ch in range(lay["n_channel"]):
+        yy = y_i.copy()
+        plug.lib.sodm_plugin_host_fire(yy.ctypes.data, ch)
+        T = {s: [np.zeros(3) for _ in lst] for s, lst in rates.items()}
+        (s, i, e), = [k for k, c in lay["channel_slots"].items() if c == ch]
+        T[s][i][e] = 1
+        new = gm.SEIRD.apply_transitionings(0.0, 1.0, T, **kw, **model.parameters)
+        assert np.array_equal(yy, np.concatenate([np.ravel(v) for v in new]).astype(np.int32)), ch

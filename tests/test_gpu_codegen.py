@@ -1,0 +1,141 @@
+"""GPU parity tests of GENERATED models (codegen.py + plugin.py): model classes that declare no hand-written functor
+run from their own Python functions.  Bars as for the built-in functors: tau-leap / SSA in law (KS against ensembles
+produced by the unmodified reference, or by the pinned oracle for models the reference fixtures do not hold), ODE within
+rtol 1e-6 of the reference's scipy RK45 and with the same step sequence as the hand-written functors."""
+import numpy as np
+import pytest
+
+import cases
+import gen_models as gm
+from oracle import jump as ojump
+from oracle import models as omodels
+
+pytestmark = pytest.mark.gpu
+
+
+def test_generated_influenza_matches_reference_ensemble(golden):
+    from pysodm_b200 import tutorial_data as td
+    e = golden["jump_ensemble"]
+    model = gm.make_influenza()
+    n = 40_000
+    out = model.sim([td.INFLUENZA_START, td.INFLUENZA_END], N=n, tau=0.5, seed=3, output_dtype="int32")
+    mine = np.concatenate([np.moveaxis(out[s].values, 0, -1)[e["flu_times"]] for s in td.INFLUENZA_STATES], axis=1)  # [T, 28, n]
+    mine = np.moveaxis(mine, 0, 1)                                      # [28, T, n]
+    ref = np.transpose(e["flu_ens"], (1, 2, 0))
+    cases.assert_ks_ok(cases.ks_pvalues(mine, ref), "generated influenza vs reference ensemble")
+    tot = sum(out[s].values.astype(np.int64) for s in ("S", "E", "Ip", "Iud", "Id", "R"))
+    assert (tot == tot[:, :1, :]).all() and min(out[s].values.min() for s in td.INFLUENZA_STATES) >= 0
+    # and it is the same law as the hand-written functor: first two moments at 4e4 draws
+    from pysodm_b200 import tutorial_models as tm
+    hand = tm.JumpProcess_influenza_model(td.INFLUENZA_INITIAL_STATES, td.INFLUENZA_PARAMETERS,
+                                          coordinates={"age_group": td.AGE_GROUPS},
+                                          time_dependent_parameters={"N": td.influenza_contact_function})
+    ref2 = hand.sim([td.INFLUENZA_START, td.INFLUENZA_END], N=n, tau=0.5, seed=4, output_dtype="int32")
+    a, b = out["Im_inc"].values.astype(np.float64), ref2["Im_inc"].values.astype(np.float64)
+    se = np.sqrt((a.var(axis=0) + b.var(axis=0)) / n) + 1e-9
+    assert np.all(np.abs(a.mean(axis=0) - b.mean(axis=0)) < 5.5 * se)
+
+
+def test_generated_sir_si_tau_leap_and_ssa(golden):
+    e, g = golden["jump_ensemble"], golden["ssa"]
+    model = gm.make_sirsi()
+    out = model.sim(120, N=20000, tau=0.5, seed=5, output_dtype="int32")
+    flat = np.concatenate([np.moveaxis(out[s].values.reshape(20000, 121, -1), 0, -1) for s in model.states_names], axis=1)
+    mine = np.moveaxis(flat[e["sirsi_times"]], 0, 1)                    # [14, T, n]
+    cases.assert_ks_ok(cases.ks_pvalues(mine, np.transpose(e["sirsi_ens"], (1, 2, 0))), "generated SIR_SI vs reference")
+    # SSA on the down-scaled populations the reference fixture was made with
+    small = gm.GenSirSi({"S": g["sirsi_small_y0"][0:4], "I": g["sirsi_small_y0"][4:8], "R": g["sirsi_small_y0"][8:12],
+                         "S_v": g["sirsi_small_y0"][12], "I_v": g["sirsi_small_y0"][13]}, dict(gm.SIRSI_PARAMS),
+                        coordinates={"age_group": ["a", "b", "c", "d"]})
+    assert small.device_model is model.device_model                     # same functions, same shapes: one plugin
+    ssa = small.sim(30, N=10000, method="SSA", seed=6)
+    flat = np.concatenate([np.moveaxis(ssa[s].values.reshape(10000, 31, -1), 0, -1) for s in small.states_names], axis=1)
+    times = [1, 3, 7, 15, 30]
+    ref = np.transpose(g["sirsi_small_ens"], (1, 2, 0)).astype(np.float64)
+    cases.assert_ks_ok(cases.ks_pvalues(np.moveaxis(flat[times], 0, 1), ref[:, times, :]), "generated SIR_SI SSA vs reference")
+
+
+class _SeirdOracle(omodels.JumpModelSpec):
+    """The SEIRD test model in the oracle's batched form (same functions, leading batch axis)."""
+    name = "seird"
+    states = tuple((s, (3,)) for s in gm.SEIRD.states)
+    params = tuple((p, np.shape(gm.SEIRD_PARAMS[p])) for p in ['beta', 'sigma', 'gamma', 'mu', 'eta', 'rho', 'M', 'h'])
+    transitions = (("S", 1), ("E", 1), ("I", 3), ("H", 1))
+
+    @staticmethod
+    def rates(t, y, p):
+        N = y["S"] + y["E"] + y["I"] + y["H"] + y["R"]
+        foi = p["beta"] * np.einsum("ab,...b->...a", p["M"], y["I"] / N)
+        one = np.ones(y["S"].shape)
+        return {"S": [foi], "E": [p["sigma"] * one], "I": [p["gamma"] * (1 - p["h"]) * one, p["mu"] * one, p["eta"] * p["h"] * one],
+                "H": [p["rho"] * one]}
+
+    @staticmethod
+    def apply(t, tau, T, y, p):
+        return {"S": y["S"] - T["S"][0], "E": y["E"] + T["S"][0] - T["E"][0],
+                "I": y["I"] + T["E"][0] - T["I"][0] - T["I"][1] - T["I"][2], "H": y["H"] + T["I"][2] - T["H"][0],
+                "R": y["R"] + T["I"][0] + T["H"][0], "D": y["D"] + T["I"][1], "cases": y["cases"] + T["E"][0]}
+
+
+def test_new_model_with_three_exits_matches_oracle():
+    model = gm.make_seird()
+    n = 16000
+    out = model.sim(60, N=n, tau=0.5, seed=7, output_dtype="int32")
+    y0 = np.concatenate([np.ravel(np.asarray(model.initial_states[k], dtype=np.float64)) for k in model.states_names])
+    ref = ojump.tau_leap_ensemble(_SeirdOracle, y0, gm.SEIRD_PARAMS, 0, 60, 0.5, n, seed=13)      # [n, 21, 61]
+    times = [1, 5, 15, 30, 60]
+    mine = np.concatenate([np.moveaxis(out[s].values, 0, -1) for s in model.states_names], axis=1)      # [61, 21, n]
+    cases.assert_ks_ok(cases.ks_pvalues(np.moveaxis(mine[times], 0, 1), np.transpose(ref[:, :, times], (1, 2, 0))),
+                       "generated SEIRD vs oracle")
+    pop = sum(out[s].values.astype(np.int64) for s in ("S", "E", "I", "H", "R", "D"))
+    assert (pop == pop[:, :1, :]).all()
+    assert (np.diff(out["cases"].values, axis=1) >= 0).all() and (np.diff(out["D"].values, axis=1) >= 0).all()
+    # without the reference's stay-probability quirk the three-exit compartment follows a visibly different law
+    plain = model.sim(60, N=n, tau=0.5, seed=7, output_dtype="int32", compat=0)
+    ps = cases.ks_pvalues(np.moveaxis(plain["D"].values, 0, -1)[[30, 60]], np.transpose(ref[:, 15:18, :][:, :, [30, 60]], (2, 1, 0)))
+    assert (ps < 0.01).mean() > 0.5
+
+
+def test_generated_odes_follow_the_hand_written_functors(golden):
+    from pysodm_b200 import engine, tutorial_data as td, tutorial_models as tm
+    # SIR_SI ODE: generated vs hand-written, same step sequence
+    gen = gm.make_sirsi(gm.GenOdeSirSi)
+    hand = gm.make_sirsi(tm.ODE_SIR_SI)
+    a, b = gen.sim(120), hand.sim(120)
+    for s in gen.states_names:
+        np.testing.assert_allclose(a[s].values, b[s].values, rtol=1e-9, atol=1e-9)
+    assert np.array_equal(gen.last_nfev.cpu().numpy(), hand.last_nfev.cpu().numpy())
+    # tutorial SIR against the reference's scipy RK45 fixture (rtol 1e-6, same number of function evaluations)
+    g = golden["ode"]
+    model = gm.GenOdeSir({"S": 1000, "I": 1}, {"beta": 0.35, "gamma": 5})
+    betas = g["sir_betas"]
+
+    def draw(parameters, N):
+        parameters["beta"] = betas
+        return parameters
+    draw.vectorized = True
+    out = model.sim(120, N=100, draw_function=draw)
+    y = np.stack([out[s].values for s in ("S", "I", "R")], axis=1)
+    np.testing.assert_allclose(y, g["sir_y"], rtol=1e-6, atol=1e-9)
+    assert np.array_equal(model.last_nfev.cpu().numpy(), g["sir_nfev"])
+    # packed-bed reactor written with NumPy slicing: generated thread-per-draw kernel vs the warp-per-draw functor
+    nx = 6
+    gp, hp = gm.make_pfr(nx), gm.make_pfr(nx, tm.packed_PFR)
+    ga, ha = gp.sim(600, output_stride=100), hp.sim(600, output_stride=100)
+    for s in ("C_F", "C_S"):
+        np.testing.assert_allclose(ga[s].values, ha[s].values, rtol=1e-8, atol=1e-12)
+    assert np.array_equal(gp.last_nfev.cpu().numpy(), hp.last_nfev.cpu().numpy())
+    # a model that exists nowhere else: against scipy on the host (the reference's own solver call, base.py:855)
+    lv = gm.make_lotka()
+    res = lv.sim(40, rtol=1e-8, atol=1e-10)
+    from scipy.integrate import solve_ivp
+
+    def rhs(t, y):
+        d = gm.LotkaVolterra.integrate(t, y[:5], y[5:], **lv.parameters)
+        return np.concatenate(d)
+    y0 = np.concatenate([lv.initial_states["prey"], lv.initial_states["pred"]])
+    ref = solve_ivp(rhs, [0, 40], y0, t_eval=np.arange(41), rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(np.concatenate([res["prey"].values, res["pred"].values], axis=1).T, ref.y, rtol=1e-6)
+    # Euler with a fixed step too
+    eu = lv.sim(10, tau=0.125)
+    assert np.isfinite(eu["prey"].values).all()
