@@ -10,7 +10,10 @@ The class API mirrors `/root/reference/src/pySODM/models/base.py`: class attribu
 (`sodm_jump_run` / `sodm_ode_run`), chunked through a double-buffered host pipeline (pipeline.py).
 
 A model class is bound to a hand-written `__device__` functor by `device_model = "<registered name>"`.  A class
-without a functor cannot be simulated: there is deliberately no CPU fallback.
+that declares none is TRANSLATED: its own Python functions (`integrate`, or `compute_rates` + `apply_transitionings`) are
+traced into straight-line C++ (codegen.py), compiled by nvcc into a plugin library (plugin.py, include/sodm_plugin.h)
+and driven by the same kernels.  A function that cannot be translated (value-dependent control flow, non-integral
+bookkeeping) raises at construction: there is deliberately no CPU fallback.
 
 Extensions over the reference signature (keyword-only, defaults = reference behaviour): `output_dtype`
 ('float64' like the reference; 'int32'/'float32' halve the 18-36 GB of config C3), `states` (subset of states to
@@ -291,8 +294,8 @@ class JumpProcess(_DeviceBackedModel):
 
     Subclasses declare `states`, `parameters`, optional `stratified_parameters` / `dimensions` /
     `dimensions_per_state`, the static methods `compute_rates(t, *states, *parameters)` and
-    `apply_transitionings(t, tau, transitionings, *states, *parameters)` (kept for documentation, validation and
-    the CPU oracle), and `device_model`, the registered functor that restates them on the device."""
+    `apply_transitionings(t, tau, transitionings, *states, *parameters)`, and optionally `device_model`, a registered
+    hand-written functor that restates them on the device; without it the two functions are translated (codegen.py)."""
     _kind = "jump"
     _rhs_name = "compute_rates"
 
@@ -438,8 +441,8 @@ class JumpProcess(_DeviceBackedModel):
 class ODE(_DeviceBackedModel):
     """Deterministic model integrated on the GPU: scipy-faithful RK45, or fixed-step Euler / RK4 when `tau` is given.
 
-    Subclasses declare `states`, `parameters`, ..., the static method `integrate(t, *states, *parameters)` (kept for
-    documentation, validation and the CPU oracle) and `device_model`."""
+    Subclasses declare `states`, `parameters`, ..., the static method `integrate(t, *states, *parameters)` and
+    optionally `device_model` (a registered hand-written functor); without it `integrate` is translated (codegen.py)."""
     _kind = "ode"
     _rhs_name = "integrate"
 

@@ -60,8 +60,8 @@ SPECS = {s.name: s for s in [
 def get(name):
     if name not in SPECS:
         raise NotImplementedError(
-            f"no device functor registered under '{name}'. pysodm_b200 runs hand-written __device__ functors only "
-            f"(registered: {sorted(SPECS)}); there is no CPU fallback for arbitrary Python models.")
+            f"no device functor registered under '{name}' (registered: {sorted(SPECS)}).  Leave `device_model` unset to "
+            "have the model's own Python functions translated instead (codegen.py); there is no CPU fallback.")
     return SPECS[name]
 
 

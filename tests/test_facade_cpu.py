@@ -31,15 +31,25 @@ def test_simulation_time_forms():
 
 
 def test_model_declaration_errors():
-    class NoFunctor(ODE):
+    class NoFunctor(ODE):                        # no hand-written functor: translated from its Python function
         states = ["A"]
         parameters = ["k"]
 
         @staticmethod
         def integrate(t, A, k):
             return -k * A,
-    with pytest.raises(NotImplementedError, match="no CPU fallback"):
-        NoFunctor({"A": 1.0}, {"k": 0.1})
+    from pysodm_b200 import plugin
+    assert isinstance(NoFunctor({"A": 1.0}, {"k": 0.1}).device_model, plugin.Plugin)
+
+    class Untranslatable(ODE):                   # value-dependent control flow cannot be traced: fails loudly, no fallback
+        states = ["A"]
+        parameters = ["k"]
+
+        @staticmethod
+        def integrate(t, A, k):
+            return (-k * A if A > 0 else 0.0),
+    with pytest.raises(NotImplementedError, match="cannot\\s+follow Python control flow"):
+        Untranslatable({"A": 1.0}, {"k": 0.1})
     with pytest.raises(ValueError, match="Missing parameters"):
         tm.ODE_SIR({"S": 1000, "I": 1}, {"beta": 0.35})
     with pytest.raises(ValueError, match="Redundant parameters"):

@@ -103,6 +103,31 @@ def main():
                                         ll_arg=4 * [0.03], lp=lp, dev=dev))
     res["C5_loglik_kernel_only"] = {"n_particles": n, "ms": ms_ll, "GBps_read": 52 * 4 * n / ms_ll / 1e6}
 
+    # Generated models (codegen.py -> plugin library) against the hand-written functors of the same model
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    import gen_models as gm
+    n = 1 << 20
+    flu = gm.make_influenza().device_model
+    full_idx = torch.from_numpy(td.influenza_schedule()).to(dev)
+    out = torch.empty((28, 162, n), dtype=torch.int32, device=dev)
+    for label, model in (("hand_written", "influenza_1718_jump"), ("generated", flu)):
+        ms = timed(lambda: engine.jump_run(model, y0f, td.influenza_flat_par(), n, 0, 162, 0.5, tdpf=(tab, full_idx), seed=1,
+                                           out_dtype=torch.int32, out=out, dev=dev))
+        res[f"C3_influenza_tau_leap_{label}"] = {"n_traj": n, "ms": ms, "traj_per_s": n / ms * 1e3}
+    del out
+    n = 1_000_000
+    sirsi = gm.make_sirsi().device_model
+    par_gen = np.concatenate([[7.0, 5.0], [0.05, 0.1, 0.2, 0.15]])            # generated flat order: beta, gamma, alpha[4]
+    out = torch.empty((14, 121, n), dtype=torch.int32, device=dev)
+    ms = timed(lambda: engine.jump_run(sirsi, y0, par_gen, n, 0, 121, 0.5, seed=1, out_dtype=torch.int32, out=out, dev=dev))
+    res["C2_sir_si_tau_leap_generated"] = {"n_traj": n, "ms": ms, "traj_per_s": n / ms * 1e3}
+    del out
+    n = 100_000
+    sir = gm.GenOdeSir({"S": 1000, "I": 1}, {"beta": 0.35, "gamma": 5}).device_model
+    out = torch.empty((3, 121, n), dtype=torch.float64, device=dev)
+    ms = timed(lambda: engine.ode_run(sir, [1000, 1, 0], [0.35, 5], n, 0, 121, var=([0], betas[None, :]), out=out, dev=dev))
+    res["C1_sir_ode_rk45_generated"] = {"n_traj": n, "ms": ms, "traj_per_s": n / ms * 1e3}
+
     text = json.dumps(res, indent=1)
     print(text)
     if len(sys.argv) > 1:
