@@ -132,7 +132,14 @@ class _DeviceBackedModel:
 
     # ---------------------------------------------------------------------------------------------------------
     def _bind_device_functor(self):
+        self._generated, self._generated_cache, self._date_params, self._time_unit_us = False, {}, [], None
+        if self._kind == "ode" and self.time_dependent_parameters:
+            # time-dependent parameter functions of an ODE run at every Runge-Kutta stage time (base.py:769-779): they are
+            # translated together with `integrate`; whether they see numbers or dates is known at sim() -> built there
+            self._generated, self.device_model = True, None
+            return None
         if not self.device_model:
+            self._generated = True
             return self._bind_generated_functor()
         spec = registry.get(self.device_model)
         if spec.kind != self._kind:
@@ -152,41 +159,102 @@ class _DeviceBackedModel:
                 raise NotImplementedError(f"device functor '{spec.name}' has no time-dependent slot for parameter "
                                           f"'{name}' (supported: {list(spec.tdpf_params)})")
 
-    def _bind_generated_functor(self):
-        """No hand-written functor declared: translate the class's own Python functions (codegen.py) and compile them
-        into a plugin library (plugin.py).  Flat parameter order: declaration order, time-dependent parameters last."""
+    def _bind_generated_functor(self, date_unit_us=None, date_range=None):
+        """No hand-written functor (or an ODE with time-dependent parameter functions): translate the class's own Python
+        functions (codegen.py) and compile them into a plugin library (plugin.py).  Flat parameter order: declaration
+        order, then parameters only the TDPFs use; a jump process's time-dependent parameters go last (they are read from
+        the per-step table); in date mode one hidden element `__t0__` (absolute time of t = 0) closes the vector.
+        date_unit_us: None = model functions receive numbers for `t`; else they receive dates (sim was given dates)."""
         from . import plugin
-        tdpf = [n for n in self.parameters_names_modeldeclaration if n in (self.time_dependent_parameters or {})]
-        order = [n for n in self.parameters_names_modeldeclaration if n not in tdpf] + tdpf
-        shapes = OrderedDict()
-        for name in order:
-            value = self.parameters[name]
-            if callable(value) or isinstance(value, (str, dict)):
-                raise NotImplementedError(f"parameter '{name}' is not numeric; generated device models take scalars and arrays")
-            shapes[name] = tuple(np.shape(np.asarray(value, dtype=np.float64)))
-        state_shapes = OrderedDict((k, tuple(self.state_shapes[k])) for k in self.states_names)
-        origin = f" of {type(self).__module__}.{type(self).__qualname__}"
-        if self._kind == "ode":
-            if tdpf:
-                raise NotImplementedError("time-dependent parameter functions are not yet available for device ODE models")
-            plug = plugin.build_ode(self.integrate, state_shapes, shapes, self.initial_states, self.parameters, origin)
+        key = date_unit_us
+        if key in self._generated_cache:
+            plug, spec, shapes, self._date_params = self._generated_cache[key]
         else:
-            plug = plugin.build_jump(self.compute_rates, self.apply_transitionings, state_shapes, shapes, tdpf,
-                                     self.initial_states, self.parameters, origin)
-        spec = registry.DeviceSpec(plug.name, self._kind, list(state_shapes.items()), list(shapes.items()), tdpf_params=tdpf)
+            tdpfs = self.time_dependent_parameters or {}
+            decl = list(self.parameters_names_modeldeclaration)
+            if self._kind == "ode":
+                tab = []
+                order = decl + [n for n in self._extra_params_TDPF if n not in decl]
+            else:
+                tab = [n for n in decl if n in tdpfs]
+                order = [n for n in decl if n not in tab] + tab
+            shapes, date_params = OrderedDict(), []
+            for name in order:
+                value = self.parameters[name]
+                if plugin.codegen._is_datelike(value):
+                    if date_unit_us is None:
+                        raise NotImplementedError(f"parameter '{name}' is a date; simulate over dates (time=[start, stop])")
+                    shapes[name] = ()
+                    date_params.append(name)
+                    continue
+                if callable(value) or isinstance(value, (str, dict)):
+                    raise NotImplementedError(f"parameter '{name}' is not numeric; generated device models take scalars, arrays and dates")
+                shapes[name] = tuple(np.shape(np.asarray(value, dtype=np.float64)))
+            if date_unit_us is not None and self._kind == "ode":
+                shapes["__t0__"] = ()
+            self._date_params = date_params
+            state_shapes = OrderedDict((k, tuple(self.state_shapes[k])) for k in self.states_names)
+            origin = f" of {type(self).__module__}.{type(self).__qualname__}"
+            if self._kind == "ode":
+                spec_t = [(name, fn, self._function_parameters[i]) for i, (name, fn) in enumerate(tdpfs.items())]
+                plug = plugin.build_ode(self.integrate, state_shapes, shapes, origin,
+                                        reference=self._reference_rhs(date_range, date_unit_us), example_states=self.initial_states,
+                                        example_params=self._example_flat(shapes, date_unit_us, date_range),
+                                        tdpf=spec_t, model_params=decl, date_unit_us=date_unit_us, date_params=date_params)
+            else:
+                plug = plugin.build_jump(self.compute_rates, self.apply_transitionings, state_shapes, shapes, tab,
+                                         self.initial_states, self.parameters, origin)
+            spec = registry.DeviceSpec(plug.name, self._kind, list(state_shapes.items()), list(shapes.items()), tdpf_params=tab)
+            self._generated_cache[key] = (plug, spec, shapes, date_params)
         self.device_model = plug
         self._model_arg = 0
         self._spec, self._spec_params = spec, shapes
         self._param_offsets, self._n_param_flat = spec.param_offsets(0)
+        self._time_unit_us = date_unit_us
         if self._n_param_flat > _ffi.MAX_PARAM or plug.info.n_state > _ffi.MAX_STATE and self._kind == "jump":
             raise NotImplementedError(f"generated models are limited to {_ffi.MAX_PARAM} flat parameter elements and "
                                       f"{_ffi.MAX_STATE} flat state elements per launch block")
+
+    def _example_flat(self, shapes, date_unit_us, date_range):
+        """Flat parameter vector of the model's current parameters (for the build-time self-check of a generated ODE)."""
+        from .codegen import date_to_units
+        parts = []
+        for name, shape in shapes.items():
+            if name == "__t0__":
+                parts.append(np.array([date_to_units(date_range[0], date_unit_us)]))
+            elif name in self._date_params:
+                parts.append(np.array([date_to_units(self.parameters[name], date_unit_us)]))
+            else:
+                parts.append(np.ravel(np.asarray(self.parameters[name], dtype=np.float64)))
+        return np.concatenate(parts) if parts else np.zeros(0)
+
+    def _reference_rhs(self, date_range, date_unit_us):
+        """The right-hand side as the reference's `func` evaluates it (base.py:746-796), on NumPy values: TDPFs with the
+        original parameter values, TDPF-only parameters dropped, then `integrate` -- used ONCE per build to check the
+        translation, never to simulate."""
+        tdpfs = self.time_dependent_parameters or {}
+        decl = list(self.parameters_names_modeldeclaration)
+
+        def rhs(t):
+            when = t
+            if date_unit_us is not None:
+                when = validation.time_to_date(float(t), date_range[0], {v: k for k, v in validation.TIME_UNIT_US.items()}[int(date_unit_us)])
+            states = {k: np.asarray(v, dtype=np.float64) for k, v in self.initial_states.items()}
+            pars = dict(self.parameters)
+            params = dict(pars)
+            for i, (name, fn) in enumerate(tdpfs.items()):
+                params[name] = fn(when, states, pars[name], **{k: pars[k] for k in self._function_parameters[i]})
+            return self.integrate(when, **states, **{k: params[k] for k in decl})
+        return rhs
 
     def _flat_y0(self, initial_states):
         return np.concatenate([np.ravel(np.asarray(v, dtype=np.float64)) for v in initial_states.values()])
 
     def _flat_param(self, name, value):
         off, n, shape = self._param_offsets[name]
+        if name in self._date_params:                           # a date: absolute time in simulation units
+            from .codegen import date_to_units
+            return np.array([date_to_units(value, self._time_unit_us)])
         arr = np.asarray(value, dtype=np.float64)
         if arr.shape != tuple(shape) and not (arr.size == 1 and not shape):
             raise ValueError(f"parameter '{name}' must have shape {tuple(shape)}, found {arr.shape}")
@@ -197,9 +265,10 @@ class _DeviceBackedModel:
         into the shared flat parameter vector, the per-trajectory rows, and the (possibly per-trajectory) y0."""
         base = self.parameters
         par = np.zeros(self._n_param_flat)
+        tabulated = set(self._spec.tdpf_params)                # read from the per-step table (jump processes), not from `par`
         for name in self._spec_params:
-            if name in (self.time_dependent_parameters or {}):
-                continue                                   # comes from the TDPF table
+            if name in tabulated or name == "__t0__":
+                continue
             par[self._param_offsets[name][0]:][:self._param_offsets[name][1]] = self._flat_param(name, base[name])
         y0 = self._flat_y0(self.initial_states)
         if not draw_function:
@@ -223,14 +292,17 @@ class _DeviceBackedModel:
                 except Exception:  # noqa: BLE001  (unhashable / exotic parameter types)
                     same = all(d[name] is first for d in dicts[1:])
                 if not same:
-                    stacked[name] = np.stack([np.asarray(d[name], dtype=np.float64) for d in dicts])
-                elif name in self._spec_params and name not in (self.time_dependent_parameters or {}):
+                    if name in self._date_params:
+                        stacked[name] = np.stack([self._flat_param(name, d[name]) for d in dicts])[:, 0]
+                    elif name in self._spec_params or name in self.initial_states_function_args:
+                        stacked[name] = np.stack([np.asarray(d[name], dtype=np.float64) for d in dicts])
+                elif name in self._spec_params and name not in tabulated:
                     par[self._param_offsets[name][0]:][:self._param_offsets[name][1]] = self._flat_param(name, first)
         var = {}
         for name, values in stacked.items():
-            if name in (self.time_dependent_parameters or {}) or name in self._extra_params_TDPF:
+            if name in tabulated or (tabulated and name in self._extra_params_TDPF):
                 raise NotImplementedError(f"parameter '{name}' is drawn per trajectory AND feeds a time-dependent "
-                                          "parameter function; the device path tabulates TDPFs once per run")
+                                          "parameter function; the device path tabulates a jump process's TDPFs once per run")
             if name in self._spec_params:
                 off, n, shape = self._param_offsets[name]
                 flat = np.asarray(values, dtype=np.float64).reshape(N, n)
@@ -462,8 +534,10 @@ class ODE(_DeviceBackedModel):
                                      self.initial_states_function, self.state_shapes, self.initial_states_function_args)
         if N != 1 and draw_function is None:
             raise ValueError(f"attempting to perform N={N} repeated simulations without using a draw function")
-        if self.time_dependent_parameters:
-            raise NotImplementedError("time-dependent parameter functions are not yet available for device ODE models")
+        if self._generated and self.time_dependent_parameters:
+            # model functions see dates when sim is given dates, numbers otherwise (base.py:759-764): one translation each
+            unit_us = validation.TIME_UNIT_US[time_unit] if date_range[0] is not None else None
+            self._bind_generated_functor(unit_us, date_range)
         if tau:
             dev_method = "RK4" if method == "RK4" else "euler"
         elif method == "RK45":
@@ -474,6 +548,9 @@ class ODE(_DeviceBackedModel):
         saved = copy.deepcopy(self.parameters)
         try:
             par, var, y0, _ = self._collect_draws(N, draw_function, draw_function_kwargs)
+            if "__t0__" in self._param_offsets:                 # absolute time of t = 0, for date-valued model logic
+                from .codegen import date_to_units
+                par[self._param_offsets["__t0__"][0]] = date_to_units(date_range[0], self._time_unit_us)
             t0, t1 = time
             n_out = int(t1 - t0 + 1)
             dev = engine.device(device)

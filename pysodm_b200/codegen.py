@@ -41,6 +41,24 @@ class Graph:
     def __init__(self):
         self.nodes = []          # (op, args, kind) ; args = node ids, or payload for leaves
         self.index = {}
+        self.forced, self.path = [], []          # branch exploration (see `explore`)
+        self.unit_us = None                      # microseconds per simulation time unit when model functions see dates
+
+    def decide(self, cond):
+        """Truth value of a symbolic condition on the CURRENT exploration path: replay the forced prefix, then take the
+        `True` side of every new condition (the driver comes back for the other side)."""
+        for c, v in self.path:
+            if c == cond.i:
+                return v                                         # the same condition again: same answer
+        k = len(self.path)
+        if k < len(self.forced):
+            if self.forced[k][0] != cond.i:
+                raise TraceError("the model function is not deterministic under re-execution (branch order changed)")
+            val = self.forced[k][1]
+        else:
+            val = True
+        self.path.append((cond.i, val))
+        return val
 
     def node(self, op, args, kind):
         key = (op, args)
@@ -144,15 +162,50 @@ class Sym:
         return self.g.node(op, (self.i,), "f")
 
     def _refuse(self, what):
-        raise TraceError(f"{what} on a model value: the device translation records straight-line arithmetic and cannot "
-                         "follow Python control flow that depends on states, parameters or time")
+        raise TraceError(f"{what} on a model value cannot be translated: the device code is straight-line arithmetic plus "
+                         "selections on comparisons (`if a < b`), a model value cannot become a Python number")
 
-    def __bool__(self): self._refuse("truth test (if / while / and / or / np.where)")
+    def __bool__(self):
+        n = self.g.nodes[self.i]
+        if n[0] == "const":
+            return bool(n[1][0])
+        if n[2] != "b":
+            self._refuse("truth test of a number")
+        return self.g.decide(self)
+
     def __float__(self): self._refuse("float() (e.g. storing a model value into a float64 array made outside the function)")
     def __int__(self): self._refuse("int()")
     def __index__(self): self._refuse("use as an index")
-    def __lt__(self, o): self._refuse("comparison")
-    __le__ = __gt__ = __ge__ = __lt__
+
+    def _compare(self, op, other):
+        o = self._lift(other)
+        if o is None:
+            if _is_datelike(other) or _is_deltalike(other):
+                raise TraceError("a number is compared with a date: the model's functions use dates, so simulate over "
+                                 "dates (time=['yyyy-mm-dd', 'yyyy-mm-dd'])")
+            return NotImplemented
+        a, b = self.g.nodes[self.i], self.g.nodes[o.i]
+        if a[0] == "const" and b[0] == "const":
+            x, y = a[1][0], b[1][0]
+            return self.g.const(int({"lt": x < y, "le": x <= y, "gt": x > y, "ge": x >= y}[op]))
+        return self.g.node(op, (self.i, o.i), "b")
+
+    def __lt__(self, o): return self._compare("lt", o)
+    def __le__(self, o): return self._compare("le", o)
+    def __gt__(self, o): return self._compare("gt", o)
+    def __ge__(self, o): return self._compare("ge", o)
+
+    def _logic(self, op, other):
+        o = self._lift(other)
+        if o is None:
+            return NotImplemented
+        return self.g.node(op, (self.i, o.i), "b")
+
+    def __and__(self, o): return self._logic("and", o)
+    def __rand__(self, o): return self._logic("and", o)
+    def __or__(self, o): return self._logic("or", o)
+    def __ror__(self, o): return self._logic("or", o)
+    def __invert__(self): return self.g.node("not", (self.i,), "b")
 
     def __eq__(self, o):
         return isinstance(o, Sym) and o.g is self.g and o.i == self.i
@@ -188,6 +241,162 @@ class Sym:
 for _name in _UNARY:                       # np.exp(object array) calls element.exp()
     setattr(Sym, _name, (lambda op: lambda self: self._unary(op))(_name))
 Sym.conjugate = lambda self: self          # np.conj / some reductions on object arrays
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# dates: what the reference hands to model functions when `sim` is given dates (base.py:759-764: `date = time_to_date(t)`)
+# ---------------------------------------------------------------------------------------------------------------------
+_EPOCH = np.datetime64("1970-01-01T00:00:00", "us")
+
+
+def date_to_units(value, unit_us):
+    """A datetime-like as ABSOLUTE time in simulation time units (time units since 1970-01-01)."""
+    d = np.datetime64(value, "us") if not hasattr(value, "to_datetime64") else value.to_datetime64().astype("datetime64[us]")
+    return float((d - _EPOCH) / np.timedelta64(1, "us")) / unit_us
+
+
+def _is_datelike(x):
+    return hasattr(x, "to_datetime64") or isinstance(x, np.datetime64) or type(x).__name__ in ("datetime", "date")
+
+
+def _is_deltalike(x):
+    return hasattr(x, "to_timedelta64") or isinstance(x, np.timedelta64) or type(x).__name__ == "timedelta"
+
+
+def _delta_to_units(value, unit_us):
+    d = value.to_timedelta64() if hasattr(value, "to_timedelta64") else np.timedelta64(value, "us") if not isinstance(value, np.timedelta64) else value
+    return float(d / np.timedelta64(1, "us")) / unit_us
+
+
+class SymDate:
+    """A symbolic datetime: `abs` = a Sym holding absolute time in simulation units.  Supports what time-dependent
+    parameter functions do with dates: ordering against datetimes / date-valued parameters, +- timedeltas, differences."""
+
+    def __init__(self, abs_sym, unit_us):
+        self.abs, self.unit_us = abs_sym, unit_us
+
+    def _other(self, o):
+        if isinstance(o, SymDate):
+            return o.abs
+        if _is_datelike(o) or isinstance(o, str):
+            return date_to_units(o, self.unit_us)
+        raise TraceError(f"cannot compare the simulation date with {type(o).__name__}")
+
+    def __lt__(self, o): return self.abs < self._other(o)
+    def __le__(self, o): return self.abs <= self._other(o)
+    def __gt__(self, o): return self.abs > self._other(o)
+    def __ge__(self, o): return self.abs >= self._other(o)
+
+    def __add__(self, o):
+        if isinstance(o, SymDelta):
+            return SymDate(self.abs + o.units, self.unit_us)
+        if _is_deltalike(o):
+            return SymDate(self.abs + _delta_to_units(o, self.unit_us), self.unit_us)
+        return NotImplemented
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        if isinstance(o, SymDelta):
+            return SymDate(self.abs - o.units, self.unit_us)
+        if _is_deltalike(o):
+            return SymDate(self.abs - _delta_to_units(o, self.unit_us), self.unit_us)
+        return SymDelta(self.abs - self._other(o), self.unit_us)
+
+    def __rsub__(self, o):
+        return SymDelta(self._other(o) - self.abs, self.unit_us)
+
+    def __getattr__(self, name):
+        raise TraceError(f"`.{name}` of the simulation date cannot be translated (calendar logic such as weekdays belongs in "
+                         "a tabulated time-dependent parameter of a jump process, or must be expressed through date comparisons)")
+
+
+class SymDelta:
+    """Difference of two symbolic dates; `units` = a Sym in simulation time units."""
+
+    def __init__(self, units, unit_us):
+        self.units, self.unit_us = units, unit_us
+
+    @property
+    def days(self):
+        return (self.units * (self.unit_us / 86400e6)).floor() if isinstance(self.units, Sym) else np.floor(self.units * self.unit_us / 86400e6)
+
+    def total_seconds(self):
+        return self.units * (self.unit_us / 1e6)
+
+    def __truediv__(self, o):
+        if _is_deltalike(o):
+            return self.units / _delta_to_units(o, self.unit_us)
+        if isinstance(o, SymDelta):
+            return self.units / o.units
+        return SymDelta(self.units / o, self.unit_us)
+
+    def __mul__(self, o): return SymDelta(self.units * o, self.unit_us)
+    __rmul__ = __mul__
+
+    def __add__(self, o):
+        if isinstance(o, SymDelta):
+            return SymDelta(self.units + o.units, self.unit_us)
+        if isinstance(o, SymDate):
+            return SymDate(o.abs + self.units, self.unit_us)
+        if _is_deltalike(o):
+            return SymDelta(self.units + _delta_to_units(o, self.unit_us), self.unit_us)
+        if _is_datelike(o):
+            return SymDate(date_to_units(o, self.unit_us) + self.units, self.unit_us)
+        return NotImplemented
+    __radd__ = __add__
+
+    def __rsub__(self, o):                                   # date - symbolic difference
+        if _is_datelike(o):
+            return SymDate(date_to_units(o, self.unit_us) - self.units, self.unit_us)
+        if _is_deltalike(o):
+            return SymDelta(_delta_to_units(o, self.unit_us) - self.units, self.unit_us)
+        return NotImplemented
+
+    def _other(self, o):
+        if isinstance(o, SymDelta):
+            return o.units
+        if _is_deltalike(o):
+            return _delta_to_units(o, self.unit_us)
+        raise TraceError(f"cannot compare a time difference with {type(o).__name__}")
+
+    def __lt__(self, o): return self.units < self._other(o)
+    def __le__(self, o): return self.units <= self._other(o)
+    def __gt__(self, o): return self.units > self._other(o)
+    def __ge__(self, o): return self.units >= self._other(o)
+
+
+_US_PER = {"weeks": 7 * 86400e6, "days": 86400e6, "hours": 3600e6, "minutes": 60e6, "seconds": 1e6, "milliseconds": 1e3,
+           "microseconds": 1.0, "W": 7 * 86400e6, "D": 86400e6, "d": 86400e6, "h": 3600e6, "min": 60e6, "s": 1e6, "ms": 1e3, "us": 1.0}
+
+
+class _PandasProxy:
+    """`pd` as seen by a traced function: conversions to datetime pass symbolic dates through, a Timedelta of a model
+    value (`pd.Timedelta(days=ramp_length)`) becomes a symbolic difference."""
+
+    def __init__(self, real, graph):
+        self._real, self._g = real, graph
+
+    def Timedelta(self, value=None, unit=None, **kw):
+        parts = list(kw.items()) + ([(unit or "ns", value)] if value is not None else [])
+        if not any(isinstance(v, Sym) for _, v in parts):
+            return self._real.Timedelta(value, unit, **kw) if value is not None else self._real.Timedelta(**kw)
+        if self._g.unit_us is None:
+            raise TraceError("pd.Timedelta of a model value needs a simulation over dates")
+        total = 0.0
+        for name, v in parts:
+            if name not in _US_PER:
+                raise TraceError(f"pd.Timedelta unit '{name}' is not supported in translated model functions")
+            total = total + v * (_US_PER[name] / self._g.unit_us)
+        return SymDelta(total, self._g.unit_us)
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    def to_datetime(self, x, *a, **k):
+        return x if isinstance(x, SymDate) else self._real.to_datetime(x, *a, **k)
+
+    def Timestamp(self, x, *a, **k):
+        return x if isinstance(x, SymDate) else self._real.Timestamp(x, *a, **k)
 
 
 def _sym_array(g, prefix, shape, kind, start):
@@ -227,9 +436,15 @@ class _NumpyProxy:
 
     def where(self, *args, **kw):
         cond = np.asarray(args[0])
-        if cond.dtype == object:
-            raise TraceError("np.where on a model value cannot be translated (value-dependent selection)")
-        return np.where(*args, **kw)
+        if cond.dtype != object or len(args) != 3:
+            return np.where(*args, **kw)
+        a, b = np.asarray(args[1], dtype=object), np.asarray(args[2], dtype=object)
+        shape = np.broadcast(cond, a, b).shape
+        out = np.empty(shape, dtype=object)
+        cb, ab, bb = (np.broadcast_to(x, shape) for x in (cond, a, b))
+        for idx in np.ndindex(shape):
+            out[idx] = select(self._g, cb[idx], ab[idx], bb[idx])
+        return out if shape else out[()]
 
     def _select(self, op, a, b):
         a, b = np.asarray(a, dtype=object), np.asarray(b, dtype=object)
@@ -242,6 +457,55 @@ class _NumpyProxy:
 
     def maximum(self, a, b, **kw): return self._select("max", a, b)
     def minimum(self, a, b, **kw): return self._select("min", a, b)
+
+
+def select(g, cond, a, b):
+    """`a if cond else b` as a node (constant conditions fold)."""
+    a = a if isinstance(a, Sym) else g.const(a)
+    b = b if isinstance(b, Sym) else g.const(b)
+    if not isinstance(cond, Sym):
+        return a if cond else b
+    c = g.nodes[cond.i]
+    if c[0] == "const":
+        return a if c[1][0] else b
+    if a.i == b.i:
+        return a
+    return g.node("select", (cond.i, a.i, b.i), "i" if a.kind == b.kind == "i" else ("b" if a.kind == b.kind == "b" else "f"))
+
+
+MAX_PATHS = 256
+
+
+def explore(g, run):
+    """Execute `run()` (-> flat list of outputs) once per control-flow path of the model function and merge the results
+    into `select` nodes: an `if` on a comparison of model values is followed down BOTH sides (first the true side, then,
+    on re-execution with the decisions so far replayed, the false side), depth first."""
+    results, forced = [], []
+    while True:
+        g.forced, g.path = forced, []
+        outs = run()
+        results.append((list(g.path), [o if isinstance(o, Sym) else g.const(o) for o in outs]))
+        path = list(g.path)
+        while path and path[-1][1] is False:
+            path.pop()
+        if not path:
+            break
+        forced = path[:-1] + [(path[-1][0], False)]
+        if len(results) >= MAX_PATHS:
+            raise TraceError(f"more than {MAX_PATHS} control-flow paths through the model function")
+    g.forced, g.path = [], []
+
+    def merge(group, depth):
+        if len(group) == 1:
+            return group[0][1]
+        cond = Sym(g, group[0][0][depth][0])
+        yes = [r for r in group if r[0][depth][1]]
+        no = [r for r in group if not r[0][depth][1]]
+        a, b = merge(yes, depth + 1), merge(no, depth + 1)
+        if len(a) != len(b):
+            raise TraceError("the branches of the model function return results of different sizes")
+        return [select(g, cond, x, y) for x, y in zip(a, b)]
+    return merge(results, 0)
 
 
 def _python_function(fn):
@@ -260,6 +524,8 @@ def _retarget(fn, graph):
     for k, v in list(g.items()):
         if v is np:
             g[k] = proxy
+        elif isinstance(v, types.ModuleType) and v.__name__ == "pandas":
+            g[k] = _PandasProxy(v, graph)
         elif getattr(v, "py_func", None) is not None and isinstance(getattr(v, "py_func"), types.FunctionType):
             g[k] = _retarget(v, graph)                   # jitted helpers called from the model function
     new = types.FunctionType(fn.__code__, g, fn.__name__, fn.__defaults__, fn.__closure__)
@@ -299,16 +565,38 @@ def _inputs(graph, state_shapes, param_shapes, kind_y):
     return kw
 
 
-def trace_ode(integrate, state_shapes, param_shapes):
-    """-> (graph, [derivative expression per flat state element])."""
+def trace_ode(integrate, state_shapes, param_shapes, tdpf=(), model_params=None, date_unit_us=None, date_params=()):
+    """-> (graph, [derivative expression per flat state element]).
+
+    tdpf: [(parameter name, function(t, states, param, **extras), [extra argument names])] -- evaluated in front of
+    `integrate` at every call, with the ORIGINAL parameter values, exactly as the reference's `func` does (base.py:769-779);
+    `model_params`: the names `integrate` takes (parameters only the TDPFs use are dropped before the call, :781-785).
+    date_unit_us: None for numeric time; else model functions receive a symbolic DATE (`SymDate`) built from `t` plus the
+    LAST flat parameter (the absolute time of t = 0, filled in by `sim`), and `date_params` arrive as dates too."""
     g = Graph()
+    g.unit_us = date_unit_us
     fn = _retarget(integrate, g)
+    tdpf = [(name, _retarget(f, g), list(extra)) for name, f, extra in tdpf]
     t = g.leaf(("t", 0), "f")
-    res = fn(t, **_inputs(g, state_shapes, param_shapes, "f"))
-    if not isinstance(res, (tuple, list)):
-        res = (res,)
-    outs = _collect(res, state_shapes, "integrate")
-    return g, [o if isinstance(o, Sym) else g.const(o) for o in outs]
+    model_params = list(model_params) if model_params is not None else [k for k in param_shapes if k != "__t0__"]
+
+    def run():
+        kw = _inputs(g, state_shapes, param_shapes, "f")
+        states = {k: kw[k] for k in state_shapes}
+        pars = {k: kw[k] for k in param_shapes if k != "__t0__"}
+        when = t
+        if date_unit_us is not None:
+            when = SymDate(t + kw["__t0__"], date_unit_us)
+            for k in date_params:
+                pars[k] = SymDate(pars[k], date_unit_us)
+        params = dict(pars)
+        for name, f, extra in tdpf:
+            params[name] = f(when, states, pars[name], **{k: pars[k] for k in extra})
+        res = fn(when, **states, **{k: params[k] for k in model_params})
+        if not isinstance(res, (tuple, list)):
+            res = (res,)
+        return _collect(res, state_shapes, "integrate")
+    return g, explore(g, run)
 
 
 def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes):
@@ -320,25 +608,39 @@ def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes):
     fn = _retarget(compute_rates, g)
     t = g.leaf(("t", 0), "f")
 
-    rates = fn(t, **_inputs(g, state_shapes, param_shapes, "f"))
-    if not isinstance(rates, dict):
-        raise TraceError("compute_rates must return a dict {state: [rate arrays]}")
-    channels = {}                                    # state -> list over transitions of flat expression lists
-    for name, lst in rates.items():
-        if name not in state_shapes:
-            raise TraceError(f"compute_rates returned rates for '{name}', which is not a state")
+    structure = []                                   # [(state, number of transitions)] in rate-dict order
+
+    def run_rates():
+        rates = fn(t, **_inputs(g, state_shapes, param_shapes, "f"))
+        if not isinstance(rates, dict):
+            raise TraceError("compute_rates must return a dict {state: [rate arrays]}")
+        shape_now, flat = [], []
+        for name, lst in rates.items():
+            if name not in state_shapes:
+                raise TraceError(f"compute_rates returned rates for '{name}', which is not a state")
+            shape_now.append((name, len(lst)))
+            for r in lst:
+                a = np.asarray(r, dtype=object)
+                want = tuple(state_shapes[name])
+                if a.shape != want:
+                    # the reference holds dimensionless states as one-element arrays, so np.array([gamma]) is a valid rate
+                    # for a scalar state (src/tests/test_JumpProcess.py:19); anything else must broadcast to the state
+                    try:
+                        a = a.reshape(want) if a.size == max(1, int(np.prod(want))) else np.broadcast_to(a, want)
+                    except ValueError:
+                        raise TraceError(f"rate of '{name}' has shape {a.shape}, expected {want} (base.py:392-401)") from None
+                flat.extend(a.reshape(-1).tolist())
+        if structure and structure != shape_now:
+            raise TraceError("compute_rates returns different transitions on different branches")
+        structure[:] = shape_now
+        return flat
+    flat_rates = explore(g, run_rates)
+    channels, k = {}, 0                              # state -> list over transitions of flat expression lists
+    for name, m in structure:
         per = []
-        for r in lst:
-            a = np.asarray(r, dtype=object)
-            want = tuple(state_shapes[name])
-            if a.shape != want:
-                # the reference holds dimensionless states as one-element arrays, so np.array([gamma]) is a valid rate
-                # for a scalar state (src/tests/test_JumpProcess.py:19); anything else must broadcast to the state
-                try:
-                    a = a.reshape(want) if a.size == max(1, int(np.prod(want))) else np.broadcast_to(a, want)
-                except ValueError:
-                    raise TraceError(f"rate of '{name}' has shape {a.shape}, expected {want} (base.py:392-401)") from None
-            per.append([x if isinstance(x, Sym) else g.const(x) for x in a.reshape(-1).tolist()])
+        for _ in range(m):
+            per.append(flat_rates[k:k + state_sizes[name]])
+            k += state_sizes[name]
         channels[name] = per
     # ---- bookkeeping: integers
     g2 = Graph()
@@ -346,8 +648,6 @@ def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes):
     t2, tau2 = g2.leaf(("t", 0), "f"), g2.leaf(("tau", 0), "f")
     T, c = {}, 0
     slots = {}                                       # (state, transition, element) -> channel number (reference order)
-    for name in state_shapes:                        # channel order of `_SSA`: states in rate-dict order
-        pass
     for name, per in channels.items():
         T[name] = []
         for i, flat in enumerate(per):
@@ -357,11 +657,12 @@ def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes):
                 slots[(name, i, e)] = c
                 c += 1
             T[name].append(arr.reshape(tuple(state_shapes[name])) if state_shapes[name] else arr[0])
-    new = fn2(t2, tau2, T, **_inputs(g2, state_shapes, param_shapes, "i"))
-    if not isinstance(new, (tuple, list)):
-        new = (new,)
-    outs = _collect(new, state_shapes, "apply_transitionings")
-    outs = [o if isinstance(o, Sym) else g2.const(o) for o in outs]
+    def run_apply():
+        new = fn2(t2, tau2, T, **_inputs(g2, state_shapes, param_shapes, "i"))
+        if not isinstance(new, (tuple, list)):
+            new = (new,)
+        return _collect(new, state_shapes, "apply_transitionings")
+    outs = explore(g2, run_apply)
     for j, o in enumerate(outs):
         if o.kind != "i":
             raise TraceError("apply_transitionings must keep compartment counts integral (sums / differences / integer "
@@ -427,6 +728,19 @@ def emit(graph, outputs, ctype, leaf_expr, prefix="v"):
             if ctype == "int" and op == "div":
                 raise TraceError("division in integer bookkeeping")
             expr = f"{a[0]} {'+-*/'['add sub mul div'.split().index(op)]} {a[1]}"
+        elif op in ("lt", "le", "gt", "ge"):
+            lines.append(f"const bool {prefix}{i} = {a[0]} {dict(lt='<', le='<=', gt='>', ge='>=')[op]} {a[1]};")
+            name[i] = f"{prefix}{i}"
+            continue
+        elif op in ("and", "or", "not"):
+            expr = f"!{a[0]}" if op == "not" else f"{a[0]} {'&&' if op == 'and' else '||'} {a[1]}"
+            lines.append(f"const bool {prefix}{i} = {expr};")
+            name[i] = f"{prefix}{i}"
+            continue
+        elif op == "select":
+            lines.append(f"const {'bool' if kind == 'b' else ctype} {prefix}{i} = {a[0]} ? {a[1]} : {a[2]};")
+            name[i] = f"{prefix}{i}"
+            continue
         elif op == "neg":
             expr = f"-{a[0]}"
         elif op == "pow":
@@ -474,9 +788,9 @@ def _reject_time(graph, outputs, what):
             stack.extend(args)
 
 
-def ode_source(integrate, state_shapes, param_shapes, origin=""):
+def ode_source(integrate, state_shapes, param_shapes, origin="", **trace_kw):
     """C++ translation unit of a plugin holding the ODE `integrate`.  -> (source, n_state, n_param)."""
-    g, outs = trace_ode(integrate, state_shapes, param_shapes)
+    g, outs = trace_ode(integrate, state_shapes, param_shapes, **trace_kw)
     n_state = len(outs)
     n_param = sum(int(np.prod(s)) if s else 1 for s in param_shapes.values())
 

@@ -108,22 +108,23 @@ def _flat(values, shapes):
     return np.concatenate([np.ravel(np.asarray(values[k], dtype=np.float64)) for k in shapes]) if shapes else np.zeros(0)
 
 
-def build_ode(integrate, state_shapes, param_shapes, example_states, example_params, origin=""):
-    """`param_shapes` in FLAT order (the model function itself is called by keyword, like the reference does)."""
-    source, n_state, n_param = codegen.ode_source(integrate, state_shapes, param_shapes, origin)
+def build_ode(integrate, state_shapes, param_shapes, origin="", reference=None, example_states=None, example_params=None,
+              **trace_kw):
+    """`param_shapes` in FLAT order (model functions are called by keyword, like the reference does).  `reference(t)` ->
+    the derivatives as the Python functions give them at `example_states` / `example_params` (flat), for the self-check."""
+    source, n_state, n_param = codegen.ode_source(integrate, state_shapes, param_shapes, origin, **trace_kw)
     plug = compile_source(source, {"n_state": n_state, "n_param": n_param})
+    if reference is None:
+        return plug
     # self-check of one evaluation against the Python function
     fn = plug.lib.sodm_plugin_host_rhs
     fn.restype, fn.argtypes = None, [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     y = _flat(example_states, state_shapes)
-    par = _flat(example_params, param_shapes)
-    par_buf = np.concatenate([par, np.zeros(1)])
+    par_buf = np.concatenate([np.asarray(example_params, dtype=np.float64), np.zeros(1)])
     dy = np.empty(n_state)
-    pyfn = codegen._python_function(integrate)
-    for t in (0.0, 1.5):
+    for t in (0.0, 1.5, 40.25):
         fn(t, y.ctypes.data, par_buf.ctypes.data, dy.ctypes.data)
-        want = pyfn(t, **{k: np.asarray(example_states[k], dtype=np.float64) for k in state_shapes},
-                    **{k: example_params[k] for k in param_shapes})
+        want = reference(t)
         want = np.concatenate([_shaped(w, s) for w, s in zip(want if isinstance(want, (tuple, list)) else (want,),
                                                              state_shapes.values())])
         scale = np.maximum(np.abs(want), 1e-300)
@@ -131,7 +132,7 @@ def build_ode(integrate, state_shapes, param_shapes, example_states, example_par
             bad = ~((np.abs(dy - want) <= 1e-9 * scale + 1e-12 * np.abs(want).max(initial=0.0)) | (np.isnan(dy) & np.isnan(want)))
         if bad.any():
             j = int(np.argmax(bad))
-            raise codegen.TraceError(f"generated `integrate` disagrees with the Python function at the initial state "
+            raise codegen.TraceError(f"generated `integrate` disagrees with the Python function at the initial state, t = {t} "
                                      f"(element {j}: {dy[j]!r} vs {want[j]!r}); the model uses a NumPy idiom the tracer "
                                      "does not reproduce")
     return plug

@@ -112,3 +112,42 @@ def make_sirsi(cls=GenSirSi, scale=1.0):
 def make_pfr(nx, cls=GenPfr):
     return cls(td.pfr_initial_states(nx), td.pfr_parameters(nx),
                coordinates={"species": ["S", "A", "Es", "W"], "x": list(range(nx))})
+
+
+# ---- time-dependent parameter functions of an ODE (same bodies as tests/golden/make_golden.py::gen_tdpf) -------------
+import pandas as pd  # noqa: E402
+
+
+def tdpf_compliance(t, states, param):
+    if t < 30:
+        return param
+    else:
+        return param / 1.5
+
+
+def tdpf_lower_infectivity(t, states, param, start_measures):
+    if pd.to_datetime(t) < start_measures:
+        return param
+    else:
+        return param / 2
+
+
+def tdpf_ramp(t, states, param, ramp_days):
+    t0 = pd.Timestamp('2020-02-10')
+    if t < t0:
+        return param
+    elif t < t0 + pd.Timedelta(days=ramp_days):
+        frac = (t - t0) / pd.Timedelta(days=1) / ramp_days
+        return param * (1 - 0.6 * frac)
+    return param * 0.4 * (1 + 1e-4 * states['I'])
+
+
+def make_tdpf_models():
+    """-> (numeric-time step model, date-switch model with a date parameter, ramp model reading a state).  The tutorial
+    SIR class HAS a hand-written functor; with a time-dependent parameter function it is translated instead."""
+    y0 = {"S": 1000, "I": 1}
+    a = tm.ODE_SIR(y0, {"beta": 0.35, "gamma": 5}, time_dependent_parameters={"beta": tdpf_compliance})
+    b = tm.ODE_SIR(y0, {"beta": 0.35, "gamma": 5, "start_measures": pd.Timestamp("2020-02-05")},
+                   time_dependent_parameters={"beta": tdpf_lower_infectivity})
+    c = tm.ODE_SIR(y0, {"beta": 0.35, "gamma": 5, "ramp_days": 14.0}, time_dependent_parameters={"beta": tdpf_ramp})
+    return a, b, c

@@ -375,6 +375,67 @@ def gen_optimizers():
     save('optimizers.npz', **out)
 
 
+def tdpf_compliance(t, states, param):
+    """Step change on NUMERIC time (the pattern of src/tests/test_ODE.py:541-545)."""
+    if t < 30:
+        return param
+    else:
+        return param / 1.5
+
+
+def tdpf_lower_infectivity(t, states, param, start_measures):
+    """Date-valued switch with a date PARAMETER (tutorials/SIR/workflow_tutorial.py:201-205)."""
+    if pd.to_datetime(t) < start_measures:
+        return param
+    else:
+        return param / 2
+
+
+def tdpf_ramp(t, states, param, ramp_days):
+    """Linear ramp between two dates + dependence on the state (reads I)."""
+    t0 = pd.Timestamp('2020-02-10')
+    if t < t0:
+        return param
+    elif t < t0 + pd.Timedelta(days=ramp_days):
+        frac = (t - t0) / pd.Timedelta(days=1) / ramp_days
+        return param * (1 - 0.6 * frac)
+    return param * 0.4 * (1 + 1e-4 * states['I'])
+
+
+def gen_tdpf():
+    """ODE runs of the unmodified reference with time-dependent parameter functions (evaluated at every RK stage,
+    base.py:769-779): numeric time, date time with a date-valued parameter, a ramp that also reads a state."""
+    class ODE_SIR(base.ODE):
+        states = ['S', 'I', 'R']
+        parameters = ['beta', 'gamma']
+
+        @staticmethod
+        def integrate(t, S, I, R, beta, gamma):
+            N = S + I + R
+            dS = -beta * S * I / N
+            dI = beta * S * I / N - 1 / gamma * I
+            dR = 1 / gamma * I
+            return dS, dI, dR
+    out = {}
+    m = ODE_SIR({'S': 1000, 'I': 1}, {'beta': 0.35, 'gamma': 5}, time_dependent_parameters={'beta': tdpf_compliance})
+    r = m.sim(120)
+    out['numeric_y'], out['numeric_nfev'] = r['y'], np.array(r['nfev'])
+    r = m.sim(120, rtol=1e-8)
+    out['numeric_rtol1e-8_y'], out['numeric_rtol1e-8_nfev'] = r['y'], np.array(r['nfev'])
+    m = ODE_SIR({'S': 1000, 'I': 1}, {'beta': 0.35, 'gamma': 5, 'start_measures': pd.Timestamp('2020-02-05')},
+                time_dependent_parameters={'beta': tdpf_lower_infectivity})
+    ys, nf, starts = [], [], []
+    for shift in (0, 3.5, 11.25, 40):
+        m.parameters['start_measures'] = pd.Timestamp('2020-02-05') + pd.Timedelta(days=shift)
+        r = m.sim(['2020-01-01', '2020-04-30'])
+        ys.append(r['y']); nf.append(r['nfev']); starts.append(shift)
+    out['date_y'], out['date_nfev'], out['date_shift_days'] = np.stack(ys), np.array(nf), np.array(starts)
+    m = ODE_SIR({'S': 1000, 'I': 1}, {'beta': 0.35, 'gamma': 5, 'ramp_days': 14.0}, time_dependent_parameters={'beta': tdpf_ramp})
+    r = m.sim(['2020-01-01', '2020-04-30'])
+    out['ramp_y'], out['ramp_nfev'] = r['y'], np.array(r['nfev'])
+    save('tdpf.npz', **out)
+
+
 class _FakeVariable:
     def __init__(self, values):
         self.values = values
@@ -426,6 +487,6 @@ def gen_post():
 
 
 if __name__ == '__main__':
-    what = sys.argv[1:] or ['jump_single', 'ssa', 'jump_ensemble', 'schedule', 'ode', 'loglik', 'optimizers', 'post']
+    what = sys.argv[1:] or ['jump_single', 'ssa', 'jump_ensemble', 'schedule', 'ode', 'loglik', 'optimizers', 'post', 'tdpf']
     for w in what:
         globals()['gen_' + w]()

@@ -44,10 +44,15 @@ def test_tracer_records_numpy_arithmetic():
 def test_tracer_refuses_what_it_cannot_translate():
     shapes, pars = {"S": (), "I": ()}, {"beta": ()}
 
-    def branchy(t, S, I, beta):
-        return (-beta * S if S > 0 else 0.0), beta * I
-    with pytest.raises(codegen.TraceError, match="comparison"):
-        codegen.trace_ode(branchy, shapes, pars)
+    def needs_a_number(t, S, I, beta):
+        return -beta * S * np.arange(3.0)[int(I)], beta * I
+    with pytest.raises(codegen.TraceError, match="cannot become a Python number"):
+        codegen.trace_ode(needs_a_number, shapes, pars)
+
+    def calendar(t, S, I, beta):
+        return (-beta * S if t.weekday() < 5 else 0.0), beta * I
+    with pytest.raises(codegen.TraceError, match="calendar logic"):
+        codegen.trace_ode(calendar, shapes, {"beta": (), "__t0__": ()}, date_unit_us=86400e6)
 
     def wrong_shape(t, S, I, beta):
         return np.ones(3) * S, I
@@ -72,8 +77,83 @@ def test_tracer_refuses_what_it_cannot_translate():
     with pytest.raises(NotImplementedError):                      # still no CPU fallback: a model must translate or fail
         class Bad(gm.ODE):
             states, parameters = ["S", "I"], ["beta"]
-            integrate = staticmethod(branchy)
+            integrate = staticmethod(needs_a_number)
         Bad({"S": 1.0, "I": 1.0}, {"beta": 0.1})
+
+
+def test_branches_on_model_values_become_selections():
+    def f(t, S, I, beta, k):
+        if t < 0:
+            b = beta
+        elif t < 10 and S > 5:
+            b = beta / 1.5
+        else:
+            b = beta * k
+        inf = np.where(I > 1, b * S * I, 0.0)
+        return -inf, inf
+    g, outs = codegen.trace_ode(f, {"S": (), "I": ()}, {"beta": (), "k": ()})
+    lines, exprs = codegen.emit(g, outs, "double", lambda n: "t" if n[0] == "t" else f"{n[0]}[{n[1]}]")
+    assert sum(" ? " in ln for ln in lines) >= 6 and any("t < 10.0" in ln for ln in lines)
+
+    # evaluate the DAG on numbers: every path of the Python function is reproduced
+    def ev(i, env, memo):
+        if i in memo:
+            return memo[i]
+        op, args, _ = g.nodes[i]
+        if op == "in":
+            r = env[args[0]]
+        elif op == "const":
+            r = args[0]
+        else:
+            a = [ev(j, env, memo) for j in args]
+            r = {"add": lambda: a[0] + a[1], "sub": lambda: a[0] - a[1], "mul": lambda: a[0] * a[1], "div": lambda: a[0] / a[1],
+                 "neg": lambda: -a[0], "lt": lambda: a[0] < a[1], "gt": lambda: a[0] > a[1], "le": lambda: a[0] <= a[1],
+                 "ge": lambda: a[0] >= a[1], "select": lambda: a[1] if a[0] else a[2]}[op]()
+        memo[i] = r
+        return r
+    for t, S, I in [(-1.0, 9.0, 3.0), (5.0, 9.0, 3.0), (5.0, 2.0, 3.0), (50.0, 9.0, 3.0), (5.0, 9.0, 0.5)]:
+        env = {("t", 0): t, ("y", 0): S, ("y", 1): I, ("par", 0): 0.3, ("par", 1): 2.0}
+        got = [ev(o.i, env, {}) for o in outs]
+        assert np.allclose(got, f(t, S, I, 0.3, 2.0), rtol=1e-15)
+
+
+def test_ode_time_dependent_parameter_functions_translate_and_match_the_reference(golden):
+    """The translated composite (TDPFs + integrate), evaluated ON THE HOST through the plugin's self-check hook and
+    integrated with the reference's own solver call (scipy RK45, base.py:855), reproduces the unmodified reference."""
+    import ctypes as C
+    from datetime import datetime
+    from scipy.integrate import solve_ivp
+    g = golden["tdpf"]
+    num, date, ramp = gm.make_tdpf_models()
+
+    def integrate_on_host(model, par, n_out, rtol=1e-4):
+        fn = model.device_model.lib.sodm_plugin_host_rhs
+        fn.restype, fn.argtypes = None, [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        buf = np.concatenate([par, [0.0]])
+
+        def rhs(t, y):
+            dy = np.empty(3)
+            yy = np.ascontiguousarray(y)
+            fn(float(t), yy.ctypes.data, buf.ctypes.data, dy.ctypes.data)
+            return dy
+        return solve_ivp(rhs, [0, n_out - 1], [1000.0, 1.0, 0.0], t_eval=np.arange(n_out), rtol=rtol)
+    num._bind_generated_functor(None, [None])
+    r = integrate_on_host(num, np.array([0.35, 5.0]), 121)
+    np.testing.assert_allclose(r.y, g["numeric_y"], rtol=1e-9, atol=1e-9)
+    assert r.nfev == int(g["numeric_nfev"])
+    start = datetime(2020, 1, 1)
+    date._bind_generated_functor(86400e6, [start])
+    assert date._date_params == ["start_measures"] and list(date._param_offsets) == ["beta", "gamma", "start_measures", "__t0__"]
+    t0_abs = codegen.date_to_units(start, 86400e6)
+    for i, shift in enumerate(g["date_shift_days"]):
+        par = np.array([0.35, 5.0, t0_abs + 35 + shift, t0_abs])               # 2020-02-05 is day 35
+        r = integrate_on_host(date, par, 121)
+        np.testing.assert_allclose(r.y, g["date_y"][i], rtol=1e-9, atol=1e-9)
+        assert r.nfev == int(g["date_nfev"][i])
+    ramp._bind_generated_functor(86400e6, [start])
+    r = integrate_on_host(ramp, np.array([0.35, 5.0, 14.0, t0_abs]), 121)
+    np.testing.assert_allclose(r.y, g["ramp_y"], rtol=1e-9, atol=1e-9)
+    assert r.nfev == int(g["ramp_nfev"])
 
 
 @pytest.mark.parametrize("make", [gm.make_influenza, gm.make_sirsi, gm.make_seird, gm.make_lotka, lambda: gm.make_pfr(5),

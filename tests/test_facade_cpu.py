@@ -41,14 +41,14 @@ def test_model_declaration_errors():
     from pysodm_b200 import plugin
     assert isinstance(NoFunctor({"A": 1.0}, {"k": 0.1}).device_model, plugin.Plugin)
 
-    class Untranslatable(ODE):                   # value-dependent control flow cannot be traced: fails loudly, no fallback
+    class Untranslatable(ODE):                   # a model value used as a Python number cannot be traced: fails loudly, no fallback
         states = ["A"]
         parameters = ["k"]
 
         @staticmethod
         def integrate(t, A, k):
-            return (-k * A if A > 0 else 0.0),
-    with pytest.raises(NotImplementedError, match="cannot\\s+follow Python control flow"):
+            return -k * A * np.arange(3.0)[int(A)],
+    with pytest.raises(NotImplementedError, match="cannot become a Python number"):
         Untranslatable({"A": 1.0}, {"k": 0.1})
     with pytest.raises(ValueError, match="Missing parameters"):
         tm.ODE_SIR({"S": 1000, "I": 1}, {"beta": 0.35})

@@ -139,3 +139,44 @@ def test_generated_odes_follow_the_hand_written_functors(golden):
     # Euler with a fixed step too
     eu = lv.sim(10, tau=0.125)
     assert np.isfinite(eu["prey"].values).all()
+
+
+def test_ode_time_dependent_parameter_functions(golden):
+    """TDPFs of an ODE are evaluated at every RK stage time (base.py:769-779): translated with `integrate`, the device
+    run follows the reference's scipy run step for step -- numeric time, dates with a date-valued parameter (also drawn
+    per trajectory, tutorials/SIR/workflow_tutorial.py:201-223), and a ramp that reads a state."""
+    import pandas as pd
+    g = golden["tdpf"]
+    num, date, ramp = gm.make_tdpf_models()
+    out = num.sim(120)
+    y = np.stack([out[s].values for s in ("S", "I", "R")])
+    np.testing.assert_allclose(y, g["numeric_y"], rtol=1e-6, atol=1e-9)
+    assert int(num.last_nfev[0]) == int(g["numeric_nfev"])
+    out = num.sim(120, rtol=1e-8)
+    np.testing.assert_allclose(np.stack([out[s].values for s in ("S", "I", "R")]), g["numeric_rtol1e-8_y"], rtol=1e-7, atol=1e-9)
+    assert int(num.last_nfev[0]) == int(g["numeric_rtol1e-8_nfev"])
+    assert num.parameters == {"beta": 0.35, "gamma": 5}
+
+    # one launch for the four start dates: the date parameter varies per trajectory
+    shifts = list(g["date_shift_days"])
+    it = iter([shifts[0]] + shifts)                                  # the draw function is called once for validation first
+
+    def draw(parameters):
+        parameters["start_measures"] = pd.Timestamp("2020-02-05") + pd.Timedelta(days=float(next(it)))
+        return parameters
+    span = ["2020-01-01", "2020-04-30"]
+    out = date.sim(span, N=len(shifts), draw_function=draw)
+    assert tuple(out["I"].dims) == ("draws", "date")
+    y = np.stack([out[s].values for s in ("S", "I", "R")], axis=1)          # [draws, state, time]
+    np.testing.assert_allclose(y, g["date_y"], rtol=1e-6, atol=1e-9)
+    assert np.array_equal(date.last_nfev.cpu().numpy(), g["date_nfev"])
+    assert date.parameters["start_measures"] == pd.Timestamp("2020-02-05")     # restored after sim
+    single = date.sim(span)
+    np.testing.assert_allclose(single["I"].values, g["date_y"][0][1], rtol=1e-6, atol=1e-9)
+
+    out = ramp.sim(span)
+    np.testing.assert_allclose(np.stack([out[s].values for s in ("S", "I", "R")]), g["ramp_y"], rtol=1e-6, atol=1e-9)
+    assert int(ramp.last_nfev[0]) == int(g["ramp_nfev"])
+    # the same model on numeric time is a different translation (dates cannot be compared with numbers)
+    with pytest.raises(NotImplementedError):
+        ramp.sim(120)
