@@ -76,8 +76,8 @@ extern "C" {
 #define SODM_ODE_EULER     1   /* explicit Euler with step tau + interpolation (base.py:800-819) */
 #define SODM_ODE_RK4       2   /* classical fixed-step RK4 (extension; the reference has none) */
 
-#define SODM_MAX_PARAM 32      /* flat parameter elements per model */
-#define SODM_MAX_STATE 32      /* flat state elements of a jump model */
+#define SODM_MAX_PARAM 64      /* flat parameter elements per model */
+#define SODM_MAX_STATE 64      /* flat state elements of a jump model */
 
 typedef struct sodm_model_info {
     int32_t kind;          /* SODM_KIND_* */

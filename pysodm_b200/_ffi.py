@@ -21,7 +21,7 @@ JUMP_TAU_LEAP, JUMP_SSA = 0, 1
 ODE_RK45, ODE_EULER, ODE_RK4 = 0, 1, 2
 LL_POISSON, LL_NORMAL, LL_LOGNORMAL, LL_NEGBIN = 0, 1, 2, 3
 ARG_NONE, ARG_SCALAR, ARG_COLUMN, ARG_FULL = 0, 1, 2, 3
-MAX_PARAM, MAX_STATE = 32, 32
+MAX_PARAM, MAX_STATE = 64, 64
 NOISE_POISSON, NOISE_GAUSSIAN_ABS, NOISE_GAUSSIAN_REL, NOISE_NEGBIN = 0, 1, 2, 3
 NOISE_ST_BAD_MEAN = 1
 MAX_RANKS = 4

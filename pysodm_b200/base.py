@@ -194,6 +194,11 @@ class _DeviceBackedModel:
                 shapes["__t0__"] = ()
             self._date_params = date_params
             state_shapes = OrderedDict((k, tuple(self.state_shapes[k])) for k in self.states_names)
+            n_par = sum(int(np.prod(v)) if v else 1 for v in shapes.values())
+            n_st = sum(int(np.prod(v)) if v else 1 for v in state_shapes.values())
+            if n_par > _ffi.MAX_PARAM or (n_st > _ffi.MAX_STATE and self._kind == "jump"):
+                raise NotImplementedError(f"generated models are limited to {_ffi.MAX_PARAM} flat parameter elements (found "
+                                          f"{n_par}) and, for jump processes, {_ffi.MAX_STATE} flat state elements (found {n_st})")
             origin = f" of {type(self).__module__}.{type(self).__qualname__}"
             if self._kind == "ode":
                 spec_t = [(name, fn, self._function_parameters[i]) for i, (name, fn) in enumerate(tdpfs.items())]
@@ -211,9 +216,6 @@ class _DeviceBackedModel:
         self._spec, self._spec_params = spec, shapes
         self._param_offsets, self._n_param_flat = spec.param_offsets(0)
         self._time_unit_us = date_unit_us
-        if self._n_param_flat > _ffi.MAX_PARAM or plug.info.n_state > _ffi.MAX_STATE and self._kind == "jump":
-            raise NotImplementedError(f"generated models are limited to {_ffi.MAX_PARAM} flat parameter elements and "
-                                      f"{_ffi.MAX_STATE} flat state elements per launch block")
 
     def _example_flat(self, shapes, date_unit_us, date_range):
         """Flat parameter vector of the model's current parameters (for the build-time self-check of a generated ODE)."""

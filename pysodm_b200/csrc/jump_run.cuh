@@ -15,8 +15,8 @@
 
 namespace sodm {
 
-constexpr int MAX_PARAM = 32;   // flat parameter elements passed by value
-constexpr int MAX_STATE = 32;   // flat state elements of a jump model
+constexpr int MAX_PARAM = 64;   // flat parameter elements passed by value
+constexpr int MAX_STATE = 64;   // flat state elements of a jump model
 
 enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, TUNE_COOPERATIVE = 256u };
 

@@ -28,7 +28,7 @@
 
 namespace sodm {
 
-constexpr int ODE_MAX_PARAM = 32;
+constexpr int ODE_MAX_PARAM = 64;
 
 struct OdeLaunch {
     int64_t n_traj, ld_in, ld_out;
