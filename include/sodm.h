@@ -259,6 +259,32 @@ int sodm_draws_order_stats(const void* in, int32_t dtype, int64_t n_cells, int64
                            const int64_t* ranks, int32_t n_ranks, double* out /* (device) [n_ranks][n_cells] */,
                            void* stream);
 
+/* Order statistics of an ensemble SHARDED by trajectory over several GPUs: the same radix search in phases whose small
+ * per-cell tables the caller combines across ranks (one all-reduce each) -- trajectories never move, histograms do.
+ *   state arrays (device, int64 unless noted; keys are order-preserving integers with the sign bit flipped so that signed
+ *   MIN / MAX order them):  lo[n_cells], hi[n_cells], nan_flag[n_cells] (int32), settled[n_cells] (int32, zero-initialised),
+ *   prefix[2][n_cells][n_ranks] (second half is scratch), remaining[n_cells][n_ranks] (initialised with the GLOBAL ranks).
+ *   1. SODM_SELECT_MINMAX     fills lo / hi / nan_flag from the local shard   -> all-reduce MIN(lo), MAX(hi), MAX(nan_flag)
+ *   2. repeat ceil(key bits / 11) times (cells settle early and are then skipped):
+ *        SODM_SELECT_HISTOGRAM  hist[n_cells][n_ranks][2048] (uint32) of the local shard   -> all-reduce SUM(hist)
+ *        SODM_SELECT_PICK       every rank advances prefix / remaining / settled identically
+ *   3. SODM_SELECT_DECODE     out[n_ranks][n_cells] as in sodm_draws_order_stats */
+#define SODM_SELECT_MINMAX    0
+#define SODM_SELECT_HISTOGRAM 1
+#define SODM_SELECT_PICK      2
+#define SODM_SELECT_DECODE    3
+#define SODM_SELECT_BINS      2048
+typedef struct sodm_select_state {
+    int64_t* lo;
+    int64_t* hi;
+    int32_t* nan_flag;
+    int32_t* settled;
+    int64_t* prefix;
+    int64_t* remaining;
+} sodm_select_state;
+int sodm_draws_select_phase(int32_t phase, const void* in, int32_t dtype, int64_t n_cells, int64_t n_traj, int64_t ld,
+                            int32_t n_ranks, const sodm_select_state* state, uint32_t* hist, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,7 @@ MAX_PARAM, MAX_STATE = 64, 64
 NOISE_POISSON, NOISE_GAUSSIAN_ABS, NOISE_GAUSSIAN_REL, NOISE_NEGBIN = 0, 1, 2, 3
 NOISE_ST_BAD_MEAN = 1
 MAX_RANKS = 4
+SELECT_MINMAX, SELECT_HISTOGRAM, SELECT_PICK, SELECT_DECODE, SELECT_BINS = 0, 1, 2, 3, 2048
 
 
 class ModelInfo(C.Structure):
@@ -74,6 +75,11 @@ class NoiseArgs(C.Structure):
                 ("stream", C.c_void_p)]
 
 
+class SelectState(C.Structure):
+    _fields_ = [("lo", C.c_void_p), ("hi", C.c_void_p), ("nan_flag", C.c_void_p), ("settled", C.c_void_p),
+                ("prefix", C.c_void_p), ("remaining", C.c_void_p)]
+
+
 # every symbol include/sodm.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "sodm_abi_version": (C.c_int, []),
@@ -92,6 +98,8 @@ SYMBOLS = {
     "sodm_draws_sum": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "sodm_draws_order_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                          C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.c_void_p]),
+    "sodm_draws_select_phase": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                          C.POINTER(SelectState), C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -339,20 +339,28 @@ class _DeviceBackedModel:
 
     def _sim_on_device(self, run, var, y0, variables, n_rows, n_kept, N, sim_dtype, dev, date_range, t0, t1, raise_on_status,
                        time_coord=None):
-        """One launch for all N trajectories into a resident [row][time][N] buffer -> DeviceEnsemble."""
+        """One launch for this rank's trajectories into a resident [row][time][n_local] buffer -> DeviceEnsemble.
+        Under torch.distributed the N draws are sharded as contiguous ranges (sharding.shard_range): every rank evaluated
+        the same N draws on the host (same NumPy seed on every rank = same ensemble as one GPU would give), simulates its
+        slice with Philox streams keyed by the GLOBAL draw index, and the ensemble's mean / quantile reduce across ranks."""
         import torch
+        from . import sharding
         from .ensemble import DeviceEnsemble
-        buf = torch.empty((n_rows, n_kept, N), dtype=sim_dtype, device=dev)
+        lo, hi = sharding.shard_range(N)
+        n = hi - lo
+        buf = torch.empty((n_rows, n_kept, n), dtype=sim_dtype, device=dev)
         keys = sorted(var)
-        v = (keys, torch.from_numpy(np.stack([var[k] for k in keys])).to(dev)) if keys else None
-        y = torch.from_numpy(np.ascontiguousarray(y0)).to(dev)
-        status = torch.zeros(N, dtype=torch.int32, device=dev)
-        run(buf, v, y, status)
+        v = (keys, torch.from_numpy(np.stack([var[k][lo:hi] for k in keys])).to(dev)) if keys else None
+        y0 = np.ascontiguousarray(y0 if y0.ndim == 1 else y0[:, lo:hi])
+        y = torch.from_numpy(y0).to(dev)
+        status = torch.zeros(n, dtype=torch.int32, device=dev)
+        run(buf, v, y, status, lo, n)
         raise_on_status(status)
         time_name = "date" if date_range[0] is not None else "time"
         if time_coord is None:
             time_coord = date_range if date_range[0] is not None else np.arange(t0, t1 + 1)
-        return DeviceEnsemble(buf, variables, self.dimensions_per_state, self.state_coordinates, time_name, time_coord)
+        return DeviceEnsemble(buf, variables, self.dimensions_per_state, self.state_coordinates, time_name, time_coord,
+                              traj_id0=lo, n_global=N)
 
     def _to_dataset(self, host, variables, N, time_name, time_coord):
         arrays = OrderedDict()
@@ -461,10 +469,12 @@ class JumpProcess(_DeviceBackedModel):
             if seed is None:
                 seed = int(np.random.randint(0, 2 ** 32)) | (int(np.random.randint(0, 2 ** 31)) << 32)
             if output == "device":
+                from . import sharding
+                seed = sharding.agree_on(seed)               # one ensemble across the ranks of a torch.distributed job
                 return self._sim_on_device(
-                    lambda buf, v, y, st: engine.jump_run(
-                        self.device_model, y, par, N, t0, n_out, tau, method=method, var=v, tdpf=self._to_device_tdpf(tdpf, dev),
-                        compat=compat, seed=seed, out_dtype=sim_dtype, state_sel=rows, out=buf, status=st, dev=dev),
+                    lambda buf, v, y, st, lo, n: engine.jump_run(
+                        self.device_model, y, par, n, t0, n_out, tau, method=method, var=v, tdpf=self._to_device_tdpf(tdpf, dev),
+                        compat=compat, seed=seed, traj_id0=lo, out_dtype=sim_dtype, state_sel=rows, out=buf, status=st, dev=dev),
                     var, y0, variables, len(rows), n_out, N, sim_dtype, dev, date_range, t0, t1, self._raise_on_status)
             if output != "host":
                 raise ValueError("output must be 'host' or 'device'")
@@ -565,8 +575,8 @@ class ODE(_DeviceBackedModel):
                 coord = date_range if date_range[0] is not None else grid
                 coord = coord[-1:] if output_last_only else coord[::int(output_stride)]
 
-                def run(buf, v, y, st):
-                    _, nfev, st_ = engine.ode_run(self.device_model, y, par, N, t0, n_out, method=dev_method, rtol=rtol,
+                def run(buf, v, y, st, lo, n):
+                    _, nfev, st_ = engine.ode_run(self.device_model, y, par, n, t0, n_out, method=dev_method, rtol=rtol,
                                                   atol=atol, tau=tau or 0.0, var=v, model_arg=self._model_arg,
                                                   out_stride=output_stride, out_last_only=output_last_only, out=buf, dev=dev)
                     st.copy_(st_)

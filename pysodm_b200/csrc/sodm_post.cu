@@ -318,6 +318,180 @@ __global__ void __launch_bounds__(SELECT_THREADS) draws_select_kernel(const T* _
     }
 }
 
+// ---- order statistics of cells whose trajectories are spread over several GPUs ------------------------------------
+// The fused kernel above needs a whole column in one place.  When an ensemble is sharded by trajectory, the same radix
+// search runs in PHASES whose per-cell tables are combined across ranks by the caller (one NCCL all-reduce each) -- the
+// data never moves, only histograms do:
+//   minmax    local smallest / largest key and a NaN flag per cell            -> all-reduce MIN / MAX / MAX
+//   histogram one digit of the elements matching each rank's settled prefix   -> all-reduce SUM   ([cell][rank][bin])
+//   pick      (identical on every rank) the bin holding each requested rank; settles up to 11 more bits
+//   decode    keys -> values
+// Keys travel as int64 with the sign bit flipped, so that signed MIN / MAX order them like the unsigned keys.
+struct SelectState {           // device arrays, all-reduced / updated between phases
+    long long* lo;             // [n_cells]            smallest key (biased)
+    long long* hi;             // [n_cells]            largest key (biased)
+    int32_t* nan_flag;         // [n_cells]
+    int32_t* settled;          // [n_cells]            bits of (key - lo) already decided
+    long long* prefix;         // [n_cells][n_ranks]   decided high bits
+    long long* remaining;      // [n_cells][n_ranks]   rank among the elements that match the prefix
+};
+constexpr unsigned long long KEY_BIAS = 0x8000000000000000ull;
+
+__device__ __forceinline__ int bits_of(unsigned long long range) {
+    int b = 0;
+    while (b < 64 && (range >> b) != 0) ++b;
+    return b;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SELECT_THREADS) draws_minmax_kernel(const T* __restrict__ in, int64_t n_traj, int64_t ld, SelectState st) {
+    using R = Radix<T>;
+    using Key = typename R::Key;
+    __shared__ Key warp_lo[SELECT_THREADS / 32], warp_hi[SELECT_THREADS / 32];
+    __shared__ int any_nan;
+    if (threadIdx.x == 0) any_nan = 0;
+    __syncthreads();
+    const T* col = in + (int64_t)blockIdx.x * ld;
+    Key lo = ~(Key)0, hi = 0;
+    bool saw_nan = false;
+    for_each_key(col, n_traj, [&](T x) {
+        saw_nan |= R::is_nan(x);
+        const Key k = R::encode(x);
+        lo = k < lo ? k : lo;
+        hi = k > hi ? k : hi;
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const Key l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) { warp_lo[threadIdx.x >> 5] = lo; warp_hi[threadIdx.x >> 5] = hi; }
+    if (saw_nan) any_nan = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < SELECT_THREADS / 32; ++w) {
+            lo = warp_lo[w] < lo ? warp_lo[w] : lo;
+            hi = warp_hi[w] > hi ? warp_hi[w] : hi;
+        }
+        // an empty shard contributes the neutral elements of MIN / MAX
+        st.lo[blockIdx.x] = (long long)(((unsigned long long)lo) ^ KEY_BIAS);
+        st.hi[blockIdx.x] = (long long)(((unsigned long long)hi) ^ KEY_BIAS);
+        if (n_traj == 0) { st.lo[blockIdx.x] = 0x7fffffffffffffffll; st.hi[blockIdx.x] = (long long)0x8000000000000000ull; }
+        st.nan_flag[blockIdx.x] = any_nan;
+    }
+}
+
+// hist[(cell * n_ranks + j) * BINS + b]; cells that are already settled are skipped without touching their column
+template <typename T>
+__global__ void __launch_bounds__(SELECT_THREADS) draws_histogram_kernel(const T* __restrict__ in, int64_t n_traj, int64_t ld,
+                                                                          SelectState st, int n_ranks, uint32_t* __restrict__ hist) {
+    using R = Radix<T>;
+    using Key = typename R::Key;
+    __shared__ uint32_t h[MAX_RANKS][BINS];
+    const int64_t c = blockIdx.x;
+    const unsigned long long lo = ((unsigned long long)st.lo[c]) ^ KEY_BIAS, hi = ((unsigned long long)st.hi[c]) ^ KEY_BIAS;
+    const int total_bits = bits_of(hi - lo), settled = st.settled[c];
+    uint32_t* out = hist + c * n_ranks * BINS;
+    if (settled >= total_bits) return;                                  // uniform over the block
+    const int bits = (total_bits - settled) < DIGIT_BITS ? (total_bits - settled) : DIGIT_BITS;
+    const int shift = total_bits - settled - bits;
+    for (int b = threadIdx.x; b < n_ranks * BINS; b += blockDim.x) (&h[0][0])[b] = 0;
+    __syncthreads();
+    const uint32_t mask = (1u << bits) - 1u;
+    const T* col = in + c * ld;
+    if (settled == 0) {                                                 // every rank shares the empty prefix: slot 0
+        for_each_key(col, n_traj, [&](T x) {
+            const unsigned long long k = (unsigned long long)R::encode(x) - lo;
+            atomicAdd(&h[0][(uint32_t)(k >> shift) & mask], 1u);
+        });
+    } else {
+        unsigned long long p[MAX_RANKS];
+#pragma unroll
+        for (int j = 0; j < MAX_RANKS; ++j) p[j] = j < n_ranks ? (unsigned long long)st.prefix[c * n_ranks + j] : ~0ull;
+        for_each_key(col, n_traj, [&](T x) {
+            const unsigned long long k = (unsigned long long)R::encode(x) - lo;
+            const unsigned long long high = k >> (shift + bits);
+            const uint32_t digit = (uint32_t)(k >> shift) & mask;
+            bool done = false;                                          // ranks with equal prefixes: count once, in the first slot
+#pragma unroll
+            for (int j = 0; j < MAX_RANKS; ++j)
+                if (j < n_ranks && !done && high == p[j]) { atomicAdd(&h[j][digit], 1u); done = true; }
+        });
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < n_ranks * BINS; b += blockDim.x) out[b] = (&h[0][0])[b];
+    (void)sizeof(Key);
+}
+
+// one warp per (cell, rank): the bin of the all-reduced histogram that holds the rank
+__global__ void __launch_bounds__(128) draws_pick_kernel(SelectState st, int n_ranks, int64_t n_cells, const uint32_t* __restrict__ hist) {
+    const int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (item >= n_cells * n_ranks) return;
+    const int64_t c = item / n_ranks;
+    const int j = (int)(item % n_ranks);
+    const unsigned long long lo = ((unsigned long long)st.lo[c]) ^ KEY_BIAS, hi = ((unsigned long long)st.hi[c]) ^ KEY_BIAS;
+    const int total_bits = bits_of(hi - lo), settled = st.settled[c];
+    if (settled >= total_bits) return;
+    const int bits = (total_bits - settled) < DIGIT_BITS ? (total_bits - settled) : DIGIT_BITS;
+    // the histogram of this rank's prefix lives in the FIRST slot with that prefix
+    int slot = 0;
+    if (settled > 0) {
+        const long long mine = st.prefix[c * n_ranks + j];
+        slot = j;
+        for (int q = 0; q < j; ++q) if (st.prefix[c * n_ranks + q] == mine) { slot = q; break; }
+    }
+    const uint32_t* h = hist + (c * n_ranks + slot) * BINS;
+    constexpr int PER = BINS / 32;
+    unsigned long long local = 0;
+    for (int b = 0; b < PER; ++b) local += h[lane * PER + b];
+    unsigned long long incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const long long want = st.remaining[c * n_ranks + j];
+    const long long before = (long long)(incl - local);
+    if (want >= before && want < (long long)incl) {
+        long long cum = before;
+        int b = 0;
+        for (; b < PER - 1; ++b) {
+            const uint32_t cnt = h[lane * PER + b];
+            if (want < cum + cnt) break;
+            cum += cnt;
+        }
+        const unsigned long long old = settled ? (unsigned long long)st.prefix[c * n_ranks + j] : 0ull;
+        // written to a shadow slot and published by draws_advance_kernel: other warps of this cell still read `prefix`
+        st.prefix[(n_cells + c) * n_ranks + j] = (long long)((old << bits) | (unsigned long long)(lane * PER + b));
+        st.remaining[c * n_ranks + j] = want - cum;
+    }
+}
+
+__global__ void draws_advance_kernel(SelectState st, int n_ranks, int64_t n_cells) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const unsigned long long lo = ((unsigned long long)st.lo[c]) ^ KEY_BIAS, hi = ((unsigned long long)st.hi[c]) ^ KEY_BIAS;
+    const int total_bits = bits_of(hi - lo), settled = st.settled[c];
+    if (settled >= total_bits) return;
+    const int bits = (total_bits - settled) < DIGIT_BITS ? (total_bits - settled) : DIGIT_BITS;
+    for (int j = 0; j < n_ranks; ++j) st.prefix[c * n_ranks + j] = st.prefix[(n_cells + c) * n_ranks + j];
+    st.settled[c] = settled + bits;
+}
+
+template <typename T>
+__global__ void draws_decode_kernel(SelectState st, int n_ranks, int64_t n_cells, double* __restrict__ out) {
+    using R = Radix<T>;
+    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_cells * n_ranks) return;
+    const int64_t c = item / n_ranks;
+    const int j = (int)(item % n_ranks);
+    const unsigned long long lo = ((unsigned long long)st.lo[c]) ^ KEY_BIAS;
+    const unsigned long long key = lo + (st.settled[c] ? (unsigned long long)st.prefix[c * n_ranks + j] : 0ull);
+    out[(int64_t)j * n_cells + c] = st.nan_flag[c] ? __longlong_as_double(0x7ff8000000000000ll) : R::decode((typename R::Key)key);
+}
+
 template <typename Tin, typename Tout>
 static int launch_noise_typed(const sodm_noise_args* a, cudaStream_t s) {
     const Tin* in = (const Tin*)a->in;
@@ -422,6 +596,65 @@ extern "C" int sodm_draws_order_stats(const void* in, int32_t dtype, int64_t n_c
         case SODM_I32: draws_select_kernel<int32_t><<<grid, SELECT_THREADS, 0, s>>>((const int32_t*)in, n_traj, ld, rl, n_cells, out); break;
         case SODM_F32: draws_select_kernel<float><<<grid, SELECT_THREADS, 0, s>>>((const float*)in, n_traj, ld, rl, n_cells, out); break;
         default:       draws_select_kernel<double><<<grid, SELECT_THREADS, 0, s>>>((const double*)in, n_traj, ld, rl, n_cells, out); break;
+    }
+    SODM_CUDA_CHECK(cudaGetLastError());
+    return SODM_OK;
+}
+
+// ---- phases of the sharded order statistics (see SelectState) ----------------------------------------------------
+static SelectState select_state(const sodm_select_state* p) {
+    SelectState st;
+    st.lo = (long long*)p->lo; st.hi = (long long*)p->hi; st.nan_flag = p->nan_flag; st.settled = p->settled;
+    st.prefix = (long long*)p->prefix; st.remaining = (long long*)p->remaining;
+    return st;
+}
+
+extern "C" int sodm_draws_select_phase(int32_t phase, const void* in, int32_t dtype, int64_t n_cells, int64_t n_traj, int64_t ld,
+                                       int32_t n_ranks, const sodm_select_state* state, uint32_t* hist, double* out, void* stream) {
+    int rc = check_columns("sodm_draws_select_phase", in, dtype, n_cells, n_traj, ld);
+    if (rc != SODM_OK) return rc;
+    if (!state || !state->lo || !state->hi || !state->nan_flag || !state->settled || !state->prefix || !state->remaining)
+        return fail(SODM_EINVAL, "sodm_draws_select_phase: incomplete state");
+    if (n_ranks < 1 || n_ranks > MAX_RANKS) return fail(SODM_EINVAL, "sodm_draws_select_phase: n_ranks %d outside 1..%d", n_ranks, MAX_RANKS);
+    if (n_cells == 0) return SODM_OK;
+    if (n_cells > 2147483647LL) return fail(SODM_EINVAL, "sodm_draws_select_phase: too many cells");
+    cudaStream_t s = (cudaStream_t)stream;
+    const SelectState st = select_state(state);
+    const unsigned grid = (unsigned)n_cells;
+    switch (phase) {
+        case SODM_SELECT_MINMAX:
+            switch (dtype) {
+                case SODM_I32: draws_minmax_kernel<int32_t><<<grid, SELECT_THREADS, 0, s>>>((const int32_t*)in, n_traj, ld, st); break;
+                case SODM_F32: draws_minmax_kernel<float><<<grid, SELECT_THREADS, 0, s>>>((const float*)in, n_traj, ld, st); break;
+                default:       draws_minmax_kernel<double><<<grid, SELECT_THREADS, 0, s>>>((const double*)in, n_traj, ld, st); break;
+            }
+            break;
+        case SODM_SELECT_HISTOGRAM:
+            if (!hist) return fail(SODM_EINVAL, "sodm_draws_select_phase: null histogram");
+            switch (dtype) {
+                case SODM_I32: draws_histogram_kernel<int32_t><<<grid, SELECT_THREADS, 0, s>>>((const int32_t*)in, n_traj, ld, st, n_ranks, hist); break;
+                case SODM_F32: draws_histogram_kernel<float><<<grid, SELECT_THREADS, 0, s>>>((const float*)in, n_traj, ld, st, n_ranks, hist); break;
+                default:       draws_histogram_kernel<double><<<grid, SELECT_THREADS, 0, s>>>((const double*)in, n_traj, ld, st, n_ranks, hist); break;
+            }
+            break;
+        case SODM_SELECT_PICK: {
+            if (!hist) return fail(SODM_EINVAL, "sodm_draws_select_phase: null histogram");
+            const int64_t warps = n_cells * n_ranks;
+            draws_pick_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, s>>>(st, n_ranks, n_cells, hist);
+            draws_advance_kernel<<<(unsigned)((n_cells + 127) / 128), 128, 0, s>>>(st, n_ranks, n_cells);
+            break;
+        }
+        case SODM_SELECT_DECODE: {
+            if (!out) return fail(SODM_EINVAL, "sodm_draws_select_phase: null output");
+            const unsigned g = (unsigned)((n_cells * n_ranks + 127) / 128);
+            switch (dtype) {
+                case SODM_I32: draws_decode_kernel<int32_t><<<g, 128, 0, s>>>(st, n_ranks, n_cells, out); break;
+                case SODM_F32: draws_decode_kernel<float><<<g, 128, 0, s>>>(st, n_ranks, n_cells, out); break;
+                default:       draws_decode_kernel<double><<<g, 128, 0, s>>>(st, n_ranks, n_cells, out); break;
+            }
+            break;
+        }
+        default: return fail(SODM_EINVAL, "sodm_draws_select_phase: unknown phase %d", phase);
     }
     SODM_CUDA_CHECK(cudaGetLastError());
     return SODM_OK;

@@ -344,3 +344,39 @@ def draws_order_stats(ens, ranks, dev=None, stream=None):
         _ffi.check(lib.sodm_draws_order_stats(ens.data_ptr(), _TORCH_DT[ens.dtype], n_cells, n_traj, ld, arr, len(part),
                                               out[lo:lo + len(part)].data_ptr(), _stream_ptr(stream)), lib)
     return out
+
+
+class SelectPhases:
+    """Order statistics of an ensemble SHARDED by trajectory (`sodm_draws_select_phase`): this object owns the per-cell
+    state of one search; `sharding.order_stats_sharded` drives the phases and all-reduces the tables in between."""
+
+    def __init__(self, ens, global_ranks, dev=None):
+        self.dev = dev or device()
+        self.lib = _ffi.load()
+        self.ens = ens
+        self.n_cells, self.n_traj, self.ld = _as_cells(ens) if ens.shape[-1] > 0 else (int(np.prod(ens.shape[:-1])), 0, 1)
+        self.ranks = [int(r) for r in global_ranks]
+        if not 1 <= len(self.ranks) <= _ffi.MAX_RANKS:
+            raise ValueError(f"between 1 and {_ffi.MAX_RANKS} ranks per search")
+        J, nc = len(self.ranks), self.n_cells
+        i64 = dict(dtype=torch.int64, device=self.dev)
+        self.lo, self.hi = torch.empty(nc, **i64), torch.empty(nc, **i64)
+        self.nan_flag = torch.zeros(nc, dtype=torch.int32, device=self.dev)
+        self.settled = torch.zeros(nc, dtype=torch.int32, device=self.dev)
+        self.prefix = torch.zeros((2, nc, J), **i64)
+        self.remaining = torch.tensor(self.ranks, **i64).repeat(nc, 1).contiguous()
+        self.hist = torch.zeros((nc, J, _ffi.SELECT_BINS), dtype=torch.int32, device=self.dev)
+        self.state = _ffi.SelectState(self.lo.data_ptr(), self.hi.data_ptr(), self.nan_flag.data_ptr(), self.settled.data_ptr(),
+                                      self.prefix.data_ptr(), self.remaining.data_ptr())
+        self.key_bits = 64 if ens.dtype == torch.float64 else 32
+
+    def run(self, phase, out=None, stream=None):
+        _ffi.check(self.lib.sodm_draws_select_phase(
+            int(phase), self.ens.data_ptr() if self.n_traj else None, _TORCH_DT[self.ens.dtype], self.n_cells, self.n_traj,
+            self.ld, len(self.ranks), C.byref(self.state), self.hist.data_ptr(), out.data_ptr() if out is not None else None,
+            _stream_ptr(stream)), self.lib)
+
+    def result(self):
+        out = torch.empty((len(self.ranks),) + tuple(self.ens.shape[:-1]), dtype=torch.float64, device=self.dev)
+        self.run(_ffi.SELECT_DECODE, out=out)
+        return out

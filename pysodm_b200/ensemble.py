@@ -44,8 +44,10 @@ def _lerp(a, b, t):
 class DeviceDataArray:
     """One state variable of a device-resident ensemble: CUDA tensor `[*state_dims, time, draws]`."""
 
-    def __init__(self, data, name, state_dims, coords, time_name, has_draws=True):
+    def __init__(self, data, name, state_dims, coords, time_name, n_global=None):
         self.data, self.name = data, name
+        # draws of ALL ranks when the ensemble is sharded by trajectory over a torch.distributed job (else the local count)
+        self.n_global = int(n_global) if n_global is not None else int(data.shape[-1])
         self.state_dims = list(state_dims)
         self.time_name = time_name
         self.coords = OrderedDict(coords)
@@ -60,11 +62,15 @@ class DeviceDataArray:
 
     @property
     def n_draws(self):
-        return int(self.data.shape[-1])
+        return self.n_global
+
+    @property
+    def sharded(self):
+        return self.n_global != int(self.data.shape[-1])
 
     @property
     def shape(self):
-        return tuple(int(self.data.shape[self._device_dims.index(d)]) for d in self.dims)
+        return tuple(self.n_global if d == "draws" else int(self.data.shape[self._device_dims.index(d)]) for d in self.dims)
 
     def __getitem__(self, key):
         if isinstance(key, str):
@@ -93,7 +99,7 @@ class DeviceDataArray:
                 coords[dim] = [labels[i] for i in np.asarray(idx).tolist()]
         state_dims = [d for d in self.state_dims if not (scalar and d == dim)]
         time_name = None if (scalar and dim == self.time_name) else self.time_name
-        return DeviceDataArray(data, self.name, state_dims, coords, time_name)
+        return DeviceDataArray(data, self.name, state_dims, coords, time_name, self.n_global)
 
     def isel(self, indexers=None, **kw):
         out = self
@@ -143,7 +149,8 @@ class DeviceDataArray:
     def mean(self, dim="draws"):
         if dim != "draws":
             raise NotImplementedError("device ensembles reduce over 'draws'")
-        s = engine.draws_sum(self._packed())
+        from . import sharding
+        s = sharding.sum_sharded(engine.draws_sum(self._packed()))
         return self._host_result(s.cpu().numpy() / self.n_draws)
 
     def quantile(self, q, dim="draws"):
@@ -157,7 +164,8 @@ class DeviceDataArray:
         n = self.n_draws
         plan = [_bracketing_ranks(n, v) for v in qs]
         ranks = sorted({r for lo, hi, _ in plan for r in (lo, hi)})
-        stats = engine.draws_order_stats(self._packed(), ranks).cpu().numpy()
+        from . import sharding
+        stats = sharding.order_stats_sharded(self._packed(), ranks).cpu().numpy()
         where = {r: i for i, r in enumerate(ranks)}
         out = np.stack([_lerp(stats[where[lo]], stats[where[hi]], g) for lo, hi, g in plan])
         if np.ndim(q) == 0:
@@ -167,7 +175,7 @@ class DeviceDataArray:
     # ---- full copy ---------------------------------------------------------------------------------------
     @property
     def values(self):
-        """Host ndarray in the reference's order `(draws, time, *state_dims)` (float64), through the layout kernel
+        """Host ndarray of the LOCAL draws in the reference's order `(draws, time, *state_dims)` (float64), through the layout kernel
         `sodm_to_draws_major` (the transpose the reference does with moveaxis + concat, base.py:1009-1010, :569-571)."""
         n_state = len(self.state_dims)
         shape = [int(x) for x in self.data.shape]
@@ -199,8 +207,9 @@ def _norm(v):
 class DeviceEnsemble:
     """All state variables of a device-resident ensemble over ONE buffer `[row][time][draws]`."""
 
-    def __init__(self, buffer, variables, dims_per_state, coords_per_state, time_name, time_coord, traj_id0=0):
-        self.buffer = buffer                       # CUDA tensor [n_rows, n_time, n_draws]
+    def __init__(self, buffer, variables, dims_per_state, coords_per_state, time_name, time_coord, traj_id0=0, n_global=None):
+        self.buffer = buffer                       # CUDA tensor [n_rows, n_time, n_local_draws]
+        self.n_global = int(n_global) if n_global is not None else int(buffer.shape[2])
         self.variables = list(variables)           # pipeline.Variable: name, first row, shape
         self.dims_per_state, self.coords_per_state = dims_per_state, coords_per_state
         self.time_name, self.time_coord = time_name, time_coord
@@ -212,11 +221,11 @@ class DeviceEnsemble:
             coords = OrderedDict([(time_name, list(time_coord))])
             for d, c in zip(dims_per_state[v.name], coords_per_state[v.name]):
                 coords[d] = list(c)
-            self.data_vars[v.name] = DeviceDataArray(view, v.name, dims_per_state[v.name], coords, time_name)
+            self.data_vars[v.name] = DeviceDataArray(view, v.name, dims_per_state[v.name], coords, time_name, self.n_global)
 
     @property
     def n_draws(self):
-        return int(self.buffer.shape[2])
+        return self.n_global
 
     def __getitem__(self, key):
         if key in self.data_vars:
@@ -242,7 +251,7 @@ class DeviceEnsemble:
         if tuple(buffer.shape) != tuple(self.buffer.shape):
             raise ValueError("buffer shape differs")
         return DeviceEnsemble(buffer, self.variables, self.dims_per_state, self.coords_per_state, self.time_name,
-                              self.time_coord, self.traj_id0)
+                              self.time_coord, self.traj_id0, self.n_global)
 
     def _host_dataset(self, arrays):
         if _xr is not None:
@@ -252,7 +261,8 @@ class DeviceEnsemble:
     def mean(self, dim="draws"):
         if dim != "draws":
             raise NotImplementedError("device ensembles reduce over 'draws'")
-        s = engine.draws_sum(self.buffer).cpu().numpy() / self.n_draws          # one launch for every variable
+        from . import sharding
+        s = sharding.sum_sharded(engine.draws_sum(self.buffer)).cpu().numpy() / self.n_draws       # one launch for every variable
         out = OrderedDict()
         for v in self.variables:
             block = s[v.r0:v.r0 + v.n_dim].reshape(*v.shape, s.shape[1])
@@ -266,7 +276,7 @@ class DeviceEnsemble:
         """Full host copy with the reference's dims and coords (`base.py:969-1042`)."""
         from .dataset import make_dataset
         arrays = OrderedDict((k, da.values) for k, da in self.data_vars.items())
-        n = self.n_draws
+        n = int(self.buffer.shape[2])
         if n == 1:
             arrays = OrderedDict((k, a[0]) for k, a in arrays.items())
         return make_dataset(arrays, self.dims_per_state, self.coords_per_state, self.time_name, self.time_coord, n)

@@ -30,7 +30,8 @@ def _raise_on_status(status, kind):
 
 def _apply(output, kind, param, seed, integer_result):
     import torch
-    seed = _seed(seed)
+    from .. import sharding
+    seed = sharding.agree_on(_seed(seed))
     if isinstance(output, DeviceEnsemble):
         buf = output.buffer
         out_dtype = buf.dtype if (integer_result or buf.dtype != torch.int32) else torch.float64

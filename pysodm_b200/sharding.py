@@ -19,6 +19,16 @@ def world():
     return 0, 1
 
 
+def agree_on(value):
+    """Rank 0's integer (a seed drawn from NumPy's global generator, say) on every rank."""
+    rank, ws = world()
+    if ws == 1:
+        return int(value)
+    box = [int(value)]
+    dist.broadcast_object_list(box, src=0)
+    return int(box[0])
+
+
 def shard_range(n_total, rank=None, world_size=None):
     """Contiguous [lo, hi) of `n_total` units owned by `rank`; the first n_total % G ranks get one extra unit."""
     if rank is None or world_size is None:
@@ -34,6 +44,9 @@ def all_gather_concat(local, n_total, axis=0):
     if ws == 1:
         return local
     t = local if isinstance(local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local))
+    origin = t.device
+    if dist.get_backend() == "gloo" and t.is_cuda:            # gloo collectives run on host memory
+        t = t.cpu()
     t = t.movedim(axis, 0).contiguous()
     sizes = [shard_range(n_total, r, ws)[1] - shard_range(n_total, r, ws)[0] for r in range(ws)]
     longest = max(sizes)
@@ -43,7 +56,7 @@ def all_gather_concat(local, n_total, axis=0):
     parts = [torch.empty_like(t) for _ in range(ws)]
     dist.all_gather(parts, t)
     out = torch.cat([p[:s] for p, s in zip(parts, sizes)]).movedim(0, axis)
-    return out if isinstance(local, torch.Tensor) else out.cpu().numpy()
+    return out.to(origin) if isinstance(local, torch.Tensor) else out.cpu().numpy()
 
 
 def batch_sharded(objective, thetas, **kw):
@@ -60,3 +73,48 @@ def batch_sharded(objective, thetas, **kw):
     if backend == "nccl":
         t = t.cuda()
     return all_gather_concat(t, thetas.shape[0]).cpu().numpy()
+
+
+# ---- reductions over draws of an ensemble sharded by trajectory --------------------------------------------------------
+def _all_reduce(t, op):
+    """In-place all-reduce of a (CUDA) tensor; gloo (CPU tests, single-GPU multi-process tests) goes through host memory."""
+    if dist.get_backend() == "gloo" and t.is_cuda:
+        h = t.cpu()
+        dist.all_reduce(h, op=op)
+        t.copy_(h)
+    else:
+        dist.all_reduce(t, op=op)
+    return t
+
+
+def sum_sharded(local_sum):
+    """Sum over ALL ranks' draws from the per-rank sums (`engine.draws_sum`); counts stay exact (FP64 of int64 sums)."""
+    rank, ws = world()
+    return local_sum if ws == 1 else _all_reduce(local_sum.clone(), dist.ReduceOp.SUM)
+
+
+def order_stats_sharded(ens_local, global_ranks):
+    """The global_ranks[j]-th smallest value (0-based, over the union of all ranks' draws) of every cell of an ensemble
+    whose trajectory axis is sharded over the ranks -> float64 [len(global_ranks), ...] on every rank.
+
+    Radix select in phases (`sodm_draws_select_phase`): the data stays where it is; per pass one all-reduce of the
+    per-cell histograms ([cells][ranks][2048] int32) -- the one real exchange on this path.  Single rank: the fused
+    kernel (`engine.draws_order_stats`)."""
+    from . import _ffi, engine
+    rank, ws = world()
+    if ws == 1:
+        return engine.draws_order_stats(ens_local, global_ranks)
+    outs = []
+    global_ranks = [int(r) for r in global_ranks]
+    for lo in range(0, len(global_ranks), _ffi.MAX_RANKS):
+        search = engine.SelectPhases(ens_local, global_ranks[lo:lo + _ffi.MAX_RANKS])
+        search.run(_ffi.SELECT_MINMAX)
+        _all_reduce(search.lo, dist.ReduceOp.MIN)
+        _all_reduce(search.hi, dist.ReduceOp.MAX)
+        _all_reduce(search.nan_flag, dist.ReduceOp.MAX)
+        for _ in range(-(-search.key_bits // 11)):
+            search.run(_ffi.SELECT_HISTOGRAM)
+            _all_reduce(search.hist, dist.ReduceOp.SUM)
+            search.run(_ffi.SELECT_PICK)
+        outs.append(search.result())
+    return torch.cat(outs)

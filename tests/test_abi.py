@@ -36,8 +36,8 @@ def test_struct_layout_matches_header():
     import subprocess
     import tempfile
     from pysodm_b200 import _ffi
-    src = ('#include <stdio.h>\n#include "sodm.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(sodm_model_info),'
-           ' sizeof(sodm_jump_args), sizeof(sodm_ode_args), sizeof(sodm_loglik_args), sizeof(sodm_noise_args)); return 0;}\n')
+    src = ('#include <stdio.h>\n#include "sodm.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(sodm_model_info),'
+           ' sizeof(sodm_jump_args), sizeof(sodm_ode_args), sizeof(sodm_loglik_args), sizeof(sodm_noise_args), sizeof(sodm_select_state)); return 0;}\n')
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
@@ -45,7 +45,7 @@ def test_struct_layout_matches_header():
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [C.sizeof(_ffi.ModelInfo), C.sizeof(_ffi.JumpArgs), C.sizeof(_ffi.OdeArgs),
-                     C.sizeof(_ffi.LoglikArgs), C.sizeof(_ffi.NoiseArgs)]
+                     C.sizeof(_ffi.LoglikArgs), C.sizeof(_ffi.NoiseArgs), C.sizeof(_ffi.SelectState)]
 
 
 def test_model_registry(lib):

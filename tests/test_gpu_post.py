@@ -237,3 +237,57 @@ def test_device_ensemble_ode_and_full_size_properties():
     assert np.all(np.diff(qv, axis=0) >= 0)
     mv = np.asarray(m["Im_inc"].values)
     assert np.all(qv[0] <= mv) and np.all(mv <= qv[-1])
+
+
+def _run_ranks(world, backend, path):
+    import socket
+    import subprocess
+    import sys
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = str(s.getsockname()[1])
+    worker = __file__.replace("test_gpu_post.py", "dist_post_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), str(world), port, backend, path], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+
+
+def test_sharded_ensemble_reduces_like_one_gpu(tmp_path):
+    """An ensemble sharded by trajectory over the ranks of a torch.distributed job: mean, quantiles (radix select in
+    phases with one all-reduce of the histograms per pass) and noise equal the single-process results bit for bit.
+    Runs with as many GPUs as the box has (NCCL when there are >= 2, else two ranks on one GPU over gloo)."""
+    import torch
+    from pysodm_b200 import tutorial_data as td, tutorial_models as tm
+    from pysodm_b200.optimization.utils import add_negative_binomial_noise
+    world = 2 if torch.cuda.device_count() < 3 else 3
+    backend = "nccl" if torch.cuda.device_count() >= world else "gloo"
+    path = str(tmp_path / "sharded.npz")
+    _run_ranks(world, backend, path)
+    got = np.load(path)
+    model = tm.JumpProcess_influenza_model(td.INFLUENZA_INITIAL_STATES, td.INFLUENZA_PARAMETERS,
+                                           coordinates={"age_group": td.AGE_GROUPS},
+                                           time_dependent_parameters={"N": td.influenza_contact_function})
+
+    def draw(parameters, N):
+        rng = np.random.default_rng(0)
+        parameters["beta"] = rng.uniform(0.015, 0.02, size=N)
+        return parameters
+    draw.vectorized = True
+    n = 5001
+    ens = model.sim(["2017-12-01", "2018-01-10"], N=n, tau=0.5, seed=21, output="device", draw_function=draw)
+    full = ens.to_dataset()
+    assert np.array_equal(got["full_S"], np.asarray(full["S"].values))                 # union of the shards == one GPU
+    assert np.array_equal(got["full_Im"], np.asarray(full["Im_inc"].values))
+    qs = [0.0, 0.025, 0.5, 0.975, 1.0]
+    for key, name in (("S", "S"), ("Im", "Im_inc")):
+        h = np.asarray(full[name].values)
+        assert np.array_equal(got["mean_" + key], h.mean(axis=0))
+        assert np.array_equal(got["q_" + key], np.quantile(h, qs, axis=0))
+    noisy = add_negative_binomial_noise(ens, 0.03, seed=5)
+    assert np.array_equal(got["full_noisy"], noisy["Im_inc"].values)                   # noise keyed by global draw id
+    assert np.array_equal(got["qn"], np.quantile(noisy["Im_inc"].values[:, :, 2], 0.9, axis=0))
+    e = np.asarray(full["E"].values) * 0.37 - 11.0
+    assert np.array_equal(got["qf"], np.quantile(e, [0.1, 0.66], axis=0))
+    assert np.allclose(got["mf"], e.mean(axis=0), rtol=1e-13)
