@@ -186,6 +186,7 @@ def run_gpu_arm(args):
             raise SystemExit("bench.py --gpus N with N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     dev = engine.device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"            # NCCL's version banner goes to STDOUT, which carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.n_traj
