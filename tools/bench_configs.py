@@ -69,7 +69,13 @@ def main():
 
     # C4: packed PFR nx = 25, RK45, t in [0, 8000] s, 1e5 draws of the 5 kinetic parameters; output = final profile
     n = 100_000
-    post = rng.normal(1.0, 0.03, size=(5, n)) * np.array([7.88e-04, 0.055, 2.64, 0.079, 0.418])[:, None]
+    # draws = posterior samples of the five kinetic parameters, rows picked with replacement; the reference's
+    # samples file exists only in the build container, so a synthetic posterior of the same size and spread stands in here
+    from pysodm_b200 import samples as sm
+    chain = rng.normal(1.0, 0.03, size=(10, 90, 5)) * np.array([7.88e-04, 0.055, 2.64, 0.079, 0.418])
+    posterior = sm.dump_samples(chain, {k: (1,) for k in ("Vf_Ks", "R_AS", "R_AW", "R_Es", "K_eq")})
+    drawn = sm.draw_function_from_samples(posterior, rng=rng)({}, N=n)
+    post = np.stack([drawn[k] for k in ("Vf_Ks", "R_AS", "R_AW", "R_Es", "K_eq")])
     var = ([4, 5, 6, 8, 7], torch.from_numpy(post).to(dev))
     out = torch.empty((200, 1, n), dtype=torch.float64, device=dev)
     ms = timed(lambda: engine.ode_run("packed_pfr_ode", td.pfr_flat_y0(25), td.pfr_flat_par(25), n, 0, 8001, model_arg=25,
