@@ -101,12 +101,14 @@ __host__ __device__ __forceinline__ float deviance_f(float k, float lam, float d
 
 // Poisson(lam), lam >= 0 finite.  lam < 10: sequential-search inversion; else Hoermann's PTRS ("The transformed
 // rejection method for generating Poisson random variables", 1993).
-__host__ __device__ inline double sample_poisson(ElementRng& rng, double lam) {
+// `seeded`: the first attempt uses the given words (the negative-binomial path hands over the unused bits of the block
+// its gamma variate came from, so that a typical element costs ONE Philox block); later attempts draw fresh pairs.
+__host__ __device__ inline double sample_poisson(ElementRng& rng, double lam, bool seeded = false, uint32_t wu0 = 0u, uint32_t wv0 = 0u) {
     if (lam == 0.0) return 0.0;
     const float lf = (float)lam;
     if (lam < 10.0) {
-        uint32_t wa, wb;
-        rng.pair(wa, wb);
+        uint32_t wa = wu0, wb;
+        if (!seeded) rng.pair(wa, wb);
         float f = fast_exp(-lf), u = u01f(wa), k = 0.0f;
         while (u > f && k < 1024.0f) {
             u -= f;
@@ -124,8 +126,8 @@ __host__ __device__ inline double sample_poisson(ElementRng& rng, double lam) {
     const float v_r = 0.9277f - fast_div(3.6224f, b - 2.0f);
     const bool wide = lam >= 4194304.0;                                      // FP32 no longer resolves k - lam
     for (int attempt = 0; attempt < 1000; ++attempt) {
-        uint32_t wu, wv;
-        rng.pair(wu, wv);
+        uint32_t wu = wu0, wv = wv0;
+        if (!seeded || attempt > 0) rng.pair(wu, wv);
         const float u = u01f(wu) - 0.5f, v = u01f(wv);
         const float us = 0.5f - fabsf(u);
         const float t = (fast_div(2.0f * a, us) + b) * u;
@@ -149,8 +151,11 @@ __host__ __device__ inline double sample_poisson(ElementRng& rng, double lam) {
     return floor(lam);        // unreachable in practice (acceptance > 0.86 per attempt)
 }
 
-// Gamma(shape, 1): Marsaglia & Tsang (2000) for shape >= 1, boosted by U^(1/shape) below.  One Philox block per attempt.
-__host__ __device__ inline float sample_standard_gamma(ElementRng& rng, float shape) {
+// Gamma(shape, 1): Marsaglia & Tsang (2000) for shape >= 1, boosted by U^(1/shape) below.  One Philox block per attempt:
+// (wr, wa) -> the normal variate, the top 24 bits of wu -> the acceptance uniform, wb -> the boost uniform (shape < 1).
+// `spare_u`, `spare_v` return words for ONE further attempt of a downstream sampler, built from bits this attempt did
+// not look at: wb as it is (shape >= 1), and the low bytes of wa, wu, wb (each consumer reads the top 24 bits of a word).
+__host__ __device__ inline float sample_standard_gamma(ElementRng& rng, float shape, bool& spare, uint32_t& spare_u, uint32_t& spare_v) {
     const float d = (shape < 1.0f ? shape + 1.0f : shape) - 1.0f / 3.0f;
     const float c = fast_div(1.0f, fast_sqrt(9.0f * d));
     for (int attempt = 0; attempt < 1000; ++attempt) {
@@ -164,8 +169,14 @@ __host__ __device__ inline float sample_standard_gamma(ElementRng& rng, float sh
         const float v = t * t * t;
         const float u = u01f(wu);
         const bool ok = u < 1.0f - 0.0331f * (z * z) * (z * z) || logf(u) < 0.5f * z * z + d * (1.0f - v + logf(v));
-        if (ok) return d * v * (shape < 1.0f ? powf(u01f(wb), 1.0f / shape) : 1.0f);
+        if (ok) {
+            spare = shape >= 1.0f;
+            spare_u = wb;
+            spare_v = ((wa & 0xffu) << 24) | ((wu & 0xffu) << 16) | ((wb & 0xffu) << 8);
+            return d * v * (shape < 1.0f ? powf(u01f(wb), 1.0f / shape) : 1.0f);
+        }
     }
+    spare = false;
     return d;
 }
 
@@ -179,7 +190,10 @@ __host__ __device__ __forceinline__ double count_noise(ElementRng& rng, double a
     if (x == 0.0) return 0.0;                                                // Poisson(0); NB with p = 1
     if (!NEGBIN) return sample_poisson(rng, x);
     const double n = 1.0 / alpha;
-    return sample_poisson(rng, (double)sample_standard_gamma(rng, (float)n) * (x / n));
+    bool spare;
+    uint32_t su, sv;
+    const float g = sample_standard_gamma(rng, (float)n, spare, su, sv);
+    return sample_poisson(rng, (double)g * (x / n), spare, su, sv);
 }
 
 __host__ __device__ __forceinline__ double gaussian_noise(bool relative, double sigma, double x, float z) {

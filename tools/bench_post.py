@@ -55,18 +55,17 @@ def main(n=1_000_000, path=None):
     f64 = torch.rand((28 * 8, n), dtype=torch.float64, device=dev)
     ms = timed(lambda: engine.draws_order_stats(f64, [n_lo, n_lo + 1, n_hi, n_hi + 1]))
     res["order_stats_f64_224_cells"] = {"ms": ms, "passes": 6, "GBps_six_reads": 6 * f64.numel() * 8 / ms / 1e6}
-    # the reference's host path beside it, on a bounded sample: NumPy on `cells` columns of the same ensemble
+    # the reference's host path beside it, on a bounded sample: the NumPy calls of optimization/utils.py:30,64,91-92 and
+    # of xarray's mean / quantile, on `cells` columns of the same ensemble
     import time
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    from oracle import post
     cells = 16
     sample = ens[24, :cells].cpu().numpy().astype(np.float64)                 # Im_inc of one age group, 16 dates x n draws
     cpu = {"sample": f"{cells} cells x {n} draws (float64, as the reference holds them), one host thread"}
-    for name, fn in (("noise_negative_binomial", lambda: post.add_negative_binomial_noise(sample, 0.03)),
-                     ("noise_poisson", lambda: post.add_poisson_noise(sample)),
-                     ("noise_gaussian_relative", lambda: post.add_gaussian_noise(sample, 0.04, True)),
-                     ("mean", lambda: post.mean_over_draws(sample, axis=1)),
-                     ("quantile_q025_q975", lambda: post.quantile_over_draws(sample, [0.025, 0.975], axis=1))):
+    for name, fn in (("noise_negative_binomial", lambda: np.random.negative_binomial(1 / 0.03, (1 / 0.03) / (sample + 1 / 0.03))),
+                     ("noise_poisson", lambda: np.random.poisson(sample)),
+                     ("noise_gaussian_relative", lambda: np.random.normal(sample, np.abs(0.04 * sample))),
+                     ("mean", lambda: np.mean(sample, axis=1)),
+                     ("quantile_q025_q975", lambda: np.quantile(sample, [0.025, 0.975], axis=1))):
         t0 = time.perf_counter()
         fn()
         dt = time.perf_counter() - t0
