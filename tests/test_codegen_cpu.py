@@ -220,3 +220,50 @@ def test_three_exits_and_bookkeeping_of_a_new_model():
         T[s][i][e] = 1
         new = gm.SEIRD.apply_transitionings(0.0, 1.0, T, **kw, **model.parameters)
         assert np.array_equal(yy, np.concatenate([np.ravel(v) for v in new]).astype(np.int32)), ch
+
+
+def test_random_numpy_expressions_translate_exactly():
+    """Fuzz: random compositions of the NumPy idioms model functions use (broadcasting, slices, matmul, reductions,
+    stacking, ufuncs, branches) -- the compiled functor, evaluated on the host, agrees with NumPy to rounding."""
+    import ctypes as C
+    rng = np.random.default_rng(123)
+    n = 4
+
+    def build(seed):
+        r = np.random.default_rng(seed)
+        M = r.uniform(0.5, 2.0, size=(n, n))
+        w = r.uniform(0.1, 1.0, size=n)
+        k1, k2, k3 = r.integers(0, 6, size=3)
+
+        def integrate(t, A, B, s, p, q):
+            tot = A + B + s
+            x = [A / tot, np.sqrt(A * B + 1.0), np.exp(-0.1 * A) * B, (M @ A) / np.sum(B), A[::-1] * w, np.tanh(0.01 * (A - B))][k1]
+            y = [np.concatenate([A[1:], A[:1]]) - A, np.cumsum(B)[-1] * np.ones(n), np.stack([A, B]).sum(axis=0) * q,
+                 np.where(A > B, A - B, 0.5 * (B - A)), np.maximum(A, 2.0 * B) - np.minimum(A, B), (A ** 2 + p) / (1.0 + B)][k2]
+            if t < 3.0:
+                z = p * s
+            elif s > 1.0 and q < 5.0:
+                z = np.log1p(s) + np.dot(w, x)
+            else:
+                z = -s / [1.0, 2.0, q][k3 % 3]
+            dA = -p * x + y * 0.01
+            dB = p * x - q * B * 0.001 + np.abs(np.sin(0.3 * t))
+            return dA, dB, z - 0.1 * s
+        return integrate
+    shapes = {"A": (n,), "B": (n,), "s": ()}
+    pars = {"p": (), "q": ()}
+    for seed in range(12):
+        fn = build(seed)
+        src, n_state, n_param = codegen.ode_source(fn, shapes, pars)
+        plug = plugin.compile_source(src, {"n_state": n_state})
+        host = plug.lib.sodm_plugin_host_rhs
+        host.restype, host.argtypes = None, [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        for _ in range(6):
+            A, B = rng.uniform(0.5, 20, size=n), rng.uniform(0.5, 20, size=n)
+            s, p, q, t = rng.uniform(0.2, 3), rng.uniform(0.1, 1), rng.uniform(0.5, 8), rng.uniform(0, 6)
+            y = np.concatenate([A, B, [s]])
+            par = np.array([p, q, 0.0])
+            dy = np.empty(n_state)
+            host(float(t), y.ctypes.data, par.ctypes.data, dy.ctypes.data)
+            want = np.concatenate([np.ravel(v) for v in fn(t, A, B, s, p, q)])
+            np.testing.assert_allclose(dy, want, rtol=1e-12, atol=1e-13, err_msg=f"seed {seed}")
