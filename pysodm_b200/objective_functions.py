@@ -314,20 +314,27 @@ class log_posterior_probability:
             lp = lp + np.where(above | below, -np.inf, 0.0)
         model = self.model
         dev = engine.device(device)
+        kw = self.simulation_kwargs
+        time_unit = kw.get("time_unit", "D")
+        if getattr(model, "_generated", False) and model._kind == "ode" and model.time_dependent_parameters:
+            # an ODE's time-dependent parameter functions are translated per time mode (numbers / dates), base.py
+            dated = self.time_index == "date"
+            model._bind_generated_functor(TIME_UNIT_US[time_unit] if dated else None, [self.start_sim if dated else None])
         # parameter vector -> flat device parameter elements
         par, _, y0, _ = model._collect_draws(1, None, {})
+        if "__t0__" in model._param_offsets:
+            from .codegen import date_to_units
+            par[model._param_offsets["__t0__"][0]] = date_to_units(self.start_sim, model._time_unit_us)
         var, col = {}, 0
         for name, size in zip(self.parameters_names, self._sizes):
             if name not in model._param_offsets:
                 raise NotImplementedError(f"calibrated parameter '{name}' is not a parameter of the device functor")
-            if name in (model.time_dependent_parameters or {}):
+            if name in model._spec.tdpf_params:              # tabulated per step (jump processes): no per-particle value
                 raise NotImplementedError(f"calibrated parameter '{name}' is time dependent")
             off = model._param_offsets[name][0]
             for e in range(size):
                 var[off + e] = np.ascontiguousarray(thetas[:, col + e], dtype=np.float64)
             col += size
-        kw = self.simulation_kwargs
-        time_unit = kw.get("time_unit", "D")
         if self.time_index == "date":
             unit = TIME_UNIT_US[time_unit]
             t0, t1 = 0, int(np.ceil((self.end_sim - self.start_sim).total_seconds() * 1e6 / unit))

@@ -180,3 +180,26 @@ def test_ode_time_dependent_parameter_functions(golden):
     # the same model on numeric time is a different translation (dates cannot be compared with numbers)
     with pytest.raises(NotImplementedError):
         ramp.sim(120)
+
+
+def test_log_posterior_of_a_generated_ode_with_a_time_dependent_parameter():
+    """`log_posterior_probability.batch` on a translated model: one launch for all thetas equals sim + the oracle's
+    likelihood theta by theta (dates as time index, a date-valued TDPF parameter, calibrated beta and gamma)."""
+    import pandas as pd
+    from oracle import loglik as oll
+    from pysodm_b200.objective_functions import ll_poisson, log_posterior_probability
+    _, date, _ = gm.make_tdpf_models()
+    dates = pd.date_range("2020-01-10", "2020-04-01", freq="7D")
+    data = pd.Series(np.linspace(5, 400, len(dates)).round(), index=pd.Index(dates, name="date"))
+    lpp = log_posterior_probability(date, ["beta", "gamma"], [(0.1, 1.0), (1.0, 10.0)], [data], ["I"], [ll_poisson], [[]],
+                                    start_sim=pd.Timestamp("2020-01-01"))
+    thetas = np.array([[0.3, 5.0], [0.35, 5.0], [0.4, 4.0], [0.5, 6.5]])
+    lp = lpp.batch(thetas.copy())
+    want = []
+    for b, g_ in thetas:
+        date.parameters.update(beta=b, gamma=g_)
+        out = date.sim(["2020-01-01", "2020-03-27"])               # the objective simulates up to the last data point
+        y = np.stack([out[s].values for s in ("S", "I", "R")])
+        t_data = np.array([(d - pd.Timestamp("2020-01-01")).days for d in dates], dtype=np.float64)
+        want.append(oll.log_likelihood("poisson", y, 0.0, [[1]], t_data, data.to_numpy(), None))
+    np.testing.assert_allclose(lp, want, rtol=1e-9)
