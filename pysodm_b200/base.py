@@ -140,7 +140,12 @@ class _DeviceBackedModel:
             return None
         if not self.device_model:
             self._generated = True
-            return self._bind_generated_functor()
+            try:
+                return self._bind_generated_functor()
+            except NotImplementedError as exc:
+                if "date" not in str(exc):
+                    raise
+                return None                                  # the functions work on dates: translated at sim(), given dates
         spec = registry.get(self.device_model)
         if spec.kind != self._kind:
             raise TypeError(f"device functor '{spec.name}' is a {spec.kind} model, {type(self).__name__} is a {self._kind} model")
@@ -190,8 +195,10 @@ class _DeviceBackedModel:
                 if callable(value) or isinstance(value, (str, dict)):
                     raise NotImplementedError(f"parameter '{name}' is not numeric; generated device models take scalars, arrays and dates")
                 shapes[name] = tuple(np.shape(np.asarray(value, dtype=np.float64)))
-            if date_unit_us is not None and self._kind == "ode":
+            if date_unit_us is not None:                      # hidden: absolute time of t = 0 (before the tabulated TDPF block)
+                tail = [(k, shapes.pop(k)) for k in list(shapes) if k in tab]
                 shapes["__t0__"] = ()
+                shapes.update(tail)
             self._date_params = date_params
             state_shapes = OrderedDict((k, tuple(self.state_shapes[k])) for k in self.states_names)
             n_par = sum(int(np.prod(v)) if v else 1 for v in shapes.values())
@@ -208,7 +215,8 @@ class _DeviceBackedModel:
                                         tdpf=spec_t, model_params=decl, date_unit_us=date_unit_us, date_params=date_params)
             else:
                 plug = plugin.build_jump(self.compute_rates, self.apply_transitionings, state_shapes, shapes, tab,
-                                         self.initial_states, self.parameters, origin)
+                                         self.initial_states, self.parameters, origin, date_unit_us=date_unit_us,
+                                         date_params=date_params, start_date=date_range[0] if date_range else None)
             spec = registry.DeviceSpec(plug.name, self._kind, list(state_shapes.items()), list(shapes.items()), tdpf_params=tab)
             self._generated_cache[key] = (plug, spec, shapes, date_params)
         self.device_model = plug
@@ -439,9 +447,19 @@ class JumpProcess(_DeviceBackedModel):
         if draw_function:
             validation.draw_function(draw_function, draw_function_kwargs, copy.deepcopy(self.parameters),
                                      self.initial_states_function, self.state_shapes, self.initial_states_function_args)
+        if self._generated:
+            # model functions that use the time see dates when sim runs over dates (base.py:365-373): one translation each
+            want = validation.TIME_UNIT_US[time_unit] if date_range[0] is not None else None
+            plug = self.device_model
+            mode_sensitive = plug is None or plug.layout.get("uses_time") or self._date_params or self._time_unit_us is not None
+            if mode_sensitive and (plug is None or self._time_unit_us != want):
+                self._bind_generated_functor(want, date_range)
         saved = copy.deepcopy(self.parameters)
         try:
             par, var, y0, _ = self._collect_draws(N, draw_function, draw_function_kwargs)
+            if "__t0__" in self._param_offsets:
+                from .codegen import date_to_units
+                par[self._param_offsets["__t0__"][0]] = date_to_units(date_range[0], self._time_unit_us)
             t0, t1 = time
             n_out = int(t1 - t0 + 1)
             dev = engine.device(device)

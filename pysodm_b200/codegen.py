@@ -599,19 +599,32 @@ def trace_ode(integrate, state_shapes, param_shapes, tdpf=(), model_params=None,
     return g, explore(g, run)
 
 
-def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes):
+def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes, date_unit_us=None, date_params=()):
     """-> dict with the rate graph (per state: list of transitions, each a flat list of expressions) and the bookkeeping
     graph (new value per flat state element as integer expressions of states `y` and transitionings `T`)."""
     state_sizes = {k: (int(np.prod(s)) if s else 1) for k, s in state_shapes.items()}
     # ---- rates: floating point
     g = Graph()
+    g.unit_us = date_unit_us
     fn = _retarget(compute_rates, g)
     t = g.leaf(("t", 0), "f")
 
     structure = []                                   # [(state, number of transitions)] in rate-dict order
 
+    def model_inputs(graph, kind_y, tt):
+        """(time argument, keyword arguments) as the reference passes them: a date when sim runs over dates."""
+        kw = _inputs(graph, state_shapes, param_shapes, kind_y)
+        when = tt
+        if date_unit_us is not None:
+            when = SymDate(tt + kw["__t0__"], date_unit_us)
+            for k in date_params:
+                kw[k] = SymDate(kw[k], date_unit_us)
+        kw.pop("__t0__", None)
+        return when, kw
+
     def run_rates():
-        rates = fn(t, **_inputs(g, state_shapes, param_shapes, "f"))
+        when, kw = model_inputs(g, "f", t)
+        rates = fn(when, **kw)
         if not isinstance(rates, dict):
             raise TraceError("compute_rates must return a dict {state: [rate arrays]}")
         shape_now, flat = [], []
@@ -644,6 +657,7 @@ def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes):
         channels[name] = per
     # ---- bookkeeping: integers
     g2 = Graph()
+    g2.unit_us = date_unit_us
     fn2 = _retarget(apply_transitionings, g2)
     t2, tau2 = g2.leaf(("t", 0), "f"), g2.leaf(("tau", 0), "f")
     T, c = {}, 0
@@ -658,7 +672,8 @@ def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes):
                 c += 1
             T[name].append(arr.reshape(tuple(state_shapes[name])) if state_shapes[name] else arr[0])
     def run_apply():
-        new = fn2(t2, tau2, T, **_inputs(g2, state_shapes, param_shapes, "i"))
+        when2, kw2 = model_inputs(g2, "i", t2)
+        new = fn2(when2, tau2, T, **kw2)
         if not isinstance(new, (tuple, list)):
             new = (new,)
         return _collect(new, state_shapes, "apply_transitionings")
@@ -788,6 +803,22 @@ def _reject_time(graph, outputs, what):
             stack.extend(args)
 
 
+def _uses_input(graph, outputs, prefix):
+    seen, stack = set(), [o.i for o in outputs]
+    while stack:
+        i = stack.pop()
+        if i in seen:
+            continue
+        seen.add(i)
+        op, args, _ = graph.nodes[i]
+        if op == "in":
+            if args[0][0] == prefix:
+                return True
+        elif op != "const":
+            stack.extend(args)
+    return False
+
+
 def ode_source(integrate, state_shapes, param_shapes, origin="", **trace_kw):
     """C++ translation unit of a plugin holding the ODE `integrate`.  -> (source, n_state, n_param)."""
     g, outs = trace_ode(integrate, state_shapes, param_shapes, **trace_kw)
@@ -822,7 +853,8 @@ extern "C" void sodm_plugin_host_rhs(double t, const double* y, const double* pa
     return src, n_state, n_param
 
 
-def jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes, tdpf_params=(), origin=""):
+def jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes, tdpf_params=(), origin="",
+                date_unit_us=None, date_params=()):
     """C++ translation unit of a plugin holding a jump process.  `param_shapes` must list the time-dependent parameters
     LAST (they are read from the per-step table instead of the parameter vector).
     -> (source, layout) with layout = dict(n_state, n_param, n_channel, n_draw, tdpf_offset, tdpf_count, slot_of)."""
@@ -830,7 +862,7 @@ def jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes,
     n_tdpf = len(tdpf_params)
     if n_tdpf and names[-n_tdpf:] != list(tdpf_params):
         raise ValueError("time-dependent parameters must come last in the flat parameter order")
-    tr = trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes)
+    tr = trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes, date_unit_us, date_params)
     sizes = {k: (int(np.prod(s)) if s else 1) for k, s in param_shapes.items()}
     n_param = sum(sizes.values())
     tdpf_count = sum(sizes[k] for k in tdpf_params)
@@ -878,11 +910,13 @@ def jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes,
     if n_draw == 0:
         raise TraceError("apply_transitionings reads none of the transitionings")
     all_rates = [x for name, per in tr["channels"].items() for flat in per for x in flat]
-    _reject_time(g, all_rates, "compute_rates")
+    uses_time = _uses_input(g, all_rates, "t")       # e.g. seasonal forcing written into compute_rates
 
     def leaf_f(name):
         if name[0] == "y":
             return f"(float)y[{name[1]}]"
+        if name[0] == "t":
+            return "(float)t"
         if name[0] == "par":
             e = name[1]
             return f"tab[{e - tdpf_offset}]" if tdpf_count and e >= tdpf_offset else f"pre.par[{e}]"
@@ -891,6 +925,8 @@ def jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes,
     def leaf_d(name):
         if name[0] == "y":
             return f"(double)y[{name[1]}]"
+        if name[0] == "t":
+            return "t"
         if name[0] == "par":
             return f"par[{name[1]}]"
         raise TraceError(f"unexpected input {name}")
@@ -940,6 +976,7 @@ struct GenModel {{
     static constexpr int NS = {n_state}, NPAR = {npar_arr}, NCH = {tr['n_channel']}, TDPF_OFFSET = {tdpf_offset}, TDPF_COUNT = {tdpf_count};
     static constexpr int NDRAW = {n_draw};
     static constexpr uint64_t DEP_MASK = {dep_mask}ull;
+    static constexpr bool USES_TIME = {'true' if uses_time else 'false'};
     struct Pre {{ float par[{npar_arr}]; }};
     __host__ __device__ static Pre prepare(const double* par, float, bool) {{
         Pre pre;
@@ -949,8 +986,8 @@ struct GenModel {{
     }}
     // rates in FP32 as in the hand-written functors; law of the draws: jump_models.cuh header (reference base.py:283-348)
     template <class W>
-    __host__ __device__ static void propose(const int* y, const Pre& pre, const float* tab, float tau, bool quirk, W& w) {{
-        (void)tab; (void)pre;
+    __host__ __device__ static void propose(const int* y, const Pre& pre, const float* tab, float tau, bool quirk, W& w, double t = 0.0) {{
+        (void)tab; (void)pre; (void)t;
 {_indent(f_lines)}
 {_indent(put)}
     }}
@@ -962,6 +999,7 @@ struct GenModel {{
     }}
     __host__ __device__ static void propensities(const int* y, const double* par, double* a) {{
         (void)par;
+        const double t = 0.0; (void)t;                 // SSA is refused for models whose rates use the time (supports_ssa = 0)
 {_indent(d_lines)}
 {_indent(prop)}
     }}
@@ -984,10 +1022,10 @@ struct HostList {{
     __host__ __device__ int get(int d) const {{ return n[d]; }}
 }};
 }}
-extern "C" void sodm_plugin_host_propose(const int* y, const double* par, const float* tab, double tau, int quirk, int* n, float* p) {{
+extern "C" void sodm_plugin_host_propose(const int* y, const double* par, const float* tab, double tau, int quirk, double t, int* n, float* p) {{
     HostList w;
     const auto pre = ::sodm::GenModel::prepare(par, (float)tau, quirk != 0);
-    ::sodm::GenModel::propose(y, pre, tab, (float)tau, quirk != 0, w);
+    ::sodm::GenModel::propose(y, pre, tab, (float)tau, quirk != 0, w, t);
     for (int d = 0; d < {n_draw}; ++d) {{ n[d] = w.n[d]; p[d] = w.p[d]; }}
 }}
 extern "C" void sodm_plugin_host_apply(int* y, const int* draws) {{
@@ -1000,5 +1038,5 @@ extern "C" void sodm_plugin_host_fire(int* y, int ch) {{ ::sodm::GenModel::fire(
 """
     layout = {"n_state": n_state, "n_param": n_param, "n_channel": tr["n_channel"], "n_draw": n_draw,
               "tdpf_offset": tdpf_offset, "tdpf_count": tdpf_count, "slot_of": slot_of, "groups": groups,
-              "channel_slots": tr["slots"], "dep_mask": dep_mask}
+              "channel_slots": tr["slots"], "dep_mask": dep_mask, "uses_time": uses_time}
     return src, layout

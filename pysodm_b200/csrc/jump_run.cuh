@@ -409,6 +409,11 @@ __host__ __device__ __forceinline__ void sample_worklist_walk(WalkRng& rng, Work
     }
 }
 
+// A functor whose rates depend on the time itself (generated models with seasonal forcing, say) declares
+// `static constexpr bool USES_TIME = true` and takes the step's start time as a last argument of `propose`.
+template <class M, class = void> struct functor_uses_time { static constexpr bool value = false; };
+template <class M> struct functor_uses_time<M, decltype((void)M::USES_TIME)> { static constexpr bool value = M::USES_TIME; };
+
 // One trajectory per lane.  `active` = the lane owns a trajectory; the remaining lanes of a partially filled warp
 // still take part in the warp-cooperative sampling (they own no items) but neither load nor store.
 template <class M, typename OutT, bool ALIGNED, bool COOP>
@@ -447,7 +452,8 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
             for (int s = 0; s < M::NS; ++s) y_old[s] = y[s];
         }
         const float* tab = M::TDPF_COUNT ? table + (int64_t)L.tdpf_index[k] * M::TDPF_COUNT : table;
-        M::propose(y, pre, tab, tau, quirk, w);
+        if constexpr (functor_uses_time<M>::value) M::propose(y, pre, tab, tau, quirk, w, ALIGNED ? L.t0 + (double)k * L.tau : t);
+        else M::propose(y, pre, tab, tau, quirk, w);
         key.step = (uint32_t)k;
         if constexpr (COOP) sample_worklist_coop<M::NDRAW, (uint64_t)M::DEP_MASK>(key, w, st);
         else sample_worklist_walk<M::NDRAW, (uint64_t)M::DEP_MASK>(rng, w, st);

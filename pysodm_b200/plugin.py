@@ -139,46 +139,64 @@ def build_ode(integrate, state_shapes, param_shapes, origin="", reference=None, 
 
 
 def build_jump(compute_rates, apply_transitionings, state_shapes, param_shapes, tdpf_params, example_states,
-               example_params, origin=""):
-    source, layout = codegen.jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes, tdpf_params, origin)
+               example_params, origin="", date_unit_us=None, date_params=(), start_date=None):
+    """`example_params`: {name: value} of every entry of `param_shapes` except the hidden `__t0__`; in date mode
+    (`date_unit_us`) the model functions see dates: `start_date` is the date of t = 0 used by the self-check."""
+    source, layout = codegen.jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes, tdpf_params, origin,
+                                         date_unit_us=date_unit_us, date_params=date_params)
     plug = compile_source(source, layout)
     lib = plug.lib
     lib.sodm_plugin_host_propose.restype = None
-    lib.sodm_plugin_host_propose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    lib.sodm_plugin_host_propose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_void_p,
+                                             C.c_void_p]
     lib.sodm_plugin_host_apply.restype = None
     lib.sodm_plugin_host_apply.argtypes = [C.c_void_p, C.c_void_p]
     lib.sodm_plugin_host_propensities.restype = None
     lib.sodm_plugin_host_propensities.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sodm_plugin_host_fire.restype = None
     lib.sodm_plugin_host_fire.argtypes = [C.c_void_p, C.c_int]
-    verify_jump(plug, compute_rates, apply_transitionings, state_shapes, param_shapes, example_states, example_params)
+    verify_jump(plug, compute_rates, apply_transitionings, state_shapes, param_shapes, example_states, example_params,
+                date_unit_us=date_unit_us, date_params=date_params, start_date=start_date)
     return plug
 
 
-def host_propose(plug, y, par, tau, quirk=True):
-    """(n[NDRAW], p[NDRAW]) of one tau-leap step as the generated functor lists them, evaluated on the host."""
+def host_propose(plug, y, par, tau, quirk=True, t=0.0):
+    """(n[NDRAW], p[NDRAW]) of one tau-leap step at time t as the generated functor lists them, evaluated on the host."""
     lay = plug.layout
     y_i = np.ascontiguousarray(y, dtype=np.int32)
     par_d = np.concatenate([np.asarray(par, dtype=np.float64), np.zeros(1)])
     tab = np.ascontiguousarray(par_d[lay["tdpf_offset"]:lay["tdpf_offset"] + max(lay["tdpf_count"], 1)], dtype=np.float32)
     n = np.empty(lay["n_draw"], dtype=np.int32)
     p = np.empty(lay["n_draw"], dtype=np.float32)
-    plug.lib.sodm_plugin_host_propose(y_i.ctypes.data, par_d.ctypes.data, tab.ctypes.data, float(tau), int(quirk),
+    plug.lib.sodm_plugin_host_propose(y_i.ctypes.data, par_d.ctypes.data, tab.ctypes.data, float(tau), int(quirk), float(t),
                                       n.ctypes.data, p.ctypes.data)
     return n, p
 
 
-def verify_jump(plug, compute_rates, apply_transitionings, state_shapes, param_shapes, states, params, tau=0.5):
-    """One step's probabilities and one random bookkeeping update, generated functor vs the Python functions."""
+def verify_jump(plug, compute_rates, apply_transitionings, state_shapes, param_shapes, states, params, tau=0.5,
+                date_unit_us=None, date_params=(), start_date=None, t=3.5):
+    """One step's probabilities (at time t) and one random bookkeeping update, generated functor vs the Python functions."""
     lay = plug.layout
     rates_fn = codegen._python_function(compute_rates)
     apply_fn = codegen._python_function(apply_transitionings)
     kw = {k: np.asarray(states[k], dtype=np.float64) for k in state_shapes}
-    kw.update({k: params[k] for k in param_shapes})
+    kw.update({k: params[k] for k in param_shapes if k != "__t0__"})
+    when = t
+    parts = []
+    for k, shape in param_shapes.items():
+        if k == "__t0__":
+            parts.append(np.array([codegen.date_to_units(start_date, date_unit_us)]))
+        elif k in date_params:
+            parts.append(np.array([codegen.date_to_units(params[k], date_unit_us)]))
+        else:
+            parts.append(np.ravel(np.asarray(params[k], dtype=np.float64)))
+    par = np.concatenate(parts) if parts else np.zeros(0)
+    if date_unit_us is not None:
+        from datetime import timedelta
+        when = start_date + timedelta(microseconds=t * date_unit_us)
     y = _flat(states, state_shapes)
-    par = _flat(params, param_shapes)
-    rates = rates_fn(0.0, **kw)
-    n, p = host_propose(plug, y, par, tau, quirk=True)
+    rates = rates_fn(when, **kw)
+    n, p = host_propose(plug, y, par, tau, quirk=True, t=t)
     # expected conditional probabilities (reference law with the stay-probability quirk, base.py:336-346)
     for name, e, m, drawn, first in lay["groups"]:
         r = [float(_shaped(rates[name][i], state_shapes[name])[e]) for i in range(m)]
@@ -203,7 +221,7 @@ def verify_jump(plug, compute_rates, apply_transitionings, state_shapes, param_s
                     arr[e] = rng.integers(0, 50)
                     draws[lay["slot_of"][c]] = int(arr[e])
             T[name].append(arr.reshape(tuple(state_shapes[name])) if state_shapes[name] else arr[0])
-    want = apply_fn(0.0, tau, T, **kw)
+    want = apply_fn(when, tau, T, **kw)
     want = np.concatenate([_shaped(w, s) for w, s in zip(want, state_shapes.values())])
     y_i = np.ascontiguousarray(y, dtype=np.int32)
     plug.lib.sodm_plugin_host_apply(y_i.ctypes.data, draws.ctypes.data)

@@ -151,3 +151,27 @@ def make_tdpf_models():
                    time_dependent_parameters={"beta": tdpf_lower_infectivity})
     c = tm.ODE_SIR(y0, {"beta": 0.35, "gamma": 5, "ramp_days": 14.0}, time_dependent_parameters={"beta": tdpf_ramp})
     return a, b, c
+
+
+class SeasonalSIR(JumpProcess):
+    """Seasonal forcing written INTO compute_rates (uses `t`), plus a lockdown between two dates when run over dates."""
+    states = ['S', 'I', 'R']
+    parameters = ['beta', 'gamma', 'amp']
+
+    @staticmethod
+    def compute_rates(t, S, I, R, beta, gamma, amp):
+        if isinstance(t, (int, float)) or not hasattr(t, 'abs') and not hasattr(t, 'year'):
+            season = 1 + amp * np.cos(2 * np.pi * t / 50.0)
+        else:
+            season = 1.0
+            if t >= pd.Timestamp('2021-02-01') and t < pd.Timestamp('2021-02-20'):
+                season = 1 - amp
+        return {'S': [beta * season * I / (S + I + R)], 'I': [gamma]}
+
+    @staticmethod
+    def apply_transitionings(t, tau, transitionings, S, I, R, beta, gamma, amp):
+        return S - transitionings['S'][0], I + transitionings['S'][0] - transitionings['I'][0], R + transitionings['I'][0]
+
+
+def make_seasonal():
+    return SeasonalSIR({'S': 99000, 'I': 1000}, {'beta': 0.5, 'gamma': 0.2, 'amp': 0.6})

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import cases
+import pandas as pd
 import gen_models as gm
 from oracle import jump as ojump
 from oracle import models as omodels
@@ -203,3 +204,45 @@ def test_log_posterior_of_a_generated_ode_with_a_time_dependent_parameter():
         t_data = np.array([(d - pd.Timestamp("2020-01-01")).days for d in dates], dtype=np.float64)
         want.append(oll.log_likelihood("poisson", y, 0.0, [[1]], t_data, data.to_numpy(), None))
     np.testing.assert_allclose(lp, want, rtol=1e-9)
+
+
+def test_rates_that_use_the_time_itself():
+    """`compute_rates(t, ...)` with seasonal forcing in `t` (numeric time) and a date window (date time): the step's start
+    time reaches the generated functor; parity against the oracle's tau-leap with the same Python function."""
+    from datetime import datetime, timedelta
+    model = gm.make_seasonal()
+    n = 12000
+    out = model.sim(100, N=n, tau=0.5, seed=3, output_dtype="int32")
+
+    class Oracle(omodels.JumpModelSpec):
+        name, states, params = "seasonal", (("S", ()), ("I", ()), ("R", ())), (("beta", ()), ("gamma", ()), ("amp", ()))
+        transitions = (("S", 1), ("I", 1))
+        when = staticmethod(lambda t: t)
+
+        @classmethod
+        def rates(cls, t, y, p):
+            r = gm.SeasonalSIR.compute_rates(cls.when(t), y["S"], y["I"], y["R"], p["beta"], p["gamma"], p["amp"])
+            return {"S": [np.asarray(r["S"][0], dtype=np.float64)], "I": [r["I"][0] * np.ones(np.shape(y["I"]))]}
+
+        @staticmethod
+        def apply(t, tau, T, y, p):
+            return {"S": y["S"] - T["S"][0], "I": y["I"] + T["S"][0] - T["I"][0], "R": y["R"] + T["I"][0]}
+    par = {"beta": 0.5, "gamma": 0.2, "amp": 0.6}
+    ref = ojump.tau_leap_ensemble(Oracle, np.array([99000.0, 1000.0, 0.0]), par, 0, 100, 0.5, n, seed=4)
+    times = [5, 20, 40, 70, 100]
+    mine = np.stack([np.moveaxis(out[s].values, 0, -1) for s in ("S", "I", "R")])          # [3, 101, n]
+    cases.assert_ks_ok(cases.ks_pvalues(mine[:, times], np.transpose(ref[:, :, times], (1, 2, 0))), "seasonal SIR (numeric time)")
+    # the forcing matters: without it the epidemic is visibly different
+    flat = gm.SeasonalSIR({'S': 99000, 'I': 1000}, {'beta': 0.5, 'gamma': 0.2, 'amp': 0.0}).sim(100, N=n, tau=0.5, seed=3, output_dtype="int32")
+    assert abs(np.median(flat["R"].values[:, 40]) - np.median(out["R"].values[:, 40])) > 2000
+    with pytest.raises(Exception, match="SSA"):
+        model.sim(10, N=4, method="SSA")
+    # over dates the same class takes the other branch of its compute_rates (a lockdown window between two dates)
+    start = datetime(2021, 1, 1)
+    dated = model.sim(["2021-01-01", "2021-04-11"], N=n, tau=0.5, seed=5, output_dtype="int32")
+    Oracle.when = staticmethod(lambda t: pd.Timestamp(start + timedelta(days=float(t))))
+    ref = ojump.tau_leap_ensemble(Oracle, np.array([99000.0, 1000.0, 0.0]), par, 0, 100, 0.5, n, seed=6, chunk=n)
+    mine = np.stack([np.moveaxis(dated[s].values, 0, -1) for s in ("S", "I", "R")])
+    cases.assert_ks_ok(cases.ks_pvalues(mine[:, times], np.transpose(ref[:, :, times], (1, 2, 0))), "seasonal SIR (dates)")
+    back = model.sim(100, N=64, tau=0.5, seed=3, output_dtype="int32")                           # and back to numeric time
+    assert np.array_equal(back["I"].values, out["I"].values[:64])
