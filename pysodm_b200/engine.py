@@ -43,7 +43,8 @@ def device(index=None) -> torch.device:
 def _dev_f64(x, dev):
     if isinstance(x, torch.Tensor):
         return x.to(device=dev, dtype=torch.float64).contiguous()
-    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+    a = np.ascontiguousarray(x, dtype=np.float64)
+    return torch.from_numpy(a if a.flags.writeable else a.copy()).to(dev)
 
 
 def _dev_i32(x, dev):
