@@ -9,7 +9,10 @@
 
 namespace sodm {
 
-constexpr int JUMP_BLOCK = 128;
+#ifndef SODM_JUMP_BLOCK
+#define SODM_JUMP_BLOCK 128
+#endif
+constexpr int JUMP_BLOCK = SODM_JUMP_BLOCK;
 // Resident blocks per SM the compiler must allow for.  The samplers are latency / instruction-fetch bound (ncu:
 // `no_instruction` is the top stall), so resident warps matter more than registers: measured on influenza,
 // per-lane walk 352 / 272 / 262 / 259 ms at 1 / 5 / 6 / 8 blocks, cooperative 339 / 294 / 311 / 426 ms.
