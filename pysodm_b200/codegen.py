@@ -891,20 +891,23 @@ def jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes,
     _reject_time(g2, tr["new_states"], "apply_transitionings")
     # ---- draw slots: per compartment element, its exits in order; trailing exits nobody reads are not drawn (their
     # probability still enters the normaliser W of the reference's quirk, base.py:339-342)
+    # Slot ORDER: element-major (element 0 of every state, then element 1, ...), i.e. one age group's compartments after
+    # the other.  Measured on influenza (B200): 137 ms per 10^6 trajectories against 148 ms state-major -- a lane's cheap
+    # and expensive draws then alternate, which keeps the lanes of a warp closer together (profiles/r1_sampler_ab.txt).
     slot_of, groups, n_draw, dep_mask = {}, [], 0, 0
-    for name, per in tr["channels"].items():
-        m = len(per)
-        for e in range(tr["state_sizes"][name]):
-            drawn = m
-            while drawn > 0 and tr["slots"][(name, drawn - 1, e)] not in used_T:
-                drawn -= 1
-            first = n_draw
-            for i in range(drawn):
-                slot_of[tr["slots"][(name, i, e)]] = n_draw
-                if i > 0:
-                    dep_mask |= 1 << n_draw
-                n_draw += 1
-            groups.append((name, e, m, drawn, first))
+    order = sorted(((e, si, name) for si, name in enumerate(tr["channels"]) for e in range(tr["state_sizes"][name])))
+    for e, _, name in order:
+        m = len(tr["channels"][name])
+        drawn = m
+        while drawn > 0 and tr["slots"][(name, drawn - 1, e)] not in used_T:
+            drawn -= 1
+        first = n_draw
+        for i in range(drawn):
+            slot_of[tr["slots"][(name, i, e)]] = n_draw
+            if i > 0:
+                dep_mask |= 1 << n_draw
+            n_draw += 1
+        groups.append((name, e, m, drawn, first))
     if n_draw > 64:
         raise TraceError(f"{n_draw} binomial draws per step; the sampler's work list holds at most 64")
     if n_draw == 0:
