@@ -222,7 +222,11 @@ __host__ __device__ __forceinline__ int binomial_inversion_word(int n, float p, 
 //   btrs_candidate : setup + candidate k + BTRS box test            -> BIN_DONE | BIN_RETRY (k outside 0..n) | BIN_SQUEEZE
 //   btrs_squeeze   : scaled uniform + BTPE squeeze on the same words -> BIN_DONE | BIN_RETRY | BIN_EXACT (lhs set)
 enum : int { BIN_SQUEEZE = 5 };
-__host__ __device__ __forceinline__ int btrs_candidate(int n, float p, uint32_t wu, uint32_t wv, int& k) {
+// What the acceptance tests need from the candidate stage (so that they do not recompute the hat).
+struct BtrsHat {
+    float stddev, b, a, us, v;
+};
+__host__ __device__ __forceinline__ int btrs_candidate(int n, float p, uint32_t wu, uint32_t wv, int& k, BtrsHat& hat) {
     const float nf = (float)n;
     const float np_ = nf * p;
     const float stddev = fast_sqrt(np_ * (1.0f - p));
@@ -232,6 +236,7 @@ __host__ __device__ __forceinline__ int btrs_candidate(int n, float p, uint32_t 
     const float u = u01(wu) - 0.5f;
     const float v = u01(wv);
     const float us = 0.5f - fabsf(u);
+    hat.stddev = stddev; hat.b = b; hat.a = a; hat.us = us; hat.v = v;
     if (np_ < 4194304.0f) {
         k = (int)floorf(fmaf(fast_div(2.0f * a, us) + b, u, np_ + 0.5f));
     } else {
@@ -242,17 +247,19 @@ __host__ __device__ __forceinline__ int btrs_candidate(int n, float p, uint32_t 
     if (k < 0 || k > n) return BIN_RETRY;
     return BIN_SQUEEZE;
 }
-__host__ __device__ __forceinline__ int btrs_squeeze(int n, float p, int k, uint32_t wu, uint32_t wv, float& lhs) {
+__host__ __device__ __forceinline__ int btrs_candidate(int n, float p, uint32_t wu, uint32_t wv, int& k) {
+    BtrsHat hat;
+    return btrs_candidate(n, p, wu, wv, k, hat);
+}
+// log of the scaled uniform that the acceptance tests compare with log f(k)/f(m)   (BTRS step 3.1)
+__host__ __device__ __forceinline__ float btrs_lhs(const BtrsHat& h) {
+    const float alpha = (2.83f + fast_div(5.1f, h.b)) * h.stddev;
+    return fast_log(fast_div(h.v * alpha, fast_div(h.a, h.us * h.us) + h.b));
+}
+__host__ __device__ __forceinline__ int btrs_squeeze(int n, float p, int k, const BtrsHat& h, float& lhs) {
     const float nf = (float)n;
     const float npq = nf * p * (1.0f - p);
-    const float stddev = fast_sqrt(npq);
-    const float b = 1.15f + 2.53f * stddev;
-    const float a = -0.0873f + 0.0248f * b + 0.01f * p;
-    const float alpha = (2.83f + fast_div(5.1f, b)) * stddev;
-    const float u = u01(wu) - 0.5f;
-    const float v = u01(wv);
-    const float us = 0.5f - fabsf(u);
-    lhs = fast_log(fast_div(v * alpha, fast_div(a, us * us) + b));
+    lhs = btrs_lhs(h);
     const float mf = floorf((nf + 1.0f) * p);
     const float x = fabsf((float)k - mf);
     if (x < 0.5f * npq - 1.0f) {
@@ -264,6 +271,17 @@ __host__ __device__ __forceinline__ int btrs_squeeze(int n, float p, int k, uint
         if (lhs > t + rho + eps) return BIN_RETRY;
     }
     return BIN_EXACT;
+}
+// the same from the two random words alone (queue-based processing regenerates the hat of a parked candidate)
+__host__ __device__ __forceinline__ int btrs_squeeze(int n, float p, int k, uint32_t wu, uint32_t wv, float& lhs) {
+    BtrsHat h;
+    const float npq = (float)n * p * (1.0f - p);
+    h.stddev = fast_sqrt(npq);
+    h.b = 1.15f + 2.53f * h.stddev;
+    h.a = -0.0873f + 0.0248f * h.b + 0.01f * p;
+    h.us = 0.5f - fabsf(u01(wu) - 0.5f);
+    h.v = u01(wv);
+    return btrs_squeeze(n, p, k, h, lhs);
 }
 
 // The exact acceptance test of candidate k (FP32 where harmless, FP64 otherwise).  Out of line on the device: it runs
@@ -279,16 +297,6 @@ bool btrs_exact_accept(int n, float p, int k, float lhs) {
     if (mf < SODM_F32_MODE_LIMIT && nf < 16777216.0f) return lhs <= binomial_log_ratio_f32(nf, p, mf, (float)k);
     const double nd = (double)n, pd = (double)p;
     return (double)lhs <= binomial_log_ratio(nd, pd, floor((nd + 1.0) * pd), (double)k);
-}
-
-// log of the scaled uniform that the acceptance tests compare with log f(k)/f(m)   (BTRS step 3.1)
-__host__ __device__ __forceinline__ float btrs_lhs(int n, float p, uint32_t wu, uint32_t wv) {
-    const float stddev = fast_sqrt((float)n * p * (1.0f - p));
-    const float b = 1.15f + 2.53f * stddev;
-    const float a = -0.0873f + 0.0248f * b + 0.01f * p;
-    const float alpha = (2.83f + fast_div(5.1f, b)) * stddev;
-    const float us = 0.5f - fabsf(u01(wu) - 0.5f);
-    return fast_log(fast_div(u01(wv) * alpha, fast_div(a, us * us) + b));
 }
 
 // One complete BTRS attempt of a single lane (per-lane walk); requires 0 < p <= 0.5 and n*p >= 10.
@@ -324,15 +332,16 @@ __host__ __device__ __forceinline__ bool binomial_try_words(int n, float p, uint
     if (state == BIN_INVERT) {
         kk = binomial_inversion_word(n, pp, wu);
     } else {
-        state = btrs_candidate(n, pp, wu, wv, kk);
+        BtrsHat hat;
+        state = btrs_candidate(n, pp, wu, wv, kk, hat);
         if (state == BIN_RETRY) done = false;
         else if (state == BIN_SQUEEZE) {
             float lhs = 0.0f;
             if (SODM_DIRECT_EXACT && (float)n * pp < 0.9f * SODM_F32_MODE_LIMIT) {
-                lhs = btrs_lhs(n, pp, wu, wv);
+                lhs = btrs_lhs(hat);
                 state = BIN_EXACT;
             } else {
-                state = btrs_squeeze(n, pp, kk, wu, wv, lhs);
+                state = btrs_squeeze(n, pp, kk, hat, lhs);
             }
             if (state == BIN_RETRY) done = false;
             else if (state == BIN_EXACT) done = btrs_exact_accept(n, pp, kk, lhs);
