@@ -44,8 +44,9 @@ def _lerp(a, b, t):
 class DeviceDataArray:
     """One state variable of a device-resident ensemble: CUDA tensor `[*state_dims, time, draws]`."""
 
-    def __init__(self, data, name, state_dims, coords, time_name, n_global=None):
+    def __init__(self, data, name, state_dims, coords, time_name, n_global=None, traj_id0=0):
         self.data, self.name = data, name
+        self.traj_id0 = int(traj_id0)            # global index of this rank's first draw (keys the noise streams)
         # draws of ALL ranks when the ensemble is sharded by trajectory over a torch.distributed job (else the local count)
         self.n_global = int(n_global) if n_global is not None else int(data.shape[-1])
         self.state_dims = list(state_dims)
@@ -99,7 +100,7 @@ class DeviceDataArray:
                 coords[dim] = [labels[i] for i in np.asarray(idx).tolist()]
         state_dims = [d for d in self.state_dims if not (scalar and d == dim)]
         time_name = None if (scalar and dim == self.time_name) else self.time_name
-        return DeviceDataArray(data, self.name, state_dims, coords, time_name, self.n_global)
+        return DeviceDataArray(data, self.name, state_dims, coords, time_name, self.n_global, self.traj_id0)
 
     def isel(self, indexers=None, **kw):
         out = self
@@ -221,7 +222,8 @@ class DeviceEnsemble:
             coords = OrderedDict([(time_name, list(time_coord))])
             for d, c in zip(dims_per_state[v.name], coords_per_state[v.name]):
                 coords[d] = list(c)
-            self.data_vars[v.name] = DeviceDataArray(view, v.name, dims_per_state[v.name], coords, time_name, self.n_global)
+            self.data_vars[v.name] = DeviceDataArray(view, v.name, dims_per_state[v.name], coords, time_name, self.n_global,
+                                                     self.traj_id0)
 
     @property
     def n_draws(self):

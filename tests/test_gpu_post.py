@@ -192,6 +192,13 @@ def test_device_ensemble_matches_host_path_and_numpy():
     band = noisy["Im_inc"].quantile([0.025, 0.975])
     assert np.all(np.asarray(band.values)[0] <= np.asarray(band.values)[1])
     assert np.array_equal(np.asarray(band.values), np.quantile(mine, [0.025, 0.975], axis=0))
+    # noise on one variable only (what the tutorial plots): same law, a seventh of the work
+    one_noisy = add_negative_binomial_noise(ens["Im_inc"].sel(age_group=td.AGE_GROUPS[1]), 0.03, seed=8)
+    assert one_noisy.dims == ("draws", "date") and one_noisy.shape == (n, 46)
+    ref1 = post.add_negative_binomial_noise(np.asarray(host["Im_inc"].values)[:, :, 1], 0.03, np.random.RandomState(2))
+    ps = cases.ks_pvalues(one_noisy.values[:, times].T, ref1[:, times].T.astype(np.float64))
+    cases.assert_ks_ok(ps, "NB noise on one state variable")
+    assert np.array_equal(np.asarray(one_noisy.quantile(0.5).values), np.quantile(one_noisy.values, 0.5, axis=0))
     # host Datasets go through the device as well (drop-in form of the reference call)
     small = model.sim(span, N=50, tau=0.5, seed=2)
     for fn, args in ((add_poisson_noise, ()), (add_negative_binomial_noise, (0.03,)), (add_gaussian_noise, (0.04,))):
