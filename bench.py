@@ -186,8 +186,19 @@ def run_gpu_arm(args):
             raise SystemExit("bench.py --gpus N with N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     dev = engine.device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"            # NCCL's version banner goes to STDOUT, which carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to STDOUT when the communicator is created; stdout carries exactly one JSON line,
+        # so file descriptor 1 points at stderr until the first collective has gone through
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     n = args.n_traj
     y0 = torch.from_numpy(td.influenza_flat_y0()).to(dev)
