@@ -185,6 +185,15 @@ def run_gpu_arm(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("bench.py --gpus N with N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     dev = engine.device(local)
+    all_cpus = os.sched_getaffinity(0)
+    if not args.no_affinity:
+        # one process per GPU: run (and first-touch the pinned result buffers) on the CPU cores of the GPU's own NUMA node
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device()))
+        except Exception as exc:  # noqa: BLE001  (affinity is an optimisation, never a requirement)
+            print(f"bench: CPU affinity not set ({exc})", file=sys.stderr)
     if world > 1:
         # NCCL prints its version banner to STDOUT when the communicator is created; stdout carries exactly one JSON line,
         # so file descriptor 1 points at stderr until the first collective has gone through
@@ -385,6 +394,7 @@ def run_gpu_arm(args):
         # CPU baseline beside it (N = 1 only): bounded sample on the host cores
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)        # the CPU arm gets every host core, not just the GPU's NUMA node
             os.environ.setdefault("OMP_NUM_THREADS", "1")
             rate, dt, cores = cpu_reference_rate(per_core=1024, rounds=1)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
@@ -423,6 +433,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-workflow", action="store_true")
+    ap.add_argument("--no-affinity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
