@@ -829,6 +829,10 @@ def ode_source(integrate, state_shapes, param_shapes, origin="", **trace_kw):
         return {"t": "t", "y": f"y[{name[1]}]", "par": f"par[{name[1]}]"}[name[0]]
     lines, exprs = emit(g, outs, "double", leaf)
     body = _indent(lines) + "\n" + _indent([f"dy[{j}] = {e};" for j, e in enumerate(exprs)])
+    # large systems: warp-per-draw layout when the equations fall into a few shapes (then the thread functor above only
+    # serves the host self-check and its kernel is not instantiated)
+    warp = ode_warp_source(g, outs, n_state, n_param) if n_state >= WARP_MIN_STATES else None
+    entry = "SODM_ODE_PLUGIN(::sodm::GenModel)" if warp is None else warp[0] + "\nSODM_ODE_WARP_PLUGIN(::sodm::GenModel, ::sodm::GenWarp)"
     src = f"""// GENERATED by pysodm_b200.codegen from the Python function `integrate`{origin} -- do not edit.
 // {len(g.nodes)} expression nodes, {len(lines)} statements.
 #include "plugin.cuh"
@@ -843,7 +847,7 @@ struct GenModel {{
 }};
 }}  // namespace sodm
 
-SODM_ODE_PLUGIN(::sodm::GenModel)
+{entry}
 
 // one evaluation on the HOST (the functor is __host__ __device__): build-time self-check against the Python function
 extern "C" void sodm_plugin_host_rhs(double t, const double* y, const double* par, double* dy) {{
@@ -1043,3 +1047,198 @@ extern "C" void sodm_plugin_host_fire(int* y, int ch) {{ ::sodm::GenModel::fire(
               "tdpf_offset": tdpf_offset, "tdpf_count": tdpf_count, "slot_of": slot_of, "groups": groups,
               "channel_slots": tr["slots"], "dep_mask": dep_mask, "uses_time": uses_time}
     return src, layout
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# warp-per-draw layout for large ODE systems: lanes evaluate ISOMORPHIC derivative expressions with lane-dependent operands
+# ---------------------------------------------------------------------------------------------------------------------
+# A stencil model (the packed-bed reactor: 8 x nx equations) has a handful of expression SHAPES -- interior fluid node,
+# outlet node, solid node, inlet -- each instantiated at many (species, node) positions with different operands.  For the
+# thread-per-draw functor that is 200 equations in one thread's registers; here the equations are grouped by shape, every
+# group is padded to whole warps, and position k of lane l evaluates ONE template per k (same instructions for the whole
+# warp) whose operands -- state elements, parameters, constants -- come from per-member index tables.  The state of a draw
+# lives in shared memory between stages; the integrators of ode_run.cuh drive it through the same `Sys` concept as the
+# hand-written reactor functor.
+WARP_MIN_STATES = 64
+_MAX_TREE = 4000
+
+
+def _shape_and_leaves(graph, root):
+    """Canonical shape string of the expression TREE under `root` (shared nodes expanded) and its leaves in DFS order."""
+    leaves, parts, count = [], [], [0]
+
+    def walk(i):
+        count[0] += 1
+        if count[0] > _MAX_TREE:
+            raise TraceError("derivative expression too large for the warp layout")
+        op, args, kind = graph.nodes[i]
+        if op == "in":
+            if args[0][0] == "t":
+                parts.append("t")
+            else:
+                parts.append("L")
+                leaves.append((args[0][0], args[0][1]))
+            return
+        if op == "const":
+            parts.append("L")
+            leaves.append(("c", float(args[0])))
+            return
+        parts.append(op + "(")
+        for a in args:
+            walk(a)
+            parts.append(",")
+        parts.append(")")
+    walk(root.i)
+    return "".join(parts), leaves
+
+
+def warp_layout(graph, outs):
+    """Group the outputs by shape.  -> list of classes {members: [flat state index], slots: [(kind, values per member)],
+    position_of_leaf: [slot id per leaf position]}, in an order that puts large classes first."""
+    by_shape = {}
+    for j, o in enumerate(outs):
+        shape, leaves = _shape_and_leaves(graph, o)
+        by_shape.setdefault(shape, []).append((j, leaves))
+    classes = []
+    for shape, items in by_shape.items():
+        members = [j for j, _ in items]
+        n_leaf = len(items[0][1])
+        slots, slot_of_pos, seen = [], [], {}
+        for pos in range(n_leaf):
+            kinds = {lv[pos][0] for _, lv in items}
+            if len(kinds) != 1:
+                # the same position is a state in one member and a parameter / constant in another: not one template
+                return None
+            kind = kinds.pop()
+            values = tuple(lv[pos][1] for _, lv in items)
+            key = (kind, values)
+            if key not in seen:
+                seen[key] = len(slots)
+                slots.append((kind, values))
+            slot_of_pos.append(seen[key])
+        classes.append({"members": members, "slots": slots, "slot_of_pos": slot_of_pos, "root": outs[members[0]]})
+    classes.sort(key=lambda c: -len(c["members"]))
+    return classes
+
+
+def _template_graph(graph, cls):
+    """The representative member's expression rebuilt over slot leaves (hash-consing merges what repeats)."""
+    g = Graph()
+    pos = [0]
+
+    def build(i):
+        op, args, kind = graph.nodes[i]
+        if op == "in" and args[0][0] == "t":
+            return g.leaf(("t", 0), "f")
+        if op in ("in", "const"):
+            s = cls["slot_of_pos"][pos[0]]
+            pos[0] += 1
+            return g.leaf(("slot", s), "f")
+        kids = [build(a) for a in args]
+        return g.node(op, tuple(k.i for k in kids), kind)
+    return g, build(cls["root"].i)
+
+
+def ode_warp_source(graph, outs, n_state, n_param):
+    """C++ of the warp-per-draw functor `GenWarp` (appended to the plugin's translation unit), or None when the model does
+    not decompose into a few shapes.  -> (source, n_local)"""
+    try:
+        classes = warp_layout(graph, outs)
+    except TraceError:
+        return None
+    if classes is None or len(classes) > 24:
+        return None
+    # positions: class after class, each padded to whole warps
+    perm, k0 = [], []
+    for c in classes:
+        k0.append(len(perm) // 32)
+        perm.extend(c["members"])
+        perm.extend([-1] * (-len(c["members"]) % 32))
+    n_local = len(perm) // 32
+    if n_local > 32:
+        return None
+    tables, funcs = [], []
+    for ci, c in enumerate(classes):
+        g, root = _template_graph(graph, c)
+        m = len(c["members"])
+        decl = []
+
+        def slot_expr(s, ci=ci, c=c, decl=decl, m=m):
+            kind, values = c["slots"][s]
+            same = all(v == values[0] for v in values)
+            if kind == "c":
+                if same:
+                    v = values[0]
+                    return ("NAN" if math.isnan(v) else ("-" if v < 0 else "") + "INFINITY") if not math.isfinite(v) else repr(float(v))
+                name = f"kC{ci}_{s}"
+                tables.append(f"SODM_BOTH_TABLES(double, {name}, {m}, {{{', '.join(repr(float(v)) for v in values)}}})")
+                decl.append(f"const double s{s} = SODM_TAB({name})[r];")
+                return f"s{s}"
+            arr = "ys" if kind == "y" else "pr"
+            if same:
+                return f"{arr}[{int(values[0])}]"
+            step = values[1] - values[0] if m > 1 else 0
+            if all(values[q] == values[0] + q * step for q in range(m)):
+                decl.append(f"const double s{s} = {arr}[{int(values[0])} + {int(step)} * r];")
+                return f"s{s}"
+            name = f"kI{ci}_{s}"
+            tables.append(f"SODM_BOTH_TABLES(short, {name}, {m}, {{{', '.join(str(int(v)) for v in values)}}})")
+            decl.append(f"const double s{s} = {arr}[SODM_TAB({name})[r]];")
+            return f"s{s}"
+        exprs = {}
+
+        def leaf(name):
+            if name[0] == "t":
+                return "t"
+            if name[1] not in exprs:
+                exprs[name[1]] = slot_expr(name[1])
+            return exprs[name[1]]
+        lines, res = emit(g, [root], "double", leaf, prefix=f"w{ci}_")
+        funcs.append(f"""    // shape {ci}: {m} equations, {len(c['slots'])} operand slots
+    __host__ __device__ static __forceinline__ double shape{ci}(double t, const double* ys, const double* pr, int r) {{
+        (void)t; (void)ys; (void)pr; (void)r;
+{_indent(decl)}
+{_indent(lines)}
+        return {res[0]};
+    }}""")
+    body = []
+    for k in range(n_local):
+        ci = max(i for i in range(len(classes)) if k0[i] <= k)
+        m = len(classes[ci]["members"])
+        body.append(f"{{ const int r = {32 * (k - k0[ci])} + lane; dy[{k}] = r < {m} ? shape{ci}(t, ys, pr, r) : 0.0; }}")
+    nl = "\n"
+    src = f"""
+// ---- warp-per-draw layout: {len(classes)} expression shapes over {n_state} equations, {n_local} positions per lane ----------------
+// index / constant tables exist twice: in device memory for the kernels, in host memory for the build-time self-check
+#ifdef __CUDA_ARCH__
+#define SODM_TAB(name) name##_d
+#else
+#define SODM_TAB(name) name##_h
+#endif
+#define SODM_BOTH_TABLES(T, name, n, ...) static __device__ const T name##_d[n] = __VA_ARGS__; static const T name##_h[n] = __VA_ARGS__;
+namespace sodm {{
+{nl.join(tables)}
+SODM_BOTH_TABLES(short, kPerm, {len(perm)}, {{{', '.join(str(p) for p in perm)}}})
+struct GenWarp {{
+    static constexpr int N = {n_state}, NPAR = {max(n_param, 1)}, NL = {n_local};
+    __host__ __device__ static __forceinline__ int flat_index(int k, int lane) {{ return SODM_TAB(kPerm)[32 * k + lane]; }}
+{nl.join(funcs)}
+    // derivatives of this lane's positions from the draw's full state `ys` and parameters `pr`
+    __host__ __device__ static __forceinline__ void rhs_lane(double t, const double* ys, const double* pr, int lane, double* dy) {{
+{_indent(body)}
+    }}
+}};
+}}  // namespace sodm
+
+extern "C" void sodm_plugin_host_rhs_warp(double t, const double* y, const double* par, double* dy) {{
+    for (int lane = 0; lane < 32; ++lane) {{
+        double d[::sodm::GenWarp::NL];
+        ::sodm::GenWarp::rhs_lane(t, y, par, lane, d);
+        for (int k = 0; k < ::sodm::GenWarp::NL; ++k) {{
+            const int j = ::sodm::GenWarp::flat_index(k, lane);
+            if (j >= 0) dy[j] = d[k];
+        }}
+    }}
+}}
+"""
+    return src, n_local

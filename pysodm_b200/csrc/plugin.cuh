@@ -77,7 +77,105 @@ char* error_buffer() {
         return ::sodm::fail(SODM_EUNSUPPORTED, "this plugin holds an ODE model");                 \
     }
 
+// Large generated ODE systems: warp-per-draw (codegen.ode_warp_source).  W = the generated shape functor (GenWarp), M = the
+// thread functor of the same model, kept for the host self-check only.
+#define SODM_ODE_WARP_PLUGIN(M, W)                                                                \
+    SODM_PLUGIN_COMMON()                                                                          \
+    static sodm_model_info plugin_info() {                                                        \
+        sodm_model_info info = {};                                                                \
+        info.kind = SODM_KIND_ODE;                                                                \
+        info.n_state = W::N;                                                                      \
+        info.n_param = W::NPAR;                                                                   \
+        return info;                                                                              \
+    }                                                                                             \
+    extern "C" int sodm_plugin_info(sodm_model_info* out) {                                       \
+        if (!out) return ::sodm::fail(SODM_EINVAL, "sodm_plugin_info: null output");              \
+        *out = plugin_info();                                                                     \
+        return SODM_OK;                                                                           \
+    }                                                                                             \
+    extern "C" int sodm_plugin_ode_run(const sodm_ode_args* a) {                                  \
+        static_assert(W::NPAR <= ::sodm::ODE_MAX_PARAM, "too many flat parameter elements");      \
+        ::sodm::OdeLaunch L;                                                                      \
+        const int rc = ::sodm::build_ode_launch_for(a, L, plugin_info());                         \
+        if (rc != SODM_OK) return rc;                                                             \
+        if (a->n_traj == 0) return SODM_OK;                                                       \
+        return ::sodm::launch_gen_warp<W>(L, a->method, a->out_dtype, (cudaStream_t)a->stream);   \
+    }                                                                                             \
+    extern "C" int sodm_plugin_jump_run(const sodm_jump_args*) {                                  \
+        return ::sodm::fail(SODM_EUNSUPPORTED, "this plugin holds an ODE model");                 \
+    }
+
 namespace sodm {
+
+// One warp per draw for a generated ODE: the draw's state and parameters live in shared memory between stages; position k
+// of lane l holds equation W::flat_index(k, l) (equations grouped by expression shape, groups padded to whole warps), so
+// that `rhs_lane` runs ONE template per k for the whole warp.
+template <class W>
+struct GenWarpSystem {
+    static constexpr int NL = W::NL;
+    double* ys;            // shared: full state of this draw (input of the current right-hand-side evaluation)
+    const double* pr;      // shared: parameters of this draw
+    int lane;
+    uint32_t valid;        // bit k: position k of this lane holds an equation
+    __device__ __forceinline__ int n_total() const { return W::N; }
+    __device__ __forceinline__ bool active(int k) const { return (valid >> k) & 1u; }
+    __device__ __forceinline__ bool leader() const { return lane == 0; }
+    __device__ __forceinline__ int global_index(int k) const { return W::flat_index(k, lane); }
+    __device__ __forceinline__ double reduce(double x) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        return x;
+    }
+    __device__ __forceinline__ void rhs(double t, const double* y, double* dy) const {
+        __syncwarp();                                            // every lane is done reading the previous stage's state
+#pragma unroll
+        for (int k = 0; k < NL; ++k)
+            if (active(k)) ys[W::flat_index(k, lane)] = y[k];
+        __syncwarp();
+        W::rhs_lane(t, ys, pr, lane, dy);
+    }
+};
+
+template <class W, typename OutT>
+__global__ void __launch_bounds__(ODE_BLOCK) ode_gen_warp_kernel(const __grid_constant__ OdeLaunch L, int method) {
+    extern __shared__ double gen_warp_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= L.n_traj) return;                                   // whole warps leave together
+    double* ys = gen_warp_smem + (size_t)warp * (W::N + W::NPAR);
+    double* pr = ys + W::N;
+    for (int e = lane; e < W::NPAR; e += 32)
+        pr[e] = L.var_row[e] >= 0 ? L.var_values[(int64_t)L.var_row[e] * L.ld_in + i] : L.par[e];
+    GenWarpSystem<W> sys{ys, pr, lane, 0u};
+    double y[W::NL];
+#pragma unroll
+    for (int k = 0; k < W::NL; ++k) {
+        const int j = W::flat_index(k, lane);
+        y[k] = 0.0;
+        if (j >= 0) {
+            sys.valid |= 1u << k;
+            y[k] = L.y0_bcast ? L.y0[j] : L.y0[(int64_t)j * L.ld_in + i];
+        }
+    }
+    __syncwarp();
+    if (method == SODM_ODE_RK45) rk45_run<GenWarpSystem<W>, OutT>(sys, L, i, y);
+    else if (method == SODM_ODE_EULER) fixed_step_run<GenWarpSystem<W>, OutT, false>(sys, L, i, y);
+    else fixed_step_run<GenWarpSystem<W>, OutT, true>(sys, L, i, y);
+}
+
+template <class W>
+static int launch_gen_warp(const OdeLaunch& L, int method, int dtype, cudaStream_t stream) {
+    static_assert(W::NL <= 32, "at most 32 positions per lane");
+    const int64_t threads = L.n_traj * 32;
+    const unsigned grid = (unsigned)((threads + ODE_BLOCK - 1) / ODE_BLOCK);
+    const size_t smem = (size_t)(ODE_BLOCK / 32) * (W::N + W::NPAR) * sizeof(double);
+    if (smem > 200 * 1024) return fail(SODM_EUNSUPPORTED, "model needs %zu bytes of shared memory per block", smem);
+    void (*kernel)(OdeLaunch, int) = dtype == SODM_F64 ? ode_gen_warp_kernel<W, double> : ode_gen_warp_kernel<W, float>;
+    SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+    kernel<<<grid, ODE_BLOCK, smem, stream>>>(L, method);
+    SODM_CUDA_CHECK(cudaGetLastError());
+    return SODM_OK;
+}
 
 // A generated model gets the kernels a front end can ask for -- int32 output on the aligned grid, FP64 otherwise, SSA in
 // FP64 -- with the default (walk) sampler: a third of the instantiations of a built-in model, ~15 s of nvcc.

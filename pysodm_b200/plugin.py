@@ -122,8 +122,18 @@ def build_ode(integrate, state_shapes, param_shapes, origin="", reference=None, 
     y = _flat(example_states, state_shapes)
     par_buf = np.concatenate([np.asarray(example_params, dtype=np.float64), np.zeros(1)])
     dy = np.empty(n_state)
+    warp_fn = getattr(plug.lib, "sodm_plugin_host_rhs_warp", None)     # present when the warp-per-draw layout was generated
+    if warp_fn is not None:
+        warp_fn.restype, warp_fn.argtypes = None, fn.argtypes
+        plug.layout["warp"] = True
     for t in (0.0, 1.5, 40.25):
         fn(t, y.ctypes.data, par_buf.ctypes.data, dy.ctypes.data)
+        if warp_fn is not None:                                        # the shape templates must give what the plain functor gives
+            dw = np.full(n_state, np.nan)
+            warp_fn(t, y.ctypes.data, par_buf.ctypes.data, dw.ctypes.data)
+            if not np.allclose(dw, dy, rtol=1e-12, atol=0.0, equal_nan=True):
+                j = int(np.argmax(~np.isclose(dw, dy, rtol=1e-12, atol=0.0, equal_nan=True)))
+                raise codegen.TraceError(f"warp-layout translation disagrees with the plain functor (element {j}: {dw[j]!r} vs {dy[j]!r})")
         want = reference(t)
         want = np.concatenate([_shaped(w, s) for w, s in zip(want if isinstance(want, (tuple, list)) else (want,),
                                                              state_shapes.values())])

@@ -267,3 +267,42 @@ def test_random_numpy_expressions_translate_exactly():
             host(float(t), y.ctypes.data, par.ctypes.data, dy.ctypes.data)
             want = np.concatenate([np.ravel(v) for v in fn(t, A, B, s, p, q)])
             np.testing.assert_allclose(dy, want, rtol=1e-12, atol=1e-13, err_msg=f"seed {seed}")
+
+
+def test_large_stencil_models_take_the_warp_layout():
+    """>= 64 equations that fall into a few expression shapes: the translation groups them by shape, pads every group to
+    whole warps and emits one template per position; evaluated on the host, the templates reproduce the plain functor and
+    the Python function (the self-check inside build_ode), for the packed-bed reactor and for a reaction-diffusion ring."""
+    pfr = gm.make_pfr(25)
+    assert pfr.device_model.layout.get("warp") and pfr.device_model.info.n_state == 200
+    g, outs = codegen.trace_ode(type(pfr).integrate, {k: tuple(v) for k, v in pfr.state_shapes.items()},
+                                {k: tuple(np.shape(pfr.parameters[k])) for k in pfr._spec_params})
+    classes = codegen.warp_layout(g, outs)
+    assert sorted(len(c["members"]) for c in classes) == [8, 48, 48, 96]        # inlet, solid (two signs), fluid incl. outlet
+
+    class Ring(gm.ODE):                                     # two species on a ring of 40 cells: 80 equations, 2 shapes
+        states, parameters, dimensions = ["u", "v"], ["D", "a", "b"], ["cell"]
+
+        @staticmethod
+        def integrate(t, u, v, D, a, b):
+            lap = np.roll(u, 1) - 2 * u + np.roll(u, -1)
+            return D * lap + a - (b + 1) * u + u ** 2 * v, b * u - u ** 2 * v + 0.1 * D * (np.roll(v, 1) - 2 * v + np.roll(v, -1))
+    rng = np.random.default_rng(0)
+    ring = Ring({"u": 1 + 0.1 * rng.random(40), "v": 3 + 0.1 * rng.random(40)}, {"D": 0.2, "a": 1.0, "b": 3.0},
+                coordinates={"cell": list(range(40))})
+    assert ring.device_model.layout.get("warp")
+
+    class Irregular(gm.ODE):                                # 64 equations, every one of a different shape: stays thread-per-draw
+        states, parameters, dimensions = ["x"], ["k"], ["i"]
+
+        @staticmethod
+        def integrate(t, x, k):
+            out = np.zeros(64)
+            for i in range(64):
+                acc = -k * x[i]
+                for j in range(i % 29 + 1):
+                    acc = acc + 1e-3 * x[(i + j) % 64] * (j + 1)
+                out[i] = acc
+            return out,
+    irr = Irregular({"x": np.ones(64)}, {"k": 0.1}, coordinates={"i": list(range(64))})
+    assert not irr.device_model.layout.get("warp")

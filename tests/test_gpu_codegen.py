@@ -126,6 +126,25 @@ def test_generated_odes_follow_the_hand_written_functors(golden):
     for s in ("C_F", "C_S"):
         np.testing.assert_allclose(ga[s].values, ha[s].values, rtol=1e-8, atol=1e-12)
     assert np.array_equal(gp.last_nfev.cpu().numpy(), hp.last_nfev.cpu().numpy())
+    # at nx = 25 (200 equations) the generated model takes the WARP-per-draw layout: equations grouped by expression shape,
+    # one template per position for the whole warp -- against the hand-written warp functor, draws of the kinetic parameters
+    nx = 25
+    gp, hp = gm.make_pfr(nx), gm.make_pfr(nx, tm.packed_PFR)
+    assert gp.device_model.layout.get("warp")
+
+    def draw(parameters, N):
+        r = np.random.default_rng(3)
+        parameters["Vf_Ks"] = 7.88e-04 * r.uniform(0.8, 1.2, size=N)
+        parameters["K_eq"] = 0.418 * r.uniform(0.8, 1.2, size=N)
+        return parameters
+    draw.vectorized = True
+    ga = gp.sim(2000, N=37, draw_function=draw, output_stride=500)
+    ha = hp.sim(2000, N=37, draw_function=draw, output_stride=500)
+    for s in ("C_F", "C_S"):
+        np.testing.assert_allclose(ga[s].values, ha[s].values, rtol=1e-8, atol=1e-12)
+    assert np.array_equal(gp.last_nfev.cpu().numpy(), hp.last_nfev.cpu().numpy())
+    eu_g, eu_h = gp.sim(50, tau=0.5, output_last_only=True), hp.sim(50, tau=0.5, output_last_only=True)
+    np.testing.assert_allclose(eu_g["C_F"].values, eu_h["C_F"].values, rtol=1e-10, atol=1e-14)
     # a model that exists nowhere else: against scipy on the host (the reference's own solver call, base.py:855)
     lv = gm.make_lotka()
     res = lv.sim(40, rtol=1e-8, atol=1e-10)

@@ -134,12 +134,12 @@ def main():
     ms = timed(lambda: engine.ode_run(sir, [1000, 1, 0], [0.35, 5], n, 0, 121, var=([0], betas[None, :]), out=out, dev=dev))
     res["C1_sir_ode_rk45_generated"] = {"n_traj": n, "ms": ms, "traj_per_s": n / ms * 1e3}
 
-    # C4 through the GENERATED thread-per-draw functor (200 equations per thread) against the hand-written warp-per-draw one
+    # C4 through the GENERATED functor (warp-per-draw layout from expression shapes) against the hand-written warp-per-draw one
     n = 20_000
     pfr = gm.make_pfr(25).device_model
     post_small = torch.from_numpy(post[:, :n].copy()).to(dev)
     out = torch.empty((200, 1, n), dtype=torch.float64, device=dev)
-    for label, model, arg in (("generated_thread_per_draw", pfr, 0), ("hand_written_warp_per_draw", "packed_pfr_ode", 25)):
+    for label, model, arg in (("generated_warp_per_draw", pfr, 0), ("hand_written_warp_per_draw", "packed_pfr_ode", 25)):
         ms = timed(lambda: engine.ode_run(model, td.pfr_flat_y0(25), td.pfr_flat_par(25), n, 0, 8001, model_arg=arg,
                                           out_last_only=True, var=([4, 5, 6, 8, 7], post_small), out=out, dev=dev), reps=1)
         res[f"C4_packed_pfr_nx25_{label}"] = {"n_traj": n, "ms": ms, "traj_per_s": n / ms * 1e3}
