@@ -1181,6 +1181,19 @@ def ode_warp_source(graph, outs, n_state, n_param):
             if all(values[q] == values[0] + q * step for q in range(m)):
                 decl.append(f"const double s{s} = {arr}[{int(values[0])} + {int(step)} * r];")
                 return f"s{s}"
+            # two-level affine (species x node): index = a + b (r mod P) + c (r div P) -- no table either
+            for P in range(2, m // 2 + 1):
+                if m % P:
+                    continue
+                a0 = values[0]
+                b1 = values[1] - values[0]
+                c1 = values[P] - values[0]
+                if all(values[q] == a0 + b1 * (q % P) + c1 * (q // P) for q in range(m)):
+                    if f"const int q{P} = r / {P};" not in decl:
+                        decl.insert(0, f"const int m{P} = r - q{P} * {P};")
+                        decl.insert(0, f"const int q{P} = r / {P};")
+                    decl.append(f"const double s{s} = {arr}[{int(a0)} + {int(b1)} * m{P} + {int(c1)} * q{P}];")
+                    return f"s{s}"
             name = f"kI{ci}_{s}"
             tables.append(f"SODM_BOTH_TABLES(short, {name}, {m}, {{{', '.join(str(int(v)) for v in values)}}})")
             decl.append(f"const double s{s} = {arr}[SODM_TAB({name})[r]];")

@@ -136,8 +136,11 @@ struct GenWarpSystem {
     }
 };
 
+#ifndef SODM_GEN_WARP_MIN_BLOCKS
+#define SODM_GEN_WARP_MIN_BLOCKS 3       // as for the hand-written reactor kernel: FP64 dependency chains want resident warps
+#endif
 template <class W, typename OutT>
-__global__ void __launch_bounds__(ODE_BLOCK) ode_gen_warp_kernel(const __grid_constant__ OdeLaunch L, int method) {
+__global__ void __launch_bounds__(ODE_BLOCK, SODM_GEN_WARP_MIN_BLOCKS) ode_gen_warp_kernel(const __grid_constant__ OdeLaunch L, int method) {
     extern __shared__ double gen_warp_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
