@@ -13,6 +13,7 @@
 //                which the cell's values actually differ (typically 2 passes), one shared-memory histogram per
 //                distinct prefix among the requested ranks
 #include "common.cuh"
+#include <type_traits>
 #include "noise.cuh"
 
 namespace sodm {
@@ -49,8 +50,15 @@ __global__ void __launch_bounds__(256, 4) gaussian_noise_kernel(const Tin* __res
             float z[4];
             normal_quad(seed, (uint64_t)(traj_id0 + i), (uint32_t)g, z);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (4 * g + q < n_cells) out[(4 * g + q) * ld + i] = (Tout)gaussian_noise(RELATIVE, sigma, (double)x[q], z[q]);
+            for (int q = 0; q < 4; ++q) {
+                if (4 * g + q >= n_cells) continue;
+                if constexpr (std::is_same<Tout, float>::value && sizeof(Tin) == 4) {   // float32 result: no reason to go through FP64
+                    const float xf = (float)x[q], sf = (float)sigma;
+                    out[(4 * g + q) * ld + i] = (Tout)(xf + (RELATIVE ? fabsf(sf * xf) : sf) * z[q]);
+                } else {
+                    out[(4 * g + q) * ld + i] = (Tout)gaussian_noise(RELATIVE, sigma, (double)x[q], z[q]);
+                }
+            }
         }
     }
 }
