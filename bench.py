@@ -306,45 +306,53 @@ def run_gpu_arm(args):
     # sim -> negative-binomial observation noise -> mean and 95 % band over draws (calibration.py:231,245-246), with
     # only the drawn parameters going in and the (time, age) summaries coming out over PCIe
     workflow = None
-    if world == 1 and not args.no_workflow:
+    if not args.no_workflow:
+        from pysodm_b200 import sharding
         del host_out, pipe
         torch.cuda.empty_cache()
         ens = torch.empty((N_STATE, N_OUT, n), dtype=torch.int32, device=dev)
         noisy = torch.empty_like(ens)
-        lo_r, hi_r = int(np.floor((n - 1) * 0.025)), int(np.floor((n - 1) * 0.975))
-        ranks = [lo_r, min(lo_r + 1, n - 1), hi_r, min(hi_r + 1, n - 1)]
+        n_all = n * world                                       # the ensemble of ALL ranks: reductions cross the GPUs
+        lo_r, hi_r = int(np.floor((n_all - 1) * 0.025)), int(np.floor((n_all - 1) * 0.975))
+        ranks = [lo_r, min(lo_r + 1, n_all - 1), hi_r, min(hi_r + 1, n_all - 1)]
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 
         def workflow_step(seed):
             d = draws_host.to(dev, non_blocking=True)
             marks[0].record()
             engine.jump_run("influenza_1718_jump", y0, par, n, 0, N_OUT, TAU, var=(VAR_INDEX, d), tdpf=(table, index),
-                            seed=seed, traj_id0=0, out_dtype=torch.int32, out=ens, status=status, dev=dev)
+                            seed=seed, traj_id0=rank * n, out_dtype=torch.int32, out=ens, status=status, dev=dev)
             marks[1].record()
-            engine.noise("negative_binomial", ens, 0.03, seed=seed, out=noisy, dev=dev)
+            engine.noise("negative_binomial", ens, 0.03, seed=seed, traj_id0=rank * n, out=noisy, dev=dev)
             marks[2].record()
-            mean = engine.draws_sum(noisy, dev=dev)
+            mean = sharding.sum_sharded(engine.draws_sum(noisy, dev=dev))                 # N > 1: all-reduce of the sums
             marks[3].record()
-            band = engine.draws_order_stats(noisy, ranks, dev=dev)
+            band = sharding.order_stats_sharded(noisy, ranks)        # N > 1: radix select in phases, histograms all-reduced
             marks[4].record()
             return mean.cpu(), band.cpu()                      # the step's result reaches the host
 
         workflow_step(50)
-        torch.cuda.synchronize(dev)
+        barrier()
         wf_steps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
         for k in range(wf_steps):
             mean_h, band_h = workflow_step(2000 + k)
-        torch.cuda.synchronize(dev)
+        barrier()
         wf_s = time.perf_counter() - t0
         stages = [marks[i].elapsed_time(marks[i + 1]) for i in range(4)]
-        workflow = {"value": n * wf_steps / wf_s, "unit": UNIT, "ms_per_step": wf_s / wf_steps * 1e3,
+        wf_t = torch.tensor([wf_s] + stages, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(wf_t, op=dist.ReduceOp.MAX)
+        wf_s, stages = float(wf_t[0]), [float(x) for x in wf_t[1:]]
+        workflow = {"value": n_all * wf_steps / wf_s, "unit": UNIT, "ms_per_step": wf_s / wf_steps * 1e3,
                     "stages_ms": dict(zip(["sim", "negative_binomial_noise", "mean", "quantile_band"], stages)),
                     "h2d_bytes_per_step": int(draws_host.numel() * 8),
                     "d2h_bytes_per_step": int((mean_h.numel() + band_h.numel()) * 8),
-                    "gpu_launches_per_step": 4,
-                    "what": "sim -> add_negative_binomial_noise(alpha=0.03) -> mean + 2.5 % / 97.5 % order statistics over "
-                            "draws, all on the device (sodm_noise, sodm_draws_sum, sodm_draws_order_stats)"}
+                    "gpu_launches_per_step": 4 if world == 1 else 4 + 8,
+                    "collectives_per_step": 0 if world == 1 else 7,
+                    "what": "sim -> add_negative_binomial_noise(alpha=0.03) -> mean + 2.5 % / 97.5 % order statistics over the "
+                            "draws of ALL ranks, on the device (sodm_noise, sodm_draws_sum, sodm_draws_order_stats / "
+                            "sodm_draws_select_phase + NCCL all-reduce of sums and radix histograms)"}
         del ens, noisy
 
     # ---- max over ranks, final NCCL gather of per-rank summaries --------------------------------------------
