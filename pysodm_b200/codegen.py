@@ -937,19 +937,40 @@ def jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes,
         if name[0] == "par":
             return f"par[{name[1]}]"
         raise TraceError(f"unexpected input {name}")
-    f_lines, f_exprs = emit(g, all_rates, "float", leaf_f)
+    # Rates that depend neither on the state, nor on the time, nor on a tabulated parameter are constants of the trajectory:
+    # their leave probabilities 1 - exp(-tau rate) are formed once, in `prepare` (as the hand-written functors do), instead of
+    # one expm1 per exit and step.
+    def varies(sym):
+        seen, stack = set(), [sym.i]
+        while stack:
+            i = stack.pop()
+            if i in seen:
+                continue
+            seen.add(i)
+            op, args, _ = g.nodes[i]
+            if op == "in":
+                if args[0][0] in ("y", "t") or (args[0][0] == "par" and tdpf_count and args[0][1] >= tdpf_offset):
+                    return True
+            elif op != "const":
+                stack.extend(args)
+        return False
+    keys = [(name, i, e) for name, per in tr["channels"].items() for i, flat in enumerate(per) for e in range(len(flat))]
+    hoisted = [k for k, sym in zip(keys, all_rates) if not varies(sym)]
+    hoist_index = {k: n for n, k in enumerate(hoisted)}
+    step_rates = [sym for k, sym in zip(keys, all_rates) if k not in hoist_index]
+    f_lines, f_exprs = emit(g, step_rates, "float", leaf_f)
+    f_exprs = iter(f_exprs)
     d_lines, d_exprs = emit(g, all_rates, "double", leaf_d, prefix="u")
-    rate_expr, rate_expr_d, k = {}, {}, 0
-    for name, per in tr["channels"].items():
-        for i, flat in enumerate(per):
-            for e in range(len(flat)):
-                rate_expr[(name, i, e)] = f_exprs[k]
-                rate_expr_d[(name, i, e)] = d_exprs[k]
-                k += 1
+    rate_expr_d = dict(zip(keys, d_exprs))
+    rate_expr = {k: (None if k in hoist_index else next(f_exprs)) for k in keys}
+    h_lines, h_exprs = emit(g, [sym for k, sym in zip(keys, all_rates) if k in hoist_index], "float",
+                            lambda nm: f"(float)par[{nm[1]}]", prefix="c")
+    pre_lines = h_lines + [f"pre.p[{n}] = leave_prob({x}, tau);" for n, x in enumerate(h_exprs)]
     put = []
     for name, e, m, drawn, first in groups:
         j = state_off[name] + e
-        ps = [f"leave_prob({rate_expr[(name, i, e)]}, tau)" for i in range(m)]
+        ps = [f"pre.p[{hoist_index[(name, i, e)]}]" if (name, i, e) in hoist_index else f"leave_prob({rate_expr[(name, i, e)]}, tau)"
+              for i in range(m)]
         put.append("{")
         for i in range(m):
             put.append(f"    const float p{i} = {ps[i]};")
@@ -984,11 +1005,13 @@ struct GenModel {{
     static constexpr int NDRAW = {n_draw};
     static constexpr uint64_t DEP_MASK = {dep_mask}ull;
     static constexpr bool USES_TIME = {'true' if uses_time else 'false'};
-    struct Pre {{ float par[{npar_arr}]; }};
-    __host__ __device__ static Pre prepare(const double* par, float, bool) {{
+    struct Pre {{ float par[{npar_arr}]; float p[{max(len(hoisted), 1)}]; }};
+    __host__ __device__ static Pre prepare(const double* par, float tau, bool) {{
         Pre pre;
+        (void)tau;
 #pragma unroll
         for (int e = 0; e < {npar_arr}; ++e) pre.par[e] = (float)par[e];
+{_indent(pre_lines)}
         return pre;
     }}
     // rates in FP32 as in the hand-written functors; law of the draws: jump_models.cuh header (reference base.py:283-348)
