@@ -167,20 +167,21 @@ struct SirSiJump {
 // channels   : S->E (4), E->Ip (4), Ip->Iud (4), Ip->Id (4), Iud->R (4), Id->R (4)
 // ------------------------------------------------------------------------------------------------
 // Slot of draw `kind` (0 S->E, 1 E->Ip, 2 Ip->Iud, 3 Ip->Id, 4 Iud->R, 5 Id->R) of age group a.
-// The ORDER in which a lane walks its draws changes nothing in the law but 7 % in the run time (profiles/r1_sampler_ab.txt):
+// The ORDER in which a lane walks its draws changes nothing in the law but 15 % in the run time (profiles/r1_sampler_ab.txt):
 // lanes start a step together and drift apart, so the draws with small means (cheap, and of mixed regime: trivial /
 // inversion / BTRS) go first, while the lanes still move in step, and the large-mean BTRS draws last, where lanes that have
-// drifted apart at least execute the same code.  Default: age groups by ascending population (0, 3, 1, 2), within a group
-// Id->R, Iud->R, Ip->Iud, Ip->Id, E->Ip, S->E (130.9 ms per 10^6 trajectories); 0 = by age group as declared, 6a + kind
-// (137.4 ms); 1 = by compartment (147.8 ms).
+// drifted apart at least execute the same code.  Default (11): all 24 draws by ascending season-average mean n min(p, 1-p)
+// (125.8 ms per 10^6 trajectories); 6 = age groups by ascending population, within a group Id->R, Iud->R, Ip pair, E->Ip,
+// S->E (130.9 ms); 0 = as declared, 6a + kind (137.4 ms); 1 = by compartment, S->E first (147.8 ms).
 #ifndef SODM_FLU_SLOT_ORDER
-#define SODM_FLU_SLOT_ORDER 6
+#define SODM_FLU_SLOT_ORDER 11
 #endif
 __host__ __device__ constexpr int flu_slot(int a, int kind) {
     switch (SODM_FLU_SLOT_ORDER) {
         case 0: return 6 * a + kind;
         case 1: return kind == 0 ? a : kind == 1 ? 4 + a : kind == 2 ? 8 + 2 * a : kind == 3 ? 9 + 2 * a : kind == 4 ? 16 + a : 20 + a;
-        default: return 6 * (a == 0 ? 0 : a == 3 ? 1 : a == 1 ? 2 : 3) + (kind == 0 ? 5 : kind == 1 ? 4 : kind == 2 ? 2 : kind == 3 ? 3 : kind == 4 ? 1 : 0);
+        case 6: return 6 * (a == 0 ? 0 : a == 3 ? 1 : a == 1 ? 2 : 3) + (kind == 0 ? 5 : kind == 1 ? 4 : kind == 2 ? 2 : kind == 3 ? 3 : kind == 4 ? 1 : 0);
+        default: { constexpr int t[4][6] = {{4, 5, 1, 2, 0, 3}, {17, 16, 14, 15, 13, 8}, {22, 23, 19, 20, 21, 18}, {12, 11, 9, 10, 7, 6}}; return t[a][kind]; }
     }
 }
 
