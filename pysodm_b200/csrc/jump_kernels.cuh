@@ -23,6 +23,10 @@ constexpr int JUMP_BLOCK = SODM_JUMP_BLOCK;
 #define SODM_COOP_MIN_BLOCKS 5
 #endif
 
+// shared-memory words of the per-lane draw order (one byte per draw and lane), for functors that ask for re-sorting
+template <class M>
+__host__ __device__ constexpr int order_words() { return functor_reorder<M>::value > 0 ? (M::NDRAW * JUMP_BLOCK + 3) / 4 : 0; }
+
 template <class M, typename OutT, bool ALIGNED, bool COOP>
 __global__ void __launch_bounds__(JUMP_BLOCK, COOP ? SODM_COOP_MIN_BLOCKS : SODM_WALK_MIN_BLOCKS) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
     extern __shared__ float smem[];
@@ -43,7 +47,9 @@ __global__ void __launch_bounds__(JUMP_BLOCK, COOP ? SODM_COOP_MIN_BLOCKS : SODM
     w.qx = w.qs + COOP_QS_CAP;
     w.stride = JUMP_BLOCK;
     w.lane = lane;
-    float* table = smem + 2 * M::NDRAW * JUMP_BLOCK + (COOP ? WARPS * QW : 0);       // the walk sampler has no queues
+    // the walk sampler has no queues; it keeps one byte per (draw, lane) for the lane's draw order instead
+    w.ord = reinterpret_cast<uint8_t*>(smem + 2 * M::NDRAW * JUMP_BLOCK) + warp * 32;
+    float* table = smem + 2 * M::NDRAW * JUMP_BLOCK + (COOP ? WARPS * QW : order_words<M>());
     const int n_tab = L.n_tdpf_values * M::TDPF_COUNT;
     for (int e = threadIdx.x; e < n_tab; e += blockDim.x) table[e] = (float)L.tdpf_table[e];   // ABI speaks FP64, rates are FP32
     __syncthreads();
@@ -65,7 +71,8 @@ static int launch_jump(const JumpLaunch& L, int method, bool aligned, cudaStream
     const unsigned grid = (unsigned)((L.n_traj + JUMP_BLOCK - 1) / JUMP_BLOCK);
     if (method == SODM_JUMP_TAU_LEAP) {
         const bool coop = (L.compat & TUNE_COOPERATIVE) != 0u;
-        const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK + (coop ? (size_t)(JUMP_BLOCK / 32) * coop_queue_words(M::NDRAW) : 0) +
+        const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK +
+                             (coop ? (size_t)(JUMP_BLOCK / 32) * coop_queue_words(M::NDRAW) : (size_t)order_words<M>()) +
                              (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
         void (*kernel)(JumpLaunch) = aligned ? (coop ? tau_leap_kernel<M, OutT, true, true> : tau_leap_kernel<M, OutT, true, false>)
                                              : (coop ? tau_leap_kernel<M, OutT, false, true> : tau_leap_kernel<M, OutT, false, false>);

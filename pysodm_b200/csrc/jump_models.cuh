@@ -195,8 +195,12 @@ __host__ __device__ constexpr bool flu_slots_valid() {       // a permutation of
 }
 static_assert(flu_slots_valid(), "SODM_FLU_SLOT_ORDER does not describe a valid slot order");
 
+#ifndef SODM_FLU_REORDER_EVERY
+#define SODM_FLU_REORDER_EVERY 0
+#endif
 struct InfluenzaJump {
     static constexpr int NS = 28, NPAR = 24, NCH = 24, TDPF_OFFSET = 8, TDPF_COUNT = 16;
+    static constexpr int REORDER_EVERY = SODM_FLU_REORDER_EVERY;       // 0: the hand-tuned static slot order below
     struct Pre { float beta, cE, cD; float cIp0[4], cIp1[4]; };
 
     __host__ __device__ static Pre prepare(const double* par, float tau, bool quirk) {

@@ -116,6 +116,7 @@ struct WorkList {
     uint16_t* qx;       // candidates the squeeze could not settle, waiting for the exact test; payload = k, log(scaled v)
     uint32_t* qx_k;
     float* qx_l;
+    uint8_t* ord;       // per-lane walk: the order in which this lane takes its draws, [q * stride + lane] -> slot (or null)
     int stride;
     int lane;
     unsigned lanes;     // device: lanes of the warp that run a trajectory
@@ -378,16 +379,68 @@ struct WalkRng {
     uint32_t w0, w1, w2, w3;
     bool second;
 };
+// Steps between re-sorts of a lane's draw order: a functor declares `static constexpr int REORDER_EVERY = K` to have its
+// draws re-sorted every K steps (generated models: nobody tuned their slot order); without the member -- the hand-written
+// functors, whose slot order is tuned by hand -- the order is the functor's own.  Measured on influenza (ms per 10^6):
+// declaration order 137.4; re-sorted every 4 / 16 / 64 / 128 steps 135.0 / 129.0 / 127.9 / 126.6; sorted ONCE at the first
+// step 125.6; best hand-tuned static order 125.8.  Frequent re-sorting loses because every lane then follows its own
+// order and the lanes of a warp stop sharing slots; one sort from the (shared or similar) initial state keeps them aligned.
+template <class M, class = void> struct functor_reorder { static constexpr int value = 0; };
+template <class M> struct functor_reorder<M, decltype((void)M::REORDER_EVERY)> { static constexpr int value = M::REORDER_EVERY; };
+
+// Units of the draw list: a slot together with the slots conditional on it (bit d of DEP_MASK: d belongs to the unit of d-1).
 template <int NDRAW, uint64_t DEP_MASK>
+struct DrawUnits {
+    int n_units = 0;
+    int first[NDRAW] = {};
+    int size[NDRAW] = {};
+    constexpr DrawUnits() {
+        for (int d = 0; d < NDRAW; ++d) {
+            if ((DEP_MASK >> d) & 1ull) ++size[n_units - 1];
+            else { first[n_units] = d; size[n_units] = 1; ++n_units; }
+        }
+    }
+};
+
+// Re-sort this lane's draw order by ascending current mean n min(p, 1 - p) of each unit's first slot.  The ORDER changes
+// nothing in the law; it decides how well the lanes of a warp share code paths: lanes start a step together and drift
+// apart, so cheap small-mean draws (of mixed regime) go first and the large-mean BTRS draws last, where drifted lanes
+// still execute the same instructions (measured on influenza, static orders: 137 -> 126 ms per 10^6 trajectories,
+// profiles/r1_sampler_ab.txt).  Sorting by the lane's OWN state keeps a trajectory independent of its warp neighbours
+// (results do not depend on sharding or chunking).  Branch-free rank sort: NU^2 compares per re-sort.
+template <int NDRAW, uint64_t DEP_MASK>
+__host__ __device__ __forceinline__ void reorder_draws(WorkList& w) {
+    constexpr DrawUnits<NDRAW, DEP_MASK> U{};
+    const int S = w.stride, lane = w.lane;
+    float key[NDRAW];
+#pragma unroll
+    for (int u = 0; u < U.n_units; ++u) {
+        const float p = w.p[U.first[u] * S + lane];
+        const float k = (float)w.n[U.first[u] * S + lane] * fminf(p, 1.0f - p);
+        key[u] = k == k ? k : 0.0f;                              // NaN probabilities are flagged by the sampler; keep a total order
+    }
+#pragma unroll
+    for (int u = 0; u < U.n_units; ++u) {
+        int pos = 0;
+#pragma unroll
+        for (int v = 0; v < U.n_units; ++v)
+            if (v != u) pos += (key[v] < key[u] || (key[v] == key[u] && v < u)) ? U.size[v] : 0;
+#pragma unroll
+        for (int e = 0; e < U.size[u]; ++e) w.ord[(pos + e) * S + lane] = (uint8_t)(U.first[u] + e);
+    }
+}
+
+template <int NDRAW, uint64_t DEP_MASK, bool REORDERED>
 __host__ __device__ __forceinline__ void sample_worklist_walk(WalkRng& rng, WorkList& w, uint32_t& st) {
     const int S = w.stride, lane = w.lane;
-    int d = 0, chain = 0;                // chain = what the earlier exits of the same compartment element have taken
+    int q = 0, chain = 0;                // chain = what the earlier exits of the same compartment element have taken
     // Every trip is one attempt that consumes exactly two Philox words, and every lane starts a step on a fresh block
     // (the half-used one of the previous step is dropped): the lanes of a warp then refill on the same trips, so the
     // generator -- a sixth of the kernel's instructions -- always runs with the whole warp.  Letting each lane carry
     // its leftover pair across steps halves the active lanes per refill and costs 11 % (profiles/r1_sampler_ab.txt).
     rng.second = false;
-    while (d < NDRAW) {
+    while (q < NDRAW) {
+        const int d = REORDERED ? (int)w.ord[q * S + lane] : q;
         int n = w.n[d * S + lane];
         const float p = w.p[d * S + lane];
         const bool dep = (DEP_MASK >> d) & 1ull;
@@ -404,7 +457,7 @@ __host__ __device__ __forceinline__ void sample_worklist_walk(WalkRng& rng, Work
             if (k < 0) { st |= ST_BAD_PROB; k = 0; }
             w.n[d * S + lane] = k;
             chain = dep ? chain + k : k;
-            ++d;
+            ++q;
         }
     }
 }
@@ -456,7 +509,13 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
         else M::propose(y, pre, tab, tau, quirk, w);
         key.step = (uint32_t)k;
         if constexpr (COOP) sample_worklist_coop<M::NDRAW, (uint64_t)M::DEP_MASK>(key, w, st);
-        else sample_worklist_walk<M::NDRAW, (uint64_t)M::DEP_MASK>(rng, w, st);
+        else {
+            constexpr int EVERY = functor_reorder<M>::value;
+            if constexpr (EVERY > 0) {
+                if (k % EVERY == 0) reorder_draws<M::NDRAW, (uint64_t)M::DEP_MASK>(w);
+            }
+            sample_worklist_walk<M::NDRAW, (uint64_t)M::DEP_MASK, (EVERY > 0)>(rng, w, st);
+        }
         M::apply(y, w);
         if (ALIGNED) {
             if (--until_out == 0) {

@@ -189,7 +189,8 @@ static int launch_plugin_jump(const JumpLaunch& L, int method, bool aligned, int
         if (dtype != SODM_F64) return fail(SODM_EUNSUPPORTED, "generated models write SSA output as float64");
         ssa_kernel<M, double><<<grid, JUMP_BLOCK, 0, stream>>>(L);
     } else {
-        const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
+        const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)order_words<M>() +
+                             (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
         void (*kernel)(JumpLaunch) = nullptr;
         if (aligned && dtype == SODM_I32) kernel = tau_leap_kernel<M, int32_t, true, false>;
         else if (aligned && dtype == SODM_F64) kernel = tau_leap_kernel<M, double, true, false>;

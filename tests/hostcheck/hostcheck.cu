@@ -24,7 +24,8 @@ static void run_host(const JumpLaunch& L, int method, bool aligned) {
         uint16_t qm[M::NDRAW], qs[COOP_QS_CAP], qx[COOP_QX_CAP];
         uint32_t qsu[COOP_QS_CAP], qsv[COOP_QS_CAP], qxk[COOP_QX_CAP];
         float qxl[COOP_QX_CAP];
-        WorkList w{wn, wp, qm, qs, qsu, qsv, qx, qxk, qxl, 1, 0, 1u};
+        uint8_t ord[M::NDRAW];
+        WorkList w{wn, wp, qm, qs, qsu, qsv, qx, qxk, qxl, ord, 1, 0, 1u};
         if (method == SODM_JUMP_TAU_LEAP) {
             const bool walk = (L.compat & TUNE_COOPERATIVE) != 0u;   // template flag = cooperative sampler
             if (aligned) { if (walk) tau_leap_trajectory<M, OutT, true, true>(L, i, true, table.data(), w);
