@@ -1,0 +1,385 @@
+"""Ensemble MCMC with ONE batched objective evaluation per half-ensemble update.
+
+Next-row seam of the hot path ("emcee via vectorize=True").  The reference's
+`run_EnsembleSampler` (`/root/reference/src/pySODM/optimization/mcmc.py:15-231`) hands the objective to
+`emcee.EnsembleSampler` together with a process pool, which scores the proposals of half the walkers one by one
+(`:172-176`).  Here the proposals of a half go through `objective.batch(Q)` -- one launch of the simulation + likelihood
+kernels for all of them when the objective is a `pysodm_b200.objective_functions.log_posterior_probability` -- while the
+walker bookkeeping (D <= ~10 numbers per walker) stays on the host, so 10^5 walkers cost what 10^5 PSO particles cost.
+
+emcee is a third-party dependency of the reference (unpinned in `setup.py`, not vendored, not in this image), so the
+sampler is a restatement of the published algorithms the reference's default cocktail (`mcmc.py:22-28`) names:
+  stretch move        Goodman & Weare 2010, a = 2, acceptance z^(D-1) p(q)/p(s);
+  differential evol.  ter Braak 2006, q = s + gamma (c_a - c_b) + eps, gamma = 2.38/sqrt(2D) or 1, eps ~ N(0, 1e-5^2);
+  snooker             ter Braak & Vrugt 2008, gamma = 1.7, acceptance (|q-z|/|s-z|)^(D-1) p(q)/p(s);
+  KDE move            independence proposal from a Gaussian KDE (Scott's rule) of the complementary walkers.
+Every move updates the ensemble in two halves (a random split per iteration), the walkers of one half proposing from
+the other, which is what keeps the parallel update in detailed balance (Foreman-Mackey et al. 2013).  Each move leaves
+the target invariant (tests/test_mcmc_cpu.py samples a correlated Gaussian with every move on its own and with the
+cocktail); a seeded run does not reproduce emcee's random stream.
+
+Chains are kept in memory and checkpointed as `.npz` (the reference's HDF5 backend needs h5py, absent here); samples
+are written in the reference's NetCDF layout through `pysodm_b200.samples`.  The diagnostic figures of the reference
+need matplotlib and are outside the path.
+"""
+import datetime
+import os
+import sys
+
+import numpy as np
+
+from ..samples import dump_samples
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# moves: propose(s[Ns, D], c[Nc, D], rng) -> q[Ns, D], log of the Hastings factor [Ns]
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _pick_distinct(rng, n_pool, n_rows, k):
+    """k distinct indices into a pool of n_pool, independently for each of n_rows rows."""
+    if n_pool < k:
+        raise ValueError(f"a move needs at least {k} walkers in the complementary half, got {n_pool}")
+    idx = np.empty((n_rows, k), dtype=np.int64)
+    idx[:, 0] = rng.integers(0, n_pool, n_rows)
+    for j in range(1, k):
+        # draw from the n_pool - j remaining slots and step over the ones already taken (in ascending order)
+        r = rng.integers(0, n_pool - j, n_rows)
+        taken = np.sort(idx[:, :j], axis=1)
+        for t in range(j):
+            r += r >= taken[:, t]
+        idx[:, j] = r
+    return idx
+
+
+class StretchMove:
+    def __init__(self, a=2.0, **_ignored):
+        self.a = float(a)
+
+    def propose(self, s, c, rng):
+        Ns, D = s.shape
+        zz = ((self.a - 1.0) * rng.random(Ns) + 1.0) ** 2 / self.a
+        other = c[rng.integers(0, len(c), Ns)]
+        return other - (other - s) * zz[:, None], (D - 1.0) * np.log(zz)
+
+
+class DEMove:
+    def __init__(self, sigma=1.0e-5, gamma0=None):
+        self.sigma, self.gamma0 = float(sigma), gamma0
+
+    def propose(self, s, c, rng):
+        Ns, D = s.shape
+        g0 = 2.38 / np.sqrt(2.0 * D) if self.gamma0 is None else float(self.gamma0)
+        ab = _pick_distinct(rng, len(c), Ns, 2)
+        q = s + g0 * (c[ab[:, 0]] - c[ab[:, 1]]) + self.sigma * rng.standard_normal(Ns)[:, None]
+        return q, np.zeros(Ns)
+
+
+class DESnookerMove:
+    def __init__(self, gammas=1.7):
+        self.gammas = float(gammas)
+
+    def propose(self, s, c, rng):
+        Ns, D = s.shape
+        w = _pick_distinct(rng, len(c), Ns, 3)
+        z, z1, z2 = c[w[:, 0]], c[w[:, 1]], c[w[:, 2]]
+        delta = s - z
+        norm = np.linalg.norm(delta, axis=1)
+        u = delta / norm[:, None]
+        q = s + u * (self.gammas * (np.sum(u * z1, axis=1) - np.sum(u * z2, axis=1)))[:, None]
+        return q, (D - 1.0) * (np.log(np.linalg.norm(q - z, axis=1)) - np.log(norm))
+
+
+class KDEMove:
+    """`max_points` bounds the kernel count (a uniform subset of the complementary half, chosen without looking at the
+    walkers being moved, is as valid a basis for an independence proposal as the whole half): the density evaluations
+    are O(Ns * points) on the host, which at 10^5 walkers would dwarf the batched objective."""
+
+    def __init__(self, bw_method=None, max_points=4096):
+        self.bw_method, self.max_points = bw_method, max_points
+
+    def propose(self, s, c, rng):
+        from scipy.stats import gaussian_kde
+        if self.max_points and len(c) > self.max_points:
+            c = c[rng.choice(len(c), self.max_points, replace=False)]
+        kde = gaussian_kde(c.T, bw_method=self.bw_method)
+        q = kde.resample(len(s), seed=rng).T
+        return q, kde.logpdf(s.T) - kde.logpdf(q.T)
+
+
+def default_moves():
+    """The reference's cocktail and weights (`mcmc.py:22-28`)."""
+    return [(DEMove(), 0.5 * 0.5 * 0.9), (DEMove(gamma0=1.0), 0.5 * 0.5 * 0.1), (DESnookerMove(), 0.5 * 0.5),
+            (KDEMove(bw_method="scott"), 0.25), (StretchMove(), 0.25)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# integrated autocorrelation time (what `emcee.autocorr.integrated_time(chain, tol=0)` reports to the reference's
+# convergence test, `visualization.py:49`, `mcmc.py:215-222`): FFT autocorrelation averaged over walkers, Sokal window c=5
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _autocorr_1d(x):
+    n = 1 << int(np.ceil(np.log2(max(len(x), 1))))
+    f = np.fft.fft(x - np.mean(x), n=2 * n)
+    acf = np.fft.ifft(f * np.conjugate(f))[:len(x)].real
+    return acf / acf[0] if acf[0] != 0 else np.full(len(x), np.nan)
+
+
+def integrated_time(chain, c=5.0):
+    """chain[iteration, walker, D] -> tau[D]."""
+    chain = np.asarray(chain, dtype=np.float64)
+    n_t, n_w, n_d = chain.shape
+    tau = np.empty(n_d)
+    for d in range(n_d):
+        f = np.zeros(n_t)
+        for k in range(n_w):
+            f += _autocorr_1d(chain[:, k, d])
+        taus = 2.0 * np.cumsum(f / n_w) - 1.0
+        m = np.arange(len(taus)) < c * taus
+        tau[d] = taus[np.argmin(m) if np.any(~m) else len(taus) - 1]
+    return tau
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the sampler
+# ---------------------------------------------------------------------------------------------------------------------
+
+class EnsembleSampler:
+    """The part of `emcee.EnsembleSampler` the reference uses: `sample` / `run_mcmc`, `get_chain`, `get_log_prob`,
+    `iteration`, `acceptance_fraction`, `get_autocorr_time`; `log_prob_fn` is scored through its `.batch` when it has one."""
+
+    def __init__(self, nwalkers, ndim, log_prob_fn, moves=None, args=None, kwargs=None, seed=None, backend=None):
+        self.nwalkers, self.ndim = int(nwalkers), int(ndim)
+        if self.nwalkers < 2 * self.ndim:
+            raise ValueError("The number of walkers must be at least twice the number of parameters")
+        args, kwargs = tuple(args or ()), dict(kwargs or {})
+        if hasattr(log_prob_fn, "batch") and not args and not kwargs:
+            self._score = lambda X: np.asarray(log_prob_fn.batch(np.array(X, dtype=np.float64)), dtype=np.float64)
+        else:
+            self._score = lambda X: np.array([log_prob_fn(np.array(x, dtype=np.float64), *args, **kwargs) for x in X],
+                                             dtype=np.float64)
+        moves = default_moves() if moves is None else moves
+        if not isinstance(moves, (list, tuple)):
+            moves = [(moves, 1.0)]
+        self._moves = [m[0] if isinstance(m, (list, tuple)) else m for m in moves]
+        w = np.array([m[1] if isinstance(m, (list, tuple)) else 1.0 for m in moves], dtype=np.float64)
+        self._weights = w / w.sum()
+        self.rng = np.random.default_rng(seed)
+        self.backend = backend
+        self._store = np.empty((0, self.nwalkers, self.ndim))    # capacity >= _n rows; rows [:_n] are the chain
+        self._store_lp = np.empty((0, self.nwalkers))
+        self._n = 0
+        self._accepted = np.zeros(self.nwalkers)
+        self.n_batches = 0                               # objective launches so far
+        if backend is not None and os.path.exists(backend):
+            with np.load(backend) as f:
+                self._store, self._store_lp, self._accepted = f["chain"], f["log_prob"], f["accepted"]
+            if self._store.shape[1:] != (self.nwalkers, self.ndim):
+                raise ValueError(f"backend '{backend}' holds chains of shape {self._store.shape[1:]}, "
+                                 f"expected {(self.nwalkers, self.ndim)}")
+            self._n = self._store.shape[0]
+
+    # -- storage ---------------------------------------------------------------------------------------------------
+    @property
+    def iteration(self):
+        return self._n
+
+    @property
+    def _chain(self):
+        return self._store[:self._n]
+
+    @property
+    def _log_prob(self):
+        return self._store_lp[:self._n]
+
+    @property
+    def acceptance_fraction(self):
+        return self._accepted / max(self.iteration, 1)
+
+    def get_chain(self, discard=0, thin=1, flat=False):
+        v = self._chain[discard + thin - 1::thin]
+        return v.reshape(-1, self.ndim) if flat else v
+
+    def get_log_prob(self, discard=0, thin=1, flat=False):
+        v = self._log_prob[discard + thin - 1::thin]
+        return v.reshape(-1) if flat else v
+
+    def get_autocorr_time(self, discard=0, thin=1, c=5.0, **_ignored):
+        return thin * integrated_time(self.get_chain(discard=discard, thin=thin), c=c)
+
+    def save(self, filename=None):
+        filename = filename or self.backend
+        if filename:
+            tmp = filename + ".tmp.npz"
+            np.savez(tmp, chain=self._chain, log_prob=self._log_prob, accepted=self._accepted)
+            os.replace(tmp, filename)
+
+    # -- sampling --------------------------------------------------------------------------------------------------
+    def _check_start(self, x):
+        x = np.array(x, dtype=np.float64)
+        if x.shape != (self.nwalkers, self.ndim):
+            raise ValueError(f"incompatible input dimensions {x.shape}, expected {(self.nwalkers, self.ndim)}")
+        if not np.all(np.isfinite(x)):
+            raise ValueError("Initial state has non-finite coordinates")
+        if np.linalg.cond(np.atleast_2d(np.cov(x, rowvar=False))) > 1e8:
+            raise ValueError("Initial state has a large condition number. Make sure that your walkers are linearly "
+                             "independent for the best performance")
+        return x
+
+    def sample(self, initial_state, iterations=1, store=True, progress=False, log_prob0=None, **_ignored):
+        """Generator: one ensemble update (two half updates, two batched evaluations) per item."""
+        x = self._check_start(initial_state)
+        if log_prob0 is None:
+            lp = self._score(x)
+            self.n_batches += 1
+        else:
+            lp = np.array(log_prob0, dtype=np.float64)
+        if np.any(np.isnan(lp)):
+            raise ValueError("The initial log_prob was NaN")
+        if store and self._store.shape[0] < self._n + iterations:
+            self._store = np.concatenate([self._chain, np.empty((iterations, self.nwalkers, self.ndim))])
+            self._store_lp = np.concatenate([self._log_prob, np.empty((iterations, self.nwalkers))])
+        half = self.nwalkers // 2
+        for it in range(iterations):
+            move = self._moves[self.rng.choice(len(self._moves), p=self._weights)]
+            order = self.rng.permutation(self.nwalkers)
+            for mine, others in ((order[:half], order[half:]), (order[half:], order[:half])):
+                q, log_factor = move.propose(x[mine], x[others], self.rng)
+                new_lp = self._score(q)                     # may clip q in place, like the reference's objective
+                self.n_batches += 1
+                if np.any(np.isnan(new_lp)):
+                    raise ValueError("Probability function returned NaN")
+                with np.errstate(invalid="ignore"):
+                    log_ratio = log_factor + new_lp - lp[mine]
+                log_ratio[~np.isfinite(new_lp)] = -np.inf
+                ok = log_ratio > np.log(self.rng.random(len(mine)))
+                x[mine[ok]], lp[mine[ok]] = q[ok], new_lp[ok]
+                self._accepted[mine[ok]] += 1
+            if store:
+                self._store[self._n], self._store_lp[self._n] = x, lp
+                self._n += 1
+            if progress:
+                print(f"\riteration {it + 1}/{iterations}", end="" if it + 1 < iterations else "\n", file=sys.stderr)
+            yield x, lp
+
+    def run_mcmc(self, initial_state, nsteps, **kwargs):
+        out = None
+        for out in self.sample(initial_state, iterations=nsteps, **kwargs):
+            pass
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's front end
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _validate_settings_dict(settings_dict):
+    """NetCDF-exportable values only (reference `mcmc.py:380-412`): int/float/bool/str, homogeneous non-empty lists
+    of those, 1-D integer or float arrays."""
+    for key, value in settings_dict.items():
+        if isinstance(value, list):
+            ok = bool(value) and type(value[0]) in (int, float, str, bool) and all(type(v) is type(value[0]) or
+                                                                                 isinstance(v, type(value[0])) for v in value)
+            why = "lists must be homogeneous and contain only int, float, bool or str."
+        elif isinstance(value, np.ndarray):
+            ok = value.ndim == 1 and value.dtype.kind in "if"
+            why = "numpy arrays must be 1D and contain only int or float."
+        else:
+            ok = isinstance(value, (int, float, bool, str))
+            why = ("valid types are: (scalar values) int, float, bool, str. (arrays) homogeneous lists containing int, "
+                   "float, str, bool. 1D numpy arrays containing int or float.")
+        if not ok:
+            raise TypeError(f"Invalid datatype in `settings_dict` for key: '{key}' (type: {type(value)}). {why}")
+
+
+def _directory(path):
+    if not path:
+        return os.getcwd() + "/"
+    path = os.path.join(os.getcwd(), path if path.endswith("/") else path + "/")
+    os.makedirs(path, exist_ok=True)
+    return path
+
+
+def run_EnsembleSampler(pos, max_n, identifier, objective_function, objective_function_args=None,
+                        objective_function_kwargs=None, moves=None, fig_path=None, samples_path=None, print_n=10,
+                        discard=0, thin=1, backend=None, processes=1, progress=True, settings_dict={}, seed=None):
+    """The reference's `run_EnsembleSampler` (`mcmc.py:15-231`): set up the sampler (fresh, or continued from `backend`),
+    run at most `max_n` iterations, every `print_n` iterations write the samples file and test convergence (chain longer
+    than 50 integrated autocorrelation times AND their mean changed by < 3 %).  `processes` and `fig_path` are accepted
+    for compatibility (the evaluation is batched; figures are not drawn).  Returns (sampler, samples)."""
+    pos = np.asarray(pos, dtype=np.float64)
+    samples_path = _directory(samples_path)
+    run_date = str(datetime.date.today())
+    nwalkers, ndim = pos.shape
+    settings_dict = dict(settings_dict)
+    settings_dict.update({"discard": discard, "thin": thin})
+    _validate_settings_dict(settings_dict)
+    print("\nMarkov-Chain Monte-Carlo sampling\n=================================\n")
+    if not backend:
+        fn_backend = samples_path + f"{identifier}_BACKEND_{run_date}.npz"
+        if os.path.exists(fn_backend):
+            os.remove(fn_backend)
+        print(f"Created new backend: '{fn_backend}'\n\nStarting new run\n----------------\n")
+    else:
+        fn_backend = backend if os.path.exists(backend) else os.path.splitext(backend)[0] + ".npz"
+        if not os.path.exists(fn_backend):
+            raise FileNotFoundError("backend not found.")
+        print(f"Found existing backend:'{fn_backend}'\n\nContinuing run\n--------------\n")
+    sampler = EnsembleSampler(nwalkers, ndim, objective_function, moves=moves, args=objective_function_args,
+                              kwargs=objective_function_kwargs, seed=seed, backend=fn_backend)
+    if backend:
+        pos = sampler.get_chain()[-1]
+    fn_samples = samples_path + f"{identifier}_SAMPLES_{run_date}.nc"
+    print(f"Parameters: {ndim}\nMarkov chains: {nwalkers}\nBatched objective evaluation: {nwalkers // 2} walkers per call")
+    print(f"Iterations: {max_n}" + (f" (found {sampler.iteration} previous iterations)" if backend else ""))
+    print(f"Automatically checking convergence every {print_n} iterations")
+    print(f"Saving samples every {print_n} iterations\nSamples: {fn_samples}\n")
+    sys.stdout.flush()
+
+    iteration_0, old_tau, samples, done = sampler.iteration, np.inf, None, 0
+    for _ in sampler.sample(pos, iterations=max_n, progress=progress, store=True):
+        done += 1
+        if not ((sampler.iteration % print_n == 0) or (done == max_n)):
+            continue
+        sampler.save()
+        samples = dump_samples(sampler.get_chain(discard=discard, thin=thin), objective_function.parameter_shapes,
+                               filename=fn_samples, settings_dict=settings_dict)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            tau = integrated_time(sampler.get_chain())
+            converged = np.all(np.max(tau) * 50.0 < sampler.iteration)
+            converged &= np.all(np.abs(np.mean(old_tau) - np.mean(tau)) / np.mean(tau) < 0.03)
+        old_tau = tau
+        if converged:
+            print("Convergence: The chain is longer than 50 times the intergrated autocorrelation time.\n")
+            break
+        print("Non-convergence: The chain is shorter than 50 times the integrated autocorrelation time.\n")
+        sys.stdout.flush()
+    return sampler, samples
+
+
+def perturbate_theta(theta, pert, multiplier=2, bounds=None, verbose=None):
+    """Starting positions of `multiplier * len(theta)` chains: the estimate, clipped so that the perturbed values stay
+    inside the bounds, times `1 + pert * U(-1, 1)`; redrawn while the matrix is singular (reference `mcmc.py:234-308`,
+    same use of NumPy's global generator).  Returns (ndim, nwalkers, pos)."""
+    if len(theta) != len(pert):
+        raise Exception('The parameter value array "theta" must have the same length as the perturbation value array "pert".')
+    if len(bounds) != len(theta):
+        raise Exception("If bounds is not None, it must contain a tuple for every parameter in theta")
+    theta = np.array(theta)
+    low = [b[0] / (1 - p) for b, p in zip(bounds, pert)]
+    high = [b[1] / (1 + p) for b, p in zip(bounds, pert)]
+    ndim = len(theta)
+    nwalkers = ndim * multiplier
+    theta = np.clip(theta, low, high)
+    for attempt in range(21):
+        pos = theta + theta * pert * np.random.uniform(low=-1, high=1, size=(nwalkers, ndim))
+        if np.linalg.cond(pos) != np.inf:
+            break
+        if verbose:
+            print("Condition number too high, recalculating perturbations. Perhaps one or more of the bounds is zero?")
+            sys.stdout.flush()
+    else:
+        raise Exception("Attempted 20 times to perturb parameter values but the condition number remains too large.")
+    if verbose:
+        print("Total number of markov chains: " + str(nwalkers) + "\n")
+        sys.stdout.flush()
+    return ndim, nwalkers, pos

@@ -235,3 +235,34 @@ def test_pso_calibration_recovers_parameter(td, capsys):
     assert abs(theta[0] - 0.9) / 0.9 < 0.02
     theta_nm, _ = optimization.nelder_mead(lpp, np.array([0.6]), [0.2], max_iter=30)
     assert abs(theta_nm[0] - 0.9) / 0.9 < 0.02
+
+
+def test_ensemble_mcmc_samples_the_posterior(td, tmp_path, monkeypatch):
+    """The reference's MCMC leg in miniature (src/tests/test_calibration.py:195-209): walkers started around an
+    estimate sample the posterior of beta; every half-ensemble update is ONE batched device evaluation.  The chain's
+    mean and spread are compared with the posterior tabulated on a grid through the same objective."""
+    from pysodm_b200 import tutorial_models as tm
+    from pysodm_b200.objective_functions import ll_negative_binomial, log_posterior_probability
+    from pysodm_b200.optimization import mcmc
+    monkeypatch.chdir(tmp_path)
+    truth = tm.ODE_SIR_rate({"S": 1_000_000 - 10, "I": 10}, {"beta": 0.9, "gamma": 0.2})
+    t = np.arange(10, 31, 4)
+    data = pd.Series(truth.sim(30)["I"].values[t], index=pd.Index(t.astype(float), name="time"))
+    model = tm.ODE_SIR_rate({"S": 1_000_000 - 10, "I": 10}, {"beta": 0.5, "gamma": 0.2})
+    lpp = log_posterior_probability(model, ["beta"], [(0.1, 2.0)], [data], ["I"], [ll_negative_binomial], [0.05],
+                                    start_sim=0)
+    grid = np.linspace(0.8, 1.0, 4001)
+    w = np.exp(lpp.batch(grid[:, None].copy()) - lpp(np.array([0.9])))
+    w /= w.sum()
+    mean = float(np.sum(w * grid))
+    std = float(np.sqrt(np.sum(w * (grid - mean) ** 2)))
+    assert 1e-3 < std < 0.03
+    np.random.seed(1)
+    ndim, nwalkers, pos = mcmc.perturbate_theta([0.9], pert=[0.02], multiplier=64, bounds=lpp.expanded_bounds)
+    sampler, samples = mcmc.run_EnsembleSampler(pos, 150, "sir", lpp, samples_path="out/", print_n=50, discard=50,
+                                                progress=False, seed=3)
+    assert sampler.n_batches == 1 + 2 * sampler.iteration
+    x = samples["beta"].ravel()
+    assert x.shape == ((sampler.iteration - 50) * 64,)
+    assert abs(x.mean() - mean) < 0.15 * std and abs(x.std() / std - 1) < 0.15
+    assert 0.1 < sampler.acceptance_fraction.mean() < 0.9
