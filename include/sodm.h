@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SODM_ABI_VERSION 2
+#define SODM_ABI_VERSION 3
 
 /* error codes */
 #define SODM_OK            0
@@ -284,6 +284,45 @@ typedef struct sodm_select_state {
 } sodm_select_state;
 int sodm_draws_select_phase(int32_t phase, const void* in, int32_t dtype, int64_t n_cells, int64_t n_traj, int64_t ld,
                             int32_t n_ranks, const sodm_select_state* state, uint32_t* hist, double* out, void* stream);
+
+/* ---- optimiser populations on the device ----------------------------------------------------------------------
+ * What the reference's optimisers do to the whole population on the host between two evaluations of the objective:
+ *   swarm update + clamp          src/pySODM/optimization/pso.py:207-216            -> sodm_pso_move
+ *   personal bests, arg min       src/pySODM/optimization/pso.py:229-236            -> sodm_pso_best
+ *   proposal density of the KDE move of the default cocktail   src/pySODM/optimization/mcmc.py:26 (emcee KDEMove,
+ *   scipy.stats.gaussian_kde.logpdf)                                               -> sodm_kde_logpdf
+ * Populations are FP64 structure-of-arrays [n_dim][ld] on the device (member i, dimension d at base[d * ld + i]) -- the
+ * layout of `var_values`, so a population is passed to sodm_jump_run / sodm_ode_run without a transpose. */
+#define SODM_POPULATION_MAX_DIM 16
+
+typedef struct sodm_pso_args {
+    int32_t       n_dim;
+    int64_t       n, ld;
+    double*       x;           /* (device) [n_dim][ld] positions, updated in place                                  */
+    double*       v;           /* (device) [n_dim][ld] velocities, updated in place                                 */
+    const double* p;           /* (device) [n_dim][ld] best position of every particle                              */
+    const double* g;           /* (device) [n_dim] best position of the swarm                                       */
+    const double* lb;          /* (host) [n_dim]                                                                    */
+    const double* ub;          /* (host) [n_dim], ub > lb                                                           */
+    double        omega, phip, phig;
+    uint64_t      seed;        /* r_p, r_g ~ U[0,1): Philox keyed by (seed, member_id0 + i, iteration)              */
+    int64_t       iteration;   /* 0 .. 2^32 - 1                                                                     */
+    int64_t       member_id0;  /* global index of particle 0 of this shard                                          */
+    void*         stream;
+} sodm_pso_args;
+/* v = omega v + phip r_p (p - x) + phig r_g (g - x);  x = clamp(x + v, lb, ub) */
+int sodm_pso_move(const sodm_pso_args* args);
+
+/* p, fp <- x, fx where fx < fp (and feasible[i] != 0 when `feasible` is given); then i* = np.argmin(fp) (first index of the
+ * minimum, NaN first):  best[0] = fp[i*], best[1 .. n_dim] = p[:, i*], *best_index = i*.  All pointers are device memory. */
+int sodm_pso_best(int32_t n_dim, int64_t n, int64_t ld, const double* x, const double* fx, const uint8_t* feasible,
+                  double* p, double* fp, double* best /* [1 + n_dim] */, int64_t* best_index, void* stream);
+
+/* out[j] = log sum_k exp(-|q_j - x_k|^2 / 2) + log_norm for WHITENED points x (kernel centres) and queries q: with
+ * L L^T = the kernel covariance, x = L^-1 data, q = L^-1 query and log_norm = -log(n_points) - log|L| - n_dim/2 log(2 pi)
+ * this is gaussian_kde(data).logpdf(query). */
+int sodm_kde_logpdf(int32_t n_dim, const double* points, int64_t n_points, int64_t ld_points, const double* queries,
+                    int64_t n_queries, int64_t ld_queries, double log_norm, double* out /* [n_queries] */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PYSODM_B200_LIB") or os.path.join(_HERE, "libsodm.so")     # override: tuning builds only
 
 # constants mirrored from include/sodm.h
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, EINVAL, EMODEL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4
 KIND_JUMP, KIND_ODE = 0, 1
 I32, F32, F64 = 0, 1, 2
@@ -81,6 +81,15 @@ class SelectState(C.Structure):
 
 
 # every symbol include/sodm.h declares: name -> (restype, argtypes)
+class PsoArgs(C.Structure):
+    _fields_ = [("n_dim", C.c_int32), ("n", C.c_int64), ("ld", C.c_int64), ("x", C.c_void_p), ("v", C.c_void_p),
+                ("p", C.c_void_p), ("g", C.c_void_p), ("lb", C.c_void_p), ("ub", C.c_void_p), ("omega", C.c_double),
+                ("phip", C.c_double), ("phig", C.c_double), ("seed", C.c_uint64), ("iteration", C.c_int64),
+                ("member_id0", C.c_int64), ("stream", C.c_void_p)]
+
+
+POPULATION_MAX_DIM = 16
+
 SYMBOLS = {
     "sodm_abi_version": (C.c_int, []),
     "sodm_last_error": (C.c_char_p, []),
@@ -98,6 +107,11 @@ SYMBOLS = {
     "sodm_draws_sum": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "sodm_draws_order_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                          C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.c_void_p]),
+    "sodm_pso_move": (C.c_int, [C.POINTER(PsoArgs)]),
+    "sodm_pso_best": (C.c_int, [C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sodm_kde_logpdf": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                  C.c_double, C.c_void_p, C.c_void_p]),
     "sodm_draws_select_phase": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                           C.POINTER(SelectState), C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -381,3 +381,103 @@ class SelectPhases:
         out = torch.empty((len(self.ranks),) + tuple(self.ens.shape[:-1]), dtype=torch.float64, device=self.dev)
         self.run(_ffi.SELECT_DECODE, out=out)
         return out
+
+
+# ---- optimiser populations (sodm_pso_move / sodm_pso_best / sodm_kde_logpdf) --------------------------------------------
+# Populations are float64 CUDA tensors [n_dim, n] (structure-of-arrays, the layout of per-trajectory parameters).
+
+def _population(t, what):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.dim() == 2 and
+            (t.shape[1] <= 1 or t.stride(1) == 1)):
+        raise TypeError(f"{what} must be a float64 CUDA tensor [n_dim, n] with unit stride along n")
+    if not 1 <= t.shape[0] <= _ffi.POPULATION_MAX_DIM:
+        raise ValueError(f"{what}: between 1 and {_ffi.POPULATION_MAX_DIM} dimensions, got {t.shape[0]}")
+    return t
+
+
+def _ld(t):
+    """Leading stride of a population (torch reports arbitrary strides for dimensions of size 1)."""
+    return int(t.stride(0)) if t.shape[0] > 1 else max(int(t.shape[1]), 1)
+
+
+def pso_move(x, v, p, g, lb, ub, omega, phip, phig, seed, iteration, member_id0=0, stream=None):
+    """One swarm update in place (`sodm_pso_move`): x, v, p [n_dim, n]; g [n_dim] on the device; lb, ub host values."""
+    lib = _ffi.load()
+    x, v, p = _population(x, "x"), _population(v, "v"), _population(p, "p")
+    if not (x.shape == v.shape == p.shape and _ld(x) == _ld(v) == _ld(p)):
+        raise ValueError("x, v and p must share shape and leading stride")
+    lb_h, ub_h = np.ascontiguousarray(lb, dtype=np.float64), np.ascontiguousarray(ub, dtype=np.float64)
+    if lb_h.shape != (x.shape[0],) or ub_h.shape != (x.shape[0],) or g.shape != (x.shape[0],) or g.dtype != torch.float64:
+        raise ValueError("g, lb and ub need one float64 value per dimension")
+    a = _ffi.PsoArgs()
+    a.n_dim, a.n, a.ld = int(x.shape[0]), int(x.shape[1]), _ld(x)
+    a.x, a.v, a.p, a.g = x.data_ptr(), v.data_ptr(), p.data_ptr(), g.data_ptr()
+    a.lb, a.ub = lb_h.ctypes.data, ub_h.ctypes.data
+    a.omega, a.phip, a.phig = float(omega), float(phip), float(phig)
+    a.seed, a.iteration, a.member_id0 = int(seed) & 0xFFFFFFFFFFFFFFFF, int(iteration), int(member_id0)
+    a.stream = _stream_ptr(stream)
+    _ffi.check(lib.sodm_pso_move(C.byref(a)), lib)
+
+
+def pso_best(x, fx, p, fp, feasible=None, best=None, best_index=None, stream=None):
+    """Personal bests in place and the swarm's best (`sodm_pso_best`) -> (best[1 + n_dim] = (fp[i*], p[:, i*]),
+    best_index[1]) device tensors; asynchronous."""
+    lib = _ffi.load()
+    x, p = _population(x, "x"), _population(p, "p")
+    n_dim, n = x.shape
+    if p.shape != x.shape or _ld(p) != _ld(x):
+        raise ValueError("x and p must share shape and leading stride")
+    for name, t in (("fx", fx), ("fp", fp)):
+        if not (t.is_cuda and t.dtype == torch.float64 and t.shape == (n,) and t.is_contiguous()):
+            raise TypeError(f"{name} must be a contiguous float64 CUDA tensor [{n}]")
+    if feasible is not None and not (feasible.is_cuda and feasible.dtype in (torch.uint8, torch.bool) and
+                                     feasible.shape == (n,) and feasible.is_contiguous()):
+        raise TypeError(f"feasible must be a contiguous bool / uint8 CUDA tensor [{n}]")
+    if best is None:
+        best = torch.empty(1 + n_dim, dtype=torch.float64, device=x.device)
+    if best_index is None:
+        best_index = torch.empty(1, dtype=torch.int64, device=x.device)
+    _ffi.check(lib.sodm_pso_best(n_dim, n, _ld(x), x.data_ptr(), fx.data_ptr(),
+                                 feasible.data_ptr() if feasible is not None else None, p.data_ptr(), fp.data_ptr(),
+                                 best.data_ptr(), best_index.data_ptr(), _stream_ptr(stream)), lib)
+    return best, best_index
+
+
+def kde_logpdf(points, queries, log_norm=0.0, out=None, stream=None):
+    """log sum_k exp(-|q_j - x_k|^2 / 2) + log_norm for whitened points [n_dim, K] and queries [n_dim, M]
+    (`sodm_kde_logpdf`) -> float64 CUDA tensor [M]."""
+    lib = _ffi.load()
+    points, queries = _population(points, "points"), _population(queries, "queries")
+    if points.shape[0] != queries.shape[0]:
+        raise ValueError("points and queries differ in dimension")
+    if out is None:
+        out = torch.empty(queries.shape[1], dtype=torch.float64, device=queries.device)
+    _ffi.check(lib.sodm_kde_logpdf(int(points.shape[0]), points.data_ptr(), int(points.shape[1]), _ld(points),
+                                   queries.data_ptr(), int(queries.shape[1]), _ld(queries), float(log_norm),
+                                   out.data_ptr(), _stream_ptr(stream)), lib)
+    return out
+
+
+def gaussian_kde_logpdf(data, queries, bw_method="scott", dev=None):
+    """`scipy.stats.gaussian_kde(data.T, bw_method).logpdf(queries.T)` for host arrays data[K, D], queries[M, D]: the
+    D x D factorisation and the whitening on the host, the K x M pair sum on the device."""
+    dev = dev or device()
+    data, queries = np.asarray(data, dtype=np.float64), np.asarray(queries, dtype=np.float64)
+    K, D = data.shape
+    if bw_method in (None, "scott"):
+        factor = K ** (-1.0 / (D + 4))
+    elif bw_method == "silverman":
+        factor = (K * (D + 2) / 4.0) ** (-1.0 / (D + 4))
+    elif np.isscalar(bw_method):
+        factor = float(bw_method)
+    else:
+        raise ValueError("bw_method must be 'scott', 'silverman' or a number")
+    cov = np.atleast_2d(np.cov(data, rowvar=False, bias=False)) * factor ** 2
+    L = np.linalg.cholesky(cov)
+    from scipy.linalg import solve_triangular
+    pts = solve_triangular(L, data.T, lower=True)                   # [D, K]
+    qs = solve_triangular(L, queries.T, lower=True)                 # [D, M]
+    log_norm = -np.log(K) - np.sum(np.log(np.diag(L))) - 0.5 * D * np.log(2.0 * np.pi)
+    out = kde_logpdf(torch.from_numpy(np.ascontiguousarray(pts)).to(dev), torch.from_numpy(np.ascontiguousarray(qs)).to(dev),
+                     log_norm)
+    return out.cpu().numpy()

@@ -306,14 +306,39 @@ class log_posterior_probability:
         thetas = np.asarray(thetas)
         if thetas.ndim != 2 or thetas.shape[1] != self.n_theta:
             raise ValueError(f"thetas must have shape [P, {self.n_theta}]")
-        P = thetas.shape[0]
         lp = self.compute_log_prior_probability(thetas)
         for j, (lo, hi) in enumerate(self.expanded_bounds):
             above, below = thetas[:, j] > hi, thetas[:, j] < lo
             thetas[above, j], thetas[below, j] = hi, lo
             lp = lp + np.where(above | below, -np.inf, 0.0)
-        model = self.model
         dev = engine.device(device)
+        lp_d = self._device_log_likelihood([np.ascontiguousarray(thetas[:, j], dtype=np.float64) for j in range(self.n_theta)],
+                                           thetas.shape[0], seed, dev)
+        if return_device:
+            return lp_d + torch.from_numpy(lp).to(dev)
+        return lp + lp_d.cpu().numpy()
+
+    def batch_device(self, thetas, seed=None):
+        """lp[P] (float64 CUDA tensor) for a population that LIVES on the device: `thetas` is a float64 CUDA tensor
+        [D, P] (structure-of-arrays, one row per expanded parameter -- the layout the simulators read per-trajectory
+        parameters in, so nothing is transposed or copied).  For optimisers that keep their population on the device
+        (`optimization.pso(..., device_update=True)`).  The caller keeps the population inside the bounds (the device
+        swarm update clamps); only uniform priors are available here (their value inside the bounds is 0), anything
+        else needs the host path (`batch`)."""
+        import torch
+        if any(fn is not log_prior_uniform for fn in self.log_prior_prob_fnc):
+            raise NotImplementedError("batch_device supports uniform priors only; use batch()")
+        if not (isinstance(thetas, torch.Tensor) and thetas.is_cuda and thetas.dtype == torch.float64 and
+                thetas.dim() == 2 and thetas.shape[0] == self.n_theta):
+            raise ValueError(f"thetas must be a float64 CUDA tensor [{self.n_theta}, P]")
+        return self._device_log_likelihood([thetas[j] for j in range(self.n_theta)], thetas.shape[1], seed, thetas.device)
+
+    def _device_log_likelihood(self, columns, P, seed, dev):
+        """Sum of the weighted log-likelihoods of P parameter vectors given as one column (host array or CUDA tensor of P
+        values) per expanded parameter -> float64 CUDA tensor [P]."""
+        import torch
+        from . import engine
+        model = self.model
         kw = self.simulation_kwargs
         time_unit = kw.get("time_unit", "D")
         if getattr(model, "_generated", False) and model._kind == "ode" and model.time_dependent_parameters:
@@ -333,7 +358,7 @@ class log_posterior_probability:
                 raise NotImplementedError(f"calibrated parameter '{name}' is time dependent")
             off = model._param_offsets[name][0]
             for e in range(size):
-                var[off + e] = np.ascontiguousarray(thetas[:, col + e], dtype=np.float64)
+                var[off + e] = columns[col + e]
             col += size
         if self.time_index == "date":
             unit = TIME_UNIT_US[time_unit]
@@ -382,9 +407,7 @@ class log_posterior_probability:
                               ll_arg=self.log_likelihood_fnc_args[i], weight=self.weights[i], lp=lp_d, status=st_ll, dev=dev)
         if int(st_ll.max()) & _ffi.ST_NONFINITE:
             raise ValueError("simulation output contains nan, likely due to numerical unstability. try using more conservative bounds.")
-        if return_device:
-            return lp_d + torch.from_numpy(lp).to(dev)
-        return lp + lp_d.cpu().numpy()
+        return lp_d
 
     def __call__(self, thetas):
         thetas = np.asarray(thetas)

@@ -1,0 +1,147 @@
+"""GPU parity tests of the optimiser-population kernels (sodm_pso_move, sodm_pso_best, sodm_kde_logpdf) against
+oracle/population.py, and of the device-resident particle swarm against the host one."""
+import numpy as np
+import pytest
+
+import hostcheck_util as hc
+from oracle import population as opop
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    from pysodm_b200 import engine
+    engine.device(0)
+    return engine, torch
+
+
+def _dev(eng, a):
+    engine, torch = eng
+    return torch.from_numpy(np.ascontiguousarray(a)).to(engine.device(0))
+
+
+@pytest.mark.parametrize("D,K,M", [(1, 7, 1), (2, 256, 129), (3, 1000, 5000), (5, 4096, 3000), (9, 300, 257), (16, 513, 64)])
+def test_kde_logpdf_matches_scipy(eng, D, K, M):
+    engine, torch = eng
+    rng = np.random.default_rng(D * 1000 + K)
+    A = rng.normal(size=(D, D)) + 2 * np.eye(D)
+    data = rng.normal(size=(K, D)) @ A.T + rng.normal(size=D)
+    queries = rng.normal(size=(M, D)) @ A.T * 1.5
+    queries[0] = data[0]                                      # on a kernel centre
+    queries[-1] = data.mean(axis=0) + 60 * data.std(axis=0)   # far in the tail: densities ~ e^-1000 must not underflow
+    for bw in ("scott", "silverman", 0.37):
+        got = engine.gaussian_kde_logpdf(data, queries, bw)
+        want = opop.kde_logpdf(data, queries, bw)
+        assert np.all(np.isfinite(got))
+        np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-10)
+
+
+def test_kde_logpdf_validation(eng):
+    engine, torch = eng
+    from pysodm_b200._ffi import SodmError
+    pts = _dev(eng, np.zeros((3, 8)))
+    with pytest.raises(ValueError):
+        engine.kde_logpdf(pts, _dev(eng, np.zeros((2, 8))))
+    with pytest.raises(ValueError):
+        engine.kde_logpdf(_dev(eng, np.zeros((17, 8))), _dev(eng, np.zeros((17, 8))))
+    with pytest.raises(SodmError):
+        engine.kde_logpdf(_dev(eng, np.zeros((3, 0))), pts)
+    assert engine.kde_logpdf(pts, _dev(eng, np.zeros((3, 0)))).shape == (0,)
+
+
+@pytest.mark.parametrize("S,D", [(1, 1), (257, 3), (100_000, 5), (4099, 16)])
+def test_pso_move_matches_oracle(eng, S, D):
+    """Same uniforms (Philox keyed by (seed, particle, iteration), one block per dimension: r_p from words 0-1, r_g from
+    words 2-3, 53 bits each) -> the reference's update expression; FMA contraction on the device allows 1-2 ulp."""
+    engine, torch = eng
+    rng = np.random.default_rng(S + D)
+    lb, ub = -1.0 - rng.random(D), 1.0 + rng.random(D)
+    x, p = rng.uniform(lb, ub, size=(2, S, D))
+    v = rng.uniform(-2, 2, size=(S, D))
+    g = rng.uniform(lb, ub)
+    seed, it, id0 = 0x1234_5678_9ABC_DEF0, 7, 10 ** 10
+    xd, vd, pd = _dev(eng, x.T), _dev(eng, v.T), _dev(eng, p.T)
+    engine.pso_move(xd, vd, pd, _dev(eng, g), lb, ub, 0.8, 0.7, 0.9, seed, it, member_id0=id0)
+    check = np.unique(np.concatenate([[0, S - 1], rng.integers(0, S, 200)]))
+    rp, rg = np.empty((len(check), D)), np.empty((len(check), D))
+    for r, i in enumerate(check):
+        w = hc.philox(seed, id0 + int(i), it, D).astype(np.uint64)
+        rp[r] = ((w[:, 0] << np.uint64(32) | w[:, 1]) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+        rg[r] = ((w[:, 2] << np.uint64(32) | w[:, 3]) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+    want_x, want_v = opop.pso_move(x[check], v[check], p[check], g, lb, ub, 0.8, 0.7, 0.9, rp, rg)
+    got_x, got_v = xd.cpu().numpy().T, vd.cpu().numpy().T
+    np.testing.assert_allclose(got_v[check], want_v, rtol=1e-13, atol=1e-14)
+    np.testing.assert_allclose(got_x[check], want_x, rtol=1e-13, atol=1e-14)
+    assert np.all(got_x >= lb) and np.all(got_x <= ub)
+    assert np.any(got_x == lb) or np.any(got_x == ub) or S < 100        # the clamp is exercised
+    # a shard of the swarm reproduces its slice (streams keyed by the global particle index)
+    if S > 100:
+        lo = S // 3
+        xs, vs = _dev(eng, x[lo:].T), _dev(eng, v[lo:].T)
+        engine.pso_move(xs, vs, _dev(eng, p[lo:].T), _dev(eng, g), lb, ub, 0.8, 0.7, 0.9, seed, it, member_id0=id0 + lo)
+        assert np.array_equal(xs.cpu().numpy(), got_x[lo:].T) and np.array_equal(vs.cpu().numpy(), got_v[lo:].T)
+
+
+@pytest.mark.parametrize("S,D", [(1, 2), (1000, 3), (70_001, 5)])
+def test_pso_best_matches_oracle(eng, S, D):
+    engine, torch = eng
+    rng = np.random.default_rng(S)
+    x, p = rng.normal(size=(2, S, D))
+    fx = np.round(rng.normal(size=S), 1)                      # many ties: the FIRST minimum wins
+    fp = np.round(rng.normal(size=S), 1)
+    fp[rng.integers(0, S, S // 10 + 1)] = np.inf
+    feasible = rng.random(S) < 0.8
+    for feas in (None, feasible):
+        pd, fpd = _dev(eng, p.T), _dev(eng, fp)
+        best, idx = engine.pso_best(_dev(eng, x.T), _dev(eng, fx), pd, fpd,
+                                    feasible=None if feas is None else _dev(eng, feas))
+        want_p, want_fp, i_min = opop.pso_best(x, fx, p, fp, feas)
+        assert np.array_equal(pd.cpu().numpy().T, want_p) and np.array_equal(fpd.cpu().numpy(), want_fp)
+        assert int(idx) == i_min
+        assert np.array_equal(best.cpu().numpy(), np.concatenate([[want_fp[i_min]], want_p[i_min]]))
+    # NaN scores: never better than a personal best (fx < fp is False), but np.argmin puts a NaN personal best first
+    fp2 = fp.copy()
+    if S > 10:
+        fp2[[S // 2, S // 2 + 3]] = np.nan
+        fx2 = fx.copy()
+        fx2[:5] = np.nan
+        pd, fpd = _dev(eng, p.T), _dev(eng, fp2)
+        best, idx = engine.pso_best(_dev(eng, x.T), _dev(eng, fx2), pd, fpd)
+        want_p, want_fp, i_min = opop.pso_best(x, fx2, p, fp2)
+        assert int(idx) == i_min == S // 2
+        assert np.array_equal(fpd.cpu().numpy(), want_fp, equal_nan=True)
+
+
+def test_device_swarm_calibrates_like_the_host_swarm(eng, capsys):
+    """The calibration of tests/test_gpu_facade.py::test_pso_calibration_recovers_parameter with the swarm kept on the
+    device: same optimum; per iteration nothing but 1 + D numbers comes back."""
+    import pandas as pd
+    from pysodm_b200 import optimization, tutorial_models as tm
+    from pysodm_b200.objective_functions import ll_poisson, log_posterior_probability
+    truth = tm.ODE_SIR_rate({"S": 1_000_000 - 10, "I": 10}, {"beta": 0.9, "gamma": 0.2})
+    out = truth.sim(40)
+    t = np.arange(10, 41, 2)
+    data = pd.Series(out["I"].values[t], index=pd.Index(t.astype(float), name="time"))
+    model = tm.ODE_SIR_rate({"S": 1_000_000 - 10, "I": 10}, {"beta": 0.5, "gamma": 0.2})
+    lpp = log_posterior_probability(model, ["beta", "gamma"], [(0.1, 2.0), (0.05, 1.0)], [data], ["I"], [ll_poisson], [[]],
+                                    start_sim=0)
+    np.random.seed(0)
+    theta_h, score_h = optimization.pso(lpp, swarmsize=256, max_iter=40)
+    np.random.seed(0)
+    theta_d, score_d = optimization.pso(lpp, swarmsize=256, max_iter=40, device_update=True)
+    assert "Swarm update on the device" in capsys.readouterr().out
+    for theta in (theta_h, theta_d):
+        assert abs(theta[0] - 0.9) / 0.9 < 0.02 and abs(theta[1] - 0.2) / 0.2 < 0.05
+    assert abs(score_d - score_h) < 1e-3 * abs(score_h) + 1.0
+    # the reported score is the objective at the reported position
+    assert abs(-lpp(np.array(theta_d)) - score_d) <= 1e-9 * abs(score_d)
+    # the device evaluation of a resident population equals the host-fed one
+    engine, torch = eng
+    X = np.column_stack([np.linspace(0.5, 1.5, 33), np.linspace(0.1, 0.4, 33)])
+    assert np.array_equal(lpp.batch_device(_dev(eng, X.T)).cpu().numpy(), lpp.batch(X.copy()))
+    with pytest.raises(ValueError, match="inside the objective's bounds"):
+        optimization.pso(lpp, bounds=[(0.0, 3.0), (0.05, 1.0)], swarmsize=8, max_iter=1, device_update=True)
+    with pytest.raises(NotImplementedError):
+        optimization.pso(lpp, swarmsize=8, max_iter=1, device_update=True, transform_pars=lambda x: x)

@@ -35,12 +35,23 @@ class Gaussian:
         return -0.5 * np.einsum("ni,ij,nj->n", d, PREC, d)
 
 
+def scipy_logpdf(data, queries, bw_method):
+    """The oracle of `sodm_kde_logpdf` (scipy.stats.gaussian_kde), standing in for the device on the CPU."""
+    from scipy.stats import gaussian_kde
+    return gaussian_kde(data.T, bw_method=bw_method).logpdf(queries.T)
+
+
+def cocktail():
+    return [(m if not isinstance(m, mcmc.KDEMove) else mcmc.KDEMove(bw_method="scott", logpdf=scipy_logpdf), w)
+            for m, w in mcmc.default_moves()]
+
+
 def start(n, seed=0):
     return MU + np.random.default_rng(seed).normal(size=(n, 3))
 
 
 @pytest.mark.parametrize("move", [mcmc.StretchMove(), mcmc.DEMove(), mcmc.DEMove(gamma0=1.0), mcmc.DESnookerMove(),
-                                  mcmc.KDEMove(bw_method="scott"), None],
+                                  mcmc.KDEMove(bw_method="scott", logpdf=scipy_logpdf), cocktail()],
                          ids=["stretch", "de", "de_gamma1", "snooker", "kde", "cocktail"])
 def test_move_samples_the_target(move):
     f = Gaussian()
@@ -87,7 +98,7 @@ def test_infinite_log_prob_is_rejected():
             return lp
     x0 = start(64)
     x0[:, 0] = MU[0] + np.abs(x0[:, 0] - MU[0]) + 0.01
-    s = mcmc.EnsembleSampler(64, 3, Box(), seed=2)
+    s = mcmc.EnsembleSampler(64, 3, Box(), moves=cocktail(), seed=2)
     s.run_mcmc(x0, 50)
     assert np.all(s.get_chain()[:, :, 0] >= MU[0]) and np.all(np.isfinite(s.get_log_prob()))
 
@@ -113,7 +124,8 @@ def test_run_ensemble_sampler_files_and_restart(tmp_path, monkeypatch, capsys):
     assert np.all(np.abs(pos / np.array([1.0, -2.0, 0.5]) - 1) <= 0.3)
     settings = {"start_calibration": 0, "starting_estimate": [1.0, -2.0, 0.5], "tag": "x"}
     sampler, samples = mcmc.run_EnsembleSampler(pos, 30, "user", f, (), samples_path="out/", fig_path="out/", print_n=10,
-                                                discard=5, thin=2, settings_dict=settings, progress=False, seed=1)
+                                                discard=5, thin=2, settings_dict=settings, progress=False, seed=1,
+                                                moves=cocktail())
     today = str(datetime.date.today())
     assert sampler.iteration == 30 and f.single_calls == 0
     assert samples["a"].shape == (12, 12) and samples["b"].shape == (12, 12, 2)
@@ -124,11 +136,12 @@ def test_run_ensemble_sampler_files_and_restart(tmp_path, monkeypatch, capsys):
     assert "Non-convergence" in capsys.readouterr().out
     # restart: the reference passes the backend's file name (an .hdf5 name resolves to the .npz written beside it)
     s2, samples2 = mcmc.run_EnsembleSampler(pos, 20, "user", f, (), samples_path="out/", print_n=10, progress=False,
-                                            backend=f"out/user_BACKEND_{today}.hdf5", settings_dict=settings, seed=2)
+                                            backend=f"out/user_BACKEND_{today}.hdf5", settings_dict=settings, seed=2,
+                                            moves=cocktail())
     assert s2.iteration == 50 and np.array_equal(s2.get_chain()[:30], sampler.get_chain())
     assert samples2["a"].shape == (50, 12)
     with pytest.raises(FileNotFoundError):
-        mcmc.run_EnsembleSampler(pos, 5, "user", f, backend="out/none.hdf5", progress=False)
+        mcmc.run_EnsembleSampler(pos, 5, "user", f, backend="out/none.hdf5", progress=False, moves=cocktail())
     with pytest.raises(TypeError, match="settings_dict"):
         mcmc.run_EnsembleSampler(pos, 5, "user", f, settings_dict={"when": datetime.date.today()}, progress=False)
     with pytest.raises(TypeError, match="homogeneous"):
