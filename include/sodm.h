@@ -324,6 +324,50 @@ int sodm_pso_best(int32_t n_dim, int64_t n, int64_t ld, const double* x, const d
 int sodm_kde_logpdf(int32_t n_dim, const double* points, int64_t n_points, int64_t ld_points, const double* queries,
                     int64_t n_queries, int64_t ld_queries, double log_norm, double* out /* [n_queries] */, void* stream);
 
+/* Ensemble-MCMC moves of the reference's default cocktail (src/pySODM/optimization/mcmc.py:22-28; emcee's red-blue scheme:
+ * the walkers listed in `mine` propose from the walkers listed in `others`, the random split of the iteration):
+ *   SODM_MOVE_STRETCH  q = c + z (s - c), z = ((a-1) u + 1)^2 / a, log factor (D-1) log z          param = a  (emcee: 2)
+ *   SODM_MOVE_DE       q = s + gamma (c_a - c_b) + eps, eps ~ N(0, sigma^2), log factor 0           param = gamma (<= 0: 2.38/sqrt(2D))
+ *   SODM_MOVE_SNOOKER  q = s + gamma (u.z1 - u.z2) u, u = (s - z)/|s - z|, log factor (D-1) log(|q-z|/|s-z|)   param = gamma (emcee: 1.7)
+ * Random numbers: Philox keyed by (seed, walker index, 2 * iteration) for the proposal and (.., 2 * iteration + 1) for the
+ * acceptance, so a run does not depend on launch geometry. */
+#define SODM_MOVE_STRETCH 0
+#define SODM_MOVE_DE      1
+#define SODM_MOVE_SNOOKER 2
+#define SODM_WALKERS_ST_NAN 1      /* a proposal scored NaN (emcee: "Probability function returned NaN") */
+
+typedef struct sodm_walker_move_args {
+    int32_t        kind;        /* SODM_MOVE_*                                                                       */
+    int32_t        n_dim;
+    int64_t        n_walkers, ld;
+    const double*  x;           /* (device) [n_dim][ld] the ensemble                                                 */
+    const int64_t* mine;        /* (device) [n_mine] walkers being moved                                             */
+    int64_t        n_mine;
+    const int64_t* others;      /* (device) [n_others] the complementary walkers                                     */
+    int64_t        n_others;
+    double         param, sigma;
+    double*        q;           /* (device) [n_dim][ld_q] proposals, column j for walker mine[j]                     */
+    int64_t        ld_q;
+    double*        log_factor;  /* (device) [n_mine] log of the Hastings factor                                      */
+    uint64_t       seed;
+    int64_t        iteration;   /* 0 .. 2^31 - 1                                                                     */
+    void*          stream;
+} sodm_walker_move_args;
+int sodm_walkers_propose(const sodm_walker_move_args* args);
+
+/* Clip x into [lb, ub] (host arrays) in place; penalty[i] = -inf where anything was clipped, else 0: the reference's
+ * treatment of an out-of-bounds theta (src/pySODM/optimization/objective_functions.py:301-307). */
+int sodm_population_clip(int32_t n_dim, int64_t n, int64_t ld, double* x, const double* lb, const double* ub,
+                         double* penalty /* (device) [n] */, void* stream);
+
+/* Walker mine[j] moves to q[:, j] (x, lp updated in place, accepted[mine[j]] += 1) when
+ * log_factor[j] + new_lp[j] - lp[mine[j]] > log u; a clipped proposal (penalty[j] < 0) or an infinite score never moves;
+ * a NaN score sets SODM_WALKERS_ST_NAN. */
+int sodm_walkers_accept(int32_t n_dim, int64_t n_walkers, int64_t ld, double* x, double* lp, const int64_t* mine,
+                        int64_t n_mine, const double* q, int64_t ld_q, const double* new_lp, const double* penalty /* or NULL */,
+                        const double* log_factor, uint64_t seed, int64_t iteration, int64_t* accepted /* [n_walkers] */,
+                        int32_t* status /* or NULL */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,3 +36,64 @@ def kde_logpdf(data, queries, bw_method="scott"):
     """log-density of a Gaussian KDE of data[K, D] at queries[M, D] (scipy.stats.gaussian_kde)."""
     from scipy.stats import gaussian_kde
     return gaussian_kde(np.asarray(data).T, bw_method=bw_method).logpdf(np.asarray(queries).T)
+
+
+# ---- ensemble-MCMC moves (the reference's cocktail, /root/reference/src/pySODM/optimization/mcmc.py:22-28) --------------
+# emcee is a third-party dependency absent from this image: these restate the published moves (Goodman & Weare 2010;
+# ter Braak 2006; ter Braak & Vrugt 2008) one walker at a time, drawing from an explicit stream of 32-bit words so
+# that the device kernels can be checked value for value.  "Parity unpinned" against emcee itself: the statistical
+# tests (tests/test_mcmc_cpu.py, tests/test_gpu_facade.py) check that each move samples a known target.
+
+class Words:
+    """Uniforms, bounded integers and normals from a stream of uint32 words (two words per draw, high word first)."""
+
+    def __init__(self, words):
+        self.w, self.i = np.asarray(words, dtype=np.uint64).reshape(-1), 0
+
+    def _u64(self):
+        v = (int(self.w[self.i]) << 32) | int(self.w[self.i + 1])
+        self.i += 2
+        return v
+
+    def uniform(self):                                  # [0, 1), 53 bits
+        return (self._u64() >> 11) * 2.0 ** -53
+
+    def below(self, n):                                 # 0 .. n-1: high half of the 64 x 64 bit product
+        return (self._u64() * int(n)) >> 64
+
+    def normal(self):                                   # Box-Muller, the cosine branch
+        u1, u2 = 1.0 - self.uniform(), self.uniform()
+        return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
+def walker_propose(kind, x, me, others, param, sigma, words):
+    """One walker's proposal.  x [n, D]; `others` the index list of the complementary half; kind 'stretch' | 'de' |
+    'snooker'.  Returns (q [D], log Hastings factor)."""
+    r = Words(words)
+    s, D = x[me], x.shape[1]
+    if kind == "stretch":
+        z = ((param - 1.0) * r.uniform() + 1.0) ** 2 / param
+        c = x[others[r.below(len(others))]]
+        return c - (c - s) * z, (D - 1.0) * np.log(z)
+    if kind == "de":
+        gamma = param if param > 0 else 2.38 / np.sqrt(2.0 * D)
+        ia, ib = r.below(len(others)), r.below(len(others) - 1)
+        ib += ib >= ia
+        return s + gamma * (x[others[ia]] - x[others[ib]]) + sigma * r.normal(), 0.0
+    i0, i1, i2 = r.below(len(others)), r.below(len(others) - 1), r.below(len(others) - 2)
+    i1 += i1 >= i0
+    lo, hi = min(i0, i1), max(i0, i1)
+    i2 += i2 >= lo
+    i2 += i2 >= hi
+    z, z1, z2 = x[others[i0]], x[others[i1]], x[others[i2]]
+    delta = s - z
+    norm = np.linalg.norm(delta)
+    u = delta / norm
+    q = s + u * param * (np.dot(u, z1) - np.dot(u, z2))
+    return q, (D - 1.0) * (np.log(np.linalg.norm(q - z)) - np.log(norm))
+
+
+def walker_accepts(lp_old, lp_new, log_factor, words):
+    """Metropolis-Hastings with u on (0, 1]; an infinite score never moves the walker."""
+    log_u = np.log(1.0 - Words(words).uniform())
+    return bool(np.isfinite(lp_new) and log_factor + lp_new - lp_old > log_u)

@@ -88,7 +88,16 @@ class PsoArgs(C.Structure):
                 ("member_id0", C.c_int64), ("stream", C.c_void_p)]
 
 
+class WalkerMoveArgs(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_dim", C.c_int32), ("n_walkers", C.c_int64), ("ld", C.c_int64), ("x", C.c_void_p),
+                ("mine", C.c_void_p), ("n_mine", C.c_int64), ("others", C.c_void_p), ("n_others", C.c_int64),
+                ("param", C.c_double), ("sigma", C.c_double), ("q", C.c_void_p), ("ld_q", C.c_int64),
+                ("log_factor", C.c_void_p), ("seed", C.c_uint64), ("iteration", C.c_int64), ("stream", C.c_void_p)]
+
+
 POPULATION_MAX_DIM = 16
+MOVE_STRETCH, MOVE_DE, MOVE_SNOOKER = 0, 1, 2
+WALKERS_ST_NAN = 1
 
 SYMBOLS = {
     "sodm_abi_version": (C.c_int, []),
@@ -112,6 +121,12 @@ SYMBOLS = {
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sodm_kde_logpdf": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                   C.c_double, C.c_void_p, C.c_void_p]),
+    "sodm_walkers_propose": (C.c_int, [C.POINTER(WalkerMoveArgs)]),
+    "sodm_population_clip": (C.c_int, [C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
+    "sodm_walkers_accept": (C.c_int, [C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "sodm_draws_select_phase": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                           C.POINTER(SelectState), C.c_void_p, C.c_void_p, C.c_void_p]),
 }

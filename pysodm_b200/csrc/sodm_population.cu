@@ -144,6 +144,129 @@ __global__ void __launch_bounds__(128) kde_logpdf_kernel(const double* __restric
     if (j < n_queries) out[j] = log(sum) - 0.5 * d_min + log_norm;
 }
 
+
+// ---- ensemble-MCMC moves (emcee's red-blue scheme: the walkers of one half propose from the other half) ----------------
+// One thread per moved walker.  Walkers are addressed through index lists (`mine`, `others`: the random split of the
+// iteration), so the ensemble itself never moves; the gathers touch n_dim columns of a few MB that live in L2.
+struct WalkerRng {
+    Philox4x32 g;
+    uint32_t w[4];
+    int used;
+    __device__ void init(uint64_t seed, uint64_t walker, uint32_t purpose) { g.init(seed, walker, purpose); used = 4; }
+    __device__ uint32_t word() {
+        if (used == 4) { g.next4(w); used = 0; }
+        return w[used++];
+    }
+    __device__ double uniform() { const uint32_t hi = word(); return u53(hi, word()); }          // [0, 1)
+    __device__ int64_t below(int64_t n) {                                                         // uniform on 0 .. n-1
+        const uint32_t hi = word();
+        return (int64_t)__umul64hi(((uint64_t)hi << 32) | word(), (uint64_t)n);
+    }
+    __device__ double normal() {                                                                  // Box-Muller, one of the pair
+        const double u1 = 1.0 - uniform(), u2 = uniform();
+        return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    }
+};
+
+__global__ void __launch_bounds__(128) walkers_propose_kernel(sodm_walker_move_args a) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.n_mine) return;
+    const int D = a.n_dim;
+    const int64_t me = a.mine[j];
+    WalkerRng rng;
+    rng.init(a.seed, (uint64_t)me, (uint32_t)a.iteration * 2u);
+    const double* x = a.x;
+    double lf = 0.0;
+    if (a.kind == SODM_MOVE_STRETCH) {
+        // Goodman & Weare: z ~ g(z) on [1/a, a], q = c + z (s - c), factor z^(D-1)
+        const double u = rng.uniform();
+        const double t = (a.param - 1.0) * u + 1.0;
+        const double z = t * t / a.param;
+        const int64_t c = a.others[rng.below(a.n_others)];
+        for (int d = 0; d < D; ++d) {
+            const double cd = x[d * a.ld + c];
+            a.q[d * a.ld_q + j] = cd - (cd - x[d * a.ld + me]) * z;
+        }
+        lf = (D - 1.0) * log(z);
+    } else if (a.kind == SODM_MOVE_DE) {
+        // ter Braak: q = s + gamma (c_a - c_b) + eps, two distinct walkers of the other half, eps ~ N(0, sigma^2)
+        const double gamma = a.param > 0.0 ? a.param : 2.38 / sqrt(2.0 * D);
+        int64_t ia = rng.below(a.n_others), ib = rng.below(a.n_others - 1);
+        ib += ib >= ia;
+        const int64_t ca = a.others[ia], cb = a.others[ib];
+        const double eps = a.sigma * rng.normal();
+        for (int d = 0; d < D; ++d)
+            a.q[d * a.ld_q + j] = x[d * a.ld + me] + gamma * (x[d * a.ld + ca] - x[d * a.ld + cb]) + eps;
+    } else {
+        // ter Braak & Vrugt snooker: along the line through s and z, a jump of gamma times the difference of the
+        // projections of two more walkers; factor (|q - z| / |s - z|)^(D-1)
+        int64_t i0 = rng.below(a.n_others), i1 = rng.below(a.n_others - 1), i2 = rng.below(a.n_others - 2);
+        i1 += i1 >= i0;
+        const int64_t lo = i0 < i1 ? i0 : i1, hi = i0 < i1 ? i1 : i0;
+        i2 += i2 >= lo;
+        i2 += i2 >= hi;
+        const int64_t z = a.others[i0], z1 = a.others[i1], z2 = a.others[i2];
+        double norm2 = 0.0, proj = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double delta = x[d * a.ld + me] - x[d * a.ld + z];
+            norm2 = fma(delta, delta, norm2);
+            proj = fma(delta, x[d * a.ld + z1] - x[d * a.ld + z2], proj);
+        }
+        const double norm = sqrt(norm2);
+        const double step = a.param * proj / norm2;                  // gamma (u.z1 - u.z2) u = step * delta
+        double qn2 = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double sd = x[d * a.ld + me], zd = x[d * a.ld + z];
+            const double qd = sd + step * (sd - zd);
+            a.q[d * a.ld_q + j] = qd;
+            qn2 = fma(qd - zd, qd - zd, qn2);
+        }
+        lf = (D - 1.0) * (0.5 * log(qn2) - log(norm));
+    }
+    a.log_factor[j] = lf;
+}
+
+// Clip a population into the bounds IN PLACE and note who had to be clipped: the reference's objective clips an
+// out-of-bounds theta and scores it -inf (objective_functions.py:301-307).
+__global__ void __launch_bounds__(256) population_clip_kernel(int n_dim, int64_t n, int64_t ld, double* __restrict__ x, Bounds b,
+                                                              double* __restrict__ penalty) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        bool out = false;
+        for (int d = 0; d < n_dim; ++d) {
+            const double v = x[d * ld + i];
+            if (v > b.ub[d]) { x[d * ld + i] = b.ub[d]; out = true; }
+            else if (v < b.lb[d]) { x[d * ld + i] = b.lb[d]; out = true; }
+        }
+        penalty[i] = out ? -1.0 / 0.0 : 0.0;
+    }
+}
+
+// Metropolis-Hastings: walker mine[j] moves to q[:, j] when log_factor + new_lp (+ penalty) - lp > log u.
+__global__ void __launch_bounds__(128) walkers_accept_kernel(int n_dim, int64_t ld, double* __restrict__ x, double* __restrict__ lp,
+                                                             const int64_t* __restrict__ mine, int64_t n_mine,
+                                                             const double* __restrict__ q, int64_t ld_q,
+                                                             const double* __restrict__ new_lp, const double* __restrict__ penalty,
+                                                             const double* __restrict__ log_factor, uint64_t seed,
+                                                             uint32_t iteration, int64_t* __restrict__ accepted,
+                                                             int32_t* __restrict__ status) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_mine) return;
+    const int64_t me = mine[j];
+    WalkerRng rng;
+    rng.init(seed, (uint64_t)me, iteration * 2u + 1u);
+    const double cand = new_lp[j];
+    if (cand != cand) {
+        if (status) atomicOr(status, SODM_WALKERS_ST_NAN);
+        return;
+    }
+    if (penalty && penalty[j] < 0.0) return;                         // clipped into the bounds: scored -inf
+    const double log_u = log(1.0 - rng.uniform());                   // u on (0, 1]
+    if (isinf(cand) || !(log_factor[j] + cand - lp[me] > log_u)) return;     // a non-finite score never moves a walker
+    lp[me] = cand;
+    for (int d = 0; d < n_dim; ++d) x[d * ld + me] = q[d * ld_q + j];
+    accepted[me] += 1;
+}
+
 template <int D>
 static int launch_kde(const double* points, int64_t n_points, int64_t ld_p, const double* queries, int64_t n_queries,
                       int64_t ld_q, double log_norm, double* out, cudaStream_t s) {
@@ -222,4 +345,50 @@ extern "C" int sodm_kde_logpdf(int32_t n_dim, const double* points, int64_t n_po
 #undef SODM_KDE_CASE
     }
     return fail(SODM_EINVAL, "sodm_kde_logpdf: n_dim %d", n_dim);
+}
+
+extern "C" int sodm_walkers_propose(const sodm_walker_move_args* a) {
+    if (!a) return fail(SODM_EINVAL, "sodm_walkers_propose: null args");
+    int rc = check_population("sodm_walkers_propose", a->n_dim, a->n_walkers, a->ld);
+    if (rc != SODM_OK) return rc;
+    if (a->n_mine < 0 || a->ld_q < a->n_mine) return fail(SODM_EINVAL, "sodm_walkers_propose: n_mine = %lld, ld_q = %lld", (long long)a->n_mine, (long long)a->ld_q);
+    if (a->n_mine == 0) return SODM_OK;
+    const int need = a->kind == SODM_MOVE_STRETCH ? 1 : a->kind == SODM_MOVE_DE ? 2 : a->kind == SODM_MOVE_SNOOKER ? 3 : -1;
+    if (need < 0) return fail(SODM_EINVAL, "sodm_walkers_propose: unknown move %d", a->kind);
+    if (a->n_others < need) return fail(SODM_EINVAL, "sodm_walkers_propose: the move needs %d walkers in the other half, got %lld", need, (long long)a->n_others);
+    if (a->kind == SODM_MOVE_STRETCH && !(a->param > 1.0)) return fail(SODM_EINVAL, "sodm_walkers_propose: stretch scale a must exceed 1");
+    if (!a->x || !a->mine || !a->others || !a->q || !a->log_factor) return fail(SODM_EINVAL, "sodm_walkers_propose: null array");
+    if (a->iteration < 0 || a->iteration > 0x7FFFFFFFLL) return fail(SODM_EINVAL, "sodm_walkers_propose: iteration out of range");
+    walkers_propose_kernel<<<(unsigned)((a->n_mine + 127) / 128), 128, 0, (cudaStream_t)a->stream>>>(*a);
+    SODM_CUDA_CHECK(cudaGetLastError());
+    return SODM_OK;
+}
+
+extern "C" int sodm_population_clip(int32_t n_dim, int64_t n, int64_t ld, double* x, const double* lb, const double* ub,
+                                    double* penalty, void* stream) {
+    int rc = check_population("sodm_population_clip", n_dim, n, ld);
+    if (rc != SODM_OK) return rc;
+    if (n == 0) return SODM_OK;
+    if (!x || !lb || !ub || !penalty) return fail(SODM_EINVAL, "sodm_population_clip: null array");
+    Bounds b;
+    for (int d = 0; d < n_dim; ++d) { b.lb[d] = lb[d]; b.ub[d] = ub[d]; }
+    population_clip_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n_dim, n, ld, x, b, penalty);
+    SODM_CUDA_CHECK(cudaGetLastError());
+    return SODM_OK;
+}
+
+extern "C" int sodm_walkers_accept(int32_t n_dim, int64_t n_walkers, int64_t ld, double* x, double* lp, const int64_t* mine,
+                                   int64_t n_mine, const double* q, int64_t ld_q, const double* new_lp, const double* penalty,
+                                   const double* log_factor, uint64_t seed, int64_t iteration, int64_t* accepted,
+                                   int32_t* status, void* stream) {
+    int rc = check_population("sodm_walkers_accept", n_dim, n_walkers, ld);
+    if (rc != SODM_OK) return rc;
+    if (n_mine < 0 || ld_q < n_mine) return fail(SODM_EINVAL, "sodm_walkers_accept: n_mine = %lld, ld_q = %lld", (long long)n_mine, (long long)ld_q);
+    if (n_mine == 0) return SODM_OK;
+    if (!x || !lp || !mine || !q || !new_lp || !log_factor || !accepted) return fail(SODM_EINVAL, "sodm_walkers_accept: null array");
+    if (iteration < 0 || iteration > 0x7FFFFFFFLL) return fail(SODM_EINVAL, "sodm_walkers_accept: iteration out of range");
+    walkers_accept_kernel<<<(unsigned)((n_mine + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        n_dim, ld, x, lp, mine, n_mine, q, ld_q, new_lp, penalty, log_factor, seed, (uint32_t)iteration, accepted, status);
+    SODM_CUDA_CHECK(cudaGetLastError());
+    return SODM_OK;
 }

@@ -443,6 +443,76 @@ def pso_best(x, fx, p, fp, feasible=None, best=None, best_index=None, stream=Non
     return best, best_index
 
 
+def _index_list(t, what):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.int64 and t.dim() == 1 and t.is_contiguous()):
+        raise TypeError(f"{what} must be a contiguous int64 CUDA tensor")
+    return t
+
+
+MOVE_KINDS = {"stretch": _ffi.MOVE_STRETCH, "de": _ffi.MOVE_DE, "snooker": _ffi.MOVE_SNOOKER}
+
+
+def walkers_propose(kind, x, mine, others, param, sigma=0.0, seed=0, iteration=0, q=None, log_factor=None, stream=None):
+    """Proposals of the walkers `mine` from the walkers `others` of the ensemble x [n_dim, n_walkers] (`sodm_walkers_propose`;
+    kind 'stretch' | 'de' | 'snooker') -> (q [n_dim, n_mine], log_factor [n_mine]) device tensors; asynchronous."""
+    lib = _ffi.load()
+    x, mine, others = _population(x, "x"), _index_list(mine, "mine"), _index_list(others, "others")
+    n_dim, n_mine = int(x.shape[0]), int(mine.shape[0])
+    if q is None:
+        q = torch.empty((n_dim, n_mine), dtype=torch.float64, device=x.device)
+    if log_factor is None:
+        log_factor = torch.empty(n_mine, dtype=torch.float64, device=x.device)
+    q = _population(q, "q")
+    if q.shape != (n_dim, n_mine) or log_factor.shape != (n_mine,) or log_factor.dtype != torch.float64 or not log_factor.is_contiguous():
+        raise ValueError("q must be [n_dim, n_mine] and log_factor a contiguous float64 tensor [n_mine]")
+    a = _ffi.WalkerMoveArgs()
+    a.kind = MOVE_KINDS[kind] if isinstance(kind, str) else int(kind)
+    a.n_dim, a.n_walkers, a.ld = n_dim, int(x.shape[1]), _ld(x)
+    a.x, a.mine, a.n_mine, a.others, a.n_others = x.data_ptr(), mine.data_ptr(), n_mine, others.data_ptr(), int(others.shape[0])
+    a.param, a.sigma = float(param), float(sigma)
+    a.q, a.ld_q, a.log_factor = q.data_ptr(), _ld(q), log_factor.data_ptr()
+    a.seed, a.iteration, a.stream = int(seed) & 0xFFFFFFFFFFFFFFFF, int(iteration), _stream_ptr(stream)
+    _ffi.check(lib.sodm_walkers_propose(C.byref(a)), lib)
+    return q, log_factor
+
+
+def population_clip(x, lb, ub, penalty=None, stream=None):
+    """Clip x [n_dim, n] into [lb, ub] (host values) in place (`sodm_population_clip`) -> penalty [n]: -inf where a value
+    was clipped, else 0 (the reference objective's treatment of an out-of-bounds theta)."""
+    lib = _ffi.load()
+    x = _population(x, "x")
+    lb_h, ub_h = np.ascontiguousarray(lb, dtype=np.float64), np.ascontiguousarray(ub, dtype=np.float64)
+    if lb_h.shape != (x.shape[0],) or ub_h.shape != (x.shape[0],):
+        raise ValueError("lb and ub need one value per dimension")
+    if penalty is None:
+        penalty = torch.empty(x.shape[1], dtype=torch.float64, device=x.device)
+    _ffi.check(lib.sodm_population_clip(int(x.shape[0]), int(x.shape[1]), _ld(x), x.data_ptr(), lb_h.ctypes.data, ub_h.ctypes.data,
+                                        penalty.data_ptr(), _stream_ptr(stream)), lib)
+    return penalty
+
+
+def walkers_accept(x, lp, mine, q, new_lp, log_factor, accepted, penalty=None, seed=0, iteration=0, status=None, stream=None):
+    """Metropolis-Hastings test of the proposals q [n_dim, n_mine] of the walkers `mine` (`sodm_walkers_accept`): x, lp and
+    accepted are updated in place; status (int32 [1]) collects SODM_WALKERS_ST_NAN."""
+    lib = _ffi.load()
+    x, q, mine = _population(x, "x"), _population(q, "q"), _index_list(mine, "mine")
+    n_dim, n, n_mine = int(x.shape[0]), int(x.shape[1]), int(mine.shape[0])
+    if q.shape != (n_dim, n_mine):
+        raise ValueError("q must be [n_dim, n_mine]")
+    for name, t, m in (("lp", lp, n), ("new_lp", new_lp, n_mine), ("log_factor", log_factor, n_mine), ("penalty", penalty, n_mine)):
+        if t is not None and not (t.is_cuda and t.dtype == torch.float64 and t.shape == (m,) and t.is_contiguous()):
+            raise TypeError(f"{name} must be a contiguous float64 CUDA tensor [{m}]")
+    if not (accepted.is_cuda and accepted.dtype == torch.int64 and accepted.shape == (n,) and accepted.is_contiguous()):
+        raise TypeError(f"accepted must be a contiguous int64 CUDA tensor [{n}]")
+    if status is not None and not (status.is_cuda and status.dtype == torch.int32 and status.numel() >= 1):
+        raise TypeError("status must be an int32 CUDA tensor")
+    _ffi.check(lib.sodm_walkers_accept(n_dim, n, _ld(x), x.data_ptr(), lp.data_ptr(), mine.data_ptr(), n_mine, q.data_ptr(), _ld(q),
+                                       new_lp.data_ptr(), penalty.data_ptr() if penalty is not None else None,
+                                       log_factor.data_ptr(), int(seed) & 0xFFFFFFFFFFFFFFFF, int(iteration),
+                                       accepted.data_ptr(), status.data_ptr() if status is not None else None,
+                                       _stream_ptr(stream)), lib)
+
+
 def kde_logpdf(points, queries, log_norm=0.0, out=None, stream=None):
     """log sum_k exp(-|q_j - x_k|^2 / 2) + log_norm for whitened points [n_dim, K] and queries [n_dim, M]
     (`sodm_kde_logpdf`) -> float64 CUDA tensor [M]."""

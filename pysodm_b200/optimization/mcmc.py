@@ -160,8 +160,15 @@ class EnsembleSampler:
     """The part of `emcee.EnsembleSampler` the reference uses: `sample` / `run_mcmc`, `get_chain`, `get_log_prob`,
     `iteration`, `acceptance_fraction`, `get_autocorr_time`; `log_prob_fn` is scored through its `.batch` when it has one."""
 
-    def __init__(self, nwalkers, ndim, log_prob_fn, moves=None, args=None, kwargs=None, seed=None, backend=None):
+    def __init__(self, nwalkers, ndim, log_prob_fn, moves=None, args=None, kwargs=None, seed=None, backend=None,
+                 device_update=False):
         self.nwalkers, self.ndim = int(nwalkers), int(ndim)
+        self._device_update = bool(device_update)
+        if self._device_update:
+            if not hasattr(log_prob_fn, "batch_device") or args or kwargs:
+                raise TypeError("device_update=True needs an objective with `batch_device` (log_posterior_probability) "
+                                "and no extra arguments")
+            self._objective = log_prob_fn
         if self.nwalkers < 2 * self.ndim:
             raise ValueError("The number of walkers must be at least twice the number of parameters")
         args, kwargs = tuple(args or ()), dict(kwargs or {})
@@ -183,6 +190,7 @@ class EnsembleSampler:
         self._n = 0
         self._accepted = np.zeros(self.nwalkers)
         self.n_batches = 0                               # objective launches so far
+        self._half_updates = 0                           # Philox stream index of the device moves
         if backend is not None and os.path.exists(backend):
             with np.load(backend) as f:
                 self._store, self._store_lp, self._accepted = f["chain"], f["log_prob"], f["accepted"]
@@ -252,6 +260,9 @@ class EnsembleSampler:
             self._store = np.concatenate([self._chain, np.empty((iterations, self.nwalkers, self.ndim))])
             self._store_lp = np.concatenate([self._log_prob, np.empty((iterations, self.nwalkers))])
         half = self.nwalkers // 2
+        if self._device_update:
+            yield from self._sample_on_device(x, lp, iterations, store, progress)
+            return
         for it in range(iterations):
             move = self._moves[self.rng.choice(len(self._moves), p=self._weights)]
             order = self.rng.permutation(self.nwalkers)
@@ -273,6 +284,59 @@ class EnsembleSampler:
             if progress:
                 print(f"\riteration {it + 1}/{iterations}", end="" if it + 1 < iterations else "\n", file=sys.stderr)
             yield x, lp
+
+    def _sample_on_device(self, x, lp, iterations, store, progress):
+        """The ensemble lives on the device as float64 [D, n_walkers] (the layout `batch_device` reads): per half update one
+        `sodm_walkers_propose` (stretch / DE / snooker; the KDE move is proposed on the host from a copy of the ensemble),
+        `sodm_population_clip` (the reference objective's clip + -inf), the simulation and likelihood kernels, and
+        `sodm_walkers_accept`.  The host sees the ensemble once per iteration (the stored chain).  Random numbers: Philox
+        keyed by (seed, walker, half-update counter), so a run does not depend on the launch geometry."""
+        import torch
+        from .. import engine
+        dev = engine.device()
+        obj = self._objective
+        lb, ub = np.array([b[0] for b in obj.expanded_bounds], dtype=np.float64), np.array([b[1] for b in obj.expanded_bounds], dtype=np.float64)
+        n, D, half = self.nwalkers, self.ndim, self.nwalkers // 2
+        x_d = torch.from_numpy(np.ascontiguousarray(x.T)).to(dev)
+        lp_d = torch.from_numpy(np.ascontiguousarray(lp)).to(dev)
+        acc_d = torch.from_numpy(self._accepted.astype(np.int64)).to(dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(self.rng.integers(0, 2 ** 63)))
+        seed = int(self.rng.integers(0, 2 ** 63))
+        for it in range(iterations):
+            move = self._moves[self.rng.choice(len(self._moves), p=self._weights)]
+            order = torch.randperm(n, device=dev, generator=gen)
+            for mine, others in ((order[:half], order[half:]), (order[half:], order[:half])):
+                mine, others = mine.contiguous(), others.contiguous()
+                k = self._half_updates
+                self._half_updates += 1
+                if isinstance(move, StretchMove):
+                    q, lf = engine.walkers_propose("stretch", x_d, mine, others, move.a, 0.0, seed, k)
+                elif isinstance(move, DEMove):
+                    q, lf = engine.walkers_propose("de", x_d, mine, others, 0.0 if move.gamma0 is None else move.gamma0,
+                                                   move.sigma, seed, k)
+                elif isinstance(move, DESnookerMove):
+                    q, lf = engine.walkers_propose("snooker", x_d, mine, others, move.gammas, 0.0, seed, k)
+                else:                                           # host proposal (KDE move, user moves) from a copy of the ensemble
+                    xh = x_d.cpu().numpy().T
+                    qh, lfh = move.propose(xh[mine.cpu().numpy()], xh[others.cpu().numpy()], self.rng)
+                    q = torch.from_numpy(np.ascontiguousarray(qh.T)).to(dev)
+                    lf = torch.from_numpy(np.ascontiguousarray(lfh, dtype=np.float64)).to(dev)
+                penalty = engine.population_clip(q, lb, ub)
+                new_lp = obj.batch_device(q)
+                self.n_batches += 1
+                engine.walkers_accept(x_d, lp_d, mine, q, new_lp, lf, acc_d, penalty=penalty, seed=seed, iteration=k, status=status)
+            xh, lph = x_d.cpu().numpy().T, lp_d.cpu().numpy()      # also the iteration's synchronisation point
+            if int(status.item()):
+                raise ValueError("Probability function returned NaN")
+            self._accepted = acc_d.cpu().numpy().astype(np.float64)
+            if store:
+                self._store[self._n], self._store_lp[self._n] = xh, lph
+                self._n += 1
+            if progress:
+                print(f"\riteration {it + 1}/{iterations}", end="" if it + 1 < iterations else "\n", file=sys.stderr)
+            yield xh, lph
 
     def run_mcmc(self, initial_state, nsteps, **kwargs):
         out = None
@@ -314,11 +378,13 @@ def _directory(path):
 
 def run_EnsembleSampler(pos, max_n, identifier, objective_function, objective_function_args=None,
                         objective_function_kwargs=None, moves=None, fig_path=None, samples_path=None, print_n=10,
-                        discard=0, thin=1, backend=None, processes=1, progress=True, settings_dict={}, seed=None):
+                        discard=0, thin=1, backend=None, processes=1, progress=True, settings_dict={}, seed=None,
+                        device_update=False):
     """The reference's `run_EnsembleSampler` (`mcmc.py:15-231`): set up the sampler (fresh, or continued from `backend`),
     run at most `max_n` iterations, every `print_n` iterations write the samples file and test convergence (chain longer
     than 50 integrated autocorrelation times AND their mean changed by < 3 %).  `processes` and `fig_path` are accepted
-    for compatibility (the evaluation is batched; figures are not drawn).  Returns (sampler, samples)."""
+    for compatibility (the evaluation is batched; figures are not drawn); `device_update=True` keeps the ensemble on the
+    device (`EnsembleSampler._sample_on_device`).  Returns (sampler, samples)."""
     pos = np.asarray(pos, dtype=np.float64)
     samples_path = _directory(samples_path)
     run_date = str(datetime.date.today())
@@ -338,7 +404,8 @@ def run_EnsembleSampler(pos, max_n, identifier, objective_function, objective_fu
             raise FileNotFoundError("backend not found.")
         print(f"Found existing backend:'{fn_backend}'\n\nContinuing run\n--------------\n")
     sampler = EnsembleSampler(nwalkers, ndim, objective_function, moves=moves, args=objective_function_args,
-                              kwargs=objective_function_kwargs, seed=seed, backend=fn_backend)
+                              kwargs=objective_function_kwargs, seed=seed, backend=fn_backend,
+                              device_update=device_update)
     if backend:
         pos = sampler.get_chain()[-1]
     fn_samples = samples_path + f"{identifier}_SAMPLES_{run_date}.nc"

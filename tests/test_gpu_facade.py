@@ -237,7 +237,8 @@ def test_pso_calibration_recovers_parameter(td, capsys):
     assert abs(theta_nm[0] - 0.9) / 0.9 < 0.02
 
 
-def test_ensemble_mcmc_samples_the_posterior(td, tmp_path, monkeypatch):
+@pytest.mark.parametrize("device_update", [False, True])
+def test_ensemble_mcmc_samples_the_posterior(td, tmp_path, monkeypatch, device_update):
     """The reference's MCMC leg in miniature (src/tests/test_calibration.py:195-209): walkers started around an
     estimate sample the posterior of beta; every half-ensemble update is ONE batched device evaluation.  The chain's
     mean and spread are compared with the posterior tabulated on a grid through the same objective."""
@@ -260,7 +261,7 @@ def test_ensemble_mcmc_samples_the_posterior(td, tmp_path, monkeypatch):
     np.random.seed(1)
     ndim, nwalkers, pos = mcmc.perturbate_theta([0.9], pert=[0.02], multiplier=64, bounds=lpp.expanded_bounds)
     sampler, samples = mcmc.run_EnsembleSampler(pos, 150, "sir", lpp, samples_path="out/", print_n=50, discard=50,
-                                                progress=False, seed=3)
+                                                progress=False, seed=3, device_update=device_update)
     assert sampler.n_batches == 1 + 2 * sampler.iteration
     x = samples["beta"].ravel()
     assert x.shape == ((sampler.iteration - 50) * 64,)

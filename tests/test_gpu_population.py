@@ -145,3 +145,140 @@ def test_device_swarm_calibrates_like_the_host_swarm(eng, capsys):
         optimization.pso(lpp, bounds=[(0.0, 3.0), (0.05, 1.0)], swarmsize=8, max_iter=1, device_update=True)
     with pytest.raises(NotImplementedError):
         optimization.pso(lpp, swarmsize=8, max_iter=1, device_update=True, transform_pars=lambda x: x)
+
+
+# ---- ensemble-MCMC moves on the device --------------------------------------------------------------------------------
+
+def _stream(seed, walker, purpose, n_blocks=4):
+    return hc.philox(seed, int(walker), int(purpose), n_blocks).reshape(-1)
+
+
+@pytest.mark.parametrize("kind,param,sigma", [("stretch", 2.0, 0.0), ("de", 0.0, 1e-5), ("de", 1.0, 0.3), ("snooker", 1.7, 0.0)])
+@pytest.mark.parametrize("n,D", [(7, 1), (1001, 3), (100_000, 5)])
+def test_walkers_propose_matches_oracle(eng, kind, param, sigma, n, D):
+    """Same Philox words (seed, walker, 2 * iteration) -> the published move, walker by walker; FMA contraction and the
+    device's log / cospi allow a few ulp."""
+    engine, torch = eng
+    rng = np.random.default_rng(n + D)
+    x = rng.normal(size=(n, D)) * (1.0 + np.arange(D))
+    order = rng.permutation(n)
+    mine, others = order[: n // 2], order[n // 2:]
+    seed, it = 0xFEED_FACE_CAFE_BEEF, 12345
+    q, lf = engine.walkers_propose(kind, _dev(eng, x.T), torch.from_numpy(mine).cuda(), torch.from_numpy(others).cuda(),
+                                   param, sigma, seed, it)
+    q, lf = q.cpu().numpy().T, lf.cpu().numpy()
+    assert q.shape == (len(mine), D) and np.all(np.isfinite(q)) and np.all(np.isfinite(lf))
+    for j in np.unique(np.concatenate([[0, len(mine) - 1], rng.integers(0, len(mine), 150)])):
+        want_q, want_lf = opop.walker_propose(kind, x, mine[j], others, param, sigma, _stream(seed, mine[j], 2 * it))
+        np.testing.assert_allclose(q[j], want_q, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(lf[j], want_lf, rtol=1e-11, atol=1e-12)
+    if n >= 1000:                                       # partners are spread over the whole complementary half
+        if kind == "stretch":
+            z = np.exp(lf / (D - 1.0))
+            assert 0.5 <= z.min() < 0.52 and 1.95 < z.max() <= 2.0
+            assert abs(np.mean(z) - 7.0 / 6.0) < 0.02   # E z under g(z) ~ 1/sqrt(z) on [1/2, 2]
+
+
+def test_walkers_propose_validation(eng):
+    engine, torch = eng
+    x = _dev(eng, np.zeros((3, 8)))
+    idx = torch.arange(4, device="cuda")
+    with pytest.raises(Exception, match="needs 3 walkers"):
+        engine.walkers_propose("snooker", x, idx, idx[:2], 1.7)
+    with pytest.raises(Exception, match="exceed 1"):
+        engine.walkers_propose("stretch", x, idx, idx, 1.0)
+    with pytest.raises(TypeError):
+        engine.walkers_propose("stretch", x, idx.to(torch.int32), idx, 2.0)
+    q, lf = engine.walkers_propose("stretch", x, idx[:0], idx, 2.0)
+    assert q.shape == (3, 0) and lf.shape == (0,)
+
+
+def test_population_clip_and_accept_match_oracle(eng):
+    engine, torch = eng
+    rng = np.random.default_rng(5)
+    n, D = 20_001, 4
+    lb, ub = -np.ones(D), np.array([1.0, 2.0, 0.5, 1.0])
+    q = rng.normal(size=(n, D))
+    qd = _dev(eng, q.T)
+    pen = engine.population_clip(qd, lb, ub).cpu().numpy()
+    out = np.any((q < lb) | (q > ub), axis=1)
+    assert np.array_equal(qd.cpu().numpy().T, np.clip(q, lb, ub))
+    assert np.array_equal(pen, np.where(out, -np.inf, 0.0)) and out.any() and not out.all()
+
+    N = 2 * n + 1
+    x, lp = rng.normal(size=(N, D)), rng.normal(size=N)
+    mine = rng.permutation(N)[:n]
+    new_lp, lf = rng.normal(size=n), 0.3 * rng.normal(size=n)
+    new_lp[:50] = -np.inf
+    new_lp[50:60] = np.inf
+    seed, it = 99, 7
+    xd, lpd, acc = _dev(eng, x.T), _dev(eng, lp), torch.zeros(N, dtype=torch.int64, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    engine.walkers_accept(xd, lpd, torch.from_numpy(mine).cuda(), qd, _dev(eng, new_lp), _dev(eng, lf), acc,
+                          penalty=_dev(eng, pen), seed=seed, iteration=it, status=status)
+    want_x, want_lp, want_acc = x.copy(), lp.copy(), np.zeros(N, dtype=np.int64)
+    for j, me in enumerate(mine):
+        if opop.walker_accepts(lp[me], new_lp[j] if pen[j] == 0 else -np.inf, lf[j], _stream(seed, me, 2 * it + 1, 1)):
+            want_x[me], want_lp[me], want_acc[me] = np.clip(q[j], lb, ub), new_lp[j], 1
+    assert int(status) == 0
+    assert np.array_equal(acc.cpu().numpy(), want_acc) and 0.2 < want_acc.sum() / n < 0.8
+    assert np.array_equal(xd.cpu().numpy().T, want_x) and np.array_equal(lpd.cpu().numpy(), want_lp)
+    # a NaN score is reported, not accepted
+    new_lp[100] = np.nan
+    engine.walkers_accept(xd, lpd, torch.from_numpy(mine).cuda(), qd, _dev(eng, new_lp), _dev(eng, lf), acc, status=status)
+    assert int(status) == 1 and np.isfinite(lpd.cpu().numpy()).all()
+
+
+class _GaussianTarget:
+    """A correlated Gaussian with the interface the device sampler needs (`batch`, `batch_device`, `expanded_bounds`)."""
+
+    def __init__(self, torch, D, bound=50.0):
+        rng = np.random.default_rng(D)
+        A = rng.normal(size=(D, D))
+        self.cov = A @ A.T / D + np.eye(D) * 0.3
+        self.prec = np.linalg.inv(self.cov)
+        self.prec_d = torch.from_numpy(self.prec).cuda()
+        self.expanded_bounds = [(-bound, bound)] * D
+        self.torch = torch
+
+    def batch(self, X):
+        return -0.5 * np.einsum("ij,jk,ik->i", X, self.prec, X)
+
+    def batch_device(self, X):                          # [D, P]
+        return -0.5 * (X * (self.prec_d @ X)).sum(dim=0)
+
+
+@pytest.mark.parametrize("move", ["stretch", "de", "snooker", "cocktail"])
+def test_device_ensemble_samples_a_gaussian(eng, move):
+    """Each device move on its own, and the reference's cocktail (KDE proposals from the host), leave a correlated
+    Gaussian invariant: covariance of the pooled chain within Monte-Carlo error (the CPU sampler passes the same test,
+    tests/test_mcmc_cpu.py)."""
+    engine, torch = eng
+    from pysodm_b200.optimization import mcmc
+    D, n, iters, burn = 3, 512, 400, 100
+    target = _GaussianTarget(torch, D)
+    moves = {"stretch": mcmc.StretchMove(), "de": mcmc.DEMove(sigma=1e-3), "snooker": mcmc.DESnookerMove(),
+             "cocktail": None}[move]
+    if move == "snooker":                               # the snooker alone mixes slowly (it is meant for cocktails)
+        moves = [(mcmc.DESnookerMove(), 0.5), (mcmc.DEMove(sigma=1e-3), 0.5)]
+    sampler = mcmc.EnsembleSampler(n, D, target, moves=moves, seed=11, device_update=True)
+    x0 = np.random.default_rng(0).multivariate_normal(np.zeros(D), target.cov, size=n)
+    sampler.run_mcmc(x0, iters)
+    chain = sampler.get_chain(discard=burn, flat=True)
+    assert chain.shape == ((iters - burn) * n, D)
+    assert np.all(np.abs(chain.mean(axis=0)) < 0.1 * np.sqrt(np.diag(target.cov)))
+    np.testing.assert_allclose(np.cov(chain, rowvar=False), target.cov, rtol=0.12, atol=0.04)
+    assert 0.15 < sampler.acceptance_fraction.mean() < 0.95
+    assert np.allclose(sampler.get_log_prob()[-1], target.batch(sampler.get_chain()[-1]))
+
+
+def test_device_ensemble_respects_bounds(eng):
+    """Proposals outside the objective's bounds are clipped and never accepted (objective_functions.py:301-307)."""
+    engine, torch = eng
+    from pysodm_b200.optimization import mcmc
+    target = _GaussianTarget(torch, 2, bound=0.5)
+    sampler = mcmc.EnsembleSampler(256, 2, target, moves=mcmc.StretchMove(), seed=2, device_update=True)
+    x0 = np.random.default_rng(0).uniform(-0.4, 0.4, size=(256, 2))
+    sampler.run_mcmc(x0, 100)
+    chain = sampler.get_chain(flat=True)
+    assert np.all(np.abs(chain) < 0.5) and np.abs(chain).max() > 0.45

@@ -156,3 +156,29 @@ def test_perturbate_theta_validation():
     np.random.seed(0)
     _, _, pos = mcmc.perturbate_theta([5.0, 0.2], pert=[0.5, 0.5], multiplier=3, bounds=[(0.1, 6.0), (0.1, 1.0)])
     assert pos[:, 0].max() <= 6.0 and pos[:, 1].min() >= 0.1           # clipped before perturbing
+
+
+@pytest.mark.parametrize("kind,param,sigma", [("stretch", 2.0, 0.0), ("de", 0.0, 1e-3), ("snooker", 1.7, 0.0)])
+def test_word_stream_oracle_moves_sample_the_target(kind, param, sigma):
+    """The per-walker restatement the device kernels are checked against (oracle/population.py: draws taken from an
+    explicit stream of 32-bit words) is itself a valid sampler of the same Gaussian."""
+    from oracle import population as opop
+    rng = np.random.default_rng(4)
+    n, iters, burn = 64, 500, 100
+    x = start(n)
+    f = Gaussian()
+    lp = f.batch(x)
+    keep = []
+    for it in range(iters):
+        order = rng.permutation(n)
+        for mine, others in ((order[:n // 2], order[n // 2:]), (order[n // 2:], order[:n // 2])):
+            for me in mine:
+                q, lf = opop.walker_propose(kind, x, me, others, param, sigma, rng.integers(0, 2 ** 32, 16, dtype=np.uint64))
+                new = f(q)
+                if opop.walker_accepts(lp[me], new, lf, rng.integers(0, 2 ** 32, 4, dtype=np.uint64)):
+                    x[me], lp[me] = q, new
+        if it >= burn:
+            keep.append(x.copy())
+    chain = np.concatenate(keep)
+    assert np.allclose(chain.mean(axis=0), MU, atol=0.12), chain.mean(axis=0)
+    assert np.allclose(np.cov(chain, rowvar=False), COV, atol=0.2), np.cov(chain, rowvar=False)

@@ -40,6 +40,17 @@ class Timed:
         return self.lpp(x)
 
 
+class TimedDevice(Timed):
+    def batch_device(self, X):
+        t = time.perf_counter()
+        lp = self.lpp.batch_device(X)
+        torch.cuda.synchronize()
+        self.seconds += time.perf_counter() - t
+        self.calls += 1
+        self.rows += X.shape[1]
+        return lp
+
+
 def main():
     n, iters = 100_000, 10
     model = tm.JumpProcess_influenza_model(td.INFLUENZA_INITIAL_STATES, td.INFLUENZA_PARAMETERS,
@@ -69,6 +80,21 @@ def main():
                                 "walker_updates_per_s": n * iters / wall,
                                 "acceptance": float(s.acceptance_fraction.mean())}
 
+    # the same sampler with the ensemble resident on the device (sodm_walkers_propose / _accept, sodm_population_clip)
+    for label, moves in (("cocktail", None), ("stretch", mcmc.StretchMove()), ("de", mcmc.DEMove())):
+        f = TimedDevice(lpp)
+        s = mcmc.EnsembleSampler(n, 5, f, moves=moves, seed=1, device_update=True)
+        lp0 = f.batch(pos.copy())
+        f.seconds, f.calls, f.rows = 0.0, 0, 0
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        s.run_mcmc(pos, iters, log_prob0=lp0)
+        wall = time.perf_counter() - t
+        res[f"mcmc_{label}_device_update"] = {"ms_per_iteration": wall / iters * 1e3, "ms_in_batch": f.seconds / iters * 1e3,
+                                              "ms_move_kernels_and_host": (wall - f.seconds) / iters * 1e3,
+                                              "batch_calls": f.calls, "walker_updates_per_s": n * iters / wall,
+                                              "acceptance": float(s.acceptance_fraction.mean())}
+
     f = Timed(lpp)
     np.random.seed(0)
     t = time.perf_counter()
@@ -78,16 +104,6 @@ def main():
     res["pso"] = {"ms_per_iteration": wall / f.calls * 1e3, "ms_in_batch": f.seconds / f.calls * 1e3,
                   "ms_host_bookkeeping": (wall - f.seconds) / f.calls * 1e3, "batch_calls": f.calls,
                   "particle_evaluations_per_s": f.rows / wall}
-
-    class TimedDevice(Timed):
-        def batch_device(self, X):
-            t = time.perf_counter()
-            lp = self.lpp.batch_device(X)
-            torch.cuda.synchronize()
-            self.seconds += time.perf_counter() - t
-            self.calls += 1
-            self.rows += X.shape[1]
-            return lp
 
     f = TimedDevice(lpp)
     np.random.seed(0)
