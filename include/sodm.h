@@ -329,11 +329,16 @@ int sodm_kde_logpdf(int32_t n_dim, const double* points, int64_t n_points, int64
  *   SODM_MOVE_STRETCH  q = c + z (s - c), z = ((a-1) u + 1)^2 / a, log factor (D-1) log z          param = a  (emcee: 2)
  *   SODM_MOVE_DE       q = s + gamma (c_a - c_b) + eps, eps ~ N(0, sigma^2), log factor 0           param = gamma (<= 0: 2.38/sqrt(2D))
  *   SODM_MOVE_SNOOKER  q = s + gamma (u.z1 - u.z2) u, u = (s - z)/|s - z|, log factor (D-1) log(|q-z|/|s-z|)   param = gamma (emcee: 1.7)
+ *   SODM_MOVE_KDE      see below
  * Random numbers: Philox keyed by (seed, walker index, 2 * iteration) for the proposal and (.., 2 * iteration + 1) for the
  * acceptance, so a run does not depend on launch geometry. */
 #define SODM_MOVE_STRETCH 0
 #define SODM_MOVE_DE      1
 #define SODM_MOVE_SNOOKER 2
+#define SODM_MOVE_KDE     3   /* q = c_k + L z, z ~ N(0, I): a draw from the Gaussian KDE of `others` whose kernel covariance has
+                               * the lower Cholesky factor `chol`; log_factor is NOT written: the move also fills `white` with
+                               * L^-1 times (the n_others kernel centres | the n_mine current positions | the n_mine proposals),
+                               * the arguments of sodm_kde_logpdf, and the factor is density(s) - density(q) */
 #define SODM_WALKERS_ST_NAN 1      /* a proposal scored NaN (emcee: "Probability function returned NaN") */
 
 typedef struct sodm_walker_move_args {
@@ -349,6 +354,9 @@ typedef struct sodm_walker_move_args {
     double*        q;           /* (device) [n_dim][ld_q] proposals, column j for walker mine[j]                     */
     int64_t        ld_q;
     double*        log_factor;  /* (device) [n_mine] log of the Hastings factor                                      */
+    const double*  chol;        /* (HOST) [n_dim][n_dim] row-major lower Cholesky factor (SODM_MOVE_KDE), else NULL      */
+    double*        white;       /* (device) [n_dim][ld_white] whitened coordinates (SODM_MOVE_KDE), else NULL            */
+    int64_t        ld_white;    /* >= n_others + 2 n_mine                                                            */
     uint64_t       seed;
     int64_t        iteration;   /* 0 .. 2^31 - 1                                                                     */
     void*          stream;

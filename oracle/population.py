@@ -68,7 +68,7 @@ class Words:
 
 def walker_propose(kind, x, me, others, param, sigma, words):
     """One walker's proposal.  x [n, D]; `others` the index list of the complementary half; kind 'stretch' | 'de' |
-    'snooker'.  Returns (q [D], log Hastings factor)."""
+    'snooker' | 'kde'.  Returns (q [D], log Hastings factor)."""
     r = Words(words)
     s, D = x[me], x.shape[1]
     if kind == "stretch":
@@ -80,6 +80,10 @@ def walker_propose(kind, x, me, others, param, sigma, words):
         ia, ib = r.below(len(others)), r.below(len(others) - 1)
         ib += ib >= ia
         return s + gamma * (x[others[ia]] - x[others[ib]]) + sigma * r.normal(), 0.0
+    if kind == "kde":                                   # param = lower Cholesky factor of the kernel covariance
+        c = x[others[r.below(len(others))]]
+        z = np.array([r.normal() for _ in range(D)])
+        return c + np.asarray(param) @ z, None          # the factor is a density ratio: kde_logpdf(s) - kde_logpdf(q)
     i0, i1, i2 = r.below(len(others)), r.below(len(others) - 1), r.below(len(others) - 2)
     i1 += i1 >= i0
     lo, hi = min(i0, i1), max(i0, i1)

@@ -92,11 +92,11 @@ class WalkerMoveArgs(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_dim", C.c_int32), ("n_walkers", C.c_int64), ("ld", C.c_int64), ("x", C.c_void_p),
                 ("mine", C.c_void_p), ("n_mine", C.c_int64), ("others", C.c_void_p), ("n_others", C.c_int64),
                 ("param", C.c_double), ("sigma", C.c_double), ("q", C.c_void_p), ("ld_q", C.c_int64),
-                ("log_factor", C.c_void_p), ("seed", C.c_uint64), ("iteration", C.c_int64), ("stream", C.c_void_p)]
+                ("log_factor", C.c_void_p), ("chol", C.c_void_p), ("white", C.c_void_p), ("ld_white", C.c_int64), ("seed", C.c_uint64), ("iteration", C.c_int64), ("stream", C.c_void_p)]
 
 
 POPULATION_MAX_DIM = 16
-MOVE_STRETCH, MOVE_DE, MOVE_SNOOKER = 0, 1, 2
+MOVE_STRETCH, MOVE_DE, MOVE_SNOOKER, MOVE_KDE = 0, 1, 2, 3
 WALKERS_ST_NAN = 1
 
 SYMBOLS = {

@@ -226,6 +226,65 @@ __global__ void __launch_bounds__(128) walkers_propose_kernel(sodm_walker_move_a
     a.log_factor[j] = lf;
 }
 
+// KDE move: an independence proposal from the Gaussian KDE of the walkers `others` (kernel covariance L L^T).  Also writes
+// the whitened coordinates L^-1 (centres | current positions | proposals) that the pair sum of the Hastings factor reads.
+struct KdeFactor {                                                   // packed lower triangles, (i, j) at i (i + 1) / 2 + j
+    double L[SODM_POPULATION_MAX_DIM * (SODM_POPULATION_MAX_DIM + 1) / 2];
+    double Linv[SODM_POPULATION_MAX_DIM * (SODM_POPULATION_MAX_DIM + 1) / 2];
+};
+
+__global__ void __launch_bounds__(128) walkers_kde_kernel(sodm_walker_move_args a, KdeFactor f) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int D = a.n_dim;
+    const int64_t K = a.n_others;
+    double v[SODM_POPULATION_MAX_DIM], z[SODM_POPULATION_MAX_DIM];
+    if (j < K) {                                                     // whitened kernel centres
+        const int64_t c = a.others[j];
+#pragma unroll
+        for (int d = 0; d < SODM_POPULATION_MAX_DIM; ++d) v[d] = d < D ? a.x[d * a.ld + c] : 0.0;
+#pragma unroll
+        for (int i = 0; i < SODM_POPULATION_MAX_DIM; ++i) {
+            if (i >= D) break;
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k <= i; ++k) acc = fma(f.Linv[i * (i + 1) / 2 + k], v[k], acc);
+            a.white[i * a.ld_white + j] = acc;
+        }
+    }
+    if (j >= a.n_mine) return;
+    const int64_t me = a.mine[j];
+    WalkerRng rng;
+    rng.init(a.seed, (uint64_t)me, (uint32_t)a.iteration * 2u);
+    const int64_t c = a.others[rng.below(K)];
+#pragma unroll
+    for (int d = 0; d < SODM_POPULATION_MAX_DIM; ++d) z[d] = d < D ? rng.normal() : 0.0;
+    // proposal q = c + L z; whitened proposal = L^-1 c + z; whitened current position = L^-1 s
+#pragma unroll
+    for (int d = 0; d < SODM_POPULATION_MAX_DIM; ++d) v[d] = d < D ? a.x[d * a.ld + c] : 0.0;
+#pragma unroll
+    for (int i = 0; i < SODM_POPULATION_MAX_DIM; ++i) {
+        if (i >= D) break;
+        double q = v[i], w = 0.0;
+#pragma unroll
+        for (int k = 0; k <= i; ++k) {
+            q = fma(f.L[i * (i + 1) / 2 + k], z[k], q);
+            w = fma(f.Linv[i * (i + 1) / 2 + k], v[k], w);
+        }
+        a.q[i * a.ld_q + j] = q;
+        a.white[i * a.ld_white + K + a.n_mine + j] = w + z[i];
+    }
+#pragma unroll
+    for (int d = 0; d < SODM_POPULATION_MAX_DIM; ++d) v[d] = d < D ? a.x[d * a.ld + me] : 0.0;
+#pragma unroll
+    for (int i = 0; i < SODM_POPULATION_MAX_DIM; ++i) {
+        if (i >= D) break;
+        double w = 0.0;
+#pragma unroll
+        for (int k = 0; k <= i; ++k) w = fma(f.Linv[i * (i + 1) / 2 + k], v[k], w);
+        a.white[i * a.ld_white + K + j] = w;
+    }
+}
+
 // Clip a population into the bounds IN PLACE and note who had to be clipped: the reference's objective clips an
 // out-of-bounds theta and scores it -inf (objective_functions.py:301-307).
 __global__ void __launch_bounds__(256) population_clip_kernel(int n_dim, int64_t n, int64_t ld, double* __restrict__ x, Bounds b,
@@ -353,12 +412,34 @@ extern "C" int sodm_walkers_propose(const sodm_walker_move_args* a) {
     if (rc != SODM_OK) return rc;
     if (a->n_mine < 0 || a->ld_q < a->n_mine) return fail(SODM_EINVAL, "sodm_walkers_propose: n_mine = %lld, ld_q = %lld", (long long)a->n_mine, (long long)a->ld_q);
     if (a->n_mine == 0) return SODM_OK;
-    const int need = a->kind == SODM_MOVE_STRETCH ? 1 : a->kind == SODM_MOVE_DE ? 2 : a->kind == SODM_MOVE_SNOOKER ? 3 : -1;
+    const int need = a->kind == SODM_MOVE_STRETCH ? 1 : a->kind == SODM_MOVE_DE ? 2 : a->kind == SODM_MOVE_SNOOKER ? 3 :
+                     a->kind == SODM_MOVE_KDE ? 1 : -1;
     if (need < 0) return fail(SODM_EINVAL, "sodm_walkers_propose: unknown move %d", a->kind);
     if (a->n_others < need) return fail(SODM_EINVAL, "sodm_walkers_propose: the move needs %d walkers in the other half, got %lld", need, (long long)a->n_others);
     if (a->kind == SODM_MOVE_STRETCH && !(a->param > 1.0)) return fail(SODM_EINVAL, "sodm_walkers_propose: stretch scale a must exceed 1");
-    if (!a->x || !a->mine || !a->others || !a->q || !a->log_factor) return fail(SODM_EINVAL, "sodm_walkers_propose: null array");
+    if (!a->x || !a->mine || !a->others || !a->q) return fail(SODM_EINVAL, "sodm_walkers_propose: null array");
     if (a->iteration < 0 || a->iteration > 0x7FFFFFFFLL) return fail(SODM_EINVAL, "sodm_walkers_propose: iteration out of range");
+    if (a->kind == SODM_MOVE_KDE) {
+        if (!a->chol || !a->white) return fail(SODM_EINVAL, "sodm_walkers_propose: the KDE move needs chol and white");
+        if (a->ld_white < a->n_others + 2 * a->n_mine) return fail(SODM_EINVAL, "sodm_walkers_propose: ld_white = %lld < n_others + 2 n_mine", (long long)a->ld_white);
+        const int D = a->n_dim;
+        KdeFactor f = {};
+        for (int i = 0; i < D; ++i) {
+            if (!(a->chol[i * D + i] > 0.0)) return fail(SODM_EINVAL, "sodm_walkers_propose: chol[%d][%d] is not positive", i, i);
+            for (int j = 0; j <= i; ++j) f.L[i * (i + 1) / 2 + j] = a->chol[i * D + j];
+        }
+        for (int j = 0; j < D; ++j)                                  // L^-1 by forward substitution, column by column
+            for (int i = j; i < D; ++i) {
+                double acc = i == j ? 1.0 : 0.0;
+                for (int k = j; k < i; ++k) acc -= f.L[i * (i + 1) / 2 + k] * f.Linv[k * (k + 1) / 2 + j];
+                f.Linv[i * (i + 1) / 2 + j] = acc / f.L[i * (i + 1) / 2 + i];
+            }
+        const int64_t n = a->n_mine > a->n_others ? a->n_mine : a->n_others;
+        walkers_kde_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)a->stream>>>(*a, f);
+        SODM_CUDA_CHECK(cudaGetLastError());
+        return SODM_OK;
+    }
+    if (!a->log_factor) return fail(SODM_EINVAL, "sodm_walkers_propose: null array");
     walkers_propose_kernel<<<(unsigned)((a->n_mine + 127) / 128), 128, 0, (cudaStream_t)a->stream>>>(*a);
     SODM_CUDA_CHECK(cudaGetLastError());
     return SODM_OK;

@@ -452,6 +452,32 @@ def _index_list(t, what):
 MOVE_KINDS = {"stretch": _ffi.MOVE_STRETCH, "de": _ffi.MOVE_DE, "snooker": _ffi.MOVE_SNOOKER}
 
 
+def walkers_propose_kde(x, mine, centres, chol, seed=0, iteration=0, stream=None):
+    """KDE move on the device: proposals of the walkers `mine` drawn from the Gaussian KDE of the walkers `centres` with
+    kernel covariance chol chol^T (`sodm_walkers_propose`, SODM_MOVE_KDE), and the log Hastings factor
+    density(s) - density(q) from two pair sums over the whitened coordinates (`sodm_kde_logpdf`)
+    -> (q [n_dim, n_mine], log_factor [n_mine]) device tensors; asynchronous."""
+    lib = _ffi.load()
+    x, mine, centres = _population(x, "x"), _index_list(mine, "mine"), _index_list(centres, "centres")
+    n_dim, n_mine, K = int(x.shape[0]), int(mine.shape[0]), int(centres.shape[0])
+    L = np.ascontiguousarray(chol, dtype=np.float64)
+    if L.shape != (n_dim, n_dim):
+        raise ValueError(f"chol must be [{n_dim}, {n_dim}]")
+    q = torch.empty((n_dim, n_mine), dtype=torch.float64, device=x.device)
+    white = torch.empty((n_dim, K + 2 * n_mine), dtype=torch.float64, device=x.device)
+    a = _ffi.WalkerMoveArgs()
+    a.kind, a.n_dim, a.n_walkers, a.ld = _ffi.MOVE_KDE, n_dim, int(x.shape[1]), _ld(x)
+    a.x, a.mine, a.n_mine, a.others, a.n_others = x.data_ptr(), mine.data_ptr(), n_mine, centres.data_ptr(), K
+    a.q, a.ld_q, a.log_factor = q.data_ptr(), _ld(q), None
+    a.chol, a.white, a.ld_white = L.ctypes.data, white.data_ptr(), _ld(white)
+    a.seed, a.iteration, a.stream = int(seed) & 0xFFFFFFFFFFFFFFFF, int(iteration), _stream_ptr(stream)
+    _ffi.check(lib.sodm_walkers_propose(C.byref(a)), lib)
+    if n_mine == 0:
+        return q, torch.empty(0, dtype=torch.float64, device=x.device)
+    dens = kde_logpdf(white[:, :K], white[:, K:], stream=stream)
+    return q, dens[:n_mine] - dens[n_mine:]
+
+
 def walkers_propose(kind, x, mine, others, param, sigma=0.0, seed=0, iteration=0, q=None, log_factor=None, stream=None):
     """Proposals of the walkers `mine` from the walkers `others` of the ensemble x [n_dim, n_walkers] (`sodm_walkers_propose`;
     kind 'stretch' | 'de' | 'snooker') -> (q [n_dim, n_mine], log_factor [n_mine]) device tensors; asynchronous."""

@@ -100,17 +100,23 @@ class KDEMove:
     def __init__(self, bw_method=None, max_points=4096, logpdf=None):
         self.bw_method, self.max_points, self.logpdf = bw_method, max_points, logpdf
 
+    def bandwidth(self, K, D):
+        if self.bw_method in (None, "scott"):
+            return K ** (-1.0 / (D + 4))
+        if self.bw_method == "silverman":
+            return (K * (D + 2) / 4.0) ** (-1.0 / (D + 4))
+        return float(self.bw_method)
+
+    def factor_of(self, c):
+        """Lower Cholesky factor of the kernel covariance for the centres c[K, D]."""
+        return np.linalg.cholesky(np.atleast_2d(np.cov(c, rowvar=False)) * self.bandwidth(*c.shape) ** 2)
+
     def propose(self, s, c, rng):
         if self.max_points and len(c) > self.max_points:
             c = c[rng.choice(len(c), self.max_points, replace=False)]
         K, D = c.shape
-        if self.bw_method in (None, "scott"):
-            factor = K ** (-1.0 / (D + 4))
-        elif self.bw_method == "silverman":
-            factor = (K * (D + 2) / 4.0) ** (-1.0 / (D + 4))
-        else:
-            factor = float(self.bw_method)
-        L = np.linalg.cholesky(np.atleast_2d(np.cov(c, rowvar=False)) * factor ** 2)
+        factor = self.bandwidth(K, D)
+        L = self.factor_of(c)
         q = c[rng.integers(0, K, len(s))] + rng.standard_normal((len(s), D)) @ L.T
         logpdf = self.logpdf
         if logpdf is None:
@@ -287,7 +293,7 @@ class EnsembleSampler:
 
     def _sample_on_device(self, x, lp, iterations, store, progress):
         """The ensemble lives on the device as float64 [D, n_walkers] (the layout `batch_device` reads): per half update one
-        `sodm_walkers_propose` (stretch / DE / snooker; the KDE move is proposed on the host from a copy of the ensemble),
+        `sodm_walkers_propose` (stretch / DE / snooker / KDE draws; the KDE densities through `sodm_kde_logpdf`),
         `sodm_population_clip` (the reference objective's clip + -inf), the simulation and likelihood kernels, and
         `sodm_walkers_accept`.  The host sees the ensemble once per iteration (the stored chain).  Random numbers: Philox
         keyed by (seed, walker, half-update counter), so a run does not depend on the launch geometry."""
@@ -318,7 +324,11 @@ class EnsembleSampler:
                                                    move.sigma, seed, k)
                 elif isinstance(move, DESnookerMove):
                     q, lf = engine.walkers_propose("snooker", x_d, mine, others, move.gammas, 0.0, seed, k)
-                else:                                           # host proposal (KDE move, user moves) from a copy of the ensemble
+                elif isinstance(move, KDEMove) and move.logpdf is None:
+                    centres = others[:move.max_points] if move.max_points else others    # `others` is in random order
+                    q, lf = engine.walkers_propose_kde(x_d, mine, centres, move.factor_of(x_d[:, centres].cpu().numpy().T),
+                                                       seed, k)
+                else:                                           # host proposal (user moves) from a copy of the ensemble
                     xh = x_d.cpu().numpy().T
                     qh, lfh = move.propose(xh[mine.cpu().numpy()], xh[others.cpu().numpy()], self.rng)
                     q = torch.from_numpy(np.ascontiguousarray(qh.T)).to(dev)

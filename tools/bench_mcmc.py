@@ -81,7 +81,8 @@ def main():
                                 "acceptance": float(s.acceptance_fraction.mean())}
 
     # the same sampler with the ensemble resident on the device (sodm_walkers_propose / _accept, sodm_population_clip)
-    for label, moves in (("cocktail", None), ("stretch", mcmc.StretchMove()), ("de", mcmc.DEMove())):
+    for label, moves in (("cocktail", None), ("stretch", mcmc.StretchMove()), ("de", mcmc.DEMove()),
+                         ("kde", mcmc.KDEMove(bw_method="scott"))):
         f = TimedDevice(lpp)
         s = mcmc.EnsembleSampler(n, 5, f, moves=moves, seed=1, device_update=True)
         lp0 = f.batch(pos.copy())
