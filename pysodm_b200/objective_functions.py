@@ -318,22 +318,24 @@ class log_posterior_probability:
             return lp_d + torch.from_numpy(lp).to(dev)
         return lp + lp_d.cpu().numpy()
 
-    def batch_device(self, thetas, seed=None):
+    def batch_device(self, thetas, seed=None, member_id0=0):
         """lp[P] (float64 CUDA tensor) for a population that LIVES on the device: `thetas` is a float64 CUDA tensor
         [D, P] (structure-of-arrays, one row per expanded parameter -- the layout the simulators read per-trajectory
         parameters in, so nothing is transposed or copied).  For optimisers that keep their population on the device
         (`optimization.pso(..., device_update=True)`).  The caller keeps the population inside the bounds (the device
         swarm update clamps); only uniform priors are available here (their value inside the bounds is 0), anything
-        else needs the host path (`batch`)."""
+        else needs the host path (`batch`).  `member_id0` is the global index of the first column when the population
+        is sharded over ranks (it keys the Philox streams of a stochastic model: `sharding.batch_device_sharded`)."""
         import torch
         if any(fn is not log_prior_uniform for fn in self.log_prior_prob_fnc):
             raise NotImplementedError("batch_device supports uniform priors only; use batch()")
         if not (isinstance(thetas, torch.Tensor) and thetas.is_cuda and thetas.dtype == torch.float64 and
                 thetas.dim() == 2 and thetas.shape[0] == self.n_theta):
             raise ValueError(f"thetas must be a float64 CUDA tensor [{self.n_theta}, P]")
-        return self._device_log_likelihood([thetas[j] for j in range(self.n_theta)], thetas.shape[1], seed, thetas.device)
+        return self._device_log_likelihood([thetas[j] for j in range(self.n_theta)], thetas.shape[1], seed, thetas.device,
+                                           member_id0=member_id0)
 
-    def _device_log_likelihood(self, columns, P, seed, dev):
+    def _device_log_likelihood(self, columns, P, seed, dev, member_id0=0):
         """Sum of the weighted log-likelihoods of P parameter vectors given as one column (host array or CUDA tensor of P
         values) per expanded parameter -> float64 CUDA tensor [P]."""
         import torch
@@ -391,7 +393,7 @@ class log_posterior_probability:
                 inv = 1.0 / float(tau)
                 aligned = method == "tau_leap" and 0 < tau <= 1 and inv == int(inv) and (int(inv) & (int(inv) - 1)) == 0
                 traj, st = engine.jump_run(model.device_model, y, par, P, t0, n_out, tau, method=method, var=var,
-                                           tdpf=tdpf, compat=kw.get("compat", _ffi.COMPAT_REFERENCE), seed=seed + k,
+                                           tdpf=tdpf, compat=kw.get("compat", _ffi.COMPAT_REFERENCE), seed=seed + k, traj_id0=member_id0,
                                            out_dtype=torch.int32 if aligned else torch.float64, state_sel=needed, dev=dev)
                 model._raise_on_status(st)
             else:

@@ -255,8 +255,12 @@ class EnsembleSampler:
     def sample(self, initial_state, iterations=1, store=True, progress=False, log_prob0=None, **_ignored):
         """Generator: one ensemble update (two half updates, two batched evaluations) per item."""
         x = self._check_start(initial_state)
+        if self._device_update:                              # ranks of a torch.distributed job hold replicas of the ensemble
+            from .. import sharding
+            x = sharding.same_on_every_rank(x)
+            self.rng = np.random.default_rng(sharding.agree_on(int(self.rng.integers(0, 2 ** 63))))
         if log_prob0 is None:
-            lp = self._score(x)
+            lp = sharding.batch_sharded(self._objective, x) if self._device_update else self._score(x)
             self.n_batches += 1
         else:
             lp = np.array(log_prob0, dtype=np.float64)
@@ -296,9 +300,12 @@ class EnsembleSampler:
         `sodm_walkers_propose` (stretch / DE / snooker / KDE draws; the KDE densities through `sodm_kde_logpdf`),
         `sodm_population_clip` (the reference objective's clip + -inf), the simulation and likelihood kernels, and
         `sodm_walkers_accept`.  The host sees the ensemble once per iteration (the stored chain).  Random numbers: Philox
-        keyed by (seed, walker, half-update counter), so a run does not depend on the launch geometry."""
+        keyed by (seed, walker, half-update counter), so a run does not depend on the launch geometry.  Under
+        `torch.distributed` every rank holds a replica of the ensemble (D x n doubles), proposes and accepts redundantly
+        from the same streams, and scores only its contiguous range of each half (`sharding.batch_device_sharded`: one
+        all-gather of n/2 log-posteriors per half update)."""
         import torch
-        from .. import engine
+        from .. import engine, sharding
         dev = engine.device()
         obj = self._objective
         lb, ub = np.array([b[0] for b in obj.expanded_bounds], dtype=np.float64), np.array([b[1] for b in obj.expanded_bounds], dtype=np.float64)
@@ -334,7 +341,7 @@ class EnsembleSampler:
                     q = torch.from_numpy(np.ascontiguousarray(qh.T)).to(dev)
                     lf = torch.from_numpy(np.ascontiguousarray(lfh, dtype=np.float64)).to(dev)
                 penalty = engine.population_clip(q, lb, ub)
-                new_lp = obj.batch_device(q)
+                new_lp = sharding.batch_device_sharded(obj, q)       # each rank scores its range of the proposals
                 self.n_batches += 1
                 engine.walkers_accept(x_d, lp_d, mine, q, new_lp, lf, acc_d, penalty=penalty, seed=seed, iteration=k, status=status)
             xh, lph = x_d.cpu().numpy().T, lp_d.cpu().numpy()      # also the iteration's synchronisation point

@@ -75,6 +75,35 @@ def batch_sharded(objective, thetas, **kw):
     return all_gather_concat(t, thetas.shape[0]).cpu().numpy()
 
 
+def batch_device_sharded(objective, thetas, seed=None):
+    """`objective.batch_device` for a device-resident population thetas[D, P] REPLICATED on every rank: each rank scores
+    its contiguous range of columns (Philox streams keyed by one agreed seed and the global column index), the final
+    all-gather of lp (8 bytes per member) is the only exchange; every rank returns the full lp[P] on its device."""
+    rank, ws = world()
+    if ws == 1:
+        return objective.batch_device(thetas) if seed is None else objective.batch_device(thetas, seed=seed)
+    if seed is None:
+        seed = int(np.random.randint(0, 2 ** 32)) | (int(np.random.randint(0, 2 ** 31)) << 32)
+    seed = agree_on(seed)
+    P = int(thetas.shape[1])
+    lo, hi = shard_range(P)
+    if hi > lo:
+        local = objective.batch_device(thetas[:, lo:hi], seed=seed, member_id0=lo)
+    else:
+        local = torch.zeros(0, dtype=torch.float64, device=thetas.device)
+    return all_gather_concat(local, P)
+
+
+def same_on_every_rank(array):
+    """Rank 0's copy of a host array on every rank (starting positions drawn from a rank's own generator)."""
+    rank, ws = world()
+    if ws == 1:
+        return array
+    box = [np.asarray(array)]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
 # ---- reductions over draws of an ensemble sharded by trajectory --------------------------------------------------------
 def _all_reduce(t, op):
     """In-place all-reduce of a (CUDA) tensor; gloo (CPU tests, single-GPU multi-process tests) goes through host memory."""

@@ -311,3 +311,34 @@ def test_device_ensemble_respects_bounds(eng):
     sampler.run_mcmc(x0, 100)
     chain = sampler.get_chain(flat=True)
     assert np.all(np.abs(chain) < 0.5) and np.abs(chain).max() > 0.45
+
+
+def test_sharded_device_populations_match_one_process(tmp_path):
+    """The device sampler (reference cocktail) and the device swarm under torch.distributed: replicas of the population on
+    every rank, each rank scoring its range of the proposals, one all-gather of log-posteriors per batch -- chains, scores
+    and the swarm's optimum equal the single-process run bit for bit, on every rank.  NCCL when the box has >= 2 GPUs,
+    else two ranks on one GPU over gloo."""
+    import socket
+    import subprocess
+    import sys
+    import torch
+    worker = __file__.replace("test_gpu_population.py", "dist_mcmc_worker.py")
+    world = 2
+    backend = "nccl" if torch.cuda.device_count() >= world else "gloo"
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = str(s.getsockname()[1])
+    single, sharded = str(tmp_path / "single.npz"), str(tmp_path / "sharded")
+    procs = [subprocess.Popen([sys.executable, worker, "0", "1", port, backend, single], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True)]
+    procs += [subprocess.Popen([sys.executable, worker, str(r), str(world), port, backend, sharded], stdout=subprocess.PIPE,
+                               stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+    want = np.load(single)
+    assert want["chain"].shape == (24, 66, 2) and 0.05 < want["accepted"].mean() < 0.95
+    for r in range(world):
+        got = np.load(sharded + f".rank{r}.npz")
+        for key in ("chain", "log_prob", "accepted", "theta", "score"):
+            assert np.array_equal(got[key], want[key]), (r, key)

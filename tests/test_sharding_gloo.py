@@ -28,6 +28,12 @@ class _FakeObjective:
         return (np.asarray(thetas) ** 2).sum(axis=1)
 
 
+    def batch_device(self, thetas, seed=None, member_id0=0):
+        """[D, P] -> lp[P]; a stochastic model's term depends on (seed, GLOBAL member index) only."""
+        member = torch.arange(member_id0, member_id0 + thetas.shape[1], dtype=torch.float64)
+        return (thetas ** 2).sum(dim=0) + 1e-3 * member + 1e-9 * float(seed % 1000)
+
+
 def _worker(rank, port, n, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=2)
@@ -39,6 +45,12 @@ def _worker(rank, port, n, out_dir):
         local = torch.arange(lo, hi, dtype=torch.int64)[:, None] * torch.ones(1, 4, dtype=torch.int64)
         full = sharding.all_gather_concat(local, n)
         cols = sharding.all_gather_concat(local.T.contiguous(), n, axis=1)
+        # device-resident population replicated on the ranks: each rank scores its columns, one agreed seed
+        np.random.seed(100 + rank)                            # the ranks' own generators disagree
+        lp_dev = sharding.batch_device_sharded(_FakeObjective(), torch.from_numpy(np.ascontiguousarray(thetas.T)))
+        np.save(os.path.join(out_dir, f"lpdev{rank}.npy"), lp_dev.numpy())
+        start = sharding.same_on_every_rank(np.full(3, float(rank)))
+        assert np.array_equal(start, np.zeros(3))
         np.save(os.path.join(out_dir, f"lp{rank}.npy"), lp)
         np.save(os.path.join(out_dir, f"full{rank}.npy"), full.numpy())
         np.save(os.path.join(out_dir, f"cols{rank}.npy"), cols.numpy())
@@ -55,6 +67,10 @@ def test_two_rank_gloo_gather(tmp_path, n):
     want = (np.random.default_rng(0).normal(size=(n, 3)) ** 2).sum(axis=1)
     for r in range(2):
         np.testing.assert_allclose(np.load(tmp_path / f"lp{r}.npy"), want)
+        lpdev = np.load(tmp_path / f"lpdev{r}.npy")
+        seed_term = lpdev - want - 1e-3 * np.arange(n)        # one seed for every member, the same on both ranks
+        assert np.allclose(seed_term, seed_term[0], atol=1e-12) and 0 <= seed_term[0] < 1e-6 + 1e-12
+        assert np.array_equal(lpdev, np.load(tmp_path / "lpdev0.npy"))
         full = np.load(tmp_path / f"full{r}.npy")
         assert full.shape == (n, 4) and (full[:, 0] == np.arange(n)).all()
         cols = np.load(tmp_path / f"cols{r}.npy")
