@@ -5,6 +5,7 @@
 // warp's loads/stores are coalesced 128-byte transactions, the time-dependent-parameter table (the
 // influenza contact matrices) staged once per block in shared memory and read by broadcast.
 #pragma once
+#include <cstdlib>
 #include "jump_setup.cuh"
 
 namespace sodm {
@@ -53,8 +54,11 @@ __global__ void __launch_bounds__(JUMP_BLOCK, COOP ? SODM_COOP_MIN_BLOCKS : SODM
     const int n_tab = L.n_tdpf_values * M::TDPF_COUNT;
     for (int e = threadIdx.x; e < n_tab; e += blockDim.x) table[e] = (float)L.tdpf_table[e];   // ABI speaks FP64, rates are FP32
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < L.n_traj;
+    // small ensembles leave warp slots idle: spreading the trajectories over more warps (32 >> lane_shift per warp) shortens
+    // every warp's divergent sampling loop (fewer lanes to wait for), see pick_lane_shift
+    const int lanes_used = 32 >> L.lane_shift;
+    const int64_t i = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * lanes_used + lane;
+    const bool active = lane < lanes_used && i < L.n_traj;
     w.lanes = __ballot_sync(0xffffffffu, active);
     if (w.lanes == 0u) return;                                    // whole warp past the end
     tau_leap_trajectory<M, OutT, ALIGNED, COOP>(L, i, active, table, w);
@@ -66,11 +70,39 @@ __global__ void __launch_bounds__(JUMP_BLOCK) ssa_kernel(const __grid_constant__
     if (i < L.n_traj) ssa_trajectory<M, OutT>(L, i);
 }
 
+// Trajectories per warp for the per-lane walk: the largest spread (32, 16, 8 or 4 lanes in use) that keeps the launch below
+// a third of the device's resident-warp slots.  Results do not change (Philox streams are keyed by trajectory, not by
+// lane).  Measured (profiles/r1_lane_spread_ab.txt, C5 window): a warp's 168 steps take ~6.8 ms however few lanes it has
+// (a dependent chain of Philox / log / compare per draw), and above ~10 warps per SM the kernel is issue-bound, where
+// every extra warp costs; so spreading only pays for ensembles of a few thousand trajectories (4096: 6.8 -> 5.2 ms).
+// SODM_LANE_SHIFT=0..3 in the environment overrides the choice (A/B measurements).
+static int pick_lane_shift(int64_t n_traj) {
+    static int slots = 0, forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("SODM_LANE_SHIFT");
+        forced = e && *e >= '0' && *e <= '3' ? *e - '0' : -1;
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        slots = sms * SODM_WALK_MIN_BLOCKS * (JUMP_BLOCK / 32) / 3;
+    }
+    if (forced >= 0) return forced;
+    int shift = 0;
+    while (shift < 3 && (n_traj + (32 >> (shift + 1)) - 1) / (32 >> (shift + 1)) <= slots) ++shift;
+    return shift;
+}
+
+static unsigned spread_grid(int64_t n_traj, int lane_shift) {
+    const int64_t warps = (n_traj + (32 >> lane_shift) - 1) / (32 >> lane_shift);
+    return (unsigned)((warps + JUMP_BLOCK / 32 - 1) / (JUMP_BLOCK / 32));
+}
+
 template <class M, typename OutT>
-static int launch_jump(const JumpLaunch& L, int method, bool aligned, cudaStream_t stream) {
-    const unsigned grid = (unsigned)((L.n_traj + JUMP_BLOCK - 1) / JUMP_BLOCK);
+static int launch_jump(const JumpLaunch& L0, int method, bool aligned, cudaStream_t stream) {
+    JumpLaunch L = L0;
+    const bool coop = (L.compat & TUNE_COOPERATIVE) != 0u;
+    L.lane_shift = method == SODM_JUMP_TAU_LEAP && !coop ? pick_lane_shift(L.n_traj) : 0;
+    const unsigned grid = spread_grid(L.n_traj, L.lane_shift);
     if (method == SODM_JUMP_TAU_LEAP) {
-        const bool coop = (L.compat & TUNE_COOPERATIVE) != 0u;
         const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK +
                              (coop ? (size_t)(JUMP_BLOCK / 32) * coop_queue_words(M::NDRAW) : (size_t)order_words<M>()) +
                              (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);

@@ -45,6 +45,7 @@ struct JumpLaunch {
     int32_t* status;           // [n_traj] or null
     uint32_t compat;
     int64_t max_events;        // SSA event budget per trajectory
+    int32_t lane_shift;        // tau-leap walk: a warp carries 32 >> lane_shift trajectories (small ensembles, jump_kernels.cuh)
 };
 
 template <class M>

@@ -183,8 +183,10 @@ static int launch_gen_warp(const OdeLaunch& L, int method, int dtype, cudaStream
 // A generated model gets the kernels a front end can ask for -- int32 output on the aligned grid, FP64 otherwise, SSA in
 // FP64 -- with the default (walk) sampler: a third of the instantiations of a built-in model, ~15 s of nvcc.
 template <class M>
-static int launch_plugin_jump(const JumpLaunch& L, int method, bool aligned, int dtype, cudaStream_t stream) {
-    const unsigned grid = (unsigned)((L.n_traj + JUMP_BLOCK - 1) / JUMP_BLOCK);
+static int launch_plugin_jump(const JumpLaunch& L0, int method, bool aligned, int dtype, cudaStream_t stream) {
+    JumpLaunch L = L0;
+    L.lane_shift = method == SODM_JUMP_SSA ? 0 : pick_lane_shift(L.n_traj);
+    const unsigned grid = spread_grid(L.n_traj, L.lane_shift);
     if (method == SODM_JUMP_SSA) {
         if (dtype != SODM_F64) return fail(SODM_EUNSUPPORTED, "generated models write SSA output as float64");
         ssa_kernel<M, double><<<grid, JUMP_BLOCK, 0, stream>>>(L);

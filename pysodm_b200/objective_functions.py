@@ -382,7 +382,12 @@ class log_posterior_probability:
                 tdpf = None
                 if method == "tau_leap":
                     n_steps = int(_ffi.load().sodm_jump_n_steps(float(t0), n_out, float(tau)))
-                    tdpf = model._tabulate_tdpfs(t0, n_steps, tau, start_date, time_unit)
+                    # the table depends on the window and on the model's own parameter values only: one entry is kept
+                    key = (t0, n_steps, float(tau), start_date, time_unit,
+                           tuple((nm, np.asarray(v).tobytes()) for nm, v in model.parameters.items()))
+                    if getattr(self, "_tdpf_cache", (None, None))[0] != key:
+                        self._tdpf_cache = (key, model._tabulate_tdpfs(t0, n_steps, tau, start_date, time_unit))
+                    tdpf = self._tdpf_cache[1]
                     if model._spec.tdpf_params and tdpf is None:
                         flat = np.concatenate([model._flat_param(nm, model.parameters[nm]) for nm in model._spec.tdpf_params])
                         tdpf = (flat[None, :], np.zeros(max(n_steps, 1), dtype=np.int32))

@@ -314,6 +314,7 @@ class EnsembleSampler:
         lp_d = torch.from_numpy(np.ascontiguousarray(lp)).to(dev)
         acc_d = torch.from_numpy(self._accepted.astype(np.int64)).to(dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
+        single = sharding.world()[1] == 1                    # ranks score their range of the proposals under one agreed seed
         gen = torch.Generator(device=dev)
         gen.manual_seed(int(self.rng.integers(0, 2 ** 63)))
         seed = int(self.rng.integers(0, 2 ** 63))
@@ -341,7 +342,8 @@ class EnsembleSampler:
                     q = torch.from_numpy(np.ascontiguousarray(qh.T)).to(dev)
                     lf = torch.from_numpy(np.ascontiguousarray(lfh, dtype=np.float64)).to(dev)
                 penalty = engine.population_clip(q, lb, ub)
-                new_lp = sharding.batch_device_sharded(obj, q)       # each rank scores its range of the proposals
+                sim_seed = int(self.rng.integers(0, 2 ** 63))   # drawn in every mode: the host stream does not depend on the ranks
+                new_lp = sharding.batch_device_sharded(obj, q, seed=None if single else sim_seed)
                 self.n_batches += 1
                 engine.walkers_accept(x_d, lp_d, mine, q, new_lp, lf, acc_d, penalty=penalty, seed=seed, iteration=k, status=status)
             xh, lph = x_d.cpu().numpy().T, lp_d.cpu().numpy()      # also the iteration's synchronisation point

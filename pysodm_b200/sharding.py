@@ -82,9 +82,8 @@ def batch_device_sharded(objective, thetas, seed=None):
     rank, ws = world()
     if ws == 1:
         return objective.batch_device(thetas) if seed is None else objective.batch_device(thetas, seed=seed)
-    if seed is None:
-        seed = int(np.random.randint(0, 2 ** 32)) | (int(np.random.randint(0, 2 ** 31)) << 32)
-    seed = agree_on(seed)
+    if seed is None:                                          # a caller's seed must already be the same on every rank
+        seed = agree_on(int(np.random.randint(0, 2 ** 32)) | (int(np.random.randint(0, 2 ** 31)) << 32))
     P = int(thetas.shape[1])
     lo, hi = shard_range(P)
     if hi > lo:
