@@ -194,12 +194,13 @@ class EnsembleSampler:
         self._store = np.empty((0, self.nwalkers, self.ndim))    # capacity >= _n rows; rows [:_n] are the chain
         self._store_lp = np.empty((0, self.nwalkers))
         self._n = 0
-        self._accepted = np.zeros(self.nwalkers)
+        self._accepted_host = np.zeros(self.nwalkers)
+        self._accepted_device = None                     # device sampler: the counts stay there until someone asks
         self.n_batches = 0                               # objective launches so far
         self._half_updates = 0                           # Philox stream index of the device moves
         if backend is not None and os.path.exists(backend):
             with np.load(backend) as f:
-                self._store, self._store_lp, self._accepted = f["chain"], f["log_prob"], f["accepted"]
+                self._store, self._store_lp, self._accepted_host = f["chain"], f["log_prob"], f["accepted"]
             if self._store.shape[1:] != (self.nwalkers, self.ndim):
                 raise ValueError(f"backend '{backend}' holds chains of shape {self._store.shape[1:]}, "
                                  f"expected {(self.nwalkers, self.ndim)}")
@@ -217,6 +218,12 @@ class EnsembleSampler:
     @property
     def _log_prob(self):
         return self._store_lp[:self._n]
+
+    @property
+    def _accepted(self):
+        if self._accepted_device is not None:
+            self._accepted_host = self._accepted_device.cpu().numpy().astype(np.float64)
+        return self._accepted_host
 
     @property
     def acceptance_fraction(self):
@@ -313,6 +320,7 @@ class EnsembleSampler:
         x_d = torch.from_numpy(np.ascontiguousarray(x.T)).to(dev)
         lp_d = torch.from_numpy(np.ascontiguousarray(lp)).to(dev)
         acc_d = torch.from_numpy(self._accepted.astype(np.int64)).to(dev)
+        self._accepted_device = acc_d
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         single = sharding.world()[1] == 1                    # ranks score their range of the proposals under one agreed seed
         gen = torch.Generator(device=dev)
@@ -346,12 +354,14 @@ class EnsembleSampler:
                 new_lp = sharding.batch_device_sharded(obj, q, seed=None if single else sim_seed)
                 self.n_batches += 1
                 engine.walkers_accept(x_d, lp_d, mine, q, new_lp, lf, acc_d, penalty=penalty, seed=seed, iteration=k, status=status)
-            xh, lph = x_d.cpu().numpy().T, lp_d.cpu().numpy()      # also the iteration's synchronisation point
+            # the iteration's only trip to the host (and its synchronisation point): the ensemble, transposed on the device,
+            # straight into its row of the stored chain
+            xh, lph = (self._store[self._n], self._store_lp[self._n]) if store else (np.empty((n, D)), np.empty(n))
+            torch.from_numpy(xh).copy_(x_d.T)
+            torch.from_numpy(lph).copy_(lp_d)
             if int(status.item()):
                 raise ValueError("Probability function returned NaN")
-            self._accepted = acc_d.cpu().numpy().astype(np.float64)
             if store:
-                self._store[self._n], self._store_lp[self._n] = xh, lph
                 self._n += 1
             if progress:
                 print(f"\riteration {it + 1}/{iterations}", end="" if it + 1 < iterations else "\n", file=sys.stderr)

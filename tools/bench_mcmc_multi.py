@@ -1,6 +1,7 @@
 """C5 through the device-resident optimisers on N GPUs: torchrun --nproc-per-node N tools/bench_mcmc_multi.py [out.json]
 (also runs as a single process).  10^5 walkers / particles on the influenza NB posterior; every rank holds a replica of
-the population and scores its range of each batch; wall clock per iteration on rank 0 after a barrier."""
+the population and scores its range of each batch; wall clock per iteration on rank 0 after a barrier.
+SODM_BENCH_WALKERS sets the population size (default 10^5)."""
 import io
 import json
 import os
@@ -27,7 +28,7 @@ def main():
     engine.device(local)
     if ws > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n, iters = 100_000, 10
+    n, iters = int(os.environ.get("SODM_BENCH_WALKERS", "100000")), int(os.environ.get("SODM_BENCH_ITERS", "10"))
     model = tm.JumpProcess_influenza_model(td.INFLUENZA_INITIAL_STATES, td.INFLUENZA_PARAMETERS,
                                            coordinates={"age_group": td.AGE_GROUPS},
                                            time_dependent_parameters={"N": td.influenza_contact_function})

@@ -40,6 +40,18 @@ def main():
     st = pstats.Stats(prof)
     st.sort_stats("cumulative").print_stats(45)
     st.sort_stats("tottime").print_stats(25)
+    import io
+    from contextlib import redirect_stdout
+    from pysodm_b200 import optimization
+    prof = cProfile.Profile()
+    np.random.seed(0)
+    prof.enable()
+    with redirect_stdout(io.StringIO()):
+        optimization.pso(lpp, swarmsize=n, max_iter=10, device_update=True)
+    torch.cuda.synchronize()
+    prof.disable()
+    st = pstats.Stats(prof)
+    st.sort_stats("tottime").print_stats(25)
 
 
 if __name__ == "__main__":
