@@ -530,7 +530,8 @@ class JumpProcess(_DeviceBackedModel):
 
     @staticmethod
     def _raise_on_status(status):
-        bits = int(status.max()) if status.numel() else 0
+        from . import engine
+        bits = engine.status_bits(status)
         if bits & _ffi.ST_BAD_PROB:
             raise ValueError("p < 0, p > 1 or p contains NaNs")          # NumPy's message (base.py:303)
         if bits & _ffi.ST_NONFINITE:
@@ -601,7 +602,7 @@ class ODE(_DeviceBackedModel):
                     self.last_nfev = nfev
 
                 def check(status):
-                    if N and int(status.max()) & (_ffi.ST_STEP_TOO_SMALL | _ffi.ST_NONFINITE):
+                    if N and engine.status_bits(status) & (_ffi.ST_STEP_TOO_SMALL | _ffi.ST_NONFINITE):
                         raise RuntimeError("Required step size is less than spacing between numbers.")
                 return self._sim_on_device(run, var, y0, variables, len(rows), n_kept, N, torch.float64, dev, date_range,
                                            t0, t1, check, time_coord=coord)
@@ -627,7 +628,7 @@ class ODE(_DeviceBackedModel):
                 self.last_nfev[lo:lo + n].copy_(nfev, non_blocking=True)
             pipe.run(N, launch, host)
             pipe.synchronize()
-            bits = int(status.max()) if N else 0
+            bits = engine.status_bits(status) if N else 0
             if bits & (_ffi.ST_STEP_TOO_SMALL | _ffi.ST_NONFINITE):
                 raise RuntimeError("Required step size is less than spacing between numbers.")     # scipy's message
         finally:

@@ -40,6 +40,15 @@ def device(index=None) -> torch.device:
     return torch.device("cuda", index)
 
 
+def status_bits(status):
+    """Bitwise OR of a per-trajectory status vector (SODM_ST_* flags) as a Python int -- not its maximum: a benign high bit
+    on one trajectory (SODM_ST_TRUNCATED_Y0) must not hide an error bit on another.  One device-to-host read."""
+    if status.numel() == 0:
+        return 0
+    flags = torch.stack([(status & (1 << b)).ne(0).any() for b in range(5)]).tolist()
+    return sum(1 << b for b, f in enumerate(flags) if f)
+
+
 def _dev_f64(x, dev):
     if isinstance(x, torch.Tensor):
         return x.to(device=dev, dtype=torch.float64).contiguous()

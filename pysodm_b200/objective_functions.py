@@ -412,7 +412,7 @@ class log_posterior_probability:
                 columns = plan["columns"] if remap is None else [[remap[r] for r in c] for c in plan["columns"]]
                 engine.loglik(self._kinds[i], traj, float(t0), columns, plan["t_data"], plan["ydata"],
                               ll_arg=self.log_likelihood_fnc_args[i], weight=self.weights[i], lp=lp_d, status=st_ll, dev=dev)
-        if int(st_ll.max()) & _ffi.ST_NONFINITE:
+        if engine.status_bits(st_ll) & _ffi.ST_NONFINITE:
             raise ValueError("simulation output contains nan, likely due to numerical unstability. try using more conservative bounds.")
         return lp_d
 

@@ -189,3 +189,14 @@ def test_alignment_plan():
         log_posterior_probability(m, ["beta"], [(0, 1)], [data], ["Im_inc"], [lambda a, b: 0.0], [[]])
     with pytest.raises(ValueError, match="must be of equal length"):
         log_posterior_probability(m, ["beta"], [(0, 1)], [data], ["Im_inc", "S"], [ll_poisson], [[]])
+
+
+def test_status_bits_is_an_or_not_a_maximum():
+    """A benign high flag on one trajectory must not hide an error flag on another."""
+    import torch
+    from pysodm_b200 import _ffi, engine
+    st = torch.tensor([_ffi.ST_TRUNCATED_Y0, _ffi.ST_BAD_PROB, 0, _ffi.ST_MAX_STEPS], dtype=torch.int32)
+    assert int(st.max()) & _ffi.ST_BAD_PROB == 0                       # what the maximum would report
+    assert engine.status_bits(st) == _ffi.ST_TRUNCATED_Y0 | _ffi.ST_BAD_PROB | _ffi.ST_MAX_STEPS
+    assert engine.status_bits(torch.zeros(0, dtype=torch.int32)) == 0
+    assert engine.status_bits(torch.zeros(7, dtype=torch.int32)) == 0
