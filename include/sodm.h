@@ -207,6 +207,10 @@ typedef struct sodm_loglik_args {
 
 int sodm_loglik(const sodm_loglik_args* args);
 
+/* *out |= status[0] | status[1] | .. | status[n-1] (SODM_ST_* flags of a whole launch; the caller zeroes *out).  The front
+ * end turns the flags into the reference's exceptions (base.py:303 NumPy's ValueError; objective_functions.py:264-265). */
+int sodm_status_or(const int32_t* status /* (device) [n] */, int64_t n, int32_t* out /* (device) [1] */, void* stream);
+
 /* ---- output contract: [row][time][traj] (device layout) -> [traj][time][row] per state variable -------- */
 /* For one state variable whose rows are r0 .. r0+n_dim-1:  dst[(i*n_t + j)*n_dim + d] = src[((r0+d)*n_t + j)*ld + i]
  * (base.py:1009-1010 moveaxis + :569-571 concat along "draws").  dst may be device or pinned host memory that is

@@ -107,6 +107,7 @@ SYMBOLS = {
     "sodm_model_info_get": (C.c_int, [C.c_int, C.c_int, C.POINTER(ModelInfo)]),
     "sodm_jump_run": (C.c_int, [C.POINTER(JumpArgs)]),
     "sodm_jump_n_steps": (C.c_int64, [C.c_double, C.c_int32, C.c_double]),
+    "sodm_status_or": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "sodm_ode_run": (C.c_int, [C.POINTER(OdeArgs)]),
     "sodm_ode_n_kept": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
     "sodm_loglik": (C.c_int, [C.POINTER(LoglikArgs)]),

@@ -52,9 +52,26 @@ static int launch_layout(const void* src, int64_t ld, int r0, int n_dim, int n_t
     return SODM_OK;
 }
 
+// Bitwise OR of a status vector: per-thread OR over a grid-stride loop, warp shuffle, one atomicOr per warp that saw a flag.
+__global__ void __launch_bounds__(256) status_or_kernel(const int32_t* __restrict__ status, int64_t n, int32_t* __restrict__ out) {
+    int32_t bits = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) bits |= status[i];
+    bits = __reduce_or_sync(0xffffffffu, (unsigned)bits);
+    if ((threadIdx.x & 31) == 0 && bits) atomicOr(out, bits);
+}
+
 }  // namespace sodm
 
 using namespace sodm;
+
+extern "C" int sodm_status_or(const int32_t* status, int64_t n, int32_t* out, void* stream) {
+    if (n < 0 || !out || (n > 0 && !status)) return fail(SODM_EINVAL, "sodm_status_or: null buffer or negative length");
+    if (n == 0) return SODM_OK;
+    const int64_t blocks = (n + 255) / 256;
+    status_or_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, (cudaStream_t)stream>>>(status, n, out);
+    SODM_CUDA_CHECK(cudaGetLastError());
+    return SODM_OK;
+}
 
 extern "C" int sodm_to_draws_major(const void* src, int32_t src_dtype, int64_t ld, int32_t r0, int32_t n_dim, int32_t n_t,
                                    int64_t n_traj, void* dst, int32_t dst_dtype, void* stream) {

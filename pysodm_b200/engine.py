@@ -45,8 +45,14 @@ def status_bits(status):
     on one trajectory (SODM_ST_TRUNCATED_Y0) must not hide an error bit on another.  One device-to-host read."""
     if status.numel() == 0:
         return 0
-    flags = torch.stack([(status & (1 << b)).ne(0).any() for b in range(5)]).tolist()
-    return sum(1 << b for b, f in enumerate(flags) if f)
+    if not status.is_cuda:                               # host vectors (tests): NumPy
+        return int(np.bitwise_or.reduce(status.numpy().astype(np.int64).ravel()))
+    if status.dtype != torch.int32 or not status.is_contiguous():
+        raise TypeError("status must be a contiguous int32 tensor")
+    lib = _ffi.load()
+    out = torch.zeros(1, dtype=torch.int32, device=status.device)
+    _ffi.check(lib.sodm_status_or(status.data_ptr(), int(status.numel()), out.data_ptr(), _stream_ptr(None)), lib)
+    return int(out.item())
 
 
 def _dev_f64(x, dev):

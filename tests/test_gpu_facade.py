@@ -267,3 +267,20 @@ def test_ensemble_mcmc_samples_the_posterior(td, tmp_path, monkeypatch, device_u
     assert x.shape == ((sampler.iteration - 50) * 64,)
     assert abs(x.mean() - mean) < 0.15 * std and abs(x.std() / std - 1) < 0.15
     assert 0.1 < sampler.acceptance_fraction.mean() < 0.9
+
+
+@pytest.mark.parametrize("n", [1, 33, 100_003, 3_000_000])
+def test_status_flags_are_ored_on_the_device(n):
+    """`sodm_status_or`: the launch's flags are the OR over all trajectories (a maximum would let SODM_ST_TRUNCATED_Y0 on one
+    trajectory hide SODM_ST_BAD_PROB on another)."""
+    import torch
+    from pysodm_b200 import _ffi, engine
+    engine.device(0)
+    st = torch.zeros(n, dtype=torch.int32, device="cuda")
+    assert engine.status_bits(st) == 0
+    st[n // 2] = _ffi.ST_BAD_PROB
+    st[0] = _ffi.ST_TRUNCATED_Y0
+    st[n - 1] |= _ffi.ST_MAX_STEPS
+    want = _ffi.ST_BAD_PROB | _ffi.ST_TRUNCATED_Y0 | _ffi.ST_MAX_STEPS
+    assert engine.status_bits(st) == want
+    assert engine.status_bits(st[:0]) == 0
