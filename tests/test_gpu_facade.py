@@ -278,9 +278,11 @@ def test_status_flags_are_ored_on_the_device(n):
     engine.device(0)
     st = torch.zeros(n, dtype=torch.int32, device="cuda")
     assert engine.status_bits(st) == 0
-    st[n // 2] = _ffi.ST_BAD_PROB
-    st[0] = _ffi.ST_TRUNCATED_Y0
+    st[n // 2] |= _ffi.ST_BAD_PROB
+    st[0] |= _ffi.ST_TRUNCATED_Y0
     st[n - 1] |= _ffi.ST_MAX_STEPS
     want = _ffi.ST_BAD_PROB | _ffi.ST_TRUNCATED_Y0 | _ffi.ST_MAX_STEPS
     assert engine.status_bits(st) == want
+    if n > 2:
+        assert int(st.max()) & _ffi.ST_BAD_PROB == 0
     assert engine.status_bits(st[:0]) == 0
