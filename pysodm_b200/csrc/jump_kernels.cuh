@@ -77,13 +77,13 @@ __global__ void __launch_bounds__(JUMP_BLOCK) ssa_kernel(const __grid_constant__
 // every extra warp costs; so spreading only pays for ensembles of a few thousand trajectories (4096: 6.8 -> 5.2 ms).
 // SODM_LANE_SHIFT=0..3 in the environment overrides the choice (A/B measurements).
 static int pick_lane_shift(int64_t n_traj) {
-    static int slots = 0, forced = -2;
+    static int slots = 0, forced = -2;                       // idempotent initialisation: `forced` is published last
     if (forced == -2) {
-        const char* e = getenv("SODM_LANE_SHIFT");
-        forced = e && *e >= '0' && *e <= '3' ? *e - '0' : -1;
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         slots = sms * SODM_WALK_MIN_BLOCKS * (JUMP_BLOCK / 32) / 3;
+        const char* e = getenv("SODM_LANE_SHIFT");
+        forced = e && *e >= '0' && *e <= '3' ? *e - '0' : -1;
     }
     if (forced >= 0) return forced;
     int shift = 0;

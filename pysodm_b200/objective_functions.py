@@ -322,18 +322,27 @@ class log_posterior_probability:
         """lp[P] (float64 CUDA tensor) for a population that LIVES on the device: `thetas` is a float64 CUDA tensor
         [D, P] (structure-of-arrays, one row per expanded parameter -- the layout the simulators read per-trajectory
         parameters in, so nothing is transposed or copied).  For optimisers that keep their population on the device
-        (`optimization.pso(..., device_update=True)`).  The caller keeps the population inside the bounds (the device
-        swarm update clamps); only uniform priors are available here (their value inside the bounds is 0), anything
-        else needs the host path (`batch`).  `member_id0` is the global index of the first column when the population
-        is sharded over ranks (it keys the Philox streams of a stochastic model: `sharding.batch_device_sharded`)."""
+        (`optimization.pso(..., device_update=True)`, `mcmc.EnsembleSampler(..., device_update=True)`).  The caller keeps
+        the population inside the bounds (the device swarm update clamps, the sampler clips and penalises); uniform priors
+        over those bounds contribute 0 and are skipped, any other prior is evaluated on the host for its coordinate.
+        `member_id0` is the global index of the first column when the population is sharded over ranks (it keys the Philox streams of a stochastic model: `sharding.batch_device_sharded`)."""
         import torch
-        if any(fn is not log_prior_uniform for fn in self.log_prior_prob_fnc):
-            raise NotImplementedError("batch_device supports uniform priors only; use batch()")
         if not (isinstance(thetas, torch.Tensor) and thetas.is_cuda and thetas.dtype == torch.float64 and
                 thetas.dim() == 2 and thetas.shape[0] == self.n_theta):
             raise ValueError(f"thetas must be a float64 CUDA tensor [{self.n_theta}, P]")
-        return self._device_log_likelihood([thetas[j] for j in range(self.n_theta)], thetas.shape[1], seed, thetas.device,
-                                           member_id0=member_id0)
+        lp = self._device_log_likelihood([thetas[j] for j in range(self.n_theta)], thetas.shape[1], seed, thetas.device,
+                                         member_id0=member_id0)
+        # priors that are not "uniform over the parameter's own bounds" (0 inside) are host functions of one coordinate
+        # (scipy.stats log-densities, user callables): their rows make one round trip, 8 bytes per member each way
+        rows = [j for j, (fn, kw) in enumerate(zip(self.log_prior_prob_fnc, self.log_prior_prob_fnc_args))
+                if not (fn is log_prior_uniform and tuple(kw.get("bounds", ())) == tuple(self.expanded_bounds[j]))]
+        if rows and thetas.shape[1]:
+            host = thetas[rows].cpu().numpy()
+            prior = np.zeros(thetas.shape[1])
+            for r, j in enumerate(rows):
+                prior = prior + np.asarray(self.log_prior_prob_fnc[j](host[r], **self.log_prior_prob_fnc_args[j]), dtype=np.float64)
+            lp += torch.from_numpy(prior).to(thetas.device)
+        return lp
 
     def _device_log_likelihood(self, columns, P, seed, dev, member_id0=0):
         """Sum of the weighted log-likelihoods of P parameter vectors given as one column (host array or CUDA tensor of P

@@ -141,6 +141,14 @@ def test_device_swarm_calibrates_like_the_host_swarm(eng, capsys):
     engine, torch = eng
     X = np.column_stack([np.linspace(0.5, 1.5, 33), np.linspace(0.1, 0.4, 33)])
     assert np.array_equal(lpp.batch_device(_dev(eng, X.T)).cpu().numpy(), lpp.batch(X.copy()))
+    # priors other than "uniform over the bounds" are evaluated on the host for their coordinate
+    from pysodm_b200.objective_functions import log_prior_normal, log_prior_uniform
+    lpp2 = log_posterior_probability(model, ["beta", "gamma"], [(0.1, 2.0), (0.05, 1.0)], [data], ["I"], [ll_poisson], [[]],
+                                     start_sim=0, log_prior_prob_fnc=[log_prior_normal, log_prior_uniform],
+                                     log_prior_prob_fnc_args=[{"avg": 0.9, "stdev": 0.1}, {"bounds": (0.15, 0.35)}])
+    got, want = lpp2.batch_device(_dev(eng, X.T)).cpu().numpy(), lpp2.batch(X.copy())
+    assert np.array_equal(got, want) and np.isinf(want).any() and np.isfinite(want).any()
+    assert not np.array_equal(want, lpp.batch(X.copy()))
     with pytest.raises(ValueError, match="inside the objective's bounds"):
         optimization.pso(lpp, bounds=[(0.0, 3.0), (0.05, 1.0)], swarmsize=8, max_iter=1, device_update=True)
     with pytest.raises(NotImplementedError):
