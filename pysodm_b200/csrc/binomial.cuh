@@ -55,30 +55,43 @@ struct PhiloxWords {
 // The hat function / squeeze of BTRS may be evaluated with approximate division and logarithm: an error of a few ulp
 // there moves a candidate boundary or an acceptance threshold by ~1e-7 relative, i.e. perturbs a uniform variate by
 // 1e-7 -- invisible in the sampled law.  The exact pmf ratio (binomial_log_ratio*) keeps accurate arithmetic.
+// On the device these are the bare special-function-unit instructions (MUFU.RCP / RSQ / EX2 / LG2 through the .ftz PTX
+// forms): `__fdividef`, `rsqrtf`, `__expf` and `__logf` wrap the same instruction in a denormal-range rescue (5 / 6 / 4 / 4
+// SASS instructions instead of 2) that cannot trigger here -- every operand is a normal float (us >= 2^-25, n p (1 - p) > 1,
+// arguments of log in (1e-12, 1e12)) -- so the values are bit-identical and a fifth of the kernel's instructions goes away
+// (ncu, profiles/r1_final_tau_leap_ncu_full.txt: 15.6 % of all warp instructions were __fdividef).
 __host__ __device__ __forceinline__ float fast_div(float a, float b) {
 #ifdef __CUDA_ARCH__
-    return __fdividef(a, b);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    return r * a;
 #else
     return a / b;
 #endif
 }
 __host__ __device__ __forceinline__ float fast_sqrt(float x) {      // x > 0
 #ifdef __CUDA_ARCH__
-    return x * rsqrtf(x);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return x * r;
 #else
     return sqrtf(x);
 #endif
 }
 __host__ __device__ __forceinline__ float fast_exp(float x) {
 #ifdef __CUDA_ARCH__
-    return __expf(x);
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
 #else
     return expf(x);
 #endif
 }
 __host__ __device__ __forceinline__ float fast_log(float x) {
 #ifdef __CUDA_ARCH__
-    return __logf(x);
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * 0.693147181f;
 #else
     return logf(x);
 #endif
