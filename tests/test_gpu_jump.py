@@ -5,10 +5,14 @@ tau-leap / SSA within Monte-Carlo error (two-sample KS, p > 0.01) -- checked aga
 unmodified reference (tests/golden/*.npz) and against the pinned oracle on draws with per-trajectory
 parameters.  Integer bookkeeping (conservation, determinism, shard invariance) is checked exactly.
 """
+import os
+
 import numpy as np
 import pytest
 
 import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -291,3 +295,33 @@ def test_cooperative_sampler_has_the_same_law(eng, golden):
                            tdpf=(g["flu_table"], g["flu_step_index"]), seed=21, out_dtype=torch.int32, compat=3 | 256,
                            traj_id0=777)
     assert torch.equal(part, out[:, :, 777:877])          # shard invariance holds for the cooperative schedule too
+
+
+def test_lane_spread_does_not_change_results(tmp_path):
+    """Small ensembles are spread over more warps (32 >> lane_shift trajectories per warp, csrc/jump_kernels.cuh); Philox
+    streams are keyed by trajectory, so every spread gives the same counts.  SODM_LANE_SHIFT is read once per process:
+    one subprocess per setting."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, hashlib, numpy as np, torch\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from pysodm_b200 import engine, tutorial_data as td\n"
+        "engine.device(0)\n"
+        "n = 5003\n"
+        "var = {1: np.random.default_rng(0).uniform(0.01, 0.03, n)}\n"
+        "out, st = engine.jump_run('influenza_1718_jump', td.influenza_flat_y0(), td.influenza_flat_par(), n, 0, 41, 0.5,\n"
+        "                          tdpf=(td.CONTACT_TABLE.reshape(3, 16), td.influenza_schedule()[:80]), var=var, seed=3,\n"
+        "                          out_dtype=torch.int32)\n"
+        "assert int(st.abs().sum()) == 0\n"
+        "print(hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest())\n")
+    digests = []
+    for shift in ("0", "1", "2", "3", None):
+        env = dict(os.environ)
+        env.pop("SODM_LANE_SHIFT", None)
+        if shift is not None:
+            env["SODM_LANE_SHIFT"] = shift
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append(r.stdout.strip().splitlines()[-1])
+    assert len(set(digests)) == 1, digests
