@@ -162,6 +162,26 @@ def integrated_time(chain, c=5.0):
 # the sampler
 # ---------------------------------------------------------------------------------------------------------------------
 
+class DeviceState:
+    """What the device sampler yields after an iteration: the ensemble, still on the device.  `coords` [n_walkers, D] and
+    `log_prob` [n_walkers] (emcee's names) fetch host copies on demand; `x, lp = state` unpacks like the host sampler's pair."""
+
+    def __init__(self, x, lp):
+        self.x, self.lp = x, lp                          # float64 CUDA tensors [D, n_walkers], [n_walkers] (private copies)
+
+    @property
+    def coords(self):
+        return self.x.T.contiguous().cpu().numpy()
+
+    @property
+    def log_prob(self):
+        return self.lp.cpu().numpy()
+
+    def __iter__(self):
+        yield self.coords
+        yield self.log_prob
+
+
 class EnsembleSampler:
     """The part of `emcee.EnsembleSampler` the reference uses: `sample` / `run_mcmc`, `get_chain`, `get_log_prob`,
     `iteration`, `acceptance_fraction`, `get_autocorr_time`; `log_prob_fn` is scored through its `.batch` when it has one."""
@@ -196,6 +216,7 @@ class EnsembleSampler:
         self._n = 0
         self._accepted_host = np.zeros(self.nwalkers)
         self._accepted_device = None                     # device sampler: the counts stay there until someone asks
+        self._pending = None                             # device sampler: stored iterations not yet copied to the host
         self.n_batches = 0                               # objective launches so far
         self._half_updates = 0                           # Philox stream index of the device moves
         if backend is not None and os.path.exists(backend):
@@ -213,11 +234,23 @@ class EnsembleSampler:
 
     @property
     def _chain(self):
+        self._flush()
         return self._store[:self._n]
 
     @property
     def _log_prob(self):
+        self._flush()
         return self._store_lp[:self._n]
+
+    def _flush(self):
+        """Device sampler: bring the iterations that are still in HBM into the host chain (one bulk copy)."""
+        p = self._pending
+        if p is not None and p["count"]:
+            import torch
+            b, c = p["base"], p["count"]
+            torch.from_numpy(self._store[b:b + c]).copy_(p["x"][:c])
+            torch.from_numpy(self._store_lp[b:b + c]).copy_(p["lp"][:c])
+            p["base"], p["count"] = b + c, 0
 
     @property
     def _accepted(self):
@@ -306,7 +339,9 @@ class EnsembleSampler:
         """The ensemble lives on the device as float64 [D, n_walkers] (the layout `batch_device` reads): per half update one
         `sodm_walkers_propose` (stretch / DE / snooker / KDE draws; the KDE densities through `sodm_kde_logpdf`),
         `sodm_population_clip` (the reference objective's clip + -inf), the simulation and likelihood kernels, and
-        `sodm_walkers_accept`.  The host sees the ensemble once per iteration (the stored chain).  Random numbers: Philox
+        `sodm_walkers_accept`.  Per iteration the host reads 4 bytes (the NaN flag); the stored chain stays in HBM and is copied
+        in bulk when it is read (`get_chain`, `save`), when its buffer fills, and at the end; each iteration yields a
+        `DeviceState`.  Random numbers: Philox
         keyed by (seed, walker, half-update counter), so a run does not depend on the launch geometry.  Under
         `torch.distributed` every rank holds a replica of the ensemble (D x n doubles), proposes and accepts redundantly
         from the same streams, and scores only its contiguous range of each half (`sharding.batch_device_sharded`: one
@@ -326,6 +361,23 @@ class EnsembleSampler:
         gen = torch.Generator(device=dev)
         gen.manual_seed(int(self.rng.integers(0, 2 ** 63)))
         seed = int(self.rng.integers(0, 2 ** 63))
+        if store:
+            # the chain stays in HBM (at most ~4 GB of it) and reaches the host in bulk: when the buffer is full, when
+            # someone reads the chain (get_chain, save, the convergence test of run_EnsembleSampler), and at the end
+            cap = max(1, min(iterations, int(4e9 // (n * (D + 1) * 8))))
+            self._pending = {"x": torch.empty((cap, n, D), dtype=torch.float64, device=dev),
+                             "lp": torch.empty((cap, n), dtype=torch.float64, device=dev), "base": self._n, "count": 0, "cap": cap}
+        try:
+            yield from self._device_iterations(iterations, store, progress, x_d, lp_d, acc_d, status, gen, seed, single, lb, ub)
+        finally:
+            self._flush()
+            self._pending = None
+
+    def _device_iterations(self, iterations, store, progress, x_d, lp_d, acc_d, status, gen, seed, single, lb, ub):
+        import torch
+        from .. import engine, sharding
+        dev, obj = x_d.device, self._objective
+        n, D, half = self.nwalkers, self.ndim, self.nwalkers // 2
         for it in range(iterations):
             move = self._moves[self.rng.choice(len(self._moves), p=self._weights)]
             order = torch.randperm(n, device=dev, generator=gen)
@@ -354,18 +406,19 @@ class EnsembleSampler:
                 new_lp = sharding.batch_device_sharded(obj, q, seed=None if single else sim_seed)
                 self.n_batches += 1
                 engine.walkers_accept(x_d, lp_d, mine, q, new_lp, lf, acc_d, penalty=penalty, seed=seed, iteration=k, status=status)
-            # the iteration's only trip to the host (and its synchronisation point): the ensemble, transposed on the device,
-            # straight into its row of the stored chain
-            xh, lph = (self._store[self._n], self._store_lp[self._n]) if store else (np.empty((n, D)), np.empty(n))
-            torch.from_numpy(xh).copy_(x_d.T)
-            torch.from_numpy(lph).copy_(lp_d)
-            if int(status.item()):
-                raise ValueError("Probability function returned NaN")
             if store:
+                p = self._pending
+                if p["count"] == p["cap"]:
+                    self._flush()
+                p["x"][p["count"]].copy_(x_d.T)              # [n, D], the chain's layout
+                p["lp"][p["count"]].copy_(lp_d)
+                p["count"] += 1
                 self._n += 1
+            if int(status.item()):                           # the iteration's only read from the device: 4 bytes
+                raise ValueError("Probability function returned NaN")
             if progress:
                 print(f"\riteration {it + 1}/{iterations}", end="" if it + 1 < iterations else "\n", file=sys.stderr)
-            yield xh, lph
+            yield DeviceState(x_d.clone(), lp_d.clone())
 
     def run_mcmc(self, initial_state, nsteps, **kwargs):
         out = None
