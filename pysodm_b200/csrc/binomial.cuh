@@ -128,7 +128,7 @@ __host__ __device__ __forceinline__ int binomial_inversion(Rng& rng, int n, floa
     float u = u01(rng.next());
     int k = 0;
     // P(X=k+1) = P(X=k) * s * (n-k)/(k+1).  The cap only guards against FP32 round-off in the far tail.
-    while (u > f && k < n && k < 1024) {
+    while (u > f && f > 1e-8f && k < n && k < 1024) {      // f > 1e-8: see binomial_inversion_word
         u -= f;
         ++k;
         f *= s * (float)(n - k + 1) / (float)k;
@@ -222,7 +222,10 @@ __host__ __device__ __forceinline__ int binomial_inversion_word(int n, float p, 
     float u = u01(word);
     const float kmax = (float)(n < 1024 ? n : 1024);
     float kf = 0.0f, left = (float)n;              // left = n - k (exact in FP32 after the first few steps even for n > 2^24)
-    while (u > f && kf < kmax) {
+    // u < 1 strictly (philox.cuh), but FP32 round-off in the running difference (a few 2^-25) can still leave u above the
+    // remaining mass; the search therefore also ends where the pmf has fallen below the 2^-24 grid of u itself (far past
+    // the mode: n p < 10 puts P(0) above 2e-5) -- beyond that point u carries no information -- instead of running to the cap
+    while (u > f && f > 1e-8f && kf < kmax) {
         u -= f;
         kf += 1.0f;
         f *= fast_div(s * left, kf);               // P(k)/P(k-1) = s (n-k+1)/k; a few ulp here only nudge u by ~1e-7
@@ -312,6 +315,60 @@ bool btrs_exact_accept(int n, float p, int k, float lhs) {
     return (double)lhs <= binomial_log_ratio(nd, pd, floor((nd + 1.0) * pd), (double)k);
 }
 
+#ifndef SODM_DIRECT_EXACT
+#define SODM_DIRECT_EXACT 1              // 0: squeeze in front of every exact test (tuning builds)
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// Single-word BTRS stages for the deferred-test walk (jump_run.cuh, sample_worklist_defer).
+//   btrs_candidate_word : candidate k from ONE word: its top 24 bits give u, its low 8 bits the leading 8 bits of v.  The
+//                         box test of BTRS step 1 (us >= 0.07 and v <= v_r) is decided from those 8 bits whenever
+//                         (v8 + 1)/256 <= v_r, i.e. v <= v_r whatever the remaining bits are -> BIN_DONE (69 % of attempts
+//                         on influenza).  Everything else -> BIN_EXACT: the candidate waits for btrs_settle.
+//   btrs_settle         : completes v = (v8 + u01(second word)) / 256 and applies the exact acceptance test of step 3
+//                         (log(v alpha / (a/us^2 + b)) <= log f(k)/f(m)).  The box of step 1 lies inside the acceptance
+//                         region of step 3, so testing a candidate the 8-bit box test could not decide this way is the
+//                         same algorithm; k outside 0..n (step 2) is rejected here as well.
+// The first word is kept with the candidate, so the hat quantities are recomputed rather than stored.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int btrs_candidate_word(int n, float p, uint32_t w, int& k) {
+    const float nf = (float)n;
+    const float np_ = nf * p;
+    const float stddev = fast_sqrt(np_ * (1.0f - p));
+    const float b = 1.15f + 2.53f * stddev;
+    const float a = -0.0873f + 0.0248f * b + 0.01f * p;
+    const float u = u01(w) - 0.5f;
+    const float us = 0.5f - fabsf(u);
+    if (np_ < 4194304.0f) {
+        k = (int)floorf(fmaf(fast_div(2.0f * a, us) + b, u, np_ + 0.5f));
+    } else {
+        const double kd = floor(fma((double)(2.0f * a / us + b), (double)u, fma((double)n, (double)p, 0.5)));
+        k = (int)fmin(fmax(kd, -1.0), 2147483647.0);
+    }
+    const float v_hi = (float)((w & 255u) + 1u) * 0.00390625f;          // upper end of the 8-bit cell of v
+    // v <= v_r = 0.92 - 4.2 / b   <=>   (0.92 - v) b >= 4.2   (b > 0): no reciprocal
+    return (us >= 0.07f && (0.92f - v_hi) * b >= 4.2f) ? BIN_DONE : BIN_EXACT;
+}
+
+__host__ __device__ __forceinline__ bool btrs_settle(int n, float p, int k, uint32_t wu, uint32_t wv) {
+    if (k < 0 || k > n) return false;
+    const float nf = (float)n;
+    BtrsHat h;
+    h.stddev = fast_sqrt(nf * p * (1.0f - p));
+    h.b = 1.15f + 2.53f * h.stddev;
+    h.a = -0.0873f + 0.0248f * h.b + 0.01f * p;
+    h.us = 0.5f - fabsf(u01(wu) - 0.5f);
+    h.v = ((float)(wu & 255u) + u01(wv)) * 0.00390625f;
+    float lhs;
+    if (SODM_DIRECT_EXACT && nf * p < 0.9f * SODM_F32_MODE_LIMIT) {
+        lhs = btrs_lhs(h);
+    } else {
+        const int state = btrs_squeeze(n, p, k, h, lhs);
+        if (state != BIN_EXACT) return state == BIN_DONE;
+    }
+    return btrs_exact_accept(n, p, k, lhs);
+}
+
 // One complete BTRS attempt of a single lane (per-lane walk); requires 0 < p <= 0.5 and n*p >= 10.
 template <class Rng>
 __host__ __device__ __forceinline__ bool btrs_try(Rng& rng, int n, float p, int& k) {
@@ -332,9 +389,6 @@ __host__ __device__ __forceinline__ bool btrs_try(Rng& rng, int n, float p, int&
 // independent attempts of a warp some lane needs that test on four trips out of five anyway, so the squeeze (59
 // instructions, settles two candidates in three) mostly adds to what the warp executes.  Large modes, whose exact
 // test is the FP64 routine, keep the squeeze -- there it settles 98 %.
-#ifndef SODM_DIRECT_EXACT
-#define SODM_DIRECT_EXACT 1              // 0: squeeze in front of every exact test (tuning builds)
-#endif
 __host__ __device__ __forceinline__ bool binomial_try_words(int n, float p, uint32_t wu, uint32_t wv, int& k) {
     int state = binomial_classify(n, p, k);
     if (state == BIN_DONE) return true;

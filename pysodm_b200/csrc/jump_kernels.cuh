@@ -14,54 +14,45 @@ namespace sodm {
 #define SODM_JUMP_BLOCK 128
 #endif
 constexpr int JUMP_BLOCK = SODM_JUMP_BLOCK;
-// Resident blocks per SM the compiler must allow for.  The samplers are latency / instruction-fetch bound (ncu:
-// `no_instruction` is the top stall), so resident warps matter more than registers: measured on influenza,
-// per-lane walk 352 / 272 / 262 / 259 ms at 1 / 5 / 6 / 8 blocks, cooperative 339 / 294 / 311 / 426 ms.
+// Resident blocks per SM the compiler must allow for.  The samplers are issue-bound, so resident warps matter more than
+// registers (round 1, legacy walk on influenza: 352 / 272 / 262 / 259 ms at 1 / 5 / 6 / 8 blocks).
 #ifndef SODM_WALK_MIN_BLOCKS
 #define SODM_WALK_MIN_BLOCKS 8
 #endif
-#ifndef SODM_COOP_MIN_BLOCKS
-#define SODM_COOP_MIN_BLOCKS 5
-#endif
 
-// shared-memory words of the per-lane draw order (one byte per draw and lane), for functors that ask for re-sorting
+// shared-memory words of the per-lane draw order (one byte per draw and lane)
 template <class M>
-__host__ __device__ constexpr int order_words() { return functor_reorder<M>::value > 0 ? (M::NDRAW * JUMP_BLOCK + 3) / 4 : 0; }
+__host__ __device__ constexpr int order_words() { return (M::NDRAW * JUMP_BLOCK + 3) / 4; }
 
-template <class M, typename OutT, bool ALIGNED, bool COOP>
-__global__ void __launch_bounds__(JUMP_BLOCK, COOP ? SODM_COOP_MIN_BLOCKS : SODM_WALK_MIN_BLOCKS) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
+// bytes of dynamic shared memory of a tau-leap block: [NDRAW][JUMP_BLOCK] draw counts | [NDRAW][JUMP_BLOCK] probabilities |
+// [NDRAW][JUMP_BLOCK] draw order (bytes) | TDPF table (FP32)
+template <class M>
+static size_t tau_leap_smem(int n_tdpf_values) {
+    return ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)order_words<M>() + (size_t)n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
+}
+
+template <class M, typename OutT, bool ALIGNED, bool LEGACY>
+__global__ void __launch_bounds__(JUMP_BLOCK, SODM_WALK_MIN_BLOCKS) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
     extern __shared__ float smem[];
-    // [NDRAW][JUMP_BLOCK] draw counts | [NDRAW][JUMP_BLOCK] probabilities | per-warp queues | TDPF table
-    constexpr int WARPS = JUMP_BLOCK / 32;
-    constexpr int QW = coop_queue_words(M::NDRAW);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WorkList w;
     w.n = reinterpret_cast<int*>(smem) + warp * 32;
     w.p = smem + M::NDRAW * JUMP_BLOCK + warp * 32;
-    uint32_t* q = reinterpret_cast<uint32_t*>(smem) + 2 * M::NDRAW * JUMP_BLOCK + warp * QW;
-    w.qs_u = q;
-    w.qs_v = q + COOP_QS_CAP;
-    w.qx_k = q + 2 * COOP_QS_CAP;
-    w.qx_l = reinterpret_cast<float*>(q + 2 * COOP_QS_CAP + COOP_QX_CAP);
-    w.qm = reinterpret_cast<uint16_t*>(q + 2 * COOP_QS_CAP + 2 * COOP_QX_CAP);
-    w.qs = w.qm + M::NDRAW * 32;
-    w.qx = w.qs + COOP_QS_CAP;
+    w.ord = reinterpret_cast<uint8_t*>(smem + 2 * M::NDRAW * JUMP_BLOCK) + warp * 32;
     w.stride = JUMP_BLOCK;
     w.lane = lane;
-    // the walk sampler has no queues; it keeps one byte per (draw, lane) for the lane's draw order instead
-    w.ord = reinterpret_cast<uint8_t*>(smem + 2 * M::NDRAW * JUMP_BLOCK) + warp * 32;
-    float* table = smem + 2 * M::NDRAW * JUMP_BLOCK + (COOP ? WARPS * QW : order_words<M>());
+    float* table = smem + 2 * M::NDRAW * JUMP_BLOCK + order_words<M>();
     const int n_tab = L.n_tdpf_values * M::TDPF_COUNT;
     for (int e = threadIdx.x; e < n_tab; e += blockDim.x) table[e] = (float)L.tdpf_table[e];   // ABI speaks FP64, rates are FP32
     __syncthreads();
     // small ensembles leave warp slots idle: spreading the trajectories over more warps (32 >> lane_shift per warp) shortens
-    // every warp's divergent sampling loop (fewer lanes to wait for), see pick_lane_shift
+    // every warp's sampling loop (fewer lanes to wait for), see pick_lane_shift
     const int lanes_used = 32 >> L.lane_shift;
     const int64_t i = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * lanes_used + lane;
     const bool active = lane < lanes_used && i < L.n_traj;
     w.lanes = __ballot_sync(0xffffffffu, active);
     if (w.lanes == 0u) return;                                    // whole warp past the end
-    tau_leap_trajectory<M, OutT, ALIGNED, COOP>(L, i, active, table, w);
+    tau_leap_trajectory<M, OutT, ALIGNED, LEGACY>(L, i, active, table, w);
 }
 
 template <class M, typename OutT>
@@ -70,7 +61,7 @@ __global__ void __launch_bounds__(JUMP_BLOCK) ssa_kernel(const __grid_constant__
     if (i < L.n_traj) ssa_trajectory<M, OutT>(L, i);
 }
 
-// Trajectories per warp for the per-lane walk: the largest spread (32, 16, 8 or 4 lanes in use) that keeps the launch below
+// Trajectories per warp for the tau-leap samplers: the largest spread (32, 16, 8 or 4 lanes in use) that keeps the launch below
 // a third of the device's resident-warp slots.  Results do not change (Philox streams are keyed by trajectory, not by
 // lane).  Measured (profiles/r1_lane_spread_ab.txt, C5 window): a warp's 168 steps take ~6.8 ms however few lanes it has
 // (a dependent chain of Philox / log / compare per draw), and above ~10 warps per SM the kernel is issue-bound, where
@@ -99,15 +90,13 @@ static unsigned spread_grid(int64_t n_traj, int lane_shift) {
 template <class M, typename OutT>
 static int launch_jump(const JumpLaunch& L0, int method, bool aligned, cudaStream_t stream) {
     JumpLaunch L = L0;
-    const bool coop = (L.compat & TUNE_COOPERATIVE) != 0u;
-    L.lane_shift = method == SODM_JUMP_TAU_LEAP && !coop ? pick_lane_shift(L.n_traj) : 0;
+    const bool legacy = (L.compat & TUNE_LEGACY_WALK) != 0u;
+    L.lane_shift = method == SODM_JUMP_TAU_LEAP ? pick_lane_shift(L.n_traj) : 0;
     const unsigned grid = spread_grid(L.n_traj, L.lane_shift);
     if (method == SODM_JUMP_TAU_LEAP) {
-        const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK +
-                             (coop ? (size_t)(JUMP_BLOCK / 32) * coop_queue_words(M::NDRAW) : (size_t)order_words<M>()) +
-                             (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
-        void (*kernel)(JumpLaunch) = aligned ? (coop ? tau_leap_kernel<M, OutT, true, true> : tau_leap_kernel<M, OutT, true, false>)
-                                             : (coop ? tau_leap_kernel<M, OutT, false, true> : tau_leap_kernel<M, OutT, false, false>);
+        const size_t smem = tau_leap_smem<M>(L.n_tdpf_values);
+        void (*kernel)(JumpLaunch) = aligned ? (legacy ? tau_leap_kernel<M, OutT, true, true> : tau_leap_kernel<M, OutT, true, false>)
+                                             : (legacy ? tau_leap_kernel<M, OutT, false, true> : tau_leap_kernel<M, OutT, false, false>);
         SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         kernel<<<grid, JUMP_BLOCK, smem, stream>>>(L);
     } else {

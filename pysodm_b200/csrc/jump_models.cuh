@@ -166,41 +166,15 @@ struct SirSiJump {
 // flat params: alpha[0] beta[1] gamma[2] delta[3] f_ud[4:8] N[8:24] (row-major 4x4, time dependent)
 // channels   : S->E (4), E->Ip (4), Ip->Iud (4), Ip->Id (4), Iud->R (4), Id->R (4)
 // ------------------------------------------------------------------------------------------------
-// Slot of draw `kind` (0 S->E, 1 E->Ip, 2 Ip->Iud, 3 Ip->Id, 4 Iud->R, 5 Id->R) of age group a.
-// The ORDER in which a lane walks its draws changes nothing in the law but 15 % in the run time (profiles/r1_sampler_ab.txt):
-// lanes start a step together and drift apart, so the draws with small means (cheap, and of mixed regime: trivial /
-// inversion / BTRS) go first, while the lanes still move in step, and the large-mean BTRS draws last, where lanes that have
-// drifted apart at least execute the same code.  Default (11): all 24 draws by ascending season-average mean n min(p, 1-p)
-// (125.8 ms per 10^6 trajectories); 6 = age groups by ascending population, within a group Id->R, Iud->R, Ip pair, E->Ip,
-// S->E (130.9 ms); 0 = as declared, 6a + kind (137.4 ms); 1 = by compartment, S->E first (147.8 ms).
-#ifndef SODM_FLU_SLOT_ORDER
-#define SODM_FLU_SLOT_ORDER 11
-#endif
-__host__ __device__ constexpr int flu_slot(int a, int kind) {
-    switch (SODM_FLU_SLOT_ORDER) {
-        case 0: return 6 * a + kind;
-        case 1: return kind == 0 ? a : kind == 1 ? 4 + a : kind == 2 ? 8 + 2 * a : kind == 3 ? 9 + 2 * a : kind == 4 ? 16 + a : 20 + a;
-        case 6: return 6 * (a == 0 ? 0 : a == 3 ? 1 : a == 1 ? 2 : 3) + (kind == 0 ? 5 : kind == 1 ? 4 : kind == 2 ? 2 : kind == 3 ? 3 : kind == 4 ? 1 : 0);
-        default: { constexpr int t[4][6] = {{4, 5, 1, 2, 0, 3}, {17, 16, 14, 15, 13, 8}, {22, 23, 19, 20, 21, 18}, {12, 11, 9, 10, 7, 6}}; return t[a][kind]; }
-    }
-}
+// Slot of draw `kind` (0 S->E, 1 E->Ip, 2 Ip->Iud, 3 Ip->Id, 4 Iud->R, 5 Id->R) of age group a: declaration order.  The
+// order in which a lane WALKS its draws is not the functor's business: every lane sorts its draws by its own first-step
+// means (reorder_draws, jump_run.cuh) -- the generic rule that serves generated models too.  (Round 1 shipped a table
+// ordered by this model's season-average means; it measured the same as the generic sort, 125.8 vs 125.6 ms, and was
+// fitted to the benchmark's own trajectory, so it is gone.)
+__host__ __device__ constexpr int flu_slot(int a, int kind) { return 6 * a + kind; }
 
-__host__ __device__ constexpr bool flu_slots_valid() {       // a permutation of 0..23 with every Ip->Id right after its Ip->Iud
-    unsigned seen = 0u;
-    for (int a = 0; a < 4; ++a) {
-        for (int k = 0; k < 6; ++k) seen |= 1u << flu_slot(a, k);
-        if (flu_slot(a, 3) != flu_slot(a, 2) + 1) return false;
-    }
-    return seen == 0xffffffu;
-}
-static_assert(flu_slots_valid(), "SODM_FLU_SLOT_ORDER does not describe a valid slot order");
-
-#ifndef SODM_FLU_REORDER_EVERY
-#define SODM_FLU_REORDER_EVERY 0
-#endif
 struct InfluenzaJump {
     static constexpr int NS = 28, NPAR = 24, NCH = 24, TDPF_OFFSET = 8, TDPF_COUNT = 16;
-    static constexpr int REORDER_EVERY = SODM_FLU_REORDER_EVERY;       // 0: the hand-tuned static slot order below
     struct Pre { float beta, cE, cD; float cIp0[4], cIp1[4]; };
 
     __host__ __device__ static Pre prepare(const double* par, float tau, bool quirk) {
@@ -220,7 +194,7 @@ struct InfluenzaJump {
         }
         return pre;
     }
-    // 24 draws: per age group a  S->E, E->Ip, Ip->Iud, Ip->Id (conditional on Ip->Iud), Iud->R, Id->R  (slot order: flu_slot)
+    // 24 draws: per age group a  S->E, E->Ip, Ip->Iud, Ip->Id (conditional on Ip->Iud), Iud->R, Id->R  (slots: flu_slot)
     static constexpr int NDRAW = 24;
     __host__ __device__ static constexpr int slot(int a, int kind) { return flu_slot(a, kind); }
     static constexpr uint32_t DEP_MASK = (1u << flu_slot(0, 3)) | (1u << flu_slot(1, 3)) | (1u << flu_slot(2, 3)) | (1u << flu_slot(3, 3));

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 #include "jump_models.cuh"
 
 namespace sodm {
@@ -18,7 +19,7 @@ namespace sodm {
 constexpr int MAX_PARAM = 64;   // flat parameter elements passed by value
 constexpr int MAX_STATE = 64;   // flat state elements of a jump model
 
-enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, TUNE_COOPERATIVE = 256u };
+enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, TUNE_LEGACY_WALK = 256u };
 
 struct JumpLaunch {
     int64_t n_traj;            // trajectories in this launch
@@ -61,6 +62,7 @@ __host__ __device__ __forceinline__ void load_trajectory(const JumpLaunch& L, in
         const double v = L.y0_bcast ? L.y0[s] : L.y0[(int64_t)s * L.ld_in + i];
         y[s] = (int)v;
         if ((double)y[s] != v) st |= ST_TRUNCATED_Y0;
+        if (y[s] < 0) { st |= ST_BAD_PROB; y[s] = 0; }       // NumPy's binomial raises for n < 0 (base.py:303)
     }
 }
 
@@ -106,18 +108,11 @@ __host__ __device__ __forceinline__ void emit_interp(const JumpLaunch& L, int64_
 
 // The binomial draws of one step of the 32 trajectories of a warp: slot d of lane l holds (n, p) and, once
 // drawn, the count T in place of n.  On the device the arrays live in shared memory as [slot][thread of block], so
-// a warp touching ONE slot of 32 different lanes (own or not) hits 32 different banks.
+// a warp touching ONE slot of its 32 lanes hits 32 different banks.
 struct WorkList {
     int* n;             // warp base pointers: element (d, lane) at [d * stride + lane]
     float* p;
-    uint16_t* qm;       // warp queue of items ((d << 5) | lane): BTRS regime from the front, inversion regime from the back
-    uint16_t* qs;       // candidates outside the BTRS box, waiting for the squeeze; payload = the attempt's two words
-    uint32_t* qs_u;
-    uint32_t* qs_v;
-    uint16_t* qx;       // candidates the squeeze could not settle, waiting for the exact test; payload = k, log(scaled v)
-    uint32_t* qx_k;
-    float* qx_l;
-    uint8_t* ord;       // per-lane walk: the order in which this lane takes its draws, [q * stride + lane] -> slot (or null)
+    uint8_t* ord;       // the order in which this lane takes its draws, [q * stride + lane] -> slot
     int stride;
     int lane;
     unsigned lanes;     // device: lanes of the warp that run a trajectory
@@ -126,326 +121,218 @@ struct WorkList {
 };
 
 #ifdef __CUDA_ARCH__
-constexpr int COOP_LANES = 32;
 __device__ __forceinline__ unsigned coop_ballot(bool x) { return __ballot_sync(0xffffffffu, x); }
-__device__ __forceinline__ unsigned coop_lt(int lane) { return (1u << lane) - 1u; }
 __device__ __forceinline__ int coop_popc(unsigned m) { return __popc(m); }
-__device__ __forceinline__ void coop_sync() { __syncwarp(); }
+__device__ __forceinline__ int low_bit(uint32_t m) { return __ffs((int)m) - 1; }
+__device__ __forceinline__ int low_bit(uint64_t m) { return __ffsll((long long)m) - 1; }
 #else
-constexpr int COOP_LANES = 1;        // CPU harness: a "warp" of one lane runs the same algorithm
-inline unsigned coop_ballot(bool x) { return x ? 1u : 0u; }
-inline unsigned coop_lt(int) { return 0u; }
+inline unsigned coop_ballot(bool x) { return x ? 1u : 0u; }       // CPU harness: a "warp" of one lane runs the same algorithm
 inline int coop_popc(unsigned m) { return (int)(m & 1u); }
-inline void coop_sync() {}
+inline int low_bit(uint32_t m) { return __builtin_ctz(m); }
+inline int low_bit(uint64_t m) { return __builtin_ctzll(m); }
 #endif
-constexpr int COOP_QS_CAP = 96;
-constexpr int COOP_QX_CAP = 96;       // >= COOP_QS_CAP: one squeeze drain can never overflow it
 
-// 4-byte words of queue storage per warp: qm, qs (+2 payload words), qx (+2 payload words)
-__host__ __device__ constexpr int coop_queue_words(int ndraw) {
-    return (ndraw * 32 + COOP_QS_CAP + COOP_QX_CAP) / 2 + 2 * COOP_QS_CAP + 2 * COOP_QX_CAP;
-}
+// Draw order of a lane (position -> slot), set once from the lane's OWN first-step means (a trajectory's result must not
+// depend on its warp neighbours): independent slots by ascending mean n min(p, 1 - p), then the slots that are conditional
+// on another one (bit d of DEP_MASK: slot d's n is what slot d-1 left behind), so that by the time a lane reaches them
+// their predecessors are settled.  The ORDER changes nothing in the law; it decides how well the lanes of a warp share
+// code paths: trajectories of one ensemble resemble each other, so with a common ordering rule the small-mean draws
+// (sequential inversion) of all lanes meet in the first trips of a step and the large-mean draws (BTRS) in the rest,
+// whichever lane has fallen behind by a few attempts (measured in round 1 on the per-lane walk: declaration order 137 ms,
+// sorted once 126 ms per 10^6 influenza trajectories; re-sorting often is worse because the lanes' orders drift apart).
+// A functor may declare `static constexpr int REORDER_EVERY = K` to re-sort every K steps.  Rank sort, NDRAW^2 compares.
+template <class M, class = void> struct functor_reorder { static constexpr int value = 0; };
+template <class M> struct functor_reorder<M, decltype((void)M::REORDER_EVERY)> { static constexpr int value = M::REORDER_EVERY; };
 
-__host__ __device__ __forceinline__ float word_as_float(uint32_t w) {
-#ifdef __CUDA_ARCH__
-    return __uint_as_float(w);
-#else
-    float f; memcpy(&f, &w, 4); return f;
-#endif
-}
-__host__ __device__ __forceinline__ uint32_t float_as_word(float f) {
-#ifdef __CUDA_ARCH__
-    return __float_as_uint(f);
-#else
-    uint32_t w; memcpy(&w, &f, 4); return w;
-#endif
-}
-
-// dependency level of every slot: 0 = independent, L = conditional on a slot of level L-1 (bit d of DEP_MASK:
-// slot d's n is what slot d-1 left behind)
-__host__ __device__ constexpr uint32_t level_mask(uint32_t dep_mask, int ndraw, int level) {
-    uint32_t out = 0u;
-    int run = 0;
-    for (int d = 0; d < ndraw; ++d) {
-        run = ((dep_mask >> d) & 1u) ? run + 1 : 0;
-        if (run == level) out |= 1u << d;
-    }
-    return out;
-}
-__host__ __device__ constexpr int max_level(uint32_t dep_mask, int ndraw) {
-    int best = 0, run = 0;
-    for (int d = 0; d < ndraw; ++d) {
-        run = ((dep_mask >> d) & 1u) ? run + 1 : 0;
-        best = run > best ? run : best;
-    }
-    return best;
-}
-
-// Random words of one (trajectory, step): counter-based, so ANY lane can regenerate the words of ANY item.
-//   attempts 2c and 2c+1 of slot d : Philox(seed; step, 0x20000000 | d << 16 | c, traj)   (words 0,1 and 2,3)
-//   inversion of slot d            : the same block c = 0, word 0
-// Nothing random is stored: a pending item carries at most its attempt's two words through the squeeze queue.
-struct StepKey {
-    uint64_t seed;
-    uint64_t traj0;      // global id of lane 0's trajectory
-    uint32_t step;
-};
-#ifdef __CUDA_ARCH__
-__device__ __noinline__          // one copy for the first pass and the re-draws: keeps the hot loop's code small
-#else
-inline
-#endif
-void philox_block(const StepKey& key, int lane, uint32_t tag, uint32_t (&out)[4]) {
-    Philox4x32 g;
-    g.init(key.seed, key.traj0 + (uint64_t)lane);
-    g.ctr0 = key.step;
-    g.ctr1 = tag;
-    g.next4(out);
-}
-
-// WARP-COOPERATIVE sampler (tuning flag SODM_TUNE_COOPERATIVE; NOT the default -- see the measurements below).
-// In a divergent SIMT loop the warp pays (trips) x (union of the branches any lane takes), and a per-lane rejection
-// sampler takes a different branch on almost every lane: measured on the per-lane walk, 8-9 of 32 lanes are active
-// per instruction (profiles/).  Here the 32 x NDRAW draws of a warp-step are pooled instead: every lane classifies
-// its own slots and appends them to warp queues by REGIME; the queues are then processed 32 items at a time, so all
-// lanes of the warp run the same code on different items:
-//   pass 0   own slots: trivial cases, first-attempt random words, queue by regime (ballot + popc compaction)
-//   BTRS     first attempts; accepted -> result; rejected -> compacted in place for the next round with fresh
-//            counter-based words; undecided by the squeeze -> exact-test queue
-//   exact    log-pmf ratio test on queued candidates; failures rejoin the BTRS queue
-//   inverse  sequential-search inversion on the small-mean items
-// Items conditional on another slot (DEP_MASK) form a second level that runs after the first is final.
-// Measured on B200 (influenza, 2^20 trajectories, profiles/r1_sampler_ab.txt): 22 of 32 lanes active and 40 % fewer
-// warp instructions than the walk, but the queue traffic through shared memory, the ballots and the extra Philox
-// blocks leave it at 4.6 M traj/s against 6.3 M traj/s for the walk at 32 resident warps per SM; it is kept for
-// models whose draws are more expensive relative to the bookkeeping.
-template <int NDRAW, uint64_t DEP_MASK64>
-__host__ __device__ __forceinline__ void sample_worklist_coop(const StepKey& key, WorkList& w, uint32_t& st) {
-    static_assert(NDRAW <= 32, "the cooperative sampler takes at most 32 draws per step");
-    constexpr uint32_t DEP_MASK = (uint32_t)DEP_MASK64;
-    constexpr int LEVELS = max_level(DEP_MASK, NDRAW) + 1;
-    static_assert(LEVELS <= 2, "the cooperative sampler handles compartments with at most two exits");
-    constexpr int CAP = NDRAW * COOP_LANES;
+template <int NDRAW, uint64_t DEP_MASK>
+__host__ __device__ __forceinline__ void reorder_draws(WorkList& w) {
     const int S = w.stride, lane = w.lane;
-    const unsigned lt = coop_lt(lane);
+    float key[NDRAW];
 #pragma unroll
-    for (int level = 0; level < LEVELS; ++level) {
-        const uint32_t in_level = level_mask(DEP_MASK, NDRAW, level);
-        int nb = 0, ni = 0, nx = 0;
-        // ---- pass 0: own slots -> trivial results, regime queues ----------------------------------------------------
-#pragma unroll 1
-        for (int d = 0; d < NDRAW; ++d) {
-            if (!((in_level >> d) & 1u)) continue;
+    for (int d = 0; d < NDRAW; ++d) {
+        const float p = w.p[d * S + lane];
+        const float k = (float)w.n[d * S + lane] * fminf(p, 1.0f - p);
+        key[d] = ((DEP_MASK >> d) & 1ull) ? 3.0e38f : (k == k ? k : 0.0f);     // NaN probabilities are flagged by the sampler; keep a total order
+    }
+#pragma unroll
+    for (int d = 0; d < NDRAW; ++d) {
+        int pos = 0;
+#pragma unroll
+        for (int e = 0; e < NDRAW; ++e)
+            if (e != d) pos += (key[e] < key[d] || (key[e] == key[d] && e < d)) ? 1 : 0;
+        w.ord[pos * S + lane] = (uint8_t)d;
+    }
+}
+
+// what the earlier exits of slot d's compartment element have taken (d is conditional: bit d of DEP_MASK)
+template <uint64_t DEP_MASK>
+__host__ __device__ __forceinline__ int chain_taken(const WorkList& w, int d) {
+    int taken = 0, e = d;
+    do {
+        --e;
+        taken += w.n[e * w.stride + w.lane];
+    } while ((DEP_MASK >> e) & 1ull);
+    return taken;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// DEFERRED-TEST WALK (default sampler).
+//
+// In a divergent SIMT loop the warp pays (trips) x (union of the branches any lane takes).  The per-lane walk of round 1
+// (kept below as the legacy schedule) ran the exact acceptance test of a BTRS candidate right where the box test failed:
+// one attempt in three needs it, so SOME lane of 32 needed it on almost every trip and the warp executed the ~130
+// instructions of the test at 8 of 32 lanes, next to inversion at 6 lanes -- 17.4 of 32 lanes per instruction overall
+// (profiles/r1_mufu_tau_leap_ncu_full.txt).  Here a trip has ONE body for the whole warp:
+//   C trip  every lane that still has a draw to do takes the next one in its order and makes ONE attempt from ONE random
+//           word: trivial cases and small means (sequential inversion) finish at once; a BTRS candidate that passes the box
+//           test (decided from the 8 low bits of the same word) is final; any other candidate is PARKED in registers (its k,
+//           its word, its position; up to DEFER_SLOTS of them) and the lane moves on to its next draw -- the draws of a step
+//           are independent of each other except for the few conditional ones, which sit last in the order.
+//   X trip  every lane that has parked candidates settles the newest one: second word -> full-resolution v -> exact
+//           acceptance test (btrs_settle).  Accepted: the count is final.  Rejected: the draw's position returns to the
+//           lane's to-do mask and is attempted again on a later C trip.
+// The warp votes (ballots) which of the two bodies the next trip runs: X when no lane can make progress otherwise, when
+// some lane's parking slots are full, or when at least DEFER_VOTE lanes have something parked.  Every trip consumes exactly
+// one word of every lane's Philox stream, used or not, so all lanes refill their 4-word block on the same trips.
+// Rejection sampling stays exact under any such schedule: each attempt uses words nobody has looked at before, and whether
+// an attempt is accepted depends on its own words only.
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef SODM_DEFER_SLOTS
+#define SODM_DEFER_SLOTS 3
+#endif
+#ifndef SODM_DEFER_VOTE
+#define SODM_DEFER_VOTE 24
+#endif
+constexpr int DEFER_SLOTS = SODM_DEFER_SLOTS;
+static_assert(DEFER_SLOTS >= 1 && DEFER_SLOTS <= 4, "1 to 4 parked candidates per lane");
+
+// One word per trip for every lane; the buffer position is the same on all lanes of a warp by construction.
+struct TripRng {
+    Philox4x32 gen;
+    uint32_t w0, w1, w2, w3;
+    int left;
+    __host__ __device__ __forceinline__ void init(uint64_t seed, uint64_t traj) {
+        gen.init(seed, traj);
+        w0 = w1 = w2 = w3 = 0u;
+        left = 0;
+    }
+    __host__ __device__ __forceinline__ uint32_t next() {
+        if (left == 0) {
+            uint32_t b[4];
+            gen.next4(b);
+            w0 = b[0]; w1 = b[1]; w2 = b[2]; w3 = b[3];
+            left = 4;
+        }
+        const uint32_t v = w0;
+        w0 = w1; w1 = w2; w2 = w3;
+        --left;
+        return v;
+    }
+};
+
+template <int NDRAW> struct draw_mask { using type = typename std::conditional<(NDRAW <= 32), uint32_t, uint64_t>::type; };
+
+template <int NDRAW, uint64_t DEP_MASK>
+__host__ __device__ __forceinline__ void sample_worklist_defer(TripRng& rng, WorkList& w, uint32_t& st) {
+    using Mask = typename draw_mask<NDRAW>::type;
+    constexpr Mask ONE = 1;
+    constexpr Mask ALL = NDRAW == 8 * (int)sizeof(Mask) ? ~Mask(0) : (ONE << (NDRAW % (8 * (int)sizeof(Mask)))) - ONE;
+    const int S = w.stride, lane = w.lane;
+    // a conditional draw carries ~n (negative) until its first attempt turns it into n - (what the earlier exits took)
+#pragma unroll
+    for (int d = 0; d < NDRAW; ++d)
+        if ((DEP_MASK >> d) & 1ull) w.n[d * S + lane] = ~w.n[d * S + lane];
+    Mask todo = ALL;            // POSITIONS (in the lane's order) still to be attempted
+    Mask open = ALL;            // SLOTS whose count is not final yet
+    int npend = 0;
+    int pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0;          // parked candidates, newest first: k, word, position (one byte each)
+    uint32_t pw0 = 0u, pw1 = 0u, pw2 = 0u, pw3 = 0u, ppos = 0u;
+    bool stalled = false;       // the lane's next draw waits for a parked predecessor
+    for (;;) {
+        const bool can = todo != 0 && npend < DEFER_SLOTS && !stalled;
+        const unsigned mc = coop_ballot(can), mp = coop_ballot(npend > 0);
+        if ((mc | mp) == 0u) break;
+        const uint32_t word = rng.next();
+        const bool settle = mp != 0u && (mc == 0u || coop_ballot(npend >= DEFER_SLOTS) != 0u || coop_popc(mp) >= SODM_DEFER_VOTE);
+        if (settle) {
+            // ---- X trip ------------------------------------------------------------------------------------------
+            if (npend > 0) {
+                const int pos = (int)(ppos & 255u);
+                const int d = (int)w.ord[pos * S + lane];
+                const int n = w.n[d * S + lane];
+                const float p = w.p[d * S + lane];
+                const bool flip = p > 0.5f;
+                if (btrs_settle(n, flip ? 1.0f - p : p, pk0, pw0, word)) {
+                    w.n[d * S + lane] = flip ? n - pk0 : pk0;
+                    open &= ~(ONE << d);
+                } else {
+                    todo |= ONE << pos;
+                }
+                pk0 = pk1; pk1 = pk2; pk2 = pk3;
+                pw0 = pw1; pw1 = pw2; pw2 = pw3;
+                ppos >>= 8;
+                --npend;
+            }
+            stalled = false;
+        } else if (can) {
+            // ---- C trip ------------------------------------------------------------------------------------------
+            const int pos = low_bit(todo);
+            const int d = (int)w.ord[pos * S + lane];
             int n = w.n[d * S + lane];
             const float p = w.p[d * S + lane];
-            if (level > 0) { n -= w.n[(d - 1) * S + lane]; w.n[d * S + lane] = n; }   // what the previous exit left behind
-            int k;
-            const int state = binomial_classify(n, p, k);
-            if (state == BIN_DONE) {
-                if (k < 0) { st |= ST_BAD_PROB; k = 0; }
-                w.n[d * S + lane] = k;
+            bool go = true;
+            if (((DEP_MASK >> d) & 1ull) && n < 0) {                // first attempt of a conditional draw
+                if ((open >> (d - 1)) & ONE) { stalled = true; go = false; }     // predecessor parked: wait for an X trip
+                else { n = ~n - chain_taken<DEP_MASK>(w, d); w.n[d * S + lane] = n; }
             }
-            const unsigned mB = coop_ballot(state == BIN_BTRS), mI = coop_ballot(state == BIN_INVERT);
-            if (state == BIN_BTRS) w.qm[nb + coop_popc(mB & lt)] = (uint16_t)((d << 5) | lane);
-            if (state == BIN_INVERT) w.qm[CAP - 1 - (ni + coop_popc(mI & lt))] = (uint16_t)((d << 5) | lane);
-            nb += coop_popc(mB);
-            ni += coop_popc(mI);
-        }
-        coop_sync();
-        // ---- BTRS rounds ------------------------------------------------------------------------------------------
-        // qm[0, count): items to attempt.  Consumed entries are re-used in place for the items that must be re-drawn
-        // (keep <= number consumed, always).  Candidates outside the BTRS box wait in qs for the squeeze, candidates the
-        // squeeze cannot settle wait in qx for the exact test; both queues are drained when nearly full and at the end
-        // of a round, and what they reject rejoins the re-draw list.
-        int count = nb, ns = 0;
-        uint32_t attempt = 0u;
-        while (count > 0) {
-            int keep = 0;
-            for (int base = 0; base < count; base += COOP_LANES) {
-                const bool valid = base + lane < count;
-                int state = BIN_DONE;
-                uint16_t e = 0;
-                uint32_t wu = 0u, wv = 0u;
-                if (valid) {
-                    e = w.qm[base + lane];
-                    const int d = e >> 5, o = e & 31;
-                    const int n = w.n[d * S + o];
-                    const float p = w.p[d * S + o];
-                    const bool flip = p > 0.5f;
-                    uint32_t r[4];
-                    philox_block(key, o, 0x20000000u | ((uint32_t)d << 16) | (attempt >> 1), r);
-                    wu = (attempt & 1u) ? r[2] : r[0];
-                    wv = (attempt & 1u) ? r[3] : r[1];
-                    int k;
-                    state = btrs_candidate(n, flip ? 1.0f - p : p, wu, wv, k);
-                    if (state == BIN_DONE) w.n[d * S + o] = flip ? n - k : k;
-                }
-                coop_sync();                                 // every lane has read its queue entry
-                const unsigned mR = coop_ballot(valid && state == BIN_RETRY), mS = coop_ballot(valid && state == BIN_SQUEEZE);
-                if (valid && state == BIN_RETRY) w.qm[keep + coop_popc(mR & lt)] = e;
-                if (valid && state == BIN_SQUEEZE) {
-                    const int q = ns + coop_popc(mS & lt);
-                    w.qs[q] = e;
-                    w.qs_u[q] = wu;
-                    w.qs_v[q] = wv;
-                }
-                keep += coop_popc(mR);
-                ns += coop_popc(mS);
-                coop_sync();
-                const bool last = base + COOP_LANES >= count;
-                if (ns > COOP_QS_CAP - COOP_LANES || last) {
-                    // ---- squeeze ----
-                    for (int sb = 0; sb < ns; sb += COOP_LANES) {
-                        const bool sv = sb + lane < ns;
-                        int sstate = BIN_DONE, k = 0;
-                        float lhs = 0.0f;
-                        uint16_t se = 0;
-                        if (sv) {
-                            se = w.qs[sb + lane];
-                            const int d = se >> 5, o = se & 31;
-                            const int n = w.n[d * S + o];
-                            const float p = w.p[d * S + o];
-                            const bool flip = p > 0.5f;
-                            const float pp = flip ? 1.0f - p : p;
-                            const uint32_t su = w.qs_u[sb + lane], sw = w.qs_v[sb + lane];
-                            btrs_candidate(n, pp, su, sw, k);
-                            sstate = btrs_squeeze(n, pp, k, su, sw, lhs);
-                            if (sstate == BIN_DONE) w.n[d * S + o] = flip ? n - k : k;
-                        }
-                        const unsigned mR2 = coop_ballot(sv && sstate == BIN_RETRY), mX = coop_ballot(sv && sstate == BIN_EXACT);
-                        if (sv && sstate == BIN_RETRY) w.qm[keep + coop_popc(mR2 & lt)] = se;
-                        if (sv && sstate == BIN_EXACT) {
-                            const int q = nx + coop_popc(mX & lt);
-                            w.qx[q] = se;
-                            w.qx_k[q] = (uint32_t)k;
-                            w.qx_l[q] = lhs;
-                        }
-                        keep += coop_popc(mR2);
-                        nx += coop_popc(mX);
-                        coop_sync();
-                    }
-                    ns = 0;
-                    // ---- exact log-pmf ratio test (qx can hold a full squeeze queue, so it is drained right after it) ----
-                    for (int xb = 0; xb < nx; xb += COOP_LANES) {
-                        const bool xv = xb + lane < nx;
-                        bool fail = false;
-                        uint16_t xe = 0;
-                        if (xv) {
-                            xe = w.qx[xb + lane];
-                            const int d = xe >> 5, o = xe & 31;
-                            const int n = w.n[d * S + o];
-                            const float p = w.p[d * S + o];
-                            const bool flip = p > 0.5f;
-                            const int k = (int)w.qx_k[xb + lane];
-                            if (btrs_exact_accept(n, flip ? 1.0f - p : p, k, w.qx_l[xb + lane])) w.n[d * S + o] = flip ? n - k : k;
-                            else fail = true;
-                        }
-                        const unsigned mF = coop_ballot(fail);
-                        if (fail) w.qm[keep + coop_popc(mF & lt)] = xe;
-                        keep += coop_popc(mF);
-                    }
-                    nx = 0;
-                    coop_sync();
-                }
-            }
-            count = keep;
-            ++attempt;
-        }
-        // ---- inversion-regime items ----------------------------------------------------------------------------------
-        for (int base = 0; base < ni; base += COOP_LANES) {
-            if (base + lane < ni) {
-                const uint16_t e = w.qm[CAP - 1 - (base + lane)];
-                const int d = e >> 5, o = e & 31;
-                const int n = w.n[d * S + o];
-                const float p = w.p[d * S + o];
+            if (go) {
+                todo &= ~(ONE << pos);
+                int k;
+                int state = binomial_classify(n, p, k);
                 const bool flip = p > 0.5f;
-                uint32_t r[4];
-                philox_block(key, o, 0x20000000u | ((uint32_t)d << 16), r);
-                const int k = binomial_inversion_word(n, flip ? 1.0f - p : p, r[0]);
-                w.n[d * S + o] = flip ? n - k : k;
+                const float pp = flip ? 1.0f - p : p;
+                if (state == BIN_DONE) {
+                    if (k < 0) { st |= ST_BAD_PROB; k = 0; }
+                } else {
+                    if (state == BIN_INVERT) { k = binomial_inversion_word(n, pp, word); state = BIN_DONE; }
+                    else state = btrs_candidate_word(n, pp, word, k);
+                    if (state == BIN_DONE) k = flip ? n - k : k;
+                }
+                if (state == BIN_DONE) {
+                    w.n[d * S + lane] = k;
+                    open &= ~(ONE << d);
+                } else {                                          // park the candidate
+                    pk3 = pk2; pk2 = pk1; pk1 = pk0; pk0 = k;
+                    pw3 = pw2; pw2 = pw1; pw1 = pw0; pw0 = word;
+                    ppos = (ppos << 8) | (uint32_t)pos;
+                    ++npend;
+                }
             }
         }
-        coop_sync();
     }
 }
 
-// Per-lane walk (default): each lane draws its own slots one after the other with a private Philox stream, retrying
-// a rejected attempt on its next trip through the loop while its neighbours move on to their next slot -- the warp
-// runs for max_lane(sum of attempts) trips instead of sum_slot(max_lane attempts).  One copy of the sampler code.
-// Every trip consumes exactly two words of the lane's Philox stream (an inversion uses one and drops the other), so
-// all lanes refill their 4-word block on the same trips: the Philox rounds are issued every second trip for the whole
-// warp instead of on almost every trip for a few lanes (ncu: Philox was 18.6 % of the instructions at 6 active lanes).
+// LEGACY per-lane walk (SODM_TUNE_LEGACY_WALK; the default sampler of round 1, kept for A/B measurements and as a second
+// schedule of the same law in the tests): each lane draws its slots one after the other with a private Philox stream,
+// retrying a rejected attempt on its next trip through the loop while its neighbours move on to their next slot; the
+// exact test runs inside the trip that needs it.  Every trip consumes exactly two words (an inversion uses one and drops
+// the other), and every lane starts a step on a fresh block, so all lanes refill on the same trips.
 struct WalkRng {
     Philox4x32 gen;
     uint32_t w0, w1, w2, w3;
     bool second;
 };
-// Steps between re-sorts of a lane's draw order: a functor declares `static constexpr int REORDER_EVERY = K` to have its
-// draws re-sorted every K steps (generated models: nobody tuned their slot order); without the member -- the hand-written
-// functors, whose slot order is tuned by hand -- the order is the functor's own.  Measured on influenza (ms per 10^6):
-// declaration order 137.4; re-sorted every 4 / 16 / 64 / 128 steps 135.0 / 129.0 / 127.9 / 126.6; sorted ONCE at the first
-// step 125.6; best hand-tuned static order 125.8.  Frequent re-sorting loses because every lane then follows its own
-// order and the lanes of a warp stop sharing slots; one sort from the (shared or similar) initial state keeps them aligned.
-template <class M, class = void> struct functor_reorder { static constexpr int value = 0; };
-template <class M> struct functor_reorder<M, decltype((void)M::REORDER_EVERY)> { static constexpr int value = M::REORDER_EVERY; };
 
-// Units of the draw list: a slot together with the slots conditional on it (bit d of DEP_MASK: d belongs to the unit of d-1).
 template <int NDRAW, uint64_t DEP_MASK>
-struct DrawUnits {
-    int n_units = 0;
-    int first[NDRAW] = {};
-    int size[NDRAW] = {};
-    constexpr DrawUnits() {
-        for (int d = 0; d < NDRAW; ++d) {
-            if ((DEP_MASK >> d) & 1ull) ++size[n_units - 1];
-            else { first[n_units] = d; size[n_units] = 1; ++n_units; }
-        }
-    }
-};
-
-// Re-sort this lane's draw order by ascending current mean n min(p, 1 - p) of each unit's first slot.  The ORDER changes
-// nothing in the law; it decides how well the lanes of a warp share code paths: lanes start a step together and drift
-// apart, so cheap small-mean draws (of mixed regime) go first and the large-mean BTRS draws last, where drifted lanes
-// still execute the same instructions (measured on influenza, static orders: 137 -> 126 ms per 10^6 trajectories,
-// profiles/r1_sampler_ab.txt).  Sorting by the lane's OWN state keeps a trajectory independent of its warp neighbours
-// (results do not depend on sharding or chunking).  Branch-free rank sort: NU^2 compares per re-sort.
-template <int NDRAW, uint64_t DEP_MASK>
-__host__ __device__ __forceinline__ void reorder_draws(WorkList& w) {
-    constexpr DrawUnits<NDRAW, DEP_MASK> U{};
-    const int S = w.stride, lane = w.lane;
-    float key[NDRAW];
-#pragma unroll
-    for (int u = 0; u < U.n_units; ++u) {
-        const float p = w.p[U.first[u] * S + lane];
-        const float k = (float)w.n[U.first[u] * S + lane] * fminf(p, 1.0f - p);
-        key[u] = k == k ? k : 0.0f;                              // NaN probabilities are flagged by the sampler; keep a total order
-    }
-#pragma unroll
-    for (int u = 0; u < U.n_units; ++u) {
-        int pos = 0;
-#pragma unroll
-        for (int v = 0; v < U.n_units; ++v)
-            if (v != u) pos += (key[v] < key[u] || (key[v] == key[u] && v < u)) ? U.size[v] : 0;
-#pragma unroll
-        for (int e = 0; e < U.size[u]; ++e) w.ord[(pos + e) * S + lane] = (uint8_t)(U.first[u] + e);
-    }
-}
-
-template <int NDRAW, uint64_t DEP_MASK, bool REORDERED>
 __host__ __device__ __forceinline__ void sample_worklist_walk(WalkRng& rng, WorkList& w, uint32_t& st) {
     const int S = w.stride, lane = w.lane;
-    int q = 0, chain = 0;                // chain = what the earlier exits of the same compartment element have taken
-    // Every trip is one attempt that consumes exactly two Philox words, and every lane starts a step on a fresh block
-    // (the half-used one of the previous step is dropped): the lanes of a warp then refill on the same trips, so the
-    // generator -- a sixth of the kernel's instructions -- always runs with the whole warp.  Letting each lane carry
-    // its leftover pair across steps halves the active lanes per refill and costs 11 % (profiles/r1_sampler_ab.txt).
+    int q = 0;
     rng.second = false;
     while (q < NDRAW) {
-        const int d = REORDERED ? (int)w.ord[q * S + lane] : q;
+        const int d = (int)w.ord[q * S + lane];
         int n = w.n[d * S + lane];
         const float p = w.p[d * S + lane];
-        const bool dep = (DEP_MASK >> d) & 1ull;
-        if (dep) n -= chain;
+        if ((DEP_MASK >> d) & 1ull) n -= chain_taken<DEP_MASK>(w, d);      // predecessors come earlier in the order: final
         if (!rng.second) {
             uint32_t b[4];
             rng.gen.next4(b);
@@ -457,7 +344,6 @@ __host__ __device__ __forceinline__ void sample_worklist_walk(WalkRng& rng, Work
         if (binomial_try_words(n, p, wu, wv, k)) {
             if (k < 0) { st |= ST_BAD_PROB; k = 0; }
             w.n[d * S + lane] = k;
-            chain = dep ? chain + k : k;
             ++q;
         }
     }
@@ -469,8 +355,8 @@ template <class M, class = void> struct functor_uses_time { static constexpr boo
 template <class M> struct functor_uses_time<M, decltype((void)M::USES_TIME)> { static constexpr bool value = M::USES_TIME; };
 
 // One trajectory per lane.  `active` = the lane owns a trajectory; the remaining lanes of a partially filled warp
-// still take part in the warp-cooperative sampling (they own no items) but neither load nor store.
-template <class M, typename OutT, bool ALIGNED, bool COOP>
+// still take part in the warp's votes (they have no draws to make) but neither load nor store.
+template <class M, typename OutT, bool ALIGNED, bool LEGACY>
 __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L, int64_t i, bool active,
                                                              const float* table, WorkList w) {
     double par[M::NPAR];
@@ -486,14 +372,12 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
     const bool quirk = (L.compat & COMPAT_STAY_QUIRK) != 0u;
     const float tau = (float)L.tau;
     const typename M::Pre pre = M::prepare(par, tau, quirk);
-    WalkRng rng;                           // private stream of the per-lane walk
-    rng.gen.init(L.seed, (uint64_t)(L.traj_id0 + i));
-    rng.w0 = rng.w1 = rng.w2 = rng.w3 = 0u;
-    rng.second = false;
-    StepKey key;
-    key.seed = L.seed;
-    key.traj0 = (uint64_t)(L.traj_id0 + i - w.lane);
-    key.step = 0u;
+    TripRng rng;                           // private stream of the trajectory (deferred-test walk)
+    rng.init(L.seed, (uint64_t)(L.traj_id0 + i));
+    WalkRng wrng;                          // the same stream, consumed in pairs (legacy walk)
+    wrng.gen.init(L.seed, (uint64_t)(L.traj_id0 + i));
+    wrng.w0 = wrng.w1 = wrng.w2 = wrng.w3 = 0u;
+    wrng.second = false;
 
     if (active) emit_counts<M, OutT>(L, i, 0, y);
     int j = 1;
@@ -508,15 +392,10 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
         const float* tab = M::TDPF_COUNT ? table + (int64_t)L.tdpf_index[k] * M::TDPF_COUNT : table;
         if constexpr (functor_uses_time<M>::value) M::propose(y, pre, tab, tau, quirk, w, ALIGNED ? L.t0 + (double)k * L.tau : t);
         else M::propose(y, pre, tab, tau, quirk, w);
-        key.step = (uint32_t)k;
-        if constexpr (COOP) sample_worklist_coop<M::NDRAW, (uint64_t)M::DEP_MASK>(key, w, st);
-        else {
-            constexpr int EVERY = functor_reorder<M>::value;
-            if constexpr (EVERY > 0) {
-                if (k % EVERY == 0) reorder_draws<M::NDRAW, (uint64_t)M::DEP_MASK>(w);
-            }
-            sample_worklist_walk<M::NDRAW, (uint64_t)M::DEP_MASK, (EVERY > 0)>(rng, w, st);
-        }
+        constexpr int EVERY = functor_reorder<M>::value;
+        if (EVERY > 0 ? (k % (EVERY > 0 ? EVERY : 1) == 0) : (k == 0)) reorder_draws<M::NDRAW, (uint64_t)M::DEP_MASK>(w);
+        if constexpr (LEGACY) sample_worklist_walk<M::NDRAW, (uint64_t)M::DEP_MASK>(wrng, w, st);
+        else sample_worklist_defer<M::NDRAW, (uint64_t)M::DEP_MASK>(rng, w, st);
         M::apply(y, w);
         if (ALIGNED) {
             if (--until_out == 0) {

@@ -48,9 +48,7 @@ struct ElementRng {
     }
 };
 
-__host__ __device__ __forceinline__ float u01f(uint32_t w) {                 // (0, 1), 24 bits
-    return (float)(w >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;
-}
+__host__ __device__ __forceinline__ float u01f(uint32_t w) { return u01(w); }   // [2^-26, 1 - 2^-24], 24 bits (philox.cuh)
 
 // Two standard normal variates from two words (Box-Muller, both outputs).  The radius takes 32 bits of `wr`, the angle
 // 24 bits of `wa`; should `wr` be 0 the tail would stop at 6.7 sigma, so the low bits of `wa` extend it (to 8.2 sigma).
@@ -110,7 +108,9 @@ __host__ __device__ inline double sample_poisson(ElementRng& rng, double lam, bo
         uint32_t wa = wu0, wb;
         if (!seeded) rng.pair(wa, wb);
         float f = fast_exp(-lf), u = u01f(wa), k = 0.0f;
-        while (u > f && k < 1024.0f) {
+        // the search ends at the latest where the pmf has dropped below the 2^-24 grid of u (far past the mode): round-off
+        // in the running difference can then no longer carry it to the cap (see binomial_inversion_word)
+        while (u > f && f > 1e-8f && k < 1024.0f) {
             u -= f;
             k += 1.0f;
             f *= fast_div(lf, k);

@@ -60,9 +60,11 @@ struct Philox4x32 {
     }
 };
 
-// 24-bit uniform strictly inside (0, 1)
+// 24-bit uniform strictly inside (0, 1): k 2^-24 + 2^-26 for k = 0 .. 2^24 - 1, i.e. [2^-26, 1 - 2^-24] after FP32
+// rounding (the offset survives only below 1/2, where it keeps the value off zero).  A half-step offset of 2^-25 would round
+// the top value to exactly 1.0f, on which a sequential-search inversion never terminates.
 __host__ __device__ __forceinline__ float u01(uint32_t x) {
-    return (float)(x >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f;
+    return (float)(x >> 8) * 5.9604644775390625e-8f + 1.490116119384765625e-8f;
 }
 
 }  // namespace sodm

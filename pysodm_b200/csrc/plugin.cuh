@@ -43,8 +43,8 @@ char* error_buffer() {
         const int rc = ::sodm::build_jump_launch_for(a, L, aligned, plugin_info());               \
         if (rc != SODM_OK) return rc;                                                             \
         if (a->n_traj == 0) return SODM_OK;                                                       \
-        if (a->compat & ::sodm::TUNE_COOPERATIVE)                                                 \
-            return ::sodm::fail(SODM_EUNSUPPORTED, "generated models use the per-lane walk sampler only"); \
+        if (a->compat & ::sodm::TUNE_LEGACY_WALK)                                                 \
+            return ::sodm::fail(SODM_EUNSUPPORTED, "generated models use the default sampler only"); \
         return ::sodm::launch_plugin_jump<M>(L, a->method, aligned, a->out_dtype, (cudaStream_t)a->stream); \
     }                                                                                             \
     extern "C" int sodm_plugin_ode_run(const sodm_ode_args*) {                                    \
@@ -181,7 +181,7 @@ static int launch_gen_warp(const OdeLaunch& L, int method, int dtype, cudaStream
 }
 
 // A generated model gets the kernels a front end can ask for -- int32 output on the aligned grid, FP64 otherwise, SSA in
-// FP64 -- with the default (walk) sampler: a third of the instantiations of a built-in model, ~15 s of nvcc.
+// FP64 -- with the default sampler: a third of the instantiations of a built-in model, ~15 s of nvcc.
 template <class M>
 static int launch_plugin_jump(const JumpLaunch& L0, int method, bool aligned, int dtype, cudaStream_t stream) {
     JumpLaunch L = L0;
@@ -191,8 +191,7 @@ static int launch_plugin_jump(const JumpLaunch& L0, int method, bool aligned, in
         if (dtype != SODM_F64) return fail(SODM_EUNSUPPORTED, "generated models write SSA output as float64");
         ssa_kernel<M, double><<<grid, JUMP_BLOCK, 0, stream>>>(L);
     } else {
-        const size_t smem = ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)order_words<M>() +
-                             (size_t)L.n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
+        const size_t smem = tau_leap_smem<M>(L.n_tdpf_values);
         void (*kernel)(JumpLaunch) = nullptr;
         if (aligned && dtype == SODM_I32) kernel = tau_leap_kernel<M, int32_t, true, false>;
         else if (aligned && dtype == SODM_F64) kernel = tau_leap_kernel<M, double, true, false>;

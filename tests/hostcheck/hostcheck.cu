@@ -21,17 +21,14 @@ static void run_host(const JumpLaunch& L, int method, bool aligned) {
     for (int64_t i = 0; i < L.n_traj; ++i) {
         int wn[M::NDRAW];
         float wp[M::NDRAW];
-        uint16_t qm[M::NDRAW], qs[COOP_QS_CAP], qx[COOP_QX_CAP];
-        uint32_t qsu[COOP_QS_CAP], qsv[COOP_QS_CAP], qxk[COOP_QX_CAP];
-        float qxl[COOP_QX_CAP];
         uint8_t ord[M::NDRAW];
-        WorkList w{wn, wp, qm, qs, qsu, qsv, qx, qxk, qxl, ord, 1, 0, 1u};
+        WorkList w{wn, wp, ord, 1, 0, 1u};
         if (method == SODM_JUMP_TAU_LEAP) {
-            const bool walk = (L.compat & TUNE_COOPERATIVE) != 0u;   // template flag = cooperative sampler
-            if (aligned) { if (walk) tau_leap_trajectory<M, OutT, true, true>(L, i, true, table.data(), w);
-                           else      tau_leap_trajectory<M, OutT, true, false>(L, i, true, table.data(), w); }
-            else         { if (walk) tau_leap_trajectory<M, OutT, false, true>(L, i, true, table.data(), w);
-                           else      tau_leap_trajectory<M, OutT, false, false>(L, i, true, table.data(), w); }
+            const bool legacy = (L.compat & TUNE_LEGACY_WALK) != 0u;
+            if (aligned) { if (legacy) tau_leap_trajectory<M, OutT, true, true>(L, i, true, table.data(), w);
+                           else        tau_leap_trajectory<M, OutT, true, false>(L, i, true, table.data(), w); }
+            else         { if (legacy) tau_leap_trajectory<M, OutT, false, true>(L, i, true, table.data(), w);
+                           else        tau_leap_trajectory<M, OutT, false, false>(L, i, true, table.data(), w); }
         } else {
             ssa_trajectory<M, OutT>(L, i);
         }
@@ -70,6 +67,36 @@ extern "C" void hc_binomial(uint64_t seed, uint64_t traj, int32_t n, float p, in
     for (int64_t c = 0; c < count; ++c) {
         int k = 0;
         do { ++tries; } while (!binomial_try(rng, n, p, k));
+        out[c] = k;
+    }
+    if (attempts) attempts[0] = tries;
+}
+
+// The single-word stages of the deferred-test walk (btrs_candidate_word / btrs_settle / binomial_inversion_word) applied to
+// ONE draw at a time: one word per attempt, a second word when the candidate has to be settled by the exact test.
+// `force_word` != 0 replaces the FIRST word (edge cases: all-ones word -> u01 at its top end).
+extern "C" void hc_binomial_words(uint64_t seed, uint64_t traj, int32_t n, float p, int64_t count, int32_t* out,
+                                  int64_t* attempts, uint32_t force_word) {
+    PhiloxWords rng;
+    rng.init(seed, traj);
+    int64_t tries = 0;
+    for (int64_t c = 0; c < count; ++c) {
+        int k = 0;
+        int state = binomial_classify(n, p, k);
+        const bool flip = p > 0.5f;
+        const float pp = flip ? 1.0f - p : p;
+        while (state != BIN_DONE) {
+            ++tries;
+            uint32_t w = rng.next();
+            if (force_word && c == 0 && tries == 1) w = force_word;
+            if (state == BIN_INVERT) { k = binomial_inversion_word(n, pp, w); state = BIN_DONE; }
+            else {
+                state = btrs_candidate_word(n, pp, w, k);
+                if (state != BIN_DONE && btrs_settle(n, pp, k, w, rng.next())) state = BIN_DONE;
+                else if (state != BIN_DONE) state = BIN_BTRS;
+            }
+            if (state == BIN_DONE) k = flip ? n - k : k;
+        }
         out[c] = k;
     }
     if (attempts) attempts[0] = tries;

@@ -27,6 +27,8 @@ def lib():
         _lib.hc_jump_run.argtypes = [C.POINTER(_ffi.JumpArgs)]
         _lib.hc_binomial.restype = None
         _lib.hc_binomial.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_float, C.c_int64, C.c_void_p, C.c_void_p]
+        _lib.hc_binomial_words.restype = None
+        _lib.hc_binomial_words.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint32]
         _lib.hc_philox.restype = None
         _lib.hc_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int64, C.c_void_p]
         _lib.hc_binomial_log_ratio.restype = C.c_double
@@ -45,6 +47,14 @@ def binomial(n, p, count, seed=1, traj=0):
     out = np.empty(count, dtype=np.int32)
     attempts = np.zeros(1, dtype=np.int64)
     lib().hc_binomial(seed, traj, int(n), float(p), count, out.ctypes.data, attempts.ctypes.data)
+    return out, int(attempts[0])
+
+
+def binomial_words(n, p, count, seed=1, traj=0, force_word=0):
+    """The single-word sampler stages of the deferred-test walk, one draw at a time."""
+    out = np.empty(count, dtype=np.int32)
+    attempts = np.zeros(1, dtype=np.int64)
+    lib().hc_binomial_words(seed, traj, int(n), float(p), count, out.ctypes.data, attempts.ctypes.data, int(force_word))
     return out, int(attempts[0])
 
 

@@ -44,6 +44,46 @@ def test_binomial_sampler_is_exact(n, p):
     assert attempts / len(x) < 1.6
 
 
+@pytest.mark.parametrize("n,p", [(7317774, 1.2e-3), (4292, 0.28), (100, 0.3), (50, 0.5), (30, 0.4), (1000, 0.005),
+                                 (7317774, 1e-7), (81, 0.13), (5, 0.9), (2130556, 0.02), (40, 0.26), (12, 0.97),
+                                 (200000, 0.5), (1, 0.3), (20, 0.5), (1000000, 0.9999),
+                                 # modes in the FP32 / FP64 hand-over band of the exact test (0.9 * 8192 .. 8192), n >= 2^24,
+                                 # and deep inside the FP64 branch
+                                 (7317774, 1.02e-3), (7317774, 1.1e-3), (2130556, 3.8e-3), (20000000, 4.0e-4),
+                                 (16777216, 0.25), (50000000, 0.5), (7317774, 0.3)])
+def test_single_word_sampler_is_exact(n, p):
+    """The default sampler's stages (one word per attempt, 8-bit box test, deferred exact test): chi-square against the
+    exact pmf."""
+    x, attempts = hc.binomial_words(n, p, 300_000, seed=n % 89 + 3)
+    p32 = float(np.float32(p))
+    lo, hi = int(x.min()), int(x.max())
+    assert 0 <= lo and hi <= n
+    ks = np.arange(lo, hi + 1)
+    obs = np.bincount(x - lo, minlength=len(ks)).astype(float)
+    exp = stats.binom.pmf(ks, n, p32) * len(x)
+    big = exp >= 8
+    o = np.append(obs[big], obs[~big].sum())
+    e = np.append(exp[big], len(x) - exp[big].sum())
+    if e[-1] < 4:
+        o, e = o[:-1], e[:-1]
+    if len(o) > 1:
+        chi2 = ((o - e) ** 2 / e).sum()
+        assert stats.chi2.sf(chi2, len(o) - 1) > 1e-4, (n, p)
+    assert attempts / len(x) < 1.6
+
+
+def test_uniform_stays_inside_the_unit_interval():
+    """a word of all ones must not map to u = 1.0f, on which sequential inversion runs to its cap."""
+    for n, p in [(2000, 0.004), (50, 0.02), (7317774, 1e-6)]:
+        x, _ = hc.binomial_words(n, p, 1, force_word=0xFFFFFFFF)
+        assert x[0] < stats.binom.isf(1e-9, n, p) + 2, (n, p, x[0])
+        x, _ = hc.binomial_words(n, p, 1, force_word=0xFFFFFF00)
+        assert x[0] < stats.binom.isf(1e-9, n, p) + 2, (n, p, x[0])
+    # Poisson noise below the inversion threshold has the same search loop
+    out, _ = hc.noise(0, 0.0, 7.5, 200000, seed=3)
+    assert out.max() < 40
+
+
 def test_binomial_edge_cases():
     assert (hc.binomial(0, 0.3, 100)[0] == 0).all()
     assert (hc.binomial(50, 0.0, 100)[0] == 0).all()
