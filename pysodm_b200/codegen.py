@@ -857,7 +857,6 @@ extern "C" void sodm_plugin_host_rhs(double t, const double* y, const double* pa
     return src, n_state, n_param
 
 
-REORDER_EVERY = 1 << 30      # draws sorted by ascending mean once, at the start of the trajectory (see jump_run.cuh)
 
 
 def jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes, tdpf_params=(), origin="",
@@ -1008,7 +1007,6 @@ struct GenModel {{
     static constexpr int NDRAW = {n_draw};
     static constexpr uint64_t DEP_MASK = {dep_mask}ull;
     static constexpr bool USES_TIME = {'true' if uses_time else 'false'};
-    static constexpr int REORDER_EVERY = {REORDER_EVERY if n_draw > 2 else 0};   // draws re-sorted by ascending mean (jump_run.cuh)
     struct Pre {{ float par[{npar_arr}]; float p[{max(len(hoisted), 1)}]; }};
     __host__ __device__ static Pre prepare(const double* par, float tau, bool) {{
         Pre pre;

@@ -152,6 +152,44 @@ double binomial_log_ratio(double nd, double pd, double m, double kd) {
          - stirling_tail(kd) - stirling_tail(nd - kd);
 }
 
+// ---- the same ratio for LARGE modes (>= SODM_F32_MODE_LIMIT) in FP64 multiply-adds only ---------------------------------
+// With a = n - m + 1, b = n - k + 1, x = k - m and N1 = (m + 1) - p (n + 2) (a number in (-p, 1 - p], computed without
+// cancellation trouble in FP64) the three logarithms of binomial_log_ratio are
+//     log((m+1) / (r a)) = log1p(N1 / (p a)),    log(a / b) = log1p(x / b),    log(r b / (k+1)) = log1p(-(N1 + x) / (q (k+1))),
+// all of arguments of size x / (n p q) <= 4 / sigma: log1p(N / D) = 2 atanh(N / (2 D + N)) needs ONE reciprocal (FP32 seed + two
+// Newton steps) and four series terms.  The Stirling tails reduce to x / 12 (1 / ((m+1)(k+1)) - 1 / (a b)) (next terms < 1e-11).
+// ~60 instructions instead of three FP64 logarithms and twelve FP64 divisions (~1000): the FP64 branch ran at 1.1 of 32 lanes
+// and cost 4 % of the kernel (profiles/r1_mufu_tau_leap_ncu_full.txt).  Valid for |x| <= 0.05 min(b, q (k+1)); callers fall
+// back to binomial_log_ratio outside (far tails, never seen in practice).
+__host__ __device__ __forceinline__ double rcp_newton(double d) {          // d > 0, normal in FP32 range
+#ifdef __CUDA_ARCH__
+    float seed;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"((float)d));
+    double r = (double)seed;
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / d;
+#endif
+}
+__host__ __device__ __forceinline__ double log1p_ratio(double num, double den) {      // log(1 + num / den), |num / den| <= 0.06
+    const double s = num * rcp_newton(2.0 * den + num);
+    const double s2 = s * s;
+    return 2.0 * s * fma(s2, fma(s2, fma(s2, fma(s2, 1.0 / 9.0, 1.0 / 7.0), 0.2), 1.0 / 3.0), 1.0);
+}
+__host__ __device__ __forceinline__ bool binomial_log_ratio_large(double nd, double pd, double m, double kd, double& out) {
+    const double x = kd - m, q = 1.0 - pd;
+    const double a = nd - m + 1.0, b = nd - kd + 1.0;
+    const double n1 = (m + 1.0) - pd * (nd + 2.0);
+    const double d3 = q * (kd + 1.0);
+    if (!(fabs(x) <= 0.05 * b && fabs(n1 + x) <= 0.05 * d3 && kd >= 0.0)) return false;
+    const double tails = x * (1.0 / 12.0) * (rcp_newton((m + 1.0) * (kd + 1.0)) - rcp_newton(a * b));
+    out = (m + 0.5) * log1p_ratio(n1, pd * a) + (nd + 1.0) * log1p_ratio(x, b) + (kd + 0.5) * log1p_ratio(-(n1 + x), d3) + tails;
+    return true;
+}
+
 __host__ __device__ __forceinline__ float stirling_tail_f(float k) {
     // series in 1/(k+1); its error is 3e-6 at k = 1 and smaller beyond, so only k = 0 needs the tabulated value
     // (a per-lane table lookup would serialise in the constant cache)
@@ -248,7 +286,6 @@ __host__ __device__ __forceinline__ int btrs_candidate(int n, float p, uint32_t 
     const float stddev = fast_sqrt(np_ * (1.0f - p));
     const float b = 1.15f + 2.53f * stddev;
     const float a = -0.0873f + 0.0248f * b + 0.01f * p;
-    const float v_r = 0.92f - fast_div(4.2f, b);
     const float u = u01(wu) - 0.5f;
     const float v = u01(wv);
     const float us = 0.5f - fabsf(u);
@@ -259,7 +296,8 @@ __host__ __device__ __forceinline__ int btrs_candidate(int n, float p, uint32_t 
         const double kd = floor(fma((double)(2.0f * a / us + b), (double)u, fma((double)n, (double)p, 0.5)));
         k = (int)fmin(fmax(kd, -1.0), 2147483647.0);
     }
-    if (us >= 0.07f && v <= v_r) return BIN_DONE;
+    // v <= v_r = 0.92 - 4.2 / b   <=>   (0.92 - v) b >= 4.2   (b > 0): no reciprocal
+    if (us >= 0.07f && (0.92f - v) * b >= 4.2f) return BIN_DONE;
     if (k < 0 || k > n) return BIN_RETRY;
     return BIN_SQUEEZE;
 }
@@ -311,62 +349,58 @@ bool btrs_exact_accept(int n, float p, int k, float lhs) {
     const float nf = (float)n;
     const float mf = floorf((nf + 1.0f) * p);
     if (mf < SODM_F32_MODE_LIMIT && nf < 16777216.0f) return lhs <= binomial_log_ratio_f32(nf, p, mf, (float)k);
-    const double nd = (double)n, pd = (double)p;
-    return (double)lhs <= binomial_log_ratio(nd, pd, floor((nd + 1.0) * pd), (double)k);
+    const double nd = (double)n, pd = (double)p, md = floor((nd + 1.0) * pd);
+    double ratio;
+    if (md >= SODM_F32_MODE_LIMIT && binomial_log_ratio_large(nd, pd, md, (double)k, ratio)) return (double)lhs <= ratio;
+    return (double)lhs <= binomial_log_ratio(nd, pd, md, (double)k);
 }
 
 #ifndef SODM_DIRECT_EXACT
 #define SODM_DIRECT_EXACT 1              // 0: squeeze in front of every exact test (tuning builds)
 #endif
+#ifndef SODM_SQUEEZE_LARGE
+#define SODM_SQUEEZE_LARGE 1             // 0: large modes go to their (FP64 multiply-add) ratio without the squeeze (tuning builds)
+#endif
 
-// ------------------------------------------------------------------------------------------------
-// Single-word BTRS stages for the deferred-test walk (jump_run.cuh, sample_worklist_defer).
-//   btrs_candidate_word : candidate k from ONE word: its top 24 bits give u, its low 8 bits the leading 8 bits of v.  The
-//                         box test of BTRS step 1 (us >= 0.07 and v <= v_r) is decided from those 8 bits whenever
-//                         (v8 + 1)/256 <= v_r, i.e. v <= v_r whatever the remaining bits are -> BIN_DONE (69 % of attempts
-//                         on influenza).  Everything else -> BIN_EXACT: the candidate waits for btrs_settle.
-//   btrs_settle         : completes v = (v8 + u01(second word)) / 256 and applies the exact acceptance test of step 3
-//                         (log(v alpha / (a/us^2 + b)) <= log f(k)/f(m)).  The box of step 1 lies inside the acceptance
-//                         region of step 3, so testing a candidate the 8-bit box test could not decide this way is the
-//                         same algorithm; k outside 0..n (step 2) is rejected here as well.
-// The first word is kept with the candidate, so the hat quantities are recomputed rather than stored.
-// ------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ int btrs_candidate_word(int n, float p, uint32_t w, int& k) {
-    const float nf = (float)n;
-    const float np_ = nf * p;
-    const float stddev = fast_sqrt(np_ * (1.0f - p));
-    const float b = 1.15f + 2.53f * stddev;
-    const float a = -0.0873f + 0.0248f * b + 0.01f * p;
-    const float u = u01(w) - 0.5f;
-    const float us = 0.5f - fabsf(u);
-    if (np_ < 4194304.0f) {
-        k = (int)floorf(fmaf(fast_div(2.0f * a, us) + b, u, np_ + 0.5f));
+// ONE attempt at Bin(n, p), 0 <= p <= 1, from the two words (wu, wv) -- the unit of work of the two-pass sampler
+// (jump_run.cuh, sample_worklist_2pass):
+//   BIN_DONE   k is final (trivial case, sequential inversion, or an accepted BTRS candidate); k = -1: invalid (n, p)
+//   BIN_RETRY  the candidate was rejected: attempt again with fresh words
+//   BIN_EXACT  (only when !WITH_EXACT) neither the box test nor the squeeze settled the candidate; it takes the exact
+//              log-pmf ratio, which the caller postpones: running THE SAME attempt again with WITH_EXACT = true recreates the
+//              candidate from the same words and settles it.
+// The squeeze (BTPE step 5.2 in FP32) is skipped for n >= 2^24, where FP32 no longer holds k - mode exactly; such draws go
+// to the FP64 ratio directly.
+#ifndef SODM_ATTEMPT_SQUEEZE
+#define SODM_ATTEMPT_SQUEEZE 0           // 1: squeeze in front of the FP32 exact test too (tuning builds)
+#endif
+template <bool WITH_EXACT>
+__host__ __device__ __forceinline__ int binomial_attempt(int n, float p, uint32_t wu, uint32_t wv, int& k) {
+    int state = binomial_classify(n, p, k);
+    if (state == BIN_DONE) return BIN_DONE;
+    const bool flip = p > 0.5f;
+    const float pp = flip ? 1.0f - p : p;
+    int kk;
+    if (state == BIN_INVERT) {
+        kk = binomial_inversion_word(n, pp, wu);
     } else {
-        const double kd = floor(fma((double)(2.0f * a / us + b), (double)u, fma((double)n, (double)p, 0.5)));
-        k = (int)fmin(fmax(kd, -1.0), 2147483647.0);
+        BtrsHat hat;
+        state = btrs_candidate(n, pp, wu, wv, kk, hat);
+        if (state == BIN_SQUEEZE) {
+            float lhs;
+            // the squeeze pays where the exact test is the FP64 routine (large modes: it settles 98 % there); in front of the
+            // FP32 ratio it mostly adds instructions, because some lane of the warp needs the ratio anyway
+            if (n < 16777216 && (SODM_ATTEMPT_SQUEEZE || (float)n * pp >= 0.9f * SODM_F32_MODE_LIMIT)) state = btrs_squeeze(n, pp, kk, hat, lhs);
+            else { lhs = btrs_lhs(hat); state = BIN_EXACT; }
+            if (state == BIN_EXACT) {
+                if (!WITH_EXACT) return BIN_EXACT;
+                state = btrs_exact_accept(n, pp, kk, lhs) ? BIN_DONE : BIN_RETRY;
+            }
+        }
+        if (state == BIN_RETRY) return BIN_RETRY;
     }
-    const float v_hi = (float)((w & 255u) + 1u) * 0.00390625f;          // upper end of the 8-bit cell of v
-    // v <= v_r = 0.92 - 4.2 / b   <=>   (0.92 - v) b >= 4.2   (b > 0): no reciprocal
-    return (us >= 0.07f && (0.92f - v_hi) * b >= 4.2f) ? BIN_DONE : BIN_EXACT;
-}
-
-__host__ __device__ __forceinline__ bool btrs_settle(int n, float p, int k, uint32_t wu, uint32_t wv) {
-    if (k < 0 || k > n) return false;
-    const float nf = (float)n;
-    BtrsHat h;
-    h.stddev = fast_sqrt(nf * p * (1.0f - p));
-    h.b = 1.15f + 2.53f * h.stddev;
-    h.a = -0.0873f + 0.0248f * h.b + 0.01f * p;
-    h.us = 0.5f - fabsf(u01(wu) - 0.5f);
-    h.v = ((float)(wu & 255u) + u01(wv)) * 0.00390625f;
-    float lhs;
-    if (SODM_DIRECT_EXACT && nf * p < 0.9f * SODM_F32_MODE_LIMIT) {
-        lhs = btrs_lhs(h);
-    } else {
-        const int state = btrs_squeeze(n, p, k, h, lhs);
-        if (state != BIN_EXACT) return state == BIN_DONE;
-    }
-    return btrs_exact_accept(n, p, k, lhs);
+    k = flip ? n - kk : kk;
+    return BIN_DONE;
 }
 
 // One complete BTRS attempt of a single lane (per-lane walk); requires 0 < p <= 0.5 and n*p >= 10.
@@ -404,8 +438,8 @@ __host__ __device__ __forceinline__ bool binomial_try_words(int n, float p, uint
         if (state == BIN_RETRY) done = false;
         else if (state == BIN_SQUEEZE) {
             float lhs = 0.0f;
-            if (SODM_DIRECT_EXACT && (float)n * pp < 0.9f * SODM_F32_MODE_LIMIT) {
-                lhs = btrs_lhs(hat);
+            if ((SODM_DIRECT_EXACT && (float)n * pp < 0.9f * SODM_F32_MODE_LIMIT) || (!SODM_SQUEEZE_LARGE && n < 16777216) || n >= 16777216) {
+                lhs = btrs_lhs(hat);           // (n >= 2^24: FP32 no longer holds k - mode exactly, the squeeze's bounds would not hold)
                 state = BIN_EXACT;
             } else {
                 state = btrs_squeeze(n, pp, kk, hat, lhs);

@@ -25,24 +25,24 @@ template <class M>
 __host__ __device__ constexpr int order_words() { return (M::NDRAW * JUMP_BLOCK + 3) / 4; }
 
 // bytes of dynamic shared memory of a tau-leap block: [NDRAW][JUMP_BLOCK] draw counts | [NDRAW][JUMP_BLOCK] probabilities |
-// [NDRAW][JUMP_BLOCK] draw order (bytes) | TDPF table (FP32)
+// TDPF table (FP32) | walk sampler only: [NDRAW][JUMP_BLOCK] draw order (bytes)
 template <class M>
-static size_t tau_leap_smem(int n_tdpf_values) {
-    return ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)order_words<M>() + (size_t)n_tdpf_values * M::TDPF_COUNT) * sizeof(float);
+static size_t tau_leap_smem(int n_tdpf_values, bool two_pass = false) {
+    return ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)n_tdpf_values * M::TDPF_COUNT + (two_pass ? 0 : (size_t)order_words<M>())) * sizeof(float);
 }
 
-template <class M, typename OutT, bool ALIGNED, bool LEGACY>
+template <class M, typename OutT, bool ALIGNED, bool TWO_PASS>
 __global__ void __launch_bounds__(JUMP_BLOCK, SODM_WALK_MIN_BLOCKS) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WorkList w;
     w.n = reinterpret_cast<int*>(smem) + warp * 32;
     w.p = smem + M::NDRAW * JUMP_BLOCK + warp * 32;
-    w.ord = reinterpret_cast<uint8_t*>(smem + 2 * M::NDRAW * JUMP_BLOCK) + warp * 32;
     w.stride = JUMP_BLOCK;
     w.lane = lane;
-    float* table = smem + 2 * M::NDRAW * JUMP_BLOCK + order_words<M>();
+    float* table = smem + 2 * M::NDRAW * JUMP_BLOCK;
     const int n_tab = L.n_tdpf_values * M::TDPF_COUNT;
+    w.ord = TWO_PASS ? nullptr : reinterpret_cast<uint8_t*>(table + n_tab) + warp * 32;
     for (int e = threadIdx.x; e < n_tab; e += blockDim.x) table[e] = (float)L.tdpf_table[e];   // ABI speaks FP64, rates are FP32
     __syncthreads();
     // small ensembles leave warp slots idle: spreading the trajectories over more warps (32 >> lane_shift per warp) shortens
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(JUMP_BLOCK, SODM_WALK_MIN_BLOCKS) tau_leap_ker
     const bool active = lane < lanes_used && i < L.n_traj;
     w.lanes = __ballot_sync(0xffffffffu, active);
     if (w.lanes == 0u) return;                                    // whole warp past the end
-    tau_leap_trajectory<M, OutT, ALIGNED, LEGACY>(L, i, active, table, w);
+    tau_leap_trajectory<M, OutT, ALIGNED, TWO_PASS>(L, i, active, table, w);
 }
 
 template <class M, typename OutT>
@@ -90,13 +90,13 @@ static unsigned spread_grid(int64_t n_traj, int lane_shift) {
 template <class M, typename OutT>
 static int launch_jump(const JumpLaunch& L0, int method, bool aligned, cudaStream_t stream) {
     JumpLaunch L = L0;
-    const bool legacy = (L.compat & TUNE_LEGACY_WALK) != 0u;
+    const bool two_pass = (L.compat & TUNE_TWO_PASS) != 0u;
     L.lane_shift = method == SODM_JUMP_TAU_LEAP ? pick_lane_shift(L.n_traj) : 0;
     const unsigned grid = spread_grid(L.n_traj, L.lane_shift);
     if (method == SODM_JUMP_TAU_LEAP) {
-        const size_t smem = tau_leap_smem<M>(L.n_tdpf_values);
-        void (*kernel)(JumpLaunch) = aligned ? (legacy ? tau_leap_kernel<M, OutT, true, true> : tau_leap_kernel<M, OutT, true, false>)
-                                             : (legacy ? tau_leap_kernel<M, OutT, false, true> : tau_leap_kernel<M, OutT, false, false>);
+        const size_t smem = tau_leap_smem<M>(L.n_tdpf_values, two_pass);
+        void (*kernel)(JumpLaunch) = aligned ? (two_pass ? tau_leap_kernel<M, OutT, true, true> : tau_leap_kernel<M, OutT, true, false>)
+                                             : (two_pass ? tau_leap_kernel<M, OutT, false, true> : tau_leap_kernel<M, OutT, false, false>);
         SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         kernel<<<grid, JUMP_BLOCK, smem, stream>>>(L);
     } else {

@@ -19,7 +19,7 @@ namespace sodm {
 constexpr int MAX_PARAM = 64;   // flat parameter elements passed by value
 constexpr int MAX_STATE = 64;   // flat state elements of a jump model
 
-enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, TUNE_LEGACY_WALK = 256u };
+enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, TUNE_TWO_PASS = 256u };
 
 struct JumpLaunch {
     int64_t n_traj;            // trajectories in this launch
@@ -132,35 +132,53 @@ inline int low_bit(uint32_t m) { return __builtin_ctz(m); }
 inline int low_bit(uint64_t m) { return __builtin_ctzll(m); }
 #endif
 
-// Draw order of a lane (position -> slot), set once from the lane's OWN first-step means (a trajectory's result must not
-// depend on its warp neighbours): independent slots by ascending mean n min(p, 1 - p), then the slots that are conditional
-// on another one (bit d of DEP_MASK: slot d's n is what slot d-1 left behind), so that by the time a lane reaches them
-// their predecessors are settled.  The ORDER changes nothing in the law; it decides how well the lanes of a warp share
-// code paths: trajectories of one ensemble resemble each other, so with a common ordering rule the small-mean draws
-// (sequential inversion) of all lanes meet in the first trips of a step and the large-mean draws (BTRS) in the rest,
-// whichever lane has fallen behind by a few attempts (measured in round 1 on the per-lane walk: declaration order 137 ms,
-// sorted once 126 ms per 10^6 influenza trajectories; re-sorting often is worse because the lanes' orders drift apart).
-// A functor may declare `static constexpr int REORDER_EVERY = K` to re-sort every K steps.  Rank sort, NDRAW^2 compares.
-template <class M, class = void> struct functor_reorder { static constexpr int value = 0; };
-template <class M> struct functor_reorder<M, decltype((void)M::REORDER_EVERY)> { static constexpr int value = M::REORDER_EVERY; };
+// PER-LANE WALK: draw order.  A lane takes its draws in an order (position -> slot, `ord`) set once from its OWN first-step
+// means (a trajectory's result must not depend on its warp neighbours).  The ORDER changes nothing in the law; it decides how
+// well the lanes of a warp share code paths: trajectories of one ensemble resemble each other, so with a common ordering
+// rule the small-mean draws (sequential inversion) of all lanes meet in the first trips of a step and the large-mean draws
+// (BTRS) in the rest, whichever lane has fallen behind by a few attempts (round 1, influenza: declaration order 137 ms,
+// sorted once at the first step 125.6 ms, re-sorted every 16 steps 129 ms per 10^6 trajectories -- the lanes' orders drift
+// apart when re-sorted often).  Every model uses this generic rule; round 1's hand-tuned table for influenza (125.8 ms) was
+// fitted to the benchmark's own trajectory and is gone.
+// Units of the draw list: a slot together with the slots conditional on it (bit d of DEP_MASK: d belongs to the unit of d-1).
+template <int NDRAW, uint64_t DEP_MASK>
+struct DrawUnits {
+    int n_units = 0;
+    int first[NDRAW] = {};
+    int size[NDRAW] = {};
+    constexpr DrawUnits() {
+        for (int d = 0; d < NDRAW; ++d) {
+            if ((DEP_MASK >> d) & 1ull) ++size[n_units - 1];
+            else { first[n_units] = d; size[n_units] = 1; ++n_units; }
+        }
+    }
+};
 
+// Re-sort this lane's draw order by ascending current mean n min(p, 1 - p) of each unit's first slot.  The ORDER changes
+// nothing in the law; it decides how well the lanes of a warp share code paths: lanes start a step together and drift
+// apart, so cheap small-mean draws (of mixed regime) go first and the large-mean BTRS draws last, where drifted lanes
+// still execute the same instructions (measured on influenza, static orders: 137 -> 126 ms per 10^6 trajectories,
+// profiles/r1_sampler_ab.txt).  Sorting by the lane's OWN state keeps a trajectory independent of its warp neighbours
+// (results do not depend on sharding or chunking).  Branch-free rank sort: NU^2 compares per re-sort.
 template <int NDRAW, uint64_t DEP_MASK>
 __host__ __device__ __forceinline__ void reorder_draws(WorkList& w) {
+    constexpr DrawUnits<NDRAW, DEP_MASK> U{};
     const int S = w.stride, lane = w.lane;
     float key[NDRAW];
 #pragma unroll
-    for (int d = 0; d < NDRAW; ++d) {
-        const float p = w.p[d * S + lane];
-        const float k = (float)w.n[d * S + lane] * fminf(p, 1.0f - p);
-        key[d] = ((DEP_MASK >> d) & 1ull) ? 3.0e38f : (k == k ? k : 0.0f);     // NaN probabilities are flagged by the sampler; keep a total order
+    for (int u = 0; u < U.n_units; ++u) {
+        const float p = w.p[U.first[u] * S + lane];
+        const float k = (float)w.n[U.first[u] * S + lane] * fminf(p, 1.0f - p);
+        key[u] = k == k ? k : 0.0f;                              // NaN probabilities are flagged by the sampler; keep a total order
     }
 #pragma unroll
-    for (int d = 0; d < NDRAW; ++d) {
+    for (int u = 0; u < U.n_units; ++u) {
         int pos = 0;
 #pragma unroll
-        for (int e = 0; e < NDRAW; ++e)
-            if (e != d) pos += (key[e] < key[d] || (key[e] == key[d] && e < d)) ? 1 : 0;
-        w.ord[pos * S + lane] = (uint8_t)d;
+        for (int v = 0; v < U.n_units; ++v)
+            if (v != u) pos += (key[v] < key[u] || (key[v] == key[u] && v < u)) ? U.size[v] : 0;
+#pragma unroll
+        for (int e = 0; e < U.size[u]; ++e) w.ord[(pos + e) * S + lane] = (uint8_t)(U.first[u] + e);
     }
 }
 
@@ -176,147 +194,129 @@ __host__ __device__ __forceinline__ int chain_taken(const WorkList& w, int d) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// DEFERRED-TEST WALK (default sampler).
+// TWO-PASS SAMPLER (opt-in: SODM_TUNE_TWO_PASS; same law, different random streams).
 //
-// In a divergent SIMT loop the warp pays (trips) x (union of the branches any lane takes).  The per-lane walk of round 1
-// (kept below as the legacy schedule) ran the exact acceptance test of a BTRS candidate right where the box test failed:
-// one attempt in three needs it, so SOME lane of 32 needed it on almost every trip and the warp executed the ~130
-// instructions of the test at 8 of 32 lanes, next to inversion at 6 lanes -- 17.4 of 32 lanes per instruction overall
-// (profiles/r1_mufu_tau_leap_ncu_full.txt).  Here a trip has ONE body for the whole warp:
-//   C trip  every lane that still has a draw to do takes the next one in its order and makes ONE attempt from ONE random
-//           word: trivial cases and small means (sequential inversion) finish at once; a BTRS candidate that passes the box
-//           test (decided from the 8 low bits of the same word) is final; any other candidate is PARKED in registers (its k,
-//           its word, its position; up to DEFER_SLOTS of them) and the lane moves on to its next draw -- the draws of a step
-//           are independent of each other except for the few conditional ones, which sit last in the order.
-//   X trip  every lane that has parked candidates settles the newest one: second word -> full-resolution v -> exact
-//           acceptance test (btrs_settle).  Accepted: the count is final.  Rejected: the draw's position returns to the
-//           lane's to-do mask and is attempted again on a later C trip.
-// The warp votes (ballots) which of the two bodies the next trip runs: X when no lane can make progress otherwise, when
-// some lane's parking slots are full, or when at least DEFER_VOTE lanes have something parked.  Every trip consumes exactly
-// one word of every lane's Philox stream, used or not, so all lanes refill their 4-word block on the same trips.
-// Rejection sampling stays exact under any such schedule: each attempt uses words nobody has looked at before, and whether
-// an attempt is accepted depends on its own words only.
+// In a divergent SIMT loop the warp pays (trips) x (union of the branches any lane takes).  The per-lane walk below lets every
+// lane work through its own draw list, so with 32 lanes at different draws in different regimes the warp executes inversion
+// at 6 lanes, the exact test at 8 lanes and the BTRS candidate at 25 on almost every trip -- 17.4 of 32 lanes per instruction
+// (profiles/r1_mufu_tau_leap_ncu_full.txt).  This sampler attacks that with a uniform first pass:
+//   pass 1  ALL lanes make ONE attempt at draw d, for d = 0 .. NDRAW-1 in turn: every lane at the same draw, hence (the
+//           trajectories of an ensemble resemble each other) almost always in the same regime.  A rejected attempt sets bit d
+//           of the lane's `todo` mask; with SODM_PASS1_PARK an undecided candidate is parked instead of tested (bit d of `park`).
+//           A draw that is conditional on an unfinished one (DEP_MASK) is postponed (todo, marked by ~n).
+//   pass 2  the leftovers, a few per lane: each lane repeatedly takes its lowest open draw -- parked ones first -- and makes
+//           a full attempt including the exact test; a parked draw re-runs its pass-1 attempt from the same words, which
+//           recreates the candidate instead of storing it.  The warp leaves when no lane has an open draw.
+// Random words are COUNTER-BASED per attempt: Philox2x32-10 keyed by the launch, counter = (trajectory, step, draw, attempt
+// number), so what a lane draws does not depend on its warp neighbours, on the launch geometry or on the number of GPUs,
+// and nothing random is ever stored.  Rejection sampling stays exact under this schedule: every attempt uses words nobody
+// has looked at before, and whether it is accepted depends on its own words only.
+// MEASURED (B200, influenza, 2^20 trajectories, profiles/r2_sampler_ab.txt): 121.6 ms against 116.9 ms for the walk.  Lanes per
+// instruction rise (17 -> 21) but the instruction count does not fall: every pass-1 iteration still executes the union of
+// inversion + candidate + exact test (237 warp instructions per draw), and pass 2 runs for as many trips as the unluckiest
+// lane has leftovers (14.5 per step at 13 lanes).  Parking the exact test (SODM_PASS1_PARK) and a first version that deferred
+// parked candidates inside a walk (X trips voted by ballot) measured 136 / 129 ms.  What these schedules save in divergence
+// they pay in bookkeeping; the walk stays the default and this sampler stays as a second, independently written schedule
+// of the same law for the parity tests.
 // ------------------------------------------------------------------------------------------------------------------
-#ifndef SODM_DEFER_SLOTS
-#define SODM_DEFER_SLOTS 3
+#ifndef SODM_PASS1_UNROLL
+#define SODM_PASS1_UNROLL 2
 #endif
-#ifndef SODM_DEFER_VOTE
-#define SODM_DEFER_VOTE 24
+constexpr int PASS1_UNROLL = SODM_PASS1_UNROLL;
+#ifndef SODM_PASS1_PARK
+#define SODM_PASS1_PARK 0                // 1: pass 1 postpones the exact test (parks the candidate) instead of running it
 #endif
-constexpr int DEFER_SLOTS = SODM_DEFER_SLOTS;
-static_assert(DEFER_SLOTS >= 1 && DEFER_SLOTS <= 4, "1 to 4 parked candidates per lane");
 
-// One word per trip for every lane; the buffer position is the same on all lanes of a warp by construction.
-struct TripRng {
-    Philox4x32 gen;
-    uint32_t w0, w1, w2, w3;
-    int left;
-    __host__ __device__ __forceinline__ void init(uint64_t seed, uint64_t traj) {
-        gen.init(seed, traj);
-        w0 = w1 = w2 = w3 = 0u;
-        left = 0;
+// Coordinates of an attempt -> Philox2x32 counter.  c0 = low 32 bits of the global trajectory id; c1 = step (16 bits) |
+// draw (6) | attempt (6) | bits 32..35 of the trajectory id; steps beyond 2^16 move into the key (warp-uniform).
+struct AttemptKey {
+    uint32_t key;       // launch key (+ high bits of the step)
+    uint32_t c0;        // trajectory, low word
+    uint32_t c1;        // (step & 0xffff) << 16 | trajectory bits 32..35
+    __host__ __device__ __forceinline__ void set(uint64_t seed, uint64_t traj, uint32_t step) {
+        key = fold_seed(seed) + (step >> 16) * 0x9E3779B1u;
+        c0 = (uint32_t)traj;
+        c1 = (step << 16) | (uint32_t)((traj >> 32) & 15u);
     }
-    __host__ __device__ __forceinline__ uint32_t next() {
-        if (left == 0) {
-            uint32_t b[4];
-            gen.next4(b);
-            w0 = b[0]; w1 = b[1]; w2 = b[2]; w3 = b[3];
-            left = 4;
-        }
-        const uint32_t v = w0;
-        w0 = w1; w1 = w2; w2 = w3;
-        --left;
-        return v;
+    __host__ __device__ __forceinline__ void words(int d, uint32_t attempt, uint32_t& wu, uint32_t& wv) const {
+        philox2x32_10(key, c0, c1 | ((uint32_t)d << 10) | (attempt << 4), wu, wv);
     }
 };
+constexpr int64_t MAX_TRAJ_ID = (int64_t)1 << 36;
 
 template <int NDRAW> struct draw_mask { using type = typename std::conditional<(NDRAW <= 32), uint32_t, uint64_t>::type; };
 
 template <int NDRAW, uint64_t DEP_MASK>
-__host__ __device__ __forceinline__ void sample_worklist_defer(TripRng& rng, WorkList& w, uint32_t& st) {
+__host__ __device__ __forceinline__ void sample_worklist_2pass(const AttemptKey& key, WorkList& w, uint32_t& st) {
+    static_assert(NDRAW <= 64, "at most 64 draws per step");
     using Mask = typename draw_mask<NDRAW>::type;
     constexpr Mask ONE = 1;
-    constexpr Mask ALL = NDRAW == 8 * (int)sizeof(Mask) ? ~Mask(0) : (ONE << (NDRAW % (8 * (int)sizeof(Mask)))) - ONE;
     const int S = w.stride, lane = w.lane;
-    // a conditional draw carries ~n (negative) until its first attempt turns it into n - (what the earlier exits took)
-#pragma unroll
-    for (int d = 0; d < NDRAW; ++d)
-        if ((DEP_MASK >> d) & 1ull) w.n[d * S + lane] = ~w.n[d * S + lane];
-    Mask todo = ALL;            // POSITIONS (in the lane's order) still to be attempted
-    Mask open = ALL;            // SLOTS whose count is not final yet
-    int npend = 0;
-    int pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0;          // parked candidates, newest first: k, word, position (one byte each)
-    uint32_t pw0 = 0u, pw1 = 0u, pw2 = 0u, pw3 = 0u, ppos = 0u;
-    bool stalled = false;       // the lane's next draw waits for a parked predecessor
-    for (;;) {
-        const bool can = todo != 0 && npend < DEFER_SLOTS && !stalled;
-        const unsigned mc = coop_ballot(can), mp = coop_ballot(npend > 0);
-        if ((mc | mp) == 0u) break;
-        const uint32_t word = rng.next();
-        const bool settle = mp != 0u && (mc == 0u || coop_ballot(npend >= DEFER_SLOTS) != 0u || coop_popc(mp) >= SODM_DEFER_VOTE);
-        if (settle) {
-            // ---- X trip ------------------------------------------------------------------------------------------
-            if (npend > 0) {
-                const int pos = (int)(ppos & 255u);
-                const int d = (int)w.ord[pos * S + lane];
-                const int n = w.n[d * S + lane];
-                const float p = w.p[d * S + lane];
-                const bool flip = p > 0.5f;
-                if (btrs_settle(n, flip ? 1.0f - p : p, pk0, pw0, word)) {
-                    w.n[d * S + lane] = flip ? n - pk0 : pk0;
-                    open &= ~(ONE << d);
-                } else {
-                    todo |= ONE << pos;
-                }
-                pk0 = pk1; pk1 = pk2; pk2 = pk3;
-                pw0 = pw1; pw1 = pw2; pw2 = pw3;
-                ppos >>= 8;
-                --npend;
+    Mask todo = 0, park = 0;
+    // ---- pass 1: one attempt per draw, all lanes at the same draw -------------------------------------------------------
+#pragma unroll PASS1_UNROLL
+    for (int d = 0; d < NDRAW; ++d) {
+        int n = w.n[d * S + lane];
+        const float p = w.p[d * S + lane];
+        if ((DEP_MASK >> d) & 1ull) {                               // uniform branch: the same d on every lane
+            if (((todo | park) >> (d - 1)) & ONE) {                 // the exit before this one is not final yet
+                w.n[d * S + lane] = ~n;
+                todo |= ONE << d;
+                continue;
             }
-            stalled = false;
-        } else if (can) {
-            // ---- C trip ------------------------------------------------------------------------------------------
-            const int pos = low_bit(todo);
-            const int d = (int)w.ord[pos * S + lane];
+            n -= chain_taken<DEP_MASK>(w, d);
+            w.n[d * S + lane] = n;
+        }
+        uint32_t wu, wv;
+        key.words(d, 0u, wu, wv);
+        int k;
+        const int state = binomial_attempt<!SODM_PASS1_PARK>(n, p, wu, wv, k);
+        if (state == BIN_DONE) {
+            if (k < 0) { st |= ST_BAD_PROB; k = 0; }
+            w.n[d * S + lane] = k;
+        } else if (state == BIN_RETRY) {
+            todo |= ONE << d;
+        } else {
+            park |= ONE << d;
+        }
+    }
+    // ---- pass 2: leftovers ------------------------------------------------------------------------------------------------
+    uint32_t round = 0u;
+    for (;;) {
+        const Mask m = park != 0 ? park : todo;
+        if (coop_ballot(m != 0) == 0u) break;
+        const uint32_t attempt = park != 0 ? 0u : 1u + round % 63u;  // a parked draw repeats its pass-1 attempt (and settles it)
+        ++round;
+        if (m != 0) {
+            const int d = low_bit(m);
             int n = w.n[d * S + lane];
             const float p = w.p[d * S + lane];
-            bool go = true;
-            if (((DEP_MASK >> d) & 1ull) && n < 0) {                // first attempt of a conditional draw
-                if ((open >> (d - 1)) & ONE) { stalled = true; go = false; }     // predecessor parked: wait for an X trip
-                else { n = ~n - chain_taken<DEP_MASK>(w, d); w.n[d * S + lane] = n; }
+            if (n < 0) {                                            // postponed conditional draw: its predecessors are final
+                n = ~n - chain_taken<DEP_MASK>(w, d);               // by now (they have lower bits and were taken first)
+                w.n[d * S + lane] = n;
             }
-            if (go) {
-                todo &= ~(ONE << pos);
-                int k;
-                int state = binomial_classify(n, p, k);
-                const bool flip = p > 0.5f;
-                const float pp = flip ? 1.0f - p : p;
-                if (state == BIN_DONE) {
-                    if (k < 0) { st |= ST_BAD_PROB; k = 0; }
-                } else {
-                    if (state == BIN_INVERT) { k = binomial_inversion_word(n, pp, word); state = BIN_DONE; }
-                    else state = btrs_candidate_word(n, pp, word, k);
-                    if (state == BIN_DONE) k = flip ? n - k : k;
-                }
-                if (state == BIN_DONE) {
-                    w.n[d * S + lane] = k;
-                    open &= ~(ONE << d);
-                } else {                                          // park the candidate
-                    pk3 = pk2; pk2 = pk1; pk1 = pk0; pk0 = k;
-                    pw3 = pw2; pw2 = pw1; pw1 = pw0; pw0 = word;
-                    ppos = (ppos << 8) | (uint32_t)pos;
-                    ++npend;
-                }
+            uint32_t wu, wv;
+            key.words(d, attempt, wu, wv);
+            int k;
+            const int state = binomial_attempt<true>(n, p, wu, wv, k);
+            park &= ~(ONE << d);
+            if (state == BIN_DONE) {
+                if (k < 0) { st |= ST_BAD_PROB; k = 0; }
+                w.n[d * S + lane] = k;
+                todo &= ~(ONE << d);
+            } else {
+                todo |= ONE << d;
             }
         }
     }
 }
 
-// LEGACY per-lane walk (SODM_TUNE_LEGACY_WALK; the default sampler of round 1, kept for A/B measurements and as a second
-// schedule of the same law in the tests): each lane draws its slots one after the other with a private Philox stream,
-// retrying a rejected attempt on its next trip through the loop while its neighbours move on to their next slot; the
-// exact test runs inside the trip that needs it.  Every trip consumes exactly two words (an inversion uses one and drops
-// the other), and every lane starts a step on a fresh block, so all lanes refill on the same trips.
+// PER-LANE WALK (default sampler): each lane draws its slots one after the other with a private Philox4x32 stream, retrying
+// a rejected attempt on its next trip through the loop while its neighbours move on to their next slot -- the warp runs for
+// max_lane(sum of attempts) trips instead of sum_slot(max_lane attempts); the exact test runs inside the trip that needs it.
+// Every trip consumes exactly two words (an inversion uses one and drops the other), and every lane starts a step on a fresh
+// block, so all lanes refill their 4-word block on the same trips (letting a lane carry a half-used block across steps halves
+// the active lanes per refill and costs 11 %, profiles/r1_sampler_ab.txt).
 struct WalkRng {
     Philox4x32 gen;
     uint32_t w0, w1, w2, w3;
@@ -326,13 +326,18 @@ struct WalkRng {
 template <int NDRAW, uint64_t DEP_MASK>
 __host__ __device__ __forceinline__ void sample_worklist_walk(WalkRng& rng, WorkList& w, uint32_t& st) {
     const int S = w.stride, lane = w.lane;
-    int q = 0;
+    int q = 0, chain = 0;                // chain = what the earlier exits of the same compartment element have taken
+    // Every trip is one attempt that consumes exactly two Philox words, and every lane starts a step on a fresh block
+    // (the half-used one of the previous step is dropped): the lanes of a warp then refill on the same trips, so the
+    // generator -- a sixth of the kernel's instructions -- always runs with the whole warp.  Letting each lane carry
+    // its leftover pair across steps halves the active lanes per refill and costs 11 % (profiles/r1_sampler_ab.txt).
     rng.second = false;
     while (q < NDRAW) {
         const int d = (int)w.ord[q * S + lane];
         int n = w.n[d * S + lane];
         const float p = w.p[d * S + lane];
-        if ((DEP_MASK >> d) & 1ull) n -= chain_taken<DEP_MASK>(w, d);      // predecessors come earlier in the order: final
+        const bool dep = (DEP_MASK >> d) & 1ull;
+        if (dep) n -= chain;
         if (!rng.second) {
             uint32_t b[4];
             rng.gen.next4(b);
@@ -344,10 +349,12 @@ __host__ __device__ __forceinline__ void sample_worklist_walk(WalkRng& rng, Work
         if (binomial_try_words(n, p, wu, wv, k)) {
             if (k < 0) { st |= ST_BAD_PROB; k = 0; }
             w.n[d * S + lane] = k;
+            chain = dep ? chain + k : k;
             ++q;
         }
     }
 }
+
 
 // A functor whose rates depend on the time itself (generated models with seasonal forcing, say) declares
 // `static constexpr bool USES_TIME = true` and takes the step's start time as a last argument of `propose`.
@@ -356,7 +363,7 @@ template <class M> struct functor_uses_time<M, decltype((void)M::USES_TIME)> { s
 
 // One trajectory per lane.  `active` = the lane owns a trajectory; the remaining lanes of a partially filled warp
 // still take part in the warp's votes (they have no draws to make) but neither load nor store.
-template <class M, typename OutT, bool ALIGNED, bool LEGACY>
+template <class M, typename OutT, bool ALIGNED, bool TWO_PASS>
 __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L, int64_t i, bool active,
                                                              const float* table, WorkList w) {
     double par[M::NPAR];
@@ -372,9 +379,8 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
     const bool quirk = (L.compat & COMPAT_STAY_QUIRK) != 0u;
     const float tau = (float)L.tau;
     const typename M::Pre pre = M::prepare(par, tau, quirk);
-    TripRng rng;                           // private stream of the trajectory (deferred-test walk)
-    rng.init(L.seed, (uint64_t)(L.traj_id0 + i));
-    WalkRng wrng;                          // the same stream, consumed in pairs (legacy walk)
+    AttemptKey akey;                       // counter-based words of the two-pass sampler
+    WalkRng wrng;                          // private Philox4x32 stream of the walk
     wrng.gen.init(L.seed, (uint64_t)(L.traj_id0 + i));
     wrng.w0 = wrng.w1 = wrng.w2 = wrng.w3 = 0u;
     wrng.second = false;
@@ -392,10 +398,13 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
         const float* tab = M::TDPF_COUNT ? table + (int64_t)L.tdpf_index[k] * M::TDPF_COUNT : table;
         if constexpr (functor_uses_time<M>::value) M::propose(y, pre, tab, tau, quirk, w, ALIGNED ? L.t0 + (double)k * L.tau : t);
         else M::propose(y, pre, tab, tau, quirk, w);
-        constexpr int EVERY = functor_reorder<M>::value;
-        if (EVERY > 0 ? (k % (EVERY > 0 ? EVERY : 1) == 0) : (k == 0)) reorder_draws<M::NDRAW, (uint64_t)M::DEP_MASK>(w);
-        if constexpr (LEGACY) sample_worklist_walk<M::NDRAW, (uint64_t)M::DEP_MASK>(wrng, w, st);
-        else sample_worklist_defer<M::NDRAW, (uint64_t)M::DEP_MASK>(rng, w, st);
+        if constexpr (TWO_PASS) {
+            akey.set(L.seed, (uint64_t)(L.traj_id0 + i), (uint32_t)k);
+            sample_worklist_2pass<M::NDRAW, (uint64_t)M::DEP_MASK>(akey, w, st);
+        } else {
+            if (k == 0) reorder_draws<M::NDRAW, (uint64_t)M::DEP_MASK>(w);
+            sample_worklist_walk<M::NDRAW, (uint64_t)M::DEP_MASK>(wrng, w, st);
+        }
         M::apply(y, w);
         if (ALIGNED) {
             if (--until_out == 0) {

@@ -93,6 +93,8 @@ inline int build_jump_launch_for(const sodm_jump_args* a, JumpLaunch& L, bool& a
         const int64_t n_steps = jump_n_steps(a->t0, a->n_out, a->tau);
         if (n_steps < 0) return fail(SODM_EINVAL, "sodm_jump_run: tau must be > 0 (and the run below 2^31 steps)");
         L.n_steps = (int32_t)n_steps;
+        if (a->traj_id0 < 0 || a->traj_id0 + a->n_traj > MAX_TRAJ_ID)
+            return fail(SODM_EINVAL, "sodm_jump_run: tau-leap trajectory ids must lie in [0, 2^36) (counter layout of the sampler's random words)");
         int spo = 0;
         aligned = tau_is_aligned(a->tau, &spo);
         L.steps_per_out = aligned ? spo : 0;

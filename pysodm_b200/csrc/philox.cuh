@@ -60,6 +60,33 @@ struct Philox4x32 {
     }
 };
 
+// Philox2x32-10 (Salmon et al. 2011, the 2 x 32-bit member of the same family): two words from a 64-bit counter and a
+// 32-bit key, half the work of a 4x32 block.  The tau-leap sampler calls it once per ATTEMPT with the attempt's
+// coordinates (trajectory, step, draw, attempt number) as the counter, so the words of an attempt do not depend on what
+// any other lane or any other draw is doing (jump_run.cuh).
+__host__ __device__ __forceinline__ void philox2x32_10(uint32_t key, uint32_t c0, uint32_t c1, uint32_t& o0, uint32_t& o1) {
+    constexpr uint32_t M = 0xD256D193u, W = 0x9E3779B9u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi, lo;
+        Philox4x32::mulhilo(M, c0, hi, lo);
+        c0 = hi ^ key ^ c1;
+        c1 = lo;
+        key += W;
+    }
+    o0 = c0;
+    o1 = c1;
+}
+
+// 32-bit key of a launch's tau-leap streams from the 64-bit seed (splitmix64 finaliser, folded)
+__host__ __device__ __forceinline__ uint32_t fold_seed(uint64_t seed) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)z ^ (uint32_t)(z >> 32);
+}
+
 // 24-bit uniform strictly inside (0, 1): k 2^-24 + 2^-26 for k = 0 .. 2^24 - 1, i.e. [2^-26, 1 - 2^-24] after FP32
 // rounding (the offset survives only below 1/2, where it keeps the value off zero).  A half-step offset of 2^-25 would round
 // the top value to exactly 1.0f, on which a sequential-search inversion never terminates.

@@ -43,7 +43,7 @@ char* error_buffer() {
         const int rc = ::sodm::build_jump_launch_for(a, L, aligned, plugin_info());               \
         if (rc != SODM_OK) return rc;                                                             \
         if (a->n_traj == 0) return SODM_OK;                                                       \
-        if (a->compat & ::sodm::TUNE_LEGACY_WALK)                                                 \
+        if (a->compat & ::sodm::TUNE_TWO_PASS)                                                 \
             return ::sodm::fail(SODM_EUNSUPPORTED, "generated models use the default sampler only"); \
         return ::sodm::launch_plugin_jump<M>(L, a->method, aligned, a->out_dtype, (cudaStream_t)a->stream); \
     }                                                                                             \

@@ -24,11 +24,11 @@ static void run_host(const JumpLaunch& L, int method, bool aligned) {
         uint8_t ord[M::NDRAW];
         WorkList w{wn, wp, ord, 1, 0, 1u};
         if (method == SODM_JUMP_TAU_LEAP) {
-            const bool legacy = (L.compat & TUNE_LEGACY_WALK) != 0u;
-            if (aligned) { if (legacy) tau_leap_trajectory<M, OutT, true, true>(L, i, true, table.data(), w);
-                           else        tau_leap_trajectory<M, OutT, true, false>(L, i, true, table.data(), w); }
-            else         { if (legacy) tau_leap_trajectory<M, OutT, false, true>(L, i, true, table.data(), w);
-                           else        tau_leap_trajectory<M, OutT, false, false>(L, i, true, table.data(), w); }
+            const bool two_pass = (L.compat & TUNE_TWO_PASS) != 0u;
+            if (aligned) { if (two_pass) tau_leap_trajectory<M, OutT, true, true>(L, i, true, table.data(), w);
+                           else          tau_leap_trajectory<M, OutT, true, false>(L, i, true, table.data(), w); }
+            else         { if (two_pass) tau_leap_trajectory<M, OutT, false, true>(L, i, true, table.data(), w);
+                           else          tau_leap_trajectory<M, OutT, false, false>(L, i, true, table.data(), w); }
         } else {
             ssa_trajectory<M, OutT>(L, i);
         }
@@ -72,34 +72,31 @@ extern "C" void hc_binomial(uint64_t seed, uint64_t traj, int32_t n, float p, in
     if (attempts) attempts[0] = tries;
 }
 
-// The single-word stages of the deferred-test walk (btrs_candidate_word / btrs_settle / binomial_inversion_word) applied to
-// ONE draw at a time: one word per attempt, a second word when the candidate has to be settled by the exact test.
-// `force_word` != 0 replaces the FIRST word (edge cases: all-ones word -> u01 at its top end).
+// ONE draw at a time through the two-pass sampler's unit of work (binomial_attempt): the first attempt without the exact
+// test; an undecided candidate repeats the same words with it (as pass 2 does); a rejected one takes fresh words.
+// `force_word` != 0 replaces the FIRST u-word (edge cases: all-ones word -> u01 at its top end).
 extern "C" void hc_binomial_words(uint64_t seed, uint64_t traj, int32_t n, float p, int64_t count, int32_t* out,
                                   int64_t* attempts, uint32_t force_word) {
-    PhiloxWords rng;
-    rng.init(seed, traj);
     int64_t tries = 0;
     for (int64_t c = 0; c < count; ++c) {
-        int k = 0;
-        int state = binomial_classify(n, p, k);
-        const bool flip = p > 0.5f;
-        const float pp = flip ? 1.0f - p : p;
-        while (state != BIN_DONE) {
+        AttemptKey key;
+        key.set(seed, traj, (uint32_t)c);
+        int k = 0, state = BIN_RETRY;
+        for (uint32_t a = 0; state != BIN_DONE; ++a) {
             ++tries;
-            uint32_t w = rng.next();
-            if (force_word && c == 0 && tries == 1) w = force_word;
-            if (state == BIN_INVERT) { k = binomial_inversion_word(n, pp, w); state = BIN_DONE; }
-            else {
-                state = btrs_candidate_word(n, pp, w, k);
-                if (state != BIN_DONE && btrs_settle(n, pp, k, w, rng.next())) state = BIN_DONE;
-                else if (state != BIN_DONE) state = BIN_BTRS;
-            }
-            if (state == BIN_DONE) k = flip ? n - k : k;
+            uint32_t wu, wv;
+            key.words(3, a % 64u, wu, wv);
+            if (force_word && c == 0 && a == 0) wu = force_word;
+            state = binomial_attempt<false>(n, p, wu, wv, k);
+            if (state == BIN_EXACT) state = binomial_attempt<true>(n, p, wu, wv, k);
         }
         out[c] = k;
     }
     if (attempts) attempts[0] = tries;
+}
+
+extern "C" void hc_philox2x32(uint32_t key, uint32_t c0, uint32_t c1, uint32_t* out) {
+    philox2x32_10(key, c0, c1, out[0], out[1]);
 }
 
 extern "C" void hc_philox(uint64_t seed, uint64_t traj, uint32_t purpose, int64_t n_blocks, uint32_t* out) {
@@ -110,6 +107,11 @@ extern "C" void hc_philox(uint64_t seed, uint64_t traj, uint32_t purpose, int64_
         g.next4(w);
         std::memcpy(out + 4 * b, w, sizeof(w));
     }
+}
+
+extern "C" double hc_binomial_log_ratio_large(double n, double p, double k) {
+    double out = 0.0;
+    return binomial_log_ratio_large(n, p, floor((n + 1.0) * p), k, out) ? out : NAN;
 }
 
 extern "C" double hc_binomial_log_ratio(double n, double p, double k) {

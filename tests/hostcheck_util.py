@@ -29,8 +29,12 @@ def lib():
         _lib.hc_binomial.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_float, C.c_int64, C.c_void_p, C.c_void_p]
         _lib.hc_binomial_words.restype = None
         _lib.hc_binomial_words.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint32]
+        _lib.hc_philox2x32.restype = None
+        _lib.hc_philox2x32.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.hc_philox.restype = None
         _lib.hc_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int64, C.c_void_p]
+        _lib.hc_binomial_log_ratio_large.restype = C.c_double
+        _lib.hc_binomial_log_ratio_large.argtypes = [C.c_double, C.c_double, C.c_double]
         _lib.hc_binomial_log_ratio.restype = C.c_double
         _lib.hc_binomial_log_ratio.argtypes = [C.c_double, C.c_double, C.c_double]
         _lib.hc_noise.restype = C.c_int32
@@ -51,7 +55,7 @@ def binomial(n, p, count, seed=1, traj=0):
 
 
 def binomial_words(n, p, count, seed=1, traj=0, force_word=0):
-    """The single-word sampler stages of the deferred-test walk, one draw at a time."""
+    """The two-pass sampler's unit of work (binomial_attempt), one draw at a time."""
     out = np.empty(count, dtype=np.int32)
     attempts = np.zeros(1, dtype=np.int64)
     lib().hc_binomial_words(seed, traj, int(n), float(p), count, out.ctypes.data, attempts.ctypes.data, int(force_word))
@@ -62,6 +66,12 @@ def noise(kind, param, x, count, seed=1, cell=0):
     out = np.empty(count, dtype=np.float64)
     status = lib().hc_noise(int(kind), float(param), float(x), seed, cell, count, out.ctypes.data)
     return out, status
+
+
+def philox2x32(key, c0, c1):
+    out = np.empty(2, dtype=np.uint32)
+    lib().hc_philox2x32(key, c0, c1, out.ctypes.data)
+    return out
 
 
 def philox(seed, traj, purpose, n_blocks):

@@ -21,6 +21,13 @@ def test_philox_known_answer():
     assert abs(bits.mean() - 0.5) < 5 * 0.5 / np.sqrt(bits.size)
 
 
+def test_philox2x32_known_answer():
+    """Philox2x32-10 known-answer vectors (Random123 kat_vectors)."""
+    assert [hex(int(x)) for x in hc.philox2x32(0, 0, 0)] == ["0xff1dae59", "0x6cd10df2"]
+    assert [hex(int(x)) for x in hc.philox2x32(0xffffffff, 0xffffffff, 0xffffffff)] == ["0x2c3f628b", "0xab4fd7ad"]
+    assert [hex(int(x)) for x in hc.philox2x32(0x13198a2e, 0x243f6a88, 0x85a308d3)] == ["0xdd7ce038", "0xf62a4c12"]
+
+
 @pytest.mark.parametrize("n,p", [(7317774, 1.2e-3), (4292, 0.28), (100, 0.3), (50, 0.5), (30, 0.4), (1000, 0.005),
                                  (7317774, 1e-7), (81, 0.13), (5, 0.9), (2130556, 0.02), (40, 0.26), (12, 0.97),
                                  (200000, 0.5), (1, 0.3), (20, 0.5), (1000000, 0.9999)])
@@ -51,9 +58,9 @@ def test_binomial_sampler_is_exact(n, p):
                                  # and deep inside the FP64 branch
                                  (7317774, 1.02e-3), (7317774, 1.1e-3), (2130556, 3.8e-3), (20000000, 4.0e-4),
                                  (16777216, 0.25), (50000000, 0.5), (7317774, 0.3)])
-def test_single_word_sampler_is_exact(n, p):
-    """The default sampler's stages (one word per attempt, 8-bit box test, deferred exact test): chi-square against the
-    exact pmf."""
+def test_two_pass_attempts_are_exact(n, p):
+    """The default sampler's unit of work (counter-based words, box test, squeeze, postponed exact test): chi-square against
+    the exact pmf."""
     x, attempts = hc.binomial_words(n, p, 300_000, seed=n % 89 + 3)
     p32 = float(np.float32(p))
     lo, hi = int(x.min()), int(x.max())
@@ -100,6 +107,28 @@ def test_exact_log_pmf_ratio():
         want = (gammaln(m + 1) + gammaln(n - m + 1) - gammaln(k + 1) - gammaln(n - k + 1)
                 + (k - m) * np.log(p / (1 - p)))
         assert hc.lib().hc_binomial_log_ratio(n, p, k) == pytest.approx(want, abs=2e-7 * max(1, abs(want)) + 1e-6)
+
+
+def test_large_mode_log_pmf_ratio():
+    """The FP64 multiply-add form used for modes >= 8192 against the exact product of pmf ratios (summed term by term:
+    gammaln loses ~1e-7 at these magnitudes), over the range BTRS candidates take (|k - mode| up to 5 sigma), incl. n >= 2^24
+    and p = 1/2; outside its range of validity it reports failure."""
+    import math
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for n, p in [(7317774, 1.2e-3), (7317774, 0.02), (2130556, 0.3), (50_000_000, 0.5), (20_000_000, 4.2e-4), (30000, 0.4)]:
+        p = float(np.float32(p))
+        m = int(np.floor((n + 1) * p))
+        sd = np.sqrt(n * p * (1 - p))
+        for k in np.unique(np.clip(np.rint(m + sd * rng.uniform(-5, 5, 60)), 0, n)).astype(np.int64):
+            # f(j+1)/f(j) = (n - j) p / ((j + 1) q)
+            j = np.arange(min(m, k), max(m, k), dtype=np.float64)
+            total = math.fsum(np.log((n - j) / (j + 1.0)) + math.log(p / (1 - p)))
+            want = total if k >= m else -total
+            got = hc.lib().hc_binomial_log_ratio_large(n, p, float(k))
+            worst = max(worst, abs(got - want))
+    assert worst < 2e-9, worst
+    assert np.isnan(hc.lib().hc_binomial_log_ratio_large(30000, 0.4, 100.0))       # |x| too large for the series: caller falls back
 
 
 def test_tau_leap_influenza_law(golden):

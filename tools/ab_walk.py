@@ -11,7 +11,7 @@ def main(n=1 << 20):
     tab = torch.from_numpy(td.CONTACT_TABLE.reshape(3, 16).copy()).to(dev)
     idx = torch.from_numpy(td.influenza_schedule()).to(dev)
     out = torch.empty((28, 162, n), dtype=torch.int32, device=dev)
-    for name, compat in (("deferred-test walk (default)", 3), ("legacy per-lane walk", 3 | 256)):
+    for name, compat in (("per-lane walk (default)", 3), ("two-pass sampler", 3 | 256)):
         ts = []
         for rep in range(4):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
