@@ -1,19 +1,32 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path on B200: influenza_1718 tau-leap trajectories/s (BASELINE.json metric, config 3).
+"""Benchmark of the hot path on B200.  BASELINE.json metric: "influenza_1718 tau-leap trajectories/sec; ODE ensemble
+traj/sec at 1/2/4/8 GPU".
 
     python bench.py [--gpus N] [--steps K] [--warmup W]                 (N > 1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference ...                                 (CPU arm: the oracle port on all host cores)
 
-One "step" = one pass of the hot path over one batch: N_TRAJ = 10^6 influenza trajectories (28 compartments,
-tau = 0.5, 2017-12-01 -> 2018-05-11 = 322 steps, 162 output days) with per-trajectory draws of beta and f_ud,
-int32 output [28][162][N_TRAJ] (18.1 GB per step -- far larger than the 126 MB L2, so no step can reuse cached
-data; the drawn inputs are re-uploaded for e2e).  Each rank runs its own N_TRAJ (weak scaling, no data-path
-collective: trajectories are independent); Philox streams are keyed by global trajectory id.
+HEADLINE (keys `value`, `ms_per_step`, `roofline`, `e2e` of the driver contract): BASELINE config C3.  One "step" = one pass
+of the hot path over one batch: N_TRAJ = 10^6 influenza trajectories per GPU (28 compartments, tau = 0.5,
+2017-12-01 -> 2018-05-11 = 322 steps, 162 output days) with per-trajectory draws of beta and f_ud, int32 output
+[28][162][N_TRAJ] (18.1 GB per step -- far larger than the 126 MB L2, so no step can reuse cached data; new seed every
+step).  Weak scaling: every rank runs its own N_TRAJ, Philox streams keyed by the global trajectory id.
 
-JSON keys follow the driver contract; `value` = device-resident throughput (CUDA events, max over ranks),
-`e2e` = through `pysodm_b200`'s host pipeline (pinned host draws in, full ensemble in the reference's
-(draws, time, age) layout out, H2D/D2H inside the timed region), `roofline` / `cpu_baseline` as documented in
-DESIGN.md.
+Beside it, in the same JSON line:
+  strong    the same workload with 10^6 trajectories IN TOTAL, sharded over the ranks, with and without the NCCL all-gather of
+            the int32 output shards inside the timed region (the north star's "final gather"), chunked so that the gather of
+            chunk c overlaps the kernel of chunk c+1
+  e2e       pinned host draws in, the full ensemble in the reference's (draws, time, age) layout in pinned host memory out,
+            through the host pipeline; `e2e_subset` the same for the 4 of 28 rows the tutorial reads (`states=['Im_inc']`);
+            `e2e_api` the same through the class API (`JumpProcess.sim(N=..., draw_function=...)`), once with a vectorised
+            draw function and once with a reference-style per-call draw function
+  workflow  sim -> negative-binomial noise on the observed state -> mean + 95 % band over the draws of all ranks, on the device
+  configs   every other BASELINE configuration -- C1 (SIR ODE, RK45), C2 (SIR_SI tau-leap and SSA), C4 (packed-bed PFR,
+            nx = 25 and 100), C5 (negative-binomial log-posterior of 10^5 particles, sharded over the ranks) -- each with
+            its own throughput, a roofline against a measured peak and a PARITY GATE evaluated in this run against
+            fixtures made by the unmodified reference (tests/golden/*.npz: identical nfev + rtol 1e-6 for ODEs,
+            two-sample KS for the stochastic models, 1e-9 relative for the log-likelihood)
+Timing: W >= 3 warm-ups, CUDA events on the launching stream, max over ranks; configurations whose data would fit the
+L2 are timed with an L2 flush (a 512 MB fill) between launches.
 """
 import argparse
 import json
@@ -27,6 +40,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 N_TRAJ = 1_000_000
 N_OUT = 162
@@ -37,6 +51,7 @@ BYTES_PER_TRAJ = N_STATE * N_OUT * 4 + 5 * 8 + 4      # int32 output + 5 drawn F
 VARIATES_PER_TRAJ = N_STEPS * 24
 METRIC = "influenza_1718 tau-leap trajectories/sec"
 UNIT = "trajectories/s"
+VAR_INDEX = (1, 4, 5, 6, 7)
 
 
 def synthetic_draws(n, seed):
@@ -47,9 +62,6 @@ def synthetic_draws(n, seed):
     beta = np.clip(0.0174 * (1 + 0.05 * z), 1e-6, 0.08)
     f_ud = np.clip(np.array([0.01, 0.64, 0.905, 0.60])[:, None] * u, 1e-3, 1 - 1e-3)
     return np.ascontiguousarray(np.vstack([beta[None, :], f_ud]))          # [5, n]: rows = param elements 1, 4..7
-
-
-VAR_INDEX = (1, 4, 5, 6, 7)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -120,6 +132,21 @@ def _cpu_worker(args):
     return float(y[:, 24:28, -1].mean())
 
 
+def _cpu_ode_worker(betas):
+    """C1 on the CPU: the reference's own call, scipy.integrate.solve_ivp RK45 (base.py:855), one draw after the other."""
+    from scipy.integrate import solve_ivp
+
+    def rhs(t, y, beta, gamma):
+        S, I, R = y
+        N = S + I + R
+        return [-beta * S * I / N, beta * S * I / N - 1 / gamma * I, 1 / gamma * I]
+    acc = 0.0
+    for b in betas:
+        r = solve_ivp(rhs, [0, 120], [1000.0, 1.0, 0.0], args=(b, 5.0), t_eval=np.arange(0, 121), method="RK45", rtol=1e-4)
+        acc += r.y[1, -1]
+    return acc
+
+
 def cpu_reference_rate(per_core=1024, rounds=1, pool=None, cores=None):
     """Throughput of the oracle port: `cores` processes x `per_core` trajectories per round."""
     import multiprocessing as mp
@@ -151,6 +178,11 @@ def run_reference_arm(args):
     for k in range(args.steps):
         pool.map(_cpu_worker, [(7000 * k + c, per_core) for c in range(cores)])
     dt = time.perf_counter() - t
+    # the ODE half of the metric on the same cores: C1 through scipy's solve_ivp, 64 draws per core
+    betas = np.random.default_rng(1718).uniform(0.25, 0.45, size=(cores, 64))
+    t1 = time.perf_counter()
+    pool.map(_cpu_ode_worker, list(betas))
+    dt_ode = time.perf_counter() - t1
     pool.close()
     n = cores * per_core * args.steps
     value = n / dt
@@ -165,26 +197,636 @@ def run_reference_arm(args):
                        "n_traj_per_step": cores * per_core},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "configs": {"C1_sir_ode_rk45": {"value": betas.size / dt_ode, "unit": UNIT, "cores": cores,
+                                            "what": "scipy.integrate.solve_ivp RK45 rtol 1e-4 on the tutorial SIR, 64 draws per core "
+                                                    "(the reference's own integrator call, base.py:855)"}},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------------
-# GPU arm
+# GPU arm: helpers
+# ------------------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def _events(n):
+    import torch
+    return [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+
+
+def _barrier(ctx):
+    import torch
+    import torch.distributed as dist
+    if ctx.world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(ctx.dev)
+
+
+def _max_over_ranks(ctx, values):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=ctx.dev)
+    if ctx.world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
+def _timed_launches(ctx, fn, reps=5, warm=3, flush=True):
+    """Mean device time (ms) of fn() over `reps` launches after `warm` warm-ups; an L2 flush (512 MB fill) between launches
+    when `flush` (configurations whose working set would otherwise sit in the 126 MB L2)."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(ctx.dev)
+    total = 0.0
+    for _ in range(reps):
+        if flush:
+            ctx.flush_buf.fill_(1.0)
+        a, b = _events(2)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize(ctx.dev)
+        total += a.elapsed_time(b)
+    return total / reps
+
+
+def _ks_gate(mine, ref_sorted, what):
+    """Two-sample KS per (state, time) cell: mine[cells..., n] against the reference's sorted samples ref_sorted[m, cells...].
+    BASELINE bar: p > 0.01 per cell; with hundreds of correlated cells the COUNT below 0.01 is compared with the 99.9 % point of
+    Binomial(cells, 0.01) widened to 3 % of the cells (the band the committed oracle-vs-reference null runs show,
+    tests/golden/ks_null.json), and no cell may be astronomically small."""
+    from scipy import stats
+    ref = np.moveaxis(ref_sorted, 0, -1)
+    a = mine.reshape(-1, mine.shape[-1])
+    b = ref.reshape(-1, ref.shape[-1])
+    ps = []
+    for r in range(a.shape[0]):
+        if a[r].min() == a[r].max() and b[r].min() == b[r].max() and a[r, 0] == b[r, 0]:
+            continue
+        ps.append(stats.ks_2samp(a[r], b[r]).pvalue)
+    ps = np.asarray(ps)
+    below = int((ps < 0.01).sum())
+    allowed = max(int(np.ceil(0.03 * ps.size)), int(stats.binom.isf(1e-3, ps.size, 0.01)))
+    return {"what": what, "cells": int(ps.size), "members": [int(mine.shape[-1]), int(ref_sorted.shape[0])],
+            "below_0.01": below, "allowed": allowed, "min_p": float(ps.min()) if ps.size else 1.0,
+            "pass": bool(below <= allowed and (ps.size == 0 or ps.min() > 1e-7))}
+
+
+def _hbm_roofline(ctx, bytes_per_launch, ms, note=None):
+    ach = bytes_per_launch / (ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": ach, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": ach / ctx.hbm_peak,
+         "algorithmic_bytes_per_launch": int(bytes_per_launch), "peak_source": ctx.peak_src}
+    if note:
+        r["note"] = note
+    return r
+
+
+def _measure_fp64_peak(ctx):
+    """FP64 throughput of this GPU measured with a dense FP64 matrix product (cuBLAS DGEMM 4096^3, best of 5) -- the
+    denominator of the ODE kernels' rooflines; MEASURED_PEAKS.json carries no FP64 figure."""
+    import torch
+    n = 4096
+    a = torch.randn((n, n), dtype=torch.float64, device=ctx.dev)
+    b = torch.randn((n, n), dtype=torch.float64, device=ctx.dev)
+    torch.matmul(a, b)
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = _events(2)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize(ctx.dev)
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+# ------------------------------------------------------------------------------------------------------------
+# C3 headline pieces
+# ------------------------------------------------------------------------------------------------------------
+def bench_c3_weak(ctx, args):
+    import torch
+    from pysodm_b200 import engine
+    n, dev, rank = args.n_traj, ctx.dev, ctx.rank
+    out = torch.empty((N_STATE, N_OUT, n), dtype=torch.int32, device=dev)
+    status = torch.zeros(n, dtype=torch.int32, device=dev)
+    var = (VAR_INDEX, ctx.draws_dev)
+
+    def step(seed):
+        engine.jump_run("influenza_1718_jump", ctx.y0, ctx.par, n, 0, N_OUT, TAU, var=var, tdpf=(ctx.table, ctx.index), seed=seed,
+                        traj_id0=rank * n, out_dtype=torch.int32, out=out, status=status, dev=dev)
+
+    for w in range(args.warmup):
+        step(100 + w)
+    _barrier(ctx)
+    sampler = ClockSampler(ctx.local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    _barrier(ctx)
+    ev = _events(args.steps + 1)
+    t_begin = time.time()
+    ev[0].record()
+    for k in range(args.steps):
+        step(1000 + k)
+        ev[k + 1].record()
+    _barrier(ctx)
+    t_end = time.time()
+    elapsed_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    if int(status.abs().sum()) != 0:
+        raise SystemExit("bench: trajectories reported a non-zero status")
+    checksum = int(out[24:28, -1].to(torch.int64).sum())
+    del out
+    torch.cuda.empty_cache()
+    return {"elapsed_ms": elapsed_ms, "kernel_ms": kernel_ms, "clocks": clocks, "checksum": checksum}
+
+
+def bench_c3_parity(ctx):
+    """Parity gate of the headline kernel: 20 000 trajectories at the tutorial's fixed parameters against the 20 000-member
+    ensemble of the unmodified reference (tests/golden/jump_ensemble_20k.npz), KS per (state, time) cell."""
+    import torch
+    from pysodm_b200 import engine
+    g = np.load(os.path.join(GOLDEN, "jump_ensemble_20k.npz"))
+    m = 20_000
+    out, st = engine.jump_run("influenza_1718_jump", ctx.y0, ctx.par, m, 0, N_OUT, TAU, tdpf=(ctx.table, ctx.index), seed=424242,
+                              out_dtype=torch.int32, dev=ctx.dev)
+    mine = out[:, torch.from_numpy(g["flu_times"]).to(ctx.dev), :].cpu().numpy()
+    gate = _ks_gate(mine, g["flu_sorted"], "influenza tau-leap, 20 000 device trajectories vs 20 000 reference trajectories, 28 states x 8 days")
+    gate["status_bits"] = int(engine.status_bits(st))
+    return gate
+
+
+def bench_e2e(ctx, args, rows=None, label="full"):
+    """Host-to-host through the pipeline: pinned draws in, ensemble in the reference's (draws, time, age) layout in pinned
+    host memory out.  rows = None: all 28; else the flat state rows to deliver (`states=` subset of `sim`)."""
+    import psutil
+    import torch
+    from pysodm_b200 import engine, pipeline
+    from pysodm_b200 import tutorial_data as td
+    n, dev, rank, world = args.n_traj, ctx.dev, ctx.rank, ctx.world
+    if rows is None:
+        shapes = {s: (4,) for s in td.INFLUENZA_STATES}
+        sel = None
+    else:
+        names = [td.INFLUENZA_STATES[r // 4] for r in rows[::4]]
+        shapes = {s: (4,) for s in names}
+        sel = list(rows)
+    variables, n_row = pipeline.layout_from_shapes(shapes)
+    n_e2e = args.e2e_traj or n
+    need = n_e2e * n_row * N_OUT * 4
+    avail = psutil.virtual_memory().available
+    per_rank_budget = 0.5 * avail / max(1, world)
+    if need > per_rank_budget:
+        n_e2e = max(65536, int(per_rank_budget // (n_row * N_OUT * 4)) // 65536 * 65536)
+    host_out = pipeline.alloc_host_result(variables, n_e2e, N_OUT, torch.int32)
+    pipe = pipeline.HostPipeline(variables, n_row, N_OUT, args.chunk, torch.int32, torch.int32, dev=dev)
+    y0_host = torch.from_numpy(td.influenza_flat_y0()).pin_memory()
+    table_host = torch.from_numpy(td.CONTACT_TABLE.reshape(3, 16).copy()).pin_memory()
+    index_host = torch.from_numpy(td.influenza_schedule()).pin_memory()
+    h2d_bytes = ctx.draws_host[:, :n_e2e].numel() * 8 + y0_host.numel() * 8 + table_host.numel() * 8 + index_host.numel() * 4
+    d2h_bytes = sum(t.numel() * 4 for t in host_out.values())
+
+    def e2e_step(seed):
+        y0_d = y0_host.to(dev, non_blocking=True)
+        tab_d = table_host.to(dev, non_blocking=True)
+        idx_d = index_host.to(dev, non_blocking=True)
+
+        def launch(lo, m, buf, stream):
+            chunk_draws = ctx.draws_host[:, lo:lo + m].to(dev, non_blocking=True)        # strided pinned -> device
+            engine.jump_run("influenza_1718_jump", y0_d, ctx.par, m, 0, N_OUT, TAU, var=(VAR_INDEX, chunk_draws), tdpf=(tab_d, idx_d),
+                            seed=seed, traj_id0=rank * n + lo, out_dtype=torch.int32, state_sel=sel, out=buf, dev=dev, stream=stream)
+        pipe.run(n_e2e, launch, host_out)
+        pipe.synchronize()
+
+    warm = 2
+    for w in range(warm):
+        e2e_step(100 + w)
+    _barrier(ctx)
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for k in range(steps):
+        e2e_step(1000 + k)
+    _barrier(ctx)
+    dt = time.perf_counter() - t0
+    name = list(host_out)[-1]
+    check = int(host_out[name][:, -1, :].to(torch.int64).sum())
+    launches = pipe.kernel_launches // (warm + steps)
+    del host_out, pipe
+    torch.cuda.empty_cache()
+    (dt_max,) = _max_over_ranks(ctx, [dt])
+    return {"value": world * n_e2e * steps / dt_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+            "d2h_bytes_per_step": int(d2h_bytes), "steps": steps, "n_traj_per_gpu_per_step": n_e2e, "rows_delivered": n_row,
+            "layout": "pinned host int32 (draws, time, age) per state, chunked double-buffered pipeline", "chunk": args.chunk,
+            "gpu_launches_per_step": launches, "last_seed_checksum": check, "what": label}
+
+
+def bench_e2e_api(ctx, args):
+    """The call a user makes: `JumpProcess.sim([start, end], N, tau=0.5, draw_function=..., output_dtype='int32')` on the
+    tutorial's model class (time-dependent contact matrix evaluated by the class, draws made by a Python draw function,
+    result delivered as the Dataset container).  Vectorised draw function at the full N; reference-style per-call draw
+    function at a reduced N (its N Python calls are host work that no GPU removes)."""
+    import psutil
+    from pysodm_b200 import tutorial_data as td
+    from pysodm_b200 import tutorial_models as tm
+    if ctx.world > 1:
+        return None                                       # class-API sharding goes through output='device' (workflow)
+    model = tm.JumpProcess_influenza_model(dict(td.INFLUENZA_INITIAL_STATES), dict(td.INFLUENZA_PARAMETERS),
+                                           coordinates={"age_group": td.AGE_GROUPS},
+                                           time_dependent_parameters={"N": td.influenza_contact_function})
+
+    def draw_vec(parameters, N, rng_seed):
+        d = synthetic_draws(N, rng_seed)
+        parameters["beta"] = d[0]
+        parameters["f_ud"] = np.ascontiguousarray(d[1:].T)
+        return parameters
+    draw_vec.vectorized = True
+    rng = np.random.default_rng(5)
+
+    def draw_one(parameters):
+        parameters["beta"] = float(np.clip(0.0174 * (1 + 0.05 * rng.standard_normal()), 1e-6, 0.08))
+        parameters["f_ud"] = np.clip(np.array([0.01, 0.64, 0.905, 0.60]) * rng.uniform(0.9, 1.1, 4), 1e-3, 1 - 1e-3)
+        return parameters
+
+    n = args.e2e_traj or args.n_traj
+    budget = 0.4 * psutil.virtual_memory().available
+    if n * N_STATE * N_OUT * 4 > budget:
+        n = max(65536, int(budget // (N_STATE * N_OUT * 4)) // 65536 * 65536)
+    span = [td.INFLUENZA_START, td.INFLUENZA_END]
+    res = {}
+    model.sim(span, N=4096, tau=TAU, draw_function=draw_vec, draw_function_kwargs={"rng_seed": 1}, output_dtype="int32", seed=1)
+    t0 = time.perf_counter()
+    ds = model.sim(span, N=n, tau=TAU, draw_function=draw_vec, draw_function_kwargs={"rng_seed": 7}, output_dtype="int32", seed=7)
+    dt = time.perf_counter() - t0
+    res["vectorized_draw_function"] = {"value": n / dt, "unit": UNIT, "n_traj": n, "seconds": dt,
+                                       "result_mean_Im_inc_last": float(np.asarray(ds["Im_inc"])[:, -1, :].mean())}
+    del ds
+    t0 = time.perf_counter()
+    ds = model.sim(span, N=n, tau=TAU, draw_function=draw_vec, draw_function_kwargs={"rng_seed": 8}, output_dtype="int32",
+                   states=["Im_inc"], seed=8)
+    dt = time.perf_counter() - t0
+    res["vectorized_draw_function_states_Im_inc"] = {"value": n / dt, "unit": UNIT, "n_traj": n, "seconds": dt}
+    del ds
+    n_call = min(n, 100_000)
+    t0 = time.perf_counter()
+    ds = model.sim(span, N=n_call, tau=TAU, draw_function=draw_one, output_dtype="int32", seed=9)
+    dt = time.perf_counter() - t0
+    res["per_call_draw_function"] = {"value": n_call / dt, "unit": UNIT, "n_traj": n_call, "seconds": dt,
+                                     "note": "N Python calls of the draw function on the host, as the reference makes them (base.py:550-556)"}
+    del ds
+    res["what"] = "JumpProcess_influenza_model.sim(['2017-12-01', '2018-05-11'], N, tau=0.5, draw_function, output_dtype='int32'): wall clock of the call, host to host"
+    return res
+
+
+def bench_workflow(ctx, args):
+    """The tutorial's post-processing on the device (calibration.py:231-246): sim -> add_negative_binomial_noise(alpha = 0.03)
+    -> mean and 2.5 % / 97.5 % quantiles over draws of the OBSERVED state (Im_inc, the one the tutorial plots); only the
+    drawn parameters go in and the (time, age) summaries come out over PCIe."""
+    import torch
+    import torch.distributed as dist
+    from pysodm_b200 import engine, sharding
+    n, dev, rank, world = args.n_traj, ctx.dev, ctx.rank, ctx.world
+    ens = torch.empty((N_STATE, N_OUT, n), dtype=torch.int32, device=dev)
+    obs = ens[24:28]                                         # Im_inc rows: a view, nothing is copied
+    noisy = torch.empty((4, N_OUT, n), dtype=torch.int32, device=dev)
+    status = torch.zeros(n, dtype=torch.int32, device=dev)
+    n_all = n * world
+    lo_r, hi_r = int(np.floor((n_all - 1) * 0.025)), int(np.floor((n_all - 1) * 0.975))
+    ranks = [lo_r, min(lo_r + 1, n_all - 1), hi_r, min(hi_r + 1, n_all - 1)]
+    marks = _events(5)
+
+    def workflow_step(seed):
+        d = ctx.draws_host.to(dev, non_blocking=True)
+        marks[0].record()
+        engine.jump_run("influenza_1718_jump", ctx.y0, ctx.par, n, 0, N_OUT, TAU, var=(VAR_INDEX, d), tdpf=(ctx.table, ctx.index),
+                        seed=seed, traj_id0=rank * n, out_dtype=torch.int32, out=ens, status=status, dev=dev)
+        marks[1].record()
+        engine.noise("negative_binomial", obs, 0.03, seed=seed, traj_id0=rank * n, out=noisy, dev=dev)
+        marks[2].record()
+        mean = sharding.sum_sharded(engine.draws_sum(noisy, dev=dev))                 # N > 1: all-reduce of the sums
+        marks[3].record()
+        band = sharding.order_stats_sharded(noisy, ranks)        # N > 1: radix select in phases, histograms all-reduced
+        marks[4].record()
+        return mean.cpu(), band.cpu()
+
+    workflow_step(50)
+    _barrier(ctx)
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for k in range(steps):
+        mean_h, band_h = workflow_step(2000 + k)
+    _barrier(ctx)
+    dt = time.perf_counter() - t0
+    stages = [marks[i].elapsed_time(marks[i + 1]) for i in range(4)]
+    vals = _max_over_ranks(ctx, [dt] + stages)
+    dt, stages = vals[0], vals[1:]
+    del ens, noisy
+    torch.cuda.empty_cache()
+    return {"value": n_all * steps / dt, "unit": UNIT, "ms_per_step": dt / steps * 1e3,
+            "stages_ms": dict(zip(["sim", "negative_binomial_noise", "mean", "quantile_band"], stages)),
+            "h2d_bytes_per_step": int(ctx.draws_host.numel() * 8),
+            "d2h_bytes_per_step": int((mean_h.numel() + band_h.numel()) * 8),
+            "gpu_launches_per_step": 4 if world == 1 else 4 + 8, "collectives_per_step": 0 if world == 1 else 7,
+            "what": "sim (all 28 rows kept in HBM) -> add_negative_binomial_noise(alpha=0.03) on the observed state Im_inc -> mean + "
+                    "2.5 % / 97.5 % order statistics over the draws of ALL ranks, on the device (sodm_noise, sodm_draws_sum, "
+                    "sodm_draws_order_stats / sodm_draws_select_phase + NCCL all-reduce of sums and radix histograms)"}
+
+
+def bench_c3_strong(ctx, args):
+    """BASELINE config 3 read literally: 10^6 trajectories IN TOTAL on N GPUs.  Every rank simulates its contiguous shard
+    (global trajectory ids -> the union is the single-GPU ensemble); `gathered` adds the north star's final NCCL gather
+    of the int32 output shards inside the timed region (all-gather, every rank ends with the whole ensemble), in 4 chunks so
+    that the gather of chunk c overlaps the kernel of chunk c+1."""
+    import torch
+    import torch.distributed as dist
+    from pysodm_b200 import engine, sharding
+    n_total, dev, rank, world = args.n_traj, ctx.dev, ctx.rank, ctx.world
+    lo, hi = sharding.shard_range(n_total, rank, world)
+    n = hi - lo
+    draws = torch.from_numpy(synthetic_draws(n_total, 1718)[:, lo:hi].copy()).to(dev)
+    out = torch.empty((N_STATE, N_OUT, n), dtype=torch.int32, device=dev)
+    status = torch.zeros(n, dtype=torch.int32, device=dev)
+
+    def step(seed):
+        engine.jump_run("influenza_1718_jump", ctx.y0, ctx.par, n, 0, N_OUT, TAU, var=(VAR_INDEX, draws), tdpf=(ctx.table, ctx.index),
+                        seed=seed, traj_id0=lo, out_dtype=torch.int32, out=out, status=status, dev=dev)
+    steps = args.steps
+    for w in range(3):
+        step(100 + w)
+    _barrier(ctx)
+    e0, e1 = _events(2)
+    e0.record()
+    for k in range(steps):
+        step(3000 + k)
+    e1.record()
+    _barrier(ctx)
+    (sharded_ms,) = _max_over_ranks(ctx, [e0.elapsed_time(e1) / steps])
+    res = {"n_traj_total": n_total, "n_traj_per_gpu": n, "sharded": {"value": n_total / (sharded_ms * 1e-3), "unit": UNIT, "ms_per_step": sharded_ms,
+                                                                      "what": "kernel over the shards, outputs left on their GPUs (max over ranks)"}}
+    del out
+    torch.cuda.empty_cache()
+    if world > 1 and n_total % world == 0:
+        n_chunk = 4
+        while n % n_chunk:
+            n_chunk -= 1
+        m = n // n_chunk
+        bufs = [torch.empty((N_STATE, N_OUT, m), dtype=torch.int32, device=dev) for _ in range(n_chunk)]
+        full = [torch.empty((world, N_STATE, N_OUT, m), dtype=torch.int32, device=dev) for _ in range(n_chunk)]
+        comm = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+
+        def gathered_step(seed):
+            works = []
+            for c in range(n_chunk):
+                engine.jump_run("influenza_1718_jump", ctx.y0, ctx.par, m, 0, N_OUT, TAU, var=(VAR_INDEX, draws[:, c * m:(c + 1) * m].contiguous()),
+                                tdpf=(ctx.table, ctx.index), seed=seed, traj_id0=lo + c * m, out_dtype=torch.int32, out=bufs[c],
+                                status=status[c * m:(c + 1) * m], dev=dev)
+                done = torch.cuda.Event()
+                done.record(cur)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(done)
+                    works.append(dist.all_gather_into_tensor(full[c], bufs[c], async_op=True))
+            for w in works:
+                w.wait()
+            cur.wait_stream(comm)
+        for w in range(2):
+            gathered_step(200 + w)
+        _barrier(ctx)
+        e0, e1 = _events(2)
+        e0.record()
+        for k in range(steps):
+            gathered_step(4000 + k)
+        e1.record()
+        _barrier(ctx)
+        (g_ms,) = _max_over_ranks(ctx, [e0.elapsed_time(e1) / steps])
+        gather_bytes = (world - 1) * n * N_STATE * N_OUT * 4
+        res["gathered"] = {"value": n_total / (g_ms * 1e-3), "unit": UNIT, "ms_per_step": g_ms, "chunks": n_chunk,
+                           "bytes_received_per_gpu_per_step": int(gather_bytes),
+                           "nvlink_floor_ms": gather_bytes / 900e9 * 1e3,
+                           "what": "kernel + NCCL all-gather of the int32 output shards (every GPU ends with the whole 18.1 GB ensemble), "
+                                   "gather of chunk c overlapped with the kernel of chunk c+1; the floor is the 900 GB/s NVLink ingest of one GPU"}
+        del bufs, full
+        torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the other BASELINE configurations
+# ------------------------------------------------------------------------------------------------------------
+def bench_c1(ctx):
+    """C1: tutorial SIR ODE (S0 = 1000, I0 = 1, gamma = 5), solve_ivp-faithful RK45 rtol 1e-4 atol 1e-6, t in [0, 120] -> 121
+    points, draws of beta ~ U(0.25, 0.45).  N = 100 is the reference's own size (latency of one launch), 10^5 and 4 * 10^6
+    per GPU measure throughput (the float64 output, 2 904 B per draw, is what bounds it)."""
+    import torch
+    from pysodm_b200 import engine
+    g = np.load(os.path.join(GOLDEN, "ode.npz"))
+    dev = ctx.dev
+    res = {}
+    # parity gate: the reference's 100 draws
+    out, nfev, st = engine.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], 100, 0, 121, var=([0], torch.from_numpy(g["sir_betas"][None, :]).to(dev)), dev=dev)
+    mine = out.cpu().numpy()
+    want = np.transpose(g["sir_y"], (1, 2, 0))
+    rel = float(np.max(np.abs(mine - want) / (np.abs(want) + 1e-6)))
+    res["parity"] = {"what": "100 draws of the reference run (tests/golden/ode.npz): identical nfev, max relative deviation",
+                     "nfev_identical": bool(np.array_equal(nfev.cpu().numpy(), g["sir_nfev"])), "max_rel": rel,
+                     "pass": bool(np.array_equal(nfev.cpu().numpy(), g["sir_nfev"]) and rel <= 1e-6 and int(st.abs().sum()) == 0)}
+    rng = np.random.default_rng(1718 + ctx.rank)
+    for n in (100, 100_000, 4_000_000):
+        betas = torch.from_numpy(rng.uniform(0.25, 0.45, size=n)).to(dev)[None, :]
+        out = torch.empty((3, 121, n), dtype=torch.float64, device=dev)
+        ms = _timed_launches(ctx, lambda: engine.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], n, 0, 121, var=([0], betas), out=out, dev=dev),
+                             flush=(n <= 100_000))
+        (ms,) = _max_over_ranks(ctx, [ms])
+        _, nfev, _ = engine.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], n, 0, 121, var=([0], betas), out=out, dev=dev)
+        mean_nfev = float(nfev.double().mean())
+        res[f"n{n}"] = {"value": ctx.world * n / (ms * 1e-3), "unit": UNIT, "n_traj_per_gpu": n, "ms": ms, "mean_nfev": mean_nfev,
+                        "roofline": _hbm_roofline(ctx, n * (3 * 121 * 8 + 8 + 8), ms,
+                                                  "output-bound: 2 904 B of float64 output per draw against ~150 right-hand sides of 12 flop"),
+                        "fp64_gflops": mean_nfev * 12 * n / (ms * 1e-3) / 1e9}
+        del out
+    torch.cuda.empty_cache()
+    return res
+
+
+def bench_c2(ctx, args):
+    """C2: SIR_SI vector-borne model (14 flat states, 10 binomial draws per step), tau-leap tau = 0.5 over 120 d (240 steps,
+    121 outputs, int32) at 10^4 / 10^5 / 10^6 trajectories per GPU; exact SSA on populations / 1000 (120 d) and on the full
+    populations (30 d)."""
+    import torch
+    from pysodm_b200 import engine
+    from pysodm_b200 import tutorial_data as td
+    dev = ctx.dev
+    res = {}
+    y0 = torch.from_numpy(td.sirsi_flat_y0()).to(dev)
+    par = td.sirsi_flat_par()
+    g = np.load(os.path.join(GOLDEN, "jump_ensemble_20k.npz"))
+    out, st = engine.jump_run("sir_si_jump", y0, par, 20_000, 0, 121, 0.5, seed=77, out_dtype=torch.int32, dev=dev)
+    mine = out[:, torch.from_numpy(g["sirsi_times"]).to(dev), :].cpu().numpy()
+    res["tau_leap_parity"] = _ks_gate(mine, g["sirsi_sorted"], "SIR_SI tau-leap, 20 000 device trajectories vs 20 000 reference trajectories, 14 states x 6 days")
+    for n in (10_000, 100_000, 1_000_000):
+        out = torch.empty((14, 121, n), dtype=torch.int32, device=dev)
+        ms = _timed_launches(ctx, lambda: engine.jump_run("sir_si_jump", y0, par, n, 0, 121, 0.5, seed=1, traj_id0=ctx.rank * n,
+                                                          out_dtype=torch.int32, out=out, dev=dev), flush=(n <= 100_000))
+        (ms,) = _max_over_ranks(ctx, [ms])
+        res[f"tau_leap_n{n}"] = {"value": ctx.world * n / (ms * 1e-3), "unit": UNIT, "n_traj_per_gpu": n, "ms": ms,
+                                 "binomial_variates_per_s": ctx.world * n * 240 * 10 / (ms * 1e-3),
+                                 "roofline": _hbm_roofline(ctx, n * (14 * 121 * 4 + 4), ms, "sampler-bound (2 400 exact binomial variates per trajectory), not HBM-bound")}
+        del out
+    # SSA, populations / 1000: KS gate against the reference's 400-member ensemble + throughput
+    gs = np.load(os.path.join(GOLDEN, "ssa.npz"))
+    small = gs["sirsi_small_y0"]
+    n = 10_000
+    out = torch.empty((14, 31, n), dtype=torch.float64, device=dev)
+    engine.jump_run("sir_si_jump", small, par, n, 0, 31, method="SSA", seed=5, out=out, dev=dev)
+    times = [1, 3, 7, 15, 30]
+    ref = np.sort(gs["sirsi_small_ens"][:, :, times].astype(np.float64), axis=0)
+    res["ssa_parity"] = _ks_gate(out[:, times, :].cpu().numpy(), ref, "SIR_SI SSA, populations / 1000, 30 d: 10 000 device trajectories vs the reference's 400")
+    out = torch.empty((14, 121, n), dtype=torch.float64, device=dev)
+    ms = _timed_launches(ctx, lambda: engine.jump_run("sir_si_jump", small, par, n, 0, 121, method="SSA", seed=1, traj_id0=ctx.rank * n, out=out, dev=dev),
+                         reps=2, warm=1)
+    (ms,) = _max_over_ranks(ctx, [ms])
+    # events of a trajectory = infections + recoveries + vector switches; counted from the final state where possible:
+    # every human infection and recovery moves one unit along S -> I -> R
+    fin = out[:, -1, :].double().mean(dim=1).cpu().numpy()
+    human_events = float((small[0:4].sum() - fin[0:4].sum()) + fin[8:12].sum())
+    res["ssa_pop_div_1000_120d"] = {"value": ctx.world * n / (ms * 1e-3), "unit": UNIT, "n_traj_per_gpu": n, "ms": ms,
+                                    "human_events_per_traj_mean": human_events,
+                                    "roofline": {"bound": "latency", "note": "one thread per trajectory walks a serial chain per event (two uniforms, one FP64 log, 11-term "
+                                                 "propensity scan); 10^4 trajectories fill 79 warps per SM-quarter at most: neither HBM nor issue-bound",
+                                                 "hbm": _hbm_roofline(ctx, n * 14 * 121 * 8, ms)}}
+    del out
+    n = args.ssa_full_traj
+    out = torch.empty((14, 31, n), dtype=torch.float64, device=dev)
+    e0, e1 = _events(2)
+    e0.record()
+    _, st = engine.jump_run("sir_si_jump", y0, par, n, 0, 31, method="SSA", seed=1, traj_id0=ctx.rank * n, out=out, dev=dev)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    (ms,) = _max_over_ranks(ctx, [e0.elapsed_time(e1)])
+    fin = out[:, -1, :].double().mean(dim=1).cpu().numpy()
+    start = td.sirsi_flat_y0()
+    human_events = float((start[0:4].sum() - fin[0:4].sum()) + fin[8:12].sum())
+    res["ssa_full_population_30d"] = {"value": ctx.world * n / (ms * 1e-3), "unit": UNIT, "n_traj_per_gpu": n, "ms": ms,
+                                      "human_events_per_traj_mean": human_events,
+                                      "human_events_per_s": ctx.world * n * human_events / (ms * 1e-3), "status_bits": int(engine.status_bits(st)),
+                                      "note": "vector switches S_v <-> I_v (the majority of all events) are not recoverable from the output grid; "
+                                              "human_events counts infections + recoveries only"}
+    del out
+    torch.cuda.empty_cache()
+    return res
+
+
+def bench_c4(ctx, args):
+    """C4: packed-bed plug-flow reactor by the method of lines (2 x 4 species x nx nodes: 200 equations at nx = 25, 800 at
+    nx = 100), RK45 rtol 1e-4 to t = 8000 s, draws of the 5 kinetic parameters; outputs: the final profile, and every
+    100th grid point (the reference grid of 8001 points would be 12.8 MB per draw)."""
+    import torch
+    from pysodm_b200 import engine
+    from pysodm_b200 import tutorial_data as td
+    dev = ctx.dev
+    res = {}
+    rng = np.random.default_rng(4 + ctx.rank)
+    for nx, golden_file, key, n in ((25, "ode.npz", "pfr25", args.pfr25_traj), (100, "ode_pfr100.npz", "pfr100", args.pfr100_traj)):
+        g = np.load(os.path.join(GOLDEN, golden_file))
+        post = g["pfr_posterior"][g["pfr25_pick"]] if nx == 25 else g["pfr100_posterior"]
+        k = len(post)
+        var = ([4, 5, 6, 8, 7], torch.from_numpy(np.ascontiguousarray(post.T)).to(dev))
+        out, nfev, st = engine.ode_run("packed_pfr_ode", td.pfr_flat_y0(nx), td.pfr_flat_par(nx), k, 0, 8001, model_arg=nx, out_stride=100, var=var, dev=dev)
+        want = np.transpose(g[f"{key}_y"], (1, 2, 0))
+        mine = out.cpu().numpy()
+        rel = float(np.max(np.abs(mine - want) / (np.abs(want) + 1e-6)))
+        same = bool(np.array_equal(nfev.cpu().numpy(), g[f"{key}_nfev"]))
+        entry = {"parity": {"what": f"{k} posterior draws of the reference run (tests/golden/{golden_file}), stride-100 grid: identical nfev, max relative deviation",
+                            "nfev_identical": same, "nfev": [int(x) for x in nfev.cpu().numpy()], "max_rel": rel,
+                            "pass": bool(same and rel <= 1e-6 and int(st.abs().sum()) == 0)}}
+        # synthetic posterior of the reference's spread around its point estimate (the samples file stays in the build container)
+        draws = rng.normal(1.0, 0.03, size=(5, n)) * np.array([7.88e-04, 0.055, 2.64, 0.079, 0.418])[:, None]
+        var = ([4, 5, 6, 8, 7], torch.from_numpy(draws).to(dev))
+        for label, kw, n_kept in (("final_profile", {"out_last_only": True}, 1), ("stride_100", {"out_stride": 100}, 81)):
+            out = torch.empty((8 * nx, n_kept, n), dtype=torch.float64, device=dev)
+            ms = _timed_launches(ctx, lambda: engine.ode_run("packed_pfr_ode", td.pfr_flat_y0(nx), td.pfr_flat_par(nx), n, 0, 8001, model_arg=nx,
+                                                             var=var, out=out, dev=dev, **kw), reps=2, warm=1, flush=False)
+            (ms,) = _max_over_ranks(ctx, [ms])
+            _, nfev, st = engine.ode_run("packed_pfr_ode", td.pfr_flat_y0(nx), td.pfr_flat_par(nx), n, 0, 8001, model_arg=nx, var=var, out=out, dev=dev, **kw)
+            mean_nfev = float(nfev.double().mean())
+            # flop per right-hand side: 4 species x (nx - 1) interior nodes x (upwind + dispersion + transfer: 14) fluid + 9 solid
+            # + the kinetic rate (12, one reciprocal) per node; per step (6 stages + error norm + dense output): ~55 flop per equation
+            flop = mean_nfev * (nx - 1) * (4 * 23 + 12) + (mean_nfev / 6.0) * 8 * nx * 55
+            tfl = flop * n / (ms * 1e-3) / 1e12
+            entry[label] = {"value": ctx.world * n / (ms * 1e-3), "unit": UNIT, "n_traj_per_gpu": n, "ms": ms, "mean_nfev": mean_nfev,
+                            "status_bits": int(engine.status_bits(st)),
+                            "roofline": {"bound": "fp64", "achieved": tfl, "peak": ctx.fp64_peak, "unit": "TFLOP/s", "frac": tfl / ctx.fp64_peak,
+                                         "peak_source": "measured in this run: cuBLAS DGEMM 4096^3, best of 5",
+                                         "flop_per_traj": flop, "hbm": _hbm_roofline(ctx, n * (8 * nx * n_kept * 8 + 5 * 8 + 8), ms)}}
+            del out
+        res[f"nx{nx}"] = entry
+    torch.cuda.empty_cache()
+    return res
+
+
+def bench_c5(ctx, args):
+    """C5: the influenza calibration objective -- theta = (beta, f_ud[4]) ~ U(bounds), 10^5 particles IN TOTAL sharded over
+    the ranks, one 84-day trajectory (168 steps) per particle, the 4 observed rows kept, negative-binomial log-likelihood
+    (alpha = 0.03) against 13 weekly x 4 age-group data points, NCCL all-gather of lp[P] at the end."""
+    import torch
+    from pysodm_b200 import engine, sharding
+    from pysodm_b200 import tutorial_data as td
+    dev = ctx.dev
+    P = args.c5_particles
+    lo, hi = sharding.shard_range(P, ctx.rank, ctx.world)
+    n = hi - lo
+    rng = np.random.default_rng(1718)
+    theta = np.column_stack([rng.uniform(1e-6, 0.08, P), rng.uniform(1e-3, 0.999, size=(P, 4))])[lo:hi]
+    var = ([1, 4, 5, 6, 7], torch.from_numpy(np.ascontiguousarray(theta.T)).to(dev))
+    idx = torch.from_numpy(td.influenza_schedule(n_steps=168)).to(dev)
+    ydata = rng.gamma(2.0, 150.0, size=(13, 4))
+    traj = torch.empty((4, 85, n), dtype=torch.int32, device=dev)
+    lp = torch.zeros(n, dtype=torch.float64, device=dev)
+
+    def c5():
+        lp.zero_()
+        engine.jump_run("influenza_1718_jump", ctx.y0, ctx.par, n, 0, 85, 0.5, var=var, tdpf=(ctx.table, idx), seed=3, traj_id0=lo,
+                        out_dtype=torch.int32, state_sel=[24, 25, 26, 27], out=traj, dev=dev)
+        engine.loglik("negative_binomial", traj, 0.0, [[0], [1], [2], [3]], np.arange(13) * 7.0, ydata, ll_arg=4 * [0.03], lp=lp, dev=dev)
+        return sharding.all_gather_concat(lp, P)
+    ms = _timed_launches(ctx, c5, flush=True)
+    (ms,) = _max_over_ranks(ctx, [ms])
+    full = c5()
+    ms_ll = _timed_launches(ctx, lambda: engine.loglik("negative_binomial", traj, 0.0, [[0], [1], [2], [3]], np.arange(13) * 7.0, ydata,
+                                                       ll_arg=4 * [0.03], lp=lp, dev=dev), flush=True)
+    # parity gate of the likelihood kernel: the reference's own ll_negative_binomial value on its (ymodel, ydata) pair
+    g = np.load(os.path.join(GOLDEN, "loglik.npz"))
+    ym = torch.from_numpy(np.ascontiguousarray(g["ymodel"].T[:, :, None])).to(dev)          # [4 rows][13 times][1 trajectory]
+    got, _ = engine.loglik("negative_binomial", ym, 0.0, [[0], [1], [2], [3]], np.arange(13.0), g["ydata"], ll_arg=4 * [0.03], dev=dev)
+    rel = abs(float(got[0]) - float(g["negbin_vec"])) / abs(float(g["negbin_vec"]))
+    return {"value": P / (ms * 1e-3), "unit": "log-posteriors/s", "n_particles_total": P, "n_particles_per_gpu": n, "ms": ms,
+            "loglik_kernel_ms": ms_ll, "finite_fraction": float(torch.isfinite(full).double().mean()),
+            "binomial_variates_per_s": P * 168 * 24 / (ms * 1e-3),
+            "roofline": {"bound": "hbm", **{k: v for k, v in _hbm_roofline(ctx, n * (4 * 85 * 4 * 2 + 5 * 8 + 8), ms).items() if k != "bound"},
+                         "note": "the embedded 168-step tau-leap launch is sampler-bound and, below ~10^5 trajectories per GPU, "
+                                 "latency-bound (DESIGN 5.1); the likelihood kernel alone reads 52 x 4 B per particle"},
+            "parity": {"what": "sodm_loglik vs the reference's ll_negative_binomial on its own (ymodel, ydata) (tests/golden/loglik.npz)",
+                       "rel_err": rel, "pass": bool(rel <= 1e-9)}}
+
+
 # ------------------------------------------------------------------------------------------------------------
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
-    from pysodm_b200 import engine, pipeline
+    from pysodm_b200 import engine
     from pysodm_b200 import tutorial_data as td
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("bench.py --gpus N with N > 1 must be launched with torch.distributed.run (one rank per GPU)")
-    dev = engine.device(local)
+    ctx = Ctx()
+    ctx.rank = int(os.environ.get("RANK", "0"))
+    ctx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world = ctx.rank, ctx.world
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py --gpus N with N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    ctx.dev = dev = engine.device(ctx.local)
     all_cpus = os.sched_getaffinity(0)
     if not args.no_affinity:
         # one process per GPU: run (and first-touch the pinned result buffers) on the CPU cores of the GPU's own NUMA node
@@ -209,197 +851,68 @@ def run_gpu_arm(args):
             os.dup2(saved, 1)
             os.close(saved)
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    ctx.hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    ctx.peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    ctx.flush_buf = torch.empty(128 << 20, dtype=torch.float32, device=dev)             # 512 MB > 126 MB L2
     n = args.n_traj
-    y0 = torch.from_numpy(td.influenza_flat_y0()).to(dev)
-    par = td.influenza_flat_par()
-    table = torch.from_numpy(td.CONTACT_TABLE.reshape(3, 16).copy()).to(dev)
-    index = torch.from_numpy(td.influenza_schedule()).to(dev)
-    draws_host = torch.from_numpy(synthetic_draws(n, 1718 + rank)).pin_memory()          # [5, n] pinned
-    draws_dev = draws_host.to(dev)
-    out = torch.empty((N_STATE, N_OUT, n), dtype=torch.int32, device=dev)
-    status = torch.zeros(n, dtype=torch.int32, device=dev)
-    var = (VAR_INDEX, draws_dev)
+    ctx.y0 = torch.from_numpy(td.influenza_flat_y0()).to(dev)
+    ctx.par = td.influenza_flat_par()
+    ctx.table = torch.from_numpy(td.CONTACT_TABLE.reshape(3, 16).copy()).to(dev)
+    ctx.index = torch.from_numpy(td.influenza_schedule()).to(dev)
+    ctx.draws_host = torch.from_numpy(synthetic_draws(n, 1718 + rank)).pin_memory()          # [5, n] pinned
+    ctx.draws_dev = ctx.draws_host.to(dev)
 
-    def step(seed):
-        engine.jump_run("influenza_1718_jump", y0, par, n, 0, N_OUT, TAU, var=var, tdpf=(table, index), seed=seed,
-                        traj_id0=rank * n, out_dtype=torch.int32, out=out, status=status, dev=dev)
+    t_wall = time.perf_counter()
+    head = bench_c3_weak(ctx, args)
+    parity = bench_c3_parity(ctx)
+    e2e = bench_e2e(ctx, args)
+    e2e_subset = None if args.quick else bench_e2e(ctx, args, rows=[24, 25, 26, 27], label="states=['Im_inc'] (4 of 28 rows, what the tutorial reads)")
+    e2e_api = None if (args.quick or args.no_api) else bench_e2e_api(ctx, args)
+    workflow = None if args.no_workflow else bench_workflow(ctx, args)
+    strong = None if args.quick else bench_c3_strong(ctx, args)
+    configs = None
+    if not (args.quick or args.no_configs):
+        ctx.fp64_peak = _measure_fp64_peak(ctx)
+        configs = {"C1_sir_ode_rk45": bench_c1(ctx), "C2_sir_si": bench_c2(ctx, args), "C4_packed_pfr_rk45": bench_c4(ctx, args),
+                   "C5_influenza_nb_log_posterior": bench_c5(ctx, args), "fp64_peak_tflops_measured": ctx.fp64_peak}
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    # ---- device-resident throughput -----------------------------------------------------------------------
-    for w in range(args.warmup):
-        step(100 + w)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    t_begin = time.time()
-    ev[0].record()
-    for k in range(args.steps):
-        step(1000 + k)
-        ev[k + 1].record()
-    barrier()
-    t_end = time.time()
-    elapsed_ms = ev[0].elapsed_time(ev[-1])
-    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
-    if int(status.abs().sum()) != 0:
-        raise SystemExit("bench: trajectories reported a non-zero status")
-    checksum = int(out[24:28, -1].to(torch.int64).sum())
-
-    # ---- end to end through the host pipeline -------------------------------------------------------------
-    import psutil
-    n_e2e = args.e2e_traj or n
-    need = n_e2e * N_STATE * N_OUT * 4
-    avail = psutil.virtual_memory().available
-    per_rank_budget = 0.5 * avail / max(1, world)
-    if need > per_rank_budget:
-        n_e2e = max(65536, int(per_rank_budget // (N_STATE * N_OUT * 4)) // 65536 * 65536)
-    del out
-    torch.cuda.empty_cache()
-    variables, n_row = pipeline.layout_from_shapes({s: (4,) for s in td.INFLUENZA_STATES})
-    host_out = pipeline.alloc_host_result(variables, n_e2e, N_OUT, torch.int32)
-    pipe = pipeline.HostPipeline(variables, n_row, N_OUT, args.chunk, torch.int32, torch.int32, dev=dev)
-    y0_host = torch.from_numpy(td.influenza_flat_y0()).pin_memory()
-    table_host = torch.from_numpy(td.CONTACT_TABLE.reshape(3, 16).copy()).pin_memory()
-    index_host = torch.from_numpy(td.influenza_schedule()).pin_memory()
-    h2d_bytes = draws_host[:, :n_e2e].numel() * 8 + y0_host.numel() * 8 + table_host.numel() * 8 + index_host.numel() * 4
-    d2h_bytes = sum(t.numel() * 4 for t in host_out.values())
-
-    def e2e_step(seed):
-        # every input of the step starts in (pinned) host memory; the full ensemble ends in host memory
-        y0_d = y0_host.to(dev, non_blocking=True)
-        tab_d = table_host.to(dev, non_blocking=True)
-        idx_d = index_host.to(dev, non_blocking=True)
-
-        def launch(lo, m, buf, stream):
-            chunk_draws = draws_host[:, lo:lo + m].to(dev, non_blocking=True)        # strided pinned -> device
-            engine.jump_run("influenza_1718_jump", y0_d, par, m, 0, N_OUT, TAU, var=(VAR_INDEX, chunk_draws), tdpf=(tab_d, idx_d), seed=seed,
-                            traj_id0=rank * n + lo, out_dtype=torch.int32, out=buf, dev=dev, stream=stream)
-        pipe.run(n_e2e, launch, host_out)
-        pipe.synchronize()
-
-    e2e_warm = min(args.warmup, 2)
-    for w in range(e2e_warm):
-        e2e_step(100 + w)
-    barrier()
-    e2e_steps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        e2e_step(1000 + k)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    e2e_launches = pipe.kernel_launches
-    if n_e2e == n:
-        e2e_checksum = int(host_out["Im_inc"][:, -1, :].to(torch.int64).sum())
-        last_seed_match = (e2e_steps == args.steps)
-        if last_seed_match and e2e_checksum != checksum:
-            raise SystemExit("bench: host pipeline result differs from the device-resident run")
-
-    # ---- the tutorial workflow, reduced on the device (N = 1 only) ------------------------------------------
-    # sim -> negative-binomial observation noise -> mean and 95 % band over draws (calibration.py:231,245-246), with
-    # only the drawn parameters going in and the (time, age) summaries coming out over PCIe
-    workflow = None
-    if not args.no_workflow:
-        from pysodm_b200 import sharding
-        del host_out, pipe
-        torch.cuda.empty_cache()
-        ens = torch.empty((N_STATE, N_OUT, n), dtype=torch.int32, device=dev)
-        noisy = torch.empty_like(ens)
-        n_all = n * world                                       # the ensemble of ALL ranks: reductions cross the GPUs
-        lo_r, hi_r = int(np.floor((n_all - 1) * 0.025)), int(np.floor((n_all - 1) * 0.975))
-        ranks = [lo_r, min(lo_r + 1, n_all - 1), hi_r, min(hi_r + 1, n_all - 1)]
-        marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-
-        def workflow_step(seed):
-            d = draws_host.to(dev, non_blocking=True)
-            marks[0].record()
-            engine.jump_run("influenza_1718_jump", y0, par, n, 0, N_OUT, TAU, var=(VAR_INDEX, d), tdpf=(table, index),
-                            seed=seed, traj_id0=rank * n, out_dtype=torch.int32, out=ens, status=status, dev=dev)
-            marks[1].record()
-            engine.noise("negative_binomial", ens, 0.03, seed=seed, traj_id0=rank * n, out=noisy, dev=dev)
-            marks[2].record()
-            mean = sharding.sum_sharded(engine.draws_sum(noisy, dev=dev))                 # N > 1: all-reduce of the sums
-            marks[3].record()
-            band = sharding.order_stats_sharded(noisy, ranks)        # N > 1: radix select in phases, histograms all-reduced
-            marks[4].record()
-            return mean.cpu(), band.cpu()                      # the step's result reaches the host
-
-        workflow_step(50)
-        barrier()
-        wf_steps = max(1, min(args.steps, 3))
-        t0 = time.perf_counter()
-        for k in range(wf_steps):
-            mean_h, band_h = workflow_step(2000 + k)
-        barrier()
-        wf_s = time.perf_counter() - t0
-        stages = [marks[i].elapsed_time(marks[i + 1]) for i in range(4)]
-        wf_t = torch.tensor([wf_s] + stages, dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(wf_t, op=dist.ReduceOp.MAX)
-        wf_s, stages = float(wf_t[0]), [float(x) for x in wf_t[1:]]
-        workflow = {"value": n_all * wf_steps / wf_s, "unit": UNIT, "ms_per_step": wf_s / wf_steps * 1e3,
-                    "stages_ms": dict(zip(["sim", "negative_binomial_noise", "mean", "quantile_band"], stages)),
-                    "h2d_bytes_per_step": int(draws_host.numel() * 8),
-                    "d2h_bytes_per_step": int((mean_h.numel() + band_h.numel()) * 8),
-                    "gpu_launches_per_step": 4 if world == 1 else 4 + 8,
-                    "collectives_per_step": 0 if world == 1 else 7,
-                    "what": "sim -> add_negative_binomial_noise(alpha=0.03) -> mean + 2.5 % / 97.5 % order statistics over the "
-                            "draws of ALL ranks, on the device (sodm_noise, sodm_draws_sum, sodm_draws_order_stats / "
-                            "sodm_draws_select_phase + NCCL all-reduce of sums and radix histograms)"}
-        del ens, noisy
-
-    # ---- max over ranks, final NCCL gather of per-rank summaries --------------------------------------------
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    elapsed_ms, = _max_over_ranks(ctx, [head["elapsed_ms"]])
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        summary = torch.tensor([float(checksum)], dtype=torch.float64, device=dev)
+        summary = torch.tensor([float(head["checksum"])], dtype=torch.float64, device=dev)
         gathered = [torch.zeros_like(summary) for _ in range(world)]
-        dist.all_gather(gathered, summary)          # the path's only collective: final gather (here of checksums)
-    elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+        dist.all_gather(gathered, summary)
 
     if rank == 0:
         value = world * n * args.steps / (elapsed_ms * 1e-3)
-        e2e_value = world * n_e2e * e2e_steps / (e2e_ms * 1e-3)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        k_ms = float(np.mean(kernel_ms))
+        k_ms = float(np.mean(head["kernel_ms"]))
         achieved = n * BYTES_PER_TRAJ / (k_ms * 1e-3) / 1e9
         prof = {}
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_inputs.json")))
         except OSError:
             pass
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": prof.get("dram_bytes_per_launch"), "peak_source": peak_src,
+        clocks = head["clocks"]
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_clock * 1e6
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": achieved / ctx.hbm_peak,
+                    "traffic": prof.get("dram_bytes_per_launch"), "peak_source": ctx.peak_src,
                     "kernel": "sodm::tau_leap_kernel<InfluenzaJump,int,true,false>", "kernel_ms": k_ms,
                     "algorithmic_bytes_per_launch": n * BYTES_PER_TRAJ,
-                    "note": "the kernel is ALU/issue-bound, not HBM-bound (7728 exact binomial variates per trajectory "
-                            "vs 18 KB of output); see `alu`"}
-        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
-        # issue-slot roofline: one warp instruction per cycle per SM sub-partition (148 SMs x 4) at the measured clock;
-        # instructions per trajectory and the counters below come from the committed ncu capture of this kernel
-        alu = {"binomial_variates_per_s": n * VARIATES_PER_TRAJ / (k_ms * 1e-3),
-               "warp_inst_per_traj": prof.get("warp_inst_per_traj"),
-               "issue_slot_peak_per_s": 148 * 4 * sm_clock * 1e6,
-               "ncu_issue_active_pct": prof.get("issue_active_pct"), "ncu_lanes_per_inst": prof.get("lanes_per_inst"),
-               "ncu_source": prof.get("source")}
-        if prof.get("warp_inst_per_traj"):
-            alu["achieved_warp_inst_per_s"] = prof["warp_inst_per_traj"] * n / (k_ms * 1e-3)
-            alu["frac"] = alu["achieved_warp_inst_per_s"] / alu["issue_slot_peak_per_s"]
-        roofline["alu"] = alu
-        # CPU baseline beside it (N = 1 only): bounded sample on the host cores
+                    "note": "the kernel is issue-bound, not HBM-bound (7 728 exact binomial variates per trajectory vs 18 KB of output): "
+                            "the figures that govern it are `sampler` (measured in this run) and the ncu counters under profiles/",
+                    "sampler": {"binomial_variates_per_s": n * VARIATES_PER_TRAJ / (k_ms * 1e-3),
+                                "issue_slots_per_variate": issue_peak * (k_ms * 1e-3) / (n * VARIATES_PER_TRAJ),
+                                "issue_slot_peak_per_s": issue_peak,
+                                "what": "issue slots the whole GPU offers (148 SMs x 4 schedulers x measured SM clock) per binomial variate "
+                                        "drawn, busy or not: computed from this run's kernel time, no profile involved"},
+                    "ncu": {"source": prof.get("source"), "warp_inst_per_traj": prof.get("warp_inst_per_traj"),
+                            "issue_active_pct": prof.get("issue_active_pct"), "lanes_per_inst": prof.get("lanes_per_inst"),
+                            "note": "copied from the committed ncu capture named in `source` (not measured in this run)"}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)        # the CPU arm gets every host core, not just the GPU's NUMA node
@@ -408,23 +921,25 @@ def run_gpu_arm(args):
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{cores} processes x 1024 trajectories of the same workload in {dt:.1f} s (oracle/jump.py, "
                              f"NumPy tau-leap vectorised over trajectories; the unmodified reference is ~5.6 traj/s/core)"}
+        gates = {"C3": parity.get("pass")}
+        if configs:
+            gates.update({"C1": configs["C1_sir_ode_rk45"]["parity"]["pass"], "C2_tau_leap": configs["C2_sir_si"]["tau_leap_parity"]["pass"],
+                          "C2_ssa": configs["C2_sir_si"]["ssa_parity"]["pass"], "C4_nx25": configs["C4_packed_pfr_rk45"]["nx25"]["parity"]["pass"],
+                          "C4_nx100": configs["C4_packed_pfr_rk45"]["nx100"]["parity"]["pass"],
+                          "C5": configs["C5_influenza_nb_log_posterior"]["parity"]["pass"]})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "i32 counts / f32 rates and sampler (f64 exact test above mode 8192)",
+                "scaling": "weak", "vs_baseline": None, "dtype": "i32 counts / f32 rates and sampler (f64 multiply-add exact test above mode 8192)",
                 "data": "synthetic",
                 "config": {"workload": "influenza_1718 tau-leap (BASELINE config 3): tau=0.5, 2017-12-01..2018-05-11 "
                                        "(322 steps, 162 outputs), 28 compartments, per-trajectory beta/f_ud draws",
                            "n_traj_per_gpu_per_step": n, "output": "int32 [28][162][n_traj] = 18.1 GB per step",
                            "l2_policy": "per-step output (18.1 GB) and inputs exceed the 126 MB L2; new seed each step",
-                           "parallelism": f"trajectory-sharded x{world}, no data-path collective"},
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                        "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps, "n_traj_per_gpu_per_step": n_e2e,
-                        "layout": "pinned host int32 (draws, time, age) per state, chunked double-buffered pipeline",
-                        "chunk": args.chunk},
-                "workflow": workflow,
-                "gpu_launches": args.steps, "e2e_gpu_launches_per_step": e2e_launches // (e2e_warm + e2e_steps),
-                "kernel_ms_per_step": kernel_ms}
+                           "parallelism": f"trajectory-sharded x{world}, no data-path collective (weak); see `strong` for 10^6 in total"},
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "parity_gates": gates,
+                "e2e": e2e, "e2e_subset": e2e_subset, "e2e_api": e2e_api, "workflow": workflow, "strong": strong, "configs": configs,
+                "gpu_launches": args.steps, "kernel_ms_per_step": head["kernel_ms"],
+                "bench_wall_s": time.perf_counter() - t_wall}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -439,8 +954,15 @@ def main():
     ap.add_argument("--n-traj", type=int, default=N_TRAJ)
     ap.add_argument("--e2e-traj", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=65536)
+    ap.add_argument("--ssa-full-traj", type=int, default=2048)
+    ap.add_argument("--pfr25-traj", type=int, default=100_000)
+    ap.add_argument("--pfr100-traj", type=int, default=8192)
+    ap.add_argument("--c5-particles", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-workflow", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-api", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline + e2e only")
     ap.add_argument("--no-affinity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -34,6 +34,22 @@ def _is_vectorized(fn):
     return bool(getattr(fn, "vectorized", False))
 
 
+def _fresh_parameters(base):
+    """What `copy.deepcopy(parameters)` gives a draw function, at a fraction of the cost: a new dict whose mutable values
+    (arrays, lists, dicts) are copies and whose immutable ones (numbers, strings, timestamps, functions) are shared."""
+    out = {}
+    for k, v in base.items():
+        if isinstance(v, np.ndarray):
+            out[k] = v.copy()
+        elif isinstance(v, (int, float, complex, str, bytes, bool, type(None), np.generic)) or callable(v):
+            out[k] = v
+        elif isinstance(v, list) and all(isinstance(x, (int, float, np.generic)) for x in v):
+            out[k] = list(v)
+        else:
+            out[k] = copy.deepcopy(v)
+    return out
+
+
 def _bounded_chunk(chunk, n_traj, bytes_per_traj, budget=4 << 30):
     """Trajectories per pipeline chunk: at most `chunk`, at most N, and device buffers of at most ~4 GiB each."""
     cap = max(32, int(budget // max(1, bytes_per_traj)) // 32 * 32)
@@ -293,20 +309,35 @@ class _DeviceBackedModel:
                     stacked[name] = v
             dicts = None
         else:
-            dicts = [draw_function(copy.deepcopy(base), **draw_function_kwargs) for _ in range(N)]
+            # The reference calls the draw function N times on a deep copy of the parameters (base.py:550-556).  At N = 10^6
+            # a `deepcopy` per call plus a Python-level comparison of every parameter of every draw costs more than the
+            # simulation, so: every call gets a fresh copy made by `_fresh_parameters` (arrays / lists copied, immutable
+            # values shared), the returned values are only APPENDED per name, and which names vary is decided afterwards --
+            # by identity where the function handed the same object back every time, else by ONE vectorised comparison of
+            # the stacked values.
+            dicts = [draw_function(_fresh_parameters(base), **draw_function_kwargs) for _ in range(N)]
             stacked = {}
             for name in base:
                 first = dicts[0][name]
-                try:
-                    same = all(np.array_equal(d[name], first) for d in dicts[1:])
-                except Exception:  # noqa: BLE001  (unhashable / exotic parameter types)
-                    same = all(d[name] is first for d in dicts[1:])
-                if not same:
-                    if name in self._date_params:
-                        stacked[name] = np.stack([self._flat_param(name, d[name]) for d in dicts])[:, 0]
-                    elif name in self._spec_params or name in self.initial_states_function_args:
-                        stacked[name] = np.stack([np.asarray(d[name], dtype=np.float64) for d in dicts])
-                elif name in self._spec_params and name not in tabulated:
+                if all(d[name] is first for d in dicts):
+                    same = True
+                else:
+                    try:
+                        if name in self._date_params:
+                            col = np.stack([self._flat_param(name, d[name]) for d in dicts])[:, 0]
+                        else:
+                            col = np.stack([np.asarray(d[name], dtype=np.float64) for d in dicts])
+                        same = bool(np.array_equal(col, np.broadcast_to(col[0], col.shape), equal_nan=True))
+                    except Exception:  # noqa: BLE001  (non-numeric / ragged parameter values: compare one by one)
+                        col = None
+                        try:
+                            same = all(np.array_equal(d[name], first) for d in dicts[1:])
+                        except Exception:  # noqa: BLE001
+                            same = False
+                    if not same and col is not None and (name in self._date_params or name in self._spec_params or
+                                                         name in self.initial_states_function_args):
+                        stacked[name] = col
+                if same and name in self._spec_params and name not in tabulated:
                     par[self._param_offsets[name][0]:][:self._param_offsets[name][1]] = self._flat_param(name, first)
         var = {}
         for name, values in stacked.items():

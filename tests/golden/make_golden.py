@@ -349,6 +349,55 @@ def gen_ode():
 
 
 # ------------------------------------------------------------------------------------------------
+def gen_pfr100():
+    """C4 at nx = 100 (docs/enzyme_kinetics.md:408-412): the reference's packed_PFR through solve_ivp RK45 for three
+    posterior draws, stride-100 subset of the 8001-point grid + nfev (nx = 100 had no reference parity)."""
+    import math
+    from scipy.io import netcdf_file
+    enz = ref_loader.load_tutorial_module('tutorials/enzyme_kinetics/models.py', 'ref_enzyme_models')
+    nc = netcdf_file(os.path.join(ref_loader.REFERENCE_ROOT,
+                                  'tutorials/enzyme_kinetics/data/username_SAMPLES_2025-02-05.nc'), 'r', mmap=False)
+    names = ['Vf_Ks', 'R_AS', 'R_AW', 'R_Es', 'K_eq']
+    samples = np.stack([np.array(nc.variables[k][:], dtype=np.float64).ravel() for k in names], axis=1)
+    nx = 100
+    l, Q, dt = 1, (0.20 / 60) * 10 ** -6, 0.0024
+    dp, mu, rho_B, rho_F = 0.0004755, 3.35e-03, 545, 775
+    D_AB = np.array([3.47e-07, 2.33e-07, 1.95e-07, 1.39e-06])
+    epsilon = 0.39 + 1.74 / (dt / dp + 1.140) ** 2
+    A = (dt / 2) ** 2 * math.pi
+    U = Q / A
+    u = U / epsilon
+    Re = dp * U * rho_F / mu / (1 - epsilon)
+    a = 6 * (1 - epsilon) / dp
+    kL = (0.7 * D_AB + (dp * U) / (0.18 + 0.008 * Re ** 0.59))
+    D_ax = ((1.09 / 100) * (D_AB / dp) ** (2 / 3) * (U) ** (1 / 3))
+    params = {'epsilon': epsilon, 'kL_a': kL * a, 'D_ax': D_ax, 'delta_x': l / nx, 'u': u, 'rho_B': rho_B,
+              'Vf_Ks': 7.88e-04, 'R_AS': 0.055, 'R_AW': 2.64, 'R_Es': 0.079, 'K_eq': 0.418}
+    coords = {'species': ['S', 'A', 'Es', 'W'], 'x': np.linspace(start=0, stop=l, num=nx)}
+    C_F = np.zeros([4, nx])
+    C_S = np.zeros([4, nx])
+    C_F[:, 0] = [30, 60, 0, 28]
+    C_S[:, 0] = [30, 60, 0, 28]
+    C_F[3, :] = 28
+    C_S[3, :] = 28
+    pfr = enz.packed_PFR({'C_F': C_F, 'C_S': C_S}, params, coords)
+    out = {'pfr100_y0': flat_y0(pfr)}
+    pick = [0, 456, 899]
+    ys, nf = [], []
+    t = time.time()
+    for i in pick:
+        for j, k in enumerate(names):
+            pfr.parameters[k] = samples[i, j]
+        r = pfr.sim(8000)
+        ys.append(r['y'][:, ::100].astype(np.float64))
+        nf.append(r['nfev'])
+        print(f'PFR nx=100 draw {i}: nfev={r["nfev"]} ({time.time() - t:.0f}s)', flush=True)
+    out['pfr100_pick'], out['pfr100_y'], out['pfr100_nfev'] = np.array(pick), np.stack(ys), np.array(nf)
+    out['pfr100_posterior'] = samples[pick]
+    save('ode_pfr100.npz', **out)
+
+
+# ------------------------------------------------------------------------------------------------
 def gen_loglik():
     rng = np.random.default_rng(7)
     out = {}
