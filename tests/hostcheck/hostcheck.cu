@@ -157,6 +157,7 @@ extern "C" int hc_ode_run(const sodm_ode_args* a) {
         case MODEL_PPBB_ODE:     ode_host<PpbbOde, double>(L, a->method); return SODM_OK;
         case MODEL_PACKED_PFR_ODE:
             if (L.nx == 25) { pfr_host<25, double>(L, a->method); return SODM_OK; }
+            if (L.nx == 100) { pfr_host<100, double>(L, a->method); return SODM_OK; }
             return SODM_EUNSUPPORTED;
     }
     return SODM_EMODEL;
