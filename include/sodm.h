@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SODM_ABI_VERSION 3
+#define SODM_ABI_VERSION 4
 
 /* error codes */
 #define SODM_OK            0
@@ -120,13 +120,16 @@ typedef struct sodm_jump_args {
     const double*  var_values;  /* (device) [n_var][ld_in] */
     const double*  tdpf_table;  /* (device) [n_tdpf_values][tdpf_count]; NULL if the model has tdpf_count == 0 */
     const int32_t* tdpf_index;  /* (device) [n_steps] table row in force during tau-leap step k (t_k = t0 + k*tau
-                                   accumulated in FP64 as base.py:433) */
+                                   accumulated in FP64 as base.py:433).  SSA: the functions are evaluated at event
+                                   times (base.py:376-380): entry 0 = row in force at t0 itself (first event), entry
+                                   1+k = row in force on the open interval (t0 + k*tau, t0 + (k+1)*tau), on which the
+                                   tabulated functions must be constant */
     int32_t  n_tdpf_values;
     int32_t  n_tdpf_index;      /* length of tdpf_index; must be >= the number of steps (see sodm_jump_n_steps) */
     double   t0;                /* first output time; outputs at t0, t0+1, ..., t0+n_out-1 (base.py:449) */
     int32_t  n_out;
     int32_t  n_sel;             /* 0: all states, else number of entries of state_sel */
-    double   tau;               /* tau-leap step (ignored by SSA) */
+    double   tau;               /* tau-leap step; SSA: width of a tdpf_index interval (ignored without a table) */
     const int32_t* state_sel;   /* (host)   [n_sel] flat state elements to output, in output-row order */
     void*    out;               /* (device) [n_rows][n_out][ld_out] of out_dtype, n_rows = n_sel ? n_sel : n_state */
     int32_t* status;            /* (device) [n_traj] SODM_ST_* bits, may be NULL */
@@ -194,6 +197,8 @@ typedef struct sodm_loglik_args {
     const int32_t* col_ptr;     /* (device) [n_col+1] CSR offsets into col_rows: model output rows summed into a column
                                    (the sum over dimensions absent from the data, objective_functions.py:250-252) */
     const int32_t* col_rows;    /* (device) [col_ptr[n_col]] */
+    const double*  col_weights; /* (device) [col_ptr[n_col]] weight of each row in its column, or NULL = 1: a LINEAR user
+                                   `aggregation_function` (objective_functions.py:245-248) folded into the column sums */
     double   t0;
     int32_t  n_t;               /* data time points */
     int32_t  arg_mode;          /* SODM_ARG_* */

@@ -135,13 +135,36 @@ def make_params_at(params, tdpf=None):
     return at
 
 
+def apply_tdpf_functions(t, states, pars, tdpf_functions, model_params=None):
+    """The reference's update of time-dependent parameters in front of `compute_rates` (base.py:376-386): every function
+    gets the time, the live states and the ORIGINAL value of its own parameter; its extra arguments come from the dict
+    being updated (so a later function sees an earlier one's result); parameters that only the functions use are dropped.
+
+    tdpf_functions: [(parameter name, fn(t, states, param, **extras), [extra names])] in declaration order."""
+    params = dict(pars)
+    for name, fn, extras in tdpf_functions:
+        params[name] = fn(t, states, pars[name], **{k: params[k] for k in extras})
+    if model_params is not None:
+        params = {k: v for k, v in params.items() if k in model_params}
+    return params
+
+
 def solve_discrete(model, y0, params, t0, t1, tau=0.5, method="tau_leap", tdpf=None,
-                   stay_quirk=True, first_match=True, binomial=None):
+                   stay_quirk=True, first_match=True, binomial=None, tdpf_functions=None, model_params=None,
+                   tdpf_interval=None):
     """Run one trajectory (or a batch, tau_leap only) and return (t_eval, y_eval[..., n_flat, n_t]).
 
-    y0: flat [..., n_flat] float64.  Mirrors base.py:421-440 + :442-472."""
+    y0: flat [..., n_flat] float64.  Mirrors base.py:421-440 + :442-472.
+    tdpf_functions: time-dependent parameter functions called at every step / event as `func` does (:376-380).
+    tdpf_interval: SSA with a TABULATED function (tdpf = {name: (table, index)}): index[0] is the row in force at t0 (the
+    first event is evaluated there), index[1 + floor((t - t0) / tdpf_interval)] the row in force at a later time t -- exact
+    for functions that are piecewise constant on the open intervals in between."""
     t_eval = np.arange(start=t0, stop=t1 + 1, step=1)
     params_at = make_params_at(params, tdpf)
+    if tdpf_interval is not None:
+        by_step = params_at
+        n_rows = min(len(ix) for _, ix in tdpf.values())
+        params_at = lambda k, t: by_step(0 if t == t_eval[0] else min(1 + int(np.floor((t - t_eval[0]) / tdpf_interval)), n_rows - 1), t)   # noqa: E731
     y = np.asarray(y0, dtype=np.float64)
     batch = y.shape[:-1]
     if method == "SSA" and batch:
@@ -151,6 +174,8 @@ def solve_discrete(model, y0, params, t0, t1, tau=0.5, method="tau_leap", tdpf=N
     while t < t_eval[-1]:
         p = params_at(k, t)
         states = model.unflatten(y)
+        if tdpf_functions:
+            p = apply_tdpf_functions(t, states, p, tdpf_functions, model_params)
         rates = model.rates(t, states, p)
         if method == "tau_leap":
             T, step = tau_leap_draw(model, states, rates, tau, stay_quirk, binomial), tau

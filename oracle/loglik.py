@@ -49,22 +49,26 @@ LL = {"poisson": ll_poisson, "negative_binomial": ll_negative_binomial, "normal"
       "lognormal": ll_lognormal}
 
 
-def align(y, t0, columns, t_data):
+def align(y, t0, columns, t_data, column_weights=None):
     """y[n_row, n_out] (one trajectory on the grid t0, t0+1, ..) -> ymodel[n_t, n_col].
 
-    columns[c] = rows summed into data column c; linear interpolation in time, NaN outside the grid."""
+    columns[c] = rows summed into data column c (with column_weights[c] when a linear aggregation function was folded in,
+    objective_functions.py:245-248); linear interpolation in time, NaN outside the grid."""
     y = np.asarray(y, dtype=np.float64)
     grid = t0 + np.arange(y.shape[1], dtype=np.float64)
     t_data = np.asarray(t_data, dtype=np.float64)
     out = np.empty((len(t_data), len(columns)))
     for c, rows in enumerate(columns):
-        summed = y[list(rows)].sum(axis=0)
+        if column_weights is None:
+            summed = y[list(rows)].sum(axis=0)
+        else:
+            summed = (np.asarray(column_weights[c], dtype=np.float64)[:, None] * y[list(rows)]).sum(axis=0)
         out[:, c] = np.interp(t_data, grid, summed, left=np.nan, right=np.nan)
     return out
 
 
-def log_likelihood(kind, y, t0, columns, t_data, ydata, ll_arg=None, weight=1.0):
-    ymodel = align(y, t0, columns, t_data)
+def log_likelihood(kind, y, t0, columns, t_data, ydata, ll_arg=None, weight=1.0, column_weights=None):
+    ymodel = align(y, t0, columns, t_data, column_weights)
     ydata = np.asarray(ydata, dtype=np.float64)
     if ydata.ndim == 1:
         ydata = ydata[:, None]

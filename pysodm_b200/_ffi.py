@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PYSODM_B200_LIB") or os.path.join(_HERE, "libsodm.so")     # override: tuning builds only
 
 # constants mirrored from include/sodm.h
-ABI_VERSION = 3
+ABI_VERSION = 4
 OK, EINVAL, EMODEL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4
 KIND_JUMP, KIND_ODE = 0, 1
 I32, F32, F64 = 0, 1, 2
@@ -62,7 +62,7 @@ class OdeArgs(C.Structure):
 class LoglikArgs(C.Structure):
     _fields_ = [("kind", C.c_int32), ("traj_dtype", C.c_int32), ("n_traj", C.c_int64), ("ld", C.c_int64),
                 ("traj", C.c_void_p), ("n_out", C.c_int32), ("n_col", C.c_int32),
-                ("col_ptr", C.c_void_p), ("col_rows", C.c_void_p),
+                ("col_ptr", C.c_void_p), ("col_rows", C.c_void_p), ("col_weights", C.c_void_p),
                 ("t0", C.c_double), ("n_t", C.c_int32), ("arg_mode", C.c_int32),
                 ("t_data", C.c_void_p), ("ydata", C.c_void_p), ("ll_arg", C.c_void_p),
                 ("weight", C.c_double), ("lp", C.c_void_p), ("status", C.c_void_p), ("stream", C.c_void_p)]

@@ -22,6 +22,7 @@ return), `seed`, `device`, `chunk`, `compat` (tau-leap / SSA quirk flags), and f
 """
 import copy
 import inspect
+import random as _pyrandom
 from collections import OrderedDict
 
 import numpy as np
@@ -48,6 +49,29 @@ def _fresh_parameters(base):
         else:
             out[k] = copy.deepcopy(v)
     return out
+
+
+class _StatesTouched(Exception):
+    """A time-dependent parameter function that is being tabulated on the host read the model states."""
+
+
+class _NeedsTracedTdpf(Exception):
+    """The run needs a time-dependent parameter function evaluated per trajectory (it reads the states, or one of its
+    arguments is drawn per trajectory): only a TRANSLATED function can do that."""
+
+
+class _GuardedStates:
+    """Stands in for `states` while a time-dependent parameter function is tabulated once per step for ALL trajectories:
+    such a function must not depend on the states, and instead of probing it with a few made-up states (a function that
+    happens to agree on the probes would be tabulated wrongly) every way of looking at the states raises."""
+
+    def _touched(self, *a, **k):
+        raise _StatesTouched()
+    __getitem__ = __iter__ = __len__ = __contains__ = __bool__ = __eq__ = __ne__ = _touched
+    __hash__ = None
+
+    def __getattr__(self, name):
+        raise _StatesTouched()
 
 
 def _bounded_chunk(chunk, n_traj, bytes_per_traj, budget=4 << 30):
@@ -154,6 +178,12 @@ class _DeviceBackedModel:
             # translated together with `integrate`; whether they see numbers or dates is known at sim() -> built there
             self._generated, self.device_model = True, None
             return None
+        if self.device_model and self._kind == "jump" and self.time_dependent_parameters:
+            spec = registry.get(self.device_model)
+            if any(name not in spec.tdpf_params for name in self.time_dependent_parameters):
+                # the hand-written functor reads only `spec.tdpf_params` from the per-step table: a time-dependent parameter
+                # function on any other parameter runs on the device as part of the TRANSLATED model
+                self._hand_written, self.device_model = self.device_model, None
         if not self.device_model:
             self._generated = True
             try:
@@ -175,10 +205,6 @@ class _DeviceBackedModel:
                              f"device functor '{spec.name}' {list(params)}")
         self._spec, self._spec_params = spec, params
         self._param_offsets, self._n_param_flat = spec.param_offsets(self._model_arg)
-        for name in (self.time_dependent_parameters or {}):
-            if name not in spec.tdpf_params:
-                raise NotImplementedError(f"device functor '{spec.name}' has no time-dependent slot for parameter "
-                                          f"'{name}' (supported: {list(spec.tdpf_params)})")
 
     def _bind_generated_functor(self, date_unit_us=None, date_range=None):
         """No hand-written functor (or an ODE with time-dependent parameter functions): translate the class's own Python
@@ -190,32 +216,65 @@ class _DeviceBackedModel:
         key = date_unit_us
         if key in self._generated_cache:
             plug, spec, shapes, self._date_params = self._generated_cache[key]
+            self._traced_tdpfs = list(getattr(spec, "traced_tdpfs", []))
         else:
             tdpfs = self.time_dependent_parameters or {}
             decl = list(self.parameters_names_modeldeclaration)
+            extras_of = {name: list(self._function_parameters[i]) for i, name in enumerate(tdpfs)}
+
+            def shapes_of(order, lenient=()):
+                shapes, date_params = OrderedDict(), []
+                for name in order:
+                    value = self.parameters[name]
+                    if plugin.codegen._is_datelike(value):
+                        if date_unit_us is None:
+                            if name in lenient:
+                                continue
+                            raise NotImplementedError(f"parameter '{name}' is a date; simulate over dates (time=[start, stop])")
+                        shapes[name] = ()
+                        date_params.append(name)
+                        continue
+                    if callable(value) or isinstance(value, (str, dict)):
+                        if name in lenient:
+                            continue
+                        raise NotImplementedError(f"parameter '{name}' is not numeric; generated device models take scalars, arrays and dates")
+                    shapes[name] = tuple(np.shape(np.asarray(value, dtype=np.float64)))
+                return shapes, date_params
+            traced, self._tdpf_reason = [], {}
             if self._kind == "ode":
                 tab = []
                 order = decl + [n for n in self._extra_params_TDPF if n not in decl]
             else:
-                tab = [n for n in decl if n in tdpfs]
-                order = [n for n in decl if n not in tab] + tab
-            shapes, date_params = OrderedDict(), []
-            for name in order:
-                value = self.parameters[name]
-                if plugin.codegen._is_datelike(value):
-                    if date_unit_us is None:
-                        raise NotImplementedError(f"parameter '{name}' is a date; simulate over dates (time=[start, stop])")
-                    shapes[name] = ()
-                    date_params.append(name)
-                    continue
-                if callable(value) or isinstance(value, (str, dict)):
-                    raise NotImplementedError(f"parameter '{name}' is not numeric; generated device models take scalars, arrays and dates")
-                shapes[name] = tuple(np.shape(np.asarray(value, dtype=np.float64)))
+                # Which functions can be translated?  Those are evaluated on the device at every step / event with the live
+                # states and the trajectory's own parameters, as the reference does (base.py:376-380); the others (calendar
+                # logic, look-ups keyed by the date) are tabulated on the host and must be functions of the time alone.
+                only_tdpf = [n for n in self._extra_params_TDPF if n not in decl]
+                probe, probe_dates = shapes_of(decl + only_tdpf, lenient=only_tdpf)
+                if date_unit_us is not None:
+                    probe["__t0__"] = ()
+                for name, fn in tdpfs.items():
+                    ok, why = False, "an argument is not numeric"
+                    if all(a in probe for a in extras_of[name]) and name not in probe_dates:
+                        ok, why = plugin.codegen.tdpf_traceable(fn, extras_of[name], OrderedDict(
+                            (k, tuple(self.state_shapes[k])) for k in self.states_names), probe, name, date_unit_us, probe_dates)
+                    if ok:
+                        traced.append(name)
+                    else:
+                        self._tdpf_reason[name] = why
+                tab = [n for n in decl if n in tdpfs and n not in traced]
+                for name in tab:                              # the host tabulation uses the ORIGINAL parameter values
+                    if any(a in tdpfs for a in extras_of[name]):
+                        raise NotImplementedError(f"the time-dependent parameter function of '{name}' cannot be translated "
+                                                  f"({self._tdpf_reason[name]}) and takes another time-dependent parameter as an argument")
+                need = [a for name in traced for a in extras_of[name] if a not in decl]
+                order = [n for n in decl if n not in tab] + list(dict.fromkeys(need)) + tab
+            shapes, date_params = shapes_of(order)
             if date_unit_us is not None:                      # hidden: absolute time of t = 0 (before the tabulated TDPF block)
                 tail = [(k, shapes.pop(k)) for k in list(shapes) if k in tab]
                 shapes["__t0__"] = ()
                 shapes.update(tail)
             self._date_params = date_params
+            self._traced_tdpfs = traced
             state_shapes = OrderedDict((k, tuple(self.state_shapes[k])) for k in self.states_names)
             n_par = sum(int(np.prod(v)) if v else 1 for v in shapes.values())
             n_st = sum(int(np.prod(v)) if v else 1 for v in state_shapes.values())
@@ -230,10 +289,13 @@ class _DeviceBackedModel:
                                         example_params=self._example_flat(shapes, date_unit_us, date_range),
                                         tdpf=spec_t, model_params=decl, date_unit_us=date_unit_us, date_params=date_params)
             else:
+                spec_t = [(name, tdpfs[name], extras_of[name]) for name in tdpfs if name in traced]
                 plug = plugin.build_jump(self.compute_rates, self.apply_transitionings, state_shapes, shapes, tab,
                                          self.initial_states, self.parameters, origin, date_unit_us=date_unit_us,
-                                         date_params=date_params, start_date=date_range[0] if date_range else None)
+                                         date_params=date_params, start_date=date_range[0] if date_range else None,
+                                         tdpf=spec_t, model_params=decl)
             spec = registry.DeviceSpec(plug.name, self._kind, list(state_shapes.items()), list(shapes.items()), tdpf_params=tab)
+            spec.traced_tdpfs = list(traced)
             self._generated_cache[key] = (plug, spec, shapes, date_params)
         self.device_model = plug
         self._model_arg = 0
@@ -340,10 +402,14 @@ class _DeviceBackedModel:
                 if same and name in self._spec_params and name not in tabulated:
                     par[self._param_offsets[name][0]:][:self._param_offsets[name][1]] = self._flat_param(name, first)
         var = {}
+        feeds_table = set(tabulated)                           # a tabulated function is evaluated once per step for ALL trajectories
+        for i, tname in enumerate(self.time_dependent_parameters or {}):
+            if tname in tabulated:
+                feeds_table.update(self._function_parameters[i])
         for name, values in stacked.items():
-            if name in tabulated or (tabulated and name in self._extra_params_TDPF):
-                raise NotImplementedError(f"parameter '{name}' is drawn per trajectory AND feeds a time-dependent "
-                                          "parameter function; the device path tabulates a jump process's TDPFs once per run")
+            if name in feeds_table:
+                raise _NeedsTracedTdpf(f"parameter '{name}' is drawn per trajectory and feeds the time-dependent parameter "
+                                       f"function of {sorted(tabulated)}")
             if name in self._spec_params:
                 off, n, shape = self._param_offsets[name]
                 flat = np.asarray(values, dtype=np.float64).reshape(N, n)
@@ -432,31 +498,32 @@ class JumpProcess(_DeviceBackedModel):
         validation.callable_signature(self.apply_transitionings, "apply_transitionings", self.states_names,
                                       self.parameters_names_modeldeclaration, ("t", "tau", "transitionings"))
 
+    def _tdpf_values_at(self, t, start_date, time_unit):
+        """Flat values of the TABULATED time-dependent parameters at time t: each function is called as the reference's
+        `func` calls it -- with the ORIGINAL parameter value (base.py:376-380, Q8) -- except that `states` is a guard: a
+        function that is evaluated once for all trajectories must not read them (`_StatesTouched`)."""
+        when = validation.time_to_date(float(t), start_date, time_unit) if start_date is not None else t
+        parts = []
+        for name in self._spec.tdpf_params:
+            if name in (self.time_dependent_parameters or {}):
+                fn = self.time_dependent_parameters[name]
+                i = list(self.time_dependent_parameters).index(name)
+                kw = {a: self.parameters[a] for a in self._function_parameters[i]}
+                val = fn(when, _GuardedStates(), self.parameters[name], **kw)
+            else:
+                val = self.parameters[name]
+            parts.append(self._flat_param(name, val))
+        return np.concatenate(parts)
+
     def _tabulate_tdpfs(self, t0, n_steps, tau, start_date, time_unit):
-        """Evaluate the (state-independent) TDPFs at every tau-leap step time, as the reference's `func` does per
-        step with the ORIGINAL parameter value (base.py:365-380, Q8), and de-duplicate the values."""
-        if not self.time_dependent_parameters:
+        """tau-leap: the tabulated functions at every step time t_k (accumulated in FP64 as base.py:433), de-duplicated into
+        (table[n_values][n_elements], index[n_steps])."""
+        if not self._spec.tdpf_params:
             return None
-        tdpf_names = [n for n in self._spec.tdpf_params]
         rows, index, seen = [], np.empty(n_steps, dtype=np.int32), {}
-        probe = {k: v * 0.0 for k, v in self.initial_states.items()}
         t = t0
         for k in range(n_steps):
-            when = validation.time_to_date(float(t), start_date, time_unit) if start_date is not None else t
-            parts = []
-            for name in tdpf_names:
-                if name in self.time_dependent_parameters:
-                    fn = self.time_dependent_parameters[name]
-                    i = list(self.time_dependent_parameters).index(name)
-                    kw = {a: self.parameters[a] for a in self._function_parameters[i]}
-                    val = fn(when, self.initial_states, self.parameters[name], **kw)
-                    if k in (0, n_steps // 2) and not np.array_equal(val, fn(when, probe, self.parameters[name], **kw)):
-                        raise NotImplementedError(f"the time-dependent parameter function of '{name}' depends on the "
-                                                  "model states; the device path only tabulates functions of time")
-                else:
-                    val = self.parameters[name]
-                parts.append(self._flat_param(name, val))
-            flat = np.concatenate(parts)
+            flat = self._tdpf_values_at(t, start_date, time_unit)
             key = flat.tobytes()
             if key not in seen:
                 seen[key] = len(rows)
@@ -465,9 +532,50 @@ class JumpProcess(_DeviceBackedModel):
             t = t + tau
         return np.stack(rows), index
 
+    def _tabulate_tdpf_intervals(self, t0, t1, width, start_date, time_unit):
+        """SSA: the reference evaluates the functions at every EVENT time (base.py:376-380, :399).  A function that can only be
+        tabulated must therefore be piecewise constant on the OPEN intervals (t0 + k w, t0 + (k+1) w) of the table (the
+        tutorial's contact matrix changes at midnight, and its `a < t <= b` windows put the boundary itself on the earlier
+        side: w = 1 day); that is verified at four interior points of every interval, and a function that varies inside one
+        is refused (translate it, or pass a smaller `tdpf_resolution`).  Which side a boundary belongs to is immaterial --
+        an event time hits one with probability zero -- except for the FIRST event, which is evaluated at t0 itself:
+        index[0] = row at t0, index[1 + k] = row on interval k (include/sodm.h)."""
+        if not self._spec.tdpf_params:
+            return None
+        n = max(1, int(np.ceil((t1 - t0) / width)))
+        rows, index, seen = [], np.empty(n + 1, dtype=np.int32), {}
+
+        def row_of(flat):
+            key = flat.tobytes()
+            if key not in seen:
+                seen[key] = len(rows)
+                rows.append(flat)
+            return seen[key]
+        index[0] = row_of(self._tdpf_values_at(t0, start_date, time_unit))
+        for k in range(n):
+            flat = self._tdpf_values_at(t0 + (k + 0.19) * width, start_date, time_unit)
+            for frac in (2.0 ** -20, 0.37, 0.81, 1.0 - 2.0 ** -20):
+                if not np.array_equal(flat, self._tdpf_values_at(t0 + (k + frac) * width, start_date, time_unit), equal_nan=True):
+                    raise NotImplementedError(
+                        f"SSA: a tabulated time-dependent parameter function ({list(self._spec.tdpf_params)}) changes inside the "
+                        f"interval ({t0 + k * width}, {t0 + (k + 1) * width}); functions the device cannot translate must be "
+                        "piecewise constant on intervals of `tdpf_resolution` time units")
+            index[1 + k] = row_of(flat)
+        return np.stack(rows), index
+
+    def _switch_to_translated(self, why, want_unit, date_range):
+        """Leave the hand-written functor (which can only read tabulated time-dependent parameters) for the translated
+        model, whose time-dependent parameter functions run on the device per trajectory.  Raises when a function that
+        would have to run there cannot be translated."""
+        if not self._generated:
+            self._hand_written = self.device_model
+            self.device_model, self._generated, self._generated_cache = None, True, {}
+        self._bind_generated_functor(want_unit, date_range)
+        return why
+
     def sim(self, time, N=1, draw_function=None, draw_function_kwargs={}, processes=None, method="tau_leap", tau=1,
             time_unit="D", *, output_dtype="float64", states=None, seed=None, device=None, chunk=65536,
-            compat=_ffi.COMPAT_REFERENCE, output="host"):
+            compat=_ffi.COMPAT_REFERENCE, output="host", tdpf_resolution=1.0):
         """Simulate N trajectories over `time` (see module docstring).  `processes` is accepted and ignored.
         output='device' keeps the ensemble in HBM and returns a `DeviceEnsemble` (ensemble.py) for on-device noise /
         mean / quantiles instead of copying `(draws, time, *dims)` arrays to the host."""
@@ -478,33 +586,58 @@ class JumpProcess(_DeviceBackedModel):
         if draw_function:
             validation.draw_function(draw_function, draw_function_kwargs, copy.deepcopy(self.parameters),
                                      self.initial_states_function, self.state_shapes, self.initial_states_function_args)
+        want = validation.TIME_UNIT_US[time_unit] if date_range[0] is not None else None
         if self._generated:
             # model functions that use the time see dates when sim runs over dates (base.py:365-373): one translation each
-            want = validation.TIME_UNIT_US[time_unit] if date_range[0] is not None else None
             plug = self.device_model
-            mode_sensitive = plug is None or plug.layout.get("uses_time") or self._date_params or self._time_unit_us is not None
+            mode_sensitive = (plug is None or plug.layout.get("uses_time") or self._date_params or self._time_unit_us is not None
+                              or bool(getattr(self, "_traced_tdpfs", None)))
             if mode_sensitive and (plug is None or self._time_unit_us != want):
                 self._bind_generated_functor(want, date_range)
         saved = copy.deepcopy(self.parameters)
         try:
-            par, var, y0, _ = self._collect_draws(N, draw_function, draw_function_kwargs)
+            t0, t1 = time
+            n_out = int(t1 - t0 + 1)
+            lib = _ffi.load()
+            n_steps = int(lib.sodm_jump_n_steps(float(t0), n_out, float(tau))) if method == "tau_leap" else 0
+
+            def tabulate():
+                if method == "tau_leap":
+                    return self._tabulate_tdpfs(t0, n_steps, tau, date_range[0], time_unit)
+                return self._tabulate_tdpf_intervals(float(t0), float(t1), float(tdpf_resolution), date_range[0], time_unit)
+            # Time-dependent parameter functions (base.py:376-380).  Translated ones run on the device with the live states and
+            # the trajectory's own parameters.  The others are evaluated here, once per step for all trajectories -- legitimate
+            # only for functions of the time alone: one that reads the states (guard), or is fed by a per-trajectory draw, moves
+            # the model to the translated route; if the function cannot be translated either, that is an error, not a fallback.
+            rng_state = (np.random.get_state(), _pyrandom.getstate())
+            try:
+                tdpf = tabulate()
+                par, var, y0, _ = self._collect_draws(N, draw_function, draw_function_kwargs)
+            except (_StatesTouched, _NeedsTracedTdpf) as exc:
+                # translate for this run's time mode (a function written for dates only translates when given dates)
+                before = (self._generated, self._time_unit_us, self.device_model)
+                self._switch_to_translated(str(exc), want, date_range)
+                np.random.set_state(rng_state[0])
+                _pyrandom.setstate(rng_state[1])
+                try:
+                    if before == (self._generated, self._time_unit_us, self.device_model):
+                        raise exc                              # nothing changed: the function in question is not translatable
+                    tdpf = tabulate()
+                    par, var, y0, _ = self._collect_draws(N, draw_function, draw_function_kwargs)
+                except (_StatesTouched, _NeedsTracedTdpf) as exc2:
+                    raise NotImplementedError(
+                        f"a time-dependent parameter function of {list(self._spec.tdpf_params)} must run per trajectory ("
+                        + (str(exc2) or "it reads the model states") + ") but cannot be translated for the device: "
+                        f"{getattr(self, '_tdpf_reason', {})}") from None
             if "__t0__" in self._param_offsets:
                 from .codegen import date_to_units
                 par[self._param_offsets["__t0__"][0]] = date_to_units(date_range[0], self._time_unit_us)
-            t0, t1 = time
-            n_out = int(t1 - t0 + 1)
             dev = engine.device(device)
-            lib = _ffi.load()
-            tdpf = None
-            if method == "tau_leap":
-                n_steps = int(lib.sodm_jump_n_steps(float(t0), n_out, float(tau)))
-                tdpf = self._tabulate_tdpfs(t0, n_steps, tau, date_range[0], time_unit)
-            elif self.time_dependent_parameters:
-                raise NotImplementedError("SSA with time-dependent parameter functions is not available on the device")
-            if self._spec.tdpf_params and tdpf is None and method == "tau_leap":
+            if self._spec.tdpf_params and tdpf is None:
                 # constant value of a parameter that lives in the TDPF table
                 flat = np.concatenate([self._flat_param(n, self.parameters[n]) for n in self._spec.tdpf_params])
                 tdpf = (flat[None, :], np.zeros(max(n_steps, 1), dtype=np.int32))
+            run_tau = tau if method == "tau_leap" else float(tdpf_resolution)      # SSA: width of a table interval (sodm.h)
             variables, rows = self._select_rows(states)
             host_dtype = engine.as_torch_dtype(output_dtype)
             # tau = 2^-k: every output time is a step time, counts are exact integers -> simulate in int32 and let
@@ -522,7 +655,7 @@ class JumpProcess(_DeviceBackedModel):
                 seed = sharding.agree_on(seed)               # one ensemble across the ranks of a torch.distributed job
                 return self._sim_on_device(
                     lambda buf, v, y, st, lo, n: engine.jump_run(
-                        self.device_model, y, par, n, t0, n_out, tau, method=method, var=v, tdpf=self._to_device_tdpf(tdpf, dev),
+                        self.device_model, y, par, n, t0, n_out, run_tau, method=method, var=v, tdpf=self._to_device_tdpf(tdpf, dev),
                         compat=compat, seed=seed, traj_id0=lo, out_dtype=sim_dtype, state_sel=rows, out=buf, status=st, dev=dev),
                     var, y0, variables, len(rows), n_out, N, sim_dtype, dev, date_range, t0, t1, self._raise_on_status)
             if output != "host":
@@ -540,7 +673,7 @@ class JumpProcess(_DeviceBackedModel):
             def launch(lo, n, buf, stream):
                 v = (keys, var_host[:, lo:lo + n].to(dev, non_blocking=True)) if keys else None
                 y = y0_d if y0_d.dim() == 1 else y0_d[:, lo:lo + n].contiguous()
-                engine.jump_run(self.device_model, y, par, n, t0, n_out, tau, method=method, var=v, tdpf=tdpf_d,
+                engine.jump_run(self.device_model, y, par, n, t0, n_out, run_tau, method=method, var=v, tdpf=tdpf_d,
                                 compat=compat, seed=seed, traj_id0=lo, out_dtype=sim_dtype, state_sel=rows, out=buf,
                                 status=status[lo:lo + n], dev=dev, stream=stream)
             pipe.run(N, launch, host)

@@ -187,7 +187,7 @@ class Sym:
         a, b = self.g.nodes[self.i], self.g.nodes[o.i]
         if a[0] == "const" and b[0] == "const":
             x, y = a[1][0], b[1][0]
-            return self.g.const(int({"lt": x < y, "le": x <= y, "gt": x > y, "ge": x >= y}[op]))
+            return self.g.const(int({"lt": x < y, "le": x <= y, "gt": x > y, "ge": x >= y, "eq": x == y, "ne": x != y}[op]))
         return self.g.node(op, (self.i, o.i), "b")
 
     def __lt__(self, o): return self._compare("lt", o)
@@ -207,8 +207,20 @@ class Sym:
     def __ror__(self, o): return self._logic("or", o)
     def __invert__(self): return self.g.node("not", (self.i,), "b")
 
+    # `==` / `!=` on model values are symbolic comparisons like `<` (as plain identity tests, `if S == 0:` silently
+    # traced one branch only).  The SAME node compares equal as a Python bool, which is what dict / set membership of a Sym
+    # needs (hash-consing: one node per expression); anything that cannot be a model value is simply "not equal".
     def __eq__(self, o):
-        return isinstance(o, Sym) and o.g is self.g and o.i == self.i
+        if isinstance(o, Sym) and o.g is self.g and o.i == self.i:
+            return True
+        r = self._compare("eq", o) if isinstance(o, (Sym, int, float, np.integer, np.floating, bool, np.bool_)) else NotImplemented
+        return False if r is NotImplemented else r
+
+    def __ne__(self, o):
+        if isinstance(o, Sym) and o.g is self.g and o.i == self.i:
+            return False
+        r = self._compare("ne", o) if isinstance(o, (Sym, int, float, np.integer, np.floating, bool, np.bool_)) else NotImplemented
+        return True if r is NotImplemented else r
 
     def __hash__(self):
         return hash((id(self.g), self.i))
@@ -233,7 +245,9 @@ class Sym:
             raise ValueError(f"cannot reshape a scalar into shape {tuple(shape)}")
         return out
     def __getitem__(self, key):
-        if key == () or key is Ellipsis:
+        # the reference holds a dimensionless state as a ONE-element array (utils.py:45-55), so `states['I'][0]` is valid
+        # user code there: element 0 of a scalar model value is the value itself
+        if key is Ellipsis or (isinstance(key, tuple) and (key == () or key == (0,))) or (isinstance(key, (int, np.integer)) and key in (0, -1)):
             return self
         raise IndexError("a scalar model value cannot be indexed")
 
@@ -518,6 +532,9 @@ def _python_function(fn):
 
 def _retarget(fn, graph):
     """A copy of `fn` whose global `np` / `numpy` (under whatever alias) is the tracing proxy."""
+    if isinstance(fn, types.MethodType):                 # bound method (a TDPF living on a helper object): keep its `self`
+        inner, owner = _retarget(fn.__func__, graph), fn.__self__
+        return lambda *a, **k: inner(owner, *a, **k)
     fn = _python_function(fn)
     g = dict(fn.__globals__)
     proxy = _NumpyProxy(graph)
@@ -590,8 +607,8 @@ def trace_ode(integrate, state_shapes, param_shapes, tdpf=(), model_params=None,
             for k in date_params:
                 pars[k] = SymDate(pars[k], date_unit_us)
         params = dict(pars)
-        for name, f, extra in tdpf:
-            params[name] = f(when, states, pars[name], **{k: pars[k] for k in extra})
+        for name, f, extra in tdpf:             # extra arguments from the dict being updated, own value from the original (:773-774)
+            params[name] = f(when, states, pars[name], **{k: params[k] for k in extra})
         res = fn(when, **states, **{k: params[k] for k in model_params})
         if not isinstance(res, (tuple, list)):
             res = (res,)
@@ -599,19 +616,63 @@ def trace_ode(integrate, state_shapes, param_shapes, tdpf=(), model_params=None,
     return g, explore(g, run)
 
 
-def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes, date_unit_us=None, date_params=()):
+def tdpf_traceable(fn, extras, state_shapes, param_shapes, target, date_unit_us=None, date_params=()):
+    """Can the time-dependent parameter function `fn(t, states, param, **extras)` be translated?  It is called on symbolic
+    time / states / parameters exactly as `trace_jump` will call it; calendar logic, table look-ups keyed by the date and
+    anything else that needs a concrete value raise, and the function is then TABULATED on the host instead (which in turn
+    requires that it does not read the states: base._tabulate_tdpfs hands it a guard).  -> (ok, reason)"""
+    g = Graph()
+    g.unit_us = date_unit_us
+    t = g.leaf(("t", 0), "f")
+    try:
+        f = _retarget(fn, g)
+    except TraceError as exc:
+        return False, str(exc)
+
+    def run():
+        kw = _inputs(g, state_shapes, param_shapes, "f")
+        when = t
+        if date_unit_us is not None:
+            when = SymDate(t + kw["__t0__"], date_unit_us)
+            for k in date_params:
+                kw[k] = SymDate(kw[k], date_unit_us)
+        res = f(when, {k: kw[k] for k in state_shapes}, kw[target], **{k: kw[k] for k in extras})
+        a = np.asarray(res, dtype=object)
+        want = tuple(param_shapes[target])
+        if a.shape != want and a.size != max(1, int(np.prod(want))):
+            a = np.broadcast_to(a, want)
+        for v in a.reshape(-1).tolist():
+            if not isinstance(v, (Sym, int, float, np.integer, np.floating, bool, np.bool_)):
+                raise TraceError(f"returns a {type(v).__name__}")
+        return a.reshape(-1).tolist()
+    try:
+        explore(g, run)
+    except Exception as exc:  # noqa: BLE001  (anything the symbolic call cannot digest means: not translatable)
+        return False, f"{type(exc).__name__}: {exc}"
+    return True, ""
+
+
+def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes, date_unit_us=None, date_params=(), tdpf=(),
+               model_params=None):
     """-> dict with the rate graph (per state: list of transitions, each a flat list of expressions) and the bookkeeping
-    graph (new value per flat state element as integer expressions of states `y` and transitionings `T`)."""
+    graph (new value per flat state element as integer expressions of states `y` and transitionings `T`).
+
+    tdpf: [(parameter name, function(t, states, param, **extras), [extra argument names])] -- time-dependent parameter
+    functions that are TRANSLATED (they may read the states, the time and per-trajectory parameters): evaluated in front
+    of `compute_rates` and `apply_transitionings` at every step / event exactly as the reference's `func` does
+    (base.py:376-380: own value from the original parameters, extra arguments from the dict being updated);
+    `model_params`: the names the two model functions take (parameters only the TDPFs use are dropped, :386)."""
     state_sizes = {k: (int(np.prod(s)) if s else 1) for k, s in state_shapes.items()}
     # ---- rates: floating point
     g = Graph()
     g.unit_us = date_unit_us
     fn = _retarget(compute_rates, g)
     t = g.leaf(("t", 0), "f")
+    model_params = list(model_params) if model_params is not None else [k for k in param_shapes if k != "__t0__"]
 
     structure = []                                   # [(state, number of transitions)] in rate-dict order
 
-    def model_inputs(graph, kind_y, tt):
+    def model_inputs(graph, kind_y, tt, strict=True):
         """(time argument, keyword arguments) as the reference passes them: a date when sim runs over dates."""
         kw = _inputs(graph, state_shapes, param_shapes, kind_y)
         when = tt
@@ -620,6 +681,20 @@ def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes, 
             for k in date_params:
                 kw[k] = SymDate(kw[k], date_unit_us)
         kw.pop("__t0__", None)
+        if tdpf:
+            states = {k: kw[k] for k in state_shapes}
+            pars = {k: kw[k] for k in param_shapes if k != "__t0__"}
+            params = dict(pars)
+            for name, f, extra in tdpf:
+                try:
+                    params[name] = _retarget(f, graph)(when, states, pars[name], **{k: params[k] for k in extra})
+                except TraceError:
+                    if strict:
+                        raise
+                    # bookkeeping graph: integer states; a function that cannot run on them leaves the parameter as it is
+                    # (apply_transitionings may not use parameters in a way that matters: its outputs must stay integral)
+            kw = dict(states)
+            kw.update({k: params[k] for k in model_params})
         return when, kw
 
     def run_rates():
@@ -672,7 +747,7 @@ def trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes, 
                 c += 1
             T[name].append(arr.reshape(tuple(state_shapes[name])) if state_shapes[name] else arr[0])
     def run_apply():
-        when2, kw2 = model_inputs(g2, "i", t2)
+        when2, kw2 = model_inputs(g2, "i", t2, strict=False)
         new = fn2(when2, tau2, T, **kw2)
         if not isinstance(new, (tuple, list)):
             new = (new,)
@@ -743,8 +818,8 @@ def emit(graph, outputs, ctype, leaf_expr, prefix="v"):
             if ctype == "int" and op == "div":
                 raise TraceError("division in integer bookkeeping")
             expr = f"{a[0]} {'+-*/'['add sub mul div'.split().index(op)]} {a[1]}"
-        elif op in ("lt", "le", "gt", "ge"):
-            lines.append(f"const bool {prefix}{i} = {a[0]} {dict(lt='<', le='<=', gt='>', ge='>=')[op]} {a[1]};")
+        elif op in ("lt", "le", "gt", "ge", "eq", "ne"):
+            lines.append(f"const bool {prefix}{i} = {a[0]} {dict(lt='<', le='<=', gt='>', ge='>=', eq='==', ne='!=')[op]} {a[1]};")
             name[i] = f"{prefix}{i}"
             continue
         elif op in ("and", "or", "not"):
@@ -860,7 +935,7 @@ extern "C" void sodm_plugin_host_rhs(double t, const double* y, const double* pa
 
 
 def jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes, tdpf_params=(), origin="",
-                date_unit_us=None, date_params=()):
+                date_unit_us=None, date_params=(), tdpf=(), model_params=None):
     """C++ translation unit of a plugin holding a jump process.  `param_shapes` must list the time-dependent parameters
     LAST (they are read from the per-step table instead of the parameter vector).
     -> (source, layout) with layout = dict(n_state, n_param, n_channel, n_draw, tdpf_offset, tdpf_count, slot_of)."""
@@ -868,7 +943,8 @@ def jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes,
     n_tdpf = len(tdpf_params)
     if n_tdpf and names[-n_tdpf:] != list(tdpf_params):
         raise ValueError("time-dependent parameters must come last in the flat parameter order")
-    tr = trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes, date_unit_us, date_params)
+    tr = trace_jump(compute_rates, apply_transitionings, state_shapes, param_shapes, date_unit_us, date_params, tdpf=tdpf,
+                    model_params=model_params)
     sizes = {k: (int(np.prod(s)) if s else 1) for k, s in param_shapes.items()}
     n_param = sum(sizes.values())
     tdpf_count = sum(sizes[k] for k in tdpf_params)
@@ -1029,9 +1105,10 @@ struct GenModel {{
 {_indent(a_lines)}
 {_indent(assign)}
     }}
-    __host__ __device__ static void propensities(const int* y, const double* par, double* a) {{
-        (void)par;
-        const double t = 0.0; (void)t;                 // SSA is refused for models whose rates use the time (supports_ssa = 0)
+    // SSA: propensities at the event time t (ssa_trajectory hands it over when USES_TIME); tabulated time-dependent parameters
+    // have been copied into par[TDPF_OFFSET ..] by the caller
+    __host__ __device__ static void propensities(const int* y, const double* par, double* a, double t = 0.0) {{
+        (void)par; (void)t;
 {_indent(d_lines)}
 {_indent(prop)}
     }}
@@ -1065,7 +1142,7 @@ extern "C" void sodm_plugin_host_apply(int* y, const int* draws) {{
     for (int d = 0; d < {n_draw}; ++d) w.n[d] = draws[d];
     ::sodm::GenModel::apply(y, w);
 }}
-extern "C" void sodm_plugin_host_propensities(const int* y, const double* par, double* a) {{ ::sodm::GenModel::propensities(y, par, a); }}
+extern "C" void sodm_plugin_host_propensities(const int* y, const double* par, double* a, double t) {{ ::sodm::GenModel::propensities(y, par, a, t); }}
 extern "C" void sodm_plugin_host_fire(int* y, int ch) {{ ::sodm::GenModel::fire(y, ch); }}
 """
     layout = {"n_state": n_state, "n_param": n_param, "n_channel": tr["n_channel"], "n_draw": n_draw,

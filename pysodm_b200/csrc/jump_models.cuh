@@ -234,8 +234,43 @@ struct InfluenzaJump {
             y[24 + a] = ip_id;
         }
     }
-    __host__ __device__ static void propensities(const int*, const double*, double*) {}
-    __host__ __device__ static void fire(int*, int) {}
+    // SSA (base.py:231-269): channels in the reference's order (state, transition, element) = S->E[4], E->Ip[4], Ip->Iud[4],
+    // Ip->Id[4], Iud->R[4], Id->R[4]; propensity = state * rate with the rates of models.py:47-55 in FP64.  par[8:24] holds
+    // the contact matrix in force at the event time (ssa_trajectory copies the table row there).
+    __host__ __device__ static void propensities(const int* y, const double* par, double* a) {
+        double x[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const double T = (double)y[g] + (double)y[4 + g] + (double)y[8 + g] + (double)y[12 + g] + (double)y[16 + g] + (double)y[20 + g];
+            x[g] = ((double)y[8 + g] + (double)y[12 + g] + 0.22 * (double)y[16 + g]) / T;
+        }
+        const double e_rate = 1.0 / par[0], inv_gamma = 1.0 / par[2], d_rate = 1.0 / par[3];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const double* N = par + 8 + 4 * g;
+            const double foi = par[1] * (N[0] * x[0] + N[1] * x[1] + N[2] * x[2] + N[3] * x[3]);
+            a[g] = (double)y[g] * foi;
+            a[4 + g] = (double)y[4 + g] * e_rate;
+            a[8 + g] = (double)y[8 + g] * (par[4 + g] * inv_gamma);
+            a[12 + g] = (double)y[8 + g] * ((1.0 - par[4 + g]) * inv_gamma);
+            a[16 + g] = (double)y[12 + g] * d_rate;
+            a[20 + g] = (double)y[16 + g] * d_rate;
+        }
+    }
+    // one event of channel ch (apply_transitionings with a one-hot transitionings dict, models.py:59-69); Im_inc is the
+    // Ip->Id count of THIS event: 1 for the age group that fired it, 0 elsewhere.  Static indices keep y[] in registers.
+    __host__ __device__ static void fire(int* y, int ch) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (ch == g)      { y[g] -= 1;      y[4 + g] += 1; }
+            if (ch == 4 + g)  { y[4 + g] -= 1;  y[8 + g] += 1; }
+            if (ch == 8 + g)  { y[8 + g] -= 1;  y[12 + g] += 1; }
+            if (ch == 12 + g) { y[8 + g] -= 1;  y[16 + g] += 1; }
+            if (ch == 16 + g) { y[12 + g] -= 1; y[20 + g] += 1; }
+            if (ch == 20 + g) { y[16 + g] -= 1; y[20 + g] += 1; }
+            y[24 + g] = ch == 12 + g ? 1 : 0;
+        }
+    }
 };
 
 }  // namespace sodm

@@ -443,10 +443,27 @@ __host__ __device__ __forceinline__ void ssa_trajectory(const JumpLaunch& L, int
     double t = L.t0;
     int j = 1;
     int64_t events = 0;
+    int tdpf_row = -1;                     // table row whose values are in par[TDPF_OFFSET ..] at the moment
     while (t < t_end) {
         if (events++ >= L.max_events) { st |= ST_MAX_STEPS; break; }
+        if constexpr (M::TDPF_COUNT > 0) {
+            // The reference calls the time-dependent parameter functions at every event time (base.py:376-380).  Functions the
+            // host could only tabulate are piecewise constant on the OPEN intervals (t0 + k tau, t0 + (k+1) tau) (checked
+            // there, base.py of this package; which side a boundary belongs to is immaterial, an event falls on one with
+            // probability zero) -- except the first event, which IS evaluated at t0 itself: entry 0 of tdpf_index holds the
+            // value at t0, entry 1 + k the value on interval k.
+            int64_t k = t == L.t0 ? 0 : 1 + (int64_t)floor((t - L.t0) / L.tau);
+            k = k < 0 ? 0 : (k >= L.n_steps ? (int64_t)L.n_steps - 1 : k);
+            const int row = L.tdpf_index[k];
+            if (row != tdpf_row) {
+                tdpf_row = row;
+#pragma unroll
+                for (int e = 0; e < M::TDPF_COUNT; ++e) par[M::TDPF_OFFSET + e] = L.tdpf_table[(int64_t)row * M::TDPF_COUNT + e];
+            }
+        }
         double a[M::NCH];
-        M::propensities(y, par, a);
+        if constexpr (functor_uses_time<M>::value) M::propensities(y, par, a, t);
+        else M::propensities(y, par, a);
         double R = 0.0;
 #pragma unroll
         for (int c = 0; c < M::NCH; ++c) R += a[c];

@@ -111,6 +111,17 @@ inline int build_jump_launch_for(const sodm_jump_args* a, JumpLaunch& L, bool& a
         }
     } else {
         if (!info.supports_ssa) return fail(SODM_EUNSUPPORTED, "sodm_jump_run: model %d has no SSA functor", a->model);
+        if (info.tdpf_count) {
+            // SSA evaluates time-dependent parameters at event times: tdpf_index[0] = row in force at t0 itself (the first
+            // event), tdpf_index[1 + k] = row in force on the open interval (t0 + k tau, t0 + (k+1) tau)
+            if (!a->tdpf_table || !a->tdpf_index || a->n_tdpf_values < 1 || a->n_tdpf_index < 1 || !(a->tau > 0.0))
+                return fail(SODM_EINVAL, "sodm_jump_run: SSA of a model with time-dependent parameters needs their table, "
+                                         "an interval index and the interval width in `tau`");
+            L.n_tdpf_values = a->n_tdpf_values;
+            L.tdpf_index = a->tdpf_index;
+            L.tdpf_table = a->tdpf_table;
+            L.n_steps = a->n_tdpf_index;
+        }
     }
     if (a->out_dtype == SODM_I32 && !aligned)
         return fail(SODM_EINVAL, "sodm_jump_run: int32 output needs tau-leap with tau = 2^-k (outputs are interpolated otherwise)");

@@ -28,7 +28,7 @@ char* error_buffer() {
         info.n_channel = M::NCH;                                                                  \
         info.tdpf_offset = M::TDPF_OFFSET;                                                        \
         info.tdpf_count = M::TDPF_COUNT;                                                          \
-        info.supports_ssa = ::sodm::functor_uses_time<M>::value ? 0 : 1;                          \
+        info.supports_ssa = 1;                                                                    \
         return info;                                                                              \
     }                                                                                             \
     extern "C" int sodm_plugin_info(sodm_model_info* out) {                                       \

@@ -25,7 +25,7 @@ static const ModelEntry kModels[MODEL_COUNT] = {
     {"sir_jump", SODM_KIND_JUMP, SirJump::NS, SirJump::NPAR, SirJump::NCH, 0, 0, 1},
     {"sir_si_jump", SODM_KIND_JUMP, SirSiJump::NS, SirSiJump::NPAR, SirSiJump::NCH, 0, 0, 1},
     {"influenza_1718_jump", SODM_KIND_JUMP, InfluenzaJump::NS, InfluenzaJump::NPAR, InfluenzaJump::NCH,
-     InfluenzaJump::TDPF_OFFSET, InfluenzaJump::TDPF_COUNT, 0},
+     InfluenzaJump::TDPF_OFFSET, InfluenzaJump::TDPF_COUNT, 1},
     {"sir_ode", SODM_KIND_ODE, 3, 2, 0, 0, 0, 0},
     {"sir_rate_ode", SODM_KIND_ODE, 3, 2, 0, 0, 0, 0},
     {"sir_si_ode", SODM_KIND_ODE, 14, 6, 0, 0, 0, 0},

@@ -24,6 +24,7 @@ struct LoglikLaunch {
     const void* traj;
     const int32_t* col_ptr;
     const int32_t* col_rows;
+    const double* col_weights;
     double t0;
     const double* t_data;
     const double* ydata;
@@ -134,12 +135,12 @@ __global__ void __launch_bounds__(LL_BLOCK) loglik_kernel(const __grid_constant_
                 for (int q = L.col_ptr[c]; q < L.col_ptr[c + 1]; ++q) {
                     const int64_t row = (int64_t)L.col_rows[q] * L.n_out;
                     const double lo = (double)traj[(row + j) * L.ld];
+                    double v = lo;
                     if (frac > 0.0) {
                         const double hi = (double)traj[(row + j + 1) * L.ld];
-                        ym += lo + (hi - lo) * frac;
-                    } else {
-                        ym += lo;
+                        v = lo + (hi - lo) * frac;
                     }
+                    ym += L.col_weights ? L.col_weights[q] * v : v;
                 }
             }
             if (!(ym == ym)) bad = true;                               // :264-265 / :282-283 raise on NaN
@@ -170,7 +171,7 @@ extern "C" int sodm_loglik(const sodm_loglik_args* a) {
     L.kind = a->kind; L.n_out = a->n_out; L.n_col = a->n_col; L.n_t = a->n_t;
     L.arg_mode = needs_arg ? a->arg_mode : SODM_ARG_NONE;
     L.n_traj = a->n_traj; L.ld = a->ld; L.traj = a->traj;
-    L.col_ptr = a->col_ptr; L.col_rows = a->col_rows;
+    L.col_ptr = a->col_ptr; L.col_rows = a->col_rows; L.col_weights = a->col_weights;
     L.t0 = a->t0; L.t_data = a->t_data; L.ydata = a->ydata; L.ll_arg = a->ll_arg;
     L.weight = a->weight; L.lp = a->lp; L.status = a->status;
     const unsigned grid = (unsigned)((a->n_traj + LL_BLOCK - 1) / LL_BLOCK);

@@ -108,6 +108,35 @@ class SimpleDataArray:
         order = [self._axis(d) for d in dims]
         return SimpleDataArray(np.transpose(self.values, order), dims, self.coords, self.name)
 
+    # -- arithmetic (what aggregation functions do to a state: scale, add up slices, weight along a dimension) ---------
+    def _binary(self, other, fn, swap=False):
+        if isinstance(other, SimpleDataArray):
+            if set(other.dims) - set(self.dims):
+                if set(self.dims) - set(other.dims):
+                    raise ValueError(f"cannot combine dims {self.dims} with {other.dims}")
+                return other._binary(self, fn, not swap)
+            # broadcast `other` (a subset of this array's dims) along the missing dimensions, by NAME as xarray does
+            o = other.transpose(*[d for d in self.dims if d in other.dims]).values
+            o = o.reshape([self.values.shape[self._axis(d)] if d in other.dims else 1 for d in self.dims])
+        else:
+            o = np.asarray(other)
+            if o.ndim > self.values.ndim:
+                raise ValueError("cannot broadcast an array with more dimensions than the DataArray")
+        vals = fn(o, self.values) if swap else fn(self.values, o)
+        return SimpleDataArray(vals, self.dims, self.coords, self.name)
+
+    def __add__(self, o): return self._binary(o, np.add)
+    def __radd__(self, o): return self._binary(o, np.add, True)
+    def __sub__(self, o): return self._binary(o, np.subtract)
+    def __rsub__(self, o): return self._binary(o, np.subtract, True)
+    def __mul__(self, o): return self._binary(o, np.multiply)
+    def __rmul__(self, o): return self._binary(o, np.multiply, True)
+    def __truediv__(self, o): return self._binary(o, np.divide)
+    def __neg__(self): return SimpleDataArray(-self.values, self.dims, self.coords, self.name)
+
+    def copy(self, deep=True):
+        return SimpleDataArray(self.values.copy() if deep else self.values, self.dims, self.coords, self.name)
+
     def __repr__(self):
         return f"<SimpleDataArray {self.name} {dict(zip(self.dims, self.values.shape))}>"
 

@@ -210,13 +210,15 @@ _LL_KIND = {"poisson": _ffi.LL_POISSON, "normal": _ffi.LL_NORMAL, "lognormal": _
 
 
 def loglik(kind, traj, t0, columns, t_data, ydata, ll_arg=None, weight=1.0, lp=None, status=None, dev=None,
-           stream=None):
+           stream=None, column_weights=None):
     """Accumulate the log-likelihood of every trajectory against one dataset (`sodm_loglik`).
 
     traj: device tensor [n_row, n_out, n_traj] (any of int32/float32/float64).
     columns: list (one entry per data column) of lists of rows of `traj` that are summed into that column.
     t_data: [n_t] data times in simulation time units.  ydata: [n_t, n_col].
-    ll_arg: None | scalar | [n_col] | [n_t, n_col].  Returns lp[n_traj] (float64 device tensor, accumulated)."""
+    ll_arg: None | scalar | [n_col] | [n_t, n_col].  column_weights: per column, the weight of each of its rows (a linear
+    aggregation function folded into the column sums); None = plain sums.
+    Returns lp[n_traj] (float64 device tensor, accumulated)."""
     dev = dev or device()
     lib = _ffi.load()
     n_row, n_out, n_traj = traj.shape
@@ -241,6 +243,13 @@ def loglik(kind, traj, t0, columns, t_data, ydata, ll_arg=None, weight=1.0, lp=N
     d_ptr, d_rows = _dev_i32(col_ptr, dev), _dev_i32(col_rows, dev)
     d_t, d_y = _dev_f64(t_data_h, dev), _dev_f64(ydata_h, dev)
     a.col_ptr, a.col_rows, a.t_data, a.ydata = d_ptr.data_ptr(), d_rows.data_ptr(), d_t.data_ptr(), d_y.data_ptr()
+    d_w = None
+    if column_weights is not None:
+        w = np.asarray([x for c in column_weights for x in c], dtype=np.float64)
+        if w.shape != col_rows.shape:
+            raise ValueError("column_weights must mirror the structure of columns")
+        d_w = _dev_f64(w, dev)
+        a.col_weights = d_w.data_ptr()
     a.t0, a.n_t = float(t0), int(n_t)
     d_arg = None
     if ll_arg is None:

@@ -14,6 +14,7 @@ The model/data alignment the reference does through xarray (:244-288) is compile
 the data are summed, :250-252), the data's time points in simulation time (linear interpolation, :254) and the
 `(time, *data_axes)` ordered data matrix (:256-259, :271-278).
 """
+import inspect
 import itertools
 from datetime import datetime
 
@@ -110,6 +111,71 @@ def log_prior_beta(x, a=None, b=None, loc=None, scale=None, weight=1):
     return weight * beta.logpdf(x, a, b, loc=loc, scale=scale)
 
 
+_AGG_FORMATS = ("Valid formats of aggregation functions are: 1) a list containing one function, 2) a list containing a number "
+                "of functions equal to the number of datasets, 3) a callable function.")
+
+
+def _validate_aggregation_function(aggregation_function, n_datasets):
+    """The reference's `validate_aggregation_function` (:1181-1225): same accepted forms, same messages."""
+    if isinstance(aggregation_function, list):
+        if len(aggregation_function) not in (n_datasets, 1):
+            raise ValueError("number of aggregation functions must be equal to one or the number of datasets")
+        if len(aggregation_function) == 1:
+            if not inspect.isfunction(aggregation_function[0]):
+                raise ValueError(_AGG_FORMATS)
+            return [aggregation_function[0]] * n_datasets
+        if not all(inspect.isfunction(f) or f is None for f in aggregation_function):
+            raise ValueError(_AGG_FORMATS)
+        return list(aggregation_function)
+    if inspect.isfunction(aggregation_function):
+        return [aggregation_function] * n_datasets
+    raise ValueError(_AGG_FORMATS)
+
+
+def linear_map_of(aggregation_function, state, shape, dims, coords, time_index):
+    """The matrix of a user aggregation function (reference :245-248: `out_copy = aggregation_function(out[states])`).
+
+    On the device the model output never becomes an xarray object, so the function cannot be CALLED per particle; what the
+    tutorials and the reference's tests do with it -- sum or weight a dimension, add up coordinate slices, rescale -- is a
+    LINEAR map of the state's cells that acts on every time point alike, and such a map is fully described by its matrix.
+    The function is therefore applied ONCE, at construction, to a DataArray whose "time" axis enumerates the unit basis of
+    the state's cells (plus an all-zero slice and two random slices); the result gives the matrix column by column, the
+    zero slice proves there is no offset, the random slices prove linearity and that time points are not mixed.  A function
+    that fails those checks is refused -- there is no host fallback.
+    -> (A[n_new_cells, n_cells], new_dims, new_coords, new_shape)"""
+    from .dataset import make_dataset
+    n_cells = int(np.prod(shape)) if shape else 1
+    rng = np.random.default_rng(20260101)
+    probe = np.zeros((n_cells + 3,) + tuple(shape))
+    flat = probe.reshape(n_cells + 3, n_cells)
+    flat[np.arange(n_cells), np.arange(n_cells)] = 1.0
+    flat[n_cells + 1:] = rng.uniform(0.5, 2.0, size=(2, n_cells))
+    when = (list(pd.date_range("2000-01-01", periods=n_cells + 3)) if time_index == "date" else np.arange(n_cells + 3))
+    arr = make_dataset({state: probe}, {state: list(dims)}, {state: list(coords)}, time_index, when, 1)[state]
+    try:
+        out = aggregation_function(arr)
+    except Exception as exc:  # noqa: BLE001
+        raise NotImplementedError(f"the aggregation function of state '{state}' failed on the probe DataArray "
+                                  f"(dims {tuple(arr.dims)}): {type(exc).__name__}: {exc}") from exc
+    if not hasattr(out, "dims") or time_index not in tuple(out.dims):
+        raise NotImplementedError(f"the aggregation function of state '{state}' must return a DataArray that keeps the "
+                                  f"'{time_index}' dimension")
+    new_dims = [d for d in out.dims if d != time_index]
+    out = out.transpose(time_index, *new_dims)
+    vals = np.asarray(out.values, dtype=np.float64)
+    if vals.shape[0] != n_cells + 3:
+        raise NotImplementedError(f"the aggregation function of state '{state}' changes the '{time_index}' axis")
+    new_shape = vals.shape[1:]
+    new_coords = [list(np.asarray(out.coords[d].values if hasattr(out.coords[d], "values") else out.coords[d])) for d in new_dims]
+    v = vals.reshape(n_cells + 3, -1)
+    A = v[:n_cells].T.copy()
+    ok = np.allclose(v[n_cells], 0.0, atol=1e-12) and np.allclose(v[n_cells + 1:], flat[n_cells + 1:] @ A.T, rtol=1e-10, atol=1e-12)
+    if not ok:
+        raise NotImplementedError(f"the aggregation function of state '{state}' is not a linear map of the state at each time "
+                                  "point (sums, weighted sums and selections are); it cannot be folded into the device likelihood")
+    return A, new_dims, new_coords, new_shape
+
+
 # ================================================================================================================
 class log_posterior_probability:
     def __init__(self, model, parameter_names, bounds, data, states, log_likelihood_fnc, log_likelihood_fnc_args,
@@ -125,9 +191,8 @@ class log_posterior_probability:
             raise ValueError(f"The number of datasets ({n}), model states ({len(states)}), log likelihood functions "
                              f"({len(log_likelihood_fnc)}), the extra arguments of the log likelihood function "
                              f"({len(log_likelihood_fnc_args)}), and weights ({len(weights)}) must be of equal length")
-        if aggregation_function:
-            raise NotImplementedError("user aggregation functions operate on xarray objects on the host; the device "
-                                      "path sums model dimensions absent from the data and nothing else")
+        # aggregation functions (reference :181-188, validate_aggregation_function :1181-1225): one per dataset or None
+        self.aggregation_function = _validate_aggregation_function(aggregation_function, n) if aggregation_function else n * [None]
         self.model, self.states, self.weights = model, list(states), [float(w) for w in weights]
         self.parameters_names = list(parameter_names)
         self.log_likelihood_fnc = list(log_likelihood_fnc)
@@ -254,6 +319,10 @@ class log_posterior_probability:
     def _build_plan(self, i):
         d, state, axes = self.data[i], self.states[i], self.additional_axes_data[i]
         r0, shape, dims, coords = self._state_rows(state)
+        A = None
+        if self.aggregation_function[i]:
+            # the data is matched against the AGGREGATED state (reference :245-252, compare_data_model_coordinates :1316-1321)
+            A, dims, coords, shape = linear_map_of(self.aggregation_function[i], state, shape, dims, coords, self.time_index)
         for ax in axes:
             if ax not in dims:
                 raise Exception(f"{i}th dataset: index level '{ax}' is not a dimension of model state '{state}' {dims}")
@@ -284,11 +353,19 @@ class log_posterior_probability:
                 if all(idx[dims.index(ax)] == k for ax, k in fixed.items()):
                     rows.append(r0 + (int(np.ravel_multi_index(idx, shape)) if shape else 0))
             columns.append(rows)
+        weights = None
+        if A is not None:
+            # `rows` above index cells of the aggregated state: column = sum over them of (row of A) . (cells of the model state)
+            cols_w = [A[[r - r0 for r in rows]].sum(axis=0) for rows in columns]
+            columns = [[r0 + int(c) for c in np.flatnonzero(w)] for w in cols_w]
+            weights = [[float(w[c]) for c in np.flatnonzero(w)] for w in cols_w]
+            if all(x == 1.0 for w in weights for x in w):
+                weights = None
         arg = self.log_likelihood_fnc_args[i]
         if arg is not None and arg.ndim > 0 and arg.shape not in ((ydata.shape[1],), ydata.shape) and arg.size != 1:
             raise ValueError(f"the extra argument of the {i}th log-likelihood function has shape {arg.shape}, "
                              f"which does not match the data {ydata.shape}")
-        return {"columns": columns, "t_data": t_data, "ydata": ydata}
+        return {"columns": columns, "weights": weights, "t_data": t_data, "ydata": ydata}
 
     # -------------------------------------------------------------------------------------------------------------
     def compute_log_prior_probability(self, thetas):
@@ -352,8 +429,9 @@ class log_posterior_probability:
         model = self.model
         kw = self.simulation_kwargs
         time_unit = kw.get("time_unit", "D")
-        if getattr(model, "_generated", False) and model._kind == "ode" and model.time_dependent_parameters:
-            # an ODE's time-dependent parameter functions are translated per time mode (numbers / dates), base.py
+        if getattr(model, "_generated", False) and model.time_dependent_parameters and (
+                model._kind == "ode" or model.device_model is None or getattr(model, "_traced_tdpfs", None)):
+            # translated time-dependent parameter functions exist per time mode (numbers / dates), base.py
             dated = self.time_index == "date"
             model._bind_generated_functor(TIME_UNIT_US[time_unit] if dated else None, [self.start_sim if dated else None])
         # parameter vector -> flat device parameter elements
@@ -367,6 +445,13 @@ class log_posterior_probability:
                 raise NotImplementedError(f"calibrated parameter '{name}' is not a parameter of the device functor")
             if name in model._spec.tdpf_params:              # tabulated per step (jump processes): no per-particle value
                 raise NotImplementedError(f"calibrated parameter '{name}' is time dependent")
+            for k_t, t_name in enumerate(model.time_dependent_parameters or {}):
+                # a TABULATED function is evaluated once for all particles (with model.parameters): a calibrated argument
+                # would silently keep its base value inside it.  Translated functions read the particle's own.
+                if model._kind == "jump" and t_name in model._spec.tdpf_params and name in model._function_parameters[k_t]:
+                    raise NotImplementedError(f"calibrated parameter '{name}' is an argument of the time-dependent parameter "
+                                              f"function of '{t_name}', which could only be tabulated "
+                                              f"({getattr(model, '_tdpf_reason', {}).get(t_name, 'hand-written functor')})")
             off = model._param_offsets[name][0]
             for e in range(size):
                 var[off + e] = columns[col + e]
@@ -388,18 +473,25 @@ class log_posterior_probability:
         for k, y in enumerate(y0_sets):
             if model._kind == "jump":
                 tau, method = kw.get("tau", 1), kw.get("method", "tau_leap")
-                tdpf = None
-                if method == "tau_leap":
-                    n_steps = int(_ffi.load().sodm_jump_n_steps(float(t0), n_out, float(tau)))
-                    # the table depends on the window and on the model's own parameter values only: one entry is kept
-                    key = (t0, n_steps, float(tau), start_date, time_unit,
-                           tuple((nm, np.asarray(v).tobytes()) for nm, v in model.parameters.items()))
-                    if getattr(self, "_tdpf_cache", (None, None))[0] != key:
-                        self._tdpf_cache = (key, model._tabulate_tdpfs(t0, n_steps, tau, start_date, time_unit))
-                    tdpf = self._tdpf_cache[1]
-                    if model._spec.tdpf_params and tdpf is None:
-                        flat = np.concatenate([model._flat_param(nm, model.parameters[nm]) for nm in model._spec.tdpf_params])
-                        tdpf = (flat[None, :], np.zeros(max(n_steps, 1), dtype=np.int32))
+                n_steps = int(_ffi.load().sodm_jump_n_steps(float(t0), n_out, float(tau))) if method == "tau_leap" else 0
+                # the table depends on the window and on the model's own parameter values only: one entry is kept
+                key = (method, t0, n_out, float(tau), start_date, time_unit,
+                       tuple((nm, np.asarray(v).tobytes()) for nm, v in model.parameters.items()))
+                if getattr(self, "_tdpf_cache", (None, None))[0] != key:
+                    from .base import _StatesTouched
+                    try:
+                        table = (model._tabulate_tdpfs(t0, n_steps, tau, start_date, time_unit) if method == "tau_leap"
+                                 else model._tabulate_tdpf_intervals(float(t0), float(t1), 1.0, start_date, time_unit))
+                    except _StatesTouched:
+                        raise NotImplementedError("a time-dependent parameter function that could only be tabulated reads the "
+                                                  f"model states: {getattr(model, '_tdpf_reason', {})}") from None
+                    self._tdpf_cache = (key, table)
+                tdpf = self._tdpf_cache[1]
+                if model._spec.tdpf_params and tdpf is None:
+                    flat = np.concatenate([model._flat_param(nm, model.parameters[nm]) for nm in model._spec.tdpf_params])
+                    tdpf = (flat[None, :], np.zeros(max(n_steps, 1), dtype=np.int32))
+                if method != "tau_leap":
+                    tau = 1.0                                 # SSA: width of a table interval (include/sodm.h)
                 # only the rows the datasets look at leave the simulator; exact integer counts when tau = 2^-k
                 which_sets = range(len(self.data)) if not self.initial_states else [k]
                 needed = sorted({r for i in which_sets for c in self._plan[i]["columns"] for r in c})
@@ -420,7 +512,8 @@ class log_posterior_probability:
                 plan = self._plan[i]
                 columns = plan["columns"] if remap is None else [[remap[r] for r in c] for c in plan["columns"]]
                 engine.loglik(self._kinds[i], traj, float(t0), columns, plan["t_data"], plan["ydata"],
-                              ll_arg=self.log_likelihood_fnc_args[i], weight=self.weights[i], lp=lp_d, status=st_ll, dev=dev)
+                              ll_arg=self.log_likelihood_fnc_args[i], weight=self.weights[i], lp=lp_d, status=st_ll, dev=dev,
+                              column_weights=plan["weights"])
         if engine.status_bits(st_ll) & _ffi.ST_NONFINITE:
             raise ValueError("simulation output contains nan, likely due to numerical unstability. try using more conservative bounds.")
         return lp_d

@@ -149,11 +149,13 @@ def build_ode(integrate, state_shapes, param_shapes, origin="", reference=None, 
 
 
 def build_jump(compute_rates, apply_transitionings, state_shapes, param_shapes, tdpf_params, example_states,
-               example_params, origin="", date_unit_us=None, date_params=(), start_date=None):
+               example_params, origin="", date_unit_us=None, date_params=(), start_date=None, tdpf=(), model_params=None):
     """`example_params`: {name: value} of every entry of `param_shapes` except the hidden `__t0__`; in date mode
-    (`date_unit_us`) the model functions see dates: `start_date` is the date of t = 0 used by the self-check."""
+    (`date_unit_us`) the model functions see dates: `start_date` is the date of t = 0 used by the self-check.
+    `tdpf`: translated time-dependent parameter functions [(name, fn, extras)] (codegen.trace_jump); `tdpf_params`: the
+    parameters that are read from the per-step table instead."""
     source, layout = codegen.jump_source(compute_rates, apply_transitionings, state_shapes, param_shapes, tdpf_params, origin,
-                                         date_unit_us=date_unit_us, date_params=date_params)
+                                         date_unit_us=date_unit_us, date_params=date_params, tdpf=tdpf, model_params=model_params)
     plug = compile_source(source, layout)
     lib = plug.lib
     lib.sodm_plugin_host_propose.restype = None
@@ -162,11 +164,11 @@ def build_jump(compute_rates, apply_transitionings, state_shapes, param_shapes, 
     lib.sodm_plugin_host_apply.restype = None
     lib.sodm_plugin_host_apply.argtypes = [C.c_void_p, C.c_void_p]
     lib.sodm_plugin_host_propensities.restype = None
-    lib.sodm_plugin_host_propensities.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sodm_plugin_host_propensities.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
     lib.sodm_plugin_host_fire.restype = None
     lib.sodm_plugin_host_fire.argtypes = [C.c_void_p, C.c_int]
     verify_jump(plug, compute_rates, apply_transitionings, state_shapes, param_shapes, example_states, example_params,
-                date_unit_us=date_unit_us, date_params=date_params, start_date=start_date)
+                date_unit_us=date_unit_us, date_params=date_params, start_date=start_date, tdpf=tdpf, model_params=model_params)
     return plug
 
 
@@ -184,14 +186,22 @@ def host_propose(plug, y, par, tau, quirk=True, t=0.0):
 
 
 def verify_jump(plug, compute_rates, apply_transitionings, state_shapes, param_shapes, states, params, tau=0.5,
-                date_unit_us=None, date_params=(), start_date=None, t=3.5):
-    """One step's probabilities (at time t) and one random bookkeeping update, generated functor vs the Python functions."""
+                date_unit_us=None, date_params=(), start_date=None, t=3.5, tdpf=(), model_params=None):
+    """One step's probabilities (at time t) and one random bookkeeping update, generated functor vs the Python functions
+    (translated time-dependent parameter functions applied first, as the reference's `func` does, base.py:376-386)."""
     lay = plug.layout
     rates_fn = codegen._python_function(compute_rates)
     apply_fn = codegen._python_function(apply_transitionings)
     kw = {k: np.asarray(states[k], dtype=np.float64) for k in state_shapes}
-    kw.update({k: params[k] for k in param_shapes if k != "__t0__"})
+    pars = {k: params[k] for k in param_shapes if k != "__t0__"}
     when = t
+    if date_unit_us is not None:
+        from datetime import timedelta
+        when = start_date + timedelta(microseconds=t * date_unit_us)
+    live = dict(pars)
+    for name, fn, extra in tdpf:
+        live[name] = codegen._python_function(fn)(when, dict(kw), pars[name], **{k: live[k] for k in extra})
+    kw.update({k: live[k] for k in (model_params if model_params is not None else pars)})
     parts = []
     for k, shape in param_shapes.items():
         if k == "__t0__":
@@ -201,9 +211,6 @@ def verify_jump(plug, compute_rates, apply_transitionings, state_shapes, param_s
         else:
             parts.append(np.ravel(np.asarray(params[k], dtype=np.float64)))
     par = np.concatenate(parts) if parts else np.zeros(0)
-    if date_unit_us is not None:
-        from datetime import timedelta
-        when = start_date + timedelta(microseconds=t * date_unit_us)
     y = _flat(states, state_shapes)
     rates = rates_fn(when, **kw)
     n, p = host_propose(plug, y, par, tau, quirk=True, t=t)

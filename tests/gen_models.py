@@ -175,3 +175,44 @@ class SeasonalSIR(JumpProcess):
 
 def make_seasonal():
     return SeasonalSIR({'S': 99000, 'I': 1000}, {'beta': 0.5, 'gamma': 0.2, 'amp': 0.6})
+
+
+# ---- jump process whose time-dependent parameter functions read the states, the time and a drawn parameter ------------
+import tdpf_jump_models as tj  # noqa: E402
+
+
+class TdpfSIR(JumpProcess):
+    states = tj.STATES
+    parameters = tj.PARAMETERS
+    compute_rates = staticmethod(tj.compute_rates)
+    apply_transitionings = staticmethod(tj.apply_transitionings)
+
+
+def make_tdpf_jump(cfg=None):
+    cfg = cfg or tj.TAU_LEAP
+    return TdpfSIR(dict(cfg['initial_states']), dict(cfg['parameters']),
+                   time_dependent_parameters={'beta': tj.feedback, 'gamma': tj.slower_recovery})
+
+
+# ---- doubly stratified SIR (reference: src/tests/test_calibration.py:571-588), for aggregation functions -----------------
+class SIRdoublestratified(ODE):
+    states = ['S', 'I', 'R']
+    parameters = ['gamma']
+    stratified_parameters = [['beta'], []]
+    dimensions = ['age_groups', 'spatial_units']
+
+    @staticmethod
+    def integrate(t, S, I, R, gamma, beta):
+        beta = np.expand_dims(beta, axis=1)
+        N = S + I + R
+        dS = -beta * S * I / N
+        dI = beta * S * I / N - gamma * I
+        dR = gamma * I
+        return dS, dI, dR
+
+
+def make_double_sir():
+    init = {"S": [[500_000 - 1, 400_000 - 5, 300_000 - 9], [250_000 - 2, 350_000 - 4, 450_000 - 8]],
+            "I": [[1, 5, 9], [2, 4, 8]]}
+    return SIRdoublestratified(init, {"gamma": 0.2, "beta": np.array([0.35, 0.3])},
+                               coordinates={'age_groups': ['0-20', '20-120'], 'spatial_units': [0, 1, 2]})

@@ -578,6 +578,95 @@ def gen_post():
     save('post.npz', **out)
 
 
+# ------------------------------------------------------------------------------------------------
+# jump processes with state- / time-dependent TDPFs, SSA with TDPFs, a drawn parameter feeding a TDPF (base.py:376-380)
+# ------------------------------------------------------------------------------------------------
+sys.path.insert(0, os.path.dirname(HERE))
+import tdpf_jump_models as tj  # noqa: E402
+
+
+class TdpfSIR(base.JumpProcess):                 # module level: the reference's process pool pickles the model
+    states = tj.STATES
+    parameters = tj.PARAMETERS
+    compute_rates = staticmethod(tj.compute_rates)
+    apply_transitionings = staticmethod(tj.apply_transitionings)
+
+
+def make_tdpf_jump(cfg):
+    return TdpfSIR(initial_states=dict(cfg['initial_states']), parameters=dict(cfg['parameters']),
+                   time_dependent_parameters={'beta': tj.feedback, 'gamma': tj.slower_recovery}), tj
+
+
+def make_influenza_small():
+    """The tutorial model on a population / 1000 (an SSA run is ~10^4 events) with its calendar contact function."""
+    flu, cf, df, start = make_influenza()
+    for k, v in flu.initial_states.items():
+        flu.initial_states[k] = np.rint(np.asarray(v, dtype=np.float64) / 1000.0)
+    flu.initial_states['Ip'] = np.array([2.0, 3.0, 6.0, 2.0])
+    flu.initial_states['E'] = np.array([2.0, 4.0, 8.0, 2.0])
+    return flu, cf, start
+
+
+def gen_tdpf_jump(n=2000, n_ssa=600, processes=8):
+    out = {}
+    # ---- tau-leap, both TDPFs; seeded single runs (oracle: bit-exact) + ensemble (device: KS)
+    m, _ = make_tdpf_jump(tj.TAU_LEAP)
+    out['tl_y0'] = flat_y0(m)
+    ys = []
+    for sd in (31, 32):
+        np.random.seed(sd)
+        ys.append(m.sim(60, N=1, tau=0.5)['y'])
+    out['tl_seeds'], out['tl_y'] = np.array([31, 32]), np.stack(ys)
+    t = time.time()
+    np.random.seed(3100)
+    res = m.sim(60, N=n, tau=0.5, processes=processes)
+    Y = np.stack([r['y'] for r in res])
+    print(f'TDPF tau-leap ensemble n={n}: {time.time() - t:.1f}s')
+    times = np.array([2, 5, 10, 15, 20, 25, 30, 40, 50, 60])
+    out['tl_times'], out['tl_sorted'] = times, np.sort(Y[:, :, times], axis=0).astype(np.int32)
+    out['tl_mean'] = Y.mean(axis=0)
+    # ---- the same with k_fb drawn per trajectory (feeds the TDPF of beta)
+    t = time.time()
+    np.random.seed(3200)
+    res = m.sim(60, N=n, tau=0.5, draw_function=tj.draw_k_fb, processes=processes)
+    Y = np.stack([r['y'] for r in res])
+    print(f'TDPF tau-leap ensemble with drawn k_fb n={n}: {time.time() - t:.1f}s')
+    out['tld_sorted'] = np.sort(Y[:, :, times], axis=0).astype(np.int32)
+    out['tld_mean'] = Y.mean(axis=0)
+    # ---- SSA, both TDPFs evaluated at event times
+    m, _ = make_tdpf_jump(tj.SSA)
+    out['ssa_y0'] = flat_y0(m)
+    ys = []
+    for sd in (41, 42):
+        np.random.seed(sd)
+        random.seed(1000 + sd)
+        ys.append(m.sim(40, N=1, method='SSA')['y'])
+    out['ssa_seeds'], out['ssa_y'] = np.array([41, 42]), np.stack(ys)
+    t = time.time()
+    np.random.seed(4100)
+    random.seed(4100)
+    res = m.sim(40, N=n_ssa, method='SSA', processes=processes)
+    Y = np.stack([r['y'] for r in res])
+    print(f'TDPF SSA ensemble n={n_ssa}: {time.time() - t:.1f}s')
+    times = np.array([2, 5, 8, 12, 16, 20, 25, 30, 40])
+    out['ssa_times'], out['ssa_ens'] = times, Y[:, :, times].astype(np.float32)
+    # ---- influenza / 1000, SSA, calendar contact function on dates (tabulated per day on the device side)
+    flu, cf, start = make_influenza_small()
+    out['flu_small_y0'] = flat_y0(flu)
+    t = time.time()
+    np.random.seed(5100)
+    random.seed(5100)
+    res = flu.sim([start, '2018-02-01'], N=n_ssa, method='SSA', processes=processes)
+    Y = np.stack([r['y'] for r in res])
+    print(f'influenza/1000 SSA ensemble n={n_ssa}: {time.time() - t:.1f}s')
+    times = np.array([3, 7, 14, 21, 28, 35, 42, 49, 56, 62])
+    out['flu_small_times'], out['flu_small_ens'] = times, Y[:, :, times].astype(np.float32)
+    out['flu_small_n_out'] = np.array(Y.shape[-1])
+    table, idx = contact_schedule(cf, start, Y.shape[-1] - 1, 1.0)
+    out['flu_small_table'], out['flu_small_day_index'] = table, idx
+    save('tdpf_jump.npz', **out)
+
+
 if __name__ == '__main__':
     what = sys.argv[1:] or ['jump_single', 'ssa', 'jump_ensemble', 'schedule', 'ode', 'loglik', 'optimizers', 'post', 'tdpf']
     for w in what:

@@ -207,7 +207,7 @@ def test_three_exits_and_bookkeeping_of_a_new_model():
     par = np.concatenate([np.ravel(np.asarray(model.parameters[k], dtype=np.float64)) for k in model._spec_params])
     a = np.empty(lay["n_channel"])
     y_i = y.astype(np.int32)
-    plug.lib.sodm_plugin_host_propensities(y_i.ctypes.data, np.concatenate([par, [0.0]]).ctypes.data, a.ctypes.data)
+    plug.lib.sodm_plugin_host_propensities(y_i.ctypes.data, np.concatenate([par, [0.0]]).ctypes.data, a.ctypes.data, 0.0)
     kw = {k: np.asarray(model.initial_states[k], dtype=np.float64) for k in model.states_names}
     rates = gm.SEIRD.compute_rates(0.0, **kw, **model.parameters)
     want = np.concatenate([np.ravel(kw[s] * np.asarray(r, dtype=np.float64)) for s, lst in rates.items() for r in lst])
@@ -306,3 +306,33 @@ def test_large_stencil_models_take_the_warp_layout():
             return out,
     irr = Irregular({"x": np.ones(64)}, {"k": 0.1}, coordinates={"i": list(range(64))})
     assert not irr.device_model.layout.get("warp")
+
+
+def test_equality_on_model_values_is_symbolic():
+    """`==` / `!=` used to be node identity, so `if I == 0:` silently traced one branch.  Both are comparisons now."""
+    from pysodm_b200.base import JumpProcess
+
+    class EqSir(JumpProcess):
+        states = ['S', 'I', 'R']
+        parameters = ['beta', 'gamma']
+
+        @staticmethod
+        def compute_rates(t, S, I, R, beta, gamma):
+            if I == 0:
+                r = 0.0 * beta
+            else:
+                r = beta * (I / (S + I + R))
+            g_ = gamma if t != 5 else 2 * gamma
+            return {'S': [r], 'I': [g_ * np.ones(1)]}
+
+        @staticmethod
+        def apply_transitionings(t, tau, transitionings, S, I, R, beta, gamma):
+            T = transitionings
+            return S - T['S'][0], I + T['S'][0] - T['I'][0], R + T['I'][0]
+    m = EqSir({'S': 990, 'I': 10}, {'beta': 0.9, 'gamma': 0.2})
+    par = np.array([0.9, 0.2])
+    q = lambda x: x / (1 + x)                                            # noqa: E731  (stay-probability quirk, single exit)
+    _, p = plugin.host_propose(m.device_model, [990, 10, 0], par, 0.5, t=3.0)
+    assert np.allclose(p, [q(1 - np.exp(-0.5 * 0.9 * 0.01)), q(1 - np.exp(-0.1))], rtol=2e-5)
+    _, p = plugin.host_propose(m.device_model, [990, 0, 10], par, 0.5, t=5.0)       # I == 0 and t == 5: the other branches
+    assert p[0] == 0.0 and np.isclose(p[1], q(1 - np.exp(-0.2)), rtol=2e-5)

@@ -286,3 +286,38 @@ def test_status_flags_are_ored_on_the_device(n):
     if n > 2:
         assert int(st.max()) & _ffi.ST_BAD_PROB == 0
     assert engine.status_bits(st[:0]) == 0
+
+
+def test_log_posterior_with_aggregation_function(td):
+    """`aggregation_function` (reference objective_functions.py:245-248; its test: src/tests/test_calibration.py:624-668): the
+    doubly stratified SIR of that test, data by age group only.  The device value must equal the reference's recipe done by
+    hand on the host: simulate, apply the function to out[state], interpolate to the data times, score."""
+    import gen_models as gm
+    from pysodm_b200.objective_functions import ll_negative_binomial, ll_normal, log_posterior_probability
+    model = gm.make_double_sir()
+    t = np.arange(0, 50, 7, dtype=float)
+    idx = pd.MultiIndex.from_product([t, ["0-20", "20-120"]], names=["time", "age_groups"])
+    rng = np.random.default_rng(3)
+    data = pd.Series(rng.gamma(2.0, 40.0, size=len(idx)), index=idx, name="cases")
+
+    def total(output):
+        return output.sum(dim="spatial_units")
+
+    def weighted(output):
+        return output.sel(spatial_units=0) + 2.0 * output.sel(spatial_units=2)
+    lpp = log_posterior_probability(model, ["beta"], [(1e-6, 1)], [data, data], ["I", "I"], [ll_negative_binomial, ll_normal],
+                                    [0.03 * np.ones(2), 25.0], start_sim=0, aggregation_function=[total, weighted],
+                                    simulation_kwargs={"rtol": 1e-9})
+    thetas = np.array([[0.35, 0.30], [0.25, 0.4], [0.5, 0.2]])
+    lp = lpp.batch(thetas.copy())
+    want = []
+    for th in thetas:
+        model.parameters["beta"] = th
+        out = model.sim(49, rtol=1e-9)
+        ll = 0.0
+        for agg, fn, arg in ((total, ll_negative_binomial, 0.03 * np.ones(2)), (weighted, ll_normal, 25.0)):
+            a = agg(out["I"])                                         # dims (time, age_groups)
+            ym = np.asarray(a.values, dtype=np.float64)[::7]          # data times are grid points
+            ll += fn(ym, data.to_numpy().reshape(len(t), 2), arg)
+        want.append(ll)
+    np.testing.assert_allclose(lp, want, rtol=1e-8)
