@@ -340,7 +340,7 @@ __host__ __device__ __forceinline__ void sample_worklist_walk(WalkRng& rng, Work
         if (dep) n -= chain;
         if (!rng.second) {
             uint32_t b[4];
-            rng.gen.next4(b);
+            rng.gen.next4_rounds<SODM_WALK_PHILOX_ROUNDS>(b);
             rng.w0 = b[0]; rng.w1 = b[1]; rng.w2 = b[2]; rng.w3 = b[3];
         }
         const uint32_t wu = rng.second ? rng.w2 : rng.w0, wv = rng.second ? rng.w3 : rng.w1;

@@ -123,10 +123,24 @@ __host__ __device__ __forceinline__ void fill_nan_from(Sys& sys, const OdeLaunch
 // ------------------------------------------------------------------------------------------------
 // scipy-faithful RK45
 // ------------------------------------------------------------------------------------------------
-template <class Sys, typename OutT>
-__host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, int64_t i, double* y) {
+// Where the stage derivatives K2 .. K6 of a step live.  K1 (= K7 of the previous step, FSAL) and K7 stay in registers;
+// K2 .. K6 are written once per attempt and read back by the later stage combinations, the 5th-order solution, the error
+// estimate and -- rarely -- the dense output, so a system with many local elements can park them in shared memory
+// (the reactor kernel: 40 of 72 live doubles per lane leave the register file, sodm_ode.cu).  Same arithmetic either way.
+template <int NL>
+struct RegisterStages {
+    double k[5][NL];
+    __host__ __device__ __forceinline__ double get(int j, int e) const { return k[j][e]; }
+    __host__ __device__ __forceinline__ void put(int j, const double* v) {
+#pragma unroll
+        for (int e = 0; e < NL; ++e) k[j][e] = v[e];
+    }
+};
+
+template <class Sys, typename OutT, class Stages>
+__host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, int64_t i, double* y, Stages& S) {
     constexpr int NL = Sys::NL;
-    double K1[NL], K2[NL], K3[NL], K4[NL], K5[NL], K6[NL], K7[NL];   // K1 = f(t, y) (FSAL) ... K7 = f(t+h, y_new)
+    double K1[NL], K7[NL], kt[NL];                                   // K1 = f(t, y) (FSAL), K7 = f(t+h, y_new); kt: a stage on its way into S
     double ytmp[NL], ynew[NL], scale[NL];
     const double rtol = fmax(L.rtol, 100.0 * DBL_EPSILON);            // validate_tol
     const double atol = L.atol;
@@ -152,10 +166,10 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
             h0 = fmin(h0, interval);
 #pragma unroll
             for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + h0 * K1[e];
-            sys.rhs(t + h0, ytmp, K2); ++nfev;
+            sys.rhs(t + h0, ytmp, kt); ++nfev;
 #pragma unroll
-            for (int e = 0; e < NL; ++e) K3[e] = K2[e] - K1[e];
-            const double d2 = rms_scaled(sys, K3, scale) / h0;
+            for (int e = 0; e < NL; ++e) kt[e] = kt[e] - K1[e];
+            const double d2 = rms_scaled(sys, kt, scale) / h0;
             const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 0.2);
             h_abs = fmin(fmin(100.0 * h0, h1), interval);
         }
@@ -182,24 +196,24 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
             // ---- rk_step ---------------------------------------------------------------------
 #pragma unroll
             for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A21) * h;
-            sys.rhs(t + (1.0 / 5.0) * h, ytmp, K2);
+            sys.rhs(t + (1.0 / 5.0) * h, ytmp, kt); S.put(0, kt);
 #pragma unroll
-            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A31 + K2[e] * DP_A32) * h;
-            sys.rhs(t + (3.0 / 10.0) * h, ytmp, K3);
+            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A31 + S.get(0, e) * DP_A32) * h;
+            sys.rhs(t + (3.0 / 10.0) * h, ytmp, kt); S.put(1, kt);
 #pragma unroll
-            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A41 + K2[e] * DP_A42 + K3[e] * DP_A43) * h;
-            sys.rhs(t + (4.0 / 5.0) * h, ytmp, K4);
-#pragma unroll
-            for (int e = 0; e < NL; ++e)
-                ytmp[e] = y[e] + (K1[e] * DP_A51 + K2[e] * DP_A52 + K3[e] * DP_A53 + K4[e] * DP_A54) * h;
-            sys.rhs(t + (8.0 / 9.0) * h, ytmp, K5);
+            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A41 + S.get(0, e) * DP_A42 + S.get(1, e) * DP_A43) * h;
+            sys.rhs(t + (4.0 / 5.0) * h, ytmp, kt); S.put(2, kt);
 #pragma unroll
             for (int e = 0; e < NL; ++e)
-                ytmp[e] = y[e] + (K1[e] * DP_A61 + K2[e] * DP_A62 + K3[e] * DP_A63 + K4[e] * DP_A64 + K5[e] * DP_A65) * h;
-            sys.rhs(t + h, ytmp, K6);
+                ytmp[e] = y[e] + (K1[e] * DP_A51 + S.get(0, e) * DP_A52 + S.get(1, e) * DP_A53 + S.get(2, e) * DP_A54) * h;
+            sys.rhs(t + (8.0 / 9.0) * h, ytmp, kt); S.put(3, kt);
 #pragma unroll
             for (int e = 0; e < NL; ++e)
-                ynew[e] = y[e] + h * (K1[e] * DP_B1 + K3[e] * DP_B3 + K4[e] * DP_B4 + K5[e] * DP_B5 + K6[e] * DP_B6);
+                ytmp[e] = y[e] + (K1[e] * DP_A61 + S.get(0, e) * DP_A62 + S.get(1, e) * DP_A63 + S.get(2, e) * DP_A64 + S.get(3, e) * DP_A65) * h;
+            sys.rhs(t + h, ytmp, kt); S.put(4, kt);
+#pragma unroll
+            for (int e = 0; e < NL; ++e)
+                ynew[e] = y[e] + h * (K1[e] * DP_B1 + S.get(1, e) * DP_B3 + S.get(2, e) * DP_B4 + S.get(3, e) * DP_B5 + S.get(4, e) * DP_B6);
             sys.rhs(t + h, ynew, K7);
             nfev += 6;
             // ---- error norm --------------------------------------------------------------------
@@ -207,7 +221,7 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
 #pragma unroll
             for (int e = 0; e < NL; ++e) {
                 const double sc = atol + fmax(fabs(y[e]), fabs(ynew[e])) * rtol;
-                const double err = (K1[e] * DP_E1 + K3[e] * DP_E3 + K4[e] * DP_E4 + K5[e] * DP_E5 + K6[e] * DP_E6 +
+                const double err = (K1[e] * DP_E1 + S.get(1, e) * DP_E3 + S.get(2, e) * DP_E4 + S.get(3, e) * DP_E5 + S.get(4, e) * DP_E6 +
                                     K7[e] * DP_E7) * h;
                 const double r = sys.active(e) ? err / sc : 0.0;
                 acc += r * r;
@@ -234,15 +248,15 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
 #pragma unroll
                 for (int e = 0; e < NL; ++e) {
                     const double q0 = K1[e];                        // P[0] = [1, ...] and P[s>0][0] = 0
-                    const double q1 = K1[e] * (-8048581381.0 / 2820520608.0) + K3[e] * (131558114200.0 / 32700410799.0) +
-                                      K4[e] * (-1754552775.0 / 470086768.0) + K5[e] * (127303824393.0 / 49829197408.0) +
-                                      K6[e] * (-282668133.0 / 205662961.0) + K7[e] * (40617522.0 / 29380423.0);
-                    const double q2 = K1[e] * (8663915743.0 / 2820520608.0) + K3[e] * (-68118460800.0 / 10900136933.0) +
-                                      K4[e] * (14199869525.0 / 1410260304.0) + K5[e] * (-318862633887.0 / 49829197408.0) +
-                                      K6[e] * (2019193451.0 / 616988883.0) + K7[e] * (-110615467.0 / 29380423.0);
-                    const double q3 = K1[e] * (-12715105075.0 / 11282082432.0) + K3[e] * (87487479700.0 / 32700410799.0) +
-                                      K4[e] * (-10690763975.0 / 1880347072.0) + K5[e] * (701980252875.0 / 199316789632.0) +
-                                      K6[e] * (-1453857185.0 / 822651844.0) + K7[e] * (69997945.0 / 29380423.0);
+                    const double q1 = K1[e] * (-8048581381.0 / 2820520608.0) + S.get(1, e) * (131558114200.0 / 32700410799.0) +
+                                      S.get(2, e) * (-1754552775.0 / 470086768.0) + S.get(3, e) * (127303824393.0 / 49829197408.0) +
+                                      S.get(4, e) * (-282668133.0 / 205662961.0) + K7[e] * (40617522.0 / 29380423.0);
+                    const double q2 = K1[e] * (8663915743.0 / 2820520608.0) + S.get(1, e) * (-68118460800.0 / 10900136933.0) +
+                                      S.get(2, e) * (14199869525.0 / 1410260304.0) + S.get(3, e) * (-318862633887.0 / 49829197408.0) +
+                                      S.get(4, e) * (2019193451.0 / 616988883.0) + K7[e] * (-110615467.0 / 29380423.0);
+                    const double q3 = K1[e] * (-12715105075.0 / 11282082432.0) + S.get(1, e) * (87487479700.0 / 32700410799.0) +
+                                      S.get(2, e) * (-10690763975.0 / 1880347072.0) + S.get(3, e) * (701980252875.0 / 199316789632.0) +
+                                      S.get(4, e) * (-1453857185.0 / 822651844.0) + K7[e] * (69997945.0 / 29380423.0);
                     ytmp[e] = y[e] + h * (q0 * x + q1 * x2 + q2 * x3 + q3 * x4);
                 }
                 store_grid<Sys, OutT>(sys, L, i, kj, ytmp);
@@ -258,6 +272,13 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
         if (L.nfev) L.nfev[i] = nfev;
         if (L.status) L.status[i] = (int32_t)st;
     }
+}
+
+// the stages in registers (thread-per-trajectory systems)
+template <class Sys, typename OutT>
+__host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, int64_t i, double* y) {
+    RegisterStages<Sys::NL> S;
+    rk45_run<Sys, OutT, RegisterStages<Sys::NL>>(sys, L, i, y, S);
 }
 
 // ------------------------------------------------------------------------------------------------

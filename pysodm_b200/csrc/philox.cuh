@@ -12,6 +12,15 @@
 
 namespace sodm {
 
+// Rounds of the tau-leap walk's generator.  Philox4x32 is "Crush-resistant" from 7 rounds on (Salmon, Moraes, Dror & Shaw,
+// SC'11, table 2: Philox4x32-7 passes the whole of BigCrush); 10 is the published default with a safety margin.  The walk
+// draws ~2 x 10^4 words per trajectory and the generator was 12.8 % of its instructions (profiles/r2_tau_leap_ncu_full.txt):
+// 7 rounds measure 108.8 against 113.3 ms per 2^20 influenza trajectories (B200, profiles/r2_variants_ab.txt).  Everything else
+// (SSA, noise, optimiser moves) keeps 10 rounds; the law is checked by the same chi-square / KS tests either way.
+#ifndef SODM_WALK_PHILOX_ROUNDS
+#define SODM_WALK_PHILOX_ROUNDS 7
+#endif
+
 struct Philox4x32 {
     uint32_t key0, key1;      // seed
     uint32_t ctr0, ctr1;      // running block counter (64 bit)
@@ -38,13 +47,15 @@ struct Philox4x32 {
     }
 
     // Generates the next block of 4 x 32 random bits and advances the counter.
-    __host__ __device__ __forceinline__ void next4(uint32_t (&out)[4]) {
+    __host__ __device__ __forceinline__ void next4(uint32_t (&out)[4]) { next4_rounds<10>(out); }
+    template <int ROUNDS>
+    __host__ __device__ __forceinline__ void next4_rounds(uint32_t (&out)[4]) {
         constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
         constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
         uint32_t c0 = ctr0, c1 = ctr1, c2 = ctr2, c3 = ctr3;
         uint32_t k0 = key0, k1 = key1;
 #pragma unroll
-        for (int r = 0; r < 10; ++r) {
+        for (int r = 0; r < ROUNDS; ++r) {
             uint32_t hi0, lo0, hi1, lo1;
             mulhilo(M0, c0, hi0, lo0);
             mulhilo(M1, c2, hi1, lo1);

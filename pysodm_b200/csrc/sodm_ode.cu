@@ -2,95 +2,164 @@
 //
 // Small systems (SIR, SIR-SI, PPBB): one thread per parameter draw, whole state + the seven RK stages in
 // registers, FP64, per-trajectory adaptive step control (lanes of a warp run their own step sequences).
-// Packed-bed reactor (8*nx coupled equations): one WARP per draw, NPL consecutive axial nodes per lane, the
-// three-point stencil through register shuffles, error norms through butterfly reductions -- every lane
-// of the warp takes the same accept/reject decisions, so a trajectory never diverges.
+// Packed-bed reactor (8*nx coupled equations): 1 / 2 / 4 WARPS per draw, one axial node per lane, the three-point
+// stencil through register shuffles (+ a shared-memory edge exchange between the warps of a draw), error norms through
+// butterfly reductions -- every lane of a draw takes the same accept/reject decisions, so a trajectory never diverges.
 // Replaces /root/reference/src/pySODM/models/base.py:950-957 (the loop over draws in `ODE.sim`) and the
 // `solve_ivp` / `_solve_discrete` calls below it (:853-855).
 #include "ode_kernels.cuh"
 
 namespace sodm {
 
-// resident blocks per SM for the reactor kernel: 248 registers / 2 blocks without the bound; measured on B200 (1e5 draws,
-// nx = 25): 330 / 294 / 310 ms at 2 / 3 / 4 blocks -- the kernel waits on FP64 dependency chains, so a third block helps
-// more than the spills cost
+// ---- packed-bed reactor: NW warps per draw, ONE axial node (8 equations) per lane ------------------------------------------
+// Round 1 gave a lane NPL = ceil(nx / 32) nodes and kept all 9 Runge-Kutta vectors in registers: 72 doubles + 19 per-draw
+// coefficients per lane at nx <= 32 (168 registers under a 3-block bound, 9 % of the executed instructions local-memory
+// spills, 12 warps per SM), 288 doubles at nx = 100 (everything spilled: 4.6 % of the FP64 peak).  Now
+//   * a lane always owns one node; a draw takes NW = 1 / 2 / 4 warps (nx <= 32 / 64 / 128); the warps of a draw exchange their
+//     edge nodes and their partial norms through shared memory, one named barrier per exchange (double-buffered), and
+//     take identical accept / reject decisions, so a draw never diverges;
+//   * the stage derivatives K2 .. K6 live in shared memory ([stage][element][thread]: conflict-free 8-byte columns), the
+//     per-draw coefficients too (read by broadcast); registers hold y, the stage input, K1 and K7: 128 registers, 4 blocks.
+constexpr int PFR_BLOCK = 128;
 #ifndef SODM_PFR_MIN_BLOCKS
-#define SODM_PFR_MIN_BLOCKS 3
+#define SODM_PFR_MIN_BLOCKS 4
 #endif
 
-// One warp per trajectory; lane l owns axial nodes l*NPL .. l*NPL+NPL-1.
-// Local element e = (phase*4 + species)*NPL + k  (phase 0 = fluid C_F, 1 = solid C_S; k = node within lane).
-template <int NPL>
-struct PfrWarpSystem {
-    static constexpr int NL = 8 * NPL;
-    PfrNode::Coef coef;
-    int nx, lane;
+struct SharedStages {                      // K2 .. K6 of this lane: element (j, e) at base[(j * 8 + e) * PFR_BLOCK]
+    double* base;
+    __device__ __forceinline__ double get(int j, int e) const { return base[(j * 8 + e) * PFR_BLOCK]; }
+    __device__ __forceinline__ void put(int j, const double* v) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) base[(j * 8 + e) * PFR_BLOCK] = v[e];
+    }
+};
+
+template <int NW>
+__device__ __forceinline__ void draw_barrier(int id) {
+    if (NW == 1) __syncwarp();
+    else if (NW * 32 == PFR_BLOCK) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(NW * 32) : "memory");
+}
+
+// Local element e = phase * 4 + species (phase 0 = fluid C_F, 1 = solid C_S) of axial node `node`.
+template <int NW>
+struct PfrBlockSystem {
+    static constexpr int NL = 8;
+    const PfrNode::Coef* coef;      // shared, one per draw
+    double* edge;                   // shared, this draw: [2 parities][NW][2 sides][4 species]
+    double* part;                   // shared, this draw: [2 parities][NW]
+    int nx, node, lane, wid, bar;   // wid = warp within the draw; bar = named barrier of the draw
+    int px, pr;                     // parities of the two exchange buffers
     __device__ __forceinline__ int n_total() const { return 8 * nx; }
-    __device__ __forceinline__ bool active(int e) const { return lane * NPL + (e % NPL) < nx; }
-    __device__ __forceinline__ bool leader() const { return lane == 0; }
-    __device__ __forceinline__ int global_index(int e) const { return (e / NPL) * nx + lane * NPL + (e % NPL); }
-    __device__ __forceinline__ double reduce(double x) const {
+    __device__ __forceinline__ bool active(int) const { return node < nx; }
+    __device__ __forceinline__ bool leader() const { return node == 0; }
+    __device__ __forceinline__ int global_index(int e) const { return e * nx + node; }
+    __device__ __forceinline__ double reduce(double x) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (NW > 1) {
+            if (lane == 0) part[pr * NW + wid] = x;
+            draw_barrier<NW>(bar);
+            x = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) x += part[pr * NW + w];     // same order in every warp: identical decisions
+            pr ^= 1;
+        }
         return x;
     }
-    __device__ __forceinline__ void rhs(double, const double* y, double* dy) const {
-        double from_left[4], from_right[4];
+    __device__ __forceinline__ void rhs(double, const double* y, double* dy) {
+        double cl[4], cr[4];
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            from_left[s] = __shfl_up_sync(0xffffffffu, y[s * NPL + NPL - 1], 1);    // last node of lane-1
-            from_right[s] = __shfl_down_sync(0xffffffffu, y[s * NPL], 1);           // first node of lane+1
+            cl[s] = __shfl_up_sync(0xffffffffu, y[s], 1);
+            cr[s] = __shfl_down_sync(0xffffffffu, y[s], 1);
         }
+        if (NW > 1) {                                            // the neighbours of a warp's edge lanes live in other warps
+            double* mine = edge + ((px * NW + wid) * 2) * 4;
+            if (lane == 0 || lane == 31) {
 #pragma unroll
-        for (int k = 0; k < NPL; ++k) {
-            const int j = lane * NPL + k;
-            double cl[4], cm[4], cr[4], cs[4], dcf[4], dcs[4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                cm[s] = y[s * NPL + k];
-                cl[s] = k > 0 ? y[s * NPL + k - 1] : from_left[s];
-                cr[s] = k < NPL - 1 ? y[s * NPL + k + 1] : from_right[s];
-                cs[s] = y[(4 + s) * NPL + k];
+                for (int s = 0; s < 4; ++s) mine[(lane == 31 ? 4 : 0) + s] = y[s];
             }
-            PfrNode::rhs(coef, j == 0, j == nx - 1, cl, cm, cr, cs, dcf, dcs);
-            const bool on = j < nx;
+            draw_barrier<NW>(bar);
+            if (lane == 0 && wid > 0) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                dy[s * NPL + k] = on ? dcf[s] : 0.0;
-                dy[(4 + s) * NPL + k] = on ? dcs[s] : 0.0;
+                for (int s = 0; s < 4; ++s) cl[s] = edge[((px * NW + wid - 1) * 2 + 1) * 4 + s];
             }
+            if (lane == 31 && wid < NW - 1) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) cr[s] = edge[((px * NW + wid + 1) * 2) * 4 + s];
+            }
+            px ^= 1;
+        }
+        double dcf[4], dcs[4];
+        PfrNode::rhs(*coef, node == 0, node == nx - 1, cl, y, cr, y + 4, dcf, dcs);
+        const bool on = node < nx;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            dy[s] = on ? dcf[s] : 0.0;
+            dy[4 + s] = on ? dcs[s] : 0.0;
         }
     }
 };
 
-template <int NPL, typename OutT>
-__global__ void __launch_bounds__(ODE_BLOCK, SODM_PFR_MIN_BLOCKS) ode_pfr_warp_kernel(const __grid_constant__ OdeLaunch L, int method) {
-    const int lane = threadIdx.x & 31;
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= L.n_traj) return;                                   // whole warps leave together
-    double par[PfrNode::NPAR];
-    load_ode_params<PfrNode::NPAR>(L, i, par);
-    PfrWarpSystem<NPL> sys{PfrNode::coefficients(par), L.nx, lane};
-    double y[8 * NPL];
+template <int NW>
+constexpr size_t pfr_smem_bytes() {
+    constexpr int draws = PFR_BLOCK / (32 * NW);
+    return (size_t)5 * 8 * PFR_BLOCK * sizeof(double) + draws * sizeof(PfrNode::Coef) +
+           draws * (2 * NW * 2 * 4 + 2 * NW) * sizeof(double);
+}
+
+template <int NW, typename OutT>
+__global__ void __launch_bounds__(PFR_BLOCK, SODM_PFR_MIN_BLOCKS) ode_pfr_warp_kernel(const __grid_constant__ OdeLaunch L, int method) {
+    extern __shared__ double pfr_smem[];
+    constexpr int DRAWS = PFR_BLOCK / (32 * NW);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = warp / NW;                                     // draw within the block
+    const int64_t i = (int64_t)blockIdx.x * DRAWS + d;
+    if (i >= L.n_traj) return;                                   // all warps of a draw leave together
+    double* stages = pfr_smem;
+    PfrNode::Coef* coefs = reinterpret_cast<PfrNode::Coef*>(pfr_smem + 5 * 8 * PFR_BLOCK);
+    double* xch = reinterpret_cast<double*>(coefs + DRAWS) + d * (2 * NW * 2 * 4 + 2 * NW);
+    PfrBlockSystem<NW> sys;
+    sys.coef = coefs + d;
+    sys.edge = xch;
+    sys.part = xch + 2 * NW * 2 * 4;
+    sys.nx = L.nx; sys.lane = lane; sys.wid = warp % NW; sys.node = sys.wid * 32 + lane;
+    sys.bar = 1 + d; sys.px = 0; sys.pr = 0;
+    if (sys.node == 0) {                                         // the draw's coefficients: formed once, read by broadcast
+        double par[PfrNode::NPAR];
+        load_ode_params<PfrNode::NPAR>(L, i, par);
+        coefs[d] = PfrNode::coefficients(par);
+    }
+    draw_barrier<NW>(sys.bar);
+    double y[8];
 #pragma unroll
-    for (int e = 0; e < 8 * NPL; ++e) {
+    for (int e = 0; e < 8; ++e) {
         y[e] = 0.0;
         if (sys.active(e)) {
             const int s = sys.global_index(e);
             y[e] = L.y0_bcast ? L.y0[s] : L.y0[(int64_t)s * L.ld_in + i];
         }
     }
-    if (method == SODM_ODE_RK45) rk45_run<PfrWarpSystem<NPL>, OutT>(sys, L, i, y);
-    else if (method == SODM_ODE_EULER) fixed_step_run<PfrWarpSystem<NPL>, OutT, false>(sys, L, i, y);
-    else fixed_step_run<PfrWarpSystem<NPL>, OutT, true>(sys, L, i, y);
+    if (method == SODM_ODE_RK45) {
+        SharedStages S{stages + threadIdx.x};
+        rk45_run<PfrBlockSystem<NW>, OutT, SharedStages>(sys, L, i, y, S);
+    } else if (method == SODM_ODE_EULER) fixed_step_run<PfrBlockSystem<NW>, OutT, false>(sys, L, i, y);
+    else fixed_step_run<PfrBlockSystem<NW>, OutT, true>(sys, L, i, y);
 }
 
-template <int NPL>
+template <int NW>
 static int launch_pfr(const OdeLaunch& L, int method, int dtype, cudaStream_t stream) {
-    const int64_t threads = L.n_traj * 32;
-    const unsigned grid = (unsigned)((threads + ODE_BLOCK - 1) / ODE_BLOCK);
-    if (dtype == SODM_F64) ode_pfr_warp_kernel<NPL, double><<<grid, ODE_BLOCK, 0, stream>>>(L, method);
-    else                   ode_pfr_warp_kernel<NPL, float><<<grid, ODE_BLOCK, 0, stream>>>(L, method);
+    constexpr int DRAWS = PFR_BLOCK / (32 * NW);
+    const unsigned grid = (unsigned)((L.n_traj + DRAWS - 1) / DRAWS);
+    const size_t smem = pfr_smem_bytes<NW>();
+    if (dtype == SODM_F64) {
+        SODM_CUDA_CHECK(cudaFuncSetAttribute(ode_pfr_warp_kernel<NW, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ode_pfr_warp_kernel<NW, double><<<grid, PFR_BLOCK, smem, stream>>>(L, method);
+    } else {
+        SODM_CUDA_CHECK(cudaFuncSetAttribute(ode_pfr_warp_kernel<NW, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ode_pfr_warp_kernel<NW, float><<<grid, PFR_BLOCK, smem, stream>>>(L, method);
+    }
     SODM_CUDA_CHECK(cudaGetLastError());
     return SODM_OK;
 }
@@ -116,7 +185,7 @@ extern "C" int sodm_ode_run(const sodm_ode_args* a) {
         case MODEL_SIR_SI_ODE:   return launch_thread<SirSiOde>(L, a->method, a->out_dtype, stream);
         case MODEL_PPBB_ODE:     return launch_thread<PpbbOde>(L, a->method, a->out_dtype, stream);
         case MODEL_PACKED_PFR_ODE:
-            if (L.nx <= 32) return launch_pfr<1>(L, a->method, a->out_dtype, stream);
+            if (L.nx <= 32) return launch_pfr<1>(L, a->method, a->out_dtype, stream);     // warps per draw
             if (L.nx <= 64) return launch_pfr<2>(L, a->method, a->out_dtype, stream);
             return launch_pfr<4>(L, a->method, a->out_dtype, stream);
     }

@@ -255,8 +255,17 @@ def test_rates_that_use_the_time_itself():
     flat = gm.SeasonalSIR({'S': 99000, 'I': 1000}, {'beta': 0.5, 'gamma': 0.2, 'amp': 0.0}).sim(100, N=n, tau=0.5, seed=3, output_dtype="int32")
     a, b = np.median(flat["I"].values[:, 6]), np.median(out["I"].values[:, 6])
     assert b > 1.5 * a, (a, b)                       # forcing starts at 1 + amp = 1.6: a visibly faster take-off
-    with pytest.raises(Exception, match="SSA"):
-        model.sim(10, N=4, method="SSA")
+    # SSA evaluates the rates at every EVENT time (base.py:392, :399): the time reaches `propensities` too.  Small population,
+    # against the oracle's SSA loop over the same Python function.
+    small = gm.SeasonalSIR({'S': 780, 'I': 20}, {'beta': 0.5, 'gamma': 0.2, 'amp': 0.6})
+    ssa = small.sim(30, N=4000, method="SSA", seed=9)
+    import random
+    np.random.seed(12)
+    random.seed(12)
+    ref_ssa = np.stack([ojump.solve_discrete(Oracle, np.array([780.0, 20.0, 0.0]), par, 0, 30, method="SSA")[1] for _ in range(200)])
+    mine_ssa = np.stack([np.moveaxis(ssa[s].values, 0, -1) for s in ("S", "I", "R")])      # [3, 31, n]
+    t_ssa = [3, 8, 15, 22, 30]
+    cases.assert_ks_ok(cases.ks_pvalues(mine_ssa[:, t_ssa], np.transpose(ref_ssa[:, :, t_ssa], (1, 2, 0))), "seasonal SIR, SSA")
     # over dates the same class takes the other branch of its compute_rates (a lockdown window between two dates)
     start = datetime(2021, 1, 1)
     dated = model.sim(["2021-01-01", "2021-04-11"], N=n, tau=0.5, seed=5, output_dtype="int32")
