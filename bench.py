@@ -617,6 +617,60 @@ def bench_c3_strong(ctx, args):
                                    "gather of chunk c overlapped with the kernel of chunk c+1; the floor is the 900 GB/s NVLink ingest of one GPU"}
         del bufs, full
         torch.cuda.empty_cache()
+    if world > 1:
+        res["fused_gather"] = _bench_fused_gather(ctx, args, draws, status, lo, n)
+    return res
+
+
+def _bench_fused_gather(ctx, args, draws, status, lo, n):
+    """The same strong-scaling step with the gather INSIDE the simulation kernel: every rank's tau-leap kernel stores each
+    output row into its own copy of the ensemble and into the 7 peers' copies over NVLink (`sodm_jump_args.out_peers`, buffers
+    mapped once through CUDA IPC by `sharding.PeerEnsemble`) -- one launch per rank and a 4-byte all-reduce as the completion
+    handshake instead of an 18 GB all-gather behind the kernel.  Gate: a peer's shard as it arrived here equals the same
+    trajectories recomputed locally, bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from pysodm_b200 import engine, sharding
+    n_total, dev, rank, world = args.n_traj, ctx.dev, ctx.rank, ctx.world
+    try:
+        ens = sharding.PeerEnsemble(N_STATE, N_OUT, n_total, torch.int32, dev)       # raises on every rank together
+    except RuntimeError as exc:                              # no peer mapping on this box: say so, keep the NCCL figure
+        return {"unavailable": str(exc)[:300]}
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def step(seed):
+        engine.jump_run("influenza_1718_jump", ctx.y0, ctx.par, n, 0, N_OUT, TAU, var=(VAR_INDEX, draws), tdpf=(ctx.table, ctx.index),
+                        seed=seed, traj_id0=lo, out_dtype=torch.int32, out=ens.local, status=status, dev=dev,
+                        out_peers=ens.peer_columns)
+        dist.all_reduce(flag)                                # completion handshake: every rank's stores have been issued and drained
+    for w in range(3):
+        step(300 + w)
+    _barrier(ctx)
+    e0, e1 = _events(2)
+    e0.record()
+    for k in range(args.steps):
+        step(5000 + k)
+    e1.record()
+    _barrier(ctx)
+    (ms,) = _max_over_ranks(ctx, [e0.elapsed_time(e1) / args.steps])
+    # gate: the next rank's shard, as its kernel wrote it into THIS GPU's memory, against a local recomputation
+    other = (rank + 1) % world
+    olo, ohi = sharding.shard_range(n_total, other, world)
+    odraws = torch.from_numpy(synthetic_draws(n_total, 1718)[:, olo:ohi].copy()).to(dev)
+    want, _ = engine.jump_run("influenza_1718_jump", ctx.y0, ctx.par, ohi - olo, 0, N_OUT, TAU, var=(VAR_INDEX, odraws),
+                              tdpf=(ctx.table, ctx.index), seed=5000 + args.steps - 1, traj_id0=olo, out_dtype=torch.int32, dev=dev)
+    same = torch.tensor([float(torch.equal(ens.full[:, :, olo:ohi], want)), float(torch.equal(ens.full[:, :, lo:lo + n], ens.local))], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    gather_bytes = (world - 1) * n * N_STATE * N_OUT * 4
+    res = {"value": n_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "launches_per_step": 1, "collectives_per_step": 1,
+           "bytes_stored_to_peers_per_gpu_per_step": int(gather_bytes), "nvlink_floor_ms": gather_bytes / 900e9 * 1e3,
+           "parity": {"what": "a peer's shard as its kernel stored it here == the same trajectories recomputed locally (bit-exact, every rank)",
+                      "pass": bool(same.min().item() == 1.0)},
+           "what": "tau-leap kernel stores every output row to its own and to the peers' ensemble buffers over NVLink (CUDA IPC "
+                   "mappings); every GPU ends with the whole 18.1 GB ensemble; 4-byte all-reduce as completion handshake"}
+    del want
+    ens.close()
+    torch.cuda.empty_cache()
     return res
 
 

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SODM_ABI_VERSION 4
+#define SODM_ABI_VERSION 5
 
 /* error codes */
 #define SODM_OK            0
@@ -78,6 +78,7 @@ extern "C" {
 #define SODM_ODE_RK4       2   /* classical fixed-step RK4 (extension; the reference has none) */
 
 #define SODM_MAX_PARAM 64      /* flat parameter elements per model */
+#define SODM_MAX_PEERS 7       /* peer destinations of a jump launch (an 8-GPU box) */
 #define SODM_MAX_STATE 64      /* flat state elements of a jump model */
 
 typedef struct sodm_model_info {
@@ -135,9 +136,28 @@ typedef struct sodm_jump_args {
     int32_t* status;            /* (device) [n_traj] SODM_ST_* bits, may be NULL */
     int64_t  max_events;        /* SSA: event budget per trajectory (0 = 2^62) */
     void*    stream;
+    void* const* out_peers;     /* (host) [n_out_peers] device pointers: further destinations with the layout of `out`
+                                   (buffers of PEER GPUs mapped into this process, see sodm_peer_enable).  Every output
+                                   element is stored to `out` and to each of them by the simulation kernel itself: the
+                                   "final gather of outputs" over NVLink happens while the trajectories run, there is no
+                                   separate collective.  NULL / 0: plain local output. */
+    int32_t  n_out_peers;       /* <= SODM_MAX_PEERS */
+    int32_t  reserved2;
 } sodm_jump_args;
 
 int sodm_jump_run(const sodm_jump_args* args);
+/* Lets kernels of the current device store into memory of `peer_device` (cudaDeviceEnablePeerAccess; "already enabled" and
+ * the device itself are not errors).  The peer buffer itself is mapped by the host framework (CUDA IPC handle). */
+int sodm_peer_enable(int peer_device);
+/* Peer-visible buffers for `out_peers`.  The one exception to "no allocation": a CUDA IPC handle names a whole cudaMalloc
+ * allocation, so the library allocates these itself.  Rank r calls sodm_peer_alloc on its device, sends the 64 handle bytes
+ * to the other processes (any host channel), and every other process maps the buffer with sodm_peer_open on ITS current
+ * device (peer access is enabled by the mapping).  Close every mapping before the owner frees the buffer. */
+#define SODM_PEER_HANDLE_BYTES 64
+int sodm_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle /* [SODM_PEER_HANDLE_BYTES] out */);
+int sodm_peer_open(const unsigned char* handle, void** ptr);
+int sodm_peer_close(void* ptr);
+int sodm_peer_free(void* ptr);
 /* Number of tau-leap steps the reference's loop `while t < t1: t = t + tau` takes (base.py:428-434). */
 int64_t sodm_jump_n_steps(double t0, int32_t n_out, double tau);
 

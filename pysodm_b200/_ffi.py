@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PYSODM_B200_LIB") or os.path.join(_HERE, "libsodm.so")     # override: tuning builds only
 
 # constants mirrored from include/sodm.h
-ABI_VERSION = 4
+ABI_VERSION = 5
 OK, EINVAL, EMODEL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4
 KIND_JUMP, KIND_ODE = 0, 1
 I32, F32, F64 = 0, 1, 2
@@ -22,6 +22,7 @@ ODE_RK45, ODE_EULER, ODE_RK4 = 0, 1, 2
 LL_POISSON, LL_NORMAL, LL_LOGNORMAL, LL_NEGBIN = 0, 1, 2, 3
 ARG_NONE, ARG_SCALAR, ARG_COLUMN, ARG_FULL = 0, 1, 2, 3
 MAX_PARAM, MAX_STATE = 64, 64
+MAX_PEERS, PEER_HANDLE_BYTES = 7, 64
 NOISE_POISSON, NOISE_GAUSSIAN_ABS, NOISE_GAUSSIAN_REL, NOISE_NEGBIN = 0, 1, 2, 3
 NOISE_ST_BAD_MEAN = 1
 MAX_RANKS = 4
@@ -44,7 +45,8 @@ class JumpArgs(C.Structure):
                 ("n_tdpf_values", C.c_int32), ("n_tdpf_index", C.c_int32),
                 ("t0", C.c_double), ("n_out", C.c_int32), ("n_sel", C.c_int32), ("tau", C.c_double),
                 ("state_sel", C.c_void_p), ("out", C.c_void_p), ("status", C.c_void_p),
-                ("max_events", C.c_int64), ("stream", C.c_void_p)]
+                ("max_events", C.c_int64), ("stream", C.c_void_p),
+                ("out_peers", C.c_void_p), ("n_out_peers", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class OdeArgs(C.Structure):
@@ -106,6 +108,11 @@ SYMBOLS = {
     "sodm_model_id": (C.c_int, [C.c_char_p]),
     "sodm_model_info_get": (C.c_int, [C.c_int, C.c_int, C.POINTER(ModelInfo)]),
     "sodm_jump_run": (C.c_int, [C.POINTER(JumpArgs)]),
+    "sodm_peer_enable": (C.c_int, [C.c_int]),
+    "sodm_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "sodm_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "sodm_peer_close": (C.c_int, [C.c_void_p]),
+    "sodm_peer_free": (C.c_int, [C.c_void_p]),
     "sodm_jump_n_steps": (C.c_int64, [C.c_double, C.c_int32, C.c_double]),
     "sodm_status_or": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "sodm_ode_run": (C.c_int, [C.POINTER(OdeArgs)]),

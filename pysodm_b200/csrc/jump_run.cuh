@@ -47,6 +47,8 @@ struct JumpLaunch {
     uint32_t compat;
     int64_t max_events;        // SSA event budget per trajectory
     int32_t lane_shift;        // tau-leap walk: a warp carries 32 >> lane_shift trajectories (small ensembles, jump_kernels.cuh)
+    int32_t n_peers;           // further destinations of every output element (peer GPUs' buffers, same layout as `out`)
+    void* peer_out[7];
 };
 
 template <class M>
@@ -73,6 +75,14 @@ __host__ __device__ __forceinline__ void emit_counts(const JumpLaunch& L, int64_
     for (int s = 0; s < M::NS; ++s) {
         if (L.out_off[s] >= 0) out[L.out_off[s]] = (OutT)y[s];
     }
+    // fused gather: the same coalesced rows go straight into the peers' buffers over NVLink (posted stores; uniform branch)
+    for (int p = 0; p < L.n_peers; ++p) {
+        OutT* peer = (OutT*)L.peer_out[p] + i + (int64_t)j * L.ld_out;
+#pragma unroll
+        for (int s = 0; s < M::NS; ++s) {
+            if (L.out_off[s] >= 0) peer[L.out_off[s]] = (OutT)y[s];
+        }
+    }
 }
 
 // value at grid time g of the straight line through (t_old, y_old), (t_new, y_new) -- np.interp's own
@@ -98,6 +108,8 @@ __host__ __device__ __forceinline__ void emit_interp(const JumpLaunch& L, int64_
             const double v = (g == t_new) ? (double)y_new[s]
                                           : lerp_np(g, t_old, t_new, (double)y_old[s], (double)y_new[s]);
             out[((int64_t)L.out_row[s] * L.n_out + j) * L.ld_out] = (OutT)v;
+            for (int p = 0; p < L.n_peers; ++p)
+                ((OutT*)L.peer_out[p] + i)[((int64_t)L.out_row[s] * L.n_out + j) * L.ld_out] = (OutT)v;
         }
     }
 }

@@ -87,6 +87,13 @@ inline int build_jump_launch_for(const sodm_jump_args* a, JumpLaunch& L, bool& a
     L.status = a->status;
     L.compat = a->compat;
     L.max_events = a->max_events > 0 ? a->max_events : ((int64_t)1 << 62);
+    if (a->n_out_peers < 0 || a->n_out_peers > SODM_MAX_PEERS || (a->n_out_peers && !a->out_peers))
+        return fail(SODM_EINVAL, "sodm_jump_run: 0 <= n_out_peers <= %d and out_peers must be given", SODM_MAX_PEERS);
+    L.n_peers = a->n_out_peers;
+    for (int p = 0; p < a->n_out_peers; ++p) {
+        if (!a->out_peers[p]) return fail(SODM_EINVAL, "sodm_jump_run: out_peers[%d] is null", p);
+        L.peer_out[p] = a->out_peers[p];
+    }
 
     aligned = false;
     if (a->method == SODM_JUMP_TAU_LEAP) {

@@ -54,6 +54,62 @@ extern "C" int sodm_init(int device) {
     return SODM_OK;
 }
 
+extern "C" int sodm_peer_enable(int peer_device) {
+    int dev = 0, count = 0;
+    SODM_CUDA_CHECK(cudaGetDevice(&dev));
+    SODM_CUDA_CHECK(cudaGetDeviceCount(&count));
+    if (peer_device < 0 || peer_device >= count) return fail(SODM_EINVAL, "sodm_peer_enable: device %d of %d", peer_device, count);
+    if (peer_device == dev) return SODM_OK;
+    int can = 0;
+    SODM_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) return fail(SODM_EUNSUPPORTED, "sodm_peer_enable: device %d cannot address device %d", dev, peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return SODM_OK; }
+    SODM_CUDA_CHECK(e);
+    return SODM_OK;
+}
+
+// Peer-visible output buffers.  A CUDA IPC handle names a whole cudaMalloc allocation, so these buffers are the one thing the
+// library allocates itself (everything else is caller-owned, include/sodm.h "Conventions").
+extern "C" int sodm_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle) {
+    if (bytes <= 0 || !ptr || !handle) return fail(SODM_EINVAL, "sodm_peer_alloc: bytes > 0, ptr and handle must be given");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SODM_PEER_HANDLE_BYTES, "sodm.h: SODM_PEER_HANDLE_BYTES");
+    void* p = nullptr;
+    SODM_CUDA_CHECK(cudaMalloc(&p, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        cudaGetLastError();
+        return fail(SODM_ECUDA, "sodm_peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, sizeof h);
+    *ptr = p;
+    return SODM_OK;
+}
+
+extern "C" int sodm_peer_open(const unsigned char* handle, void** ptr) {
+    if (!handle || !ptr) return fail(SODM_EINVAL, "sodm_peer_open: handle and ptr must be given");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    SODM_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr = p;
+    return SODM_OK;
+}
+
+extern "C" int sodm_peer_close(void* ptr) {
+    if (!ptr) return SODM_OK;
+    SODM_CUDA_CHECK(cudaIpcCloseMemHandle(ptr));
+    return SODM_OK;
+}
+
+extern "C" int sodm_peer_free(void* ptr) {
+    if (!ptr) return SODM_OK;
+    SODM_CUDA_CHECK(cudaFree(ptr));
+    return SODM_OK;
+}
+
 extern "C" int sodm_model_id(const char* name) {
     if (!name) return fail(SODM_EINVAL, "sodm_model_id: null name");
     for (int m = 0; m < MODEL_COUNT; ++m)

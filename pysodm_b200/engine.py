@@ -105,11 +105,13 @@ def _pack_var(var, n_traj, dev):
 
 def jump_run(model, y0, par, n_traj, t0, n_out, tau=0.5, method="tau_leap", var=None, tdpf=None,
              compat=_ffi.COMPAT_REFERENCE, seed=0, traj_id0=0, out_dtype=torch.float64, state_sel=None,
-             out=None, status=None, max_events=0, dev=None, stream=None):
+             out=None, status=None, max_events=0, dev=None, stream=None, out_peers=None):
     """Run n_traj jump-process trajectories (`sodm_jump_run`).
 
     model: registered functor name.  y0: [n_state] (shared) or [n_state, n_traj].  par: [n_param] host values.
     var: {flat parameter element: per-trajectory values}.  tdpf: (table[n_values, tdpf_count], step_index[n_steps]).
+    out_peers: raw device pointers (ints) of peer GPUs' buffers with the layout of `out` (`sharding.PeerEnsemble`): the kernel
+    stores every output element there as well -- the gather of the shards over NVLink happens inside the simulation.
     Returns (out[n_rows, n_out, n_traj] device tensor, status[n_traj] int32 device tensor); asynchronous.
     """
     dev = dev or device()
@@ -153,6 +155,12 @@ def jump_run(model, y0, par, n_traj, t0, n_out, tau=0.5, method="tau_leap", var=
         keep.append(sel)
     a.out, a.status, a.max_events = out.data_ptr(), status.data_ptr(), int(max_events)
     a.stream = _stream_ptr(stream)
+    if out_peers:
+        if len(out_peers) > _ffi.MAX_PEERS:
+            raise ValueError(f"at most {_ffi.MAX_PEERS} peer destinations, got {len(out_peers)}")
+        peers = (C.c_void_p * len(out_peers))(*[int(p) for p in out_peers])
+        a.out_peers, a.n_out_peers = C.cast(peers, C.c_void_p), len(out_peers)
+        keep.append(peers)
     if plug is not None:
         plug.jump_run(a)
     else:

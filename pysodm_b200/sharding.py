@@ -146,3 +146,90 @@ def order_stats_sharded(ens_local, global_ranks):
             search.run(_ffi.SELECT_PICK)
         outs.append(search.result())
     return torch.cat(outs)
+
+
+class _RawDeviceBuffer:
+    """A device allocation of libsodm (sodm_peer_alloc / sodm_peer_open) as seen by `torch.as_tensor`."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerEnsemble:
+    """The whole ensemble `[n_rows, n_out, n_total]` resident on EVERY GPU of the job, filled by the simulation kernels
+    themselves: rank r simulates columns [lo_r, hi_r) and its kernel stores each output element into its own buffer and into
+    the other ranks' buffers over NVLink (`sodm_jump_args.out_peers`).  This is the "final gather of outputs" of a sharded
+    run without a collective: the peer stores are posted while the trajectories run, so the transfer hides behind the
+    sampler instead of following it.  The buffers are allocated by libsodm (a CUDA IPC handle names a whole cudaMalloc
+    allocation) and mapped into the other processes once, at construction; the 64-byte handles travel over the job's
+    `torch.distributed` group.  One node only (NVLink / NVSwitch peers)."""
+
+    def __init__(self, n_rows, n_out, n_total, dtype=torch.int32, dev=None):
+        import ctypes as C
+        from . import _ffi, engine
+        self.lib = _ffi.load()
+        self.dev = dev or engine.device()
+        self.rank, self.world = world()
+        if self.world - 1 > _ffi.MAX_PEERS:
+            raise ValueError(f"at most {_ffi.MAX_PEERS + 1} ranks, got {self.world}")
+        self.shape = (int(n_rows), int(n_out), int(n_total))
+        self.lo, self.hi = shard_range(n_total, self.rank, self.world)
+        itemsize = torch.empty(0, dtype=dtype).element_size()
+        typestr = {torch.int32: "<i4", torch.float32: "<f4", torch.float64: "<f8"}[dtype]
+        nbytes = itemsize * self.shape[0] * self.shape[1] * self.shape[2]
+        # every rank goes through the same collectives whatever fails locally, and all ranks raise together
+        ptr, handle, error = C.c_void_p(), C.create_string_buffer(_ffi.PEER_HANDLE_BYTES), None
+        self._own, self._mapped, self.peer_columns = None, [], []      # peer_columns: column lo of every OTHER rank's buffer
+        try:
+            _ffi.check(self.lib.sodm_peer_alloc(nbytes, C.byref(ptr), handle), self.lib)
+            self._own = ptr.value
+        except _ffi.SodmError as exc:
+            error = str(exc)
+        handles = [(self.rank, torch.cuda.current_device(), handle.raw, error)]
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (self.rank, torch.cuda.current_device(), handle.raw, error))
+        error = next((e for _, _, _, e in handles if e), None)
+        if error is None:
+            try:
+                for r, device_index, raw, _ in handles:
+                    if r == self.rank:
+                        continue
+                    _ffi.check(self.lib.sodm_peer_enable(int(device_index)), self.lib)
+                    p = C.c_void_p()
+                    _ffi.check(self.lib.sodm_peer_open(raw, C.byref(p)), self.lib)
+                    self._mapped.append(p.value)
+                    self.peer_columns.append(p.value + self.lo * itemsize)
+            except _ffi.SodmError as exc:
+                error = str(exc)
+        if self.world > 1:
+            errors = [None] * self.world
+            dist.all_gather_object(errors, error)
+            error = next((e for e in errors if e), None)
+        if error is not None:
+            self._release()
+            raise RuntimeError(f"PeerEnsemble: {error}")
+        self.full = torch.as_tensor(_RawDeviceBuffer(self._own, self.shape, typestr), device=self.dev)
+        self.local = self.full[:, :, self.lo:self.hi]          # what this rank's kernel writes (row stride n_total)
+
+    def fence(self):
+        """Every rank's stores have landed everywhere: local stream drained, then a barrier of the job."""
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            dist.barrier()
+
+    def _release(self):
+        from . import _ffi
+        for p in self._mapped:
+            _ffi.check(self.lib.sodm_peer_close(p), self.lib)
+        self._mapped = []
+        if self.world > 1:
+            dist.barrier()                       # nobody still maps this rank's buffer
+        self.full = self.local = None
+        if self._own:
+            _ffi.check(self.lib.sodm_peer_free(self._own), self.lib)
+            self._own = None
+
+    def close(self):
+        self.fence()
+        self._release()

@@ -329,3 +329,58 @@ def test_lane_spread_does_not_change_results(tmp_path):
         assert r.returncode == 0, r.stderr[-2000:]
         digests.append(r.stdout.strip().splitlines()[-1])
     assert len(set(digests)) == 1, digests
+
+
+def test_peer_destinations_receive_the_same_rows(eng, golden):
+    """`sodm_jump_args.out_peers`: the kernel stores every output element to `out` and to each further destination (peer
+    GPUs' buffers in a sharded run; plain second buffers of this GPU here) -- aligned tau-leap, interpolated tau-leap, SSA."""
+    import torch
+    g = golden["jump_single"]
+    full = torch.full((28, cases.FLU_N_OUT, 2000), -1, dtype=torch.int32, device="cuda")
+    twin = [torch.full_like(full, -1) for _ in range(2)]
+    lo, n = 500, 777
+    kw = dict(tdpf=(g["flu_table"], g["flu_step_index"]), seed=99, out_dtype=torch.int32, traj_id0=lo)
+    want, _ = eng.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, n, 0, cases.FLU_N_OUT, 0.5, **kw)
+    eng.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, n, 0, cases.FLU_N_OUT, 0.5, out=full[:, :, lo:lo + n],
+                 out_peers=[t[:, :, lo:].data_ptr() for t in twin], **kw)
+    assert torch.equal(full[:, :, lo:lo + n], want)
+    for t in twin:
+        assert torch.equal(t, full) and int((t[:, :, :lo] != -1).sum()) == 0 and int((t[:, :, lo + n:] != -1).sum()) == 0
+    tdpf = (g["flu_tau03_table"], g["flu_tau03_step_index"])
+    a = torch.zeros((28, 46, 300), dtype=torch.float64, device="cuda")
+    b = torch.zeros_like(a)
+    eng.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, 300, 0, 46, 0.3, tdpf=tdpf, seed=8, out=a, out_peers=[b.data_ptr()])
+    assert torch.equal(a, b) and float(a.abs().sum()) > 0
+    s = golden["ssa"]
+    a = torch.zeros((14, 31, 256), dtype=torch.float64, device="cuda")
+    b = torch.zeros_like(a)
+    eng.jump_run("sir_si_jump", s["sirsi_small_y0"], cases.SIRSI_PAR, 256, 0, 31, method="SSA", seed=9, out=a, out_peers=[b.data_ptr()])
+    assert torch.equal(a, b) and float(a.abs().sum()) > 0
+    with pytest.raises(Exception, match="peer"):
+        eng.jump_run("sir_si_jump", s["sirsi_small_y0"], cases.SIRSI_PAR, 8, 0, 31, out_peers=[0])
+
+
+def test_fused_gather_over_peer_mappings(eng, golden, tmp_path):
+    """Two or three ranks, each simulating its shard: the kernels store straight into every rank's copy of the ensemble (CUDA
+    IPC mappings, `sharding.PeerEnsemble`) and rank 0's copy equals the single-process run bit for bit.  NCCL over distinct GPUs
+    when the box has them, else two processes sharing one GPU over gloo (the IPC mapping is the same mechanism)."""
+    import socket
+    import subprocess
+    import sys
+    import torch
+    world = 2 if torch.cuda.device_count() < 3 else 3
+    backend = "nccl" if torch.cuda.device_count() >= world else "gloo"
+    path = str(tmp_path / "peer.npz")
+    with socket.socket() as sck:
+        sck.bind(("127.0.0.1", 0))
+        port = str(sck.getsockname()[1])
+    worker = __file__.replace("test_gpu_jump.py", "dist_peer_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), str(world), port, backend, path], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+    g = golden["jump_single"]
+    want, _ = eng.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, 3001, 0, cases.FLU_N_OUT, 0.5,
+                           tdpf=(g["flu_table"], g["flu_step_index"]), seed=99, out_dtype=torch.int32)
+    assert np.array_equal(np.load(path)["full"], _cpu(want))
