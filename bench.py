@@ -186,6 +186,15 @@ def run_reference_arm(args):
     pool.close()
     n = cores * per_core * args.steps
     value = n / dt
+    # the UNMODIFIED reference beside its port: its own public call on all host cores, 8 trajectories per core
+    try:
+        from oracle import ref_stage
+        u_rate, u_dt, u_mean = ref_stage.time_unmodified(8 * cores, cores)
+        unmodified = {"value": u_rate, "unit": UNIT, "cores": cores, "kind": "reference",
+                      "sample": f"JumpProcess.sim([start, end], N={8 * cores}, tau=0.5, processes={cores}) of the unmodified reference "
+                                f"(oracle/_ref/reference, staged by build()) in {u_dt:.1f} s; mean Im_inc at the last day {u_mean:.2f}"}
+    except Exception as exc:                                  # not staged on this box: say so
+        unmodified = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
     sample = (f"{cores} processes x {per_core} trajectories x {args.steps} steps of the same workload "
               f"(oracle/jump.py: NumPy tau-leap vectorised over trajectories, reference law incl. the stay-probability "
               f"quirk, legacy NumPy binomial); the unmodified reference itself runs ~5.6 traj/s/core "
@@ -196,6 +205,7 @@ def run_reference_arm(args):
             "config": {"workload": "influenza_1718 tau-leap tau=0.5, 2017-12-01..2018-05-11, per-trajectory beta/f_ud draws",
                        "n_traj_per_step": cores * per_core},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline_unmodified": unmodified,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "configs": {"C1_sir_ode_rk45": {"value": betas.size / dt_ode, "unit": UNIT, "cores": cores,
                                             "what": "scipy.integrate.solve_ivp RK45 rtol 1e-4 on the tutorial SIR, 64 draws per core "
@@ -255,9 +265,9 @@ def _timed_launches(ctx, fn, reps=5, warm=3, flush=True):
 
 def _ks_gate(mine, ref_sorted, what):
     """Two-sample KS per (state, time) cell: mine[cells..., n] against the reference's sorted samples ref_sorted[m, cells...].
-    BASELINE bar: p > 0.01 per cell; with hundreds of correlated cells the COUNT below 0.01 is compared with the 99.9 % point of
-    Binomial(cells, 0.01) widened to 3 % of the cells (the band the committed oracle-vs-reference null runs show,
-    tests/golden/ks_null.json), and no cell may be astronomically small."""
+    BASELINE bar: p > 0.01 per cell; over hundreds of correlated cells the COUNT below 0.01 is compared with the 98.5 % point of
+    the committed same-law null (tests/golden/ks_null.npz: 200 oracle-vs-oracle pairs per model, ~4 % of the cells), or the
+    99.9 % point of Binomial(cells, 0.01) when there are few cells; no cell may fall a decade below the null's smallest p."""
     from scipy import stats
     ref = np.moveaxis(ref_sorted, 0, -1)
     a = mine.reshape(-1, mine.shape[-1])
@@ -269,10 +279,13 @@ def _ks_gate(mine, ref_sorted, what):
         ps.append(stats.ks_2samp(a[r], b[r]).pvalue)
     ps = np.asarray(ps)
     below = int((ps < 0.01).sum())
-    allowed = max(int(np.ceil(0.03 * ps.size)), int(stats.binom.isf(1e-3, ps.size, 0.01)))
+    null = np.load(os.path.join(GOLDEN, "ks_null.npz"))
+    frac = float(np.quantile(np.concatenate([null[w + "_below_001"] / float(null[w + "_cells"]) for w in ("flu", "sirsi")]), 0.985))
+    floor_p = 0.1 * float(min(null["flu_min_p"].min(), null["sirsi_min_p"].min()))
+    allowed = max(int(np.ceil(frac * ps.size)), int(stats.binom.isf(1e-3, ps.size, 0.01)))
     return {"what": what, "cells": int(ps.size), "members": [int(mine.shape[-1]), int(ref_sorted.shape[0])],
             "below_0.01": below, "allowed": allowed, "min_p": float(ps.min()) if ps.size else 1.0,
-            "pass": bool(below <= allowed and (ps.size == 0 or ps.min() > 1e-7))}
+            "pass": bool(below <= allowed and (ps.size == 0 or ps.min() > floor_p))}
 
 
 def _hbm_roofline(ctx, bytes_per_launch, ms, note=None):

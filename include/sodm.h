@@ -66,9 +66,9 @@ extern "C" {
 #define SODM_COMPAT_STAY_QUIRK      1u  /* tau-leap: reference's stay probability 1 - sum_{i<m-1} p_i (base.py:339-342) */
 #define SODM_COMPAT_SSA_FIRST_MATCH 2u  /* SSA: reaction looked up by propensity VALUE, first match wins (base.py:254) */
 #define SODM_COMPAT_REFERENCE       3u
-#define SODM_TUNE_TWO_PASS         256u  /* tuning, not semantics: the two-pass sampler (all lanes at the same draw, leftovers
-                                           afterwards; counter-based words) instead of the default per-lane walk
-                                           (csrc/jump_run.cuh); same law, different random streams */
+#define SODM_TUNE_QUEUE            256u  /* tuning, not semantics: the queue sampler (the draws of a warp's trajectories are
+                                           items any lane may work on, batched by regime; counter-based words) instead of the
+                                           per-lane walk (csrc/jump_run.cuh); same law, different random streams */
 
 /* methods */
 #define SODM_JUMP_TAU_LEAP 0

@@ -24,15 +24,26 @@ constexpr int JUMP_BLOCK = SODM_JUMP_BLOCK;
 template <class M>
 __host__ __device__ constexpr int order_words() { return (M::NDRAW * JUMP_BLOCK + 3) / 4; }
 
-// bytes of dynamic shared memory of a tau-leap block: [NDRAW][JUMP_BLOCK] draw counts | [NDRAW][JUMP_BLOCK] probabilities |
-// TDPF table (FP32) | walk sampler only: [NDRAW][JUMP_BLOCK] draw order (bytes)
+// shared-memory words of the queue sampler's item arrays (16 bits per draw and lane)
 template <class M>
-static size_t tau_leap_smem(int n_tdpf_values, bool two_pass = false) {
-    return ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)n_tdpf_values * M::TDPF_COUNT + (two_pass ? 0 : (size_t)order_words<M>())) * sizeof(float);
+__host__ __device__ constexpr int queue_words() { return M::NDRAW * JUMP_BLOCK; }
+
+// bytes of dynamic shared memory of a tau-leap block: [NDRAW][JUMP_BLOCK] draw counts | [NDRAW][JUMP_BLOCK] probabilities |
+// TDPF table (FP32) | walk sampler: [NDRAW][JUMP_BLOCK] draw order (bytes); queue sampler: [warp][2 * NDRAW * 32] items (16 bits)
+template <class M>
+static size_t tau_leap_smem(int n_tdpf_values, bool queue = false) {
+    return ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)n_tdpf_values * M::TDPF_COUNT + (size_t)(queue ? queue_words<M>() : order_words<M>())) * sizeof(float);
 }
 
-template <class M, typename OutT, bool ALIGNED, bool TWO_PASS>
-__global__ void __launch_bounds__(JUMP_BLOCK, SODM_WALK_MIN_BLOCKS) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
+// The same kernel is compiled for two register budgets (results are identical, the arithmetic is the same): MINB = 8 resident
+// blocks per SM (64 registers, some spills) for launches that fill the GPU, where resident warps buy issue slots, and
+// MINB = 5 (96 registers, no spills) for launches of at most one wave, whose duration is ONE warp's chain of dependent
+// instructions from the first step to the last -- there the spills only lengthen that chain (B200, influenza, 168 steps,
+// profiles/r2_small_launches.txt: 12 500 trajectories 4.66 -> 3.93 ms, 1024: 3.54 -> 2.92 ms; 10^6: 108.7 -> 112.7 ms).
+constexpr int LATENCY_MIN_BLOCKS = 5;
+
+template <class M, typename OutT, bool ALIGNED, bool QUEUE, int MINB>
+__global__ void __launch_bounds__(JUMP_BLOCK, MINB) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WorkList w;
@@ -42,7 +53,8 @@ __global__ void __launch_bounds__(JUMP_BLOCK, SODM_WALK_MIN_BLOCKS) tau_leap_ker
     w.lane = lane;
     float* table = smem + 2 * M::NDRAW * JUMP_BLOCK;
     const int n_tab = L.n_tdpf_values * M::TDPF_COUNT;
-    w.ord = TWO_PASS ? nullptr : reinterpret_cast<uint8_t*>(table + n_tab) + warp * 32;
+    w.ord = QUEUE ? nullptr : reinterpret_cast<uint8_t*>(table + n_tab) + warp * 32;
+    w.queue = QUEUE ? reinterpret_cast<uint16_t*>(table + n_tab) + warp * (2 * M::NDRAW * 32) : nullptr;
     for (int e = threadIdx.x; e < n_tab; e += blockDim.x) table[e] = (float)L.tdpf_table[e];   // ABI speaks FP64, rates are FP32
     __syncthreads();
     // small ensembles leave warp slots idle: spreading the trajectories over more warps (32 >> lane_shift per warp) shortens
@@ -52,7 +64,7 @@ __global__ void __launch_bounds__(JUMP_BLOCK, SODM_WALK_MIN_BLOCKS) tau_leap_ker
     const bool active = lane < lanes_used && i < L.n_traj;
     w.lanes = __ballot_sync(0xffffffffu, active);
     if (w.lanes == 0u) return;                                    // whole warp past the end
-    tau_leap_trajectory<M, OutT, ALIGNED, TWO_PASS>(L, i, active, table, w);
+    tau_leap_trajectory<M, OutT, ALIGNED, QUEUE>(L, i, active, table, w);
 }
 
 template <class M, typename OutT>
@@ -82,6 +94,22 @@ static int pick_lane_shift(int64_t n_traj) {
     return shift;
 }
 
+static int device_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms = v;
+    }
+    return sms;
+}
+// SODM_LATENCY_BUILD=0 in the environment keeps every launch on the 8-blocks-per-SM build (A/B measurements, tests)
+static bool latency_build_disabled() {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("SODM_LATENCY_BUILD"); off = e && *e == '0' ? 1 : 0; }
+    return off == 1;
+}
+
 static unsigned spread_grid(int64_t n_traj, int lane_shift) {
     const int64_t warps = (n_traj + (32 >> lane_shift) - 1) / (32 >> lane_shift);
     return (unsigned)((warps + JUMP_BLOCK / 32 - 1) / (JUMP_BLOCK / 32));
@@ -90,13 +118,18 @@ static unsigned spread_grid(int64_t n_traj, int lane_shift) {
 template <class M, typename OutT>
 static int launch_jump(const JumpLaunch& L0, int method, bool aligned, cudaStream_t stream) {
     JumpLaunch L = L0;
-    const bool two_pass = (L.compat & TUNE_TWO_PASS) != 0u;
+    const bool queue = (L.compat & TUNE_QUEUE) != 0u;
     L.lane_shift = method == SODM_JUMP_TAU_LEAP ? pick_lane_shift(L.n_traj) : 0;
     const unsigned grid = spread_grid(L.n_traj, L.lane_shift);
     if (method == SODM_JUMP_TAU_LEAP) {
-        const size_t smem = tau_leap_smem<M>(L.n_tdpf_values, two_pass);
-        void (*kernel)(JumpLaunch) = aligned ? (two_pass ? tau_leap_kernel<M, OutT, true, true> : tau_leap_kernel<M, OutT, true, false>)
-                                             : (two_pass ? tau_leap_kernel<M, OutT, false, true> : tau_leap_kernel<M, OutT, false, false>);
+        const size_t smem = tau_leap_smem<M>(L.n_tdpf_values, queue);
+        // the queue sampler exists in the 96-register build only (at 64 registers it spills in its batch loop: 155 vs 118 ms)
+        constexpr int T = SODM_WALK_MIN_BLOCKS, Q = LATENCY_MIN_BLOCKS;
+        const bool one_wave = (int64_t)grid <= (int64_t)device_sm_count() * LATENCY_MIN_BLOCKS && !latency_build_disabled();
+        void (*kernel)(JumpLaunch);
+        if (queue) kernel = aligned ? tau_leap_kernel<M, OutT, true, true, Q> : tau_leap_kernel<M, OutT, false, true, Q>;
+        else if (one_wave) kernel = aligned ? tau_leap_kernel<M, OutT, true, false, Q> : tau_leap_kernel<M, OutT, false, false, Q>;
+        else kernel = aligned ? tau_leap_kernel<M, OutT, true, false, T> : tau_leap_kernel<M, OutT, false, false, T>;
         SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         kernel<<<grid, JUMP_BLOCK, smem, stream>>>(L);
     } else {

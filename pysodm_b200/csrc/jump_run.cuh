@@ -19,7 +19,7 @@ namespace sodm {
 constexpr int MAX_PARAM = 64;   // flat parameter elements passed by value
 constexpr int MAX_STATE = 64;   // flat state elements of a jump model
 
-enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, TUNE_TWO_PASS = 256u };
+enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, TUNE_QUEUE = 256u };
 
 struct JumpLaunch {
     int64_t n_traj;            // trajectories in this launch
@@ -124,7 +124,8 @@ __host__ __device__ __forceinline__ void emit_interp(const JumpLaunch& L, int64_
 struct WorkList {
     int* n;             // warp base pointers: element (d, lane) at [d * stride + lane]
     float* p;
-    uint8_t* ord;       // the order in which this lane takes its draws, [q * stride + lane] -> slot
+    uint8_t* ord;       // walk: the order in which this lane takes its draws, [q * stride + lane] -> slot
+    uint16_t* queue;    // queue sampler: the warp's item array, 2 * NDRAW * 32 entries
     int stride;
     int lane;
     unsigned lanes;     // device: lanes of the warp that run a trajectory
@@ -206,119 +207,204 @@ __host__ __device__ __forceinline__ int chain_taken(const WorkList& w, int d) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// TWO-PASS SAMPLER (opt-in: SODM_TUNE_TWO_PASS; same law, different random streams).
+// QUEUE SAMPLER (SODM_TUNE_QUEUE; same law as the walk, different random streams).
 //
 // In a divergent SIMT loop the warp pays (trips) x (union of the branches any lane takes).  The per-lane walk below lets every
 // lane work through its own draw list, so with 32 lanes at different draws in different regimes the warp executes inversion
-// at 6 lanes, the exact test at 8 lanes and the BTRS candidate at 25 on almost every trip -- 17.4 of 32 lanes per instruction
-// (profiles/r1_mufu_tau_leap_ncu_full.txt).  This sampler attacks that with a uniform first pass:
-//   pass 1  ALL lanes make ONE attempt at draw d, for d = 0 .. NDRAW-1 in turn: every lane at the same draw, hence (the
-//           trajectories of an ensemble resemble each other) almost always in the same regime.  A rejected attempt sets bit d
-//           of the lane's `todo` mask; with SODM_PASS1_PARK an undecided candidate is parked instead of tested (bit d of `park`).
-//           A draw that is conditional on an unfinished one (DEP_MASK) is postponed (todo, marked by ~n).
-//   pass 2  the leftovers, a few per lane: each lane repeatedly takes its lowest open draw -- parked ones first -- and makes
-//           a full attempt including the exact test; a parked draw re-runs its pass-1 attempt from the same words, which
-//           recreates the candidate instead of storing it.  The warp leaves when no lane has an open draw.
-// Random words are COUNTER-BASED per attempt: Philox2x32-10 keyed by the launch, counter = (trajectory, step, draw, attempt
-// number), so what a lane draws does not depend on its warp neighbours, on the launch geometry or on the number of GPUs,
-// and nothing random is ever stored.  Rejection sampling stays exact under this schedule: every attempt uses words nobody
-// has looked at before, and whether it is accepted depends on its own words only.
-// MEASURED (B200, influenza, 2^20 trajectories, profiles/r2_sampler_ab.txt): 121.6 ms against 116.9 ms for the walk.  Lanes per
-// instruction rise (17 -> 21) but the instruction count does not fall: every pass-1 iteration still executes the union of
-// inversion + candidate + exact test (237 warp instructions per draw), and pass 2 runs for as many trips as the unluckiest
-// lane has leftovers (14.5 per step at 13 lanes).  Parking the exact test (SODM_PASS1_PARK) and a first version that deferred
-// parked candidates inside a walk (X trips voted by ballot) measured 136 / 129 ms.  What these schedules save in divergence
-// they pay in bookkeeping; the walk stays the default and this sampler stays as a second, independently written schedule
-// of the same law for the parity tests.
+// at 7 lanes, the exact test at 8 lanes and the BTRS candidate at 26 on almost every trip -- 17.9 of 32 lanes per instruction,
+// 423 thread-slots per variate of which 234 do work (profiles/r2_tau_leap_ncu_full.txt).  Round 2's first attempt (all lanes
+// at the same draw, leftovers afterwards) raised the lanes per instruction but still executed the union of the regimes on
+// every trip (121.7 against 108.8 ms).  This sampler separates the REGIMES instead of the draws:
+//   * the (n, p) of all draws of the warp's trajectories sit in shared memory ([slot][lane]); a draw is an ITEM
+//     (slot, lane, attempt number) of 16 bits and any lane may work on any item;
+//   * classification (one uniform pass over the slots) settles the trivial draws and pushes the others on two stacks in the
+//     warp's queue array: sequential inversion from the bottom, BTRS from the top (ballot + popc give the positions);
+//   * the inversion stack is drained 32 items at a time -- every lane in the inversion loop;
+//   * then BTRS: a batch pops 32 items, every lane draws a candidate and runs the box test -- all lanes in the same code.
+//     Accepted candidates are stored; rejected ones go back on the BTRS stack with the next attempt number; undecided ones go
+//     on the EXACT stack (bottom of the array, free by now).  When 32 undecided items have gathered (or nothing else is
+//     left) a batch re-creates their candidates from the same words and runs the exact test on all lanes.
+//   * draws conditional on another draw (DEP_MASK) form further LEVELS: level l starts when level l - 1 is final.
+// With fewer than 32 trajectories per warp (small ensembles, lane_shift) the idle lanes work on their neighbours' items: a
+// trajectory's 24 draws are spread over the warp.
+// Random words are COUNTER-BASED per attempt: Philox2x32 keyed by the launch, counter = (trajectory, step, slot, attempt
+// number), so what an item draws does not depend on which lane handles it, on its warp neighbours, on the launch geometry
+// or on the number of GPUs.  Rejection sampling stays exact under any schedule: every attempt uses words nobody has looked at
+// before, and whether it is accepted depends on its own words only.
 // ------------------------------------------------------------------------------------------------------------------
-#ifndef SODM_PASS1_UNROLL
-#define SODM_PASS1_UNROLL 2
-#endif
-constexpr int PASS1_UNROLL = SODM_PASS1_UNROLL;
-#ifndef SODM_PASS1_PARK
-#define SODM_PASS1_PARK 0                // 1: pass 1 postpones the exact test (parks the candidate) instead of running it
+#ifndef SODM_QUEUE_PHILOX_ROUNDS
+#define SODM_QUEUE_PHILOX_ROUNDS 10
 #endif
 
 // Coordinates of an attempt -> Philox2x32 counter.  c0 = low 32 bits of the global trajectory id; c1 = step (16 bits) |
-// draw (6) | attempt (6) | bits 32..35 of the trajectory id; steps beyond 2^16 move into the key (warp-uniform).
+// slot (6) | attempt (6) | bits 32..35 of the trajectory id; steps beyond 2^16 move into the key (warp-uniform).
 struct AttemptKey {
     uint32_t key;       // launch key (+ high bits of the step)
-    uint32_t c0;        // trajectory, low word
-    uint32_t c1;        // (step & 0xffff) << 16 | trajectory bits 32..35
-    __host__ __device__ __forceinline__ void set(uint64_t seed, uint64_t traj, uint32_t step) {
+    uint32_t step16;    // (step & 0xffff) << 16
+    uint64_t traj0;     // global id of the trajectory of lane 0 of this warp
+    __host__ __device__ __forceinline__ void set(uint64_t seed, uint64_t traj_lane0, uint32_t step) {
         key = fold_seed(seed) + (step >> 16) * 0x9E3779B1u;
-        c0 = (uint32_t)traj;
-        c1 = (step << 16) | (uint32_t)((traj >> 32) & 15u);
+        step16 = step << 16;
+        traj0 = traj_lane0;
     }
-    __host__ __device__ __forceinline__ void words(int d, uint32_t attempt, uint32_t& wu, uint32_t& wv) const {
-        philox2x32_10(key, c0, c1 | ((uint32_t)d << 10) | (attempt << 4), wu, wv);
+    __host__ __device__ __forceinline__ void words(int l, int d, uint32_t attempt, uint32_t& wu, uint32_t& wv) const {
+        const uint64_t t = traj0 + (uint64_t)l;
+        philox2x32<SODM_QUEUE_PHILOX_ROUNDS>(key, (uint32_t)t, step16 | ((uint32_t)d << 10) | (attempt << 4) | (uint32_t)((t >> 32) & 15u), wu, wv);
     }
 };
 constexpr int64_t MAX_TRAJ_ID = (int64_t)1 << 36;
 
-template <int NDRAW> struct draw_mask { using type = typename std::conditional<(NDRAW <= 32), uint32_t, uint64_t>::type; };
-
+// chain position of every slot: 0 for an independent draw, l for the l-th draw conditional on it (bit d of DEP_MASK)
 template <int NDRAW, uint64_t DEP_MASK>
-__host__ __device__ __forceinline__ void sample_worklist_2pass(const AttemptKey& key, WorkList& w, uint32_t& st) {
-    static_assert(NDRAW <= 64, "at most 64 draws per step");
-    using Mask = typename draw_mask<NDRAW>::type;
-    constexpr Mask ONE = 1;
-    const int S = w.stride, lane = w.lane;
-    Mask todo = 0, park = 0;
-    // ---- pass 1: one attempt per draw, all lanes at the same draw -------------------------------------------------------
-#pragma unroll PASS1_UNROLL
-    for (int d = 0; d < NDRAW; ++d) {
-        int n = w.n[d * S + lane];
-        const float p = w.p[d * S + lane];
-        if ((DEP_MASK >> d) & 1ull) {                               // uniform branch: the same d on every lane
-            if (((todo | park) >> (d - 1)) & ONE) {                 // the exit before this one is not final yet
-                w.n[d * S + lane] = ~n;
-                todo |= ONE << d;
-                continue;
-            }
-            n -= chain_taken<DEP_MASK>(w, d);
-            w.n[d * S + lane] = n;
-        }
-        uint32_t wu, wv;
-        key.words(d, 0u, wu, wv);
-        int k;
-        const int state = binomial_attempt<!SODM_PASS1_PARK>(n, p, wu, wv, k);
-        if (state == BIN_DONE) {
-            if (k < 0) { st |= ST_BAD_PROB; k = 0; }
-            w.n[d * S + lane] = k;
-        } else if (state == BIN_RETRY) {
-            todo |= ONE << d;
-        } else {
-            park |= ONE << d;
+struct DrawLevels {
+    int level[NDRAW] = {};
+    int n_levels = 1;
+    uint64_t mask[4] = {};          // slots of level 0..3
+    constexpr DrawLevels() {
+        for (int d = 0; d < NDRAW; ++d) {
+            level[d] = ((DEP_MASK >> d) & 1ull) ? level[d - 1] + 1 : 0;
+            if (level[d] + 1 > n_levels) n_levels = level[d] + 1;
+            if (level[d] < 4) mask[level[d]] |= 1ull << d;
         }
     }
-    // ---- pass 2: leftovers ------------------------------------------------------------------------------------------------
-    uint32_t round = 0u;
-    for (;;) {
-        const Mask m = park != 0 ? park : todo;
-        if (coop_ballot(m != 0) == 0u) break;
-        const uint32_t attempt = park != 0 ? 0u : 1u + round % 63u;  // a parked draw repeats its pass-1 attempt (and settles it)
-        ++round;
-        if (m != 0) {
-            const int d = low_bit(m);
-            int n = w.n[d * S + lane];
-            const float p = w.p[d * S + lane];
-            if (n < 0) {                                            // postponed conditional draw: its predecessors are final
-                n = ~n - chain_taken<DEP_MASK>(w, d);               // by now (they have lower bits and were taken first)
-                w.n[d * S + lane] = n;
+};
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ int coop_rank(unsigned m, int lane) { return __popc(m & ((1u << lane) - 1u)); }
+__device__ __forceinline__ void coop_sync() { __syncwarp(); }
+constexpr int COOP_WIDTH = 32;
+#else
+constexpr int COOP_WIDTH = 1;
+inline int coop_rank(unsigned, int) { return 0; }                  // CPU harness: a "warp" of one lane runs the same algorithm
+inline void coop_sync() {}
+#endif
+
+// item = slot << 5 | lane | attempt << 11
+__host__ __device__ __forceinline__ uint32_t next_attempt(uint32_t item) {
+    // 5 bits of attempt number; an item rejected 31 times in a row (probability < 1e-18) continues on numbers 16..31
+    return (item >> 11) == 31u ? ((item & 0x7ffu) | (16u << 11)) : item + (1u << 11);
+}
+
+template <int NDRAW, uint64_t DEP_MASK>
+__host__ __device__ __forceinline__ void sample_worklist_queue(const AttemptKey& key, WorkList& w, bool active, uint32_t& st) {
+    static_assert(NDRAW <= 64, "at most 64 draws per step");
+    constexpr DrawLevels<NDRAW, DEP_MASK> LV{};
+    static_assert(LV.n_levels <= 4, "at most 3 conditional draws in a row");
+    constexpr int CAP = NDRAW * COOP_WIDTH, WIDTH = COOP_WIDTH;
+    const int S = w.stride, lane = w.lane;
+    uint16_t* Q = w.queue;
+#pragma unroll 1
+    for (int lvl = 0; lvl < LV.n_levels; ++lvl) {
+        const uint64_t slots = lvl == 0 ? LV.mask[0] : (lvl == 1 ? LV.mask[1] : (lvl == 2 ? LV.mask[2] : LV.mask[3]));
+        // ---- first attempt in place: every lane takes slot d of its OWN trajectory -- the trajectories of an ensemble resemble
+        // each other, so the lanes are almost always in the same regime.  Trivial draws and accepted BTRS candidates are
+        // final; the rest becomes items on three stacks: inversion (bottom of the first half of the array, upwards), rejected
+        // candidates (top of the first half, downwards, attempt 1), undecided candidates (second half).  An item is on one
+        // stack at a time, so the first two cannot meet.
+        int nI = 0, nB = 0, nE = 0;
+        constexpr int MID = CAP;
+#pragma unroll 1
+        for (uint64_t todo = slots; todo != 0; todo &= todo - 1) {
+            const int d = low_bit(todo);
+            int state = BIN_DONE;
+            bool retry = false, undecided = false;
+            if (active) {
+                int n = w.n[d * S + lane];
+                const float p = w.p[d * S + lane];
+                if (lvl > 0) {                                      // the earlier exits of this compartment element are final
+                    n -= chain_taken<DEP_MASK>(w, d);
+                    w.n[d * S + lane] = n;
+                }
+                int k;
+                state = binomial_classify(n, p, k);
+                if (state == BIN_BTRS) {
+                    const bool flip = p > 0.5f;
+                    const float pp = flip ? 1.0f - p : p;
+                    uint32_t wu, wv;
+                    key.words(lane, d, 0u, wu, wv);
+                    int kk;
+                    BtrsHat hat;
+                    int s2 = btrs_candidate(n, pp, wu, wv, kk, hat);
+                    if (s2 == BIN_SQUEEZE && n < 16777216 && (float)n * pp >= 0.9f * SODM_F32_MODE_LIMIT) {
+                        float lhs;
+                        s2 = btrs_squeeze(n, pp, kk, hat, lhs);
+                    }
+                    retry = s2 == BIN_RETRY;
+                    undecided = s2 == BIN_SQUEEZE || s2 == BIN_EXACT;
+                    k = flip ? n - kk : kk;
+                    if (s2 == BIN_DONE) state = BIN_DONE;
+                }
+                if (state == BIN_DONE) {
+                    if (k < 0) { st |= ST_BAD_PROB; k = 0; }
+                    w.n[d * S + lane] = k;
+                }
             }
-            uint32_t wu, wv;
-            key.words(d, attempt, wu, wv);
-            int k;
-            const int state = binomial_attempt<true>(n, p, wu, wv, k);
-            park &= ~(ONE << d);
-            if (state == BIN_DONE) {
-                if (k < 0) { st |= ST_BAD_PROB; k = 0; }
-                w.n[d * S + lane] = k;
-                todo &= ~(ONE << d);
-            } else {
-                todo |= ONE << d;
+            const unsigned mI = coop_ballot(state == BIN_INVERT), mR = coop_ballot(retry), mE = coop_ballot(undecided);
+            const uint32_t item = (uint32_t)((d << 5) | lane);
+            if (state == BIN_INVERT) Q[nI + coop_rank(mI, lane)] = (uint16_t)item;
+            if (retry) Q[CAP - 1 - (nB + coop_rank(mR, lane))] = (uint16_t)(item | (1u << 11));
+            if (undecided) Q[MID + nE + coop_rank(mE, lane)] = (uint16_t)item;
+            nI += coop_popc(mI);
+            nB += coop_popc(mR);
+            nE += coop_popc(mE);
+        }
+        coop_sync();
+        // ---- sequential inversion, 32 items at a time ------------------------------------------------------------------------
+        for (int base = 0; base < nI; base += WIDTH) {
+            if (base + lane < nI) {
+                const uint32_t item = Q[base + lane];
+                const int d = (int)(item >> 5) & 63, l = (int)item & 31;
+                const int n = w.n[d * S + l];
+                const float p = w.p[d * S + l];
+                const bool flip = p > 0.5f;
+                uint32_t wu, wv;
+                key.words(l, d, 0u, wu, wv);
+                const int kk = binomial_inversion_word(n, flip ? 1.0f - p : p, wu);
+                w.n[d * S + l] = flip ? n - kk : kk;
             }
+        }
+        coop_sync();
+        // ---- leftovers: rejected candidates and exact tests ---------------------
+        while (nB > 0 || nE > 0) {
+            const bool candidates = nB >= WIDTH || (nB > 0 && nE < WIDTH);
+            const int have = candidates ? nB : nE;
+            const int take = have < WIDTH ? have : WIDTH;
+            const bool mine = lane < take;
+            uint32_t item = 0u;
+            if (mine) item = candidates ? Q[CAP - nB + lane] : Q[MID + nE - take + lane];
+            if (candidates) nB -= take; else nE -= take;
+            coop_sync();                                            // the popped entries have been read before anything is pushed
+            bool retry = false, undecided = false;
+            if (mine) {
+                const int d = (int)(item >> 5) & 63, l = (int)item & 31;
+                const int n = w.n[d * S + l];
+                const float p = w.p[d * S + l];
+                const bool flip = p > 0.5f;
+                const float pp = flip ? 1.0f - p : p;
+                uint32_t wu, wv;
+                key.words(l, d, item >> 11, wu, wv);
+                int kk;
+                BtrsHat hat;
+                int state = btrs_candidate(n, pp, wu, wv, kk, hat);
+                if (candidates) {
+                    // large modes, whose exact test is the FP64 routine, pass the squeeze first (it settles 98 % there)
+                    if (state == BIN_SQUEEZE && n < 16777216 && (float)n * pp >= 0.9f * SODM_F32_MODE_LIMIT) {
+                        float lhs;
+                        state = btrs_squeeze(n, pp, kk, hat, lhs);
+                    }
+                    retry = state == BIN_RETRY;
+                    undecided = state == BIN_SQUEEZE || state == BIN_EXACT;
+                } else {
+                    retry = !btrs_exact_accept(n, pp, kk, btrs_lhs(hat));
+                }
+                if (!retry && !undecided) w.n[d * S + l] = flip ? n - kk : kk;
+            }
+            const unsigned mR = coop_ballot(retry), mE = coop_ballot(undecided);
+            if (retry) Q[CAP - 1 - (nB + coop_rank(mR, lane))] = (uint16_t)next_attempt(item);
+            if (undecided) Q[MID + nE + coop_rank(mE, lane)] = (uint16_t)item;
+            nB += coop_popc(mR);
+            nE += coop_popc(mE);
+            coop_sync();
         }
     }
 }
@@ -375,7 +461,7 @@ template <class M> struct functor_uses_time<M, decltype((void)M::USES_TIME)> { s
 
 // One trajectory per lane.  `active` = the lane owns a trajectory; the remaining lanes of a partially filled warp
 // still take part in the warp's votes (they have no draws to make) but neither load nor store.
-template <class M, typename OutT, bool ALIGNED, bool TWO_PASS>
+template <class M, typename OutT, bool ALIGNED, bool QUEUE>
 __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L, int64_t i, bool active,
                                                              const float* table, WorkList w) {
     double par[M::NPAR];
@@ -391,7 +477,7 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
     const bool quirk = (L.compat & COMPAT_STAY_QUIRK) != 0u;
     const float tau = (float)L.tau;
     const typename M::Pre pre = M::prepare(par, tau, quirk);
-    AttemptKey akey;                       // counter-based words of the two-pass sampler
+    AttemptKey akey;                       // counter-based words of the queue sampler
     WalkRng wrng;                          // private Philox4x32 stream of the walk
     wrng.gen.init(L.seed, (uint64_t)(L.traj_id0 + i));
     wrng.w0 = wrng.w1 = wrng.w2 = wrng.w3 = 0u;
@@ -410,9 +496,9 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
         const float* tab = M::TDPF_COUNT ? table + (int64_t)L.tdpf_index[k] * M::TDPF_COUNT : table;
         if constexpr (functor_uses_time<M>::value) M::propose(y, pre, tab, tau, quirk, w, ALIGNED ? L.t0 + (double)k * L.tau : t);
         else M::propose(y, pre, tab, tau, quirk, w);
-        if constexpr (TWO_PASS) {
-            akey.set(L.seed, (uint64_t)(L.traj_id0 + i), (uint32_t)k);
-            sample_worklist_2pass<M::NDRAW, (uint64_t)M::DEP_MASK>(akey, w, st);
+        if constexpr (QUEUE) {
+            akey.set(L.seed, (uint64_t)(L.traj_id0 + i - w.lane), (uint32_t)k);
+            sample_worklist_queue<M::NDRAW, (uint64_t)M::DEP_MASK>(akey, w, active, st);
         } else {
             if (k == 0) reorder_draws<M::NDRAW, (uint64_t)M::DEP_MASK>(w);
             sample_worklist_walk<M::NDRAW, (uint64_t)M::DEP_MASK>(wrng, w, st);

@@ -75,10 +75,11 @@ struct Philox4x32 {
 // 32-bit key, half the work of a 4x32 block.  The tau-leap sampler calls it once per ATTEMPT with the attempt's
 // coordinates (trajectory, step, draw, attempt number) as the counter, so the words of an attempt do not depend on what
 // any other lane or any other draw is doing (jump_run.cuh).
-__host__ __device__ __forceinline__ void philox2x32_10(uint32_t key, uint32_t c0, uint32_t c1, uint32_t& o0, uint32_t& o1) {
+template <int ROUNDS>
+__host__ __device__ __forceinline__ void philox2x32(uint32_t key, uint32_t c0, uint32_t c1, uint32_t& o0, uint32_t& o1) {
     constexpr uint32_t M = 0xD256D193u, W = 0x9E3779B9u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         uint32_t hi, lo;
         Philox4x32::mulhilo(M, c0, hi, lo);
         c0 = hi ^ key ^ c1;
@@ -87,6 +88,10 @@ __host__ __device__ __forceinline__ void philox2x32_10(uint32_t key, uint32_t c0
     }
     o0 = c0;
     o1 = c1;
+}
+
+__host__ __device__ __forceinline__ void philox2x32_10(uint32_t key, uint32_t c0, uint32_t c1, uint32_t& o0, uint32_t& o1) {
+    philox2x32<10>(key, c0, c1, o0, o1);
 }
 
 // 32-bit key of a launch's tau-leap streams from the 64-bit seed (splitmix64 finaliser, folded)

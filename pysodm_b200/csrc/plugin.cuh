@@ -43,7 +43,7 @@ char* error_buffer() {
         const int rc = ::sodm::build_jump_launch_for(a, L, aligned, plugin_info());               \
         if (rc != SODM_OK) return rc;                                                             \
         if (a->n_traj == 0) return SODM_OK;                                                       \
-        if (a->compat & ::sodm::TUNE_TWO_PASS)                                                 \
+        if (a->compat & ::sodm::TUNE_QUEUE)                                                 \
             return ::sodm::fail(SODM_EUNSUPPORTED, "generated models use the default sampler only"); \
         return ::sodm::launch_plugin_jump<M>(L, a->method, aligned, a->out_dtype, (cudaStream_t)a->stream); \
     }                                                                                             \
@@ -193,9 +193,12 @@ static int launch_plugin_jump(const JumpLaunch& L0, int method, bool aligned, in
     } else {
         const size_t smem = tau_leap_smem<M>(L.n_tdpf_values);
         void (*kernel)(JumpLaunch) = nullptr;
-        if (aligned && dtype == SODM_I32) kernel = tau_leap_kernel<M, int32_t, true, false>;
-        else if (aligned && dtype == SODM_F64) kernel = tau_leap_kernel<M, double, true, false>;
-        else if (!aligned && dtype == SODM_F64) kernel = tau_leap_kernel<M, double, false, false>;
+        constexpr int T = SODM_WALK_MIN_BLOCKS;
+        // launches of at most one wave of the posterior path (int32, aligned grid) take the 96-register build (jump_kernels.cuh)
+        const bool one_wave = (int64_t)grid <= (int64_t)device_sm_count() * LATENCY_MIN_BLOCKS && !latency_build_disabled();
+        if (aligned && dtype == SODM_I32) kernel = one_wave ? tau_leap_kernel<M, int32_t, true, false, LATENCY_MIN_BLOCKS> : tau_leap_kernel<M, int32_t, true, false, T>;
+        else if (aligned && dtype == SODM_F64) kernel = tau_leap_kernel<M, double, true, false, T>;
+        else if (!aligned && dtype == SODM_F64) kernel = tau_leap_kernel<M, double, false, false, T>;
         else return fail(SODM_EUNSUPPORTED, "generated models write int32 (tau = 2^-k) or float64 output");
         if (smem > 200 * 1024) return fail(SODM_EUNSUPPORTED, "model needs %zu bytes of shared memory per block", smem);
         SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 96 * 1024 ? smem : 96 * 1024)));

@@ -39,18 +39,36 @@ def ks_pvalues(a, b):
     return ps.reshape(a.shape[:-1])
 
 
-def assert_ks_ok(ps, what, p_single=0.01, min_global=1e-4):
-    """The parity bar (BASELINE.json): KS p > 0.01 per (state, time).  With hundreds of cells a few p-values
-    below 0.01 occur by chance under the null (1 % of them), and the cells are strongly CORRELATED (the same
-    trajectories seen at neighbouring times / in coupled compartments), so chance failures come in clusters:
-    pinned-oracle-vs-pinned-oracle runs of the same size show 0.5-4 % of cells below 0.01.  The test therefore
-    requires (i) the NUMBER below 0.01 to stay within that null band (4 % of the cells, or the 99.9 % point of
-    Binomial(cells, 0.01) when there are few cells; a wrong law -- e.g. dropping the stay-probability quirk -- fails
-    > 90 % of the cells) and (ii) no cell to be astronomically small."""
+_NULL_FRACTION = None
+
+
+def null_fraction(level=0.985):
+    """Fraction of (state, time) cells below p = 0.01 that a SAME-LAW comparison stays under with probability `level`, from
+    the committed null fixture tests/golden/ks_null.npz (tests/golden/make_ks_null.py: 200 independent pairs of 20 000-member
+    ensembles of the pinned oracle per model, same states / output times as the parity fixtures; pooled over the influenza
+    and SIR_SI models).  The null is NOT Binomial(cells, 0.01): the cells are strongly correlated (the same trajectories at
+    neighbouring times, coupled compartments), so most replicates have 0-2 cells below 0.01 and a few have a whole cluster
+    (influenza: up to 22 of 224; SIR_SI: 4 of 200 replicates with 36-46 of 84)."""
+    global _NULL_FRACTION
+    if _NULL_FRACTION is None:
+        import os
+        d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ks_null.npz"))
+        frac = np.concatenate([d[w + "_below_001"] / float(d[w + "_cells"]) for w in ("flu", "sirsi")])
+        _NULL_FRACTION = (float(np.quantile(frac, level)), float(min(d["flu_min_p"].min(), d["sirsi_min_p"].min())))
+    return _NULL_FRACTION
+
+
+def assert_ks_ok(ps, what, p_single=0.01):
+    """The parity bar (BASELINE.json): KS p > 0.01 per (state, time).  Over hundreds of correlated cells some p-values fall
+    below 0.01 under the null itself, in clusters; how many is MEASURED, not argued: the allowance is the 98.5 % point of the
+    committed oracle-vs-oracle null (`null_fraction`, ~4 % of the cells), or the 99.9 % point of Binomial(cells, 0.01) when
+    there are few cells -- i.e. a correct sampler fails a test with probability ~1.5 %, while a wrong law (dropping the
+    stay-probability quirk, say) fails > 90 % of the cells.  No cell may fall a decade below the smallest p-value the null
+    fixture has seen over 200 x 308 cells (1.5e-4)."""
     from scipy import stats
     ps = np.asarray(ps).ravel()
     n_fail = int(np.sum(ps < p_single))
-    # allowed = the larger of 4 % of the cells (clustered chance failures) and the 99.9 % point of Binomial(cells, 1 %)
-    allowed = max(int(np.ceil(0.04 * ps.size)), int(stats.binom.isf(1e-3, ps.size, p_single)))
+    frac, null_min_p = null_fraction()
+    allowed = max(int(np.ceil(frac * ps.size)), int(stats.binom.isf(1e-3, ps.size, p_single)))
     assert n_fail <= allowed, f"{what}: {n_fail} of {ps.size} KS tests have p < {p_single} (allowed {allowed})"
-    assert ps.min() > min_global / max(1, ps.size) * 10, f"{what}: min KS p-value {ps.min():.3e} over {ps.size} cells"
+    assert ps.min() > 0.1 * null_min_p, f"{what}: min KS p-value {ps.min():.3e} over {ps.size} cells"

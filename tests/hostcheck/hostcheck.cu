@@ -22,9 +22,10 @@ static void run_host(const JumpLaunch& L, int method, bool aligned) {
         int wn[M::NDRAW];
         float wp[M::NDRAW];
         uint8_t ord[M::NDRAW];
-        WorkList w{wn, wp, ord, 1, 0, 1u};
+        uint16_t queue[2 * M::NDRAW];
+        WorkList w{wn, wp, ord, queue, 1, 0, 1u};
         if (method == SODM_JUMP_TAU_LEAP) {
-            const bool two_pass = (L.compat & TUNE_TWO_PASS) != 0u;
+            const bool two_pass = (L.compat & TUNE_QUEUE) != 0u;
             if (aligned) { if (two_pass) tau_leap_trajectory<M, OutT, true, true>(L, i, true, table.data(), w);
                            else          tau_leap_trajectory<M, OutT, true, false>(L, i, true, table.data(), w); }
             else         { if (two_pass) tau_leap_trajectory<M, OutT, false, true>(L, i, true, table.data(), w);
@@ -85,7 +86,7 @@ extern "C" void hc_binomial_words(uint64_t seed, uint64_t traj, int32_t n, float
         for (uint32_t a = 0; state != BIN_DONE; ++a) {
             ++tries;
             uint32_t wu, wv;
-            key.words(3, a % 64u, wu, wv);
+            key.words(0, 3, a % 64u, wu, wv);
             if (force_word && c == 0 && a == 0) wu = force_word;
             state = binomial_attempt<false>(n, p, wu, wv, k);
             if (state == BIN_EXACT) state = binomial_attempt<true>(n, p, wu, wv, k);

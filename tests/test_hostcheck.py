@@ -143,6 +143,24 @@ def test_tau_leap_influenza_law(golden):
     assert (tot == tot[:, :1, :]).all()
 
 
+def test_queue_sampler_law_on_the_host(golden):
+    """The queue sampler (SODM_TUNE_QUEUE: regime-separated batches, counter-based words per attempt) run as a warp of ONE lane:
+    same law as the reference, population conserved, shard invariant."""
+    g, e = golden["jump_single"], golden["jump_ensemble"]
+    kw = dict(tdpf=(g["flu_table"], g["flu_step_index"]), out_dtype=np.int32, seed=6, compat=3 | 256)
+    out, st = hc.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, 12000, 0, cases.FLU_N_OUT, 0.5, **kw)
+    assert (st == 0).all()
+    ref = np.transpose(e["flu_ens"], (1, 2, 0))
+    cases.assert_ks_ok(cases.ks_pvalues(out[:, e["flu_times"], :], ref), "queue sampler (host) vs reference ensemble")
+    tot = out[:24].reshape(6, 4, cases.FLU_N_OUT, -1).sum(axis=0)
+    assert (tot == tot[:, :1, :]).all() and out.min() >= 0
+    part, _ = hc.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, 50, 0, cases.FLU_N_OUT, 0.5, traj_id0=300, **kw)
+    assert np.array_equal(part, out[:, :, 300:350])
+    out, _ = hc.jump_run("sir_si_jump", g["sirsi_y0"], cases.SIRSI_PAR, 12000, 0, 121, 0.5, out_dtype=np.int32, compat=3 | 256)
+    cases.assert_ks_ok(cases.ks_pvalues(out[:, e["sirsi_times"], :], np.transpose(e["sirsi_ens"], (1, 2, 0))),
+                       "queue sampler, SIR_SI (host) vs reference ensemble")
+
+
 def test_tau_leap_sir_si_law(golden):
     g, e = golden["jump_single"], golden["jump_ensemble"]
     out, st = hc.jump_run("sir_si_jump", g["sirsi_y0"], cases.SIRSI_PAR, 12000, 0, 121, 0.5, out_dtype=np.int32)

@@ -10,7 +10,7 @@ cap() {  # name, kernel regex, launches to skip, command...
     ncu -i gpurun_out/r2_$name.ncu-rep --page raw --csv 2>/dev/null | gzip > gpurun_out/r2_$name.raw.csv.gz
     ncu -i gpurun_out/r2_$name.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/r2_$name.source.csv.gz
     python tools/summarize_ncu.py gpurun_out/r2_$name.ncu-rep "$@" > gpurun_out/r2_$name.summary.txt 2>&1
-    if [ $name = tau_leap ]; then python tools/summarize_profile.py gpurun_out/r2_$name.ncu-rep 262144 gpurun_out/r2_tau_leap_ncu_full.txt > /dev/null 2>&1; fi
+    if [ $name = tau_leap ] || [ $name = queue ]; then python tools/summarize_profile.py gpurun_out/r2_$name.ncu-rep 262144 gpurun_out/r2_${name}_ncu_full.txt "$LABEL" 48 > /dev/null 2>&1; fi
     rm -f gpurun_out/r2_$name.ncu-rep
     tail -n 1 gpurun_out/r2_ncu_$name.log
 }
@@ -18,6 +18,7 @@ want=${@:-tau_leap sirsi pfr25 pfr100 sir_ode ssa loglik}
 for w in $want; do
   case $w in
     tau_leap) cap tau_leap tau_leap 2 python tools/profile_kernel.py 262144 ;;
+    queue)    cap queue tau_leap 2 python tools/profile_kernel.py 262144 259 ;;
     sirsi)    cap sirsi tau_leap 1 python tools/profile_configs.py sirsi ;;
     pfr25)    cap pfr25 ode_pfr 1 python tools/profile_configs.py pfr25 ;;
     pfr100)   cap pfr100 ode_pfr 1 python tools/profile_configs.py pfr100 1024 ;;

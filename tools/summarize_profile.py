@@ -9,6 +9,7 @@ import sys
 
 rep, n, out_txt = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 label = sys.argv[4] if len(sys.argv) > 4 else ""
+top = int(sys.argv[5]) if len(sys.argv) > 5 else 24
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -78,7 +79,7 @@ for s in sections:
         tot += ie
 agg.sort(reverse=True)
 txt += "\nper source line (share of executed warp instructions, average active lanes):\n"
-for ie, te, f, ln, text in agg[:24]:
+for ie, te, f, ln, text in agg[:top]:
     txt += f"{ie / tot:6.2%} lanes={te / max(ie, 1):5.1f} {f}:{ln}  {text}\n"
 open(out_txt, "w").write(txt)
 json.dump({"source": f"{out_txt} (ncu --set full, {n} trajectories, default kernel)", "warp_inst_per_traj": inst / n,
