@@ -7,19 +7,57 @@ namespace sodm {
 
 constexpr int ODE_BLOCK = 128;
 
+// RK45 output windows (ode_run.cuh, rk45_run_windowed): systems of at most ODE_WINDOW_MAX_N equations park W grid points per
+// thread in shared memory and store them warp-wide; W = as many as fit in ODE_WINDOW_BYTES per block, at most 16 (a lane that
+// runs ahead of its warp waits at most one window, so a longer window buys nothing).  Larger systems keep the direct stores:
+// with one or two points per window the lanes would step in lockstep per grid point.
+constexpr int ODE_WINDOW_MAX_N = 8;
+constexpr int ODE_WINDOW_BYTES = 64 * 1024;
+template <class M>
+__host__ __device__ constexpr int ode_window() {
+    if (M::N > ODE_WINDOW_MAX_N) return 0;
+    const int w = ODE_WINDOW_BYTES / (M::N * ODE_BLOCK * (int)sizeof(double));
+    return w > 16 ? 16 : w;
+}
+
 template <class M, typename OutT>
 __global__ void __launch_bounds__(ODE_BLOCK) ode_thread_kernel(const __grid_constant__ OdeLaunch L, int method) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < L.n_traj) ode_thread_trajectory<M, OutT>(L, method, i);
+    if (i < L.n_traj) ode_thread_trajectory<M, OutT, ode_window<M>() == 0>(L, method, i);
+}
+
+// the same for RK45 with windowed output: every thread of the block takes part in the warp-wide stores, owner of a trajectory or not
+#ifndef SODM_ODE_WINDOWED_MIN_BLOCKS
+#define SODM_ODE_WINDOWED_MIN_BLOCKS 4      // 128 registers; measured on C1 at 4 x 10^6 draws: 11.5 ms unbounded (162 registers), 10.0 ms at 4, 13.4 ms at 5
+#endif
+template <class M, typename OutT>
+__global__ void __launch_bounds__(ODE_BLOCK, SODM_ODE_WINDOWED_MIN_BLOCKS) ode_thread_rk45_windowed_kernel(const __grid_constant__ OdeLaunch L) {
+    extern __shared__ double ode_window_smem[];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    ode_thread_trajectory_windowed<M, OutT>(L, i, i < L.n_traj, ode_window_smem + threadIdx.x, ode_window<M>(), ODE_BLOCK);
+}
+
+template <class M, typename OutT>
+static int launch_thread_dtype(const OdeLaunch& L, int method, cudaStream_t stream) {
+    const unsigned grid = (unsigned)((L.n_traj + ODE_BLOCK - 1) / ODE_BLOCK);
+    if constexpr (ode_window<M>() > 0) {
+        if (method == SODM_ODE_RK45) {
+            constexpr int smem = ode_window<M>() * M::N * ODE_BLOCK * (int)sizeof(double);
+            SODM_CUDA_CHECK(cudaFuncSetAttribute(ode_thread_rk45_windowed_kernel<M, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            ode_thread_rk45_windowed_kernel<M, OutT><<<grid, ODE_BLOCK, smem, stream>>>(L);
+            SODM_CUDA_CHECK(cudaGetLastError());
+            return SODM_OK;
+        }
+    }
+    ode_thread_kernel<M, OutT><<<grid, ODE_BLOCK, 0, stream>>>(L, method);
+    SODM_CUDA_CHECK(cudaGetLastError());
+    return SODM_OK;
 }
 
 template <class M>
 static int launch_thread(const OdeLaunch& L, int method, int dtype, cudaStream_t stream) {
-    const unsigned grid = (unsigned)((L.n_traj + ODE_BLOCK - 1) / ODE_BLOCK);
-    if (dtype == SODM_F64) ode_thread_kernel<M, double><<<grid, ODE_BLOCK, 0, stream>>>(L, method);
-    else                   ode_thread_kernel<M, float><<<grid, ODE_BLOCK, 0, stream>>>(L, method);
-    SODM_CUDA_CHECK(cudaGetLastError());
-    return SODM_OK;
+    if (dtype == SODM_F64) return launch_thread_dtype<M, double>(L, method, stream);
+    return launch_thread_dtype<M, float>(L, method, stream);
 }
 
 }  // namespace sodm

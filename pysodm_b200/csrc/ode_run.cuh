@@ -79,12 +79,14 @@ struct OdeLaunch {
 // kept grid index of grid point g, or -1
 __host__ __device__ __forceinline__ int kept_index(const OdeLaunch& L, int g) {
     if (L.out_last_only) return g == L.n_out - 1 ? 0 : -1;
+    if (L.out_stride == 1) return g;                                  // (a runtime integer division is ~25 instructions)
     return (g % L.out_stride) == 0 ? g / L.out_stride : -1;
 }
 
 // smallest kept grid index >= g (n_out if there is none): lets the output loops jump over grid points that are not kept
 __host__ __device__ __forceinline__ int next_kept(const OdeLaunch& L, int g) {
     if (L.out_last_only) return g <= L.n_out - 1 ? L.n_out - 1 : L.n_out;
+    if (L.out_stride == 1) return g < L.n_out ? g : L.n_out;
     const int r = g % L.out_stride;
     const int k = r == 0 ? g : g + (L.out_stride - r);
     return k < L.n_out ? k : L.n_out;
@@ -137,23 +139,29 @@ struct RegisterStages {
     }
 };
 
-template <class Sys, typename OutT, class Stages>
-__host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, int64_t i, double* y, Stages& S) {
-    constexpr int NL = Sys::NL;
-    double K1[NL], K7[NL], kt[NL];                                   // K1 = f(t, y) (FSAL), K7 = f(t+h, y_new); kt: a stage on its way into S
-    double ytmp[NL], ynew[NL], scale[NL];
-    const double rtol = fmax(L.rtol, 100.0 * DBL_EPSILON);            // validate_tol
-    const double atol = L.atol;
-    const double t_bound = L.t0 + (double)(L.n_out - 1);
-    double t = L.t0;
-    uint32_t st = ST_OK;
-    int nfev = 0;
-    int g = 0;                                                        // next grid point to emit
+// The pieces of scipy's RK45 (`RungeKutta.__init__` -> select_initial_step, `_step_impl`, `RkDenseOutput`), shared by the two
+// drivers below: the same arithmetic in the same order whichever driver runs it.
+template <class Sys, class Stages>
+struct Rk45 {
+    static constexpr int NL = Sys::NL;
+    double K1[NL], K7[NL];           // K1 = f(t, y) (FSAL), K7 = f(t + h, y_new)
+    double ynew[NL];
+    double rtol, atol, t_bound, t, h_abs, h, t_new;
+    int nfev;
+    uint32_t st;
 
-    sys.rhs(t, y, K1); ++nfev;
-    // ---- select_initial_step -------------------------------------------------------------------
-    double h_abs;
-    {
+    // RungeKutta.__init__: f(t0, y0) and select_initial_step
+    __host__ __device__ __forceinline__ void init(Sys& sys, const OdeLaunch& L, const double* y) {
+        double kt[NL], ytmp[NL], scale[NL];
+        rtol = fmax(L.rtol, 100.0 * DBL_EPSILON);                    // validate_tol
+        atol = L.atol;
+        t_bound = L.t0 + (double)(L.n_out - 1);
+        t = L.t0;
+        st = ST_OK;
+        nfev = 0;
+        h = 0.0;
+        t_new = t;
+        sys.rhs(t, y, K1); ++nfev;
         const double interval = fabs(t_bound - t);
         if (interval == 0.0) {
             h_abs = 0.0;
@@ -174,18 +182,14 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
             h_abs = fmin(fmin(100.0 * h0, h1), interval);
         }
     }
-    if (t == t_bound) {                                              // zero-length run: only y0 is output
-        const int kj = kept_index(L, 0);
-        if (kj >= 0) store_grid<Sys, OutT>(sys, L, i, kj, y);
-        g = 1;
-    }
-    int64_t steps = 0;
-    while (t < t_bound) {
-        if (steps++ >= L.max_steps) { st |= ST_MAX_STEPS; break; }
+
+    // `_step_impl`: attempts until one is accepted.  On success (t, t + h] = (t, t_new] is covered by y -> ynew with the stages in
+    // K1, S, K7; returns false when the step size underflows or the error norm is not finite (status bits set).
+    __host__ __device__ __forceinline__ bool step(Sys& sys, const double* y, Stages& S) {
+        double kt[NL], ytmp[NL];
         const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);   // double overload on host AND device
         if (h_abs < min_step) h_abs = min_step;
         bool rejected = false, failed = false;
-        double h, t_new;
         for (;;) {
             if (h_abs < min_step) { failed = true; break; }
             h = h_abs;
@@ -237,42 +241,163 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
             h_abs *= fmax(0.2, 0.9 * pow(error_norm, -0.2));
             rejected = true;
         }
-        if (failed) { st |= ST_STEP_TOO_SMALL; break; }
-        // ---- dense output for the grid points in (t_old, t_new] (and t0 itself on the first step) ------
-        g = next_kept(L, g);
-        while (g < L.n_out && L.t0 + (double)g <= t_new) {
-            const int kj = kept_index(L, g);
-            {
-                const double x = (L.t0 + (double)g - t) / h;
-                const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+        if (failed) st |= ST_STEP_TOO_SMALL;
+        return !failed;
+    }
+
+    // RkDenseOutput of the last accepted step at grid time tg in [t, t_new]
+    __host__ __device__ __forceinline__ void dense(const double* y, const Stages& S, double tg, double* out) const {
+        const double x = (tg - t) / h;
+        const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
 #pragma unroll
-                for (int e = 0; e < NL; ++e) {
-                    const double q0 = K1[e];                        // P[0] = [1, ...] and P[s>0][0] = 0
-                    const double q1 = K1[e] * (-8048581381.0 / 2820520608.0) + S.get(1, e) * (131558114200.0 / 32700410799.0) +
-                                      S.get(2, e) * (-1754552775.0 / 470086768.0) + S.get(3, e) * (127303824393.0 / 49829197408.0) +
-                                      S.get(4, e) * (-282668133.0 / 205662961.0) + K7[e] * (40617522.0 / 29380423.0);
-                    const double q2 = K1[e] * (8663915743.0 / 2820520608.0) + S.get(1, e) * (-68118460800.0 / 10900136933.0) +
-                                      S.get(2, e) * (14199869525.0 / 1410260304.0) + S.get(3, e) * (-318862633887.0 / 49829197408.0) +
-                                      S.get(4, e) * (2019193451.0 / 616988883.0) + K7[e] * (-110615467.0 / 29380423.0);
-                    const double q3 = K1[e] * (-12715105075.0 / 11282082432.0) + S.get(1, e) * (87487479700.0 / 32700410799.0) +
-                                      S.get(2, e) * (-10690763975.0 / 1880347072.0) + S.get(3, e) * (701980252875.0 / 199316789632.0) +
-                                      S.get(4, e) * (-1453857185.0 / 822651844.0) + K7[e] * (69997945.0 / 29380423.0);
-                    ytmp[e] = y[e] + h * (q0 * x + q1 * x2 + q2 * x3 + q3 * x4);
-                }
-                store_grid<Sys, OutT>(sys, L, i, kj, ytmp);
-            }
-            g = next_kept(L, g + 1);
+        for (int e = 0; e < NL; ++e) {
+            const double q0 = K1[e];                        // P[0] = [1, ...] and P[s>0][0] = 0
+            const double q1 = K1[e] * (-8048581381.0 / 2820520608.0) + S.get(1, e) * (131558114200.0 / 32700410799.0) +
+                              S.get(2, e) * (-1754552775.0 / 470086768.0) + S.get(3, e) * (127303824393.0 / 49829197408.0) +
+                              S.get(4, e) * (-282668133.0 / 205662961.0) + K7[e] * (40617522.0 / 29380423.0);
+            const double q2 = K1[e] * (8663915743.0 / 2820520608.0) + S.get(1, e) * (-68118460800.0 / 10900136933.0) +
+                              S.get(2, e) * (14199869525.0 / 1410260304.0) + S.get(3, e) * (-318862633887.0 / 49829197408.0) +
+                              S.get(4, e) * (2019193451.0 / 616988883.0) + K7[e] * (-110615467.0 / 29380423.0);
+            const double q3 = K1[e] * (-12715105075.0 / 11282082432.0) + S.get(1, e) * (87487479700.0 / 32700410799.0) +
+                              S.get(2, e) * (-10690763975.0 / 1880347072.0) + S.get(3, e) * (701980252875.0 / 199316789632.0) +
+                              S.get(4, e) * (-1453857185.0 / 822651844.0) + K7[e] * (69997945.0 / 29380423.0);
+            out[e] = y[e] + h * (q0 * x + q1 * x2 + q2 * x3 + q3 * x4);
         }
+    }
+
+    // accept the step: y <- y_new, FSAL
+    __host__ __device__ __forceinline__ void commit(double* y) {
 #pragma unroll
         for (int e = 0; e < NL; ++e) { y[e] = ynew[e]; K1[e] = K7[e]; }
         t = t_new;
     }
+};
+
+// Driver 1: every grid point is stored as soon as its step is accepted.  For systems whose lanes move in lockstep (the
+// reactor kernel: all lanes of a draw belong to ONE trajectory) and for the CPU harness.
+template <class Sys, typename OutT, class Stages>
+__host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, int64_t i, double* y, Stages& S) {
+    constexpr int NL = Sys::NL;
+    Rk45<Sys, Stages> R;
+    double ytmp[NL];
+    int g = 0;                                                        // next grid point to emit
+    R.init(sys, L, y);
+    if (R.t == R.t_bound) {                                          // zero-length run: only y0 is output
+        const int kj = kept_index(L, 0);
+        if (kj >= 0) store_grid<Sys, OutT>(sys, L, i, kj, y);
+        g = 1;
+    }
+    int64_t steps = 0;
+    while (R.t < R.t_bound) {
+        if (steps++ >= L.max_steps) { R.st |= ST_MAX_STEPS; break; }
+        if (!R.step(sys, y, S)) break;
+        // ---- dense output for the grid points in (t_old, t_new] (and t0 itself on the first step) ------
+        g = next_kept(L, g);
+        while (g < L.n_out && L.t0 + (double)g <= R.t_new) {
+            R.dense(y, S, L.t0 + (double)g, ytmp);
+            store_grid<Sys, OutT>(sys, L, i, kept_index(L, g), ytmp);
+            g = next_kept(L, g + 1);
+        }
+        R.commit(y);
+    }
     if (g < L.n_out) fill_nan_from<Sys, OutT>(sys, L, i, g);
     if (sys.leader()) {
-        if (L.nfev) L.nfev[i] = nfev;
-        if (L.status) L.status[i] = (int32_t)st;
+        if (L.nfev) L.nfev[i] = R.nfev;
+        if (L.status) L.status[i] = (int32_t)R.st;
     }
 }
+
+#ifdef __CUDACC__
+// Driver 2 (device, one trajectory per THREAD): the lanes of a warp run their own step sequences, so with driver 1 every lane
+// reaches grid point j at a different moment and its 8-byte store lands alone in a 32-byte sector: ncu on C1 (tutorial SIR,
+// 10^6 draws) showed 11.4 GB of DRAM traffic for 2.9 GB of output -- partial-sector writes that L2 completes by reading the
+// line back (profiles/r2_sir_ode_ncu_summary.txt).  Here the kept grid points are delivered in WINDOWS of W consecutive
+// points: a lane parks its values in shared memory ([point][element][thread]), stops stepping once its window is full, and
+// when the whole warp is there every (element, point) row is stored by all lanes at once -- 256 contiguous bytes.  A lane
+// that runs ahead waits at most one window; the warp takes max-over-lanes steps either way.  The arithmetic is driver 1's.
+template <class Sys, typename OutT, class Stages>
+__device__ __forceinline__ void rk45_run_windowed(Sys& sys, const OdeLaunch& L, int64_t i, bool valid, double* y, Stages& S,
+                                                  double* win, int W, int stride) {
+    constexpr int NL = Sys::NL;
+    constexpr unsigned FULL = 0xffffffffu;
+    Rk45<Sys, Stages> R;
+    double ytmp[NL];
+    bool pending = false, dead = !valid;
+    // the next kept grid point: grid index g, kept index kj (kept points are g = 0, s, 2 s, .. or the last one alone); carried
+    // along instead of being recomputed by division
+    const int g_step = L.out_last_only ? L.n_out : L.out_stride;
+    int g = L.out_last_only ? L.n_out - 1 : 0, kj = 0;
+    if (valid) {
+        R.init(sys, L, y);
+        if (R.t == R.t_bound) {                                      // zero-length run: y0 alone
+#pragma unroll
+            for (int e = 0; e < NL; ++e) win[e * stride] = y[e];
+            kj = L.n_kept;
+        }
+    } else {
+        R.st = ST_OK; R.nfev = 0; R.t = R.t_bound = R.t_new = 0.0; R.h = 1.0;
+        kj = L.n_kept;
+    }
+    int64_t steps = 0;
+    int lo = 0;                                                       // first kept index of the current window
+    while (lo < L.n_kept) {
+        const int hi = lo + W < L.n_kept ? lo + W : L.n_kept;
+        // (a) what the pending step covers of this window
+        if (pending) {
+            while (kj < hi && L.t0 + (double)g <= R.t_new) {
+                R.dense(y, S, L.t0 + (double)g, ytmp);
+                const int kk = kj - lo;
+#pragma unroll
+                for (int e = 0; e < NL; ++e) win[(kk * NL + e) * stride] = ytmp[e];
+                g += g_step; ++kj;
+            }
+            if (!(kj < L.n_kept && L.t0 + (double)g <= R.t_new)) {   // the step has delivered all its points
+                R.commit(y);
+                pending = false;
+            }
+        }
+        // (b) a trajectory that was abandoned reports NaN from there on (as scipy's failed solve leaves no values)
+        if (dead && valid) {
+            for (; kj < hi; ++kj, g += g_step) {
+                const int kk = kj - lo;
+#pragma unroll
+                for (int e = 0; e < NL; ++e) win[(kk * NL + e) * stride] = NAN;
+            }
+        }
+        // (c) window complete on every lane: store it, one (element, point) row per instruction
+        const bool full = kj >= hi;
+        if (__all_sync(FULL, full)) {
+            if (valid) {
+                OutT* out = (OutT*)L.out + i;
+                for (int kk = 0; kk < hi - lo; ++kk) {
+#pragma unroll
+                    for (int e = 0; e < NL; ++e)
+                        out[((int64_t)sys.global_index(e) * L.n_kept + lo + kk) * L.ld_out] = (OutT)win[(kk * NL + e) * stride];
+                }
+            }
+            lo = hi;
+            continue;
+        }
+        // (d) the next step
+        if (!full && !pending && !dead) {
+            if (!(R.t < R.t_bound)) dead = true;                      // (cannot happen: the last step ends on t_bound)
+            else if (steps++ >= L.max_steps) { R.st |= ST_MAX_STEPS; dead = true; }
+            else if (R.step(sys, y, S)) pending = true;
+            else dead = true;
+        }
+    }
+    // a strided grid may end before t_bound: the reference's solver still integrates to the end (its nfev and status say so)
+    while (valid && !dead && R.t < R.t_bound) {
+        if (steps++ >= L.max_steps) { R.st |= ST_MAX_STEPS; break; }
+        if (!R.step(sys, y, S)) break;
+        R.commit(y);
+    }
+    if (valid) {
+        if (L.nfev) L.nfev[i] = R.nfev;
+        if (L.status) L.status[i] = (int32_t)R.st;
+    }
+}
+#endif
 
 // the stages in registers (thread-per-trajectory systems)
 template <class Sys, typename OutT>
@@ -409,14 +534,30 @@ __host__ __device__ __forceinline__ void load_ode_params(const OdeLaunch& L, int
     }
 }
 
+#ifdef __CUDACC__
+// thread-per-trajectory RK45 with windowed, coalesced output (rk45_run_windowed); `valid` = the thread owns a trajectory
 template <class M, typename OutT>
+__device__ __forceinline__ void ode_thread_trajectory_windowed(const OdeLaunch& L, int64_t i, bool valid, double* win, int W, int stride) {
+    double par[M::NPAR], y[M::N];
+    const int64_t src = valid ? i : 0;
+    load_ode_params<M::NPAR>(L, src, par);
+#pragma unroll
+    for (int s = 0; s < M::N; ++s) y[s] = L.y0_bcast ? L.y0[s] : L.y0[(int64_t)s * L.ld_in + src];
+    ThreadSystem<M> sys{par};
+    RegisterStages<M::N> S;
+    rk45_run_windowed<ThreadSystem<M>, OutT, RegisterStages<M::N>>(sys, L, i, valid, y, S, win, W, stride);
+}
+#endif
+
+// WITH_RK45 = false: the kernel of a model whose RK45 runs through the windowed driver carries the fixed-step schemes only
+template <class M, typename OutT, bool WITH_RK45 = true>
 __host__ __device__ __forceinline__ void ode_thread_trajectory(const OdeLaunch& L, int method, int64_t i) {
     double par[M::NPAR], y[M::N];
     load_ode_params<M::NPAR>(L, i, par);
 #pragma unroll
     for (int s = 0; s < M::N; ++s) y[s] = L.y0_bcast ? L.y0[s] : L.y0[(int64_t)s * L.ld_in + i];
     ThreadSystem<M> sys{par};
-    if (method == SODM_ODE_RK45) rk45_run<ThreadSystem<M>, OutT>(sys, L, i, y);
+    if (WITH_RK45 && method == SODM_ODE_RK45) rk45_run<ThreadSystem<M>, OutT>(sys, L, i, y);
     else if (method == SODM_ODE_EULER) fixed_step_run<ThreadSystem<M>, OutT, false>(sys, L, i, y);
     else fixed_step_run<ThreadSystem<M>, OutT, true>(sys, L, i, y);
 }

@@ -11,6 +11,7 @@ cap() {  # name, kernel regex, launches to skip, command...
     ncu -i gpurun_out/r2_$name.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/r2_$name.source.csv.gz
     python tools/summarize_ncu.py gpurun_out/r2_$name.ncu-rep "$@" > gpurun_out/r2_$name.summary.txt 2>&1
     if [ $name = tau_leap ] || [ $name = queue ]; then python tools/summarize_profile.py gpurun_out/r2_$name.ncu-rep 262144 gpurun_out/r2_${name}_ncu_full.txt "$LABEL" 48 > /dev/null 2>&1; fi
+    python tools/top_lines.py gpurun_out/r2_$name.ncu-rep 40 > gpurun_out/r2_$name.lines.txt 2>&1
     rm -f gpurun_out/r2_$name.ncu-rep
     tail -n 1 gpurun_out/r2_ncu_$name.log
 }
