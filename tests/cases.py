@@ -26,6 +26,54 @@ def flu_draws(n, seed=1718):
     return beta, f_ud
 
 
+def _oracle_chunk(job):
+    which, n, seed, times, with_draws = job
+    from oracle import jump, models
+    from pysodm_b200 import tutorial_data as td
+    if which == "flu":
+        par = dict(FLU_PAR_DICT)
+        if with_draws:
+            beta, f_ud = flu_draws(n, seed)
+            par.update(beta=beta, f_ud=f_ud)
+        y = jump.tau_leap_ensemble(models.InfluenzaJump, td.influenza_flat_y0(), par, 0, FLU_N_OUT - 1, 0.5, n,
+                                   tdpf={"N": (td.CONTACT_TABLE, td.influenza_schedule())}, seed=seed, chunk=1024)
+    else:
+        y = jump.tau_leap_ensemble(models.SIRSIJump, td.sirsi_flat_y0(), dict(td.SIRSI_PARAMETERS), 0, 120, 0.5, n, seed=seed, chunk=2048)
+    return y[:, :, times].astype(np.int32)
+
+
+def oracle_ensemble_parallel(which, n, times, seed=5000, with_draws=False, per_job=2048):
+    """n trajectories of the pinned oracle (oracle/jump.py, reference law) on all host cores -> int32 [n, states, len(times)].
+    Config C3's per-trajectory draws (`flu_draws`) are re-drawn per job from the job's seed: the same DISTRIBUTION of
+    parameters as the device run, not the same values."""
+    import multiprocessing as mp
+    import os
+    jobs = [(which, min(per_job, n - lo), seed + 7 * k, np.asarray(times), with_draws) for k, lo in enumerate(range(0, n, per_job))]
+    with mp.get_context("fork").Pool(min(len(jobs), os.cpu_count())) as pool:
+        parts = pool.map(_oracle_chunk, jobs, chunksize=1)
+    return np.concatenate(parts, axis=0)
+
+
+def ks_pvalues_counts_device(a, b):
+    """Two-sample KS p-values of integer samples, computed on the device: a[cells, na], b[cells, nb] (torch int32 CUDA tensors)
+    -> NumPy [cells].  Statistic from the two cumulated histograms over the cell's value range; p from the asymptotic
+    Kolmogorov law with en = na nb / (na + nb) (scipy.stats.ks_2samp's `asymp` mode, which it uses at these sizes)."""
+    import torch
+    from scipy.stats import distributions
+    na, nb = a.shape[1], b.shape[1]
+    ps = np.ones(a.shape[0])
+    for r in range(a.shape[0]):
+        lo = int(min(a[r].min(), b[r].min()))
+        hi = int(max(a[r].max(), b[r].max()))
+        if lo == hi:
+            continue
+        ca = torch.cumsum(torch.bincount((a[r] - lo).long(), minlength=hi - lo + 1), 0).double() / na
+        cb = torch.cumsum(torch.bincount((b[r] - lo).long(), minlength=hi - lo + 1), 0).double() / nb
+        d = float((ca - cb).abs().max())
+        ps[r] = float(np.clip(distributions.kstwo.sf(d, np.round(na * nb / (na + nb))), 0, 1))
+    return ps
+
+
 def ks_pvalues(a, b):
     """Two-sample KS p-values along the last axis of a[..., na] vs b[..., nb]; constant-equal cells give 1."""
     from scipy import stats

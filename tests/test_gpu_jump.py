@@ -103,6 +103,38 @@ def test_per_trajectory_draws_match_oracle(eng, golden):
     cases.assert_ks_ok(cases.ks_pvalues(mine, np.transpose(ref[:, :, times], (1, 2, 0))), "C3 draws GPU vs oracle")
 
 
+@pytest.mark.slow
+def test_full_size_ensembles_match_the_oracle_per_cell(eng, golden):
+    """BASELINE configs at their FULL size against large oracle ensembles (the 10^6 runs were only mean-checked).
+    C3: 10^6 influenza trajectories, full season, per-trajectory beta / f_ud draws, against 10^5 trajectories of the pinned
+    oracle with parameters from the same distribution -- two-sample KS per (state, time) cell, resolution ~0.4 % in the
+    CDF.  C2: 10^6 SIR_SI tau-leap trajectories against 10^5.  Same bar as every ensemble test (cases.assert_ks_ok)."""
+    import torch
+    g = golden["jump_single"]
+    n, m = 1_000_000, 100_000
+    times = [1, 7, 28, 56, 84, 120, 161]
+    beta, f_ud = cases.flu_draws(n)
+    var = {cases.FLU_IDX_BETA: beta}
+    var.update({k: f_ud[:, i] for i, k in enumerate(cases.FLU_IDX_FUD)})
+    out, st = eng.jump_run("influenza_1718_jump", g["flu_y0"], cases.FLU_PAR, n, 0, cases.FLU_N_OUT, 0.5, var=var,
+                           tdpf=(g["flu_table"], g["flu_step_index"]), seed=31, out_dtype=torch.int32)
+    assert int(st.abs().sum()) == 0
+    mine = out[:, times, :].reshape(-1, n).contiguous()
+    del out
+    ref = cases.oracle_ensemble_parallel("flu", m, times, seed=9000, with_draws=True)             # [m, 28, T]
+    ref_d = torch.from_numpy(np.ascontiguousarray(np.transpose(ref, (1, 2, 0)).reshape(-1, m))).cuda()
+    cases.assert_ks_ok(cases.ks_pvalues_counts_device(mine, ref_d), "C3 at N = 10^6 vs 10^5 oracle trajectories")
+    del mine, ref_d
+    times2 = [1, 10, 30, 60, 90, 120]
+    out, st = eng.jump_run("sir_si_jump", g["sirsi_y0"], cases.SIRSI_PAR, n, 0, 121, 0.5, seed=32, out_dtype=torch.int32)
+    assert int(st.abs().sum()) == 0
+    mine = out[:, times2, :].reshape(-1, n).contiguous()
+    del out
+    ref = cases.oracle_ensemble_parallel("sirsi", m, times2, seed=9500)
+    ref_d = torch.from_numpy(np.ascontiguousarray(np.transpose(ref, (1, 2, 0)).reshape(-1, m))).cuda()
+    cases.assert_ks_ok(cases.ks_pvalues_counts_device(mine, ref_d), "C2 at N = 10^6 vs 10^5 oracle trajectories")
+
+
 def test_test_sir_final_size(eng, golden):
     """The reference's own assertion (src/tests/test_JumpProcess.py:144-151) + KS against the oracle."""
     import torch
