@@ -638,7 +638,7 @@ def bench_c3_strong(ctx, args):
 def _bench_fused_gather(ctx, args, draws, status, lo, n):
     """The same strong-scaling step with the gather INSIDE the simulation kernel: every rank's tau-leap kernel stores each
     output row into its own copy of the ensemble and into the 7 peers' copies over NVLink (`sodm_jump_args.out_peers`, buffers
-    mapped once through CUDA IPC by `sharding.PeerEnsemble`) -- one launch per rank and a 4-byte all-reduce as the completion
+    shared once through CUDA virtual-memory mappings by `sharding.PeerEnsemble`) -- one launch per rank and a 4-byte all-reduce as the completion
     handshake instead of an 18 GB all-gather behind the kernel.  Gate: a peer's shard as it arrived here equals the same
     trajectories recomputed locally, bit for bit."""
     import torch
@@ -679,7 +679,8 @@ def _bench_fused_gather(ctx, args, draws, status, lo, n):
            "bytes_stored_to_peers_per_gpu_per_step": int(gather_bytes), "nvlink_floor_ms": gather_bytes / 900e9 * 1e3,
            "parity": {"what": "a peer's shard as its kernel stored it here == the same trajectories recomputed locally (bit-exact, every rank)",
                       "pass": bool(same.min().item() == 1.0)},
-           "what": "tau-leap kernel stores every output row to its own and to the peers' ensemble buffers over NVLink (CUDA IPC "
+           "mapping": ens.mapping,
+           "what": "tau-leap kernel stores every output row to its own and to the peers' ensemble buffers over NVLink (peer "
                    "mappings); every GPU ends with the whole 18.1 GB ensemble; 4-byte all-reduce as completion handshake"}
     del want
     ens.close()

@@ -70,6 +70,10 @@ extern "C" {
                                            items any lane may work on, batched by regime; counter-based words) instead of the
                                            per-lane walk (csrc/jump_run.cuh); same law, different random streams */
 
+#define SODM_TUNE_LATENCY          512u  /* tuning: the 96-register build of the tau-leap kernel (no spills, 5 blocks per SM) for
+                                           launches of about one wave or less (csrc/jump_kernels.cuh); same law, but about 3 in
+                                           10^5 trajectories round differently than in the default build */
+
 /* methods */
 #define SODM_JUMP_TAU_LEAP 0
 #define SODM_JUMP_SSA      1
@@ -157,6 +161,11 @@ int sodm_peer_enable(int peer_device);
 int sodm_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle /* [SODM_PEER_HANDLE_BYTES] out */);
 int sodm_peer_open(const unsigned char* handle, void** ptr);
 int sodm_peer_close(void* ptr);
+/* The same gather by DMA: copies `rows` rows of `width_bytes` (this rank's columns of a [row][time][n_total] buffer) from `src`
+ * to `dst` (a mapped peer buffer) with the copy engines -- no SM is involved, so it overlaps a running simulation kernel
+ * completely.  Asynchronous on `stream`. */
+int sodm_peer_copy2d(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes, int64_t width_bytes,
+                     int64_t rows, void* stream);
 int sodm_peer_free(void* ptr);
 /* Number of tau-leap steps the reference's loop `while t < t1: t = t + tau` takes (base.py:428-434). */
 int64_t sodm_jump_n_steps(double t0, int32_t n_out, double tau);

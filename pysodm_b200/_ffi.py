@@ -17,6 +17,7 @@ KIND_JUMP, KIND_ODE = 0, 1
 I32, F32, F64 = 0, 1, 2
 ST_BAD_PROB, ST_NONFINITE, ST_STEP_TOO_SMALL, ST_MAX_STEPS, ST_TRUNCATED_Y0 = 1, 2, 4, 8, 16
 COMPAT_STAY_QUIRK, COMPAT_SSA_FIRST_MATCH, COMPAT_REFERENCE = 1, 2, 3
+TUNE_QUEUE, TUNE_LATENCY = 256, 512
 JUMP_TAU_LEAP, JUMP_SSA = 0, 1
 ODE_RK45, ODE_EULER, ODE_RK4 = 0, 1, 2
 LL_POISSON, LL_NORMAL, LL_LOGNORMAL, LL_NEGBIN = 0, 1, 2, 3
@@ -113,6 +114,7 @@ SYMBOLS = {
     "sodm_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "sodm_peer_close": (C.c_int, [C.c_void_p]),
     "sodm_peer_free": (C.c_int, [C.c_void_p]),
+    "sodm_peer_copy2d": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "sodm_jump_n_steps": (C.c_int64, [C.c_double, C.c_int32, C.c_double]),
     "sodm_status_or": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "sodm_ode_run": (C.c_int, [C.POINTER(OdeArgs)]),

@@ -35,11 +35,16 @@ static size_t tau_leap_smem(int n_tdpf_values, bool queue = false) {
     return ((size_t)2 * M::NDRAW * JUMP_BLOCK + (size_t)n_tdpf_values * M::TDPF_COUNT + (size_t)(queue ? queue_words<M>() : order_words<M>())) * sizeof(float);
 }
 
-// The same kernel is compiled for two register budgets (results are identical, the arithmetic is the same): MINB = 8 resident
-// blocks per SM (64 registers, some spills) for launches that fill the GPU, where resident warps buy issue slots, and
-// MINB = 5 (96 registers, no spills) for launches of at most one wave, whose duration is ONE warp's chain of dependent
-// instructions from the first step to the last -- there the spills only lengthen that chain (B200, influenza, 168 steps,
-// profiles/r2_small_launches.txt: 12 500 trajectories 4.66 -> 3.93 ms, 1024: 3.54 -> 2.92 ms; 10^6: 108.7 -> 112.7 ms).
+// The same kernel is compiled for two register budgets: MINB = 8 resident blocks per SM (64 registers, some spills) for
+// launches that fill the GPU, where resident warps buy issue slots, and MINB = 5 (96 registers, no spills), selected by
+// SODM_TUNE_LATENCY, for launches of about one wave or less, whose duration is ONE warp's chain of dependent instructions from
+// the first step to the last -- there the spills only lengthen that chain (B200, influenza, 168 steps,
+// profiles/r2_small_launches.txt: 12 500 trajectories 4.66 -> 3.90 ms, 1024: 3.54 -> 2.92 ms; 10^6: 108.7 -> 112.7 ms).
+// It is a FLAG of the caller, not a choice of the launcher: the two builds are the same source, but ptxas contracts
+// different multiply-add pairs under the two register budgets, so about 3 in 10^5 trajectories take a different accept /
+// reject decision somewhere (measured: 2 of 60 000 final states differ; with -fmad=false none do, at +3.2 % on the headline
+// launch).  Same law, different rounding: a run is reproducible and shard-invariant for a given flag, and a launcher that
+// switched builds by launch size would make results depend on the number of GPUs.
 constexpr int LATENCY_MIN_BLOCKS = 5;
 
 template <class M, typename OutT, bool ALIGNED, bool QUEUE, int MINB>
@@ -94,22 +99,6 @@ static int pick_lane_shift(int64_t n_traj) {
     return shift;
 }
 
-static int device_sm_count() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, v = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        sms = v;
-    }
-    return sms;
-}
-// SODM_LATENCY_BUILD=0 in the environment keeps every launch on the 8-blocks-per-SM build (A/B measurements, tests)
-static bool latency_build_disabled() {
-    static int off = -1;
-    if (off < 0) { const char* e = getenv("SODM_LATENCY_BUILD"); off = e && *e == '0' ? 1 : 0; }
-    return off == 1;
-}
-
 static unsigned spread_grid(int64_t n_traj, int lane_shift) {
     const int64_t warps = (n_traj + (32 >> lane_shift) - 1) / (32 >> lane_shift);
     return (unsigned)((warps + JUMP_BLOCK / 32 - 1) / (JUMP_BLOCK / 32));
@@ -125,10 +114,10 @@ static int launch_jump(const JumpLaunch& L0, int method, bool aligned, cudaStrea
         const size_t smem = tau_leap_smem<M>(L.n_tdpf_values, queue);
         // the queue sampler exists in the 96-register build only (at 64 registers it spills in its batch loop: 155 vs 118 ms)
         constexpr int T = SODM_WALK_MIN_BLOCKS, Q = LATENCY_MIN_BLOCKS;
-        const bool one_wave = (int64_t)grid <= (int64_t)device_sm_count() * LATENCY_MIN_BLOCKS && !latency_build_disabled();
+        const bool latency = (L.compat & TUNE_LATENCY) != 0u;
         void (*kernel)(JumpLaunch);
         if (queue) kernel = aligned ? tau_leap_kernel<M, OutT, true, true, Q> : tau_leap_kernel<M, OutT, false, true, Q>;
-        else if (one_wave) kernel = aligned ? tau_leap_kernel<M, OutT, true, false, Q> : tau_leap_kernel<M, OutT, false, false, Q>;
+        else if (latency) kernel = aligned ? tau_leap_kernel<M, OutT, true, false, Q> : tau_leap_kernel<M, OutT, false, false, Q>;
         else kernel = aligned ? tau_leap_kernel<M, OutT, true, false, T> : tau_leap_kernel<M, OutT, false, false, T>;
         SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         kernel<<<grid, JUMP_BLOCK, smem, stream>>>(L);

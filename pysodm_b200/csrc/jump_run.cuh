@@ -19,7 +19,7 @@ namespace sodm {
 constexpr int MAX_PARAM = 64;   // flat parameter elements passed by value
 constexpr int MAX_STATE = 64;   // flat state elements of a jump model
 
-enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, TUNE_QUEUE = 256u };
+enum : uint32_t { COMPAT_STAY_QUIRK = 1u, COMPAT_SSA_FIRST_MATCH = 2u, TUNE_QUEUE = 256u, TUNE_LATENCY = 512u };
 
 struct JumpLaunch {
     int64_t n_traj;            // trajectories in this launch

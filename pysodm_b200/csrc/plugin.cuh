@@ -194,9 +194,9 @@ static int launch_plugin_jump(const JumpLaunch& L0, int method, bool aligned, in
         const size_t smem = tau_leap_smem<M>(L.n_tdpf_values);
         void (*kernel)(JumpLaunch) = nullptr;
         constexpr int T = SODM_WALK_MIN_BLOCKS;
-        // launches of at most one wave of the posterior path (int32, aligned grid) take the 96-register build (jump_kernels.cuh)
-        const bool one_wave = (int64_t)grid <= (int64_t)device_sm_count() * LATENCY_MIN_BLOCKS && !latency_build_disabled();
-        if (aligned && dtype == SODM_I32) kernel = one_wave ? tau_leap_kernel<M, int32_t, true, false, LATENCY_MIN_BLOCKS> : tau_leap_kernel<M, int32_t, true, false, T>;
+        // SODM_TUNE_LATENCY: the 96-register build (jump_kernels.cuh), offered for the posterior path (int32, aligned grid)
+        const bool latency = (L.compat & TUNE_LATENCY) != 0u;
+        if (aligned && dtype == SODM_I32) kernel = latency ? tau_leap_kernel<M, int32_t, true, false, LATENCY_MIN_BLOCKS> : tau_leap_kernel<M, int32_t, true, false, T>;
         else if (aligned && dtype == SODM_F64) kernel = tau_leap_kernel<M, double, true, false, T>;
         else if (!aligned && dtype == SODM_F64) kernel = tau_leap_kernel<M, double, false, false, T>;
         else return fail(SODM_EUNSUPPORTED, "generated models write int32 (tau = 2^-k) or float64 output");

@@ -110,6 +110,16 @@ extern "C" int sodm_peer_free(void* ptr) {
     return SODM_OK;
 }
 
+// The DMA form of the same gather: one strided 2-D copy (copy engines, no SM) of this rank's columns into a peer's buffer.
+extern "C" int sodm_peer_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width_bytes,
+                                int64_t rows, void* stream) {
+    if (!dst || !src || width_bytes <= 0 || rows <= 0 || dst_pitch < width_bytes || src_pitch < width_bytes)
+        return fail(SODM_EINVAL, "sodm_peer_copy2d: pointers, 0 < width <= pitches and rows > 0 must be given");
+    SODM_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width_bytes, (size_t)rows,
+                                      cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SODM_OK;
+}
+
 extern "C" int sodm_model_id(const char* name) {
     if (!name) return fail(SODM_EINVAL, "sodm_model_id: null name");
     for (int m = 0; m < MODEL_COUNT; ++m)

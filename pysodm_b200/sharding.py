@@ -160,12 +160,18 @@ class PeerEnsemble:
     themselves: rank r simulates columns [lo_r, hi_r) and its kernel stores each output element into its own buffer and into
     the other ranks' buffers over NVLink (`sodm_jump_args.out_peers`).  This is the "final gather of outputs" of a sharded
     run without a collective: the peer stores are posted while the trajectories run, so the transfer hides behind the
-    sampler instead of following it.  The buffers are allocated by libsodm (a CUDA IPC handle names a whole cudaMalloc
-    allocation) and mapped into the other processes once, at construction; the 64-byte handles travel over the job's
-    `torch.distributed` group.  One node only (NVLink / NVSwitch peers)."""
+    sampler instead of following it.  One node only (NVLink / NVSwitch peers).
 
-    def __init__(self, n_rows, n_out, n_total, dtype=torch.int32, dev=None):
-        import ctypes as C
+    How the buffers are shared matters more than anything in the kernel.  `mapping='vmm'` (default under NCCL): CUDA
+    virtual-memory allocations exported by file descriptor and mapped with 2 MB granularity -- torch's symmetric-memory
+    allocator does the plumbing (`torch.distributed._symmetric_memory`), the kernel only sees raw pointers.
+    `mapping='ipc'`: legacy CUDA IPC handles (`sodm_peer_alloc / sodm_peer_open`), which work between any two processes
+    (also two processes sharing one GPU, as in the tests) but map the peer buffer with small pages: the kernel's stores
+    scatter 128-byte rows over 18 GB per peer, and with three or more peers the translations thrash -- measured on 4 GPUs,
+    250 000 trajectories each: kernel alone 29.6 ms; stores to 1 / 2 / 3 peers 30.5 / 31.3 / **204 ms** through IPC mappings,
+    30.5 / 31.3 / **33.1 ms** through VMM mappings (profiles/r2_gather_probe_4gpu.txt); on 8 GPUs the IPC form took 873 ms."""
+
+    def __init__(self, n_rows, n_out, n_total, dtype=torch.int32, dev=None, mapping="auto"):
         from . import _ffi, engine
         self.lib = _ffi.load()
         self.dev = dev or engine.device()
@@ -174,12 +180,42 @@ class PeerEnsemble:
             raise ValueError(f"at most {_ffi.MAX_PEERS + 1} ranks, got {self.world}")
         self.shape = (int(n_rows), int(n_out), int(n_total))
         self.lo, self.hi = shard_range(n_total, self.rank, self.world)
-        itemsize = torch.empty(0, dtype=dtype).element_size()
-        typestr = {torch.int32: "<i4", torch.float32: "<f4", torch.float64: "<f8"}[dtype]
-        nbytes = itemsize * self.shape[0] * self.shape[1] * self.shape[2]
+        self.dtype = dtype
+        if mapping == "auto":
+            mapping = "vmm" if self.world > 1 and dist.get_backend() == "nccl" else "ipc"
+        self.mapping = mapping
+        self._own, self._mapped, self.peer_columns, self._handle = None, [], [], None      # peer_columns: column lo of every OTHER rank's buffer
         # every rank goes through the same collectives whatever fails locally, and all ranks raise together
+        error = self._map_vmm() if mapping == "vmm" else self._map_ipc()
+        if self.world > 1:
+            errors = [None] * self.world
+            dist.all_gather_object(errors, error)
+            error = next((e for e in errors if e), None)
+        if error is not None:
+            self._release()
+            raise RuntimeError(f"PeerEnsemble ({mapping}): {error}")
+        self.local = self.full[:, :, self.lo:self.hi]          # what this rank's kernel writes (row stride n_total)
+
+    def _map_vmm(self):
+        itemsize = torch.empty(0, dtype=self.dtype).element_size()
+        try:
+            import torch.distributed._symmetric_memory as symm
+            self.full = symm.empty(self.shape, dtype=self.dtype, device=self.dev)
+            self._handle = symm.rendezvous(self.full, dist.group.WORLD)
+            self._own = self.full.data_ptr()
+            self._mapped = [int(p) for r, p in enumerate(self._handle.buffer_ptrs) if r != self.rank]
+            self.peer_columns = [p + self.lo * itemsize for p in self._mapped]
+        except Exception as exc:                                   # noqa: BLE001 -- reported on every rank together
+            return f"{type(exc).__name__}: {exc}"
+        return None
+
+    def _map_ipc(self):
+        import ctypes as C
+        from . import _ffi
+        itemsize = torch.empty(0, dtype=self.dtype).element_size()
+        typestr = {torch.int32: "<i4", torch.float32: "<f4", torch.float64: "<f8"}[self.dtype]
+        nbytes = itemsize * self.shape[0] * self.shape[1] * self.shape[2]
         ptr, handle, error = C.c_void_p(), C.create_string_buffer(_ffi.PEER_HANDLE_BYTES), None
-        self._own, self._mapped, self.peer_columns = None, [], []      # peer_columns: column lo of every OTHER rank's buffer
         try:
             _ffi.check(self.lib.sodm_peer_alloc(nbytes, C.byref(ptr), handle), self.lib)
             self._own = ptr.value
@@ -200,17 +236,25 @@ class PeerEnsemble:
                     _ffi.check(self.lib.sodm_peer_open(raw, C.byref(p)), self.lib)
                     self._mapped.append(p.value)
                     self.peer_columns.append(p.value + self.lo * itemsize)
+                self.full = torch.as_tensor(_RawDeviceBuffer(self._own, self.shape, typestr), device=self.dev)
             except _ffi.SodmError as exc:
                 error = str(exc)
-        if self.world > 1:
-            errors = [None] * self.world
-            dist.all_gather_object(errors, error)
-            error = next((e for e in errors if e), None)
-        if error is not None:
-            self._release()
-            raise RuntimeError(f"PeerEnsemble: {error}")
-        self.full = torch.as_tensor(_RawDeviceBuffer(self._own, self.shape, typestr), device=self.dev)
-        self.local = self.full[:, :, self.lo:self.hi]          # what this rank's kernel writes (row stride n_total)
+        return error
+
+    def push(self, col_lo, col_hi, stream=None):
+        """The DMA form of the gather: copy columns [col_lo, col_hi) of this rank's shard (global column numbers) from its own
+        copy of the ensemble into every peer's copy with the copy engines (`sodm_peer_copy2d`: one strided 2-D copy per peer, no SM
+        involved).  Asynchronous on `stream`: queue it behind the kernel that produced the columns, on a side stream, and it
+        overlaps the next kernel completely."""
+        import ctypes as C
+        from . import _ffi, engine
+        itemsize = self.full.element_size()
+        rows, pitch = self.shape[0] * self.shape[1], self.shape[2] * itemsize
+        src = self._own + col_lo * itemsize
+        sp = engine._stream_ptr(stream)
+        for base in self._mapped:
+            _ffi.check(self.lib.sodm_peer_copy2d(C.c_void_p(base + col_lo * itemsize), pitch, C.c_void_p(src), pitch,
+                                                 (col_hi - col_lo) * itemsize, rows, sp), self.lib)
 
     def fence(self):
         """Every rank's stores have landed everywhere: local stream drained, then a barrier of the job."""
@@ -220,6 +264,13 @@ class PeerEnsemble:
 
     def _release(self):
         from . import _ffi
+        if self.mapping == "vmm":
+            self._mapped, self.peer_columns = [], []
+            if self.world > 1:
+                dist.barrier()                   # nobody still stores into this rank's buffer
+            self.full = self.local = self._handle = None           # torch's allocator unmaps and frees
+            self._own = None
+            return
         for p in self._mapped:
             _ffi.check(self.lib.sodm_peer_close(p), self.lib)
         self._mapped = []

@@ -1,4 +1,4 @@
-"""Small / sharded launches: walk against queue sampler (compat | 256) for ensembles that do not fill the GPU.
+"""Small / sharded launches: walk (default 64-register build / SODM_TUNE_LATENCY = 96-register build) against queue sampler (SODM_TUNE_QUEUE) for ensembles that do not fill the GPU.
 python tools/ab_small.py   (PYSODM_B200_LIB selects a tuning build)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -17,7 +17,7 @@ for n_out, label in ((85, "C5 window (168 steps)"), (162, "full season (322 step
         draws = torch.from_numpy(bench.synthetic_draws(n, 1718)).to(dev)
         out = torch.empty((28, n_out, n), dtype=torch.int32, device=dev)
         row = []
-        for compat in (3, 3 | 256):
+        for compat in (3, 3 | 512, 3 | 256):
             ts = []
             for rep in range(6):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -27,4 +27,4 @@ for n_out, label in ((85, "C5 window (168 steps)"), (162, "full season (322 step
                 b.record(); torch.cuda.synchronize()
                 ts.append(a.elapsed_time(b))
             row.append(min(ts[2:]))
-        print(f"  n = {n:7d}: walk {row[0]:7.3f} ms   queue {row[1]:7.3f} ms")
+        print(f"  n = {n:7d}: walk {row[0]:7.3f} ms   walk, SODM_TUNE_LATENCY {row[1]:7.3f} ms   queue {row[2]:7.3f} ms")
