@@ -874,14 +874,19 @@ def bench_c5(ctx, args):
     traj = torch.empty((4, 85, n), dtype=torch.int32, device=dev)
     lp = torch.zeros(n, dtype=torch.float64, device=dev)
 
-    def c5():
+    from pysodm_b200 import _ffi
+
+    def c5(compat=_ffi.COMPAT_REFERENCE):
         lp.zero_()
         engine.jump_run("influenza_1718_jump", ctx.y0, ctx.par, n, 0, 85, 0.5, var=var, tdpf=(ctx.table, idx), seed=3, traj_id0=lo,
-                        out_dtype=torch.int32, state_sel=[24, 25, 26, 27], out=traj, dev=dev)
+                        compat=compat, out_dtype=torch.int32, state_sel=[24, 25, 26, 27], out=traj, dev=dev)
         engine.loglik("negative_binomial", traj, 0.0, [[0], [1], [2], [3]], np.arange(13) * 7.0, ydata, ll_arg=4 * [0.03], lp=lp, dev=dev)
         return sharding.all_gather_concat(lp, P)
     ms = _timed_launches(ctx, c5, flush=True)
     (ms,) = _max_over_ranks(ctx, [ms])
+    # the same with the caller's SODM_TUNE_LATENCY flag (96-register build, for launches of about one wave or less: DESIGN 5.1)
+    ms_lat = _timed_launches(ctx, lambda: c5(_ffi.COMPAT_REFERENCE | _ffi.TUNE_LATENCY), flush=True)
+    (ms_lat,) = _max_over_ranks(ctx, [ms_lat])
     full = c5()
     ms_ll = _timed_launches(ctx, lambda: engine.loglik("negative_binomial", traj, 0.0, [[0], [1], [2], [3]], np.arange(13) * 7.0, ydata,
                                                        ll_arg=4 * [0.03], lp=lp, dev=dev), flush=True)
@@ -891,7 +896,7 @@ def bench_c5(ctx, args):
     got, _ = engine.loglik("negative_binomial", ym, 0.0, [[0], [1], [2], [3]], np.arange(13.0), g["ydata"], ll_arg=4 * [0.03], dev=dev)
     rel = abs(float(got[0]) - float(g["negbin_vec"])) / abs(float(g["negbin_vec"]))
     return {"value": P / (ms * 1e-3), "unit": "log-posteriors/s", "n_particles_total": P, "n_particles_per_gpu": n, "ms": ms,
-            "loglik_kernel_ms": ms_ll, "finite_fraction": float(torch.isfinite(full).double().mean()),
+            "ms_with_latency_flag": ms_lat, "loglik_kernel_ms": ms_ll, "finite_fraction": float(torch.isfinite(full).double().mean()),
             "binomial_variates_per_s": P * 168 * 24 / (ms * 1e-3),
             "roofline": {"bound": "hbm", **{k: v for k, v in _hbm_roofline(ctx, n * (4 * 85 * 4 * 2 + 5 * 8 + 8), ms).items() if k != "bound"},
                          "note": "the embedded 168-step tau-leap launch is sampler-bound and, below ~10^5 trajectories per GPU, "

@@ -10,14 +10,18 @@
 
 namespace sodm {
 
+// One warp per block: the hardware then balances a launch over the SMs warp by warp (a strong-scaling shard of 125 000
+// trajectories is 0.8 waves: with 128-thread blocks an SM gets 6 or 7 blocks, with 32-thread blocks 26 or 27 warps), and 28
+// resident blocks leave 72 registers per thread instead of 64.  Measured (B200, influenza, full season, profiles/r2_shard_ab.txt):
+// 125 000 trajectories 16.14 -> 15.53 ms, 10^6 103.19 -> 102.19 ms; 64- and 256-thread blocks are slower than either.
 #ifndef SODM_JUMP_BLOCK
-#define SODM_JUMP_BLOCK 128
+#define SODM_JUMP_BLOCK 32
 #endif
 constexpr int JUMP_BLOCK = SODM_JUMP_BLOCK;
 // Resident blocks per SM the compiler must allow for.  The samplers are issue-bound, so resident warps matter more than
-// registers (round 1, legacy walk on influenza: 352 / 272 / 262 / 259 ms at 1 / 5 / 6 / 8 blocks).
+// registers (round 1, legacy walk on influenza, 128-thread blocks: 352 / 272 / 262 / 259 ms at 1 / 5 / 6 / 8 blocks).
 #ifndef SODM_WALK_MIN_BLOCKS
-#define SODM_WALK_MIN_BLOCKS 8
+#define SODM_WALK_MIN_BLOCKS 28
 #endif
 
 // shared-memory words of the per-lane draw order (one byte per draw and lane)
@@ -45,7 +49,7 @@ static size_t tau_leap_smem(int n_tdpf_values, bool queue = false) {
 // reject decision somewhere (measured: 2 of 60 000 final states differ; with -fmad=false none do, at +3.2 % on the headline
 // launch).  Same law, different rounding: a run is reproducible and shard-invariant for a given flag, and a launcher that
 // switched builds by launch size would make results depend on the number of GPUs.
-constexpr int LATENCY_MIN_BLOCKS = 5;
+constexpr int LATENCY_MIN_BLOCKS = 640 / JUMP_BLOCK;      // 20 warps per SM: 96 registers
 
 template <class M, typename OutT, bool ALIGNED, bool QUEUE, int MINB>
 __global__ void __launch_bounds__(JUMP_BLOCK, MINB) tau_leap_kernel(const __grid_constant__ JumpLaunch L) {
