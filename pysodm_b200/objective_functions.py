@@ -284,6 +284,8 @@ class log_posterior_probability:
                 if arg not in (None, [], ()):
                     raise ValueError("the likelihood function `ll_poisson` takes no additional arguments")
                 self.log_likelihood_fnc_args.append(None)
+            elif isinstance(arg, pd.Series):                  # aligned with the data's own index in _build_plan
+                self.log_likelihood_fnc_args.append(arg)
             else:
                 self.log_likelihood_fnc_args.append(np.asarray(arg, dtype=np.float64))
 
@@ -361,10 +363,26 @@ class log_posterior_probability:
             weights = [[float(w[c]) for c in np.flatnonzero(w)] for w in cols_w]
             if all(x == 1.0 for w in weights for x in w):
                 weights = None
+        # the extra argument (sigma / alpha): a scalar, one value per data column, or one value per datapoint -- an array of the
+        # data's shape or a pd.Series on the data's own index (the reference's weighted-least-squares use of ll_normal,
+        # objective_functions.py:1396-1454), brought into the (time, *axes) order of `ydata` like the data itself
         arg = self.log_likelihood_fnc_args[i]
-        if arg is not None and arg.ndim > 0 and arg.shape not in ((ydata.shape[1],), ydata.shape) and arg.size != 1:
-            raise ValueError(f"the extra argument of the {i}th log-likelihood function has shape {arg.shape}, "
-                             f"which does not match the data {ydata.shape}")
+        if isinstance(arg, pd.Series):
+            if not arg.index.equals(d.index):
+                raise ValueError(f"index of pd.Series containing the extra argument of the {i}th log-likelihood function must "
+                                 f"match the index of the {i}th dataset")
+            a = arg.reorder_levels([self.time_index] + axes) if axes else arg
+            arg = a.reindex(full).to_numpy(dtype=np.float64).reshape(ydata.shape)
+        elif arg is not None and arg.ndim == 1 and ydata.shape[1] == 1 and arg.shape[0] == ydata.shape[0] and arg.size != 1:
+            arg = arg.reshape(ydata.shape)                       # one value per datapoint of a dataset without extra axes
+        if arg is not None:
+            if arg.ndim > 0 and arg.shape not in ((ydata.shape[1],), ydata.shape) and arg.size != 1:
+                raise ValueError(f"the extra argument of the {i}th log-likelihood function has shape {arg.shape}, "
+                                 f"which does not match the data {ydata.shape}")
+            if not np.all(arg > 0):                              # sigma = 0 would score +inf on the device
+                raise ValueError(f"the extra argument of the {i}th log-likelihood function ({self._kinds[i]}: standard deviation / "
+                                 "overdispersion) must be strictly positive")
+            self.log_likelihood_fnc_args[i] = arg
         return {"columns": columns, "weights": weights, "t_data": t_data, "ydata": ydata}
 
     # -------------------------------------------------------------------------------------------------------------

@@ -203,6 +203,18 @@ def test_alignment_plan():
                                      log_prior_prob_fnc=[log_prior_normal], log_prior_prob_fnc_args=[{"avg": 0.02, "stdev": 0.01}])
     from scipy.stats import norm
     assert lpp2.compute_log_prior_probability([[0.03]])[0] == pytest.approx(norm.logpdf(0.03, 0.02, 0.01))
+    # extra arguments per DATAPOINT (the reference's weighted use of ll_normal, objective_functions.py:1396-1454): a pd.Series on
+    # the data's own index is brought into the (time, age) order of the data matrix; an array of a dataset without extra axes
+    # may be 1-D; non-positive values and foreign indices are refused
+    sig = pd.Series(1.0 + np.arange(10.0), index=idx)
+    lpp3 = log_posterior_probability(m, ["beta"], [(1e-6, 0.08)], [data, data.groupby(level="date").sum()], ["Im_inc", "Id"],
+                                     [ll_normal, ll_normal], [sig, np.arange(1.0, 6.0)], start_sim="2017-12-01")
+    assert np.array_equal(lpp3.log_likelihood_fnc_args[0], (1.0 + np.arange(10.0)).reshape(2, 5).T)
+    assert lpp3.log_likelihood_fnc_args[1].shape == (5, 1)
+    with pytest.raises(ValueError, match="strictly positive"):
+        log_posterior_probability(m, ["beta"], [(1e-6, 0.08)], [data], ["Im_inc"], [ll_normal], [[0.0, 1.0]], start_sim="2017-12-01")
+    with pytest.raises(ValueError, match="must match the index"):
+        log_posterior_probability(m, ["beta"], [(1e-6, 0.08)], [data], ["Im_inc"], [ll_normal], [sig.iloc[:-1]], start_sim="2017-12-01")
     with pytest.raises(Exception, match="not a valid model parameter"):
         log_posterior_probability(m, ["zeta"], [(0, 1)], [data], ["Im_inc"], [ll_poisson], [[]])
     with pytest.raises(NotImplementedError, match="no device implementation"):
