@@ -817,7 +817,11 @@ def emit(graph, outputs, ctype, leaf_expr, prefix="v"):
         if op in ("add", "sub", "mul", "div"):
             if ctype == "int" and op == "div":
                 raise TraceError("division in integer bookkeeping")
-            expr = f"{a[0]} {'+-*/'['add sub mul div'.split().index(op)]} {a[1]}"
+            if op == "div" and ctype == "double":
+                # same quotient bit for bit, but a zero numerator does not take the FP64 division's slow path (csrc/fdiv.cuh)
+                expr = f"::sodm::div_z({a[0]}, {a[1]})"
+            else:
+                expr = f"{a[0]} {'+-*/'['add sub mul div'.split().index(op)]} {a[1]}"
         elif op in ("lt", "le", "gt", "ge", "eq", "ne"):
             lines.append(f"const bool {prefix}{i} = {a[0]} {dict(lt='<', le='<=', gt='>', ge='>=', eq='==', ne='!=')[op]} {a[1]};")
             name[i] = f"{prefix}{i}"

@@ -17,6 +17,7 @@
 //              order (state, transition, element) and the effect of one event of a channel.
 // Rates that do not depend on the state are folded into per-trajectory constants by `prepare`.
 #pragma once
+#include "fdiv.cuh"
 #include <cmath>
 #include <cstdint>
 #include "binomial.cuh"
@@ -133,14 +134,14 @@ struct SirSiJump {
     }
     __host__ __device__ static void propensities(const int* y, const double* par, double* a) {
         const double Sv = y[12], Iv = y[13];
-        const double frac_v = Iv / (Sv + Iv);
+        const double frac_v = div_z(Iv, Sv + Iv);                     // zero counts stay on the division's fast path (fdiv.cuh)
         double force = 0.0;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const double S = y[g], I = y[4 + g], R = y[8 + g];
             a[g] = S * (par[g] * frac_v);
             a[4 + g] = I * (1.0 / par[5]);
-            force += par[g] * (I / (S + I + R));
+            force += par[g] * div_z(I, S + I + R);
         }
         a[8] = Sv * force;
         a[9] = Sv * (1.0 / par[4]);
@@ -242,7 +243,7 @@ struct InfluenzaJump {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const double T = (double)y[g] + (double)y[4 + g] + (double)y[8 + g] + (double)y[12 + g] + (double)y[16 + g] + (double)y[20 + g];
-            x[g] = ((double)y[8 + g] + (double)y[12 + g] + 0.22 * (double)y[16 + g]) / T;
+            x[g] = div_z((double)y[8 + g] + (double)y[12 + g] + 0.22 * (double)y[16 + g], T);
         }
         const double e_rate = 1.0 / par[0], inv_gamma = 1.0 / par[2], d_rate = 1.0 / par[3];
 #pragma unroll

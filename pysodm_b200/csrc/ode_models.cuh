@@ -2,6 +2,7 @@
 // one model's `integrate(t, *states, *parameters)` for a single trajectory, FP64 throughout (the parity
 // bar is rtol 1e-6 against scipy's FP64 RK45).
 #pragma once
+#include "fdiv.cuh"
 #include <cmath>
 #include <cstdint>
 
@@ -67,7 +68,7 @@ struct PpbbOde {
     static constexpr int N = 4, NPAR = 6;
     __host__ __device__ static void rhs(double, const double* y, const double* par, double* dy) {
         const double S = y[0], A = y[1], Es = y[2], W = y[3];
-        const double v = par[0] * (par[1] * (S * A - (1.0 / par[5]) * Es * W) / (A + par[2] * S + par[3] * W + par[4] * Es));
+        const double v = par[0] * div_z(par[1] * (S * A - (1.0 / par[5]) * Es * W), A + par[2] * S + par[3] * W + par[4] * Es);
         dy[0] = -v;
         dy[1] = -v;
         dy[2] = v;
@@ -111,8 +112,8 @@ struct PfrNode {
             for (int i = 0; i < 4; ++i) { dcf[i] = 0.0; dcs[i] = 0.0; }
             return;
         }
-        const double v = (c.Vf_Ks * (cs[0] * cs[1] - c.inv_keq * cs[2] * cs[3]) /
-                          (cs[1] + c.R_AS * cs[0] + c.R_AW * cs[3] + c.R_Es * cs[2])) / 60.0;
+        const double v = div_z(div_z(c.Vf_Ks * (cs[0] * cs[1] - c.inv_keq * cs[2] * cs[3]),
+                                     cs[1] + c.R_AS * cs[0] + c.R_AW * cs[3] + c.R_Es * cs[2]), 60.0);   // x / y / 60, zeros on the fast path (fdiv.cuh)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const double right = outlet ? cl[i] : cr[i];

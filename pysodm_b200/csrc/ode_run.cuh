@@ -23,6 +23,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include "fdiv.cuh"
 #include "jump_models.cuh"   // status bits
 #include "ode_models.cuh"
 
@@ -97,7 +98,7 @@ __host__ __device__ __forceinline__ double rms_scaled(Sys& sys, const double* v,
     double acc = 0.0;
 #pragma unroll
     for (int e = 0; e < Sys::NL; ++e) {
-        const double r = sys.active(e) ? v[e] / scale[e] : 0.0;
+        const double r = sys.active(e) ? div_z(v[e], scale[e]) : 0.0;
         acc += r * r;
     }
     return sqrt(sys.reduce(acc)) / sqrt((double)sys.n_total());
@@ -227,7 +228,7 @@ struct Rk45 {
                 const double sc = atol + fmax(fabs(y[e]), fabs(ynew[e])) * rtol;
                 const double err = (K1[e] * DP_E1 + S.get(1, e) * DP_E3 + S.get(2, e) * DP_E4 + S.get(3, e) * DP_E5 + S.get(4, e) * DP_E6 +
                                     K7[e] * DP_E7) * h;
-                const double r = sys.active(e) ? err / sc : 0.0;
+                const double r = sys.active(e) ? div_z(err, sc) : 0.0;            // zero error estimates stay on the fast path (fdiv.cuh)
                 acc += r * r;
             }
             const double error_norm = sqrt(sys.reduce(acc)) / sqrt((double)sys.n_total());

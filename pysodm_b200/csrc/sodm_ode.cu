@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(PFR_BLOCK, SODM_PFR_MIN_BLOCKS) ode_pfr_warp_k
     double y[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        y[e] = 0.0;
-        if (sys.active(e)) {
+        y[e] = 1.0;                      // lanes without a node: results are never used, but 0 / 0 in their rate law would drag
+        if (sys.active(e)) {             // the warp through the FP64 division's slow path at every stage (fdiv.cuh)
             const int s = sys.global_index(e);
             y[e] = L.y0_bcast ? L.y0[s] : L.y0[(int64_t)s * L.ld_in + i];
         }
