@@ -409,6 +409,12 @@ __host__ __device__ __forceinline__ void sample_worklist_queue(const AttemptKey&
     }
 }
 
+// (Measured and dropped in round 2: POOLING the exact tests of a trip over the warp -- four lanes per candidate, each computing a
+// quarter of the FP32 log-pmf ratio, candidates fetched by shuffle.  The exact test is a third of the walk's executed
+// instructions at 8-11 active lanes, and the pooled form runs it at 32; but the warp vote that pooling needs makes all lanes
+// meet on every trip, and the walk lives on lanes NOT meeting: a lane inside a 20-iteration inversion holds nobody up while its
+// neighbours run ahead as a diverged group.  107.7 -> 153 ms per 2^20 trajectories; with __fns for the candidate-to-lane map
+// 175 ms.)
 // PER-LANE WALK (default sampler): each lane draws its slots one after the other with a private Philox4x32 stream, retrying
 // a rejected attempt on its next trip through the loop while its neighbours move on to their next slot -- the warp runs for
 // max_lane(sum of attempts) trips instead of sum_slot(max_lane attempts); the exact test runs inside the trip that needs it.
