@@ -88,14 +88,33 @@ __host__ __device__ __forceinline__ void emit_counts(const JumpLaunch& L, int64_
 // value at grid time g of the straight line through (t_old, y_old), (t_new, y_new) -- np.interp's own
 // arithmetic, slope*(x - xp[j]) + fp[j], kept free of FMA contraction so it rounds like NumPy
 __host__ __device__ __forceinline__ double lerp_np(double g, double t_old, double t_new, double y_old, double y_new) {
+    // A state that did not change between the two step states (all but one or two of them after an SSA event) has slope
+    // 0 / dt -- a quotient that takes the out-of-line slow path of the FP64 division (fdiv.cuh).  Such a state is divided as
+    // 1 / dt instead and its value y_old returned as it is: 0 * (g - t_old) + y_old, what np.interp computes, bit for bit.
 #ifdef __CUDA_ARCH__
-    const double slope = __ddiv_rn(__dsub_rn(y_new, y_old), __dsub_rn(t_new, t_old));
-    return __dadd_rn(__dmul_rn(slope, __dsub_rn(g, t_old)), y_old);
+    const double dy = __dsub_rn(y_new, y_old);
+    const bool flat = dy == 0.0;
+    const double slope = __ddiv_rn(flat ? 1.0 : dy, __dsub_rn(t_new, t_old));
+    const double v = __dadd_rn(__dmul_rn(slope, __dsub_rn(g, t_old)), y_old);
+    return flat ? y_old : v;
 #else
+    if (y_new == y_old) return y_old;
     volatile double slope = (y_new - y_old) / (t_new - t_old);
     volatile double prod = slope * (g - t_old);
     return prod + y_old;
 #endif
+}
+
+// The interpolation onto a grid time is needed on the few steps / events that cross one, but it is pure arithmetic on values
+// that do not change inside the crossing loop, so the compiler hoists it in front of the loop and evaluates it -- one FP64
+// division per state -- at EVERY step or event (ncu on the SSA kernel: 14 divisions per event, all through the slow path, 40 %
+// of the kernel's instructions).  Passing the step's start time through an opaque asm statement inside the loop keeps the
+// arithmetic where it belongs.
+__host__ __device__ __forceinline__ double pin_in_loop(double x) {
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+d"(x));
+#endif
+    return x;
 }
 
 template <class M, typename OutT>
@@ -520,7 +539,7 @@ __host__ __device__ __forceinline__ void tau_leap_trajectory(const JumpLaunch& L
             // general tau: interpolate onto the integer grid between consecutive step states
             const double t_new = t + L.tau;
             while (j < L.n_out && L.t0 + (double)j <= t_new) {
-                if (active) emit_interp<M, OutT>(L, i, j, L.t0 + (double)j, t, t_new, y_old, y);
+                if (active) emit_interp<M, OutT>(L, i, j, L.t0 + (double)j, pin_in_loop(t), t_new, y_old, y);
                 ++j;
             }
             t = t_new;
@@ -610,7 +629,7 @@ __host__ __device__ __forceinline__ void ssa_trajectory(const JumpLaunch& L, int
         }
         const double t_new = t + step;
         while (j < L.n_out && L.t0 + (double)j <= t_new) {
-            emit_interp<M, OutT>(L, i, j, L.t0 + (double)j, t, t_new, y_old, y);
+            emit_interp<M, OutT>(L, i, j, L.t0 + (double)j, pin_in_loop(t), t_new, y_old, y);
             ++j;
         }
         t = t_new;
