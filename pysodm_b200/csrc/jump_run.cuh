@@ -105,18 +105,6 @@ __host__ __device__ __forceinline__ double lerp_np(double g, double t_old, doubl
 #endif
 }
 
-// The interpolation onto a grid time is needed on the few steps / events that cross one, but it is pure arithmetic on values
-// that do not change inside the crossing loop, so the compiler hoists it in front of the loop and evaluates it -- one FP64
-// division per state -- at EVERY step or event (ncu on the SSA kernel: 14 divisions per event, all through the slow path, 40 %
-// of the kernel's instructions).  Passing the step's start time through an opaque asm statement inside the loop keeps the
-// arithmetic where it belongs.
-__host__ __device__ __forceinline__ double pin_in_loop(double x) {
-#ifdef __CUDA_ARCH__
-    asm volatile("" : "+d"(x));
-#endif
-    return x;
-}
-
 template <class M, typename OutT>
 __host__ __device__ __forceinline__ void emit_interp(const JumpLaunch& L, int64_t i, int j, double g,
                                                      double t_old, double t_new, const int* y_old, const int* y_new) {

@@ -465,12 +465,13 @@ __host__ __device__ __forceinline__ void fixed_step_run(Sys& sys, const OdeLaunc
             const int kj = kept_index(L, g);
             if (kj >= 0) {
                 const double tg = L.t0 + (double)g;
+                const double t_left = pin_in_loop(t);             // keeps the NL divisions below inside this loop (fdiv.cuh)
 #pragma unroll
                 for (int e = 0; e < NL; ++e) {
                     if (tg == t_new) ytmp[e] = y[e];
                     else {   // np.interp: slope*(x - xp[j]) + fp[j]
-                        const double slope = (y[e] - y_old[e]) / (t_new - t);
-                        ytmp[e] = add_rn(mul_rn(slope, tg - t), y_old[e]);
+                        const double slope = div_z(y[e] - y_old[e], t_new - t_left);
+                        ytmp[e] = add_rn(mul_rn(slope, tg - t_left), y_old[e]);
                     }
                 }
                 store_grid<Sys, OutT>(sys, L, i, kj, ytmp);
