@@ -80,6 +80,7 @@ extern "C" {
 #define SODM_ODE_RK45      0   /* scipy.integrate.solve_ivp(method='RK45') step for step (base.py:855) */
 #define SODM_ODE_EULER     1   /* explicit Euler with step tau + interpolation (base.py:800-819) */
 #define SODM_ODE_RK4       2   /* classical fixed-step RK4 (extension; the reference has none) */
+#define SODM_ODE_RK23      3   /* scipy.integrate.solve_ivp(method='RK23') step for step (validation.py:158 lists it) */
 
 #define SODM_MAX_PARAM 64      /* flat parameter elements per model */
 #define SODM_MAX_PEERS 7       /* peer destinations of a jump launch (an 8-GPU box) */

@@ -706,7 +706,7 @@ class JumpProcess(_DeviceBackedModel):
 
 # ================================================================================================================
 class ODE(_DeviceBackedModel):
-    """Deterministic model integrated on the GPU: scipy-faithful RK45, or fixed-step Euler / RK4 when `tau` is given.
+    """Deterministic model integrated on the GPU: scipy-faithful RK45 / RK23, or fixed-step Euler / RK4 when `tau` is given.
 
     Subclasses declare `states`, `parameters`, ..., the static method `integrate(t, *states, *parameters)` and
     optionally `device_model` (a registered hand-written functor); without it `integrate` is translated (codegen.py)."""
@@ -735,10 +735,10 @@ class ODE(_DeviceBackedModel):
             self._bind_generated_functor(unit_us, date_range)
         if tau:
             dev_method = "RK4" if method == "RK4" else "euler"
-        elif method == "RK45":
-            dev_method = "RK45"
+        elif method in ("RK45", "RK23"):
+            dev_method = method
         else:
-            raise NotImplementedError(f"method '{method}' has no device implementation (available: 'RK45', or a fixed "
+            raise NotImplementedError(f"method '{method}' has no device implementation (available: 'RK45', 'RK23', or a fixed "
                                       "step `tau` for Euler / method='RK4'); there is no CPU fallback")
         saved = copy.deepcopy(self.parameters)
         try:

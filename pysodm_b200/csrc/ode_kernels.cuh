@@ -30,21 +30,23 @@ __global__ void __launch_bounds__(ODE_BLOCK) ode_thread_kernel(const __grid_cons
 #ifndef SODM_ODE_WINDOWED_MIN_BLOCKS
 #define SODM_ODE_WINDOWED_MIN_BLOCKS 4      // 128 registers; measured on C1 at 4 x 10^6 draws: 11.5 ms unbounded (162 registers), 10.0 ms at 4, 13.4 ms at 5
 #endif
-template <class M, typename OutT>
+template <class M, typename OutT, class Scheme = SchemeRK45>
 __global__ void __launch_bounds__(ODE_BLOCK, SODM_ODE_WINDOWED_MIN_BLOCKS) ode_thread_rk45_windowed_kernel(const __grid_constant__ OdeLaunch L) {
     extern __shared__ double ode_window_smem[];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    ode_thread_trajectory_windowed<M, OutT>(L, i, i < L.n_traj, ode_window_smem + threadIdx.x, ode_window<M>(), ODE_BLOCK);
+    ode_thread_trajectory_windowed<M, OutT, Scheme>(L, i, i < L.n_traj, ode_window_smem + threadIdx.x, ode_window<M>(), ODE_BLOCK);
 }
 
 template <class M, typename OutT>
 static int launch_thread_dtype(const OdeLaunch& L, int method, cudaStream_t stream) {
     const unsigned grid = (unsigned)((L.n_traj + ODE_BLOCK - 1) / ODE_BLOCK);
     if constexpr (ode_window<M>() > 0) {
-        if (method == SODM_ODE_RK45) {
+        if (method == SODM_ODE_RK45 || method == SODM_ODE_RK23) {
             constexpr int smem = ode_window<M>() * M::N * ODE_BLOCK * (int)sizeof(double);
-            SODM_CUDA_CHECK(cudaFuncSetAttribute(ode_thread_rk45_windowed_kernel<M, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            ode_thread_rk45_windowed_kernel<M, OutT><<<grid, ODE_BLOCK, smem, stream>>>(L);
+            void (*kernel)(OdeLaunch) = method == SODM_ODE_RK45 ? ode_thread_rk45_windowed_kernel<M, OutT, SchemeRK45>
+                                                                : ode_thread_rk45_windowed_kernel<M, OutT, SchemeRK23>;
+            SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            kernel<<<grid, ODE_BLOCK, smem, stream>>>(L);
             SODM_CUDA_CHECK(cudaGetLastError());
             return SODM_OK;
         }

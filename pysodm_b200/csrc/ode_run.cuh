@@ -140,12 +140,100 @@ struct RegisterStages {
     }
 };
 
-// The pieces of scipy's RK45 (`RungeKutta.__init__` -> select_initial_step, `_step_impl`, `RkDenseOutput`), shared by the two
+// The two explicit pairs of scipy.integrate (`_ivp/rk.py`): what differs between RK45 (Dormand-Prince 5(4), 6 stages) and
+// RK23 (Bogacki-Shampine 3(2), 3 stages) is the tableau, the error weights, the dense-output polynomial and the exponent
+// 1 / (error_estimator_order + 1) of the step-size controller; everything else -- `select_initial_step`, `_step_impl`, the
+// evaluation of the dense output -- is `RungeKutta`'s and is written once below.  K1 = f(t, y) (first same as last) and
+// Kl = f(t + h, y_new) live in registers, the stages in between in `S` (slot j = stage j + 2).
+struct SchemeRK45 {
+    static constexpr int NQ = 4;                                   // dense output: quartic
+    __host__ __device__ static constexpr double exponent() { return 0.2; }      // 1 / (4 + 1)
+    template <class Sys, class Stages>
+    __host__ __device__ static __forceinline__ void stages(Sys& sys, double t, double h, const double* y, const double* K1, Stages& S,
+                                                           double* ynew, double* Kl) {
+        constexpr int NL = Sys::NL;
+        double kt[NL], ytmp[NL];
+#pragma unroll
+        for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A21) * h;
+        sys.rhs(t + (1.0 / 5.0) * h, ytmp, kt); S.put(0, kt);
+#pragma unroll
+        for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A31 + S.get(0, e) * DP_A32) * h;
+        sys.rhs(t + (3.0 / 10.0) * h, ytmp, kt); S.put(1, kt);
+#pragma unroll
+        for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A41 + S.get(0, e) * DP_A42 + S.get(1, e) * DP_A43) * h;
+        sys.rhs(t + (4.0 / 5.0) * h, ytmp, kt); S.put(2, kt);
+#pragma unroll
+        for (int e = 0; e < NL; ++e)
+            ytmp[e] = y[e] + (K1[e] * DP_A51 + S.get(0, e) * DP_A52 + S.get(1, e) * DP_A53 + S.get(2, e) * DP_A54) * h;
+        sys.rhs(t + (8.0 / 9.0) * h, ytmp, kt); S.put(3, kt);
+#pragma unroll
+        for (int e = 0; e < NL; ++e)
+            ytmp[e] = y[e] + (K1[e] * DP_A61 + S.get(0, e) * DP_A62 + S.get(1, e) * DP_A63 + S.get(2, e) * DP_A64 + S.get(3, e) * DP_A65) * h;
+        sys.rhs(t + h, ytmp, kt); S.put(4, kt);
+#pragma unroll
+        for (int e = 0; e < NL; ++e)
+            ynew[e] = y[e] + h * (K1[e] * DP_B1 + S.get(1, e) * DP_B3 + S.get(2, e) * DP_B4 + S.get(3, e) * DP_B5 + S.get(4, e) * DP_B6);
+        sys.rhs(t + h, ynew, Kl);
+    }
+    static constexpr int NFEV = 6;
+    template <class Stages>
+    __host__ __device__ static __forceinline__ double error(const double* K1, const Stages& S, const double* Kl, int e) {
+        return K1[e] * DP_E1 + S.get(1, e) * DP_E3 + S.get(2, e) * DP_E4 + S.get(3, e) * DP_E5 + S.get(4, e) * DP_E6 + Kl[e] * DP_E7;
+    }
+    template <class Stages>
+    __host__ __device__ static __forceinline__ void dense_q(const double* K1, const Stages& S, const double* Kl, int e, double* q) {
+        q[0] = K1[e];                                             // P[0] = [1, 0, 0, 0] and P[s > 0][0] = 0
+        q[1] = K1[e] * (-8048581381.0 / 2820520608.0) + S.get(1, e) * (131558114200.0 / 32700410799.0) +
+               S.get(2, e) * (-1754552775.0 / 470086768.0) + S.get(3, e) * (127303824393.0 / 49829197408.0) +
+               S.get(4, e) * (-282668133.0 / 205662961.0) + Kl[e] * (40617522.0 / 29380423.0);
+        q[2] = K1[e] * (8663915743.0 / 2820520608.0) + S.get(1, e) * (-68118460800.0 / 10900136933.0) +
+               S.get(2, e) * (14199869525.0 / 1410260304.0) + S.get(3, e) * (-318862633887.0 / 49829197408.0) +
+               S.get(4, e) * (2019193451.0 / 616988883.0) + Kl[e] * (-110615467.0 / 29380423.0);
+        q[3] = K1[e] * (-12715105075.0 / 11282082432.0) + S.get(1, e) * (87487479700.0 / 32700410799.0) +
+               S.get(2, e) * (-10690763975.0 / 1880347072.0) + S.get(3, e) * (701980252875.0 / 199316789632.0) +
+               S.get(4, e) * (-1453857185.0 / 822651844.0) + Kl[e] * (69997945.0 / 29380423.0);
+    }
+};
+
+// scipy's RK23 (`rk.py`: C = [0, 1/2, 3/4], A = [[1/2], [0, 3/4]], B = [2/9, 1/3, 4/9], E = [5/72, -1/12, -1/9, 1/8],
+// P = [[1, -4/3, 5/9], [0, 1, -2/3], [0, 4/3, -8/9], [0, -1, 1]]); zero coefficients are left out as in RK45 (x + 0 K = x).
+struct SchemeRK23 {
+    static constexpr int NQ = 3;                                   // dense output: cubic
+    __host__ __device__ static constexpr double exponent() { return 1.0 / 3.0; }      // 1 / (2 + 1)
+    template <class Sys, class Stages>
+    __host__ __device__ static __forceinline__ void stages(Sys& sys, double t, double h, const double* y, const double* K1, Stages& S,
+                                                           double* ynew, double* Kl) {
+        constexpr int NL = Sys::NL;
+        double kt[NL], ytmp[NL];
+#pragma unroll
+        for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * (1.0 / 2.0)) * h;
+        sys.rhs(t + (1.0 / 2.0) * h, ytmp, kt); S.put(0, kt);
+#pragma unroll
+        for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (S.get(0, e) * (3.0 / 4.0)) * h;
+        sys.rhs(t + (3.0 / 4.0) * h, ytmp, kt); S.put(1, kt);
+#pragma unroll
+        for (int e = 0; e < NL; ++e) ynew[e] = y[e] + h * (K1[e] * (2.0 / 9.0) + S.get(0, e) * (1.0 / 3.0) + S.get(1, e) * (4.0 / 9.0));
+        sys.rhs(t + h, ynew, Kl);
+    }
+    static constexpr int NFEV = 3;
+    template <class Stages>
+    __host__ __device__ static __forceinline__ double error(const double* K1, const Stages& S, const double* Kl, int e) {
+        return K1[e] * (5.0 / 72.0) + S.get(0, e) * (-1.0 / 12.0) + S.get(1, e) * (-1.0 / 9.0) + Kl[e] * (1.0 / 8.0);
+    }
+    template <class Stages>
+    __host__ __device__ static __forceinline__ void dense_q(const double* K1, const Stages& S, const double* Kl, int e, double* q) {
+        q[0] = K1[e];
+        q[1] = K1[e] * (-4.0 / 3.0) + S.get(0, e) + S.get(1, e) * (4.0 / 3.0) - Kl[e];
+        q[2] = K1[e] * (5.0 / 9.0) + S.get(0, e) * (-2.0 / 3.0) + S.get(1, e) * (-8.0 / 9.0) + Kl[e];
+    }
+};
+
+// The pieces of scipy's `RungeKutta` (`__init__` -> select_initial_step, `_step_impl`, `RkDenseOutput`), shared by the two
 // drivers below: the same arithmetic in the same order whichever driver runs it.
-template <class Sys, class Stages>
+template <class Sys, class Stages, class Scheme = SchemeRK45>
 struct Rk45 {
     static constexpr int NL = Sys::NL;
-    double K1[NL], K7[NL];           // K1 = f(t, y) (FSAL), K7 = f(t + h, y_new)
+    double K1[NL], K7[NL];           // K1 = f(t, y) (FSAL), K7 = f(t + h, y_new) (the last stage, whatever its number)
     double ynew[NL];
     double rtol, atol, t_bound, t, h_abs, h, t_new;
     int nfev;
@@ -179,7 +267,7 @@ struct Rk45 {
 #pragma unroll
             for (int e = 0; e < NL; ++e) kt[e] = kt[e] - K1[e];
             const double d2 = rms_scaled(sys, kt, scale) / h0;
-            const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 0.2);
+            const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), Scheme::exponent());
             h_abs = fmin(fmin(100.0 * h0, h1), interval);
         }
     }
@@ -187,7 +275,6 @@ struct Rk45 {
     // `_step_impl`: attempts until one is accepted.  On success (t, t + h] = (t, t_new] is covered by y -> ynew with the stages in
     // K1, S, K7; returns false when the step size underflows or the error norm is not finite (status bits set).
     __host__ __device__ __forceinline__ bool step(Sys& sys, const double* y, Stages& S) {
-        double kt[NL], ytmp[NL];
         const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);   // double overload on host AND device
         if (h_abs < min_step) h_abs = min_step;
         bool rejected = false, failed = false;
@@ -198,71 +285,43 @@ struct Rk45 {
             if (t_new - t_bound > 0.0) t_new = t_bound;
             h = t_new - t;
             h_abs = fabs(h);
-            // ---- rk_step ---------------------------------------------------------------------
-#pragma unroll
-            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A21) * h;
-            sys.rhs(t + (1.0 / 5.0) * h, ytmp, kt); S.put(0, kt);
-#pragma unroll
-            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A31 + S.get(0, e) * DP_A32) * h;
-            sys.rhs(t + (3.0 / 10.0) * h, ytmp, kt); S.put(1, kt);
-#pragma unroll
-            for (int e = 0; e < NL; ++e) ytmp[e] = y[e] + (K1[e] * DP_A41 + S.get(0, e) * DP_A42 + S.get(1, e) * DP_A43) * h;
-            sys.rhs(t + (4.0 / 5.0) * h, ytmp, kt); S.put(2, kt);
-#pragma unroll
-            for (int e = 0; e < NL; ++e)
-                ytmp[e] = y[e] + (K1[e] * DP_A51 + S.get(0, e) * DP_A52 + S.get(1, e) * DP_A53 + S.get(2, e) * DP_A54) * h;
-            sys.rhs(t + (8.0 / 9.0) * h, ytmp, kt); S.put(3, kt);
-#pragma unroll
-            for (int e = 0; e < NL; ++e)
-                ytmp[e] = y[e] + (K1[e] * DP_A61 + S.get(0, e) * DP_A62 + S.get(1, e) * DP_A63 + S.get(2, e) * DP_A64 + S.get(3, e) * DP_A65) * h;
-            sys.rhs(t + h, ytmp, kt); S.put(4, kt);
-#pragma unroll
-            for (int e = 0; e < NL; ++e)
-                ynew[e] = y[e] + h * (K1[e] * DP_B1 + S.get(1, e) * DP_B3 + S.get(2, e) * DP_B4 + S.get(3, e) * DP_B5 + S.get(4, e) * DP_B6);
-            sys.rhs(t + h, ynew, K7);
-            nfev += 6;
+            Scheme::stages(sys, t, h, y, K1, S, ynew, K7);         // rk_step
+            nfev += Scheme::NFEV;
             // ---- error norm --------------------------------------------------------------------
             double acc = 0.0;
 #pragma unroll
             for (int e = 0; e < NL; ++e) {
                 const double sc = atol + fmax(fabs(y[e]), fabs(ynew[e])) * rtol;
-                const double err = (K1[e] * DP_E1 + S.get(1, e) * DP_E3 + S.get(2, e) * DP_E4 + S.get(3, e) * DP_E5 + S.get(4, e) * DP_E6 +
-                                    K7[e] * DP_E7) * h;
+                const double err = Scheme::error(K1, S, K7, e) * h;
                 const double r = sys.active(e) ? div_z(err, sc) : 0.0;            // zero error estimates stay on the fast path (fdiv.cuh)
                 acc += r * r;
             }
             const double error_norm = sqrt(sys.reduce(acc)) / sqrt((double)sys.n_total());
             if (error_norm < 1.0) {
-                double factor = error_norm == 0.0 ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -0.2));
+                double factor = error_norm == 0.0 ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -Scheme::exponent()));
                 if (rejected) factor = fmin(1.0, factor);
                 h_abs *= factor;
                 break;
             }
             if (!(error_norm == error_norm)) { st |= ST_NONFINITE; failed = true; break; }
-            h_abs *= fmax(0.2, 0.9 * pow(error_norm, -0.2));
+            h_abs *= fmax(0.2, 0.9 * pow(error_norm, -Scheme::exponent()));
             rejected = true;
         }
         if (failed) st |= ST_STEP_TOO_SMALL;
         return !failed;
     }
 
-    // RkDenseOutput of the last accepted step at grid time tg in [t, t_new]
+    // RkDenseOutput of the last accepted step at grid time tg in [t, t_new]: y + h (q0 x + q1 x^2 + ...), x = (tg - t) / h
     __host__ __device__ __forceinline__ void dense(const double* y, const Stages& S, double tg, double* out) const {
         const double x = (tg - t) / h;
         const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
 #pragma unroll
         for (int e = 0; e < NL; ++e) {
-            const double q0 = K1[e];                        // P[0] = [1, ...] and P[s>0][0] = 0
-            const double q1 = K1[e] * (-8048581381.0 / 2820520608.0) + S.get(1, e) * (131558114200.0 / 32700410799.0) +
-                              S.get(2, e) * (-1754552775.0 / 470086768.0) + S.get(3, e) * (127303824393.0 / 49829197408.0) +
-                              S.get(4, e) * (-282668133.0 / 205662961.0) + K7[e] * (40617522.0 / 29380423.0);
-            const double q2 = K1[e] * (8663915743.0 / 2820520608.0) + S.get(1, e) * (-68118460800.0 / 10900136933.0) +
-                              S.get(2, e) * (14199869525.0 / 1410260304.0) + S.get(3, e) * (-318862633887.0 / 49829197408.0) +
-                              S.get(4, e) * (2019193451.0 / 616988883.0) + K7[e] * (-110615467.0 / 29380423.0);
-            const double q3 = K1[e] * (-12715105075.0 / 11282082432.0) + S.get(1, e) * (87487479700.0 / 32700410799.0) +
-                              S.get(2, e) * (-10690763975.0 / 1880347072.0) + S.get(3, e) * (701980252875.0 / 199316789632.0) +
-                              S.get(4, e) * (-1453857185.0 / 822651844.0) + K7[e] * (69997945.0 / 29380423.0);
-            out[e] = y[e] + h * (q0 * x + q1 * x2 + q2 * x3 + q3 * x4);
+            double q[4];
+            q[3] = 0.0;
+            Scheme::dense_q(K1, S, K7, e, q);
+            if (Scheme::NQ == 4) out[e] = y[e] + h * (q[0] * x + q[1] * x2 + q[2] * x3 + q[3] * x4);
+            else out[e] = y[e] + h * (q[0] * x + q[1] * x2 + q[2] * x3);
         }
     }
 
@@ -276,10 +335,10 @@ struct Rk45 {
 
 // Driver 1: every grid point is stored as soon as its step is accepted.  For systems whose lanes move in lockstep (the
 // reactor kernel: all lanes of a draw belong to ONE trajectory) and for the CPU harness.
-template <class Sys, typename OutT, class Stages>
+template <class Sys, typename OutT, class Stages, class Scheme = SchemeRK45>
 __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, int64_t i, double* y, Stages& S) {
     constexpr int NL = Sys::NL;
-    Rk45<Sys, Stages> R;
+    Rk45<Sys, Stages, Scheme> R;
     double ytmp[NL];
     int g = 0;                                                        // next grid point to emit
     R.init(sys, L, y);
@@ -316,12 +375,12 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
 // points: a lane parks its values in shared memory ([point][element][thread]), stops stepping once its window is full, and
 // when the whole warp is there every (element, point) row is stored by all lanes at once -- 256 contiguous bytes.  A lane
 // that runs ahead waits at most one window; the warp takes max-over-lanes steps either way.  The arithmetic is driver 1's.
-template <class Sys, typename OutT, class Stages>
+template <class Sys, typename OutT, class Stages, class Scheme = SchemeRK45>
 __device__ __forceinline__ void rk45_run_windowed(Sys& sys, const OdeLaunch& L, int64_t i, bool valid, double* y, Stages& S,
                                                   double* win, int W, int stride) {
     constexpr int NL = Sys::NL;
     constexpr unsigned FULL = 0xffffffffu;
-    Rk45<Sys, Stages> R;
+    Rk45<Sys, Stages, Scheme> R;
     double ytmp[NL];
     bool pending = false, dead = !valid;
     // the next kept grid point: grid index g, kept index kj (kept points are g = 0, s, 2 s, .. or the last one alone); carried
@@ -401,10 +460,10 @@ __device__ __forceinline__ void rk45_run_windowed(Sys& sys, const OdeLaunch& L, 
 #endif
 
 // the stages in registers (thread-per-trajectory systems)
-template <class Sys, typename OutT>
+template <class Sys, typename OutT, class Scheme = SchemeRK45>
 __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, int64_t i, double* y) {
     RegisterStages<Sys::NL> S;
-    rk45_run<Sys, OutT, RegisterStages<Sys::NL>>(sys, L, i, y, S);
+    rk45_run<Sys, OutT, RegisterStages<Sys::NL>, Scheme>(sys, L, i, y, S);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -538,7 +597,7 @@ __host__ __device__ __forceinline__ void load_ode_params(const OdeLaunch& L, int
 
 #ifdef __CUDACC__
 // thread-per-trajectory RK45 with windowed, coalesced output (rk45_run_windowed); `valid` = the thread owns a trajectory
-template <class M, typename OutT>
+template <class M, typename OutT, class Scheme = SchemeRK45>
 __device__ __forceinline__ void ode_thread_trajectory_windowed(const OdeLaunch& L, int64_t i, bool valid, double* win, int W, int stride) {
     double par[M::NPAR], y[M::N];
     const int64_t src = valid ? i : 0;
@@ -547,7 +606,7 @@ __device__ __forceinline__ void ode_thread_trajectory_windowed(const OdeLaunch& 
     for (int s = 0; s < M::N; ++s) y[s] = L.y0_bcast ? L.y0[s] : L.y0[(int64_t)s * L.ld_in + src];
     ThreadSystem<M> sys{par};
     RegisterStages<M::N> S;
-    rk45_run_windowed<ThreadSystem<M>, OutT, RegisterStages<M::N>>(sys, L, i, valid, y, S, win, W, stride);
+    rk45_run_windowed<ThreadSystem<M>, OutT, RegisterStages<M::N>, Scheme>(sys, L, i, valid, y, S, win, W, stride);
 }
 #endif
 
@@ -560,6 +619,7 @@ __host__ __device__ __forceinline__ void ode_thread_trajectory(const OdeLaunch& 
     for (int s = 0; s < M::N; ++s) y[s] = L.y0_bcast ? L.y0[s] : L.y0[(int64_t)s * L.ld_in + i];
     ThreadSystem<M> sys{par};
     if (WITH_RK45 && method == SODM_ODE_RK45) rk45_run<ThreadSystem<M>, OutT>(sys, L, i, y);
+    else if (WITH_RK45 && method == SODM_ODE_RK23) rk45_run<ThreadSystem<M>, OutT, SchemeRK23>(sys, L, i, y);
     else if (method == SODM_ODE_EULER) fixed_step_run<ThreadSystem<M>, OutT, false>(sys, L, i, y);
     else fixed_step_run<ThreadSystem<M>, OutT, true>(sys, L, i, y);
 }

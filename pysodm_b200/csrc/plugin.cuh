@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(ODE_BLOCK, SODM_GEN_WARP_MIN_BLOCKS) ode_gen_w
     }
     __syncwarp();
     if (method == SODM_ODE_RK45) rk45_run<GenWarpSystem<W>, OutT>(sys, L, i, y);
+    else if (method == SODM_ODE_RK23) rk45_run<GenWarpSystem<W>, OutT, SchemeRK23>(sys, L, i, y);
     else if (method == SODM_ODE_EULER) fixed_step_run<GenWarpSystem<W>, OutT, false>(sys, L, i, y);
     else fixed_step_run<GenWarpSystem<W>, OutT, true>(sys, L, i, y);
 }

@@ -144,6 +144,9 @@ __global__ void __launch_bounds__(PFR_BLOCK, SODM_PFR_MIN_BLOCKS) ode_pfr_warp_k
     if (method == SODM_ODE_RK45) {
         SharedStages S{stages + threadIdx.x};
         rk45_run<PfrBlockSystem<NW>, OutT, SharedStages>(sys, L, i, y, S);
+    } else if (method == SODM_ODE_RK23) {
+        SharedStages S{stages + threadIdx.x};
+        rk45_run<PfrBlockSystem<NW>, OutT, SharedStages, SchemeRK23>(sys, L, i, y, S);
     } else if (method == SODM_ODE_EULER) fixed_step_run<PfrBlockSystem<NW>, OutT, false>(sys, L, i, y);
     else fixed_step_run<PfrBlockSystem<NW>, OutT, true>(sys, L, i, y);
 }

@@ -349,6 +349,46 @@ def gen_ode():
 
 
 # ------------------------------------------------------------------------------------------------
+def gen_ode_rk23():
+    """`method='RK23'` of the reference's ODE.sim (validation.py:158 -> solve_ivp, base.py:855): the tutorial SIR for 30 draws
+    of beta, SIR_SI and the enzyme-kinetics batch reactor -> tests/golden/ode_rk23.npz."""
+    out = {}
+
+    class ODE_SIR(base.ODE):
+        states = ['S', 'I', 'R']
+        parameters = ['beta', 'gamma']
+
+        @staticmethod
+        def integrate(t, S, I, R, beta, gamma):
+            N = S + I + R
+            dS = -beta * S * I / N
+            dI = beta * S * I / N - 1 / gamma * I
+            dR = 1 / gamma * I
+            return dS, dI, dR
+    sir = ODE_SIR(initial_states={'S': 1000, 'I': 1}, parameters={'beta': 0.35, 'gamma': 5})
+    betas = np.random.default_rng(23).uniform(0.05, 3.0, size=30)          # from no epidemic to a very fast one
+    ys, nfev = [], []
+    for b in betas:
+        sir.parameters['beta'] = b
+        r = sir.sim(120, method='RK23')
+        ys.append(r['y'])
+        nfev.append(r['nfev'])
+    out['sir_betas'], out['sir_y'], out['sir_nfev'] = betas, np.stack(ys), np.array(nfev)
+    sir.parameters['beta'] = 0.35
+    r = sir.sim(120, method='RK23', rtol=1e-7)
+    out['sir_rtol1e-07_y'], out['sir_rtol1e-07_nfev'] = r['y'], np.array(r['nfev'])
+    sirsi = make_sir_si(jump=False)
+    r = sirsi.sim(120, method='RK23')
+    out['sirsi_y0'], out['sirsi_y'], out['sirsi_nfev'] = flat_y0(sirsi), r['y'], np.array(r['nfev'])
+    enz = ref_loader.load_tutorial_module('tutorials/enzyme_kinetics/models.py', 'ref_enzyme_models')
+    ppbb_par = {'c_enzyme': 10, 'Vf_Ks': 7.95e-04, 'R_AS': 0.047, 'R_AW': 1.10, 'R_Es': 0.131, 'K_eq': 0.66}
+    ppbb = enz.PPBB_model({'S': 46.0, 'A': 61.0, 'W': 37.0, 'Es': 0.0}, ppbb_par)
+    r = ppbb.sim(1500, method='RK23')
+    out['ppbb_y0'], out['ppbb_par'] = flat_y0(ppbb), np.array([ppbb_par[k] for k in ('c_enzyme', 'Vf_Ks', 'R_AS', 'R_AW', 'R_Es', 'K_eq')])
+    out['ppbb_y'], out['ppbb_nfev'] = r['y'], np.array(r['nfev'])
+    save('ode_rk23.npz', **out)
+
+
 def gen_pfr100():
     """C4 at nx = 100 (docs/enzyme_kinetics.md:408-412): the reference's packed_PFR through solve_ivp RK45 for three
     posterior draws, stride-100 subset of the 8001-point grid + nfev (nx = 100 had no reference parity)."""

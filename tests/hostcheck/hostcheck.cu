@@ -140,6 +140,7 @@ static void pfr_host(const OdeLaunch& L, int method) {
         for (int s = 0; s < 8 * NX; ++s) y[s] = L.y0_bcast ? L.y0[s] : L.y0[(int64_t)s * L.ld_in + i];
         PfrThreadSystem<NX> sys{PfrNode::coefficients(par)};
         if (method == SODM_ODE_RK45) rk45_run<PfrThreadSystem<NX>, OutT>(sys, L, i, y);
+        else if (method == SODM_ODE_RK23) rk45_run<PfrThreadSystem<NX>, OutT, SchemeRK23>(sys, L, i, y);
         else if (method == SODM_ODE_EULER) fixed_step_run<PfrThreadSystem<NX>, OutT, false>(sys, L, i, y);
         else fixed_step_run<PfrThreadSystem<NX>, OutT, true>(sys, L, i, y);
     }
