@@ -26,6 +26,10 @@ namespace sodm {
 #ifndef SODM_BINV_THRESHOLD
 #define SODM_BINV_THRESHOLD 10.0f
 #endif
+// Not a free tuning knob: BTRS's hat dominates the pmf only from n p >= 10 on (Hoermann 1993), and the bounded inversion
+// search below stops where the pmf has fallen under 1e-8, which P(X = 0) = q^n must therefore exceed: q^n >= 2^-(2 T) for
+// n p < T, p <= 1/2.  (A tuning build with T = 20 returned 0 for every draw with q^n < 1e-8 and shifted the ensemble mean by 1 %.)
+static_assert(SODM_BINV_THRESHOLD == 10.0f, "the inversion / BTRS hand-over is fixed by the validity ranges of the two samplers");
 
 // Buffered 32-bit words from a Philox stream (4 words per block, no word is wasted).
 struct PhiloxWords {
