@@ -81,6 +81,8 @@ extern "C" {
 #define SODM_ODE_EULER     1   /* explicit Euler with step tau + interpolation (base.py:800-819) */
 #define SODM_ODE_RK4       2   /* classical fixed-step RK4 (extension; the reference has none) */
 #define SODM_ODE_RK23      3   /* scipy.integrate.solve_ivp(method='RK23') step for step (validation.py:158 lists it) */
+#define SODM_ODE_DOP853    4   /* scipy.integrate.solve_ivp(method='DOP853') step for step, incl. the three extra evaluations of
+                                  its dense output on steps that contain a grid point (validation.py:158) */
 
 #define SODM_MAX_PARAM 64      /* flat parameter elements per model */
 #define SODM_MAX_PEERS 7       /* peer destinations of a jump launch (an 8-GPU box) */

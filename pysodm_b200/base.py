@@ -735,10 +735,10 @@ class ODE(_DeviceBackedModel):
             self._bind_generated_functor(unit_us, date_range)
         if tau:
             dev_method = "RK4" if method == "RK4" else "euler"
-        elif method in ("RK45", "RK23"):
+        elif method in ("RK45", "RK23", "DOP853"):
             dev_method = method
         else:
-            raise NotImplementedError(f"method '{method}' has no device implementation (available: 'RK45', 'RK23', or a fixed "
+            raise NotImplementedError(f"method '{method}' has no device implementation (available: 'RK45', 'RK23', 'DOP853', or a fixed "
                                       "step `tau` for Euler / method='RK4'); there is no CPU fallback")
         saved = copy.deepcopy(self.parameters)
         try:

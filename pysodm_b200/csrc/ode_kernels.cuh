@@ -41,10 +41,11 @@ template <class M, typename OutT>
 static int launch_thread_dtype(const OdeLaunch& L, int method, cudaStream_t stream) {
     const unsigned grid = (unsigned)((L.n_traj + ODE_BLOCK - 1) / ODE_BLOCK);
     if constexpr (ode_window<M>() > 0) {
-        if (method == SODM_ODE_RK45 || method == SODM_ODE_RK23) {
+        if (method == SODM_ODE_RK45 || method == SODM_ODE_RK23 || method == SODM_ODE_DOP853) {
             constexpr int smem = ode_window<M>() * M::N * ODE_BLOCK * (int)sizeof(double);
             void (*kernel)(OdeLaunch) = method == SODM_ODE_RK45 ? ode_thread_rk45_windowed_kernel<M, OutT, SchemeRK45>
-                                                                : ode_thread_rk45_windowed_kernel<M, OutT, SchemeRK23>;
+                                      : method == SODM_ODE_RK23 ? ode_thread_rk45_windowed_kernel<M, OutT, SchemeRK23>
+                                                                : ode_thread_rk45_windowed_kernel<M, OutT, SchemeDOP853>;
             SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             kernel<<<grid, ODE_BLOCK, smem, stream>>>(L);
             SODM_CUDA_CHECK(cudaGetLastError());

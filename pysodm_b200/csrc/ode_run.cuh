@@ -130,9 +130,9 @@ __host__ __device__ __forceinline__ void fill_nan_from(Sys& sys, const OdeLaunch
 // K2 .. K6 are written once per attempt and read back by the later stage combinations, the 5th-order solution, the error
 // estimate and -- rarely -- the dense output, so a system with many local elements can park them in shared memory
 // (the reactor kernel: 40 of 72 live doubles per lane leave the register file, sodm_ode.cu).  Same arithmetic either way.
-template <int NL>
+template <int NL, int NSLOT = 5>
 struct RegisterStages {
-    double k[5][NL];
+    double k[NSLOT][NL];
     __host__ __device__ __forceinline__ double get(int j, int e) const { return k[j][e]; }
     __host__ __device__ __forceinline__ void put(int j, const double* v) {
 #pragma unroll
@@ -146,6 +146,8 @@ struct RegisterStages {
 // evaluation of the dense output -- is `RungeKutta`'s and is written once below.  K1 = f(t, y) (first same as last) and
 // Kl = f(t + h, y_new) live in registers, the stages in between in `S` (slot j = stage j + 2).
 struct SchemeRK45 {
+    static constexpr int NSLOT = 5;                                // stage vectors kept in `S`
+    static constexpr bool LAZY_DENSE = false;                      // the dense output needs nothing beyond the step's own stages
     static constexpr int NQ = 4;                                   // dense output: quartic
     __host__ __device__ static constexpr double exponent() { return 0.2; }      // 1 / (4 + 1)
     template <class Sys, class Stages>
@@ -198,6 +200,8 @@ struct SchemeRK45 {
 // scipy's RK23 (`rk.py`: C = [0, 1/2, 3/4], A = [[1/2], [0, 3/4]], B = [2/9, 1/3, 4/9], E = [5/72, -1/12, -1/9, 1/8],
 // P = [[1, -4/3, 5/9], [0, 1, -2/3], [0, 4/3, -8/9], [0, -1, 1]]); zero coefficients are left out as in RK45 (x + 0 K = x).
 struct SchemeRK23 {
+    static constexpr int NSLOT = 2;
+    static constexpr bool LAZY_DENSE = false;
     static constexpr int NQ = 3;                                   // dense output: cubic
     __host__ __device__ static constexpr double exponent() { return 1.0 / 3.0; }      // 1 / (2 + 1)
     template <class Sys, class Stages>
@@ -228,6 +232,10 @@ struct SchemeRK23 {
     }
 };
 
+}  // namespace sodm
+#include "dop853_scheme.cuh"      // SchemeDOP853: generated from scipy's coefficient module (tools/gen_dop853.py)
+namespace sodm {
+
 // The pieces of scipy's `RungeKutta` (`__init__` -> select_initial_step, `_step_impl`, `RkDenseOutput`), shared by the two
 // drivers below: the same arithmetic in the same order whichever driver runs it.
 template <class Sys, class Stages, class Scheme = SchemeRK45>
@@ -238,6 +246,7 @@ struct Rk45 {
     double rtol, atol, t_bound, t, h_abs, h, t_new;
     int nfev;
     uint32_t st;
+    bool dense_ready;                // DOP853: the three extra stages of the last accepted step have been evaluated
 
     // RungeKutta.__init__: f(t0, y0) and select_initial_step
     __host__ __device__ __forceinline__ void init(Sys& sys, const OdeLaunch& L, const double* y) {
@@ -250,6 +259,7 @@ struct Rk45 {
         nfev = 0;
         h = 0.0;
         t_new = t;
+        dense_ready = false;
         sys.rhs(t, y, K1); ++nfev;
         const double interval = fabs(t_bound - t);
         if (interval == 0.0) {
@@ -288,19 +298,25 @@ struct Rk45 {
             Scheme::stages(sys, t, h, y, K1, S, ynew, K7);         // rk_step
             nfev += Scheme::NFEV;
             // ---- error norm --------------------------------------------------------------------
-            double acc = 0.0;
+            double error_norm;
+            if constexpr (Scheme::LAZY_DENSE) {                    // DOP853: two estimators (rk.py, _estimate_error_norm)
+                error_norm = Scheme::error_norm(sys, y, ynew, K1, S, K7, h, rtol, atol);
+            } else {
+                double acc = 0.0;
 #pragma unroll
-            for (int e = 0; e < NL; ++e) {
-                const double sc = atol + fmax(fabs(y[e]), fabs(ynew[e])) * rtol;
-                const double err = Scheme::error(K1, S, K7, e) * h;
-                const double r = sys.active(e) ? div_z(err, sc) : 0.0;            // zero error estimates stay on the fast path (fdiv.cuh)
-                acc += r * r;
+                for (int e = 0; e < NL; ++e) {
+                    const double sc = atol + fmax(fabs(y[e]), fabs(ynew[e])) * rtol;
+                    const double err = Scheme::error(K1, S, K7, e) * h;
+                    const double r = sys.active(e) ? div_z(err, sc) : 0.0;        // zero error estimates stay on the fast path (fdiv.cuh)
+                    acc += r * r;
+                }
+                error_norm = sqrt(sys.reduce(acc)) / sqrt((double)sys.n_total());
             }
-            const double error_norm = sqrt(sys.reduce(acc)) / sqrt((double)sys.n_total());
             if (error_norm < 1.0) {
                 double factor = error_norm == 0.0 ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -Scheme::exponent()));
                 if (rejected) factor = fmin(1.0, factor);
                 h_abs *= factor;
+                dense_ready = false;
                 break;
             }
             if (!(error_norm == error_norm)) { st |= ST_NONFINITE; failed = true; break; }
@@ -311,17 +327,29 @@ struct Rk45 {
         return !failed;
     }
 
-    // RkDenseOutput of the last accepted step at grid time tg in [t, t_new]: y + h (q0 x + q1 x^2 + ...), x = (tg - t) / h
-    __host__ __device__ __forceinline__ void dense(const double* y, const Stages& S, double tg, double* out) const {
+    // Dense output of the last accepted step at grid time tg in [t, t_new].  RK45 / RK23 (RkDenseOutput):
+    // y + h (q0 x + q1 x^2 + ...), x = (tg - t) / h.  DOP853: three more stages on the first call of a step (solve_ivp asks
+    // for `dense_output()` only on steps that contain a grid point, and nfev counts them), then Dop853DenseOutput.
+    __host__ __device__ __forceinline__ void dense(Sys& sys, const double* y, Stages& S, double tg, double* out) {
         const double x = (tg - t) / h;
-        const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+        if constexpr (Scheme::LAZY_DENSE) {
+            if (!dense_ready) {
+                Scheme::prepare_dense(sys, t, h, y, K1, S, K7);
+                nfev += 3;
+                dense_ready = true;
+            }
 #pragma unroll
-        for (int e = 0; e < NL; ++e) {
-            double q[4];
-            q[3] = 0.0;
-            Scheme::dense_q(K1, S, K7, e, q);
-            if (Scheme::NQ == 4) out[e] = y[e] + h * (q[0] * x + q[1] * x2 + q[2] * x3 + q[3] * x4);
-            else out[e] = y[e] + h * (q[0] * x + q[1] * x2 + q[2] * x3);
+            for (int e = 0; e < NL; ++e) out[e] = Scheme::dense_eval(x, h, y, ynew, K1, S, K7, e);
+        } else {
+            const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+#pragma unroll
+            for (int e = 0; e < NL; ++e) {
+                double q[4];
+                q[3] = 0.0;
+                Scheme::dense_q(K1, S, K7, e, q);
+                if (Scheme::NQ == 4) out[e] = y[e] + h * (q[0] * x + q[1] * x2 + q[2] * x3 + q[3] * x4);
+                else out[e] = y[e] + h * (q[0] * x + q[1] * x2 + q[2] * x3);
+            }
         }
     }
 
@@ -354,7 +382,7 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
         // ---- dense output for the grid points in (t_old, t_new] (and t0 itself on the first step) ------
         g = next_kept(L, g);
         while (g < L.n_out && L.t0 + (double)g <= R.t_new) {
-            R.dense(y, S, L.t0 + (double)g, ytmp);
+            R.dense(sys, y, S, L.t0 + (double)g, ytmp);
             store_grid<Sys, OutT>(sys, L, i, kept_index(L, g), ytmp);
             g = next_kept(L, g + 1);
         }
@@ -405,7 +433,7 @@ __device__ __forceinline__ void rk45_run_windowed(Sys& sys, const OdeLaunch& L, 
         // (a) what the pending step covers of this window
         if (pending) {
             while (kj < hi && L.t0 + (double)g <= R.t_new) {
-                R.dense(y, S, L.t0 + (double)g, ytmp);
+                R.dense(sys, y, S, L.t0 + (double)g, ytmp);
                 const int kk = kj - lo;
 #pragma unroll
                 for (int e = 0; e < NL; ++e) win[(kk * NL + e) * stride] = ytmp[e];
@@ -462,8 +490,8 @@ __device__ __forceinline__ void rk45_run_windowed(Sys& sys, const OdeLaunch& L, 
 // the stages in registers (thread-per-trajectory systems)
 template <class Sys, typename OutT, class Scheme = SchemeRK45>
 __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, int64_t i, double* y) {
-    RegisterStages<Sys::NL> S;
-    rk45_run<Sys, OutT, RegisterStages<Sys::NL>, Scheme>(sys, L, i, y, S);
+    RegisterStages<Sys::NL, Scheme::NSLOT> S;
+    rk45_run<Sys, OutT, RegisterStages<Sys::NL, Scheme::NSLOT>, Scheme>(sys, L, i, y, S);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -605,8 +633,8 @@ __device__ __forceinline__ void ode_thread_trajectory_windowed(const OdeLaunch& 
 #pragma unroll
     for (int s = 0; s < M::N; ++s) y[s] = L.y0_bcast ? L.y0[s] : L.y0[(int64_t)s * L.ld_in + src];
     ThreadSystem<M> sys{par};
-    RegisterStages<M::N> S;
-    rk45_run_windowed<ThreadSystem<M>, OutT, RegisterStages<M::N>, Scheme>(sys, L, i, valid, y, S, win, W, stride);
+    RegisterStages<M::N, Scheme::NSLOT> S;
+    rk45_run_windowed<ThreadSystem<M>, OutT, RegisterStages<M::N, Scheme::NSLOT>, Scheme>(sys, L, i, valid, y, S, win, W, stride);
 }
 #endif
 
@@ -620,6 +648,7 @@ __host__ __device__ __forceinline__ void ode_thread_trajectory(const OdeLaunch& 
     ThreadSystem<M> sys{par};
     if (WITH_RK45 && method == SODM_ODE_RK45) rk45_run<ThreadSystem<M>, OutT>(sys, L, i, y);
     else if (WITH_RK45 && method == SODM_ODE_RK23) rk45_run<ThreadSystem<M>, OutT, SchemeRK23>(sys, L, i, y);
+    else if (WITH_RK45 && method == SODM_ODE_DOP853) rk45_run<ThreadSystem<M>, OutT, SchemeDOP853>(sys, L, i, y);
     else if (method == SODM_ODE_EULER) fixed_step_run<ThreadSystem<M>, OutT, false>(sys, L, i, y);
     else fixed_step_run<ThreadSystem<M>, OutT, true>(sys, L, i, y);
 }

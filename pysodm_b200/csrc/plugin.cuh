@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(ODE_BLOCK, SODM_GEN_WARP_MIN_BLOCKS) ode_gen_w
     __syncwarp();
     if (method == SODM_ODE_RK45) rk45_run<GenWarpSystem<W>, OutT>(sys, L, i, y);
     else if (method == SODM_ODE_RK23) rk45_run<GenWarpSystem<W>, OutT, SchemeRK23>(sys, L, i, y);
+    else if (method == SODM_ODE_DOP853) return;                  // refused by the launcher: 16 stage vectors x NL positions per lane
     else if (method == SODM_ODE_EULER) fixed_step_run<GenWarpSystem<W>, OutT, false>(sys, L, i, y);
     else fixed_step_run<GenWarpSystem<W>, OutT, true>(sys, L, i, y);
 }
@@ -170,6 +171,8 @@ __global__ void __launch_bounds__(ODE_BLOCK, SODM_GEN_WARP_MIN_BLOCKS) ode_gen_w
 template <class W>
 static int launch_gen_warp(const OdeLaunch& L, int method, int dtype, cudaStream_t stream) {
     static_assert(W::NL <= 32, "at most 32 positions per lane");
+    if (method == SODM_ODE_DOP853)
+        return fail(SODM_EUNSUPPORTED, "DOP853 is not offered for generated models in the warp-per-draw layout (16 stage vectors per lane)");
     const int64_t threads = L.n_traj * 32;
     const unsigned grid = (unsigned)((threads + ODE_BLOCK - 1) / ODE_BLOCK);
     const size_t smem = (size_t)(ODE_BLOCK / 32) * (W::N + W::NPAR) * sizeof(double);

@@ -102,14 +102,20 @@ struct PfrBlockSystem {
     }
 };
 
+// stage vectors a lane parks in shared memory: K2 .. K6 of RK45 (2 of them for RK23), 14 for DOP853 (dop853_scheme.cuh)
+__host__ __device__ constexpr int pfr_stage_slots(int method) { return method == SODM_ODE_DOP853 ? SchemeDOP853::NSLOT : 5; }
+
 template <int NW>
-constexpr size_t pfr_smem_bytes() {
+constexpr size_t pfr_smem_bytes(int slots) {
     constexpr int draws = PFR_BLOCK / (32 * NW);
-    return (size_t)5 * 8 * PFR_BLOCK * sizeof(double) + draws * sizeof(PfrNode::Coef) +
+    return (size_t)slots * 8 * PFR_BLOCK * sizeof(double) + draws * sizeof(PfrNode::Coef) +
            draws * (2 * NW * 2 * 4 + 2 * NW) * sizeof(double);
 }
 
-template <int NW, typename OutT>
+// RK23 and DOP853 are kernels of their own (GROUP 1, 2; GROUP 0 = RK45 + the fixed-step schemes): inside one common kernel the
+// 14 parked stage vectors and 12-term combinations of DOP853 raise the register pressure of every method (RK45: 155 -> 160 ms
+// at nx = 25, with spills in the common path).
+template <int NW, typename OutT, int GROUP = 0>
 __global__ void __launch_bounds__(PFR_BLOCK, SODM_PFR_MIN_BLOCKS) ode_pfr_warp_kernel(const __grid_constant__ OdeLaunch L, int method) {
     extern __shared__ double pfr_smem[];
     constexpr int DRAWS = PFR_BLOCK / (32 * NW);
@@ -118,7 +124,7 @@ __global__ void __launch_bounds__(PFR_BLOCK, SODM_PFR_MIN_BLOCKS) ode_pfr_warp_k
     const int64_t i = (int64_t)blockIdx.x * DRAWS + d;
     if (i >= L.n_traj) return;                                   // all warps of a draw leave together
     double* stages = pfr_smem;
-    PfrNode::Coef* coefs = reinterpret_cast<PfrNode::Coef*>(pfr_smem + 5 * 8 * PFR_BLOCK);
+    PfrNode::Coef* coefs = reinterpret_cast<PfrNode::Coef*>(pfr_smem + pfr_stage_slots(method) * 8 * PFR_BLOCK);
     double* xch = reinterpret_cast<double*>(coefs + DRAWS) + d * (2 * NW * 2 * 4 + 2 * NW);
     PfrBlockSystem<NW> sys;
     sys.coef = coefs + d;
@@ -141,12 +147,18 @@ __global__ void __launch_bounds__(PFR_BLOCK, SODM_PFR_MIN_BLOCKS) ode_pfr_warp_k
             y[e] = L.y0_bcast ? L.y0[s] : L.y0[(int64_t)s * L.ld_in + i];
         }
     }
+    if constexpr (GROUP == 2) {
+        SharedStages S{stages + threadIdx.x};
+        rk45_run<PfrBlockSystem<NW>, OutT, SharedStages, SchemeDOP853>(sys, L, i, y, S);
+        return;
+    } else if constexpr (GROUP == 1) {
+        SharedStages S{stages + threadIdx.x};
+        rk45_run<PfrBlockSystem<NW>, OutT, SharedStages, SchemeRK23>(sys, L, i, y, S);
+        return;
+    }
     if (method == SODM_ODE_RK45) {
         SharedStages S{stages + threadIdx.x};
         rk45_run<PfrBlockSystem<NW>, OutT, SharedStages>(sys, L, i, y, S);
-    } else if (method == SODM_ODE_RK23) {
-        SharedStages S{stages + threadIdx.x};
-        rk45_run<PfrBlockSystem<NW>, OutT, SharedStages, SchemeRK23>(sys, L, i, y, S);
     } else if (method == SODM_ODE_EULER) fixed_step_run<PfrBlockSystem<NW>, OutT, false>(sys, L, i, y);
     else fixed_step_run<PfrBlockSystem<NW>, OutT, true>(sys, L, i, y);
 }
@@ -155,14 +167,13 @@ template <int NW>
 static int launch_pfr(const OdeLaunch& L, int method, int dtype, cudaStream_t stream) {
     constexpr int DRAWS = PFR_BLOCK / (32 * NW);
     const unsigned grid = (unsigned)((L.n_traj + DRAWS - 1) / DRAWS);
-    const size_t smem = pfr_smem_bytes<NW>();
-    if (dtype == SODM_F64) {
-        SODM_CUDA_CHECK(cudaFuncSetAttribute(ode_pfr_warp_kernel<NW, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ode_pfr_warp_kernel<NW, double><<<grid, PFR_BLOCK, smem, stream>>>(L, method);
-    } else {
-        SODM_CUDA_CHECK(cudaFuncSetAttribute(ode_pfr_warp_kernel<NW, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ode_pfr_warp_kernel<NW, float><<<grid, PFR_BLOCK, smem, stream>>>(L, method);
-    }
+    const size_t smem = pfr_smem_bytes<NW>(pfr_stage_slots(method));
+    void (*kernel)(OdeLaunch, int);
+    if (method == SODM_ODE_DOP853) kernel = dtype == SODM_F64 ? ode_pfr_warp_kernel<NW, double, 2> : ode_pfr_warp_kernel<NW, float, 2>;
+    else if (method == SODM_ODE_RK23) kernel = dtype == SODM_F64 ? ode_pfr_warp_kernel<NW, double, 1> : ode_pfr_warp_kernel<NW, float, 1>;
+    else kernel = dtype == SODM_F64 ? ode_pfr_warp_kernel<NW, double, 0> : ode_pfr_warp_kernel<NW, float, 0>;
+    SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, PFR_BLOCK, smem, stream>>>(L, method);
     SODM_CUDA_CHECK(cudaGetLastError());
     return SODM_OK;
 }

@@ -349,9 +349,9 @@ def gen_ode():
 
 
 # ------------------------------------------------------------------------------------------------
-def gen_ode_rk23():
-    """`method='RK23'` of the reference's ODE.sim (validation.py:158 -> solve_ivp, base.py:855): the tutorial SIR for 30 draws
-    of beta, SIR_SI and the enzyme-kinetics batch reactor -> tests/golden/ode_rk23.npz."""
+def gen_ode_rk23(method='RK23', name='ode_rk23.npz'):
+    """`method='RK23'` / `'DOP853'` of the reference's ODE.sim (validation.py:158 -> solve_ivp, base.py:855): the tutorial SIR for
+    30 draws of beta, SIR_SI and the enzyme-kinetics batch reactor -> tests/golden/ode_rk23.npz / ode_dop853.npz."""
     out = {}
 
     class ODE_SIR(base.ODE):
@@ -370,23 +370,27 @@ def gen_ode_rk23():
     ys, nfev = [], []
     for b in betas:
         sir.parameters['beta'] = b
-        r = sir.sim(120, method='RK23')
+        r = sir.sim(120, method=method)
         ys.append(r['y'])
         nfev.append(r['nfev'])
     out['sir_betas'], out['sir_y'], out['sir_nfev'] = betas, np.stack(ys), np.array(nfev)
     sir.parameters['beta'] = 0.35
-    r = sir.sim(120, method='RK23', rtol=1e-7)
+    r = sir.sim(120, method=method, rtol=1e-7)
     out['sir_rtol1e-07_y'], out['sir_rtol1e-07_nfev'] = r['y'], np.array(r['nfev'])
     sirsi = make_sir_si(jump=False)
-    r = sirsi.sim(120, method='RK23')
+    r = sirsi.sim(120, method=method)
     out['sirsi_y0'], out['sirsi_y'], out['sirsi_nfev'] = flat_y0(sirsi), r['y'], np.array(r['nfev'])
     enz = ref_loader.load_tutorial_module('tutorials/enzyme_kinetics/models.py', 'ref_enzyme_models')
     ppbb_par = {'c_enzyme': 10, 'Vf_Ks': 7.95e-04, 'R_AS': 0.047, 'R_AW': 1.10, 'R_Es': 0.131, 'K_eq': 0.66}
     ppbb = enz.PPBB_model({'S': 46.0, 'A': 61.0, 'W': 37.0, 'Es': 0.0}, ppbb_par)
-    r = ppbb.sim(1500, method='RK23')
+    r = ppbb.sim(1500, method=method)
     out['ppbb_y0'], out['ppbb_par'] = flat_y0(ppbb), np.array([ppbb_par[k] for k in ('c_enzyme', 'Vf_Ks', 'R_AS', 'R_AW', 'R_Es', 'K_eq')])
     out['ppbb_y'], out['ppbb_nfev'] = r['y'], np.array(r['nfev'])
-    save('ode_rk23.npz', **out)
+    save(name, **out)
+
+
+def gen_ode_dop853():
+    gen_ode_rk23('DOP853', 'ode_dop853.npz')
 
 
 def gen_pfr100():

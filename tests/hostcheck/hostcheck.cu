@@ -141,6 +141,7 @@ static void pfr_host(const OdeLaunch& L, int method) {
         PfrThreadSystem<NX> sys{PfrNode::coefficients(par)};
         if (method == SODM_ODE_RK45) rk45_run<PfrThreadSystem<NX>, OutT>(sys, L, i, y);
         else if (method == SODM_ODE_RK23) rk45_run<PfrThreadSystem<NX>, OutT, SchemeRK23>(sys, L, i, y);
+        else if (method == SODM_ODE_DOP853) rk45_run<PfrThreadSystem<NX>, OutT, SchemeDOP853>(sys, L, i, y);
         else if (method == SODM_ODE_EULER) fixed_step_run<PfrThreadSystem<NX>, OutT, false>(sys, L, i, y);
         else fixed_step_run<PfrThreadSystem<NX>, OutT, true>(sys, L, i, y);
     }

