@@ -395,8 +395,14 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
     }
 }
 
-#ifdef __CUDACC__
-// Driver 2 (device, one trajectory per THREAD): the lanes of a warp run their own step sequences, so with driver 1 every lane
+// "every lane of the warp": the device votes; the CPU harness runs the same driver as a warp of one lane
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ bool window_all(bool x) { return __all_sync(0xffffffffu, x); }
+#else
+inline bool window_all(bool x) { return x; }
+#endif
+
+// Driver 2 (one trajectory per THREAD): the lanes of a warp run their own step sequences, so with driver 1 every lane
 // reaches grid point j at a different moment and its 8-byte store lands alone in a 32-byte sector: ncu on C1 (tutorial SIR,
 // 10^6 draws) showed 11.4 GB of DRAM traffic for 2.9 GB of output -- partial-sector writes that L2 completes by reading the
 // line back (profiles/r2_sir_ode_ncu_summary.txt).  Here the kept grid points are delivered in WINDOWS of W consecutive
@@ -404,10 +410,9 @@ __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, 
 // when the whole warp is there every (element, point) row is stored by all lanes at once -- 256 contiguous bytes.  A lane
 // that runs ahead waits at most one window; the warp takes max-over-lanes steps either way.  The arithmetic is driver 1's.
 template <class Sys, typename OutT, class Stages, class Scheme = SchemeRK45>
-__device__ __forceinline__ void rk45_run_windowed(Sys& sys, const OdeLaunch& L, int64_t i, bool valid, double* y, Stages& S,
+__host__ __device__ __forceinline__ void rk45_run_windowed(Sys& sys, const OdeLaunch& L, int64_t i, bool valid, double* y, Stages& S,
                                                   double* win, int W, int stride) {
     constexpr int NL = Sys::NL;
-    constexpr unsigned FULL = 0xffffffffu;
     Rk45<Sys, Stages, Scheme> R;
     double ytmp[NL];
     bool pending = false, dead = !valid;
@@ -454,7 +459,7 @@ __device__ __forceinline__ void rk45_run_windowed(Sys& sys, const OdeLaunch& L, 
         }
         // (c) window complete on every lane: store it, one (element, point) row per instruction
         const bool full = kj >= hi;
-        if (__all_sync(FULL, full)) {
+        if (window_all(full)) {
             if (valid) {
                 OutT* out = (OutT*)L.out + i;
                 for (int kk = 0; kk < hi - lo; ++kk) {
@@ -485,7 +490,6 @@ __device__ __forceinline__ void rk45_run_windowed(Sys& sys, const OdeLaunch& L, 
         if (L.status) L.status[i] = (int32_t)R.st;
     }
 }
-#endif
 
 // the stages in registers (thread-per-trajectory systems)
 template <class Sys, typename OutT, class Scheme = SchemeRK45>
@@ -623,10 +627,9 @@ __host__ __device__ __forceinline__ void load_ode_params(const OdeLaunch& L, int
     }
 }
 
-#ifdef __CUDACC__
 // thread-per-trajectory RK45 with windowed, coalesced output (rk45_run_windowed); `valid` = the thread owns a trajectory
 template <class M, typename OutT, class Scheme = SchemeRK45>
-__device__ __forceinline__ void ode_thread_trajectory_windowed(const OdeLaunch& L, int64_t i, bool valid, double* win, int W, int stride) {
+__host__ __device__ __forceinline__ void ode_thread_trajectory_windowed(const OdeLaunch& L, int64_t i, bool valid, double* win, int W, int stride) {
     double par[M::NPAR], y[M::N];
     const int64_t src = valid ? i : 0;
     load_ode_params<M::NPAR>(L, src, par);
@@ -636,7 +639,6 @@ __device__ __forceinline__ void ode_thread_trajectory_windowed(const OdeLaunch& 
     RegisterStages<M::N, Scheme::NSLOT> S;
     rk45_run_windowed<ThreadSystem<M>, OutT, RegisterStages<M::N, Scheme::NSLOT>, Scheme>(sys, L, i, valid, y, S, win, W, stride);
 }
-#endif
 
 // WITH_RK45 = false: the kernel of a model whose RK45 runs through the windowed driver carries the fixed-step schemes only
 template <class M, typename OutT, bool WITH_RK45 = true>

@@ -133,8 +133,9 @@ def jump_run(model, y0, par, n_traj, t0, n_out, tau=0.5, method="tau_leap", var=
 
 
 def ode_run(model, y0, par, n_traj, t0, n_out, method="RK45", rtol=1e-4, atol=1e-6, tau=0.0, var=None,
-            model_arg=0, out_stride=1, out_last_only=False):
-    """Host run of the ODE integrators.  Returns (out[n_state, n_kept, n_traj], nfev[n_traj], status[n_traj])."""
+            model_arg=0, out_stride=1, out_last_only=False, window=0, max_steps=0):
+    """Host run of the ODE integrators.  Returns (out[n_state, n_kept, n_traj], nfev[n_traj], status[n_traj]).
+    window > 0: through the device thread kernel's windowed output driver (as a warp of one lane)."""
     L = lib()
     if not hasattr(L, "_ode_ready"):
         L.hc_ode_run.restype = C.c_int
@@ -166,6 +167,7 @@ def ode_run(model, y0, par, n_traj, t0, n_out, method="RK45", rtol=1e-4, atol=1e
         keep += [idx, vals]
     a.t0, a.n_out, a.out_stride, a.out_last_only = float(t0), int(n_out), int(out_stride), int(out_last_only)
     a.rtol, a.atol, a.tau = rtol, atol, tau
+    a.reserved, a.max_steps = int(window), int(max_steps)
     a.out, a.nfev, a.status = out.ctypes.data, nfev.ctypes.data, status.ctypes.data
     rc = L.hc_ode_run(C.byref(a))
     if rc != 0:

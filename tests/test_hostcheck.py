@@ -239,3 +239,20 @@ def test_packed_pfr_nx100_kernel_code_vs_reference(golden):
     np.testing.assert_allclose(out[:, :11, 0], ref[:, :11], rtol=1e-6, atol=1e-7)
     rel = np.abs(out[:, :, 0] - ref) / (np.abs(ref) + 1e-6)
     assert rel.max() <= 5 * float(g["pfr100_ref_self_max_rel"])
+
+
+@pytest.mark.parametrize("method", ["RK45", "RK23", "DOP853"])
+def test_windowed_output_driver_equals_the_plain_driver(golden, method):
+    """The device's thread kernel delivers kept grid points in windows (rk45_run_windowed, ode_run.cuh); run here as a warp of
+    one lane it must reproduce the plain driver bit for bit: window lengths that do and do not divide the kept count, strided
+    grids, last point only, and runs abandoned at max_steps (status set, remaining points as the plain driver leaves them)."""
+    g = golden["ode"]
+    base = dict(var={0: g["sir_betas"][:12]}, method=method)
+    for kw in (dict(n_out=121), dict(n_out=121, out_stride=7), dict(n_out=122, out_stride=11), dict(n_out=121, out_last_only=True),
+               dict(n_out=2), dict(n_out=1), dict(n_out=121, max_steps=6)):
+        n_out = kw.pop("n_out")
+        want = hc.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], 12, 0, n_out, **base, **kw)
+        for window in (1, 5, 16, 200):
+            got = hc.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], 12, 0, n_out, window=window, **base, **kw)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b, equal_nan=True), (method, n_out, kw, window)
