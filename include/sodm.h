@@ -84,6 +84,10 @@ extern "C" {
 #define SODM_ODE_DOP853    4   /* scipy.integrate.solve_ivp(method='DOP853') step for step, incl. the three extra evaluations of
                                   its dense output on steps that contain a grid point (validation.py:158) */
 
+#define SODM_ODE_RADAU     5   /* scipy.integrate.solve_ivp(method='Radau') step for step: Radau IIA with scipy's finite-difference
+                                  Jacobian (validation.py:158); thread-per-trajectory models of at most 32 equations */
+#define SODM_ODE_BDF       6   /* scipy.integrate.solve_ivp(method='BDF') step for step: variable-order NDF, same Jacobian */
+
 #define SODM_MAX_PARAM 64      /* flat parameter elements per model */
 #define SODM_MAX_PEERS 7       /* peer destinations of a jump launch (an 8-GPU box) */
 #define SODM_MAX_STATE 64      /* flat state elements of a jump model */

@@ -19,7 +19,7 @@ ST_BAD_PROB, ST_NONFINITE, ST_STEP_TOO_SMALL, ST_MAX_STEPS, ST_TRUNCATED_Y0 = 1,
 COMPAT_STAY_QUIRK, COMPAT_SSA_FIRST_MATCH, COMPAT_REFERENCE = 1, 2, 3
 TUNE_QUEUE, TUNE_LATENCY = 256, 512
 JUMP_TAU_LEAP, JUMP_SSA = 0, 1
-ODE_RK45, ODE_EULER, ODE_RK4, ODE_RK23, ODE_DOP853 = 0, 1, 2, 3, 4
+ODE_RK45, ODE_EULER, ODE_RK4, ODE_RK23, ODE_DOP853, ODE_RADAU, ODE_BDF = 0, 1, 2, 3, 4, 5, 6
 LL_POISSON, LL_NORMAL, LL_LOGNORMAL, LL_NEGBIN = 0, 1, 2, 3
 ARG_NONE, ARG_SCALAR, ARG_COLUMN, ARG_FULL = 0, 1, 2, 3
 MAX_PARAM, MAX_STATE = 64, 64

@@ -706,7 +706,8 @@ class JumpProcess(_DeviceBackedModel):
 
 # ================================================================================================================
 class ODE(_DeviceBackedModel):
-    """Deterministic model integrated on the GPU: scipy-faithful RK45 / RK23, or fixed-step Euler / RK4 when `tau` is given.
+    """Deterministic model integrated on the GPU: scipy-faithful RK45 / RK23 / DOP853 / Radau / BDF, or fixed-step Euler / RK4 when
+    `tau` is given.
 
     Subclasses declare `states`, `parameters`, ..., the static method `integrate(t, *states, *parameters)` and
     optionally `device_model` (a registered hand-written functor); without it `integrate` is translated (codegen.py)."""
@@ -735,11 +736,11 @@ class ODE(_DeviceBackedModel):
             self._bind_generated_functor(unit_us, date_range)
         if tau:
             dev_method = "RK4" if method == "RK4" else "euler"
-        elif method in ("RK45", "RK23", "DOP853"):
-            dev_method = method
+        elif method in ("RK45", "RK23", "DOP853", "Radau", "BDF"):
+            dev_method = method          # Radau / BDF: thread-per-trajectory models of at most 32 equations (csrc/implicit.cuh)
         else:
-            raise NotImplementedError(f"method '{method}' has no device implementation (available: 'RK45', 'RK23', 'DOP853', or a fixed "
-                                      "step `tau` for Euler / method='RK4'); there is no CPU fallback")
+            raise NotImplementedError(f"method '{method}' has no device implementation (available: 'RK45', 'RK23', 'DOP853', 'Radau', "
+                                      "'BDF', or a fixed step `tau` for Euler / method='RK4'); there is no CPU fallback")
         saved = copy.deepcopy(self.parameters)
         try:
             par, var, y0, _ = self._collect_draws(N, draw_function, draw_function_kwargs)
@@ -752,6 +753,11 @@ class ODE(_DeviceBackedModel):
             lib = _ffi.load()
             n_kept = int(lib.sodm_ode_n_kept(n_out, int(output_stride), int(bool(output_last_only))))
             variables, rows = self._select_rows(None)
+            if dev_method in ("Radau", "BDF"):
+                plug = self.device_model
+                if len(rows) > 32 or plug == "packed_pfr_ode" or (not isinstance(plug, str) and plug.layout.get("warp")):
+                    raise NotImplementedError(f"method '{method}' keeps a dense Jacobian per trajectory: offered for models of at most "
+                                              f"32 equations in the thread-per-trajectory layout (this model: {len(rows)}); no CPU fallback")
             host_dtype = engine.as_torch_dtype(output_dtype)
             if output == "device":
                 grid = np.arange(t0, t1 + 1)

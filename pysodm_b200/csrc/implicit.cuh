@@ -1,0 +1,715 @@
+// Implicit integrators of scipy.integrate.solve_ivp for thread-per-trajectory systems: `method='Radau'` and `method='BDF'`
+// (/root/reference/src/pySODM/models/validation.py:158 lists them; base.py:855 hands `method` to solve_ivp with no Jacobian,
+// so scipy differentiates the right-hand side numerically).  scipy is a dependency of the reference, not part of it; its
+// published algorithms (scipy 1.18, integrate/_ivp/{radau,bdf,common}.py) are restated here STEP FOR STEP -- as for RK45,
+// agreement with the reference at its tolerance needs the same step sequence, Newton iterates and Jacobian refreshes:
+//   * Radau: 3-stage Radau IIA of order 5 (Hairer & Wanner, Solving ODEs II, IV.8): simplified Newton on the collocation
+//     system in the eigenbasis of the Butcher matrix (one real and one complex LU of  mu / h I - J), third-order embedded
+//     error estimate filtered by the real LU, predictive (Gustafsson) step-size controller, cubic dense output, the initial
+//     Newton guess extrapolated from the previous step's interpolant;
+//   * BDF: variable order 1..5 NDF in quasi-constant step form (Shampine & Reichelt, The MATLAB ODE suite; Byrne &
+//     Hindmarsh 1975): backward-difference array D, rescaled by R(factor) U on every step-size change, order selection from
+//     the error estimates of orders k - 1, k, k + 1 after k + 1 equal steps;
+//   * the Jacobian by forward differences with the column-wise adaptive increment of `num_jac` (Salane 1986; Shampine &
+//     Reichelt): right-hand-side calls made there are NOT counted in `nfev` (scipy's `fun_vectorized` bypasses the counter);
+//   * dense LU with partial pivoting (LAPACK getrf / getrs order: row interchanges, multipliers scaled by the reciprocal
+//     pivot, complex pivots chosen by |re| + |im|).
+// The steppers expose the interface of `Rk45` (ode_run.cuh): init / step / dense / commit and the fields the output drivers
+// read, so both drivers (direct and windowed stores) serve them unchanged.  State lives in per-thread arrays (the Jacobian
+// and its factorisations are indexed at run time: local memory, L1-resident for the system sizes admitted here).
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+namespace sodm {
+
+struct SchemeRadau { static constexpr int NSLOT = 1; };
+struct SchemeBDF   { static constexpr int NSLOT = 1; };
+constexpr int IMPLICIT_MAX_N = 32;          // dense Jacobian + up to three factorisations per THREAD
+
+__host__ __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= DBL_MAX; }
+// products / sums that must not be contracted into an FMA (the increment of num_jac is defined by its rounding)
+__host__ __device__ __forceinline__ double imp_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b;
+    return r;
+#endif
+}
+__host__ __device__ __forceinline__ double imp_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b;
+    return r;
+#endif
+}
+
+// ---- dense LU, real and complex ----------------------------------------------------------------------------------------
+template <int N>
+struct LuReal {
+    double a[N * N];
+    int piv[N];
+    __host__ __device__ void factor() {
+        for (int k = 0; k < N; ++k) {
+            int p = k;
+            double best = fabs(a[k * N + k]);
+            for (int i = k + 1; i < N; ++i) {
+                const double v = fabs(a[i * N + k]);
+                if (v > best) { best = v; p = i; }
+            }
+            piv[k] = p;
+            if (p != k)
+                for (int j = 0; j < N; ++j) { const double x = a[k * N + j]; a[k * N + j] = a[p * N + j]; a[p * N + j] = x; }
+            const double d = a[k * N + k];
+            if (d != 0.0) {
+                const double r = 1.0 / d;
+                for (int i = k + 1; i < N; ++i) a[i * N + k] *= r;
+            }
+            for (int i = k + 1; i < N; ++i) {
+                const double l = a[i * N + k];
+                for (int j = k + 1; j < N; ++j) a[i * N + j] -= l * a[k * N + j];
+            }
+        }
+    }
+    __host__ __device__ void solve(double* b) const {
+        for (int k = 0; k < N; ++k) {
+            const int p = piv[k];
+            if (p != k) { const double x = b[k]; b[k] = b[p]; b[p] = x; }
+        }
+        for (int i = 1; i < N; ++i) {
+            double s = b[i];
+            for (int j = 0; j < i; ++j) s -= a[i * N + j] * b[j];
+            b[i] = s;
+        }
+        for (int i = N - 1; i >= 0; --i) {
+            double s = b[i];
+            for (int j = i + 1; j < N; ++j) s -= a[i * N + j] * b[j];
+            b[i] = s / a[i * N + i];
+        }
+    }
+};
+
+template <int N>
+struct LuComplex {
+    double re[N * N], im[N * N];
+    int piv[N];
+    __host__ __device__ void factor() {
+        for (int k = 0; k < N; ++k) {
+            int p = k;
+            double best = fabs(re[k * N + k]) + fabs(im[k * N + k]);
+            for (int i = k + 1; i < N; ++i) {
+                const double v = fabs(re[i * N + k]) + fabs(im[i * N + k]);
+                if (v > best) { best = v; p = i; }
+            }
+            piv[k] = p;
+            if (p != k)
+                for (int j = 0; j < N; ++j) {
+                    double x = re[k * N + j]; re[k * N + j] = re[p * N + j]; re[p * N + j] = x;
+                    x = im[k * N + j]; im[k * N + j] = im[p * N + j]; im[p * N + j] = x;
+                }
+            const double dr = re[k * N + k], di = im[k * N + k];
+            if (dr != 0.0 || di != 0.0) {
+                const double m = 1.0 / (dr * dr + di * di);
+                const double rr = dr * m, ri = -di * m;                    // 1 / pivot
+                for (int i = k + 1; i < N; ++i) {
+                    const double xr = re[i * N + k], xi = im[i * N + k];
+                    re[i * N + k] = xr * rr - xi * ri;
+                    im[i * N + k] = xr * ri + xi * rr;
+                }
+            }
+            for (int i = k + 1; i < N; ++i) {
+                const double lr = re[i * N + k], li = im[i * N + k];
+                for (int j = k + 1; j < N; ++j) {
+                    const double ur = re[k * N + j], ui = im[k * N + j];
+                    re[i * N + j] -= lr * ur - li * ui;
+                    im[i * N + j] -= lr * ui + li * ur;
+                }
+            }
+        }
+    }
+    __host__ __device__ void solve(double* br, double* bi) const {
+        for (int k = 0; k < N; ++k) {
+            const int p = piv[k];
+            if (p != k) {
+                double x = br[k]; br[k] = br[p]; br[p] = x;
+                x = bi[k]; bi[k] = bi[p]; bi[p] = x;
+            }
+        }
+        for (int i = 1; i < N; ++i) {
+            double sr = br[i], si = bi[i];
+            for (int j = 0; j < i; ++j) {
+                sr -= re[i * N + j] * br[j] - im[i * N + j] * bi[j];
+                si -= re[i * N + j] * bi[j] + im[i * N + j] * br[j];
+            }
+            br[i] = sr; bi[i] = si;
+        }
+        for (int i = N - 1; i >= 0; --i) {
+            double sr = br[i], si = bi[i];
+            for (int j = i + 1; j < N; ++j) {
+                sr -= re[i * N + j] * br[j] - im[i * N + j] * bi[j];
+                si -= re[i * N + j] * bi[j] + im[i * N + j] * br[j];
+            }
+            const double dr = re[i * N + i], di = im[i * N + i];
+            const double m = 1.0 / (dr * dr + di * di);
+            br[i] = (sr * dr + si * di) * m;
+            bi[i] = (si * dr - sr * di) * m;
+        }
+    }
+};
+
+// ---- what Radau and BDF share: tolerances, first step, the finite-difference Jacobian ---------------------------------------
+template <class Sys>
+struct ImplicitBase {
+    static constexpr int N = Sys::NL;
+    // read by the output drivers
+    double t, t_bound, t_new, h;
+    int nfev;
+    uint32_t st;
+    double ynew[N];
+    // solver state
+    double rtol, atol, newton_tol, h_abs;
+    double J[N * N], jac_factor[N];
+    bool have_factor;
+
+    __host__ __device__ static double rms(const double* v, const double* scale) {
+        double acc = 0.0;
+        for (int e = 0; e < N; ++e) { const double r = v[e] / scale[e]; acc += r * r; }
+        return sqrt(acc) / sqrt((double)N);
+    }
+
+    // validate_tol, newton_tol and `select_initial_step` with the method's error-estimator order; f0 = f(t0, y0) is given
+    __host__ __device__ void init_common(Sys& sys, const OdeLaunch& L, const double* y, const double* f0, int order) {
+        rtol = fmax(L.rtol, 100.0 * DBL_EPSILON);
+        atol = L.atol;
+        newton_tol = fmax(10.0 * DBL_EPSILON / L.rtol, fmin(0.03, sqrt(L.rtol)));
+        t_bound = L.t0 + (double)(L.n_out - 1);
+        t = L.t0;
+        t_new = t;
+        h = 0.0;
+        st = ST_OK;
+        have_factor = false;
+        const double interval = fabs(t_bound - t);
+        if (interval == 0.0) { h_abs = 0.0; return; }
+        double scale[N], y1[N], f1[N];
+        for (int e = 0; e < N; ++e) scale[e] = atol + fabs(y[e]) * rtol;
+        const double d0 = rms(y, scale), d1 = rms(f0, scale);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, interval);
+        for (int e = 0; e < N; ++e) y1[e] = y[e] + h0 * f0[e];
+        sys.rhs(t + h0, y1, f1); ++nfev;
+        for (int e = 0; e < N; ++e) f1[e] = f1[e] - f0[e];
+        const double d2 = rms(f1, scale) / h0;
+        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 1.0 / (double)(order + 1));
+        h_abs = fmin(fmin(100.0 * h0, h1), interval);
+    }
+
+    // `num_jac` (dense): J[:, j] from a forward difference in y_j whose relative increment `jac_factor[j]` persists between
+    // calls and is adapted so that the difference stays clear of its own round-off; f = f(tt, yy).  Not counted in nfev.
+    __host__ __device__ void num_jac(Sys& sys, double tt, const double* yy, const double* f) {
+        const double EPS = DBL_EPSILON;
+        const double DIFF_REJECT = pow(EPS, 0.875), DIFF_SMALL = pow(EPS, 0.75), DIFF_BIG = pow(EPS, 0.25);
+        const double MIN_FACTOR = 1e3 * EPS;
+        if (!have_factor) {
+            const double f0 = sqrt(EPS);
+            for (int j = 0; j < N; ++j) jac_factor[j] = f0;
+            have_factor = true;
+        }
+        double yp[N], fn[N], diff[N];
+        for (int e = 0; e < N; ++e) yp[e] = yy[e];
+        for (int j = 0; j < N; ++j) {
+            const double sign = f[j] >= 0.0 ? 1.0 : -1.0;
+            const double y_scale = sign * fmax(atol, fabs(yy[j]));
+            double fac = jac_factor[j];
+            double hj = imp_add(imp_add(yy[j], imp_mul(fac, y_scale)), -yy[j]);
+            while (hj == 0.0) {
+                fac *= 10.0;
+                hj = imp_add(imp_add(yy[j], imp_mul(fac, y_scale)), -yy[j]);
+            }
+            yp[j] = imp_add(yy[j], hj);
+            sys.rhs(tt, yp, fn);
+            int mi = 0;
+            double max_diff = -1.0;
+            for (int e = 0; e < N; ++e) {
+                diff[e] = fn[e] - f[e];
+                const double a = fabs(diff[e]);
+                if (a > max_diff) { max_diff = a; mi = e; }           // first maximum, as argmax
+            }
+            double scale = fmax(fabs(f[mi]), fabs(fn[mi]));
+            if (max_diff < DIFF_REJECT * scale) {
+                const double new_fac = 10.0 * fac;
+                const double h_new = imp_add(imp_add(yy[j], imp_mul(new_fac, y_scale)), -yy[j]);
+                yp[j] = imp_add(yy[j], h_new);
+                sys.rhs(tt, yp, fn);
+                int mi2 = 0;
+                double max_diff_new = -1.0;
+                for (int e = 0; e < N; ++e) {
+                    const double a = fabs(fn[e] - f[e]);
+                    if (a > max_diff_new) { max_diff_new = a; mi2 = e; }
+                }
+                const double scale_new = fmax(fabs(f[mi2]), fabs(fn[mi2]));
+                if (max_diff * scale_new < max_diff_new * scale) {
+                    fac = new_fac;
+                    hj = h_new;
+                    for (int e = 0; e < N; ++e) diff[e] = fn[e] - f[e];
+                    scale = scale_new;
+                    max_diff = max_diff_new;
+                }
+            }
+            yp[j] = yy[j];
+            for (int e = 0; e < N; ++e) J[e * N + j] = diff[e] / hj;
+            if (max_diff < DIFF_SMALL * scale) fac *= 10.0;
+            if (max_diff > DIFF_BIG * scale) fac *= 0.1;
+            jac_factor[j] = fmax(fac, MIN_FACTOR);
+        }
+    }
+};
+
+// ---- Radau IIA ------------------------------------------------------------------------------------------------------------
+template <class Sys>
+struct RadauStepper : ImplicitBase<Sys> {
+    using B = ImplicitBase<Sys>;
+    static constexpr int N = Sys::NL;
+    static constexpr int NEWTON_MAXITER = 6;
+    using B::t; using B::t_bound; using B::t_new; using B::h; using B::nfev; using B::st; using B::ynew;
+    using B::rtol; using B::atol; using B::newton_tol; using B::h_abs; using B::J;
+
+    double f[N], fnew[N];
+    double h_abs_old, error_norm_old;
+    bool have_old, current_jac, lu_valid, have_sol;
+    LuReal<N> lur;
+    LuComplex<N> luc;
+    double Z[3][N];
+    double sol_t_old, sol_h, sol_y_old[N], Q[N][3];       // interpolant of the last accepted step
+
+    template <class Stages>
+    __host__ __device__ void init(Sys& sys, const OdeLaunch& L, const double* y, Stages&) { init(sys, L, y); }
+    __host__ __device__ void init(Sys& sys, const OdeLaunch& L, const double* y) {
+        nfev = 0;
+        sys.rhs(L.t0, y, f); ++nfev;
+        B::init_common(sys, L, y, f, 3);
+        have_old = false;
+        have_sol = false;
+        lu_valid = false;
+        B::num_jac(sys, t, y, f);
+        current_jac = true;
+    }
+
+    // the interpolant of the last accepted step at time tg (also outside its interval: the Newton guess extrapolates)
+    __host__ __device__ void sol(double tg, double* out) const {
+        const double x = (tg - sol_t_old) / sol_h;
+        const double x2 = x * x, x3 = x2 * x;
+        for (int e = 0; e < N; ++e) out[e] = (Q[e][0] * x + Q[e][1] * x2 + Q[e][2] * x3) + sol_y_old[e];
+    }
+
+    __host__ __device__ static double predict_factor(double ha, bool old_ok, double ha_old, double en, double en_old) {
+        double multiplier = 1.0;
+        if (old_ok && en != 0.0) multiplier = ha / ha_old * pow(en_old / en, 0.25);
+        return fmin(1.0, multiplier) * pow(en, -0.25);
+    }
+
+    // `solve_collocation_system`: simplified Newton iterations for Z (3 x N), started from Z (in/out)
+    __host__ __device__ bool newton(Sys& sys, const double* y, const double* scale, int& n_iter, double& rate, bool& rate_ok) {
+        const double S6 = sqrt(6.0);
+        const double C[3] = {(4.0 - S6) / 10.0, (4.0 + S6) / 10.0, 1.0};
+        const double c13 = pow(3.0, 1.0 / 3.0), c23 = pow(3.0, 2.0 / 3.0);
+        const double MU_REAL = 3.0 + c23 - c13;
+        const double MU_CR = 3.0 + 0.5 * (c13 - c23), MU_CI = -0.5 * (pow(3.0, 5.0 / 6.0) + pow(3.0, 7.0 / 6.0));
+        const double T[3][3] = {{0.09443876248897524, -0.14125529502095421, 0.03002919410514742},
+                                {0.25021312296533332, 0.20412935229379994, -0.38294211275726192},
+                                {1.0, 1.0, 0.0}};
+        const double TI[3][3] = {{4.17871859155190428, 0.32768282076106237, 0.52337644549944951},
+                                 {-4.17871859155190428, -0.32768282076106237, 0.47662355450055044},
+                                 {0.50287263494578682, -2.57192694985560522, 0.59603920482822492}};
+        const double M_real = MU_REAL / h, Mcr = MU_CR / h, Mci = MU_CI / h;
+        double W[3][N], F[3][N], ytmp[N], br[N], bi[N], b0[N];
+        for (int i = 0; i < 3; ++i)
+            for (int e = 0; e < N; ++e) W[i][e] = TI[i][0] * Z[0][e] + TI[i][1] * Z[1][e] + TI[i][2] * Z[2][e];
+        double dW_norm_old = 0.0;
+        bool have_norm = false, converged = false;
+        rate_ok = false;
+        rate = 0.0;
+        int k = 0;
+        for (; k < NEWTON_MAXITER; ++k) {
+            bool ok = true;
+            for (int i = 0; i < 3; ++i) {
+                for (int e = 0; e < N; ++e) ytmp[e] = y[e] + Z[i][e];
+                sys.rhs(t + h * C[i], ytmp, F[i]); ++nfev;
+                for (int e = 0; e < N; ++e) ok = ok && finite_d(F[i][e]);
+            }
+            if (!ok) break;
+            for (int e = 0; e < N; ++e) {
+                b0[e] = (F[0][e] * TI[0][0] + F[1][e] * TI[0][1] + F[2][e] * TI[0][2]) - M_real * W[0][e];
+                // TI_COMPLEX = TI[1] + i TI[2];  M_complex (W1 + i W2)
+                const double fr = F[0][e] * TI[1][0] + F[1][e] * TI[1][1] + F[2][e] * TI[1][2];
+                const double fi = F[0][e] * TI[2][0] + F[1][e] * TI[2][1] + F[2][e] * TI[2][2];
+                br[e] = fr - (Mcr * W[1][e] - Mci * W[2][e]);
+                bi[e] = fi - (Mcr * W[2][e] + Mci * W[1][e]);
+            }
+            lur.solve(b0);
+            luc.solve(br, bi);
+            double acc = 0.0;
+            for (int e = 0; e < N; ++e) {
+                const double r0 = b0[e] / scale[e], r1 = br[e] / scale[e], r2 = bi[e] / scale[e];
+                acc += r0 * r0 + r1 * r1 + r2 * r2;
+            }
+            const double dW_norm = sqrt(acc) / sqrt(3.0 * (double)N);
+            if (have_norm) { rate = dW_norm / dW_norm_old; rate_ok = true; }
+            if (rate_ok && (rate >= 1.0 || pow(rate, (double)(NEWTON_MAXITER - k)) / (1.0 - rate) * dW_norm > newton_tol)) break;
+            for (int e = 0; e < N; ++e) { W[0][e] += b0[e]; W[1][e] += br[e]; W[2][e] += bi[e]; }
+            for (int i = 0; i < 3; ++i)
+                for (int e = 0; e < N; ++e) Z[i][e] = T[i][0] * W[0][e] + T[i][1] * W[1][e] + T[i][2] * W[2][e];
+            if (dW_norm == 0.0 || (rate_ok && rate / (1.0 - rate) * dW_norm < newton_tol)) { converged = true; break; }
+            dW_norm_old = dW_norm;
+            have_norm = true;
+        }
+        n_iter = k < NEWTON_MAXITER ? k + 1 : NEWTON_MAXITER;
+        return converged;
+    }
+
+    __host__ __device__ void factorise() {
+        const double c13 = pow(3.0, 1.0 / 3.0), c23 = pow(3.0, 2.0 / 3.0);
+        const double MU_REAL = 3.0 + c23 - c13;
+        const double MU_CR = 3.0 + 0.5 * (c13 - c23), MU_CI = -0.5 * (pow(3.0, 5.0 / 6.0) + pow(3.0, 7.0 / 6.0));
+        const double mr = MU_REAL / h, cr = MU_CR / h, ci = MU_CI / h;
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) {
+                const double d = i == j ? 1.0 : 0.0;
+                lur.a[i * N + j] = mr * d - J[i * N + j];
+                luc.re[i * N + j] = cr * d - J[i * N + j];
+                luc.im[i * N + j] = ci * d;
+            }
+        lur.factor();
+        luc.factor();
+        lu_valid = true;
+    }
+
+    template <class Stages>
+    __host__ __device__ bool step(Sys& sys, const double* y, Stages&) {
+        const double S6 = sqrt(6.0);
+        const double C[3] = {(4.0 - S6) / 10.0, (4.0 + S6) / 10.0, 1.0};
+        const double E[3] = {(-13.0 - 7.0 * S6) / 3.0, (-13.0 + 7.0 * S6) / 3.0, -1.0 / 3.0};
+        const double P[3][3] = {{13.0 / 3.0 + 7.0 * S6 / 3.0, -23.0 / 3.0 - 22.0 * S6 / 3.0, 10.0 / 3.0 + 5.0 * S6},
+                                {13.0 / 3.0 - 7.0 * S6 / 3.0, -23.0 / 3.0 + 22.0 * S6 / 3.0, 10.0 / 3.0 - 5.0 * S6},
+                                {1.0 / 3.0, -8.0 / 3.0, 10.0 / 3.0}};
+        const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);
+        double ha, ha_old = 0.0, en_old = 0.0;
+        bool old_ok;
+        if (h_abs < min_step) { ha = min_step; old_ok = false; }
+        else { ha = h_abs; old_ok = have_old; ha_old = h_abs_old; en_old = error_norm_old; }
+        bool rejected = false, rate_ok = false;
+        int n_iter = 0;
+        double rate = 0.0, error_norm = 0.0, safety = 0.0;
+        double scale[N], err[N], ze[N], ytmp[N];
+        for (;;) {
+            if (ha < min_step) { st |= ST_STEP_TOO_SMALL; return false; }
+            h = ha;
+            t_new = t + h;
+            if (t_new - t_bound > 0.0) t_new = t_bound;
+            h = t_new - t;
+            ha = fabs(h);
+            for (int e = 0; e < N; ++e) scale[e] = atol + fabs(y[e]) * rtol;
+            bool converged = false;
+            for (;;) {
+                if (!lu_valid) factorise();
+                if (!have_sol) {
+                    for (int i = 0; i < 3; ++i)
+                        for (int e = 0; e < N; ++e) Z[i][e] = 0.0;
+                } else {
+                    for (int i = 0; i < 3; ++i) {
+                        sol(t + h * C[i], ytmp);
+                        for (int e = 0; e < N; ++e) Z[i][e] = ytmp[e] - y[e];
+                    }
+                }
+                converged = newton(sys, y, scale, n_iter, rate, rate_ok);
+                if (converged || current_jac) break;
+                B::num_jac(sys, t, y, f);
+                current_jac = true;
+                lu_valid = false;
+            }
+            if (!converged) {
+                ha *= 0.5;
+                lu_valid = false;
+                continue;
+            }
+            for (int e = 0; e < N; ++e) {
+                ynew[e] = y[e] + Z[2][e];
+                ze[e] = (Z[0][e] * E[0] + Z[1][e] * E[1] + Z[2][e] * E[2]) / h;
+                err[e] = f[e] + ze[e];
+            }
+            lur.solve(err);
+            for (int e = 0; e < N; ++e) scale[e] = atol + fmax(fabs(y[e]), fabs(ynew[e])) * rtol;
+            error_norm = B::rms(err, scale);
+            safety = 0.9 * (2 * NEWTON_MAXITER + 1) / (double)(2 * NEWTON_MAXITER + n_iter);
+            if (rejected && error_norm > 1.0) {
+                for (int e = 0; e < N; ++e) ytmp[e] = y[e] + err[e];
+                sys.rhs(t, ytmp, err); ++nfev;
+                for (int e = 0; e < N; ++e) err[e] = err[e] + ze[e];
+                lur.solve(err);
+                error_norm = B::rms(err, scale);
+            }
+            if (!(error_norm == error_norm)) { st |= ST_NONFINITE | ST_STEP_TOO_SMALL; return false; }
+            if (error_norm > 1.0) {
+                const double factor = predict_factor(ha, old_ok, ha_old, error_norm, en_old);
+                ha *= fmax(0.2, safety * factor);
+                lu_valid = false;
+                rejected = true;
+            } else break;
+        }
+        const bool recompute_jac = n_iter > 2 && rate > 1e-3;
+        double factor = predict_factor(ha, old_ok, ha_old, error_norm, en_old);
+        factor = fmin(10.0, safety * factor);
+        if (!recompute_jac && factor < 1.2) factor = 1.0;
+        else lu_valid = false;
+        sys.rhs(t_new, ynew, fnew); ++nfev;
+        if (recompute_jac) { B::num_jac(sys, t_new, ynew, fnew); current_jac = true; }
+        else current_jac = false;
+        h_abs_old = h_abs;
+        error_norm_old = error_norm;
+        have_old = true;
+        h_abs = ha * factor;
+        sol_t_old = t;
+        sol_h = t_new - t;
+        for (int e = 0; e < N; ++e) {
+            sol_y_old[e] = y[e];
+            for (int j = 0; j < 3; ++j) Q[e][j] = Z[0][e] * P[0][j] + Z[1][e] * P[1][j] + Z[2][e] * P[2][j];
+        }
+        have_sol = true;
+        return true;
+    }
+
+    template <class Stages>
+    __host__ __device__ void dense(Sys&, const double*, Stages&, double tg, double* out) { sol(tg, out); }
+
+    __host__ __device__ void commit(double* y) {
+        for (int e = 0; e < N; ++e) { y[e] = ynew[e]; f[e] = fnew[e]; }
+        t = t_new;
+    }
+};
+
+// ---- BDF / NDF ------------------------------------------------------------------------------------------------------------
+template <class Sys>
+struct BdfStepper : ImplicitBase<Sys> {
+    using B = ImplicitBase<Sys>;
+    static constexpr int N = Sys::NL;
+    static constexpr int MAX_ORDER = 5, NEWTON_MAXITER = 4;
+    using B::t; using B::t_bound; using B::t_new; using B::h; using B::nfev; using B::st; using B::ynew;
+    using B::rtol; using B::atol; using B::newton_tol; using B::h_abs; using B::J;
+
+    double D[MAX_ORDER + 3][N];
+    double gamma[MAX_ORDER + 1], alpha[MAX_ORDER + 1], error_const[MAX_ORDER + 1];
+    int order, n_equal_steps;
+    bool lu_valid;
+    LuReal<N> lu;
+
+    // `change_D`: D[:order + 1] <- (R(factor) U)^T D[:order + 1]
+    __host__ __device__ static void compute_R(int ord, double factor, double R[MAX_ORDER + 1][MAX_ORDER + 1]) {
+        for (int j = 0; j <= ord; ++j) R[0][j] = 1.0;
+        for (int i = 1; i <= ord; ++i) {
+            R[i][0] = 0.0;
+            for (int j = 1; j <= ord; ++j) R[i][j] = R[i - 1][j] * (((double)(i - 1) - factor * (double)j) / (double)i);
+        }
+    }
+    __host__ __device__ void change_D(int ord, double factor) {
+        double R[MAX_ORDER + 1][MAX_ORDER + 1], U[MAX_ORDER + 1][MAX_ORDER + 1], RU[MAX_ORDER + 1][MAX_ORDER + 1];
+        compute_R(ord, factor, R);
+        compute_R(ord, 1.0, U);
+        for (int i = 0; i <= ord; ++i)
+            for (int j = 0; j <= ord; ++j) {
+                double s = 0.0;
+                for (int k = 0; k <= ord; ++k) s += R[i][k] * U[k][j];
+                RU[i][j] = s;
+            }
+        double col[MAX_ORDER + 1];
+        for (int e = 0; e < N; ++e) {
+            for (int i = 0; i <= ord; ++i) col[i] = D[i][e];
+            for (int i = 0; i <= ord; ++i) {
+                double s = 0.0;
+                for (int k = 0; k <= ord; ++k) s += RU[k][i] * col[k];
+                D[i][e] = s;
+            }
+        }
+    }
+
+    template <class Stages>
+    __host__ __device__ void init(Sys& sys, const OdeLaunch& L, const double* y, Stages&) { init(sys, L, y); }
+    __host__ __device__ void init(Sys& sys, const OdeLaunch& L, const double* y) {
+        double f[N];
+        nfev = 0;
+        sys.rhs(L.t0, y, f); ++nfev;
+        B::init_common(sys, L, y, f, 1);
+        B::num_jac(sys, t, y, f);
+        const double kappa[MAX_ORDER + 1] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
+        gamma[0] = 0.0;
+        for (int k = 1; k <= MAX_ORDER; ++k) gamma[k] = gamma[k - 1] + 1.0 / (double)k;
+        for (int k = 0; k <= MAX_ORDER; ++k) {
+            alpha[k] = (1.0 - kappa[k]) * gamma[k];
+            error_const[k] = kappa[k] * gamma[k] + 1.0 / (double)(k + 1);
+        }
+        for (int e = 0; e < N; ++e) { D[0][e] = y[e]; D[1][e] = f[e] * h_abs; }
+        for (int k = 2; k < MAX_ORDER + 3; ++k)
+            for (int e = 0; e < N; ++e) D[k][e] = 0.0;
+        order = 1;
+        n_equal_steps = 0;
+        lu_valid = false;
+    }
+
+    __host__ __device__ bool newton(Sys& sys, const double* y_predict, double c, const double* psi, const double* scale,
+                                    int& n_iter, double* d) {
+        double f[N], dy[N];
+        for (int e = 0; e < N; ++e) { d[e] = 0.0; ynew[e] = y_predict[e]; }
+        double dy_norm_old = 0.0;
+        bool have_norm = false, converged = false;
+        int k = 0;
+        for (; k < NEWTON_MAXITER; ++k) {
+            sys.rhs(t_new, ynew, f); ++nfev;
+            bool ok = true;
+            for (int e = 0; e < N; ++e) ok = ok && finite_d(f[e]);
+            if (!ok) break;
+            for (int e = 0; e < N; ++e) dy[e] = (c * f[e] - psi[e]) - d[e];
+            lu.solve(dy);
+            const double dy_norm = B::rms(dy, scale);
+            double rate = 0.0;
+            const bool rate_ok = have_norm;
+            if (rate_ok) rate = dy_norm / dy_norm_old;
+            if (rate_ok && (rate >= 1.0 || pow(rate, (double)(NEWTON_MAXITER - k)) / (1.0 - rate) * dy_norm > newton_tol)) break;
+            for (int e = 0; e < N; ++e) { ynew[e] += dy[e]; d[e] += dy[e]; }
+            if (dy_norm == 0.0 || (rate_ok && rate / (1.0 - rate) * dy_norm < newton_tol)) { converged = true; break; }
+            dy_norm_old = dy_norm;
+            have_norm = true;
+        }
+        n_iter = k < NEWTON_MAXITER ? k + 1 : NEWTON_MAXITER;
+        return converged;
+    }
+
+    template <class Stages>
+    __host__ __device__ bool step(Sys& sys, const double*, Stages&) {
+        const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);
+        double ha;
+        if (h_abs < min_step) {
+            ha = min_step;
+            change_D(order, min_step / h_abs);
+            n_equal_steps = 0;
+        } else ha = h_abs;
+        bool current_jac = false;
+        double y_predict[N], scale[N], psi[N], d[N], tmp[N];
+        double error_norm = 0.0, safety = 0.0;
+        int n_iter = 0;
+        for (;;) {
+            if (ha < min_step) { st |= ST_STEP_TOO_SMALL; return false; }
+            h = ha;
+            t_new = t + h;
+            if (t_new - t_bound > 0.0) {
+                t_new = t_bound;
+                change_D(order, fabs(t_new - t) / ha);
+                n_equal_steps = 0;
+                lu_valid = false;
+            }
+            h = t_new - t;
+            ha = fabs(h);
+            for (int e = 0; e < N; ++e) {
+                double s = D[0][e];
+                for (int k = 1; k <= order; ++k) s += D[k][e];
+                y_predict[e] = s;
+                scale[e] = atol + rtol * fabs(s);
+                double p = 0.0;
+                for (int k = 1; k <= order; ++k) p += D[k][e] * gamma[k];
+                psi[e] = p / alpha[order];
+            }
+            const double c = h / alpha[order];
+            bool converged = false;
+            for (;;) {
+                if (!lu_valid) {
+                    for (int i = 0; i < N; ++i)
+                        for (int j = 0; j < N; ++j) lu.a[i * N + j] = (i == j ? 1.0 : 0.0) - c * J[i * N + j];
+                    lu.factor();
+                    lu_valid = true;
+                }
+                converged = newton(sys, y_predict, c, psi, scale, n_iter, d);
+                if (converged || current_jac) break;
+                sys.rhs(t_new, y_predict, tmp);                     // `fun_single`: not counted
+                B::num_jac(sys, t_new, y_predict, tmp);
+                lu_valid = false;
+                current_jac = true;
+            }
+            if (!converged) {
+                ha *= 0.5;
+                change_D(order, 0.5);
+                n_equal_steps = 0;
+                lu_valid = false;
+                continue;
+            }
+            safety = 0.9 * (2 * NEWTON_MAXITER + 1) / (double)(2 * NEWTON_MAXITER + n_iter);
+            for (int e = 0; e < N; ++e) {
+                scale[e] = atol + rtol * fabs(ynew[e]);
+                tmp[e] = error_const[order] * d[e];
+            }
+            error_norm = B::rms(tmp, scale);
+            if (!(error_norm == error_norm)) { st |= ST_NONFINITE | ST_STEP_TOO_SMALL; return false; }
+            if (error_norm > 1.0) {
+                const double factor = fmax(0.2, safety * pow(error_norm, -1.0 / (double)(order + 1)));
+                ha *= factor;
+                change_D(order, factor);
+                n_equal_steps = 0;
+                // (scipy keeps the factorisation here: c changes with h, but LU is only reset where the code above says so)
+            } else break;
+        }
+        n_equal_steps += 1;
+        h_abs = ha;
+        for (int e = 0; e < N; ++e) {
+            D[order + 2][e] = d[e] - D[order + 1][e];
+            D[order + 1][e] = d[e];
+            for (int i = order; i >= 0; --i) D[i][e] += D[i + 1][e];
+        }
+        if (n_equal_steps < order + 1) return true;
+        double en[3];
+        if (order > 1) {
+            for (int e = 0; e < N; ++e) tmp[e] = error_const[order - 1] * D[order][e];
+            en[0] = B::rms(tmp, scale);
+        } else en[0] = INFINITY;
+        en[1] = error_norm;
+        if (order < MAX_ORDER) {
+            for (int e = 0; e < N; ++e) tmp[e] = error_const[order + 1] * D[order + 2][e];
+            en[2] = B::rms(tmp, scale);
+        } else en[2] = INFINITY;
+        int best = 0;
+        double fmaxv = -1.0;
+        for (int i = 0; i < 3; ++i) {
+            const double fi = pow(en[i], -1.0 / (double)(order + i));
+            if (fi > fmaxv) { fmaxv = fi; best = i; }
+        }
+        order += best - 1;
+        const double factor = fmin(10.0, safety * fmaxv);
+        h_abs *= factor;
+        change_D(order, factor);
+        n_equal_steps = 0;
+        lu_valid = false;
+        return true;
+    }
+
+    // BdfDenseOutput, built from the state AFTER the step (new order, new step size, rescaled differences)
+    template <class Stages>
+    __host__ __device__ void dense(Sys&, const double*, Stages&, double tg, double* out) {
+        double p[MAX_ORDER];
+        double acc = 1.0;
+        for (int k = 0; k < order; ++k) {
+            const double x = (tg - (t_new - h_abs * (double)k)) / (h_abs * (double)(1 + k));
+            acc *= x;
+            p[k] = acc;
+        }
+        for (int e = 0; e < N; ++e) {
+            double s = 0.0;
+            for (int k = 0; k < order; ++k) s += D[1 + k][e] * p[k];
+            out[e] = s + D[0][e];
+        }
+    }
+
+    __host__ __device__ void commit(double* y) {
+        for (int e = 0; e < N; ++e) y[e] = ynew[e];
+        t = t_new;
+    }
+};
+
+}  // namespace sodm

@@ -37,9 +37,39 @@ __global__ void __launch_bounds__(ODE_BLOCK, SODM_ODE_WINDOWED_MIN_BLOCKS) ode_t
     ode_thread_trajectory_windowed<M, OutT, Scheme>(L, i, i < L.n_traj, ode_window_smem + threadIdx.x, ode_window<M>(), ODE_BLOCK);
 }
 
+// Radau / BDF of a system without output windows (implicit.cuh): direct stores, one kernel per method
+template <class M, typename OutT, class Scheme>
+__global__ void __launch_bounds__(ODE_BLOCK) ode_thread_implicit_kernel(const __grid_constant__ OdeLaunch L) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < L.n_traj) ode_thread_trajectory_scheme<M, OutT, Scheme>(L, i);
+}
+
+template <class M, typename OutT>
+static int launch_thread_implicit(const OdeLaunch& L, int method, cudaStream_t stream) {
+    if constexpr (M::N > IMPLICIT_MAX_N) {
+        return fail(SODM_EUNSUPPORTED, "Radau / BDF keep a dense Jacobian per thread: at most %d equations (model has %d)", IMPLICIT_MAX_N, M::N);
+    } else {
+        const unsigned grid = (unsigned)((L.n_traj + ODE_BLOCK - 1) / ODE_BLOCK);
+        if constexpr (ode_window<M>() > 0) {
+            constexpr int smem = ode_window<M>() * M::N * ODE_BLOCK * (int)sizeof(double);
+            void (*kernel)(OdeLaunch) = method == SODM_ODE_RADAU ? ode_thread_rk45_windowed_kernel<M, OutT, SchemeRadau>
+                                                                 : ode_thread_rk45_windowed_kernel<M, OutT, SchemeBDF>;
+            SODM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            kernel<<<grid, ODE_BLOCK, smem, stream>>>(L);
+        } else {
+            void (*kernel)(OdeLaunch) = method == SODM_ODE_RADAU ? ode_thread_implicit_kernel<M, OutT, SchemeRadau>
+                                                                 : ode_thread_implicit_kernel<M, OutT, SchemeBDF>;
+            kernel<<<grid, ODE_BLOCK, 0, stream>>>(L);
+        }
+        SODM_CUDA_CHECK(cudaGetLastError());
+        return SODM_OK;
+    }
+}
+
 template <class M, typename OutT>
 static int launch_thread_dtype(const OdeLaunch& L, int method, cudaStream_t stream) {
     const unsigned grid = (unsigned)((L.n_traj + ODE_BLOCK - 1) / ODE_BLOCK);
+    if (method == SODM_ODE_RADAU || method == SODM_ODE_BDF) return launch_thread_implicit<M, OutT>(L, method, stream);
     if constexpr (ode_window<M>() > 0) {
         if (method == SODM_ODE_RK45 || method == SODM_ODE_RK23 || method == SODM_ODE_DOP853) {
             constexpr int smem = ode_window<M>() * M::N * ODE_BLOCK * (int)sizeof(double);

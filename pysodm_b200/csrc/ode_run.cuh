@@ -361,12 +361,21 @@ struct Rk45 {
     }
 };
 
+}  // namespace sodm
+#include "implicit.cuh"           // RadauStepper / BdfStepper: scipy's implicit methods behind the same stepper interface
+namespace sodm {
+
+// the stepper of a scheme: the shared explicit Runge-Kutta stepper, or one of the implicit ones
+template <class Sys, class Stages, class Scheme> struct StepperFor { using type = Rk45<Sys, Stages, Scheme>; };
+template <class Sys, class Stages> struct StepperFor<Sys, Stages, SchemeRadau> { using type = RadauStepper<Sys>; };
+template <class Sys, class Stages> struct StepperFor<Sys, Stages, SchemeBDF> { using type = BdfStepper<Sys>; };
+
 // Driver 1: every grid point is stored as soon as its step is accepted.  For systems whose lanes move in lockstep (the
 // reactor kernel: all lanes of a draw belong to ONE trajectory) and for the CPU harness.
 template <class Sys, typename OutT, class Stages, class Scheme = SchemeRK45>
 __host__ __device__ __forceinline__ void rk45_run(Sys& sys, const OdeLaunch& L, int64_t i, double* y, Stages& S) {
     constexpr int NL = Sys::NL;
-    Rk45<Sys, Stages, Scheme> R;
+    typename StepperFor<Sys, Stages, Scheme>::type R;
     double ytmp[NL];
     int g = 0;                                                        // next grid point to emit
     R.init(sys, L, y);
@@ -413,7 +422,7 @@ template <class Sys, typename OutT, class Stages, class Scheme = SchemeRK45>
 __host__ __device__ __forceinline__ void rk45_run_windowed(Sys& sys, const OdeLaunch& L, int64_t i, bool valid, double* y, Stages& S,
                                                   double* win, int W, int stride) {
     constexpr int NL = Sys::NL;
-    Rk45<Sys, Stages, Scheme> R;
+    typename StepperFor<Sys, Stages, Scheme>::type R;
     double ytmp[NL];
     bool pending = false, dead = !valid;
     // the next kept grid point: grid index g, kept index kj (kept points are g = 0, s, 2 s, .. or the last one alone); carried
@@ -638,6 +647,17 @@ __host__ __device__ __forceinline__ void ode_thread_trajectory_windowed(const Od
     ThreadSystem<M> sys{par};
     RegisterStages<M::N, Scheme::NSLOT> S;
     rk45_run_windowed<ThreadSystem<M>, OutT, RegisterStages<M::N, Scheme::NSLOT>, Scheme>(sys, L, i, valid, y, S, win, W, stride);
+}
+
+// one adaptive scheme through driver 1 (direct stores): the implicit methods of systems too large for output windows
+template <class M, typename OutT, class Scheme>
+__host__ __device__ __forceinline__ void ode_thread_trajectory_scheme(const OdeLaunch& L, int64_t i) {
+    double par[M::NPAR], y[M::N];
+    load_ode_params<M::NPAR>(L, i, par);
+#pragma unroll
+    for (int s = 0; s < M::N; ++s) y[s] = L.y0_bcast ? L.y0[s] : L.y0[(int64_t)s * L.ld_in + i];
+    ThreadSystem<M> sys{par};
+    rk45_run<ThreadSystem<M>, OutT, Scheme>(sys, L, i, y);
 }
 
 // WITH_RK45 = false: the kernel of a model whose RK45 runs through the windowed driver carries the fixed-step schemes only

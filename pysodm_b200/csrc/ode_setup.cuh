@@ -27,7 +27,7 @@ inline int build_ode_launch_for(const sodm_ode_args* a, OdeLaunch& L, const sodm
         return fail(SODM_EINVAL, "sodm_ode_run: inconsistent per-trajectory parameter description");
     if (a->out_dtype != SODM_F32 && a->out_dtype != SODM_F64)
         return fail(SODM_EINVAL, "sodm_ode_run: out_dtype must be SODM_F32 or SODM_F64");
-    if (a->method < SODM_ODE_RK45 || a->method > SODM_ODE_DOP853)
+    if (a->method < SODM_ODE_RK45 || a->method > SODM_ODE_BDF)
         return fail(SODM_EINVAL, "sodm_ode_run: unknown method %d", a->method);
     L = OdeLaunch{};
     L.n_traj = a->n_traj;
@@ -55,7 +55,7 @@ inline int build_ode_launch_for(const sodm_ode_args* a, OdeLaunch& L, const sodm
     L.nfev = a->nfev;
     L.status = a->status;
     L.max_steps = a->max_steps > 0 ? a->max_steps : 2147483647LL;
-    if (a->method == SODM_ODE_RK45 || a->method == SODM_ODE_RK23 || a->method == SODM_ODE_DOP853) {
+    if (a->method == SODM_ODE_RK45 || a->method == SODM_ODE_RK23 || a->method >= SODM_ODE_DOP853) {
         if (!(a->rtol > 0.0) || !(a->atol >= 0.0)) return fail(SODM_EINVAL, "sodm_ode_run: need rtol > 0 and atol >= 0");
     } else {
         const int64_t n = jump_n_steps(a->t0, a->n_out, a->tau);

@@ -171,6 +171,8 @@ __global__ void __launch_bounds__(ODE_BLOCK, SODM_GEN_WARP_MIN_BLOCKS) ode_gen_w
 template <class W>
 static int launch_gen_warp(const OdeLaunch& L, int method, int dtype, cudaStream_t stream) {
     static_assert(W::NL <= 32, "at most 32 positions per lane");
+    if (method == SODM_ODE_RADAU || method == SODM_ODE_BDF)
+        return fail(SODM_EUNSUPPORTED, "Radau / BDF are offered for thread-per-trajectory models (at most %d equations), not for the warp-per-draw layout", IMPLICIT_MAX_N);
     if (method == SODM_ODE_DOP853)
         return fail(SODM_EUNSUPPORTED, "DOP853 is not offered for generated models in the warp-per-draw layout (16 stage vectors per lane)");
     const int64_t threads = L.n_traj * 32;

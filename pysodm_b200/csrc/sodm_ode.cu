@@ -199,6 +199,8 @@ extern "C" int sodm_ode_run(const sodm_ode_args* a) {
         case MODEL_SIR_SI_ODE:   return launch_thread<SirSiOde>(L, a->method, a->out_dtype, stream);
         case MODEL_PPBB_ODE:     return launch_thread<PpbbOde>(L, a->method, a->out_dtype, stream);
         case MODEL_PACKED_PFR_ODE:
+            if (a->method == SODM_ODE_RADAU || a->method == SODM_ODE_BDF)
+                return fail(SODM_EUNSUPPORTED, "Radau / BDF are offered for thread-per-trajectory models (at most %d equations), not for the reactor's node-per-lane layout", IMPLICIT_MAX_N);
             if (L.nx <= 32) return launch_pfr<1>(L, a->method, a->out_dtype, stream);     // warps per draw
             if (L.nx <= 64) return launch_pfr<2>(L, a->method, a->out_dtype, stream);
             return launch_pfr<4>(L, a->method, a->out_dtype, stream);

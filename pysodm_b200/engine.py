@@ -194,7 +194,7 @@ def ode_run(model, y0, par, n_traj, t0, n_out, method="RK45", rtol=1e-4, atol=1e
     status = torch.zeros(n_traj, dtype=torch.int32, device=dev)
     a = _ffi.OdeArgs()
     a.model, a.model_arg = mid, int(model_arg)
-    a.method = {"RK45": _ffi.ODE_RK45, "euler": _ffi.ODE_EULER, "RK4": _ffi.ODE_RK4, "RK23": _ffi.ODE_RK23, "DOP853": _ffi.ODE_DOP853}[method]
+    a.method = {"RK45": _ffi.ODE_RK45, "euler": _ffi.ODE_EULER, "RK4": _ffi.ODE_RK4, "RK23": _ffi.ODE_RK23, "DOP853": _ffi.ODE_DOP853, "Radau": _ffi.ODE_RADAU, "BDF": _ffi.ODE_BDF}[method]
     a.out_dtype = _TORCH_DT[out.dtype]
     a.n_traj, a.ld_in, a.ld_out = int(n_traj), int(n_traj), int(out.stride(1))
     a.y0, a.y0_broadcast = y0_d.data_ptr(), int(y0_d.dim() == 1)

@@ -393,6 +393,16 @@ def gen_ode_dop853():
     gen_ode_rk23('DOP853', 'ode_dop853.npz')
 
 
+def gen_ode_radau():
+    """`method='Radau'` (scipy's Radau IIA, finite-difference Jacobian) of the unmodified reference -> tests/golden/ode_radau.npz"""
+    gen_ode_rk23('Radau', 'ode_radau.npz')
+
+
+def gen_ode_bdf():
+    """`method='BDF'` (scipy's variable-order NDF, finite-difference Jacobian) of the unmodified reference -> tests/golden/ode_bdf.npz"""
+    gen_ode_rk23('BDF', 'ode_bdf.npz')
+
+
 def gen_pfr100():
     """C4 at nx = 100 (docs/enzyme_kinetics.md:408-412): the reference's packed_PFR through solve_ivp RK45 for three
     posterior draws, stride-100 subset of the 8001-point grid + nfev (nx = 100 had no reference parity)."""

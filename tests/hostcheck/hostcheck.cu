@@ -135,6 +135,12 @@ static void ode_host(const OdeLaunch& L, int method, int window) {
             if (method == SODM_ODE_RK45) ode_thread_trajectory_windowed<M, OutT, SchemeRK45>(L, i, true, win.data(), window, 1);
             else if (method == SODM_ODE_RK23) ode_thread_trajectory_windowed<M, OutT, SchemeRK23>(L, i, true, win.data(), window, 1);
             else ode_thread_trajectory_windowed<M, OutT, SchemeDOP853>(L, i, true, win.data(), window, 1);
+        } else if (method == SODM_ODE_RADAU || method == SODM_ODE_BDF) {        // implicit.cuh; window > 0: through the windowed driver
+            std::vector<double> win((size_t)(window > 0 ? window : 1) * M::N);
+            if (window > 0 && method == SODM_ODE_RADAU) ode_thread_trajectory_windowed<M, OutT, SchemeRadau>(L, i, true, win.data(), window, 1);
+            else if (window > 0) ode_thread_trajectory_windowed<M, OutT, SchemeBDF>(L, i, true, win.data(), window, 1);
+            else if (method == SODM_ODE_RADAU) ode_thread_trajectory_scheme<M, OutT, SchemeRadau>(L, i);
+            else ode_thread_trajectory_scheme<M, OutT, SchemeBDF>(L, i);
         } else {
             ode_thread_trajectory<M, OutT>(L, method, i);
         }
@@ -171,6 +177,7 @@ extern "C" int hc_ode_run(const sodm_ode_args* a) {
         case MODEL_SIR_SI_ODE:   ode_host<SirSiOde, double>(L, a->method, a->reserved); return SODM_OK;
         case MODEL_PPBB_ODE:     ode_host<PpbbOde, double>(L, a->method, a->reserved); return SODM_OK;
         case MODEL_PACKED_PFR_ODE:
+            if (a->method == SODM_ODE_RADAU || a->method == SODM_ODE_BDF) return SODM_EUNSUPPORTED;
             if (L.nx == 25) { pfr_host<25, double>(L, a->method); return SODM_OK; }
             if (L.nx == 100) { pfr_host<100, double>(L, a->method); return SODM_OK; }
             return SODM_EUNSUPPORTED;

@@ -154,7 +154,7 @@ def ode_run(model, y0, par, n_traj, t0, n_out, method="RK45", rtol=1e-4, atol=1e
     status = np.zeros(n_traj, dtype=np.int32)
     a = _ffi.OdeArgs()
     a.model, a.model_arg = mid, model_arg
-    a.method = {"RK45": _ffi.ODE_RK45, "euler": _ffi.ODE_EULER, "RK4": _ffi.ODE_RK4, "RK23": _ffi.ODE_RK23, "DOP853": _ffi.ODE_DOP853}[method]
+    a.method = {"RK45": _ffi.ODE_RK45, "euler": _ffi.ODE_EULER, "RK4": _ffi.ODE_RK4, "RK23": _ffi.ODE_RK23, "DOP853": _ffi.ODE_DOP853, "Radau": _ffi.ODE_RADAU, "BDF": _ffi.ODE_BDF}[method]
     a.out_dtype = _ffi.F64
     a.n_traj, a.ld_in, a.ld_out = n_traj, n_traj, n_traj
     a.y0, a.y0_broadcast = y0.ctypes.data, int(y0.ndim == 1)

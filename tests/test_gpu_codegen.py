@@ -119,6 +119,14 @@ def test_generated_odes_follow_the_hand_written_functors(golden):
     y = np.stack([out[s].values for s in ("S", "I", "R")], axis=1)
     np.testing.assert_allclose(y, g["sir_y"], rtol=1e-6, atol=1e-9)
     assert np.array_equal(model.last_nfev.cpu().numpy(), g["sir_nfev"])
+    # the implicit methods run on the translated functor too (its Jacobian is scipy's finite-difference one, implicit.cuh)
+    for method in ("Radau", "BDF"):
+        gi = golden["ode_" + method.lower()]
+        betas = gi["sir_betas"]
+        out = model.sim(120, N=30, draw_function=draw, method=method)
+        y = np.stack([out[s].values for s in ("S", "I", "R")], axis=1)
+        np.testing.assert_allclose(y, gi["sir_y"], rtol=1e-6, atol=1e-7)
+        assert np.array_equal(model.last_nfev.cpu().numpy(), gi["sir_nfev"])
     # packed-bed reactor written with NumPy slicing: generated thread-per-draw kernel vs the warp-per-draw functor
     nx = 6
     gp, hp = gm.make_pfr(nx), gm.make_pfr(nx, tm.packed_PFR)
@@ -131,6 +139,8 @@ def test_generated_odes_follow_the_hand_written_functors(golden):
     nx = 25
     gp, hp = gm.make_pfr(nx), gm.make_pfr(nx, tm.packed_PFR)
     assert gp.device_model.layout.get("warp")
+    with pytest.raises(NotImplementedError, match="dense Jacobian"):
+        gp.sim(10, method="BDF")
 
     def draw(parameters, N):
         r = np.random.default_rng(3)

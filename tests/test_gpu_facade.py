@@ -130,7 +130,7 @@ def test_ode_sim_contract_and_parity(td, golden):
     eu = model.sim(60, tau=0.25)
     np.testing.assert_allclose(eu["I"].values, g["sir_euler_y"][1], rtol=1e-12)
     # method='RK23' / 'DOP853' through the class API, against the unmodified reference's runs with those methods
-    for method in ("RK23", "DOP853"):
+    for method in ("RK23", "DOP853", "Radau", "BDF"):
         gm = golden["ode_" + method.lower()]
         model.parameters["beta"] = float(gm["sir_betas"][3])
         r = model.sim(120, method=method)

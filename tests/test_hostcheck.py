@@ -241,7 +241,31 @@ def test_packed_pfr_nx100_kernel_code_vs_reference(golden):
     assert rel.max() <= 5 * float(g["pfr100_ref_self_max_rel"])
 
 
-@pytest.mark.parametrize("method", ["RK45", "RK23", "DOP853"])
+@pytest.mark.parametrize("method", ["Radau", "BDF"])
+def test_radau_and_bdf_follow_scipy_step_for_step(golden, method):
+    """`method='Radau'` / `'BDF'` (csrc/implicit.cuh: scipy's Radau IIA and variable-order NDF with its finite-difference
+    Jacobian, simplified Newton and LU) against runs of the UNMODIFIED reference with that method (tests/golden/ode_radau.npz,
+    ode_bdf.npz): identical `nfev` on every draw -- same Newton iteration counts, rejections and Jacobian refreshes --
+    values to 1e-6 (observed 1e-8: the Newton iterates stop at newton_tol, so LAPACK-vs-own LU rounding is visible there)."""
+    g = golden["ode_" + method.lower()]
+    out, nfev, st = hc.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], 30, 0, 121, var={0: g["sir_betas"]}, method=method)
+    assert np.array_equal(nfev, g["sir_nfev"]) and (st == 0).all()
+    np.testing.assert_allclose(out, np.transpose(g["sir_y"], (1, 2, 0)), rtol=1e-6, atol=1e-7)
+    out, nfev, _ = hc.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], 1, 0, 121, method=method, rtol=1e-7)
+    assert int(nfev[0]) == int(g["sir_rtol1e-07_nfev"])
+    np.testing.assert_allclose(out[:, :, 0], g["sir_rtol1e-07_y"], rtol=1e-9, atol=1e-9)
+    out, nfev, _ = hc.ode_run("sir_si_ode", g["sirsi_y0"], cases.SIRSI_PAR, 1, 0, 121, method=method)      # 14 equations
+    assert int(nfev[0]) == int(g["sirsi_nfev"])
+    np.testing.assert_allclose(out[:, :, 0], g["sirsi_y"], rtol=1e-7, atol=1e-5)
+    out, nfev, _ = hc.ode_run("ppbb_ode", g["ppbb_y0"], g["ppbb_par"], 1, 0, 1501, method=method)
+    assert int(nfev[0]) == int(g["ppbb_nfev"])
+    np.testing.assert_allclose(out[:, :, 0], g["ppbb_y"], rtol=1e-7, atol=1e-7)
+    with pytest.raises(RuntimeError):                            # the reactor's node-per-lane layout has no dense Jacobian
+        from pysodm_b200 import tutorial_data as td
+        hc.ode_run("packed_pfr_ode", golden["ode"]["pfr25_y0"], td.pfr_flat_par(25), 1, 0, 11, model_arg=25, method=method)
+
+
+@pytest.mark.parametrize("method", ["RK45", "RK23", "DOP853", "Radau", "BDF"])
 def test_windowed_output_driver_equals_the_plain_driver(golden, method):
     """The device's thread kernel delivers kept grid points in windows (rk45_run_windowed, ode_run.cuh); run here as a warp of
     one lane it must reproduce the plain driver bit for bit: window lengths that do and do not divide the kept count, strided
