@@ -87,6 +87,37 @@ class LotkaVolterra(ODE):
         return dprey, dpred
 
 
+class Robertson(ODE):
+    """Robertson's stiff kinetics; tests/golden/make_golden.py::gen_ode_stiff runs the same function through the reference."""
+    states = ['y1', 'y2', 'y3']
+    parameters = ['k1', 'k2', 'k3']
+
+    @staticmethod
+    def integrate(t, y1, y2, y3, k1, k2, k3):
+        r1 = k1 * y1
+        r2 = k2 * y2 * y3
+        r3 = k3 * y2 * y2
+        return -r1 + r2, r1 - r2 - r3, r3
+
+
+class VanDerPol(ODE):
+    """Van der Pol oscillator, stiff for large mu (gen_ode_stiff)."""
+    states = ['x', 'v']
+    parameters = ['mu']
+
+    @staticmethod
+    def integrate(t, x, v, mu):
+        return v, mu * (1 - x * x) * v - x
+
+
+def make_robertson():
+    return Robertson({'y1': 1.0, 'y2': 0.0, 'y3': 0.0}, {'k1': 0.04, 'k2': 1e4, 'k3': 3e7})
+
+
+def make_vanderpol():
+    return VanDerPol({'x': 2.0, 'v': 0.0}, {'mu': 100.0})
+
+
 def make_lotka(n=5):
     rng = np.random.default_rng(0)
     return LotkaVolterra({'prey': 10 + rng.random(n) * 5, 'pred': 3 + rng.random(n)},

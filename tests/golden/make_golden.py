@@ -403,6 +403,56 @@ def gen_ode_bdf():
     gen_ode_rk23('BDF', 'ode_bdf.npz')
 
 
+def gen_ode_stiff():
+    """Stiff problems through the reference's ODE.sim with `method='Radau'` / `'BDF'` (base.py:855 -> solve_ivp, numerical
+    Jacobian): Robertson's kinetics (draws of k1) and the Van der Pol oscillator (draws of mu from mildly to very stiff, through
+    its fast transitions: rejected steps, failed Newton iterations, Jacobian refreshes, BDF orders up to 5)
+    -> tests/golden/ode_stiff.npz.  The same functors are compiled into the CPU harness (tests/hostcheck/hostcheck.cu) and
+    translated from Python for the device (tests/gen_models.py)."""
+    class Robertson(base.ODE):
+        states = ['y1', 'y2', 'y3']
+        parameters = ['k1', 'k2', 'k3']
+
+        @staticmethod
+        def integrate(t, y1, y2, y3, k1, k2, k3):
+            r1 = k1 * y1
+            r2 = k2 * y2 * y3
+            r3 = k3 * y2 * y2
+            return -r1 + r2, r1 - r2 - r3, r3
+
+    class VanDerPol(base.ODE):
+        states = ['x', 'v']
+        parameters = ['mu']
+
+        @staticmethod
+        def integrate(t, x, v, mu):
+            return v, mu * (1 - x * x) * v - x
+    out = {}
+    rng = np.random.default_rng(77)
+    out['rob_k1'] = rng.uniform(0.02, 0.08, size=6)
+    out['vdp_mu'] = np.array([0.5, 5.0, 20.0, 60.0, 100.0, 200.0])
+    rob = Robertson(initial_states={'y1': 1.0, 'y2': 0.0, 'y3': 0.0}, parameters={'k1': 0.04, 'k2': 1e4, 'k3': 3e7})
+    vdp = VanDerPol(initial_states={'x': 2.0, 'v': 0.0}, parameters={'mu': 100.0})
+    for method in ('Radau', 'BDF'):
+        ys, nf = [], []
+        for k1 in out['rob_k1']:
+            rob.parameters['k1'] = k1
+            r = rob.sim(40, method=method)
+            ys.append(r['y']); nf.append(r['nfev'])
+        out[f'rob_{method}_y'], out[f'rob_{method}_nfev'] = np.stack(ys), np.array(nf)
+        ys, nf = [], []
+        for mu in out['vdp_mu']:
+            vdp.parameters['mu'] = mu
+            r = vdp.sim(200, method=method)
+            ys.append(r['y']); nf.append(r['nfev'])
+        out[f'vdp_{method}_y'], out[f'vdp_{method}_nfev'] = np.stack(ys), np.array(nf)
+        rob.parameters['k1'] = 0.04
+        r = rob.sim(400, method=method, rtol=1e-6)
+        out[f'rob_{method}_long_y'], out[f'rob_{method}_long_nfev'] = r['y'], np.array(r['nfev'])
+        print(method, 'Robertson nfev', out[f'rob_{method}_nfev'], 'VdP nfev', out[f'vdp_{method}_nfev'], 'long', r['nfev'])
+    save('ode_stiff.npz', **out)
+
+
 def gen_pfr100():
     """C4 at nx = 100 (docs/enzyme_kinetics.md:408-412): the reference's packed_PFR through solve_ivp RK45 for three
     posterior draws, stride-100 subset of the 8001-point grid + nfev (nx = 100 had no reference parity)."""

@@ -164,6 +164,40 @@ static void pfr_host(const OdeLaunch& L, int method) {
     }
 }
 
+// Test-only stiff systems for the implicit methods (tests/golden/make_golden.py::gen_ode_stiff defines the same right-hand sides,
+// operation for operation, as models of the unmodified reference): a->model 0 = Robertson's kinetics, 1 = Van der Pol.
+struct RobertsonOde {
+    static constexpr int N = 3, NPAR = 3;
+    __host__ __device__ static void rhs(double, const double* y, const double* par, double* dy) {
+        const double r1 = par[0] * y[0];
+        const double r2 = par[1] * y[1] * y[2];
+        const double r3 = par[2] * y[1] * y[1];
+        dy[0] = -r1 + r2;
+        dy[1] = r1 - r2 - r3;
+        dy[2] = r3;
+    }
+};
+struct VanDerPolOde {
+    static constexpr int N = 2, NPAR = 1;
+    __host__ __device__ static void rhs(double, const double* y, const double* par, double* dy) {
+        dy[0] = y[1];
+        dy[1] = par[0] * (1 - y[0] * y[0]) * y[1] - y[0];
+    }
+};
+
+extern "C" int hc_ode_test_model_run(const sodm_ode_args* a) {
+    OdeLaunch L;
+    sodm_model_info info = {};
+    info.kind = SODM_KIND_ODE;
+    info.n_state = a->model == 0 ? RobertsonOde::N : VanDerPolOde::N;
+    info.n_param = a->model == 0 ? RobertsonOde::NPAR : VanDerPolOde::NPAR;
+    const int rc = build_ode_launch_for(a, L, info);
+    if (rc != SODM_OK) return rc;
+    if (a->model == 0) ode_host<RobertsonOde, double>(L, a->method, a->reserved);
+    else ode_host<VanDerPolOde, double>(L, a->method, a->reserved);
+    return SODM_OK;
+}
+
 extern "C" int hc_ode_run(const sodm_ode_args* a) {
     OdeLaunch L;
     sodm_model_info info;

@@ -132,6 +132,9 @@ def jump_run(model, y0, par, n_traj, t0, n_out, tau=0.5, method="tau_leap", var=
     return out, status
 
 
+TEST_ODE_MODELS = {"test:robertson": (0, 3, 3), "test:vanderpol": (1, 2, 1)}      # name -> (id, n_state, n_param)
+
+
 def ode_run(model, y0, par, n_traj, t0, n_out, method="RK45", rtol=1e-4, atol=1e-6, tau=0.0, var=None,
             model_arg=0, out_stride=1, out_last_only=False, window=0, max_steps=0):
     """Host run of the ODE integrators.  Returns (out[n_state, n_kept, n_traj], nfev[n_traj], status[n_traj]).
@@ -141,10 +144,17 @@ def ode_run(model, y0, par, n_traj, t0, n_out, method="RK45", rtol=1e-4, atol=1e
         L.hc_ode_run.restype = C.c_int
         L.hc_ode_run.argtypes = [C.POINTER(_ffi.OdeArgs)]
         L._ode_ready = True
-    mid = L.sodm_model_id(model.encode())
-    assert mid >= 0, L.sodm_last_error()
-    info = _ffi.ModelInfo()
-    assert L.sodm_model_info_get(mid, model_arg, C.byref(info)) == 0, L.sodm_last_error()
+    entry = L.hc_ode_run
+    if model in TEST_ODE_MODELS:                                # functors that exist in the harness only (stiff test problems)
+        mid, n_state, n_param = TEST_ODE_MODELS[model]
+        info = _ffi.ModelInfo(n_state=n_state, n_param=n_param)
+        entry = L.hc_ode_test_model_run
+        entry.restype, entry.argtypes = C.c_int, [C.POINTER(_ffi.OdeArgs)]
+    else:
+        mid = L.sodm_model_id(model.encode())
+        assert mid >= 0, L.sodm_last_error()
+        info = _ffi.ModelInfo()
+        assert L.sodm_model_info_get(mid, model_arg, C.byref(info)) == 0, L.sodm_last_error()
     y0 = np.ascontiguousarray(y0, dtype=np.float64)
     par = np.ascontiguousarray(par, dtype=np.float64)
     assert par.size == info.n_param, (par.size, info.n_param)
@@ -169,7 +179,7 @@ def ode_run(model, y0, par, n_traj, t0, n_out, method="RK45", rtol=1e-4, atol=1e
     a.rtol, a.atol, a.tau = rtol, atol, tau
     a.reserved, a.max_steps = int(window), int(max_steps)
     a.out, a.nfev, a.status = out.ctypes.data, nfev.ctypes.data, status.ctypes.data
-    rc = L.hc_ode_run(C.byref(a))
+    rc = entry(C.byref(a))
     if rc != 0:
         raise _ffi.SodmError(rc, L.sodm_last_error().decode())
     return out, nfev, status

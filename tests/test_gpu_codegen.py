@@ -127,6 +127,28 @@ def test_generated_odes_follow_the_hand_written_functors(golden):
         y = np.stack([out[s].values for s in ("S", "I", "R")], axis=1)
         np.testing.assert_allclose(y, gi["sir_y"], rtol=1e-6, atol=1e-7)
         assert np.array_equal(model.last_nfev.cpu().numpy(), gi["sir_nfev"])
+        # stiff problems (Robertson, Van der Pol up to mu = 200) translated from Python, against the unmodified reference
+        # running the same functions (tests/golden/ode_stiff.npz); see tests/test_hostcheck.py for the two draws left out
+        gs = golden["ode_stiff"]
+        rob, vdp = gm.make_robertson(), gm.make_vanderpol()
+
+        def draw_k1(parameters, N):
+            parameters["k1"] = gs["rob_k1"]
+            return parameters
+        draw_k1.vectorized = True
+        out = rob.sim(40, N=6, draw_function=draw_k1, method=method)
+        y = np.stack([out[s].values for s in ("y1", "y2", "y3")], axis=1)
+        np.testing.assert_allclose(y, gs[f"rob_{method}_y"], rtol=1e-6, atol=1e-12)
+        assert np.array_equal(rob.last_nfev.cpu().numpy(), gs[f"rob_{method}_nfev"])
+
+        def draw_mu(parameters, N):
+            parameters["mu"] = gs["vdp_mu"][2:]
+            return parameters
+        draw_mu.vectorized = True
+        out = vdp.sim(200, N=4, draw_function=draw_mu, method=method)
+        y = np.stack([out[s].values for s in ("x", "v")], axis=1)
+        np.testing.assert_allclose(y, gs[f"vdp_{method}_y"][2:], rtol=1e-5, atol=1e-3)
+        assert np.array_equal(vdp.last_nfev.cpu().numpy(), gs[f"vdp_{method}_nfev"][2:])
     # packed-bed reactor written with NumPy slicing: generated thread-per-draw kernel vs the warp-per-draw functor
     nx = 6
     gp, hp = gm.make_pfr(nx), gm.make_pfr(nx, tm.packed_PFR)

@@ -265,6 +265,30 @@ def test_radau_and_bdf_follow_scipy_step_for_step(golden, method):
         hc.ode_run("packed_pfr_ode", golden["ode"]["pfr25_y0"], td.pfr_flat_par(25), 1, 0, 11, model_arg=25, method=method)
 
 
+@pytest.mark.parametrize("method", ["Radau", "BDF"])
+def test_radau_and_bdf_on_stiff_problems(golden, method):
+    """Robertson's kinetics and the Van der Pol oscillator (mu = 0.5 .. 200, through its fast transitions) -- rejected steps,
+    failed Newton iterations with Jacobian refreshes, BDF orders up to 5 -- against the unmodified reference running the same
+    right-hand sides (tests/golden/ode_stiff.npz): identical `nfev` up to 17 121 evaluations.  The two mildly stiff oscillator
+    draws under BDF are compared on the first 20 time units only: over thousands of steps scipy's own `nfev` there moves with
+    a one-ulp change of y0 (6401 / 6418 / 6443), i.e. the step sequence is not reproducible across LU roundings."""
+    g = golden["ode_stiff"]
+    out, nfev, st = hc.ode_run("test:robertson", [1.0, 0, 0], [0.04, 1e4, 3e7], 6, 0, 41, var={0: g["rob_k1"]}, method=method)
+    assert np.array_equal(nfev, g[f"rob_{method}_nfev"]) and (st == 0).all()
+    np.testing.assert_allclose(out, np.transpose(g[f"rob_{method}_y"], (1, 2, 0)), rtol=1e-7, atol=1e-12)
+    out, nfev, _ = hc.ode_run("test:robertson", [1.0, 0, 0], [0.04, 1e4, 3e7], 1, 0, 401, method=method, rtol=1e-6)
+    assert int(nfev[0]) == int(g[f"rob_{method}_long_nfev"])
+    np.testing.assert_allclose(out[:, :, 0], g[f"rob_{method}_long_y"], rtol=1e-8, atol=1e-13)
+    out, nfev, st = hc.ode_run("test:vanderpol", [2.0, 0], [100.0], 6, 0, 201, var={0: g["vdp_mu"]}, method=method)
+    ref = np.transpose(g[f"vdp_{method}_y"], (1, 2, 0))
+    same = slice(0, 6) if method == "Radau" else slice(2, 6)
+    assert np.array_equal(nfev[same], g[f"vdp_{method}_nfev"][same]) and (st == 0).all()
+    # values: to the solver's tolerance where the solution jumps (a 1e-9 shift of a transition moves x by 1e-4 there), 1e-6 elsewhere
+    np.testing.assert_allclose(out[:, :21], ref[:, :21], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(out[..., same], ref[..., same], rtol=1e-5, atol=1e-3)
+    assert np.median(np.abs(out[..., same] - ref[..., same])) < 1e-9
+
+
 @pytest.mark.parametrize("method", ["RK45", "RK23", "DOP853", "Radau", "BDF"])
 def test_windowed_output_driver_equals_the_plain_driver(golden, method):
     """The device's thread kernel delivers kept grid points in windows (rk45_run_windowed, ode_run.cuh); run here as a warp of
