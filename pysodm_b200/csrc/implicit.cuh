@@ -48,46 +48,113 @@ __host__ __device__ __forceinline__ double imp_add(double a, double b) {
 }
 
 // ---- dense LU, real and complex ----------------------------------------------------------------------------------------
+// Systems of at most IMPLICIT_STATIC_N equations take a path on which EVERY array index is a compile-time constant (loops fully
+// unrolled, the pivot row reached through predicated swaps instead of a run-time row index): per-thread arrays indexed at run
+// time live in local memory, and at 512 resident threads per SM the 1.5 - 2 KB frames of these kernels overflow L1, so each
+// such access is an L2 round trip.  Same arithmetic in the same order on both paths.
+constexpr int IMPLICIT_STATIC_N = 8;
+#define SODM_UNROLL_SMALL _Pragma("unroll")
+
 template <int N>
 struct LuReal {
     double a[N * N];
     int piv[N];
     __host__ __device__ void factor() {
-        for (int k = 0; k < N; ++k) {
-            int p = k;
-            double best = fabs(a[k * N + k]);
-            for (int i = k + 1; i < N; ++i) {
-                const double v = fabs(a[i * N + k]);
-                if (v > best) { best = v; p = i; }
-            }
-            piv[k] = p;
-            if (p != k)
-                for (int j = 0; j < N; ++j) { const double x = a[k * N + j]; a[k * N + j] = a[p * N + j]; a[p * N + j] = x; }
-            const double d = a[k * N + k];
-            if (d != 0.0) {
+        if constexpr (N <= IMPLICIT_STATIC_N) {
+            SODM_UNROLL_SMALL
+            for (int k = 0; k < N; ++k) {
+                int p = k;
+                double best = fabs(a[k * N + k]);
+                SODM_UNROLL_SMALL
+                for (int i = k + 1; i < N; ++i) {
+                    const double v = fabs(a[i * N + k]);
+                    if (v > best) { best = v; p = i; }
+                }
+                piv[k] = p;
+                SODM_UNROLL_SMALL
+                for (int i = k + 1; i < N; ++i) {
+                    const bool sw = p == i;
+                    SODM_UNROLL_SMALL
+                    for (int j = 0; j < N; ++j) {
+                        const double x = a[k * N + j], y = a[i * N + j];
+                        a[k * N + j] = sw ? y : x;
+                        a[i * N + j] = sw ? x : y;
+                    }
+                }
+                const double d = a[k * N + k];
                 const double r = 1.0 / d;
-                for (int i = k + 1; i < N; ++i) a[i * N + k] *= r;
+                SODM_UNROLL_SMALL
+                for (int i = k + 1; i < N; ++i) {
+                    if (d != 0.0) a[i * N + k] *= r;
+                    const double l = a[i * N + k];
+                    SODM_UNROLL_SMALL
+                    for (int j = k + 1; j < N; ++j) a[i * N + j] -= l * a[k * N + j];
+                }
             }
-            for (int i = k + 1; i < N; ++i) {
-                const double l = a[i * N + k];
-                for (int j = k + 1; j < N; ++j) a[i * N + j] -= l * a[k * N + j];
+        } else {
+            for (int k = 0; k < N; ++k) {
+                int p = k;
+                double best = fabs(a[k * N + k]);
+                for (int i = k + 1; i < N; ++i) {
+                    const double v = fabs(a[i * N + k]);
+                    if (v > best) { best = v; p = i; }
+                }
+                piv[k] = p;
+                if (p != k)
+                    for (int j = 0; j < N; ++j) { const double x = a[k * N + j]; a[k * N + j] = a[p * N + j]; a[p * N + j] = x; }
+                const double d = a[k * N + k];
+                if (d != 0.0) {
+                    const double r = 1.0 / d;
+                    for (int i = k + 1; i < N; ++i) a[i * N + k] *= r;
+                }
+                for (int i = k + 1; i < N; ++i) {
+                    const double l = a[i * N + k];
+                    for (int j = k + 1; j < N; ++j) a[i * N + j] -= l * a[k * N + j];
+                }
             }
         }
     }
     __host__ __device__ void solve(double* b) const {
-        for (int k = 0; k < N; ++k) {
-            const int p = piv[k];
-            if (p != k) { const double x = b[k]; b[k] = b[p]; b[p] = x; }
-        }
-        for (int i = 1; i < N; ++i) {
-            double s = b[i];
-            for (int j = 0; j < i; ++j) s -= a[i * N + j] * b[j];
-            b[i] = s;
-        }
-        for (int i = N - 1; i >= 0; --i) {
-            double s = b[i];
-            for (int j = i + 1; j < N; ++j) s -= a[i * N + j] * b[j];
-            b[i] = s / a[i * N + i];
+        if constexpr (N <= IMPLICIT_STATIC_N) {
+            SODM_UNROLL_SMALL
+            for (int k = 0; k < N; ++k) {
+                SODM_UNROLL_SMALL
+                for (int i = k + 1; i < N; ++i) {
+                    const bool sw = piv[k] == i;
+                    const double x = b[k], y = b[i];
+                    b[k] = sw ? y : x;
+                    b[i] = sw ? x : y;
+                }
+            }
+            SODM_UNROLL_SMALL
+            for (int i = 1; i < N; ++i) {
+                double s = b[i];
+                SODM_UNROLL_SMALL
+                for (int j = 0; j < i; ++j) s -= a[i * N + j] * b[j];
+                b[i] = s;
+            }
+            SODM_UNROLL_SMALL
+            for (int i = N - 1; i >= 0; --i) {
+                double s = b[i];
+                SODM_UNROLL_SMALL
+                for (int j = i + 1; j < N; ++j) s -= a[i * N + j] * b[j];
+                b[i] = s / a[i * N + i];
+            }
+        } else {
+            for (int k = 0; k < N; ++k) {
+                const int p = piv[k];
+                if (p != k) { const double x = b[k]; b[k] = b[p]; b[p] = x; }
+            }
+            for (int i = 1; i < N; ++i) {
+                double s = b[i];
+                for (int j = 0; j < i; ++j) s -= a[i * N + j] * b[j];
+                b[i] = s;
+            }
+            for (int i = N - 1; i >= 0; --i) {
+                double s = b[i];
+                for (int j = i + 1; j < N; ++j) s -= a[i * N + j] * b[j];
+                b[i] = s / a[i * N + i];
+            }
         }
     }
 };
@@ -97,65 +164,150 @@ struct LuComplex {
     double re[N * N], im[N * N];
     int piv[N];
     __host__ __device__ void factor() {
-        for (int k = 0; k < N; ++k) {
-            int p = k;
-            double best = fabs(re[k * N + k]) + fabs(im[k * N + k]);
-            for (int i = k + 1; i < N; ++i) {
-                const double v = fabs(re[i * N + k]) + fabs(im[i * N + k]);
-                if (v > best) { best = v; p = i; }
-            }
-            piv[k] = p;
-            if (p != k)
-                for (int j = 0; j < N; ++j) {
-                    double x = re[k * N + j]; re[k * N + j] = re[p * N + j]; re[p * N + j] = x;
-                    x = im[k * N + j]; im[k * N + j] = im[p * N + j]; im[p * N + j] = x;
+        if constexpr (N <= IMPLICIT_STATIC_N) {
+            SODM_UNROLL_SMALL
+            for (int k = 0; k < N; ++k) {
+                int p = k;
+                double best = fabs(re[k * N + k]) + fabs(im[k * N + k]);
+                SODM_UNROLL_SMALL
+                for (int i = k + 1; i < N; ++i) {
+                    const double v = fabs(re[i * N + k]) + fabs(im[i * N + k]);
+                    if (v > best) { best = v; p = i; }
                 }
-            const double dr = re[k * N + k], di = im[k * N + k];
-            if (dr != 0.0 || di != 0.0) {
+                piv[k] = p;
+                SODM_UNROLL_SMALL
+                for (int i = k + 1; i < N; ++i) {
+                    const bool sw = p == i;
+                    SODM_UNROLL_SMALL
+                    for (int j = 0; j < N; ++j) {
+                        double x = re[k * N + j], y = re[i * N + j];
+                        re[k * N + j] = sw ? y : x;
+                        re[i * N + j] = sw ? x : y;
+                        x = im[k * N + j]; y = im[i * N + j];
+                        im[k * N + j] = sw ? y : x;
+                        im[i * N + j] = sw ? x : y;
+                    }
+                }
+                const double dr = re[k * N + k], di = im[k * N + k];
+                const bool nz = dr != 0.0 || di != 0.0;
                 const double m = 1.0 / (dr * dr + di * di);
                 const double rr = dr * m, ri = -di * m;                    // 1 / pivot
+                SODM_UNROLL_SMALL
                 for (int i = k + 1; i < N; ++i) {
-                    const double xr = re[i * N + k], xi = im[i * N + k];
-                    re[i * N + k] = xr * rr - xi * ri;
-                    im[i * N + k] = xr * ri + xi * rr;
+                    if (nz) {
+                        const double xr = re[i * N + k], xi = im[i * N + k];
+                        re[i * N + k] = xr * rr - xi * ri;
+                        im[i * N + k] = xr * ri + xi * rr;
+                    }
+                    const double lr = re[i * N + k], li = im[i * N + k];
+                    SODM_UNROLL_SMALL
+                    for (int j = k + 1; j < N; ++j) {
+                        const double ur = re[k * N + j], ui = im[k * N + j];
+                        re[i * N + j] -= lr * ur - li * ui;
+                        im[i * N + j] -= lr * ui + li * ur;
+                    }
                 }
             }
-            for (int i = k + 1; i < N; ++i) {
-                const double lr = re[i * N + k], li = im[i * N + k];
-                for (int j = k + 1; j < N; ++j) {
-                    const double ur = re[k * N + j], ui = im[k * N + j];
-                    re[i * N + j] -= lr * ur - li * ui;
-                    im[i * N + j] -= lr * ui + li * ur;
+        } else {
+            for (int k = 0; k < N; ++k) {
+                int p = k;
+                double best = fabs(re[k * N + k]) + fabs(im[k * N + k]);
+                for (int i = k + 1; i < N; ++i) {
+                    const double v = fabs(re[i * N + k]) + fabs(im[i * N + k]);
+                    if (v > best) { best = v; p = i; }
+                }
+                piv[k] = p;
+                if (p != k)
+                    for (int j = 0; j < N; ++j) {
+                        double x = re[k * N + j]; re[k * N + j] = re[p * N + j]; re[p * N + j] = x;
+                        x = im[k * N + j]; im[k * N + j] = im[p * N + j]; im[p * N + j] = x;
+                    }
+                const double dr = re[k * N + k], di = im[k * N + k];
+                if (dr != 0.0 || di != 0.0) {
+                    const double m = 1.0 / (dr * dr + di * di);
+                    const double rr = dr * m, ri = -di * m;                    // 1 / pivot
+                    for (int i = k + 1; i < N; ++i) {
+                        const double xr = re[i * N + k], xi = im[i * N + k];
+                        re[i * N + k] = xr * rr - xi * ri;
+                        im[i * N + k] = xr * ri + xi * rr;
+                    }
+                }
+                for (int i = k + 1; i < N; ++i) {
+                    const double lr = re[i * N + k], li = im[i * N + k];
+                    for (int j = k + 1; j < N; ++j) {
+                        const double ur = re[k * N + j], ui = im[k * N + j];
+                        re[i * N + j] -= lr * ur - li * ui;
+                        im[i * N + j] -= lr * ui + li * ur;
+                    }
                 }
             }
         }
     }
     __host__ __device__ void solve(double* br, double* bi) const {
-        for (int k = 0; k < N; ++k) {
-            const int p = piv[k];
-            if (p != k) {
-                double x = br[k]; br[k] = br[p]; br[p] = x;
-                x = bi[k]; bi[k] = bi[p]; bi[p] = x;
+        if constexpr (N <= IMPLICIT_STATIC_N) {
+            SODM_UNROLL_SMALL
+            for (int k = 0; k < N; ++k) {
+                SODM_UNROLL_SMALL
+                for (int i = k + 1; i < N; ++i) {
+                    const bool sw = piv[k] == i;
+                    double x = br[k], y = br[i];
+                    br[k] = sw ? y : x;
+                    br[i] = sw ? x : y;
+                    x = bi[k]; y = bi[i];
+                    bi[k] = sw ? y : x;
+                    bi[i] = sw ? x : y;
+                }
             }
-        }
-        for (int i = 1; i < N; ++i) {
-            double sr = br[i], si = bi[i];
-            for (int j = 0; j < i; ++j) {
-                sr -= re[i * N + j] * br[j] - im[i * N + j] * bi[j];
-                si -= re[i * N + j] * bi[j] + im[i * N + j] * br[j];
+            SODM_UNROLL_SMALL
+            for (int i = 1; i < N; ++i) {
+                double sr = br[i], si = bi[i];
+                SODM_UNROLL_SMALL
+                for (int j = 0; j < i; ++j) {
+                    sr -= re[i * N + j] * br[j] - im[i * N + j] * bi[j];
+                    si -= re[i * N + j] * bi[j] + im[i * N + j] * br[j];
+                }
+                br[i] = sr; bi[i] = si;
             }
-            br[i] = sr; bi[i] = si;
-        }
-        for (int i = N - 1; i >= 0; --i) {
-            double sr = br[i], si = bi[i];
-            for (int j = i + 1; j < N; ++j) {
-                sr -= re[i * N + j] * br[j] - im[i * N + j] * bi[j];
-                si -= re[i * N + j] * bi[j] + im[i * N + j] * br[j];
+            SODM_UNROLL_SMALL
+            for (int i = N - 1; i >= 0; --i) {
+                double sr = br[i], si = bi[i];
+                SODM_UNROLL_SMALL
+                for (int j = i + 1; j < N; ++j) {
+                    sr -= re[i * N + j] * br[j] - im[i * N + j] * bi[j];
+                    si -= re[i * N + j] * bi[j] + im[i * N + j] * br[j];
+                }
+                const double dr = re[i * N + i], di = im[i * N + i];
+                const double m = 1.0 / (dr * dr + di * di);
+                br[i] = (sr * dr + si * di) * m;
+                bi[i] = (si * dr - sr * di) * m;
             }
-            const double dr = re[i * N + i], di = im[i * N + i];
-            const double m = 1.0 / (dr * dr + di * di);
-            br[i] = (sr * dr + si * di) * m;
-            bi[i] = (si * dr - sr * di) * m;
+        } else {
+            for (int k = 0; k < N; ++k) {
+                const int p = piv[k];
+                if (p != k) {
+                    double x = br[k]; br[k] = br[p]; br[p] = x;
+                    x = bi[k]; bi[k] = bi[p]; bi[p] = x;
+                }
+            }
+            for (int i = 1; i < N; ++i) {
+                double sr = br[i], si = bi[i];
+                for (int j = 0; j < i; ++j) {
+                    sr -= re[i * N + j] * br[j] - im[i * N + j] * bi[j];
+                    si -= re[i * N + j] * bi[j] + im[i * N + j] * br[j];
+                }
+                br[i] = sr; bi[i] = si;
+            }
+            for (int i = N - 1; i >= 0; --i) {
+                double sr = br[i], si = bi[i];
+                for (int j = i + 1; j < N; ++j) {
+                    sr -= re[i * N + j] * br[j] - im[i * N + j] * bi[j];
+                    si -= re[i * N + j] * bi[j] + im[i * N + j] * br[j];
+                }
+                const double dr = re[i * N + i], di = im[i * N + i];
+                const double m = 1.0 / (dr * dr + di * di);
+                br[i] = (sr * dr + si * di) * m;
+                bi[i] = (si * dr - sr * di) * m;
+            }
         }
     }
 };
@@ -164,6 +316,7 @@ struct LuComplex {
 template <class Sys>
 struct ImplicitBase {
     static constexpr int N = Sys::NL;
+    static constexpr int UN = N <= IMPLICIT_STATIC_N ? N : 1;      // unroll factor of the loops over equations
     // read by the output drivers
     double t, t_bound, t_new, h;
     int nfev;
@@ -176,6 +329,7 @@ struct ImplicitBase {
 
     __host__ __device__ static double rms(const double* v, const double* scale) {
         double acc = 0.0;
+#pragma unroll UN
         for (int e = 0; e < N; ++e) { const double r = v[e] / scale[e]; acc += r * r; }
         return sqrt(acc) / sqrt((double)N);
     }
@@ -194,12 +348,15 @@ struct ImplicitBase {
         const double interval = fabs(t_bound - t);
         if (interval == 0.0) { h_abs = 0.0; return; }
         double scale[N], y1[N], f1[N];
+#pragma unroll UN
         for (int e = 0; e < N; ++e) scale[e] = atol + fabs(y[e]) * rtol;
         const double d0 = rms(y, scale), d1 = rms(f0, scale);
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         h0 = fmin(h0, interval);
+#pragma unroll UN
         for (int e = 0; e < N; ++e) y1[e] = y[e] + h0 * f0[e];
         sys.rhs(t + h0, y1, f1); ++nfev;
+#pragma unroll UN
         for (int e = 0; e < N; ++e) f1[e] = f1[e] - f0[e];
         const double d2 = rms(f1, scale) / h0;
         const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 1.0 / (double)(order + 1));
@@ -210,55 +367,61 @@ struct ImplicitBase {
     // calls and is adapted so that the difference stays clear of its own round-off; f = f(tt, yy).  Not counted in nfev.
     __host__ __device__ void num_jac(Sys& sys, double tt, const double* yy, const double* f) {
         const double EPS = DBL_EPSILON;
-        const double DIFF_REJECT = pow(EPS, 0.875), DIFF_SMALL = pow(EPS, 0.75), DIFF_BIG = pow(EPS, 0.25);
+        // EPS^0.875, EPS^0.75, EPS^0.25 (NUM_JAC_DIFF_REJECT / _SMALL / _BIG)
+        const double DIFF_REJECT = 2.0097183471152322e-14, DIFF_SMALL = 1.8189894035458565e-12, DIFF_BIG = 0.0001220703125;
         const double MIN_FACTOR = 1e3 * EPS;
         if (!have_factor) {
-            const double f0 = sqrt(EPS);
+            const double f0 = 1.4901161193847656e-08;                          // EPS^0.5
             for (int j = 0; j < N; ++j) jac_factor[j] = f0;
             have_factor = true;
         }
-        double yp[N], fn[N], diff[N];
-        for (int e = 0; e < N; ++e) yp[e] = yy[e];
+        // the column loop stays a loop (two inlined right-hand sides per column): what it indexes at run time are copies,
+        // so that the caller's y and f keep their registers
+        double yp[N], yl[N], fl[N], fn[N], diff[N];
+#pragma unroll UN
+        for (int e = 0; e < N; ++e) { yp[e] = yy[e]; yl[e] = yy[e]; fl[e] = f[e]; }
+#pragma unroll 1
         for (int j = 0; j < N; ++j) {
-            const double sign = f[j] >= 0.0 ? 1.0 : -1.0;
-            const double y_scale = sign * fmax(atol, fabs(yy[j]));
+            const double yj = yl[j];
+            const double sign = fl[j] >= 0.0 ? 1.0 : -1.0;
+            const double y_scale = sign * fmax(atol, fabs(yj));
             double fac = jac_factor[j];
-            double hj = imp_add(imp_add(yy[j], imp_mul(fac, y_scale)), -yy[j]);
+            double hj = imp_add(imp_add(yj, imp_mul(fac, y_scale)), -yj);
             while (hj == 0.0) {
                 fac *= 10.0;
-                hj = imp_add(imp_add(yy[j], imp_mul(fac, y_scale)), -yy[j]);
+                hj = imp_add(imp_add(yj, imp_mul(fac, y_scale)), -yj);
             }
-            yp[j] = imp_add(yy[j], hj);
+            yp[j] = imp_add(yj, hj);
             sys.rhs(tt, yp, fn);
-            int mi = 0;
-            double max_diff = -1.0;
+            double max_diff = -1.0, scale = 0.0;
+#pragma unroll UN
             for (int e = 0; e < N; ++e) {
                 diff[e] = fn[e] - f[e];
                 const double a = fabs(diff[e]);
-                if (a > max_diff) { max_diff = a; mi = e; }           // first maximum, as argmax
+                if (a > max_diff) { max_diff = a; scale = fmax(fabs(f[e]), fabs(fn[e])); }       // first maximum, as argmax
             }
-            double scale = fmax(fabs(f[mi]), fabs(fn[mi]));
             if (max_diff < DIFF_REJECT * scale) {
                 const double new_fac = 10.0 * fac;
-                const double h_new = imp_add(imp_add(yy[j], imp_mul(new_fac, y_scale)), -yy[j]);
-                yp[j] = imp_add(yy[j], h_new);
+                const double h_new = imp_add(imp_add(yj, imp_mul(new_fac, y_scale)), -yj);
+                yp[j] = imp_add(yj, h_new);
                 sys.rhs(tt, yp, fn);
-                int mi2 = 0;
-                double max_diff_new = -1.0;
+                double max_diff_new = -1.0, scale_new = 0.0;
+#pragma unroll UN
                 for (int e = 0; e < N; ++e) {
                     const double a = fabs(fn[e] - f[e]);
-                    if (a > max_diff_new) { max_diff_new = a; mi2 = e; }
+                    if (a > max_diff_new) { max_diff_new = a; scale_new = fmax(fabs(f[e]), fabs(fn[e])); }
                 }
-                const double scale_new = fmax(fabs(f[mi2]), fabs(fn[mi2]));
                 if (max_diff * scale_new < max_diff_new * scale) {
                     fac = new_fac;
                     hj = h_new;
+#pragma unroll UN
                     for (int e = 0; e < N; ++e) diff[e] = fn[e] - f[e];
                     scale = scale_new;
                     max_diff = max_diff_new;
                 }
             }
-            yp[j] = yy[j];
+            yp[j] = yj;
+#pragma unroll UN
             for (int e = 0; e < N; ++e) J[e * N + j] = diff[e] / hj;
             if (max_diff < DIFF_SMALL * scale) fac *= 10.0;
             if (max_diff > DIFF_BIG * scale) fac *= 0.1;
@@ -272,6 +435,7 @@ template <class Sys>
 struct RadauStepper : ImplicitBase<Sys> {
     using B = ImplicitBase<Sys>;
     static constexpr int N = Sys::NL;
+    static constexpr int UN = B::UN;
     static constexpr int NEWTON_MAXITER = 6;
     using B::t; using B::t_bound; using B::t_new; using B::h; using B::nfev; using B::st; using B::ynew;
     using B::rtol; using B::atol; using B::newton_tol; using B::h_abs; using B::J;
@@ -301,6 +465,7 @@ struct RadauStepper : ImplicitBase<Sys> {
     __host__ __device__ void sol(double tg, double* out) const {
         const double x = (tg - sol_t_old) / sol_h;
         const double x2 = x * x, x3 = x2 * x;
+#pragma unroll UN
         for (int e = 0; e < N; ++e) out[e] = (Q[e][0] * x + Q[e][1] * x2 + Q[e][2] * x3) + sol_y_old[e];
     }
 
@@ -312,11 +477,10 @@ struct RadauStepper : ImplicitBase<Sys> {
 
     // `solve_collocation_system`: simplified Newton iterations for Z (3 x N), started from Z (in/out)
     __host__ __device__ bool newton(Sys& sys, const double* y, const double* scale, int& n_iter, double& rate, bool& rate_ok) {
-        const double S6 = sqrt(6.0);
-        const double C[3] = {(4.0 - S6) / 10.0, (4.0 + S6) / 10.0, 1.0};
-        const double c13 = pow(3.0, 1.0 / 3.0), c23 = pow(3.0, 2.0 / 3.0);
-        const double MU_REAL = 3.0 + c23 - c13;
-        const double MU_CR = 3.0 + 0.5 * (c13 - c23), MU_CI = -0.5 * (pow(3.0, 5.0 / 6.0) + pow(3.0, 7.0 / 6.0));
+        // C = [(4 - sqrt 6) / 10, (4 + sqrt 6) / 10, 1]; MU_REAL = 3 + 3^(2/3) - 3^(1/3),
+        // MU_COMPLEX = 3 + (3^(1/3) - 3^(2/3)) / 2 - i (3^(5/6) + 3^(7/6)) / 2: the doubles scipy's module-level expressions evaluate to
+        const double C[3] = {0.15505102572168222, 0.6449489742783178, 1.0};
+        const double MU_REAL = 3.637834252744496, MU_CR = 2.6810828736277523, MU_CI = -3.050430199247411;
         const double T[3][3] = {{0.09443876248897524, -0.14125529502095421, 0.03002919410514742},
                                 {0.25021312296533332, 0.20412935229379994, -0.38294211275726192},
                                 {1.0, 1.0, 0.0}};
@@ -325,7 +489,9 @@ struct RadauStepper : ImplicitBase<Sys> {
                                  {0.50287263494578682, -2.57192694985560522, 0.59603920482822492}};
         const double M_real = MU_REAL / h, Mcr = MU_CR / h, Mci = MU_CI / h;
         double W[3][N], F[3][N], ytmp[N], br[N], bi[N], b0[N];
+#pragma unroll
         for (int i = 0; i < 3; ++i)
+#pragma unroll UN
             for (int e = 0; e < N; ++e) W[i][e] = TI[i][0] * Z[0][e] + TI[i][1] * Z[1][e] + TI[i][2] * Z[2][e];
         double dW_norm_old = 0.0;
         bool have_norm = false, converged = false;
@@ -334,12 +500,16 @@ struct RadauStepper : ImplicitBase<Sys> {
         int k = 0;
         for (; k < NEWTON_MAXITER; ++k) {
             bool ok = true;
+#pragma unroll
             for (int i = 0; i < 3; ++i) {
+#pragma unroll UN
                 for (int e = 0; e < N; ++e) ytmp[e] = y[e] + Z[i][e];
                 sys.rhs(t + h * C[i], ytmp, F[i]); ++nfev;
+#pragma unroll UN
                 for (int e = 0; e < N; ++e) ok = ok && finite_d(F[i][e]);
             }
             if (!ok) break;
+#pragma unroll UN
             for (int e = 0; e < N; ++e) {
                 b0[e] = (F[0][e] * TI[0][0] + F[1][e] * TI[0][1] + F[2][e] * TI[0][2]) - M_real * W[0][e];
                 // TI_COMPLEX = TI[1] + i TI[2];  M_complex (W1 + i W2)
@@ -351,6 +521,7 @@ struct RadauStepper : ImplicitBase<Sys> {
             lur.solve(b0);
             luc.solve(br, bi);
             double acc = 0.0;
+#pragma unroll UN
             for (int e = 0; e < N; ++e) {
                 const double r0 = b0[e] / scale[e], r1 = br[e] / scale[e], r2 = bi[e] / scale[e];
                 acc += r0 * r0 + r1 * r1 + r2 * r2;
@@ -358,8 +529,11 @@ struct RadauStepper : ImplicitBase<Sys> {
             const double dW_norm = sqrt(acc) / sqrt(3.0 * (double)N);
             if (have_norm) { rate = dW_norm / dW_norm_old; rate_ok = true; }
             if (rate_ok && (rate >= 1.0 || pow(rate, (double)(NEWTON_MAXITER - k)) / (1.0 - rate) * dW_norm > newton_tol)) break;
+#pragma unroll UN
             for (int e = 0; e < N; ++e) { W[0][e] += b0[e]; W[1][e] += br[e]; W[2][e] += bi[e]; }
+#pragma unroll
             for (int i = 0; i < 3; ++i)
+#pragma unroll UN
                 for (int e = 0; e < N; ++e) Z[i][e] = T[i][0] * W[0][e] + T[i][1] * W[1][e] + T[i][2] * W[2][e];
             if (dW_norm == 0.0 || (rate_ok && rate / (1.0 - rate) * dW_norm < newton_tol)) { converged = true; break; }
             dW_norm_old = dW_norm;
@@ -370,11 +544,11 @@ struct RadauStepper : ImplicitBase<Sys> {
     }
 
     __host__ __device__ void factorise() {
-        const double c13 = pow(3.0, 1.0 / 3.0), c23 = pow(3.0, 2.0 / 3.0);
-        const double MU_REAL = 3.0 + c23 - c13;
-        const double MU_CR = 3.0 + 0.5 * (c13 - c23), MU_CI = -0.5 * (pow(3.0, 5.0 / 6.0) + pow(3.0, 7.0 / 6.0));
+        const double MU_REAL = 3.637834252744496, MU_CR = 2.6810828736277523, MU_CI = -3.050430199247411;
         const double mr = MU_REAL / h, cr = MU_CR / h, ci = MU_CI / h;
+#pragma unroll UN
         for (int i = 0; i < N; ++i)
+#pragma unroll UN
             for (int j = 0; j < N; ++j) {
                 const double d = i == j ? 1.0 : 0.0;
                 lur.a[i * N + j] = mr * d - J[i * N + j];
@@ -388,12 +562,12 @@ struct RadauStepper : ImplicitBase<Sys> {
 
     template <class Stages>
     __host__ __device__ bool step(Sys& sys, const double* y, Stages&) {
-        const double S6 = sqrt(6.0);
-        const double C[3] = {(4.0 - S6) / 10.0, (4.0 + S6) / 10.0, 1.0};
-        const double E[3] = {(-13.0 - 7.0 * S6) / 3.0, (-13.0 + 7.0 * S6) / 3.0, -1.0 / 3.0};
-        const double P[3][3] = {{13.0 / 3.0 + 7.0 * S6 / 3.0, -23.0 / 3.0 - 22.0 * S6 / 3.0, 10.0 / 3.0 + 5.0 * S6},
-                                {13.0 / 3.0 - 7.0 * S6 / 3.0, -23.0 / 3.0 + 22.0 * S6 / 3.0, 10.0 / 3.0 - 5.0 * S6},
-                                {1.0 / 3.0, -8.0 / 3.0, 10.0 / 3.0}};
+        // C, E = [-13 - 7 sqrt 6, -13 + 7 sqrt 6, -1] / 3 and the interpolation matrix P, as scipy's module evaluates them
+        const double C[3] = {0.15505102572168222, 0.6449489742783178, 1.0};
+        const double E[3] = {-10.048809399827414, 1.382142733160748, -0.3333333333333333};
+        const double P[3][3] = {{10.048809399827414, -25.62959144707664, 15.580782047249224},
+                                {-1.382142733160748, 10.296258113743303, -8.914115380582556},
+                                {0.3333333333333333, -2.6666666666666665, 3.3333333333333335}};
         const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);
         double ha, ha_old = 0.0, en_old = 0.0;
         bool old_ok;
@@ -410,16 +584,21 @@ struct RadauStepper : ImplicitBase<Sys> {
             if (t_new - t_bound > 0.0) t_new = t_bound;
             h = t_new - t;
             ha = fabs(h);
+#pragma unroll UN
             for (int e = 0; e < N; ++e) scale[e] = atol + fabs(y[e]) * rtol;
             bool converged = false;
             for (;;) {
                 if (!lu_valid) factorise();
                 if (!have_sol) {
+#pragma unroll
                     for (int i = 0; i < 3; ++i)
+#pragma unroll UN
                         for (int e = 0; e < N; ++e) Z[i][e] = 0.0;
                 } else {
+#pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         sol(t + h * C[i], ytmp);
+#pragma unroll UN
                         for (int e = 0; e < N; ++e) Z[i][e] = ytmp[e] - y[e];
                     }
                 }
@@ -434,18 +613,22 @@ struct RadauStepper : ImplicitBase<Sys> {
                 lu_valid = false;
                 continue;
             }
+#pragma unroll UN
             for (int e = 0; e < N; ++e) {
                 ynew[e] = y[e] + Z[2][e];
                 ze[e] = (Z[0][e] * E[0] + Z[1][e] * E[1] + Z[2][e] * E[2]) / h;
                 err[e] = f[e] + ze[e];
             }
             lur.solve(err);
+#pragma unroll UN
             for (int e = 0; e < N; ++e) scale[e] = atol + fmax(fabs(y[e]), fabs(ynew[e])) * rtol;
             error_norm = B::rms(err, scale);
             safety = 0.9 * (2 * NEWTON_MAXITER + 1) / (double)(2 * NEWTON_MAXITER + n_iter);
             if (rejected && error_norm > 1.0) {
+#pragma unroll UN
                 for (int e = 0; e < N; ++e) ytmp[e] = y[e] + err[e];
                 sys.rhs(t, ytmp, err); ++nfev;
+#pragma unroll UN
                 for (int e = 0; e < N; ++e) err[e] = err[e] + ze[e];
                 lur.solve(err);
                 error_norm = B::rms(err, scale);
@@ -472,6 +655,7 @@ struct RadauStepper : ImplicitBase<Sys> {
         h_abs = ha * factor;
         sol_t_old = t;
         sol_h = t_new - t;
+#pragma unroll UN
         for (int e = 0; e < N; ++e) {
             sol_y_old[e] = y[e];
             for (int j = 0; j < 3; ++j) Q[e][j] = Z[0][e] * P[0][j] + Z[1][e] * P[1][j] + Z[2][e] * P[2][j];
@@ -484,6 +668,7 @@ struct RadauStepper : ImplicitBase<Sys> {
     __host__ __device__ void dense(Sys&, const double*, Stages&, double tg, double* out) { sol(tg, out); }
 
     __host__ __device__ void commit(double* y) {
+#pragma unroll UN
         for (int e = 0; e < N; ++e) { y[e] = ynew[e]; f[e] = fnew[e]; }
         t = t_new;
     }
@@ -494,41 +679,65 @@ template <class Sys>
 struct BdfStepper : ImplicitBase<Sys> {
     using B = ImplicitBase<Sys>;
     static constexpr int N = Sys::NL;
+    static constexpr int UN = B::UN;
     static constexpr int MAX_ORDER = 5, NEWTON_MAXITER = 4;
     using B::t; using B::t_bound; using B::t_new; using B::h; using B::nfev; using B::st; using B::ynew;
     using B::rtol; using B::atol; using B::newton_tol; using B::h_abs; using B::J;
 
-    double D[MAX_ORDER + 3][N];
-    double gamma[MAX_ORDER + 1], alpha[MAX_ORDER + 1], error_const[MAX_ORDER + 1];
+    double D[MAX_ORDER + 3][N];               // indexed by compile-time constants only (unrolled loops, predicated on the order)
     int order, n_equal_steps;
+    // kappa = [0, -0.1850, -1/9, -0.0823, -0.0415, 0]; gamma = [0, cumsum 1/k]; alpha = (1 - kappa) gamma;
+    // error_const = kappa gamma + 1 / (k + 1): the doubles scipy's expressions evaluate to, selected without a table in memory
+    __host__ __device__ static __forceinline__ double pick6(int k, double c0, double c1, double c2, double c3, double c4, double c5) {
+        return k == 0 ? c0 : k == 1 ? c1 : k == 2 ? c2 : k == 3 ? c3 : k == 4 ? c4 : c5;
+    }
+    __host__ __device__ static __forceinline__ double gamma_(int k) { return pick6(k, 0.0, 1.0, 1.5, 1.8333333333333333, 2.083333333333333, 2.283333333333333); }
+    __host__ __device__ static __forceinline__ double alpha_(int k) {
+        return pick6(k, 0.0, 1.185, 1.6666666666666667, 1.9842166666666667, 2.1697916666666663, 2.283333333333333);
+    }
+    __host__ __device__ static __forceinline__ double error_const_(int k) {
+        return pick6(k, 1.0, 0.315, 0.16666666666666666, 0.09911666666666669, 0.11354166666666668, 0.16666666666666666);
+    }
     bool lu_valid;
     LuReal<N> lu;
 
-    // `change_D`: D[:order + 1] <- (R(factor) U)^T D[:order + 1]
-    __host__ __device__ static void compute_R(int ord, double factor, double R[MAX_ORDER + 1][MAX_ORDER + 1]) {
-        for (int j = 0; j <= ord; ++j) R[0][j] = 1.0;
-        for (int i = 1; i <= ord; ++i) {
-            R[i][0] = 0.0;
-            for (int j = 1; j <= ord; ++j) R[i][j] = R[i - 1][j] * (((double)(i - 1) - factor * (double)j) / (double)i);
-        }
-    }
+    // `change_D`: D[:order + 1] <- (R(factor) U)^T D[:order + 1].  R[i][j] = prod_{m <= i} (m - 1 - factor j) / m does not depend
+    // on the order, and U = R(1) is the signed Pascal matrix U[k][j] = (-1)^k C(j, k) exactly in floating point (checked against
+    // scipy's compute_R), so R U is formed for the maximal order with every loop unrolled -- its leading (order + 1)^2 block is
+    // what scipy computes, the same terms in the same order -- and applied under predicates on the order.
     __host__ __device__ void change_D(int ord, double factor) {
-        double R[MAX_ORDER + 1][MAX_ORDER + 1], U[MAX_ORDER + 1][MAX_ORDER + 1], RU[MAX_ORDER + 1][MAX_ORDER + 1];
-        compute_R(ord, factor, R);
-        compute_R(ord, 1.0, U);
-        for (int i = 0; i <= ord; ++i)
-            for (int j = 0; j <= ord; ++j) {
+        constexpr int M = MAX_ORDER + 1;
+        constexpr double U[M][M] = {{1, 1, 1, 1, 1, 1}, {0, -1, -2, -3, -4, -5}, {0, 0, 1, 3, 6, 10},
+                                    {0, 0, 0, -1, -4, -10}, {0, 0, 0, 0, 1, 5}, {0, 0, 0, 0, 0, -1}};
+        double R[M][M], RU[M][M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) R[0][j] = 1.0;
+#pragma unroll
+        for (int i = 1; i < M; ++i) {
+            R[i][0] = 0.0;
+#pragma unroll
+            for (int j = 1; j < M; ++j) R[i][j] = R[i - 1][j] * (((double)(i - 1) - factor * (double)j) / (double)i);
+        }
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
                 double s = 0.0;
-                for (int k = 0; k <= ord; ++k) s += R[i][k] * U[k][j];
+#pragma unroll
+                for (int k = 0; k <= j; ++k) s += R[i][k] * U[k][j];           // U[k][j] = 0 for k > j
                 RU[i][j] = s;
             }
-        double col[MAX_ORDER + 1];
+#pragma unroll UN
         for (int e = 0; e < N; ++e) {
-            for (int i = 0; i <= ord; ++i) col[i] = D[i][e];
-            for (int i = 0; i <= ord; ++i) {
+            double col[M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) col[i] = D[i][e];
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
                 double s = 0.0;
-                for (int k = 0; k <= ord; ++k) s += RU[k][i] * col[k];
-                D[i][e] = s;
+#pragma unroll
+                for (int k = 0; k < M; ++k) s += k <= ord ? RU[k][i] * col[k] : 0.0;
+                if (i <= ord) D[i][e] = s;
             }
         }
     }
@@ -541,15 +750,11 @@ struct BdfStepper : ImplicitBase<Sys> {
         sys.rhs(L.t0, y, f); ++nfev;
         B::init_common(sys, L, y, f, 1);
         B::num_jac(sys, t, y, f);
-        const double kappa[MAX_ORDER + 1] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
-        gamma[0] = 0.0;
-        for (int k = 1; k <= MAX_ORDER; ++k) gamma[k] = gamma[k - 1] + 1.0 / (double)k;
-        for (int k = 0; k <= MAX_ORDER; ++k) {
-            alpha[k] = (1.0 - kappa[k]) * gamma[k];
-            error_const[k] = kappa[k] * gamma[k] + 1.0 / (double)(k + 1);
-        }
+#pragma unroll UN
         for (int e = 0; e < N; ++e) { D[0][e] = y[e]; D[1][e] = f[e] * h_abs; }
+#pragma unroll
         for (int k = 2; k < MAX_ORDER + 3; ++k)
+#pragma unroll UN
             for (int e = 0; e < N; ++e) D[k][e] = 0.0;
         order = 1;
         n_equal_steps = 0;
@@ -559,6 +764,7 @@ struct BdfStepper : ImplicitBase<Sys> {
     __host__ __device__ bool newton(Sys& sys, const double* y_predict, double c, const double* psi, const double* scale,
                                     int& n_iter, double* d) {
         double f[N], dy[N];
+#pragma unroll UN
         for (int e = 0; e < N; ++e) { d[e] = 0.0; ynew[e] = y_predict[e]; }
         double dy_norm_old = 0.0;
         bool have_norm = false, converged = false;
@@ -566,8 +772,10 @@ struct BdfStepper : ImplicitBase<Sys> {
         for (; k < NEWTON_MAXITER; ++k) {
             sys.rhs(t_new, ynew, f); ++nfev;
             bool ok = true;
+#pragma unroll UN
             for (int e = 0; e < N; ++e) ok = ok && finite_d(f[e]);
             if (!ok) break;
+#pragma unroll UN
             for (int e = 0; e < N; ++e) dy[e] = (c * f[e] - psi[e]) - d[e];
             lu.solve(dy);
             const double dy_norm = B::rms(dy, scale);
@@ -575,6 +783,7 @@ struct BdfStepper : ImplicitBase<Sys> {
             const bool rate_ok = have_norm;
             if (rate_ok) rate = dy_norm / dy_norm_old;
             if (rate_ok && (rate >= 1.0 || pow(rate, (double)(NEWTON_MAXITER - k)) / (1.0 - rate) * dy_norm > newton_tol)) break;
+#pragma unroll UN
             for (int e = 0; e < N; ++e) { ynew[e] += dy[e]; d[e] += dy[e]; }
             if (dy_norm == 0.0 || (rate_ok && rate / (1.0 - rate) * dy_norm < newton_tol)) { converged = true; break; }
             dy_norm_old = dy_norm;
@@ -609,20 +818,26 @@ struct BdfStepper : ImplicitBase<Sys> {
             }
             h = t_new - t;
             ha = fabs(h);
+            const double alpha_o = alpha_(order);
+#pragma unroll UN
             for (int e = 0; e < N; ++e) {
                 double s = D[0][e];
-                for (int k = 1; k <= order; ++k) s += D[k][e];
+#pragma unroll
+                for (int k = 1; k <= MAX_ORDER; ++k) s += k <= order ? D[k][e] : 0.0;
                 y_predict[e] = s;
                 scale[e] = atol + rtol * fabs(s);
                 double p = 0.0;
-                for (int k = 1; k <= order; ++k) p += D[k][e] * gamma[k];
-                psi[e] = p / alpha[order];
+#pragma unroll
+                for (int k = 1; k <= MAX_ORDER; ++k) p += k <= order ? D[k][e] * gamma_(k) : 0.0;
+                psi[e] = p / alpha_o;
             }
-            const double c = h / alpha[order];
+            const double c = h / alpha_o;
             bool converged = false;
             for (;;) {
                 if (!lu_valid) {
+#pragma unroll UN
                     for (int i = 0; i < N; ++i)
+#pragma unroll UN
                         for (int j = 0; j < N; ++j) lu.a[i * N + j] = (i == j ? 1.0 : 0.0) - c * J[i * N + j];
                     lu.factor();
                     lu_valid = true;
@@ -642,9 +857,10 @@ struct BdfStepper : ImplicitBase<Sys> {
                 continue;
             }
             safety = 0.9 * (2 * NEWTON_MAXITER + 1) / (double)(2 * NEWTON_MAXITER + n_iter);
+#pragma unroll UN
             for (int e = 0; e < N; ++e) {
                 scale[e] = atol + rtol * fabs(ynew[e]);
-                tmp[e] = error_const[order] * d[e];
+                tmp[e] = error_const_(order) * d[e];
             }
             error_norm = B::rms(tmp, scale);
             if (!(error_norm == error_norm)) { st |= ST_NONFINITE | ST_STEP_TOO_SMALL; return false; }
@@ -658,24 +874,33 @@ struct BdfStepper : ImplicitBase<Sys> {
         }
         n_equal_steps += 1;
         h_abs = ha;
+#pragma unroll UN
         for (int e = 0; e < N; ++e) {
-            D[order + 2][e] = d[e] - D[order + 1][e];
-            D[order + 1][e] = d[e];
-            for (int i = order; i >= 0; --i) D[i][e] += D[i + 1][e];
+#pragma unroll
+            for (int k = 2; k <= MAX_ORDER + 2; ++k) {
+                if (k == order + 2) { D[k][e] = d[e] - D[k - 1][e]; D[k - 1][e] = d[e]; }
+            }
+#pragma unroll
+            for (int i = MAX_ORDER; i >= 0; --i) {
+                if (i <= order) D[i][e] += D[i + 1][e];
+            }
         }
         if (n_equal_steps < order + 1) return true;
         double en[3];
         if (order > 1) {
-            for (int e = 0; e < N; ++e) tmp[e] = error_const[order - 1] * D[order][e];
+#pragma unroll UN
+            for (int e = 0; e < N; ++e) tmp[e] = error_const_(order - 1) * d_at(order, e);
             en[0] = B::rms(tmp, scale);
         } else en[0] = INFINITY;
         en[1] = error_norm;
         if (order < MAX_ORDER) {
-            for (int e = 0; e < N; ++e) tmp[e] = error_const[order + 1] * D[order + 2][e];
+#pragma unroll UN
+            for (int e = 0; e < N; ++e) tmp[e] = error_const_(order + 1) * d_at(order + 2, e);
             en[2] = B::rms(tmp, scale);
         } else en[2] = INFINITY;
         int best = 0;
         double fmaxv = -1.0;
+#pragma unroll
         for (int i = 0; i < 3; ++i) {
             const double fi = pow(en[i], -1.0 / (double)(order + i));
             if (fi > fmaxv) { fmaxv = fi; best = i; }
@@ -689,24 +914,39 @@ struct BdfStepper : ImplicitBase<Sys> {
         return true;
     }
 
+    // D[k][e] for a run-time k in 1 .. MAX_ORDER + 2
+    __host__ __device__ __forceinline__ double d_at(int k, int e) const {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 1; q <= MAX_ORDER + 2; ++q) v = q == k ? D[q][e] : v;
+        return v;
+    }
+
     // BdfDenseOutput, built from the state AFTER the step (new order, new step size, rescaled differences)
     template <class Stages>
     __host__ __device__ void dense(Sys&, const double*, Stages&, double tg, double* out) {
         double p[MAX_ORDER];
         double acc = 1.0;
-        for (int k = 0; k < order; ++k) {
-            const double x = (tg - (t_new - h_abs * (double)k)) / (h_abs * (double)(1 + k));
-            acc *= x;
-            p[k] = acc;
+#pragma unroll
+        for (int k = 0; k < MAX_ORDER; ++k) {
+            p[k] = 0.0;
+            if (k < order) {
+                const double x = (tg - (t_new - h_abs * (double)k)) / (h_abs * (double)(1 + k));
+                acc *= x;
+                p[k] = acc;
+            }
         }
+#pragma unroll UN
         for (int e = 0; e < N; ++e) {
             double s = 0.0;
-            for (int k = 0; k < order; ++k) s += D[1 + k][e] * p[k];
+#pragma unroll
+            for (int k = 0; k < MAX_ORDER; ++k) s += k < order ? D[1 + k][e] * p[k] : 0.0;
             out[e] = s + D[0][e];
         }
     }
 
     __host__ __device__ void commit(double* y) {
+#pragma unroll UN
         for (int e = 0; e < N; ++e) y[e] = ynew[e];
         t = t_new;
     }
