@@ -24,8 +24,8 @@
 
 namespace sodm {
 
-struct SchemeRadau { static constexpr int NSLOT = 1; };
-struct SchemeBDF   { static constexpr int NSLOT = 1; };
+struct SchemeRadau { static constexpr int NSLOT = 1, WINDOWED_MIN_BLOCKS = 2; };
+struct SchemeBDF   { static constexpr int NSLOT = 1, WINDOWED_MIN_BLOCKS = 2; };
 constexpr int IMPLICIT_MAX_N = 32;          // dense Jacobian + up to three factorisations per THREAD
 
 __host__ __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= DBL_MAX; }

@@ -1,6 +1,7 @@
 // Thread-per-trajectory ODE ensemble kernel and its launcher, as templates over the model functor: shared by the
 // built-in models (sodm_ode.cu) and by generated models compiled into plugin libraries (plugin.cuh).
 #pragma once
+#include <type_traits>
 #include "ode_setup.cuh"
 
 namespace sodm {
@@ -30,8 +31,14 @@ __global__ void __launch_bounds__(ODE_BLOCK) ode_thread_kernel(const __grid_cons
 #ifndef SODM_ODE_WINDOWED_MIN_BLOCKS
 #define SODM_ODE_WINDOWED_MIN_BLOCKS 4      // 128 registers; measured on C1 at 4 x 10^6 draws: 11.5 ms unbounded (162 registers), 10.0 ms at 4, 13.4 ms at 5
 #endif
+// a scheme may ask for its own residency: the implicit steppers carry a Jacobian and its factorisations per thread and run
+// faster with 2 blocks x 255 registers than with 4 x 128 (profiles/r2_implicit_minb.txt: Radau 5.16 -> 4.25 ms, BDF 11.9 -> 10.3 ms)
+template <class Scheme, class = void> struct windowed_min_blocks { static constexpr int value = SODM_ODE_WINDOWED_MIN_BLOCKS; };
+template <class Scheme> struct windowed_min_blocks<Scheme, std::void_t<decltype(Scheme::WINDOWED_MIN_BLOCKS)>> {
+    static constexpr int value = Scheme::WINDOWED_MIN_BLOCKS;
+};
 template <class M, typename OutT, class Scheme = SchemeRK45>
-__global__ void __launch_bounds__(ODE_BLOCK, SODM_ODE_WINDOWED_MIN_BLOCKS) ode_thread_rk45_windowed_kernel(const __grid_constant__ OdeLaunch L) {
+__global__ void __launch_bounds__(ODE_BLOCK, windowed_min_blocks<Scheme>::value) ode_thread_rk45_windowed_kernel(const __grid_constant__ OdeLaunch L) {
     extern __shared__ double ode_window_smem[];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     ode_thread_trajectory_windowed<M, OutT, Scheme>(L, i, i < L.n_traj, ode_window_smem + threadIdx.x, ode_window<M>(), ODE_BLOCK);

@@ -1,4 +1,4 @@
-"""One or two launches of a non-headline kernel for ncu:  python tools/profile_configs.py <pfr25|pfr100|sir_ode|ssa|loglik|sirsi> [n]"""
+"""One or two launches of a non-headline kernel for ncu:  python tools/profile_configs.py <pfr25|pfr100|sir_ode|sir_radau|sir_bdf|ssa|loglik|sirsi> [n]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -18,12 +18,13 @@ if which in ("pfr25", "pfr100"):
                                      out_last_only=True, var=var, out=out, dev=dev)
     torch.cuda.synchronize()
     print("ok", float(nfev.double().mean()), int(st.max()))
-elif which == "sir_ode":
-    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+elif which in ("sir_ode", "sir_radau", "sir_bdf"):
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else (1_000_000 if which == "sir_ode" else 100_000)
+    method = {"sir_ode": "RK45", "sir_radau": "Radau", "sir_bdf": "BDF"}[which]
     betas = torch.from_numpy(rng.uniform(0.25, 0.45, size=n)).to(dev)[None, :]
     out = torch.empty((3, 121, n), dtype=torch.float64, device=dev)
     for rep in range(2):
-        engine.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], n, 0, 121, var=([0], betas), out=out, dev=dev)
+        engine.ode_run("sir_ode", [1000, 1, 0], [0.35, 5], n, 0, 121, var=([0], betas), out=out, dev=dev, method=method)
     torch.cuda.synchronize()
     print("ok")
 elif which == "ssa":

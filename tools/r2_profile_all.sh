@@ -24,6 +24,8 @@ for w in $want; do
     pfr25)    cap pfr25 ode_pfr 1 python tools/profile_configs.py pfr25 ;;
     pfr100)   cap pfr100 ode_pfr 1 python tools/profile_configs.py pfr100 1024 ;;
     sir_ode)  cap sir_ode ode_thread 1 python tools/profile_configs.py sir_ode ;;
+    sir_radau) cap sir_radau ode_thread 1 python tools/profile_configs.py sir_radau ;;
+    sir_bdf)  cap sir_bdf ode_thread 1 python tools/profile_configs.py sir_bdf ;;
     ssa)      cap ssa ssa_kernel 1 python tools/profile_configs.py ssa ;;
     loglik)   cap loglik loglik 1 python tools/profile_configs.py loglik ;;
   esac
