@@ -47,6 +47,9 @@ __host__ __device__ __forceinline__ double imp_add(double a, double b) {
 #endif
 }
 
+// one copy of pow per kernel (its body is several hundred instructions; inlined at every use it crowds the instruction cache)
+__host__ __device__ static __noinline__ double imp_pow(double a, double b) { return pow(a, b); }
+
 // ---- dense LU, real and complex ----------------------------------------------------------------------------------------
 // Systems of at most IMPLICIT_STATIC_N equations take a path on which EVERY array index is a compile-time constant (loops fully
 // unrolled, the pivot row reached through predicated swaps instead of a run-time row index): per-thread arrays indexed at run
@@ -359,7 +362,7 @@ struct ImplicitBase {
 #pragma unroll UN
         for (int e = 0; e < N; ++e) f1[e] = f1[e] - f0[e];
         const double d2 = rms(f1, scale) / h0;
-        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 1.0 / (double)(order + 1));
+        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : imp_pow(0.01 / fmax(d1, d2), 1.0 / (double)(order + 1));
         h_abs = fmin(fmin(100.0 * h0, h1), interval);
     }
 
@@ -471,8 +474,8 @@ struct RadauStepper : ImplicitBase<Sys> {
 
     __host__ __device__ static double predict_factor(double ha, bool old_ok, double ha_old, double en, double en_old) {
         double multiplier = 1.0;
-        if (old_ok && en != 0.0) multiplier = ha / ha_old * pow(en_old / en, 0.25);
-        return fmin(1.0, multiplier) * pow(en, -0.25);
+        if (old_ok && en != 0.0) multiplier = ha / ha_old * imp_pow(en_old / en, 0.25);
+        return fmin(1.0, multiplier) * imp_pow(en, -0.25);
     }
 
     // `solve_collocation_system`: simplified Newton iterations for Z (3 x N), started from Z (in/out)
@@ -528,7 +531,7 @@ struct RadauStepper : ImplicitBase<Sys> {
             }
             const double dW_norm = sqrt(acc) / sqrt(3.0 * (double)N);
             if (have_norm) { rate = dW_norm / dW_norm_old; rate_ok = true; }
-            if (rate_ok && (rate >= 1.0 || pow(rate, (double)(NEWTON_MAXITER - k)) / (1.0 - rate) * dW_norm > newton_tol)) break;
+            if (rate_ok && (rate >= 1.0 || imp_pow(rate, (double)(NEWTON_MAXITER - k)) / (1.0 - rate) * dW_norm > newton_tol)) break;
 #pragma unroll UN
             for (int e = 0; e < N; ++e) { W[0][e] += b0[e]; W[1][e] += br[e]; W[2][e] += bi[e]; }
 #pragma unroll
@@ -782,7 +785,7 @@ struct BdfStepper : ImplicitBase<Sys> {
             double rate = 0.0;
             const bool rate_ok = have_norm;
             if (rate_ok) rate = dy_norm / dy_norm_old;
-            if (rate_ok && (rate >= 1.0 || pow(rate, (double)(NEWTON_MAXITER - k)) / (1.0 - rate) * dy_norm > newton_tol)) break;
+            if (rate_ok && (rate >= 1.0 || imp_pow(rate, (double)(NEWTON_MAXITER - k)) / (1.0 - rate) * dy_norm > newton_tol)) break;
 #pragma unroll UN
             for (int e = 0; e < N; ++e) { ynew[e] += dy[e]; d[e] += dy[e]; }
             if (dy_norm == 0.0 || (rate_ok && rate / (1.0 - rate) * dy_norm < newton_tol)) { converged = true; break; }
@@ -797,27 +800,38 @@ struct BdfStepper : ImplicitBase<Sys> {
     __host__ __device__ bool step(Sys& sys, const double*, Stages&) {
         const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);
         double ha;
+        // `change_D` has ONE call site: every rescaling of the difference array is posted as a pending factor and applied at the
+        // top of the attempt loop (inlined at each of scipy's six call sites the kernel was 258 KB of code and spent 58 % of its
+        // stall cycles waiting for instructions, profiles/r2_sir_bdf_ncu_summary.txt).  Same calls, same order, same arguments.
+        double pend = 0.0;                       // factor of the posted rescaling (0: none)
         if (h_abs < min_step) {
             ha = min_step;
-            change_D(order, min_step / h_abs);
+            pend = min_step / h_abs;
             n_equal_steps = 0;
         } else ha = h_abs;
-        bool current_jac = false;
+        bool current_jac = false, clipped = false, accepted = false;
         double y_predict[N], scale[N], psi[N], d[N], tmp[N];
         double error_norm = 0.0, safety = 0.0;
         int n_iter = 0;
         for (;;) {
-            if (ha < min_step) { st |= ST_STEP_TOO_SMALL; return false; }
-            h = ha;
-            t_new = t + h;
-            if (t_new - t_bound > 0.0) {
-                t_new = t_bound;
-                change_D(order, fabs(t_new - t) / ha);
-                n_equal_steps = 0;
-                lu_valid = false;
+            if (pend != 0.0) { change_D(order, pend); pend = 0.0; }
+            if (accepted) return true;
+            if (!clipped) {
+                if (ha < min_step) { st |= ST_STEP_TOO_SMALL; return false; }
+                h = ha;
+                t_new = t + h;
+                if (t_new - t_bound > 0.0) {
+                    t_new = t_bound;
+                    pend = fabs(t_new - t) / ha;
+                    n_equal_steps = 0;
+                    lu_valid = false;
+                    clipped = true;
+                }
+                h = t_new - t;
+                ha = fabs(h);
+                if (clipped) continue;
             }
-            h = t_new - t;
-            ha = fabs(h);
+            clipped = false;
             const double alpha_o = alpha_(order);
 #pragma unroll UN
             for (int e = 0; e < N; ++e) {
@@ -851,7 +865,7 @@ struct BdfStepper : ImplicitBase<Sys> {
             }
             if (!converged) {
                 ha *= 0.5;
-                change_D(order, 0.5);
+                pend = 0.5;
                 n_equal_steps = 0;
                 lu_valid = false;
                 continue;
@@ -865,53 +879,56 @@ struct BdfStepper : ImplicitBase<Sys> {
             error_norm = B::rms(tmp, scale);
             if (!(error_norm == error_norm)) { st |= ST_NONFINITE | ST_STEP_TOO_SMALL; return false; }
             if (error_norm > 1.0) {
-                const double factor = fmax(0.2, safety * pow(error_norm, -1.0 / (double)(order + 1)));
+                const double factor = fmax(0.2, safety * imp_pow(error_norm, -1.0 / (double)(order + 1)));
                 ha *= factor;
-                change_D(order, factor);
+                pend = factor;
                 n_equal_steps = 0;
                 // (scipy keeps the factorisation here: c changes with h, but LU is only reset where the code above says so)
-            } else break;
-        }
-        n_equal_steps += 1;
-        h_abs = ha;
-#pragma unroll UN
-        for (int e = 0; e < N; ++e) {
-#pragma unroll
-            for (int k = 2; k <= MAX_ORDER + 2; ++k) {
-                if (k == order + 2) { D[k][e] = d[e] - D[k - 1][e]; D[k - 1][e] = d[e]; }
+                continue;
             }
+            // ---- accepted ------------------------------------------------------------------------------------------------
+            n_equal_steps += 1;
+            h_abs = ha;
+#pragma unroll UN
+            for (int e = 0; e < N; ++e) {
 #pragma unroll
-            for (int i = MAX_ORDER; i >= 0; --i) {
-                if (i <= order) D[i][e] += D[i + 1][e];
+                for (int k = 2; k <= MAX_ORDER + 2; ++k) {
+                    if (k == order + 2) { D[k][e] = d[e] - D[k - 1][e]; D[k - 1][e] = d[e]; }
+                }
+#pragma unroll
+                for (int i = MAX_ORDER; i >= 0; --i) {
+                    if (i <= order) D[i][e] += D[i + 1][e];
+                }
             }
-        }
-        if (n_equal_steps < order + 1) return true;
-        double en[3];
-        if (order > 1) {
+            if (n_equal_steps < order + 1) return true;
+            double en[3];
+            en[0] = INFINITY;
+            en[1] = error_norm;
+            en[2] = INFINITY;
+#pragma unroll 1
+            for (int side = 0; side < 3; side += 2) {               // the estimates of orders k - 1 (D[k]) and k + 1 (D[k + 2])
+                if (side == 0 ? order > 1 : order < MAX_ORDER) {
+                    const double ec = error_const_(order - 1 + side);
 #pragma unroll UN
-            for (int e = 0; e < N; ++e) tmp[e] = error_const_(order - 1) * d_at(order, e);
-            en[0] = B::rms(tmp, scale);
-        } else en[0] = INFINITY;
-        en[1] = error_norm;
-        if (order < MAX_ORDER) {
-#pragma unroll UN
-            for (int e = 0; e < N; ++e) tmp[e] = error_const_(order + 1) * d_at(order + 2, e);
-            en[2] = B::rms(tmp, scale);
-        } else en[2] = INFINITY;
-        int best = 0;
-        double fmaxv = -1.0;
+                    for (int e = 0; e < N; ++e) tmp[e] = ec * d_at(order + side, e);
+                    en[side] = B::rms(tmp, scale);
+                }
+            }
+            int best = 0;
+            double fmaxv = -1.0;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const double fi = pow(en[i], -1.0 / (double)(order + i));
-            if (fi > fmaxv) { fmaxv = fi; best = i; }
+            for (int i = 0; i < 3; ++i) {
+                const double fi = imp_pow(en[i], -1.0 / (double)(order + i));
+                if (fi > fmaxv) { fmaxv = fi; best = i; }
+            }
+            order += best - 1;
+            const double factor = fmin(10.0, safety * fmaxv);
+            h_abs *= factor;
+            pend = factor;
+            n_equal_steps = 0;
+            lu_valid = false;
+            accepted = true;
         }
-        order += best - 1;
-        const double factor = fmin(10.0, safety * fmaxv);
-        h_abs *= factor;
-        change_D(order, factor);
-        n_equal_steps = 0;
-        lu_valid = false;
-        return true;
     }
 
     // D[k][e] for a run-time k in 1 .. MAX_ORDER + 2

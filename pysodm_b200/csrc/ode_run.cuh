@@ -442,57 +442,61 @@ __host__ __device__ __forceinline__ void rk45_run_windowed(Sys& sys, const OdeLa
     }
     int64_t steps = 0;
     int lo = 0;                                                       // first kept index of the current window
-    while (lo < L.n_kept) {
-        const int hi = lo + W < L.n_kept ? lo + W : L.n_kept;
-        // (a) what the pending step covers of this window
-        if (pending) {
-            while (kj < hi && L.t0 + (double)g <= R.t_new) {
-                R.dense(sys, y, S, L.t0 + (double)g, ytmp);
-                const int kk = kj - lo;
+    // ONE call site for R.step(): the windows and, behind the last one, the remaining integration of a strided grid that ends
+    // before t_bound share the loop (the implicit steppers' step() is thousands of instructions; inlined twice it no longer fits
+    // the instruction cache).  `lo` is the same in every lane of the warp, so the vote below is taken by all lanes or by none.
+    for (;;) {
+        const bool windows = lo < L.n_kept;
+        if (!windows && !(valid && !dead && R.t < R.t_bound)) break;  // a strided grid may end before t_bound: the reference's
+        bool full = false;                                            // solver still integrates to the end (nfev and status say so)
+        if (windows) {
+            const int hi = lo + W < L.n_kept ? lo + W : L.n_kept;
+            // (a) what the pending step covers of this window
+            if (pending) {
+                while (kj < hi && L.t0 + (double)g <= R.t_new) {
+                    R.dense(sys, y, S, L.t0 + (double)g, ytmp);
+                    const int kk = kj - lo;
 #pragma unroll
-                for (int e = 0; e < NL; ++e) win[(kk * NL + e) * stride] = ytmp[e];
-                g += g_step; ++kj;
-            }
-            if (!(kj < L.n_kept && L.t0 + (double)g <= R.t_new)) {   // the step has delivered all its points
-                R.commit(y);
-                pending = false;
-            }
-        }
-        // (b) a trajectory that was abandoned reports NaN from there on (as scipy's failed solve leaves no values)
-        if (dead && valid) {
-            for (; kj < hi; ++kj, g += g_step) {
-                const int kk = kj - lo;
-#pragma unroll
-                for (int e = 0; e < NL; ++e) win[(kk * NL + e) * stride] = NAN;
-            }
-        }
-        // (c) window complete on every lane: store it, one (element, point) row per instruction
-        const bool full = kj >= hi;
-        if (window_all(full)) {
-            if (valid) {
-                OutT* out = (OutT*)L.out + i;
-                for (int kk = 0; kk < hi - lo; ++kk) {
-#pragma unroll
-                    for (int e = 0; e < NL; ++e)
-                        out[((int64_t)sys.global_index(e) * L.n_kept + lo + kk) * L.ld_out] = (OutT)win[(kk * NL + e) * stride];
+                    for (int e = 0; e < NL; ++e) win[(kk * NL + e) * stride] = ytmp[e];
+                    g += g_step; ++kj;
+                }
+                if (!(kj < L.n_kept && L.t0 + (double)g <= R.t_new)) {   // the step has delivered all its points
+                    R.commit(y);
+                    pending = false;
                 }
             }
-            lo = hi;
-            continue;
+            // (b) a trajectory that was abandoned reports NaN from there on (as scipy's failed solve leaves no values)
+            if (dead && valid) {
+                for (; kj < hi; ++kj, g += g_step) {
+                    const int kk = kj - lo;
+#pragma unroll
+                    for (int e = 0; e < NL; ++e) win[(kk * NL + e) * stride] = NAN;
+                }
+            }
+            // (c) window complete on every lane: store it, one (element, point) row per instruction
+            full = kj >= hi;
+            if (window_all(full)) {
+                if (valid) {
+                    OutT* out = (OutT*)L.out + i;
+                    for (int kk = 0; kk < hi - lo; ++kk) {
+#pragma unroll
+                        for (int e = 0; e < NL; ++e)
+                            out[((int64_t)sys.global_index(e) * L.n_kept + lo + kk) * L.ld_out] = (OutT)win[(kk * NL + e) * stride];
+                    }
+                }
+                lo = hi;
+                continue;
+            }
         }
         // (d) the next step
         if (!full && !pending && !dead) {
             if (!(R.t < R.t_bound)) dead = true;                      // (cannot happen: the last step ends on t_bound)
             else if (steps++ >= L.max_steps) { R.st |= ST_MAX_STEPS; dead = true; }
-            else if (R.step(sys, y, S)) pending = true;
-            else dead = true;
+            else if (R.step(sys, y, S)) {
+                if (windows) pending = true;
+                else R.commit(y);                                     // behind the last window nothing is delivered
+            } else dead = true;
         }
-    }
-    // a strided grid may end before t_bound: the reference's solver still integrates to the end (its nfev and status say so)
-    while (valid && !dead && R.t < R.t_bound) {
-        if (steps++ >= L.max_steps) { R.st |= ST_MAX_STEPS; break; }
-        if (!R.step(sys, y, S)) break;
-        R.commit(y);
     }
     if (valid) {
         if (L.nfev) L.nfev[i] = R.nfev;
