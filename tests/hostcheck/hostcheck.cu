@@ -185,6 +185,30 @@ struct VanDerPolOde {
     }
 };
 
+// The dense LU of the implicit steppers (implicit.cuh) on a caller's matrix: n = 3 takes the compile-time-indexed path, n = 12 the
+// run-time one; `aim` != nullptr: complex.  Solves A x = b in place (b, bim); A is row-major.
+template <int N>
+static void lu_host(const double* are, const double* aim, double* bre, double* bim) {
+    if (aim) {
+        LuComplex<N> lu;
+        for (int i = 0; i < N * N; ++i) { lu.re[i] = are[i]; lu.im[i] = aim[i]; }
+        lu.factor();
+        lu.solve(bre, bim);
+    } else {
+        LuReal<N> lu;
+        for (int i = 0; i < N * N; ++i) lu.a[i] = are[i];
+        lu.factor();
+        lu.solve(bre);
+    }
+}
+extern "C" int hc_lu_solve(int n, const double* are, const double* aim, double* bre, double* bim) {
+    if (n == 3) lu_host<3>(are, aim, bre, bim);
+    else if (n == 8) lu_host<8>(are, aim, bre, bim);
+    else if (n == 12) lu_host<12>(are, aim, bre, bim);
+    else return SODM_EUNSUPPORTED;
+    return SODM_OK;
+}
+
 extern "C" int hc_ode_test_model_run(const sodm_ode_args* a) {
     OdeLaunch L;
     sodm_model_info info = {};

@@ -132,6 +132,23 @@ def jump_run(model, y0, par, n_traj, t0, n_out, tau=0.5, method="tau_leap", var=
     return out, status
 
 
+def lu_solve(A, b):
+    """A x = b through the implicit steppers' own dense LU (n = 3, 8: compile-time-indexed path; 12: run-time path)."""
+    L = lib()
+    A = np.asarray(A)
+    n = A.shape[0]
+    cplx = np.iscomplexobj(A) or np.iscomplexobj(b)
+    are = np.ascontiguousarray(A.real, dtype=np.float64)
+    aim = np.ascontiguousarray(A.imag, dtype=np.float64) if cplx else None
+    bre = np.ascontiguousarray(np.asarray(b).real, dtype=np.float64).copy()
+    bim = np.ascontiguousarray(np.asarray(b).imag, dtype=np.float64).copy() if cplx else None
+    L.hc_lu_solve.restype = C.c_int
+    L.hc_lu_solve.argtypes = [C.c_int] + 4 * [C.c_void_p]
+    rc = L.hc_lu_solve(n, are.ctypes.data, aim.ctypes.data if cplx else None, bre.ctypes.data, bim.ctypes.data if cplx else None)
+    assert rc == 0, rc
+    return bre + 1j * bim if cplx else bre
+
+
 TEST_ODE_MODELS = {"test:robertson": (0, 3, 3), "test:vanderpol": (1, 2, 1)}      # name -> (id, n_state, n_param)
 
 

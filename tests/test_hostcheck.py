@@ -265,6 +265,26 @@ def test_radau_and_bdf_follow_scipy_step_for_step(golden, method):
         hc.ode_run("packed_pfr_ode", golden["ode"]["pfr25_y0"], td.pfr_flat_par(25), 1, 0, 11, model_arg=25, method=method)
 
 
+@pytest.mark.parametrize("n", [3, 8, 12])
+def test_dense_lu_of_the_implicit_steppers(n):
+    """LuReal / LuComplex (csrc/implicit.cuh) against LAPACK on matrices that need row interchanges at every column (largest
+    entries below the diagonal), both index paths (n <= 8: compile-time indices with predicated swaps; 12: run-time indices)."""
+    from scipy.linalg import lu_factor, lu_solve
+    rng = np.random.default_rng(n)
+    for trial in range(20):
+        A = rng.normal(size=(n, n))
+        A[np.arange(n), np.arange(n)] *= 1e-3                           # weak diagonal: partial pivoting must swap
+        b = rng.normal(size=n)
+        piv = lu_factor(A)[1]
+        assert (piv != np.arange(n)).any()
+        np.testing.assert_allclose(hc.lu_solve(A, b), lu_solve(lu_factor(A), b), rtol=1e-9, atol=1e-12)
+        Ac = A + 1j * rng.normal(size=(n, n))
+        bc = b + 1j * rng.normal(size=n)
+        np.testing.assert_allclose(hc.lu_solve(Ac, bc), lu_solve(lu_factor(Ac), bc), rtol=1e-9, atol=1e-12)
+    I = np.eye(n)
+    assert np.array_equal(hc.lu_solve(I, np.arange(n, dtype=float)), np.arange(n, dtype=float))
+
+
 @pytest.mark.parametrize("method", ["Radau", "BDF"])
 def test_radau_and_bdf_on_stiff_problems(golden, method):
     """Robertson's kinetics and the Van der Pol oscillator (mu = 0.5 .. 200, through its fast transitions) -- rejected steps,
