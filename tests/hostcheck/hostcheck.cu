@@ -209,16 +209,36 @@ extern "C" int hc_lu_solve(int n, const double* are, const double* aim, double* 
     return SODM_OK;
 }
 
+// a->model 2 / 3: a chain  y_i' = a_i y_(i-1) + b_i y_i + c_i y_(i+1) - q y_i^2  of 3 / 12 equations (par = a[N], b[N], c[N], q):
+// random stiff systems for the implicit steppers against scipy itself (tests/test_hostcheck.py evaluates the same expression,
+// operation for operation, in Python); 12 equations take the run-time-indexed path of implicit.cuh
+template <int N_>
+struct ChainOde {
+    static constexpr int N = N_, NPAR = 3 * N_ + 1;
+    __host__ __device__ static void rhs(double, const double* y, const double* par, double* dy) {
+        for (int i = 0; i < N; ++i) {
+            double s = par[N + i] * y[i];
+            if (i > 0) s = par[i] * y[i - 1] + s;
+            if (i < N - 1) s = s + par[2 * N + i] * y[i + 1];
+            dy[i] = s - par[3 * N] * y[i] * y[i];
+        }
+    }
+};
+
 extern "C" int hc_ode_test_model_run(const sodm_ode_args* a) {
     OdeLaunch L;
     sodm_model_info info = {};
     info.kind = SODM_KIND_ODE;
-    info.n_state = a->model == 0 ? RobertsonOde::N : VanDerPolOde::N;
-    info.n_param = a->model == 0 ? RobertsonOde::NPAR : VanDerPolOde::NPAR;
+    const int ns[4] = {RobertsonOde::N, VanDerPolOde::N, 3, 12}, np_[4] = {RobertsonOde::NPAR, VanDerPolOde::NPAR, 10, 37};
+    if (a->model < 0 || a->model > 3) return SODM_EMODEL;
+    info.n_state = ns[a->model];
+    info.n_param = np_[a->model];
     const int rc = build_ode_launch_for(a, L, info);
     if (rc != SODM_OK) return rc;
     if (a->model == 0) ode_host<RobertsonOde, double>(L, a->method, a->reserved);
-    else ode_host<VanDerPolOde, double>(L, a->method, a->reserved);
+    else if (a->model == 1) ode_host<VanDerPolOde, double>(L, a->method, a->reserved);
+    else if (a->model == 2) ode_host<ChainOde<3>, double>(L, a->method, a->reserved);
+    else ode_host<ChainOde<12>, double>(L, a->method, a->reserved);
     return SODM_OK;
 }
 

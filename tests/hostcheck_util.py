@@ -149,7 +149,7 @@ def lu_solve(A, b):
     return bre + 1j * bim if cplx else bre
 
 
-TEST_ODE_MODELS = {"test:robertson": (0, 3, 3), "test:vanderpol": (1, 2, 1)}      # name -> (id, n_state, n_param)
+TEST_ODE_MODELS = {"test:robertson": (0, 3, 3), "test:vanderpol": (1, 2, 1), "test:chain3": (2, 3, 10), "test:chain12": (3, 12, 37)}      # name -> (id, n_state, n_param)
 
 
 def ode_run(model, y0, par, n_traj, t0, n_out, method="RK45", rtol=1e-4, atol=1e-6, tau=0.0, var=None,

@@ -285,6 +285,39 @@ def test_dense_lu_of_the_implicit_steppers(n):
     assert np.array_equal(hc.lu_solve(I, np.arange(n, dtype=float)), np.arange(n, dtype=float))
 
 
+@pytest.mark.parametrize("method", ["Radau", "BDF", "RK45"])
+@pytest.mark.parametrize("n", [3, 12])
+def test_adaptive_methods_against_scipy_on_random_stiff_chains(method, n):
+    """Random chains  y_i' = a_i y_(i-1) + b_i y_i + c_i y_(i+1) - q y_i^2  with decay rates spread over four decades, through
+    the call the reference makes (`solve_ivp(fun, [t0, t1], y0, args=..., t_eval=grid, method=method, rtol=rtol)`, ref
+    base.py:855) and through the kernel code: identical `nfev` -- i.e. the same accepted / rejected steps, Newton iterations and
+    Jacobian refreshes -- for Jacobians of varied structure; 12 equations take the run-time-indexed path of implicit.cuh."""
+    from scipy.integrate import solve_ivp
+
+    def fun(t, y, par):
+        dy = np.empty(n)
+        for i in range(n):
+            s = par[n + i] * y[i]
+            if i > 0:
+                s = par[i] * y[i - 1] + s
+            if i < n - 1:
+                s = s + par[2 * n + i] * y[i + 1]
+            dy[i] = s - par[3 * n] * y[i] * y[i]
+        return dy
+    rng = np.random.default_rng(100 + n)
+    cases_ = 8 if method != "RK45" else 3
+    for c in range(cases_):
+        stiff = 10.0 ** rng.uniform(-1, 3 if method != "RK45" else 1, size=n)
+        par = np.concatenate([rng.uniform(0, 0.5, n) * stiff, -stiff, rng.uniform(0, 0.5, n) * stiff, [rng.uniform(0, 0.1)]])
+        y0 = rng.uniform(0.5, 2.0, size=n)
+        rtol = [1e-4, 1e-6][c % 2]
+        ref = solve_ivp(fun, [0, 30], y0, args=(par,), t_eval=np.arange(31.0), method=method, rtol=rtol)
+        out, nfev, st = hc.ode_run(f"test:chain{n}", y0, par, 1, 0, 31, method=method, rtol=rtol)
+        assert int(st[0]) == 0 and ref.status == 0
+        assert int(nfev[0]) == ref.nfev, (method, n, c, int(nfev[0]), ref.nfev)
+        np.testing.assert_allclose(out[:, :, 0], ref.y, rtol=1e-6, atol=1e-9)
+
+
 @pytest.mark.parametrize("method", ["Radau", "BDF"])
 def test_radau_and_bdf_on_stiff_problems(golden, method):
     """Robertson's kinetics and the Van der Pol oscillator (mu = 0.5 .. 200, through its fast transitions) -- rejected steps,
