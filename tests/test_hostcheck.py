@@ -285,7 +285,7 @@ def test_dense_lu_of_the_implicit_steppers(n):
     assert np.array_equal(hc.lu_solve(I, np.arange(n, dtype=float)), np.arange(n, dtype=float))
 
 
-@pytest.mark.parametrize("method", ["Radau", "BDF", "RK45"])
+@pytest.mark.parametrize("method", ["Radau", "BDF", "RK45", "RK23", "DOP853"])
 @pytest.mark.parametrize("n", [3, 12])
 def test_adaptive_methods_against_scipy_on_random_stiff_chains(method, n):
     """Random chains  y_i' = a_i y_(i-1) + b_i y_i + c_i y_(i+1) - q y_i^2  with decay rates spread over four decades, through
@@ -305,17 +305,30 @@ def test_adaptive_methods_against_scipy_on_random_stiff_chains(method, n):
             dy[i] = s - par[3 * n] * y[i] * y[i]
         return dy
     rng = np.random.default_rng(100 + n)
-    cases_ = 8 if method != "RK45" else 3
-    for c in range(cases_):
-        stiff = 10.0 ** rng.uniform(-1, 3 if method != "RK45" else 1, size=n)
+    implicit = method in ("Radau", "BDF")
+    for c in range(8 if implicit else 3):
+        stiff = 10.0 ** rng.uniform(-1, 3 if implicit else 1, size=n)
         par = np.concatenate([rng.uniform(0, 0.5, n) * stiff, -stiff, rng.uniform(0, 0.5, n) * stiff, [rng.uniform(0, 0.1)]])
         y0 = rng.uniform(0.5, 2.0, size=n)
         rtol = [1e-4, 1e-6][c % 2]
         ref = solve_ivp(fun, [0, 30], y0, args=(par,), t_eval=np.arange(31.0), method=method, rtol=rtol)
         out, nfev, st = hc.ode_run(f"test:chain{n}", y0, par, 1, 0, 31, method=method, rtol=rtol)
         assert int(st[0]) == 0 and ref.status == 0
-        assert int(nfev[0]) == ref.nfev, (method, n, c, int(nfev[0]), ref.nfev)
-        np.testing.assert_allclose(out[:, :, 0], ref.y, rtol=1e-6, atol=1e-9)
+        # scipy's own reproducibility: an explicit method at its stability limit (solution decayed below atol) accepts and rejects
+        # chaotically -- one ulp on y0 moves scipy's nfev (observed 497 / 506 / 515); only a reproducible nfev can be matched
+        band = {ref.nfev}
+        for toward in (np.inf, -np.inf):
+            yp = y0.copy()
+            yp[0] = np.nextafter(yp[0], toward)
+            band.add(solve_ivp(fun, [0, 30], yp, args=(par,), t_eval=np.arange(31.0), method=method, rtol=rtol).nfev)
+        if len(band) == 1:
+            assert int(nfev[0]) == ref.nfev, (method, n, c, int(nfev[0]), ref.nfev)
+            np.testing.assert_allclose(out[:, :, 0], ref.y, rtol=1e-6, atol=1e-9)
+        else:
+            assert not implicit
+            spread = max(band) - min(band)
+            assert min(band) - spread <= int(nfev[0]) <= max(band) + spread, (method, n, c, int(nfev[0]), sorted(band))
+            np.testing.assert_allclose(out[:, :, 0], ref.y, rtol=10 * rtol, atol=1e-4)
 
 
 @pytest.mark.parametrize("method", ["Radau", "BDF"])
