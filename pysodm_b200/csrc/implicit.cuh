@@ -15,8 +15,9 @@
 //   * dense LU with partial pivoting (LAPACK getrf / getrs order: row interchanges, multipliers scaled by the reciprocal
 //     pivot, complex pivots chosen by |re| + |im|).
 // The steppers expose the interface of `Rk45` (ode_run.cuh): init / step / dense / commit and the fields the output drivers
-// read, so both drivers (direct and windowed stores) serve them unchanged.  State lives in per-thread arrays (the Jacobian
-// and its factorisations are indexed at run time: local memory, L1-resident for the system sizes admitted here).
+// read, so both drivers (direct and windowed stores) serve them unchanged.  State lives in per-thread arrays; for systems of at
+// most IMPLICIT_STATIC_N equations every index into them is a compile-time constant (see LuReal), larger ones (up to
+// IMPLICIT_MAX_N) index at run time and live in local memory.
 #pragma once
 #include <cfloat>
 #include <cmath>
