@@ -741,6 +741,11 @@ class ODE(_DeviceBackedModel):
         else:
             raise NotImplementedError(f"method '{method}' has no device implementation (available: 'RK45', 'RK23', 'DOP853', 'Radau', "
                                       "'BDF', or a fixed step `tau` for Euler / method='RK4'); there is no CPU fallback")
+        if dev_method in ("Radau", "BDF"):
+            plug, n_eq = self.device_model, len(self._select_rows(None)[1])
+            if n_eq > 32 or plug == "packed_pfr_ode" or (plug is not None and not isinstance(plug, str) and plug.layout.get("warp")):
+                raise NotImplementedError(f"method '{method}' keeps a dense Jacobian per trajectory: offered for models of at most "
+                                          f"32 equations in the thread-per-trajectory layout (this model: {n_eq}); no CPU fallback")
         saved = copy.deepcopy(self.parameters)
         try:
             par, var, y0, _ = self._collect_draws(N, draw_function, draw_function_kwargs)
@@ -753,11 +758,6 @@ class ODE(_DeviceBackedModel):
             lib = _ffi.load()
             n_kept = int(lib.sodm_ode_n_kept(n_out, int(output_stride), int(bool(output_last_only))))
             variables, rows = self._select_rows(None)
-            if dev_method in ("Radau", "BDF"):
-                plug = self.device_model
-                if len(rows) > 32 or plug == "packed_pfr_ode" or (not isinstance(plug, str) and plug.layout.get("warp")):
-                    raise NotImplementedError(f"method '{method}' keeps a dense Jacobian per trajectory: offered for models of at most "
-                                              f"32 equations in the thread-per-trajectory layout (this model: {len(rows)}); no CPU fallback")
             host_dtype = engine.as_torch_dtype(output_dtype)
             if output == "device":
                 grid = np.arange(t0, t1 + 1)

@@ -90,6 +90,13 @@ def test_state_layout_and_flat_order():
     assert p._model_arg == 25 and np.array_equal(p._flat_y0(p.initial_states), td.pfr_flat_y0(25))
     par, var, y0, _ = p._collect_draws(1, None, {})
     assert np.array_equal(par, td.pfr_flat_par(25)) and not var
+    # the implicit methods keep a dense Jacobian per trajectory: refused (before any device work) for the 200-equation reactor,
+    # as is LSODA for every model -- never a CPU fallback
+    for method in ("Radau", "BDF"):
+        with pytest.raises(NotImplementedError, match="dense Jacobian"):
+            p.sim(10, method=method)
+    with pytest.raises(NotImplementedError, match="no device implementation"):
+        p.sim(10, method="LSODA")
 
 
 def test_draw_collection_and_icf():
