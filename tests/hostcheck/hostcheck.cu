@@ -201,6 +201,16 @@ static void lu_host(const double* are, const double* aim, double* bre, double* b
         lu.solve(bre);
     }
 }
+// BdfStepper::change_D on a caller's difference array D[8][3] (rows above `order` must stay untouched)
+extern "C" void hc_bdf_change_D(int order, double factor, double* D) {
+    BdfStepper<ThreadSystem<SirOde>> R;
+    for (int k = 0; k < 8; ++k)
+        for (int e = 0; e < 3; ++e) R.D[k][e] = D[k * 3 + e];
+    R.change_D(order, factor);
+    for (int k = 0; k < 8; ++k)
+        for (int e = 0; e < 3; ++e) D[k * 3 + e] = R.D[k][e];
+}
+
 extern "C" int hc_lu_solve(int n, const double* are, const double* aim, double* bre, double* bim) {
     if (n == 3) lu_host<3>(are, aim, bre, bim);
     else if (n == 8) lu_host<8>(are, aim, bre, bim);

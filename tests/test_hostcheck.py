@@ -2,6 +2,7 @@
 __host__ __device__ sampler / stepper / integrator sources the GPU executes, compiled for the host.  These tests
 let the build container (no GPU) catch a wrong law before GPU time is spent; the `-m gpu` tests repeat the
 comparisons on the device."""
+import ctypes as C
 import numpy as np
 import pytest
 from scipy import stats
@@ -263,6 +264,27 @@ def test_radau_and_bdf_follow_scipy_step_for_step(golden, method):
     with pytest.raises(RuntimeError):                            # the reactor's node-per-lane layout has no dense Jacobian
         from pysodm_b200 import tutorial_data as td
         hc.ode_run("packed_pfr_ode", golden["ode"]["pfr25_y0"], td.pfr_flat_par(25), 1, 0, 11, model_arg=25, method=method)
+
+
+def test_bdf_difference_array_rescaling_matches_scipy():
+    """`change_D` of the BDF stepper (R(factor) U formed for the maximal order with U = the signed Pascal matrix, applied under
+    predicates on the order) against scipy's own `change_D` on random difference arrays, every order and a range of factors;
+    rows above the order stay untouched."""
+    from scipy.integrate._ivp.bdf import change_D, compute_R
+    assert np.array_equal(compute_R(5, 1), [[(-1) ** k * __import__("math").comb(j, k) for j in range(6)] for k in range(6)])
+    L = hc.lib()
+    L.hc_bdf_change_D.restype = None
+    L.hc_bdf_change_D.argtypes = [C.c_int, C.c_double, C.c_void_p]
+    rng = np.random.default_rng(5)
+    for order in range(1, 6):
+        for factor in (0.2, 0.5, 0.731, 1.0, 1.9, 10.0):
+            D = rng.normal(size=(8, 3)) * 10.0 ** rng.uniform(-6, 2, size=(8, 1))
+            want = D.copy()
+            change_D(want, order, factor)
+            got = np.ascontiguousarray(D.copy())
+            L.hc_bdf_change_D(order, factor, got.ctypes.data)
+            assert np.array_equal(got[order + 1:], D[order + 1:])
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12 * max(np.abs(D).max(), np.abs(want).max()))   # (sums cancel)
 
 
 @pytest.mark.parametrize("n", [3, 8, 12])
