@@ -235,6 +235,29 @@ struct ChainOde {
     }
 };
 
+// ImplicitBase::num_jac of a test functor at (t, y): `factor` (in/out; `have_factor` = 0 starts from scipy's default) and J (row-major)
+template <class M>
+static void num_jac_host(const double* par, double t, const double* y, double atol, int have_factor, double* factor, double* J) {
+    ThreadSystem<M> sys{par};
+    ImplicitBase<ThreadSystem<M>> B;
+    B.atol = atol;
+    B.have_factor = have_factor != 0;
+    for (int j = 0; j < M::N; ++j) B.jac_factor[j] = factor[j];
+    double f[M::N];
+    sys.rhs(t, y, f);
+    B.num_jac(sys, t, y, f);
+    for (int j = 0; j < M::N; ++j) factor[j] = B.jac_factor[j];
+    for (int i = 0; i < M::N * M::N; ++i) J[i] = B.J[i];
+}
+extern "C" int hc_num_jac(int model, const double* par, double t, const double* y, double atol, int have_factor, double* factor, double* J) {
+    if (model == 0) num_jac_host<RobertsonOde>(par, t, y, atol, have_factor, factor, J);
+    else if (model == 1) num_jac_host<VanDerPolOde>(par, t, y, atol, have_factor, factor, J);
+    else if (model == 2) num_jac_host<ChainOde<3>>(par, t, y, atol, have_factor, factor, J);
+    else if (model == 3) num_jac_host<ChainOde<12>>(par, t, y, atol, have_factor, factor, J);
+    else return SODM_EMODEL;
+    return SODM_OK;
+}
+
 extern "C" int hc_ode_test_model_run(const sodm_ode_args* a) {
     OdeLaunch L;
     sodm_model_info info = {};

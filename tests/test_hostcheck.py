@@ -266,6 +266,48 @@ def test_radau_and_bdf_follow_scipy_step_for_step(golden, method):
         hc.ode_run("packed_pfr_ode", golden["ode"]["pfr25_y0"], td.pfr_flat_par(25), 1, 0, 11, model_arg=25, method=method)
 
 
+def test_finite_difference_jacobian_matches_scipy_num_jac():
+    """`num_jac` of the implicit steppers against scipy's own on Robertson's kinetics (entries from 0.04 to 3e7, zero state
+    components: the increment search and the too-small-difference retry) and a random 12-equation chain, over three successive
+    calls so that the persisted, adapted increment factors are compared too: J and factors bit-identical."""
+    from scipy.integrate._ivp.common import num_jac
+    L = hc.lib()
+    L.hc_num_jac.restype = C.c_int
+    L.hc_num_jac.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+
+    def rob(t, y, par):
+        r1 = par[0] * y[0]
+        r2 = par[1] * y[1] * y[2]
+        r3 = par[2] * y[1] * y[1]
+        return np.array([-r1 + r2, r1 - r2 - r3, r3])
+
+    def chain(t, y, par, n=12):
+        dy = np.empty(n)
+        for i in range(n):
+            s = par[n + i] * y[i]
+            if i > 0:
+                s = par[i] * y[i - 1] + s
+            if i < n - 1:
+                s = s + par[2 * n + i] * y[i + 1]
+            dy[i] = s - par[3 * n] * y[i] * y[i]
+        return dy
+    rng = np.random.default_rng(9)
+    stiff = 10.0 ** rng.uniform(-1, 3, size=12)
+    chain_par = np.concatenate([rng.uniform(0, 0.5, 12) * stiff, -stiff, rng.uniform(0, 0.5, 12) * stiff, [0.05]])
+    for mid, fun, par, ys in ((0, rob, np.array([0.04, 1e4, 3e7]), [np.array([1.0, 0.0, 0.0]), np.array([0.98, 3.4e-5, 0.02]), np.array([0.5, 1e-6, 0.5])]),
+                              (3, chain, chain_par, [rng.uniform(0.5, 2.0, 12), rng.uniform(0, 1e-3, 12), rng.uniform(0.5, 2.0, 12)])):
+        n = ys[0].size
+        factor_ref, factor = None, np.zeros(n)
+        for call, y in enumerate(ys):
+            f = fun(0.0, y, par)
+            J_ref, factor_ref = num_jac(lambda t, Y: np.stack([fun(t, Y[:, k], par) for k in range(Y.shape[1])], axis=1), 0.0, y, f, 1e-6, factor_ref)
+            J = np.zeros((n, n))
+            y = np.ascontiguousarray(y)
+            assert L.hc_num_jac(mid, par.ctypes.data, 0.0, y.ctypes.data, 1e-6, int(call > 0), factor.ctypes.data, J.ctypes.data) == 0
+            assert np.array_equal(J, J_ref), (mid, call, np.abs(J - J_ref).max())
+            assert np.array_equal(factor, factor_ref), (mid, call)
+
+
 def test_bdf_difference_array_rescaling_matches_scipy():
     """`change_D` of the BDF stepper (R(factor) U formed for the maximal order with U = the signed Pascal matrix, applied under
     predicates on the order) against scipy's own `change_D` on random difference arrays, every order and a range of factors;
