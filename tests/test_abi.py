@@ -48,6 +48,28 @@ def test_struct_layout_matches_header():
                      C.sizeof(_ffi.LoglikArgs), C.sizeof(_ffi.NoiseArgs), C.sizeof(_ffi.SelectState)]
 
 
+def test_constants_match_header():
+    """Every SODM_* constant of include/sodm.h that the ctypes binding mirrors has the header's value (printed by a C program
+    compiled from the header): method ids (incl. the implicit ODE methods), status bits, dtypes, error codes, limits."""
+    import re
+    import subprocess
+    import tempfile
+    from pysodm_b200 import _ffi
+    header = open(os.path.join(ROOT, "include", "sodm.h")).read()
+    names = [n for n in re.findall(r"^#define (SODM_[A-Z0-9_]+)[ \t]+[-0-9(]", header, flags=re.M) if hasattr(_ffi, n[5:])]
+    assert {"SODM_ODE_RK45", "SODM_ODE_RADAU", "SODM_ODE_BDF", "SODM_ST_MAX_STEPS", "SODM_ABI_VERSION", "SODM_F64"} <= set(names)
+    src = '#include <stdio.h>\n#include "sodm.h"\nint main(void){' + "".join(f'printf("%ld\\n", (long)({n}));' for n in names) + "return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "k.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "k")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        values = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    assert len(values) == len(names)
+    for n, v in zip(names, values):
+        assert getattr(_ffi, n[5:]) == v, (n, v, getattr(_ffi, n[5:]))
+
+
 def test_model_registry(lib):
     from pysodm_b200 import _ffi
     want = {"sir_jump": (0, 3, 2), "sir_si_jump": (0, 14, 6), "influenza_1718_jump": (0, 28, 24),
